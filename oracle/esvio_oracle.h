@@ -1,0 +1,152 @@
+/*
+ * esvio_oracle.h -- CPU oracle for the ESVIO event front-end.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the shipped
+ * product path; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library, and only as the
+ * checker or the timed CPU baseline.
+ *
+ * It is a plain-C, single-thread restatement of the reference algorithm
+ * (paths relative to /root/reference):
+ *   feature_tracker/src/event_detector/event_detector.cc:149-166,212-228  SAE update
+ *   feature_tracker/src/event_detector/event_detector.cc:230-305          time surface
+ *   feature_tracker/src/event_detector/event_detector.cc:308-544          Arc* corner test
+ *   feature_tracker/src/feature_tracker.cpp:13-38                          corner selection
+ *   feature_tracker/src/feature_tracker.cpp:48-72                          border test / compaction
+ *   feature_tracker/src/feature_tracker.cpp:123-151                        min-distance mask
+ *   feature_tracker/src/feature_tracker.cpp:340-603                        per-window orchestration
+ *   feature_tracker/src/feature_tracker.cpp:910-947                        F-matrix rejection
+ *   feature_tracker/src/feature_tracker.cpp:991-1045                       undistort, velocity
+ *   camera_model/src/camera_models/PinholeCamera.cc:450-510,646-662        liftProjective
+ * and of the third-party arithmetic the path calls but the reference tree does
+ * not contain (OpenCV, version unpinned by feature_tracker/CMakeLists.txt:17;
+ * restated from the published algorithm of modules/video/src/lkpyramid.cpp,
+ * modules/imgproc/src/pyramids.cpp, modules/imgproc/src/drawing.cpp and
+ * modules/calib3d/src/{fundam,ptsetreg}.cpp and pinned against cv2 4.13.0 in
+ * the build container by tests/golden/make_golden.py).
+ *
+ * Parity status: the reference ships no tests, fixtures or golden vectors for
+ * this path, so parity of the reference-authored stages is
+ * UNPINNED by reference tests; the OpenCV-derived stages are pinned against
+ * real OpenCV (cv2) outputs committed under tests/golden/.
+ */
+#ifndef ESVIO_ORACLE_H
+#define ESVIO_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------- Surface of Active Events (one camera) ---------------- */
+typedef struct ora_sae {
+  int W, H;
+  double *sae[2];    /* last ACCEPTED event time per polarity, index x + y*W */
+  double *latest[2]; /* last event time per polarity */
+} ora_sae;
+
+ora_sae *ora_sae_create(int W, int H);
+void ora_sae_destroy(ora_sae *s);
+void ora_sae_reset(ora_sae *s);
+/* event_detector.cc:149-166 / 212-228 */
+void ora_sae_update(ora_sae *s, const uint16_t *x, const uint16_t *y, const double *t,
+                    const uint8_t *p, size_t n, double filter_threshold);
+/* event_detector.cc:230-305 (convertTo(CV_8U) rounding = round-half-even) */
+void ora_time_surface(const ora_sae *s, double t_ref, double decay_ms, int ignore_polarity,
+                      uint8_t *out);
+/* event_detector.cc:308-544 */
+int ora_is_corner(const ora_sae *s, double t, int x, int y, int p, double filter_threshold,
+                  int min_dist);
+void ora_corner_flags(const ora_sae *s, const uint16_t *x, const uint16_t *y, const double *t,
+                      const uint8_t *p, size_t n, double filter_threshold, int min_dist,
+                      uint8_t *flags);
+
+/* ---------------- raster helpers (OpenCV drawing.cpp Circle, filled) ---------------- */
+/* half_width[k] for k=0..r : row offset k from the centre is filled on [cx-hw, cx+hw]. */
+void ora_disc_half_widths(int r, int *half_width);
+void ora_fill_disc_u8(uint8_t *mask, int W, int H, int cx, int cy, int r, uint8_t value);
+
+/* feature_tracker.cpp:123-151 ; ties in track_cnt keep their current order (stable) */
+int ora_set_mask(int W, int H, int min_dist, int n, float *pts /*2n*/, int *ids, int *track_cnt,
+                 uint8_t *mask /*W*H out: 0 / 255*/);
+/* feature_tracker.cpp:13-38 */
+int ora_features_to_track(const ora_sae *left, const uint16_t *x, const uint16_t *y,
+                          const double *t, const uint8_t *p, size_t n, int max_corners,
+                          int min_dist, const uint8_t *mask, const uint8_t *ts,
+                          double ts_lk_threshold, double filter_threshold,
+                          float *out_pts /*2*max_corners*/, uint8_t *mask_out /*nullable*/);
+
+/* ---------------- OpenCV pyramid + pyramidal LK ---------------- */
+/* sizes of level l ; returns the number of levels actually built (<= max_level+1) */
+int ora_pyramid_sizes(int W, int H, int max_level, int win, int *w_out, int *h_out);
+void ora_pyr_down(const uint8_t *src, int sw, int sh, uint8_t *dst, int dw, int dh);
+void ora_scharr_deriv(const uint8_t *src, int w, int h, int16_t *dst /* 2ch */);
+void ora_calc_optical_flow_pyr_lk(const uint8_t *prev, const uint8_t *next, int W, int H,
+                                  const float *prev_pts, float *next_pts, int n, uint8_t *status,
+                                  int win, int max_level, int max_count, double epsilon,
+                                  int use_initial_flow, double min_eig_threshold);
+
+/* ---------------- camodocal pinhole ---------------- */
+typedef struct ora_pinhole {
+  double fx, fy, cx, cy, k1, k2, p1, p2;
+} ora_pinhole;
+void ora_lift_projective(const ora_pinhole *cam, double u, double v, double *x, double *y);
+
+/* ---------------- OpenCV findFundamentalMat(FM_RANSAC) mask ---------------- */
+int ora_solve_cubic(const double *c /*4*/, double *roots /*3*/);
+int ora_run_7point(const float *m1 /*14*/, const float *m2 /*14*/, double *F /*27*/);
+/* returns 1 if a model was found; mask gets 0/1 per point */
+int ora_find_fundamental_mask(const float *pts1, const float *pts2, int n, double thresh,
+                              double confidence, int max_iters, uint8_t *mask);
+
+/* ---------------- whole-window tracker (FeatureTracker::trackEvent) ---------------- */
+typedef void (*ora_lk_fn)(const uint8_t *prev, const uint8_t *next, int W, int H,
+                          const float *prev_pts, float *next_pts, int n, uint8_t *status,
+                          int max_level, int use_initial_flow);
+typedef int (*ora_fmat_fn)(const float *pts1, const float *pts2, int n, double thresh,
+                           uint8_t *mask);
+typedef void (*ora_equalize_fn)(const uint8_t *src, int W, int H, uint8_t *dst);
+
+typedef struct ora_config {
+  int width, height, max_cnt, min_dist, flow_back, equalize;
+  double f_threshold, ts_lk_threshold, decay_ms;
+  int ignore_polarity, median_blur_kernel_size;
+  double feature_filter_threshold;
+  double focal_length;
+  ora_pinhole cam[2];
+} ora_config;
+
+typedef struct ora_tracks {
+  int n_left;
+  int *id;
+  int *track_cnt;
+  float *u, *v, *un_x, *un_y, *vx, *vy;
+  int n_right;
+  int *id_right;
+  float *ru, *rv, *run_x, *run_y, *rvx, *rvy;
+  /* stage counters */
+  int n_prev, n_after_temporal, n_after_ransac, n_after_mask, n_new;
+} ora_tracks;
+
+typedef struct ora_tracker ora_tracker;
+ora_tracker *ora_tracker_create(const ora_config *cfg);
+void ora_tracker_destroy(ora_tracker *t);
+void ora_tracker_set_hooks(ora_tracker *t, ora_lk_fn lk, ora_fmat_fn fm, ora_equalize_fn eq);
+void ora_tracker_disable_ransac(ora_tracker *t, int disable);
+/* out arrays must have capacity >= cfg.max_cnt */
+int ora_tracker_track(ora_tracker *t, double cur_time, const uint16_t *lx, const uint16_t *ly,
+                      const double *lt, const uint8_t *lp, size_t nl, const uint16_t *rx,
+                      const uint16_t *ry, const double *rt, const uint8_t *rp, size_t nr,
+                      int pub_this_frame, ora_tracks *out);
+/* views of internal state, for stage-level parity checks */
+const ora_sae *ora_tracker_sae(const ora_tracker *t, int cam);
+const uint8_t *ora_tracker_time_surface(const ora_tracker *t, int cam);
+/* stage timers (seconds, accumulated): 0 sae,1 ts,2 temporal lk,3 ransac+mask+select,4 stereo lk,5 other */
+void ora_tracker_timers(const ora_tracker *t, double *out6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
