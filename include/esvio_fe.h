@@ -1,0 +1,215 @@
+/*
+ * esvio_fe.h -- C ABI of the B200-native ESVIO event front-end (libesvio_fe.so).
+ *
+ * Drop-in boundary for the hot path of arclab-hku/ESVIO's stereo_event_tracker
+ * node.  One `esvio_fe` handle replaces the reference's global
+ * `FeatureTracker trackerData` + `esvio::EventDetector detector`
+ * (feature_tracker/src/stereo_event_tracker_node.cpp:45,
+ *  feature_tracker/src/feature_tracker.cpp:7) for ONE stereo event stream.
+ *
+ * Plain pointers and sizes only; no C++/torch types.  Every entry point
+ * returns an esvio_status (0 = ok) and never throws.  A handle is not
+ * thread-safe (the reference has exactly one caller thread, sync_process,
+ * stereo_event_tracker_node.cpp:366); many handles may live in one process.
+ * All device work of a handle runs on its own CUDA stream on `device_id`.
+ *
+ * There is no CPU fallback: esvio_fe_create fails with ESVIO_FE_ENODEV when no
+ * CUDA device is usable.
+ */
+#ifndef ESVIO_FE_H
+#define ESVIO_FE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESVIO_FE_ABI_VERSION 1
+
+typedef enum esvio_status {
+  ESVIO_FE_OK = 0,
+  ESVIO_FE_EINVAL = 1,    /* bad argument / config */
+  ESVIO_FE_ENODEV = 2,    /* no usable CUDA device */
+  ESVIO_FE_ECUDA = 3,     /* CUDA runtime error (see esvio_fe_last_error) */
+  ESVIO_FE_ECAPACITY = 4, /* more events than max_events_per_window / tracks capacity too small */
+  ESVIO_FE_ESTATE = 5     /* call sequence error (e.g. wait without submit) */
+} esvio_status;
+
+/* camodocal PINHOLE calibration (config/<set>/event{0,1}_esvio.yaml;
+ * camera_model/src/camera_models/PinholeCamera.cc:292-295) */
+typedef struct esvio_pinhole {
+  double fx, fy, cx, cy, k1, k2, p1, p2;
+} esvio_pinhole;
+
+/* Mirrors the globals filled by readParameters_event
+ * (feature_tracker/src/parameters.cpp:201-229,273-275). */
+typedef struct esvio_fe_config {
+  int32_t width;                   /* COL_event */
+  int32_t height;                  /* ROW_event */
+  int32_t max_cnt;                 /* MAX_CNT */
+  int32_t min_dist;                /* MIN_DIST */
+  int32_t flow_back;               /* FLOW_BACK */
+  int32_t equalize;                /* EQUALIZE (CLAHE + normalize; not in round 1 -> EINVAL if 1) */
+  double f_threshold;              /* F_THRESHOLD */
+  double ts_lk_threshold;          /* TS_LK_THRESHOLD */
+  double decay_ms;                 /* para_decay_ms */
+  int32_t ignore_polarity;         /* para_ignore_polarity */
+  int32_t median_blur_kernel_size; /* para_median_blur_kernel_size (must be 0 in round 1) */
+  double feature_filter_threshold; /* para_feature_filter_threshold */
+  int32_t do_motion_correction;    /* Do_motion_correction (must be 0 in round 1) */
+  double focal_length;             /* FOCAL_LENGTH = 460 (parameters.cpp:274) */
+  esvio_pinhole cam[2];            /* left, right */
+  int32_t device_id;
+  int32_t max_events_per_window;   /* per camera; staging capacity */
+  int32_t use_ransac;              /* 1 = rejectWithF_event enabled (reference behaviour) */
+  int32_t reserved[7];
+} esvio_fe_config;
+
+/* One camera's events for one window (dvs_msgs/EventArray.events).
+ * Either SoA (x,y,t,p all non-NULL) or AoS (`aos` non-NULL): an array of
+ * 16-byte dvs_msgs::Event records {u16 x; u16 y; u32 sec; u32 nsec; u8 polarity; pad[3]}
+ * (feature_tracker/src/dvs_msgs/Event.h:42-52), converted on the GPU with
+ * ros::Time::toSec() arithmetic.  Caller-owned, read-only, valid for the call.
+ * Events with x >= width or y >= height are dropped and counted. */
+typedef struct esvio_events {
+  const uint16_t *x;
+  const uint16_t *y;
+  const double *t;  /* seconds, e.ts.toSec() */
+  const uint8_t *p; /* polarity 0/1 */
+  const void *aos;
+  size_t n;
+  int32_t on_device; /* 1: pointers are device pointers on the handle's device */
+  int32_t reserved;
+} esvio_events;
+
+typedef struct esvio_stats {
+  int32_t n_events[2];
+  int32_t n_dropped[2];       /* out-of-range events */
+  int32_t n_prev;             /* tracks entering the window */
+  int32_t n_after_temporal;   /* after LK + backward check + border test */
+  int32_t n_after_ransac;
+  int32_t n_after_mask;
+  int32_t n_new;              /* new Arc* corners appended */
+  int32_t n_corner_flags;     /* left events flagged corner && TS != threshold */
+  int32_t ransac_iters;
+  int32_t reserved[5];
+} esvio_stats;
+
+/* Caller-allocated outputs; replaces the public std::vectors the node reads
+ * after trackEvent (feature_tracker/src/feature_tracker.h:126-135;
+ * stereo_event_tracker_node.cpp:289-323).  Every array holds >= capacity
+ * entries, capacity >= config.max_cnt. */
+typedef struct esvio_tracks {
+  int32_t capacity;
+  int32_t n_left;
+  int32_t *id;        /* ids */
+  int32_t *track_cnt; /* track_cnt */
+  float *u, *v;       /* cur_pts */
+  float *un_x, *un_y; /* cur_un_pts */
+  float *vx, *vy;     /* pts_velocity */
+  int32_t n_right;
+  int32_t *id_right;    /* ids_right */
+  float *ru, *rv;       /* cur_right_pts */
+  float *run_x, *run_y; /* cur_un_right_pts */
+  float *rvx, *rvy;     /* right_pts_velocity */
+  esvio_stats stats;
+} esvio_tracks;
+
+/* ---- lifecycle ---- */
+typedef struct esvio_fe esvio_fe;
+
+int esvio_fe_abi_version(void);
+/* Values common to every shipped config (config/<set>/es*io.yaml front-end block):
+ * max_cnt 150, min_dist 10, flow_back 1, F_threshold 1, TS_LK_threshold 128,
+ * decay_ms 20, feature_filter_threshold 0.01, focal_length 460, use_ransac 1. */
+void esvio_fe_default_config(esvio_fe_config *cfg, int32_t width, int32_t height);
+/* replaces detector.init(COL_event, ROW_event) (feature_tracker.cpp:347-350) and
+ * stereo_readIntrinsicParameter (feature_tracker.cpp:963-976) */
+int esvio_fe_create(const esvio_fe_config *cfg, esvio_fe **out);
+void esvio_fe_destroy(esvio_fe *fe);
+/* clears SAE, previous image, tracks and the id counter */
+int esvio_fe_reset(esvio_fe *fe);
+const char *esvio_fe_strerror(int status);
+const char *esvio_fe_last_error(const esvio_fe *fe);
+
+/* ---- the hot path ---- */
+/* replaces FeatureTracker::trackEvent(cur_time, event_left, event_right)
+ * (feature_tracker.h:51; feature_tracker.cpp:340-603; call site
+ * stereo_event_tracker_node.cpp:193).  `pub_this_frame` is the reference's
+ * global PUB_THIS_FRAME (stereo_event_tracker_node.cpp:179,188).
+ * Synchronous: returns after the <= 2*max_cnt track records are on the host. */
+int esvio_fe_track(esvio_fe *fe, double cur_time, const esvio_events *left,
+                   const esvio_events *right, int32_t pub_this_frame, esvio_tracks *out);
+/* The same call split in two so the host can stage window k+1 while window k
+ * runs: at most 2 windows may be in flight; waits return results in order. */
+int esvio_fe_track_submit(esvio_fe *fe, double cur_time, const esvio_events *left,
+                          const esvio_events *right, int32_t pub_this_frame);
+int esvio_fe_track_wait(esvio_fe *fe, esvio_tracks *out);
+
+/* replaces FeatureTracker::gettimesurface() (feature_tracker.cpp:894-897): the
+ * CV_8U time surface of the last window; dst has `stride` bytes per row. */
+int esvio_fe_time_surface(esvio_fe *fe, int32_t cam, uint8_t *dst, size_t stride);
+
+/* ---- memory helpers ---- */
+void *esvio_fe_host_alloc(size_t bytes); /* pinned host memory for event staging */
+void esvio_fe_host_free(void *p);
+int esvio_fe_device_alloc(esvio_fe *fe, size_t bytes, void **out);
+int esvio_fe_device_free(esvio_fe *fe, void *p);
+int esvio_fe_copy_to_device(esvio_fe *fe, void *dst, const void *src, size_t bytes);
+
+/* ---- multi-GPU plumbing ---- */
+/* Device-resident packed track records of the last completed window
+ * (header + 15 arrays of max_cnt int32/float), for one collective
+ * (all-gather) per window; and the handle's cudaStream_t. */
+int esvio_fe_result_device_ptr(esvio_fe *fe, void **ptr, size_t *bytes);
+int esvio_fe_stream(esvio_fe *fe, void **cuda_stream);
+
+/* ---- profiling ---- */
+#define ESVIO_FE_NUM_STAGES 8
+/* CUDA-event milliseconds of the last completed window when profiling is on:
+ * 0 h2d+convert, 1 sae+ts, 2 pyramid, 3 corner flags, 4 temporal LK,
+ * 5 select (ransac+mask+corners), 6 stereo LK + pack, 7 d2h */
+int esvio_fe_set_profiling(esvio_fe *fe, int32_t on);
+int esvio_fe_get_stage_ms(esvio_fe *fe, float *ms /* ESVIO_FE_NUM_STAGES */);
+int esvio_fe_kernel_launches(esvio_fe *fe, int64_t *count); /* kernels launched so far */
+
+/* ---- stage-level entry points (used by the parity tests) ---- */
+/* plane: 0 sae[0], 1 sae[1], 2 sae_latest[0], 3 sae_latest[1]; dst = H*W doubles,
+ * index x + y*W (event_detector.h:74-79) */
+int esvio_fe_get_sae(esvio_fe *fe, int32_t cam, int32_t plane, double *dst);
+/* createSAE_* + SAEtoTimeSurface_* + pyramids only (feature_tracker.cpp:356-368) */
+int esvio_fe_stage_update(esvio_fe *fe, double t_ref, const esvio_events *left,
+                          const esvio_events *right);
+/* EventDetector::isCorner for every left event against the current SAE
+ * (event_detector.cc:308-544); flags[i] in {0,1}.  If and_ts_test != 0 the
+ * TS != TS_LK_threshold test of feature_tracker.cpp:26 is ANDed in. */
+int esvio_fe_stage_corner_flags(esvio_fe *fe, const esvio_events *left, int32_t and_ts_test,
+                                uint8_t *flags);
+/* which: 0 = current left, 1 = current right, 2 = previous left */
+int esvio_fe_get_pyramid_level(esvio_fe *fe, int32_t which, int32_t level, uint8_t *dst,
+                               int32_t *w, int32_t *h);
+/* cv::calcOpticalFlowPyrLK(prev, next, winSize 21x21, maxLevel) as the reference
+ * calls it (feature_tracker.cpp:410,417-418,490,495) on caller images (W*H u8). */
+int esvio_fe_stage_lk(esvio_fe *fe, const uint8_t *prev_img, const uint8_t *next_img,
+                      const float *prev_pts, float *next_pts, int32_t n, uint8_t *status,
+                      int32_t max_level, int32_t use_initial_flow);
+/* cv::findFundamentalMat(p1, p2, FM_RANSAC, thresh, 0.99, status)
+ * (feature_tracker.cpp:935) */
+int esvio_fe_stage_fmat_mask(esvio_fe *fe, const float *p1, const float *p2, int32_t n,
+                             double thresh, uint8_t *mask, int32_t *iters);
+/* Event_setMask + Event_FeaturesToTrack + id assignment
+ * (feature_tracker.cpp:446-468) against the current SAE / time surface. In:
+ * n tracked points; out: kept + new points (capacity max_cnt). */
+int esvio_fe_stage_select(esvio_fe *fe, const esvio_events *left, int32_t n, const float *pts,
+                          const int32_t *ids, const int32_t *track_cnt, int32_t *n_out,
+                          float *pts_out, int32_t *ids_out, int32_t *track_cnt_out,
+                          int32_t *n_kept);
+/* PinholeCamera::liftProjective (PinholeCamera.cc:450-510) -> (x/z, y/z) as f32 */
+int esvio_fe_stage_undistort(esvio_fe *fe, int32_t cam, const float *uv, int32_t n, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
