@@ -1,0 +1,247 @@
+// common.cuh -- shared types and device helpers of libesvio_fe (sm_100a only).
+//
+// HBM layout of one stereo stream (all row-major, index x + y*W as the reference's
+// Eigen::MatrixXd(W,H) planes, feature_tracker/src/event_detector/event_detector.h:74-79):
+//   sae  : double2[2 cams][H][W]   .x = sae[0] (last ACCEPTED negative), .y = sae[1]
+//   lat  : double2[2 cams][H][W]   .x = sae_latest[0],                  .y = sae_latest[1]
+//   pyr  : u8 image pyramids (level 0 = the CV_8U time surface) of cur-left (ping-pong
+//          with prev-left) and cur-right
+// Events of a window sit in HBM either as SoA (x u16, y u16, t f64, p u8) or as the raw
+// 16-byte dvs_msgs::Event records, and are re-ordered once per window into per-tile
+// runs (stable counting sort) so that one warp owns one 32x8 pixel tile in shared memory.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace esvio {
+
+constexpr int kTileW = 32;                    // pixels per tile row == one warp
+constexpr int kTileH = 8;
+constexpr int kTilePx = kTileW * kTileH;      // 256 pixels, key fits 8 bits
+constexpr int kChunkThreads = 256;
+constexpr int kChunkSteps = 8;                // events per thread in the binning kernels
+constexpr int kChunk = kChunkThreads * kChunkSteps;  // 2048 events per CTA
+constexpr int kMaxLevels = 4;                 // maxLevel = 3 (feature_tracker.cpp:410)
+constexpr int kWin = 21;                      // cv::Size(21, 21)
+constexpr int kHalfWin = 10;
+constexpr int kMaxCnt = 1024;                 // hard cap on MAX_CNT
+constexpr int kResultHdr = 32;                // int32 words in front of the result arrays
+constexpr int kResultArrays = 15;
+
+struct DevEvents {
+  const uint16_t* x;
+  const uint16_t* y;
+  const double* t;
+  const uint8_t* p;
+  const uint4* aos;  // dvs_msgs::Event records (feature_tracker/src/dvs_msgs/Event.h:42-52)
+  int n;
+};
+
+struct Ev {
+  int x, y, p;
+  double t;
+};
+
+// e.ts.toSec() == (double)sec + 1e-9 * (double)nsec (ros::Time); compiled with -fmad=false
+// so the multiply and the add round separately like the reference's x86 build.
+__device__ __forceinline__ Ev load_event(const DevEvents& e, int i) {
+  Ev r;
+  if (e.aos) {
+    const uint4 v = __ldg(e.aos + i);
+    r.x = (int)(v.x & 0xffffu);
+    r.y = (int)(v.x >> 16);
+    r.t = (double)v.y + 1e-9 * (double)v.z;
+    r.p = (v.w & 0xffu) ? 1 : 0;
+  } else {
+    r.x = __ldg(e.x + i);
+    r.y = __ldg(e.y + i);
+    r.t = __ldg(e.t + i);
+    r.p = __ldg(e.p + i) ? 1 : 0;
+  }
+  return r;
+}
+
+struct PyrDesc {
+  int levels;
+  int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+  uint32_t off[kMaxLevels];  // byte offset of the level inside one pyramid buffer
+  uint32_t bytes;            // size of one pyramid buffer
+};
+
+struct Pinhole {
+  double fx, fy, cx, cy, k1, k2, p1, p2;
+};
+
+// Per-stream tracker bookkeeping that lives on the device between windows.
+struct TrackState {
+  int n_prev;   // tracks carried in from the previous window (prev_pts.size())
+  int n_cur;    // cur_pts.size() as the window progresses
+  int n_right;  // matched right points of this window
+  int next_id;  // FeatureTracker::n_id (feature_tracker.cpp:9)
+  int n_prev_un;    // entries of prev_un_pts_map
+  int n_prev_un_r;  // entries of prev_un_right_pts_map
+  int stat_after_temporal, stat_after_ransac, stat_after_mask, stat_new;
+  int stat_corner_flags, stat_ransac_iters, stat_n_prev;
+  int pad[3];
+};
+
+// ---------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
+  return i;
+}
+
+// cvRound(float): round half to even
+__device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
+
+// ---------------------------------------------------------------------------------
+// TMA / mbarrier wrappers (PTX; SASS shows UTMALDG / UTMASTG)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0,
+                                             int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(map)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// launch wrappers implemented in the .cu files
+// ---------------------------------------------------------------------------------
+struct BinLayout {
+  int W, H, tiles_x, tiles_y, n_tiles;  // bin n_tiles collects out-of-range events
+  int max_chunks;                       // row stride of `counts`
+};
+
+struct EventStageBuffers {
+  uint32_t* counts;     // [2][n_tiles+1][max_chunks]
+  uint32_t* bin_total;  // [2][n_tiles+1]
+  uint32_t* bin_start;  // [2][n_tiles+2]
+  double* bt[2];        // binned event times
+  uint16_t* bk[2];      // binned keys: local pixel (8 bits) | polarity << 8
+};
+
+void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents ev[2],
+                       cudaStream_t s, int64_t* launches);
+
+struct SaeTsParams {
+  int W, H, tiles_x, n_tiles;
+  double t_ref, decay_sec, filter_threshold;
+  int ignore_polarity;
+  const uint32_t* bin_start;  // [2][n_tiles+2]
+  const double* bt[2];
+  const uint16_t* bk[2];
+  uint8_t* ts[2];  // level-0 images
+  int ts_pitch;
+};
+void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
+                          const CUtensorMap& map_lat, cudaStream_t s, int64_t* launches);
+
+struct CornerParams {
+  int W, H, min_dist;
+  double filter_threshold, ts_lk_threshold;
+  const double2* sae;  // left camera planes
+  const double2* lat;
+  const uint8_t* ts;   // left level-0 image (may be null when and_ts_test == 0)
+  int ts_pitch;
+  int and_ts_test;
+};
+void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* flags,
+                         cudaStream_t s, int64_t* launches);
+
+void launch_pyramids(const PyrDesc& pd, uint8_t* const pyr[2], int n_img, cudaStream_t s,
+                     int64_t* launches);
+
+// cv::calcOpticalFlowPyrLK(I, J, prev, next, status, err, Size(21,21), max_level[, 30/0.01,
+// USE_INITIAL_FLOW]); n is read on the device.
+void launch_lk(const PyrDesc& pd, const uint8_t* I, const uint8_t* J, const float2* prev_pts,
+               float2* next_pts, uint8_t* status, const int* n_ptr, int n_max, int max_level,
+               int use_initial_flow, cudaStream_t s, int64_t* launches);
+
+struct TrackBuffers {
+  TrackState* st;
+  float2 *prev_pts, *cur_pts, *rev_pts, *right_pts, *rev_left_pts;
+  int *ids, *cnt;
+  uint8_t *st_fwd, *st_bwd, *st_sf, *st_sb;
+  int* prev_un_ids;
+  float2* prev_un;
+  int* prev_un_r_ids;
+  float2* prev_un_r;
+  int32_t* result;  // kResultHdr ints + kResultArrays * max_cnt words
+};
+
+struct TrackParams {
+  int W, H, max_cnt, min_dist, flow_back;
+  double focal_length, f_threshold;
+  Pinhole cam[2];
+};
+
+void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
+                          int64_t* launches);
+void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents& left,
+                   const uint8_t* flags, cudaStream_t s, int64_t* launches);
+void launch_finalize(const TrackParams& P, const TrackBuffers& B, double cur_time,
+                     double prev_time, cudaStream_t s, int64_t* launches);
+void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
+                   int64_t* launches);
+// stage entry: F-RANSAC mask on caller points (device pointers)
+void launch_ransac_stage(const float2* p1, const float2* p2, int n, double thresh, uint8_t* mask,
+                         int* iters, cudaStream_t s, int64_t* launches);
+void launch_undistort(const Pinhole& cam, const float2* uv, int n, float2* out, cudaStream_t s,
+                      int64_t* launches);
+
+size_t select_smem_bytes(int W, int H);
+
+}  // namespace esvio

@@ -1,0 +1,779 @@
+// esvio_fe.cu -- the C ABI of libesvio_fe.so (include/esvio_fe.h): handle lifecycle, HBM
+// layout, host<->device staging and the per-window launch sequence that replaces
+// FeatureTracker::trackEvent (feature_tracker/src/feature_tracker.cpp:340-603).
+// There is no CPU path in this library: every stage is a kernel from events.cu,
+// pyramid.cu, lk.cu, select.cu, ransac.cu.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/esvio_fe.h"
+#include "common.cuh"
+
+using namespace esvio;
+
+namespace esvio {
+int select_configure(int W, int H);
+int bin_configure(int n_tiles);
+}
+
+#define FE_API extern "C" __attribute__((visibility("default")))
+
+struct esvio_fe {
+  esvio_fe_config cfg;
+  int dev;
+  cudaStream_t stream;
+  char err[256];
+  int W, H;
+  size_t npx;
+  BinLayout bl;
+  double2 *sae, *lat;  // [2][H][W]
+  CUtensorMap map_sae, map_lat;
+  PyrDesc pd;
+  uint8_t* pyr[5];  // 0/1 left ping-pong, 2 right, 3/4 scratch for esvio_fe_stage_lk
+  int cur_left;     // index of the current left pyramid (0/1); prev = 1 - cur_left
+  int windows;      // windows processed since create/reset
+  int cap;          // events per camera per window
+  uint8_t* raw[2];  // 16 B * cap per camera: SoA carve-out or dvs_msgs::Event records
+  EventStageBuffers esb;
+  uint8_t* flags;
+  TrackBuffers tb;
+  TrackParams tp;
+  int32_t* h_result[2];
+  size_t result_words;
+  int* d_scratch_n;
+  float2 *d_scratch_p0, *d_scratch_p1;
+  uint8_t* d_scratch_st;
+  double prev_time;
+  int64_t launches;
+  int q_head, q_count;  // in-flight windows (results land in h_result[(q_head + k) & 1])
+  cudaEvent_t q_done[2];
+  int profiling;
+  cudaEvent_t pev[ESVIO_FE_NUM_STAGES + 1];
+  int pev_valid;
+  float stage_ms[ESVIO_FE_NUM_STAGES];
+};
+
+static int fail(esvio_fe* fe, int code, const char* what, cudaError_t ce) {
+  if (fe) snprintf(fe->err, sizeof(fe->err), "%s: %s", what, ce == cudaSuccess ? "-" : cudaGetErrorString(ce));
+  return code;
+}
+#define CU(call)                                                   \
+  do {                                                             \
+    cudaError_t ce_ = (call);                                      \
+    if (ce_ != cudaSuccess) return fail(fe, ESVIO_FE_ECUDA, #call, ce_); \
+  } while (0)
+
+FE_API int esvio_fe_abi_version(void) { return ESVIO_FE_ABI_VERSION; }
+
+FE_API const char* esvio_fe_strerror(int s) {
+  switch (s) {
+    case ESVIO_FE_OK: return "ok";
+    case ESVIO_FE_EINVAL: return "invalid argument or configuration";
+    case ESVIO_FE_ENODEV: return "no usable CUDA device";
+    case ESVIO_FE_ECUDA: return "CUDA runtime error";
+    case ESVIO_FE_ECAPACITY: return "capacity exceeded";
+    case ESVIO_FE_ESTATE: return "call sequence error";
+    default: return "unknown status";
+  }
+}
+
+FE_API const char* esvio_fe_last_error(const esvio_fe* fe) { return fe ? fe->err : ""; }
+
+FE_API void esvio_fe_default_config(esvio_fe_config* c, int32_t width, int32_t height) {
+  memset(c, 0, sizeof(*c));
+  c->width = width;
+  c->height = height;
+  c->max_cnt = 150;
+  c->min_dist = 10;
+  c->flow_back = 1;
+  c->equalize = 0;
+  c->f_threshold = 1.0;
+  c->ts_lk_threshold = 128.0;
+  c->decay_ms = 20.0;
+  c->ignore_polarity = 0;
+  c->median_blur_kernel_size = 0;
+  c->feature_filter_threshold = 0.01;
+  c->do_motion_correction = 0;
+  c->focal_length = 460.0;
+  for (int i = 0; i < 2; ++i) {
+    c->cam[i].fx = c->cam[i].fy = 460.0;
+    c->cam[i].cx = width / 2.0;
+    c->cam[i].cy = height / 2.0;
+  }
+  c->device_id = 0;
+  c->max_events_per_window = 1 << 20;
+  c->use_ransac = 1;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void build_pyr_desc(int W, int H, PyrDesc* pd) {
+  int w = W, h = H;
+  size_t off = 0;
+  pd->levels = 0;
+  for (int l = 0; l < kMaxLevels; ++l) {
+    pd->w[l] = w;
+    pd->h[l] = h;
+    pd->pitch[l] = (int)align_up(w, 32);
+    pd->off[l] = (uint32_t)off;
+    off = align_up(off + (size_t)pd->pitch[l] * h, 256);
+    pd->levels = l + 1;
+    w = (w + 1) / 2;
+    h = (h + 1) / 2;
+    if (w <= kWin || h <= kWin) break;  // buildOpticalFlowPyramid stops here
+  }
+  for (int l = pd->levels; l < kMaxLevels; ++l) pd->w[l] = pd->h[l] = pd->pitch[l] = 0, pd->off[l] = 0;
+  pd->bytes = (uint32_t)off;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_state_map(esvio_fe* fe, double2* base, CUtensorMap* map) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess)
+    return fail(fe, ESVIO_FE_ECUDA, "cuTensorMapEncodeTiled unavailable", cudaSuccess);
+  const cuuint64_t dims[3] = {(cuuint64_t)fe->W * 2, (cuuint64_t)fe->H, 2};
+  const cuuint64_t strides[2] = {(cuuint64_t)fe->W * 16, (cuuint64_t)fe->W * fe->H * 16};
+  const cuuint32_t box[3] = {2 * kTileW, kTileH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = ((encode_tiled_fn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims,
+                                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_NONE,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(fe->err, sizeof(fe->err), "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return ESVIO_FE_ECUDA;
+  }
+  return ESVIO_FE_OK;
+}
+
+static void free_all(esvio_fe* fe) {
+  if (!fe) return;
+  cudaSetDevice(fe->dev);
+  if (fe->stream) cudaStreamSynchronize(fe->stream);
+  cudaFree(fe->sae);
+  cudaFree(fe->lat);
+  for (int i = 0; i < 5; ++i) cudaFree(fe->pyr[i]);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(fe->raw[i]);
+    cudaFree(fe->esb.bt[i]);
+    cudaFree(fe->esb.bk[i]);
+    if (fe->h_result[i]) cudaFreeHost(fe->h_result[i]);
+    if (fe->q_done[i]) cudaEventDestroy(fe->q_done[i]);
+  }
+  cudaFree(fe->esb.counts);
+  cudaFree(fe->esb.bin_total);
+  cudaFree(fe->esb.bin_start);
+  cudaFree(fe->flags);
+  cudaFree(fe->tb.st);
+  cudaFree(fe->tb.prev_pts);
+  cudaFree(fe->tb.ids);
+  cudaFree(fe->tb.st_fwd);
+  cudaFree(fe->tb.result);
+  cudaFree(fe->d_scratch_n);
+  cudaFree(fe->d_scratch_p0);
+  cudaFree(fe->d_scratch_st);
+  for (int i = 0; i <= ESVIO_FE_NUM_STAGES; ++i)
+    if (fe->pev[i]) cudaEventDestroy(fe->pev[i]);
+  if (fe->stream) cudaStreamDestroy(fe->stream);
+  free(fe);
+}
+
+static int reset_state(esvio_fe* fe) {
+  const size_t plane = fe->npx * 2 * sizeof(double2);
+  CU(cudaMemsetAsync(fe->sae, 0, plane, fe->stream));
+  CU(cudaMemsetAsync(fe->lat, 0, plane, fe->stream));
+  for (int i = 0; i < 5; ++i) CU(cudaMemsetAsync(fe->pyr[i], 0, fe->pd.bytes, fe->stream));
+  CU(cudaMemsetAsync(fe->tb.st, 0, sizeof(TrackState), fe->stream));
+  CU(cudaMemsetAsync(fe->tb.result, 0, fe->result_words * 4, fe->stream));
+  CU(cudaStreamSynchronize(fe->stream));
+  fe->cur_left = 0;
+  fe->windows = 0;
+  fe->prev_time = 0.0;
+  fe->q_head = fe->q_count = 0;
+  fe->pev_valid = 0;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
+  if (!cfg || !out) return ESVIO_FE_EINVAL;
+  *out = nullptr;
+  if (cfg->width < 64 || cfg->height < 64 || cfg->width > 8192 || cfg->height > 8192)
+    return ESVIO_FE_EINVAL;
+  if (cfg->max_cnt < 1 || cfg->max_cnt > kMaxCnt) return ESVIO_FE_EINVAL;
+  if (cfg->min_dist < 1 || cfg->min_dist > 64) return ESVIO_FE_EINVAL;
+  if (cfg->equalize || cfg->median_blur_kernel_size || cfg->do_motion_correction)
+    return ESVIO_FE_EINVAL;  // SURVEY.md section 8f "next" rows, not built yet
+  if (cfg->max_events_per_window < 1) return ESVIO_FE_EINVAL;
+  if (!(cfg->decay_ms > 0.0)) return ESVIO_FE_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device_id < 0 ||
+      cfg->device_id >= ndev) {
+    cudaGetLastError();
+    return ESVIO_FE_ENODEV;
+  }
+  esvio_fe* fe = (esvio_fe*)calloc(1, sizeof(esvio_fe));
+  if (!fe) return ESVIO_FE_EINVAL;
+  fe->cfg = *cfg;
+  fe->dev = cfg->device_id;
+  fe->W = cfg->width;
+  fe->H = cfg->height;
+  fe->npx = (size_t)fe->W * fe->H;
+  int rc = ESVIO_FE_OK;
+#define CUC(call)                                              \
+  do {                                                         \
+    cudaError_t ce_ = (call);                                  \
+    if (ce_ != cudaSuccess) {                                  \
+      fprintf(stderr, "esvio_fe_create: %s: %s\n", #call, cudaGetErrorString(ce_)); \
+      free_all(fe);                                            \
+      return ce_ == cudaErrorNoDevice ? ESVIO_FE_ENODEV : ESVIO_FE_ECUDA; \
+    }                                                          \
+  } while (0)
+  CUC(cudaSetDevice(fe->dev));
+  cudaDeviceProp prop;
+  CUC(cudaGetDeviceProperties(&prop, fe->dev));
+  if (prop.major < 10) {
+    fprintf(stderr, "esvio_fe_create: device sm_%d%d is not Blackwell (sm_100a build)\n",
+            prop.major, prop.minor);
+    free_all(fe);
+    return ESVIO_FE_ENODEV;
+  }
+  CUC(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
+
+  BinLayout& L = fe->bl;
+  L.W = fe->W;
+  L.H = fe->H;
+  L.tiles_x = (fe->W + kTileW - 1) / kTileW;
+  L.tiles_y = (fe->H + kTileH - 1) / kTileH;
+  L.n_tiles = L.tiles_x * L.tiles_y;
+  fe->cap = (int)align_up((size_t)cfg->max_events_per_window, 64);
+  L.max_chunks = (fe->cap + kChunk - 1) / kChunk;
+  const int nb = L.n_tiles + 1;
+
+  CUC(cudaMalloc(&fe->sae, fe->npx * 2 * sizeof(double2)));
+  CUC(cudaMalloc(&fe->lat, fe->npx * 2 * sizeof(double2)));
+  build_pyr_desc(fe->W, fe->H, &fe->pd);
+  for (int i = 0; i < 5; ++i) CUC(cudaMalloc(&fe->pyr[i], fe->pd.bytes));
+  for (int c = 0; c < 2; ++c) {
+    CUC(cudaMalloc(&fe->raw[c], (size_t)fe->cap * 16));
+    CUC(cudaMalloc(&fe->esb.bt[c], (size_t)fe->cap * sizeof(double)));
+    CUC(cudaMalloc(&fe->esb.bk[c], (size_t)fe->cap * sizeof(uint16_t)));
+  }
+  CUC(cudaMalloc(&fe->esb.counts, (size_t)2 * nb * L.max_chunks * sizeof(uint32_t)));
+  CUC(cudaMalloc(&fe->esb.bin_total, (size_t)2 * nb * sizeof(uint32_t)));
+  CUC(cudaMalloc(&fe->esb.bin_start, (size_t)2 * (nb + 1) * sizeof(uint32_t)));
+  CUC(cudaMalloc(&fe->flags, (size_t)fe->cap + 16));
+
+  const int M = cfg->max_cnt;
+  TrackBuffers& B = fe->tb;
+  CUC(cudaMalloc(&B.st, sizeof(TrackState)));
+  float2* f2 = nullptr;
+  CUC(cudaMalloc(&f2, sizeof(float2) * (size_t)M * 7));
+  CUC(cudaMemset(f2, 0, sizeof(float2) * (size_t)M * 7));
+  B.prev_pts = f2;
+  B.cur_pts = f2 + M;
+  B.rev_pts = f2 + 2 * M;
+  B.right_pts = f2 + 3 * M;
+  B.rev_left_pts = f2 + 4 * M;
+  B.prev_un = f2 + 5 * M;
+  B.prev_un_r = f2 + 6 * M;
+  int* i4 = nullptr;
+  CUC(cudaMalloc(&i4, sizeof(int) * (size_t)M * 4));
+  CUC(cudaMemset(i4, 0, sizeof(int) * (size_t)M * 4));
+  B.ids = i4;
+  B.cnt = i4 + M;
+  B.prev_un_ids = i4 + 2 * M;
+  B.prev_un_r_ids = i4 + 3 * M;
+  uint8_t* u4 = nullptr;
+  CUC(cudaMalloc(&u4, (size_t)M * 4));
+  CUC(cudaMemset(u4, 0, (size_t)M * 4));
+  B.st_fwd = u4;
+  B.st_bwd = u4 + M;
+  B.st_sf = u4 + 2 * M;
+  B.st_sb = u4 + 3 * M;
+  fe->result_words = kResultHdr + (size_t)kResultArrays * M;
+  CUC(cudaMalloc(&B.result, fe->result_words * 4));
+  for (int i = 0; i < 2; ++i) {
+    CUC(cudaHostAlloc(&fe->h_result[i], fe->result_words * 4, cudaHostAllocDefault));
+    CUC(cudaEventCreateWithFlags(&fe->q_done[i], cudaEventDisableTiming));
+  }
+  CUC(cudaMalloc(&fe->d_scratch_n, 64));
+  CUC(cudaMalloc(&fe->d_scratch_p0, sizeof(float2) * 2 * (size_t)kMaxCnt));
+  fe->d_scratch_p1 = fe->d_scratch_p0 + kMaxCnt;
+  CUC(cudaMalloc(&fe->d_scratch_st, kMaxCnt));
+  for (int i = 0; i <= ESVIO_FE_NUM_STAGES; ++i) CUC(cudaEventCreate(&fe->pev[i]));
+#undef CUC
+
+  TrackParams& P = fe->tp;
+  P.W = fe->W;
+  P.H = fe->H;
+  P.max_cnt = M;
+  P.min_dist = cfg->min_dist;
+  P.flow_back = cfg->flow_back;
+  P.focal_length = cfg->focal_length;
+  P.f_threshold = cfg->f_threshold;
+  for (int c = 0; c < 2; ++c) {
+    const esvio_pinhole& s = cfg->cam[c];
+    P.cam[c] = Pinhole{s.fx, s.fy, s.cx, s.cy, s.k1, s.k2, s.p1, s.p2};
+  }
+  if ((rc = make_state_map(fe, fe->sae, &fe->map_sae)) != ESVIO_FE_OK ||
+      (rc = make_state_map(fe, fe->lat, &fe->map_lat)) != ESVIO_FE_OK) {
+    fprintf(stderr, "esvio_fe_create: %s\n", fe->err);
+    free_all(fe);
+    return rc;
+  }
+  if (select_configure(fe->W, fe->H) != 0 || bin_configure(L.n_tiles) != 0) {
+    fprintf(stderr, "esvio_fe_create: sensor too large for the shared-memory mask / histogram\n");
+    free_all(fe);
+    return ESVIO_FE_EINVAL;
+  }
+  if ((rc = reset_state(fe)) != ESVIO_FE_OK) {
+    fprintf(stderr, "esvio_fe_create: %s\n", fe->err);
+    free_all(fe);
+    return rc;
+  }
+  *out = fe;
+  return ESVIO_FE_OK;
+}
+
+FE_API void esvio_fe_destroy(esvio_fe* fe) { free_all(fe); }
+
+FE_API int esvio_fe_reset(esvio_fe* fe) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  CU(cudaSetDevice(fe->dev));
+  CU(cudaStreamSynchronize(fe->stream));
+  return reset_state(fe);
+}
+
+// ---------------------------------------------------------------------------------------
+// event staging
+// ---------------------------------------------------------------------------------------
+static int stage_events(esvio_fe* fe, int cam, const esvio_events* e, DevEvents* d) {
+  memset(d, 0, sizeof(*d));
+  if (!e || e->n == 0) return ESVIO_FE_OK;
+  if (e->n > (size_t)fe->cap) return fail(fe, ESVIO_FE_ECAPACITY, "events > max_events_per_window", cudaSuccess);
+  const bool soa = e->x && e->y && e->t && e->p;
+  if (!soa && !e->aos) return fail(fe, ESVIO_FE_EINVAL, "events: need x,y,t,p or aos", cudaSuccess);
+  d->n = (int)e->n;
+  if (e->on_device) {
+    if (e->aos) d->aos = (const uint4*)e->aos;
+    else d->x = e->x, d->y = e->y, d->t = e->t, d->p = e->p;
+    return ESVIO_FE_OK;
+  }
+  uint8_t* raw = fe->raw[cam];
+  const size_t n = e->n, cap = (size_t)fe->cap;
+  if (e->aos) {
+    CU(cudaMemcpyAsync(raw, e->aos, n * 16, cudaMemcpyHostToDevice, fe->stream));
+    d->aos = (const uint4*)raw;
+  } else {
+    uint16_t* dx = (uint16_t*)raw;
+    uint16_t* dy = (uint16_t*)(raw + 2 * cap);
+    double* dt = (double*)(raw + 4 * cap);
+    uint8_t* dp = raw + 12 * cap;
+    CU(cudaMemcpyAsync(dx, e->x, n * 2, cudaMemcpyHostToDevice, fe->stream));
+    CU(cudaMemcpyAsync(dy, e->y, n * 2, cudaMemcpyHostToDevice, fe->stream));
+    CU(cudaMemcpyAsync(dt, e->t, n * 8, cudaMemcpyHostToDevice, fe->stream));
+    CU(cudaMemcpyAsync(dp, e->p, n, cudaMemcpyHostToDevice, fe->stream));
+    d->x = dx, d->y = dy, d->t = dt, d->p = dp;
+  }
+  return ESVIO_FE_OK;
+}
+
+static void prof_mark(esvio_fe* fe, int i) {
+  if (fe->profiling) cudaEventRecord(fe->pev[i], fe->stream);
+}
+
+// createSAE_* + SAEtoTimeSurface_* + pyramids (feature_tracker.cpp:356-368) into the
+// pyramid buffers `left_idx` / right
+static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev[2], int left_idx) {
+  launch_bin_events(fe->bl, fe->esb, ev, fe->stream, &fe->launches);
+  SaeTsParams sp;
+  sp.W = fe->W;
+  sp.H = fe->H;
+  sp.tiles_x = fe->bl.tiles_x;
+  sp.n_tiles = fe->bl.n_tiles;
+  sp.t_ref = t_ref;
+  sp.decay_sec = fe->cfg.decay_ms / 1000.0;
+  sp.filter_threshold = fe->cfg.feature_filter_threshold;
+  sp.ignore_polarity = fe->cfg.ignore_polarity;
+  sp.bin_start = fe->esb.bin_start;
+  sp.bt[0] = fe->esb.bt[0];
+  sp.bt[1] = fe->esb.bt[1];
+  sp.bk[0] = fe->esb.bk[0];
+  sp.bk[1] = fe->esb.bk[1];
+  sp.ts[0] = fe->pyr[left_idx];
+  sp.ts[1] = fe->pyr[2];
+  sp.ts_pitch = fe->pd.pitch[0];
+  launch_sae_update_ts(sp, fe->map_sae, fe->map_lat, fe->stream, &fe->launches);
+  prof_mark(fe, 2);
+  uint8_t* imgs[2] = {fe->pyr[left_idx], fe->pyr[2]};
+  launch_pyramids(fe->pd, imgs, 2, fe->stream, &fe->launches);
+  CU(cudaGetLastError());
+  return ESVIO_FE_OK;
+}
+
+static CornerParams corner_params(esvio_fe* fe, int left_idx, int and_ts) {
+  CornerParams cp;
+  cp.W = fe->W;
+  cp.H = fe->H;
+  cp.min_dist = fe->cfg.min_dist;
+  cp.filter_threshold = fe->cfg.feature_filter_threshold;
+  cp.ts_lk_threshold = fe->cfg.ts_lk_threshold;
+  cp.sae = fe->sae;
+  cp.lat = fe->lat;
+  cp.ts = fe->pyr[left_idx];
+  cp.ts_pitch = fe->pd.pitch[0];
+  cp.and_ts_test = and_ts;
+  return cp;
+}
+
+FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_events* left,
+                                 const esvio_events* right, int32_t pub_this_frame) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  if (fe->q_count >= 2) return fail(fe, ESVIO_FE_ESTATE, "two windows already in flight", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  cudaStream_t s = fe->stream;
+  prof_mark(fe, 0);
+  DevEvents ev[2];
+  int rc;
+  if ((rc = stage_events(fe, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
+  if ((rc = stage_events(fe, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
+  prof_mark(fe, 1);
+
+  const int cur = fe->windows == 0 ? 0 : 1 - fe->cur_left;
+  const int prev = fe->windows == 0 ? 0 : fe->cur_left;  // first window: prev_img = cur_img
+  if ((rc = run_event_stage(fe, cur_time, ev, cur)) != ESVIO_FE_OK) return rc;
+  prof_mark(fe, 3);
+  if (pub_this_frame) {
+    launch_corner_flags(corner_params(fe, cur, 1), ev[0], fe->flags, s, &fe->launches);
+  }
+  prof_mark(fe, 4);
+
+  const TrackBuffers& B = fe->tb;
+  const int M = fe->cfg.max_cnt;
+  // temporal LK (feature_tracker.cpp:405-437)
+  launch_lk(fe->pd, fe->pyr[prev], fe->pyr[cur], B.prev_pts, B.cur_pts, B.st_fwd, &B.st->n_prev, M,
+            3, 0, s, &fe->launches);
+  if (fe->cfg.flow_back) {
+    CU(cudaMemcpyAsync(B.rev_pts, B.prev_pts, sizeof(float2) * M, cudaMemcpyDeviceToDevice, s));
+    launch_lk(fe->pd, fe->pyr[cur], fe->pyr[prev], B.cur_pts, B.rev_pts, B.st_bwd, &B.st->n_prev,
+              M, 1, 1, s, &fe->launches);
+  }
+  launch_post_temporal(fe->tp, B, s, &fe->launches);
+  prof_mark(fe, 5);
+  if (pub_this_frame) {
+    if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s, &fe->launches);
+    launch_select(fe->tp, B, ev[0], fe->flags, s, &fe->launches);
+  }
+  prof_mark(fe, 6);
+  // stereo LK (feature_tracker.cpp:475-510)
+  launch_lk(fe->pd, fe->pyr[cur], fe->pyr[2], B.cur_pts, B.right_pts, B.st_sf, &B.st->n_cur, M, 3,
+            0, s, &fe->launches);
+  if (fe->cfg.flow_back)
+    launch_lk(fe->pd, fe->pyr[2], fe->pyr[cur], B.right_pts, B.rev_left_pts, B.st_sb,
+              &B.st->n_cur, M, 3, 0, s, &fe->launches);
+  launch_finalize(fe->tp, B, cur_time, fe->prev_time, s, &fe->launches);
+  prof_mark(fe, 7);
+  const int slot = (fe->q_head + fe->q_count) & 1;
+  CU(cudaMemcpyAsync(fe->h_result[slot], B.result, fe->result_words * 4, cudaMemcpyDeviceToHost, s));
+  prof_mark(fe, 8);
+  CU(cudaEventRecord(fe->q_done[slot], s));
+  CU(cudaGetLastError());
+  fe->q_count++;
+  fe->cur_left = cur;
+  fe->windows++;
+  fe->prev_time = cur_time;
+  fe->pev_valid = fe->profiling;
+  (void)left;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_track_wait(esvio_fe* fe, esvio_tracks* out) {
+  if (!fe || !out) return ESVIO_FE_EINVAL;
+  if (fe->q_count <= 0) return fail(fe, ESVIO_FE_ESTATE, "wait without submit", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  const int slot = fe->q_head;
+  CU(cudaEventSynchronize(fe->q_done[slot]));
+  fe->q_head = (fe->q_head + 1) & 1;
+  fe->q_count--;
+  const int M = fe->cfg.max_cnt;
+  if (out->capacity < M) return fail(fe, ESVIO_FE_ECAPACITY, "esvio_tracks.capacity < max_cnt", cudaSuccess);
+  const int32_t* r = fe->h_result[slot];
+  const int nl = r[0], nr = r[1];
+  out->n_left = nl;
+  out->n_right = nr;
+  const int32_t* a = r + kResultHdr;
+  void* dst[kResultArrays] = {out->id, out->track_cnt, out->u,     out->v,     out->un_x,
+                              out->un_y, out->vx,      out->vy,    out->id_right, out->ru,
+                              out->rv, out->run_x,     out->run_y, out->rvx,   out->rvy};
+  for (int k = 0; k < kResultArrays; ++k) {
+    const int cnt = k < 8 ? nl : nr;
+    if (dst[k] && cnt > 0) memcpy(dst[k], a + (size_t)k * M, (size_t)cnt * 4);
+  }
+  esvio_stats& s = out->stats;
+  memset(&s, 0, sizeof(s));
+  s.n_prev = r[2];
+  s.n_after_temporal = r[3];
+  s.n_after_ransac = r[4];
+  s.n_after_mask = r[5];
+  s.n_new = r[6];
+  s.n_corner_flags = r[7];
+  s.ransac_iters = r[8];
+  if (fe->pev_valid && fe->q_count == 0) {
+    for (int i = 0; i < ESVIO_FE_NUM_STAGES; ++i)
+      cudaEventElapsedTime(&fe->stage_ms[i], fe->pev[i], fe->pev[i + 1]);
+  }
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_track(esvio_fe* fe, double cur_time, const esvio_events* left,
+                          const esvio_events* right, int32_t pub_this_frame, esvio_tracks* out) {
+  if (!fe || !out) return ESVIO_FE_EINVAL;
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "track while windows are in flight", cudaSuccess);
+  const int rc = esvio_fe_track_submit(fe, cur_time, left, right, pub_this_frame);
+  if (rc != ESVIO_FE_OK) return rc;
+  return esvio_fe_track_wait(fe, out);
+}
+
+FE_API int esvio_fe_time_surface(esvio_fe* fe, int32_t cam, uint8_t* dst, size_t stride) {
+  if (!fe || !dst || cam < 0 || cam > 1 || stride < (size_t)fe->W) return ESVIO_FE_EINVAL;
+  CU(cudaSetDevice(fe->dev));
+  const uint8_t* src = fe->pyr[cam == 0 ? fe->cur_left : 2];
+  CU(cudaMemcpy2DAsync(dst, stride, src, fe->pd.pitch[0], fe->W, fe->H, cudaMemcpyDeviceToHost,
+                       fe->stream));
+  CU(cudaStreamSynchronize(fe->stream));
+  return ESVIO_FE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// memory helpers / plumbing / profiling
+// ---------------------------------------------------------------------------------------
+FE_API void* esvio_fe_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+FE_API void esvio_fe_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+FE_API int esvio_fe_device_alloc(esvio_fe* fe, size_t bytes, void** out) {
+  if (!fe || !out) return ESVIO_FE_EINVAL;
+  CU(cudaSetDevice(fe->dev));
+  CU(cudaMalloc(out, bytes ? bytes : 1));
+  return ESVIO_FE_OK;
+}
+FE_API int esvio_fe_device_free(esvio_fe* fe, void* p) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  CU(cudaSetDevice(fe->dev));
+  CU(cudaFree(p));
+  return ESVIO_FE_OK;
+}
+FE_API int esvio_fe_copy_to_device(esvio_fe* fe, void* dst, const void* src, size_t bytes) {
+  if (!fe || !dst || !src) return ESVIO_FE_EINVAL;
+  CU(cudaSetDevice(fe->dev));
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, fe->stream));
+  CU(cudaStreamSynchronize(fe->stream));
+  return ESVIO_FE_OK;
+}
+FE_API int esvio_fe_result_device_ptr(esvio_fe* fe, void** ptr, size_t* bytes) {
+  if (!fe || !ptr || !bytes) return ESVIO_FE_EINVAL;
+  *ptr = fe->tb.result;
+  *bytes = fe->result_words * 4;
+  return ESVIO_FE_OK;
+}
+FE_API int esvio_fe_stream(esvio_fe* fe, void** cuda_stream) {
+  if (!fe || !cuda_stream) return ESVIO_FE_EINVAL;
+  *cuda_stream = (void*)fe->stream;
+  return ESVIO_FE_OK;
+}
+FE_API int esvio_fe_set_profiling(esvio_fe* fe, int32_t on) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  fe->profiling = on != 0;
+  fe->pev_valid = 0;
+  return ESVIO_FE_OK;
+}
+FE_API int esvio_fe_get_stage_ms(esvio_fe* fe, float* ms) {
+  if (!fe || !ms) return ESVIO_FE_EINVAL;
+  if (!fe->pev_valid) return fail(fe, ESVIO_FE_ESTATE, "no profiled window", cudaSuccess);
+  memcpy(ms, fe->stage_ms, sizeof(fe->stage_ms));
+  return ESVIO_FE_OK;
+}
+FE_API int esvio_fe_kernel_launches(esvio_fe* fe, int64_t* count) {
+  if (!fe || !count) return ESVIO_FE_EINVAL;
+  *count = fe->launches;
+  return ESVIO_FE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage-level entry points (parity tests)
+// ---------------------------------------------------------------------------------------
+FE_API int esvio_fe_get_sae(esvio_fe* fe, int32_t cam, int32_t plane, double* dst) {
+  if (!fe || !dst || cam < 0 || cam > 1 || plane < 0 || plane > 3) return ESVIO_FE_EINVAL;
+  CU(cudaSetDevice(fe->dev));
+  CU(cudaStreamSynchronize(fe->stream));
+  const double2* base = (plane < 2 ? fe->sae : fe->lat) + (size_t)cam * fe->npx;
+  const char* src = (const char*)base + (plane & 1) * sizeof(double);
+  // strided gather of one double per pixel
+  CU(cudaMemcpy2D(dst, sizeof(double), src, sizeof(double2), sizeof(double), fe->npx,
+                  cudaMemcpyDeviceToHost));
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_stage_update(esvio_fe* fe, double t_ref, const esvio_events* left,
+                                 const esvio_events* right) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "windows in flight", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  DevEvents ev[2];
+  int rc;
+  if ((rc = stage_events(fe, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
+  if ((rc = stage_events(fe, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, t_ref, ev, fe->cur_left)) != ESVIO_FE_OK) return rc;
+  CU(cudaStreamSynchronize(fe->stream));
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_stage_corner_flags(esvio_fe* fe, const esvio_events* left, int32_t and_ts_test,
+                                       uint8_t* flags) {
+  if (!fe || !left || !flags) return ESVIO_FE_EINVAL;
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "windows in flight", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  DevEvents ev;
+  int rc;
+  if ((rc = stage_events(fe, 0, left, &ev)) != ESVIO_FE_OK) return rc;
+  launch_corner_flags(corner_params(fe, fe->cur_left, and_ts_test), ev, fe->flags, fe->stream,
+                      &fe->launches);
+  CU(cudaGetLastError());
+  if (ev.n > 0)
+    CU(cudaMemcpyAsync(flags, fe->flags, ev.n, cudaMemcpyDeviceToHost, fe->stream));
+  CU(cudaStreamSynchronize(fe->stream));
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_get_pyramid_level(esvio_fe* fe, int32_t which, int32_t level, uint8_t* dst,
+                                      int32_t* w, int32_t* h) {
+  if (!fe || which < 0 || which > 2 || level < 0 || level >= fe->pd.levels) return ESVIO_FE_EINVAL;
+  CU(cudaSetDevice(fe->dev));
+  if (w) *w = fe->pd.w[level];
+  if (h) *h = fe->pd.h[level];
+  if (!dst) return ESVIO_FE_OK;
+  const int idx = which == 0 ? fe->cur_left : (which == 1 ? 2 : 1 - fe->cur_left);
+  CU(cudaMemcpy2DAsync(dst, fe->pd.w[level], fe->pyr[idx] + fe->pd.off[level], fe->pd.pitch[level],
+                       fe->pd.w[level], fe->pd.h[level], cudaMemcpyDeviceToHost, fe->stream));
+  CU(cudaStreamSynchronize(fe->stream));
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_stage_lk(esvio_fe* fe, const uint8_t* prev_img, const uint8_t* next_img,
+                             const float* prev_pts, float* next_pts, int32_t n, uint8_t* status,
+                             int32_t max_level, int32_t use_initial_flow) {
+  if (!fe || !prev_img || !next_img || !prev_pts || !next_pts || !status || n < 0 ||
+      n > kMaxCnt || max_level < 0)
+    return ESVIO_FE_EINVAL;
+  if (n == 0) return ESVIO_FE_OK;
+  CU(cudaSetDevice(fe->dev));
+  cudaStream_t s = fe->stream;
+  CU(cudaMemcpy2DAsync(fe->pyr[3], fe->pd.pitch[0], prev_img, fe->W, fe->W, fe->H,
+                       cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpy2DAsync(fe->pyr[4], fe->pd.pitch[0], next_img, fe->W, fe->W, fe->H,
+                       cudaMemcpyHostToDevice, s));
+  uint8_t* imgs[2] = {fe->pyr[3], fe->pyr[4]};
+  launch_pyramids(fe->pd, imgs, 2, s, &fe->launches);
+  CU(cudaMemcpyAsync(fe->d_scratch_n, &n, sizeof(int), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(fe->d_scratch_p0, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
+  if (use_initial_flow)
+    CU(cudaMemcpyAsync(fe->d_scratch_p1, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
+  launch_lk(fe->pd, fe->pyr[3], fe->pyr[4], fe->d_scratch_p0, fe->d_scratch_p1, fe->d_scratch_st,
+            fe->d_scratch_n, n, max_level, use_initial_flow, s, &fe->launches);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(next_pts, fe->d_scratch_p1, sizeof(float2) * n, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(status, fe->d_scratch_st, n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_stage_fmat_mask(esvio_fe* fe, const float* p1, const float* p2, int32_t n,
+                                    double thresh, uint8_t* mask, int32_t* iters) {
+  if (!fe || !p1 || !p2 || !mask || n < 0 || n > kMaxCnt) return ESVIO_FE_EINVAL;
+  if (n == 0) return ESVIO_FE_OK;
+  CU(cudaSetDevice(fe->dev));
+  cudaStream_t s = fe->stream;
+  CU(cudaMemcpyAsync(fe->d_scratch_p0, p1, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(fe->d_scratch_p1, p2, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
+  launch_ransac_stage(fe->d_scratch_p0, fe->d_scratch_p1, n, thresh, fe->d_scratch_st,
+                      fe->d_scratch_n, s, &fe->launches);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(mask, fe->d_scratch_st, n, cudaMemcpyDeviceToHost, s));
+  int it = 0;
+  CU(cudaMemcpyAsync(&it, fe->d_scratch_n, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (iters) *iters = it;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_stage_select(esvio_fe* fe, const esvio_events* left, int32_t n,
+                                 const float* pts, const int32_t* ids, const int32_t* track_cnt,
+                                 int32_t* n_out, float* pts_out, int32_t* ids_out,
+                                 int32_t* track_cnt_out, int32_t* n_kept) {
+  if (!fe || !left || n < 0 || n > fe->cfg.max_cnt || !n_out || !pts_out || !ids_out ||
+      !track_cnt_out)
+    return ESVIO_FE_EINVAL;
+  if (n > 0 && (!pts || !ids || !track_cnt)) return ESVIO_FE_EINVAL;
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "windows in flight", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  cudaStream_t s = fe->stream;
+  const TrackBuffers& B = fe->tb;
+  DevEvents ev;
+  int rc;
+  if ((rc = stage_events(fe, 0, left, &ev)) != ESVIO_FE_OK) return rc;
+  TrackState st;
+  CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  st.n_cur = n;
+  CU(cudaMemcpyAsync(B.st, &st, sizeof(st), cudaMemcpyHostToDevice, s));
+  if (n > 0) {
+    CU(cudaMemcpyAsync(B.cur_pts, pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(B.ids, ids, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(B.cnt, track_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  }
+  launch_corner_flags(corner_params(fe, fe->cur_left, 1), ev, fe->flags, s, &fe->launches);
+  launch_select(fe->tp, B, ev, fe->flags, s, &fe->launches);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  *n_out = st.n_cur;
+  if (n_kept) *n_kept = st.stat_after_mask;
+  if (st.n_cur > 0) {
+    CU(cudaMemcpyAsync(pts_out, B.cur_pts, sizeof(float2) * st.n_cur, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ids_out, B.ids, sizeof(int) * st.n_cur, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(track_cnt_out, B.cnt, sizeof(int) * st.n_cur, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_stage_undistort(esvio_fe* fe, int32_t cam, const float* uv, int32_t n,
+                                    float* out) {
+  if (!fe || cam < 0 || cam > 1 || !uv || !out || n < 0 || n > kMaxCnt) return ESVIO_FE_EINVAL;
+  if (n == 0) return ESVIO_FE_OK;
+  CU(cudaSetDevice(fe->dev));
+  cudaStream_t s = fe->stream;
+  CU(cudaMemcpyAsync(fe->d_scratch_p0, uv, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
+  launch_undistort(fe->tp.cam[cam], fe->d_scratch_p0, n, fe->d_scratch_p1, s, &fe->launches);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, fe->d_scratch_p1, sizeof(float2) * n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return ESVIO_FE_OK;
+}

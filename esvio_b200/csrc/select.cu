@@ -1,0 +1,465 @@
+// select.cu -- the per-window bookkeeping of FeatureTracker::trackEvent
+// (feature_tracker/src/feature_tracker.cpp:340-603) that sits between the LK launches.
+// All of it is tiny and order-dependent, so each step is ONE CTA working on device-resident
+// counters (TrackState): nothing returns to the host until the packed result is copied out.
+#include "common.cuh"
+
+namespace esvio {
+
+// inBorder_event (feature_tracker.cpp:48-54)
+__device__ __forceinline__ bool in_border(int W, int H, float2 p) {
+  const int ix = cv_round(p.x), iy = cv_round(p.y);
+  return 1 <= ix && ix < W - 1 && 1 <= iy && iy < H - 1;
+}
+
+// FeatureTracker::distance (feature_tracker.cpp:1314-1319): float differences, double norm
+__device__ __forceinline__ double pt_dist(float2 a, float2 b) {
+  const double dx = (double)(a.x - b.x), dy = (double)(a.y - b.y);
+  return sqrt(dx * dx + dy * dy);
+}
+
+// PinholeCamera::liftProjective (camera_model/src/camera_models/PinholeCamera.cc:450-510)
+// with PinholeCamera::distortion (:646-662): 8 fixed-point iterations, fp64.
+__device__ __forceinline__ void lift_projective(const Pinhole& c, double u, double v, double& ox,
+                                                double& oy) {
+  const double inv_fx = 1.0 / c.fx, inv_fy = 1.0 / c.fy;
+  const double off_x = -c.cx / c.fx, off_y = -c.cy / c.fy;
+  const double xd = inv_fx * u + off_x, yd = inv_fy * v + off_y;
+  double xu = xd, yu = yd;
+  if (!(c.k1 == 0.0 && c.k2 == 0.0 && c.p1 == 0.0 && c.p2 == 0.0)) {
+    for (int it = 0; it < 8; ++it) {
+      const double xx = xu * xu, yy = yu * yu, xy = xu * yu;
+      const double r2 = xx + yy;
+      const double rad = c.k1 * r2 + c.k2 * r2 * r2;
+      const double ddx = xu * rad + 2.0 * c.p1 * xy + c.p2 * (r2 + 2.0 * xx);
+      const double ddy = yu * rad + 2.0 * c.p2 * xy + c.p1 * (r2 + 2.0 * yy);
+      xu = xd - ddx;
+      yu = yd - ddy;
+    }
+  }
+  ox = xu;
+  oy = yu;
+}
+
+// order-preserving compaction offsets for up to blockDim.x flags (one per thread);
+// returns the exclusive prefix, total in *total (shared)
+__device__ int block_excl_scan_1024(int flag, int* s_warp /*33 ints*/, int* total) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int in_warp = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    int v = lane < nw ? s_warp[lane] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    s_warp[lane] = incl - v;
+    if (lane == 31) s_warp[32] = incl;
+  }
+  __syncthreads();
+  const int r = s_warp[warp] + in_warp;
+  *total = s_warp[32];
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------
+// after temporal forward + backward LK (feature_tracker.cpp:419-440)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_post_temporal(TrackParams P, TrackBuffers B) {
+  __shared__ int s_warp[33];
+  TrackState* st = B.st;
+  const int n = st->n_prev;
+  const int i = threadIdx.x;
+  int keep = 0;
+  float2 pp, cp;
+  int id = 0, cnt = 0;
+  if (i < n) {
+    pp = B.prev_pts[i];
+    cp = B.cur_pts[i];
+    id = B.ids[i];
+    cnt = B.cnt[i];
+    keep = B.st_fwd[i] != 0;
+    if (P.flow_back) keep = keep && B.st_bwd[i] && pt_dist(pp, B.rev_pts[i]) <= 0.5;
+    if (keep && !in_border(P.W, P.H, cp)) keep = 0;
+  }
+  int total;
+  const int pos = block_excl_scan_1024(keep, s_warp, &total);
+  if (keep) {
+    B.prev_pts[pos] = pp;
+    B.cur_pts[pos] = cp;
+    B.ids[pos] = id;
+    B.cnt[pos] = cnt + 1;  // for (auto &n : track_cnt) n++;
+  }
+  if (i == 0) {
+    st->stat_n_prev = n;
+    st->n_cur = total;
+    st->stat_after_temporal = total;
+    st->stat_after_ransac = total;
+    st->stat_after_mask = total;
+    st->stat_new = 0;
+    st->stat_ransac_iters = 0;
+  }
+}
+
+void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
+                          int64_t* launches) {
+  k_post_temporal<<<1, 1024, 0, s>>>(P, B);
+  ++*launches;
+}
+
+// ------------------------------------------------------------------------------------
+// Event_setMask + Event_FeaturesToTrack + id assignment (feature_tracker.cpp:123-151,
+// 13-38, 446-468).  The W x H mask is one bit per pixel in shared memory.
+// ------------------------------------------------------------------------------------
+constexpr int kMaxDiscR = 64;
+
+// half widths of OpenCV's filled circle (drawing.cpp Circle, fill): row cy+-k spans
+// [cx - hw[k], cx + hw[k]]
+__device__ void disc_half_widths(int r, int* hw) {
+  for (int k = 0; k <= r; ++k) hw[k] = -1;
+  int err = 0, dx = r, dy = 0, plus = 1, minus = (r << 1) - 1;
+  while (dx >= dy) {
+    if (dx > hw[dy]) hw[dy] = dx;
+    if (dy > hw[dx]) hw[dx] = dy;
+    dy++;
+    err += plus;
+    plus += 2;
+    const int m = (err <= 0) - 1;
+    err -= minus & m;
+    dx += m;
+    minus -= m & 2;
+  }
+}
+
+// executed by one full warp: rows are distributed over lanes, so plain ORs do not collide
+__device__ __forceinline__ void fill_disc_warp(uint32_t* mask, int words, int W, int H, int cx,
+                                               int cy, int r, const int* hw) {
+  for (int k = lane_id() - r; k <= r; k += 32) {
+    const int yy = cy + k;
+    if (yy < 0 || yy >= H) continue;
+    const int h = hw[k < 0 ? -k : k];
+    if (h < 0) continue;
+    int x0 = cx - h, x1 = cx + h;
+    if (x0 < 0) x0 = 0;
+    if (x1 > W - 1) x1 = W - 1;
+    if (x0 > x1) continue;
+    uint32_t* row = mask + (size_t)yy * words;
+    const int w0 = x0 >> 5, w1 = x1 >> 5;
+    for (int w = w0; w <= w1; ++w) {
+      uint32_t bits = 0xffffffffu;
+      if (w == w0) bits &= 0xffffffffu << (x0 & 31);
+      if (w == w1) bits &= 0xffffffffu >> (31 - (x1 & 31));
+      row[w] |= bits;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ bool mask_test(const uint32_t* mask, int words, int x, int y) {
+  return (mask[(size_t)y * words + (x >> 5)] >> (x & 31)) & 1u;
+}
+
+size_t select_smem_bytes(int W, int H) { return (size_t)H * ((W + 31) / 32) * sizeof(uint32_t); }
+
+constexpr int kSelThreads = 1024;
+constexpr int kSelPerThread = 4;
+
+__global__ void __launch_bounds__(kSelThreads)
+k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict__ flags) {
+  extern __shared__ uint32_t s_mask[];
+  __shared__ int s_hw[kMaxDiscR + 1];
+  __shared__ int s_warp[33];
+  __shared__ int s_order[kMaxCnt];
+  __shared__ float2 s_pts[kMaxCnt];
+  __shared__ int s_ids[kMaxCnt], s_cnt[kMaxCnt];
+  __shared__ uint32_t s_cand[kSelThreads * kSelPerThread];
+  __shared__ int s_kept, s_found;
+
+  TrackState* st = B.st;
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const int W = P.W, H = P.H, words = (W + 31) / 32;
+  const int n = st->n_cur;
+  for (int i = tid; i < H * words; i += blockDim.x) s_mask[i] = 0;
+  if (tid == 0) {
+    disc_half_widths(P.min_dist, s_hw);
+    s_kept = 0;
+    s_found = 0;
+  }
+  // ---- Event_setMask: visit by track_cnt descending (ties keep their order), keep a
+  //      point iff its rounded pixel is still free, then blank a disc of MIN_DIST
+  if (tid < n) {
+    s_pts[tid] = B.cur_pts[tid];
+    s_ids[tid] = B.ids[tid];
+    s_cnt[tid] = B.cnt[tid];
+  }
+  __syncthreads();
+  if (tid < n) {
+    const int c = s_cnt[tid];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (s_cnt[j] > c) || (s_cnt[j] == c && j < tid);
+    s_order[rank] = tid;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int kept = 0;
+    for (int k = 0; k < n; ++k) {
+      const int i = s_order[k];
+      const float2 p = s_pts[i];
+      const int cx = cv_round(p.x), cy = cv_round(p.y);
+      if (cx < 0 || cx >= W || cy < 0 || cy >= H) continue;
+      if (!mask_test(s_mask, words, cx, cy)) {
+        if (lane == 0) {
+          B.cur_pts[kept] = p;
+          B.ids[kept] = s_ids[i];
+          B.cnt[kept] = s_cnt[i];
+        }
+        ++kept;
+        __syncwarp();
+        fill_disc_warp(s_mask, words, W, H, cx, cy, P.min_dist, s_hw);
+      }
+    }
+    if (lane == 0) s_kept = kept;
+  }
+  __syncthreads();
+  const int kept = s_kept;
+  const int want = P.max_cnt - kept;
+
+  // ---- Event_FeaturesToTrack: first come, first served in stream order
+  if (want > 0) {
+    const int step = kSelThreads * kSelPerThread;
+    for (int base = 0; base < ev.n; base += step) {
+      const int i0 = base + tid * kSelPerThread;
+      uint32_t f4 = 0;
+      if (i0 + kSelPerThread <= ev.n) {
+        f4 = *reinterpret_cast<const uint32_t*>(flags + i0);
+      } else {
+        for (int k = 0; k < kSelPerThread; ++k)
+          if (i0 + k < ev.n) f4 |= (uint32_t)flags[i0 + k] << (8 * k);
+      }
+      uint32_t cand[kSelPerThread];
+      int nc = 0;
+      if (f4) {
+        for (int k = 0; k < kSelPerThread; ++k) {
+          if ((f4 >> (8 * k)) & 0xff) {
+            const Ev e = load_event(ev, i0 + k);
+            if (!mask_test(s_mask, words, e.x, e.y)) cand[nc++] = (uint32_t)e.x | ((uint32_t)e.y << 16);
+          }
+        }
+      }
+      if (!__syncthreads_or(nc)) continue;
+      // stable compaction of this step's candidates
+      int total = 0, pos = 0;
+      {
+        // exclusive scan of nc over the block
+        int incl = nc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+          const int v = s_warp[lane];
+          int w = v;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += o;
+          }
+          s_warp[lane] = w - v;
+          if (lane == 31) s_warp[32] = w;
+        }
+        __syncthreads();
+        pos = s_warp[warp] + incl - nc;
+        total = s_warp[32];
+      }
+      for (int k = 0; k < nc; ++k) s_cand[pos + k] = cand[k];
+      __syncthreads();
+      if (warp == 0) {
+        int found = s_found;
+        for (int c = 0; c < total && found < want; ++c) {
+          const uint32_t xy = s_cand[c];
+          const int x = xy & 0xffff, y = xy >> 16;
+          if (mask_test(s_mask, words, x, y)) continue;
+          if (lane == 0) {
+            B.cur_pts[kept + found] = make_float2((float)x, (float)y);
+            B.ids[kept + found] = st->next_id + found;
+            B.cnt[kept + found] = 1;
+          }
+          ++found;
+          __syncwarp();
+          fill_disc_warp(s_mask, words, W, H, x, y, P.min_dist, s_hw);
+        }
+        if (lane == 0) s_found = found;
+      }
+      __syncthreads();
+      if (s_found >= want) break;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int found = s_found;
+    st->stat_after_mask = kept;
+    st->stat_new = found;
+    st->n_cur = kept + found;
+    st->next_id += found;
+  }
+}
+
+int select_configure(int W, int H) {
+  const size_t bytes = select_smem_bytes(W, H);
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, k_select) != cudaSuccess) return -1;
+  if (bytes + fa.sharedSizeBytes > 227 * 1024) return -1;
+  return cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)bytes) == cudaSuccess ? 0 : -1;
+}
+
+void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents& left,
+                   const uint8_t* flags, cudaStream_t s, int64_t* launches) {
+  k_select<<<1, kSelThreads, select_smem_bytes(P.W, P.H), s>>>(P, B, left, flags);
+  ++*launches;
+}
+
+// ------------------------------------------------------------------------------------
+// left undistort + velocity, stereo forward/backward check, right undistort + velocity,
+// result packing and the state roll (feature_tracker.cpp:470-473, 496-510, 570-574, 585-590)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_finalize(TrackParams P, TrackBuffers B, double cur_time, double prev_time) {
+  __shared__ int s_warp[33];
+  TrackState* st = B.st;
+  const int i = threadIdx.x;
+  const int n = st->n_cur;
+  const int M = P.max_cnt;
+  int32_t* res = B.result;
+  int32_t* r_id = res + kResultHdr;
+  int32_t* r_cnt = r_id + M;
+  float* r_u = reinterpret_cast<float*>(r_cnt + M);
+  float *r_v = r_u + M, *r_unx = r_v + M, *r_uny = r_unx + M, *r_vx = r_uny + M, *r_vy = r_vx + M;
+  int32_t* r_idr = reinterpret_cast<int32_t*>(r_vy + M);
+  float* r_ru = reinterpret_cast<float*>(r_idr + M);
+  float *r_rv = r_ru + M, *r_runx = r_rv + M, *r_runy = r_runx + M, *r_rvx = r_runy + M,
+        *r_rvy = r_rvx + M;
+  const double dt = cur_time - prev_time;
+  const int np_un = st->n_prev_un, np_un_r = st->n_prev_un_r;
+
+  float2 cp = make_float2(0.f, 0.f), un = make_float2(0.f, 0.f);
+  int id = -1;
+  int keep = 0;
+  float2 rp = make_float2(0.f, 0.f);
+  if (i < n) {
+    cp = B.cur_pts[i];
+    id = B.ids[i];
+    double x, y;
+    lift_projective(P.cam[0], (double)cp.x, (double)cp.y, x, y);
+    un = make_float2((float)x, (float)y);
+    // ptsVelocity (feature_tracker.cpp:1004-1045)
+    float vx = 0.f, vy = 0.f;
+    if (np_un > 0 && id != -1) {
+      for (int j = 0; j < np_un; ++j)
+        if (B.prev_un_ids[j] == id) {
+          const float2 q = B.prev_un[j];
+          vx = (float)((double)(un.x - q.x) / dt);
+          vy = (float)((double)(un.y - q.y) / dt);
+          break;
+        }
+    }
+    r_id[i] = id;
+    r_cnt[i] = B.cnt[i];
+    r_u[i] = cp.x;
+    r_v[i] = cp.y;
+    r_unx[i] = un.x;
+    r_uny[i] = un.y;
+    r_vx[i] = vx;
+    r_vy[i] = vy;
+    // stereo check
+    rp = B.right_pts[i];
+    keep = B.st_sf[i] != 0;
+    if (P.flow_back)
+      keep = keep && B.st_sb[i] && in_border(P.W, P.H, rp) && pt_dist(cp, B.rev_left_pts[i]) <= 0.5;
+  }
+  int total;
+  const int pos = block_excl_scan_1024(keep, s_warp, &total);
+  // all reads of prev_un / prev_un_ids are done (barriers inside the scan); roll the state
+  if (i < n) {
+    B.prev_pts[i] = cp;
+    B.prev_un_ids[i] = id;
+    B.prev_un[i] = un;
+  }
+  float2 unr = make_float2(0.f, 0.f);
+  float rvx = 0.f, rvy = 0.f;
+  if (keep) {
+    double x, y;
+    lift_projective(P.cam[1], (double)rp.x, (double)rp.y, x, y);
+    unr = make_float2((float)x, (float)y);
+    if (np_un_r > 0 && id != -1) {
+      for (int j = 0; j < np_un_r; ++j)
+        if (B.prev_un_r_ids[j] == id) {
+          const float2 q = B.prev_un_r[j];
+          rvx = (float)((double)(unr.x - q.x) / dt);
+          rvy = (float)((double)(unr.y - q.y) / dt);
+          break;
+        }
+    }
+    r_idr[pos] = id;
+    r_ru[pos] = rp.x;
+    r_rv[pos] = rp.y;
+    r_runx[pos] = unr.x;
+    r_runy[pos] = unr.y;
+    r_rvx[pos] = rvx;
+    r_rvy[pos] = rvy;
+  }
+  __syncthreads();
+  if (keep) {
+    B.prev_un_r_ids[pos] = id;
+    B.prev_un_r[pos] = unr;
+  }
+  if (i == 0) {
+    st->n_right = total;
+    st->n_prev = n;
+    st->n_prev_un = n;
+    st->n_prev_un_r = total;
+    res[0] = n;
+    res[1] = total;
+    res[2] = st->stat_n_prev;
+    res[3] = st->stat_after_temporal;
+    res[4] = st->stat_after_ransac;
+    res[5] = st->stat_after_mask;
+    res[6] = st->stat_new;
+    res[7] = st->stat_corner_flags;
+    res[8] = st->stat_ransac_iters;
+    res[9] = st->next_id;
+  }
+}
+
+void launch_finalize(const TrackParams& P, const TrackBuffers& B, double cur_time,
+                     double prev_time, cudaStream_t s, int64_t* launches) {
+  k_finalize<<<1, 1024, 0, s>>>(P, B, cur_time, prev_time);
+  ++*launches;
+}
+
+__global__ void k_undistort(Pinhole cam, const float2* __restrict__ uv, int n,
+                            float2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x, y;
+  lift_projective(cam, (double)uv[i].x, (double)uv[i].y, x, y);
+  out[i] = make_float2((float)x, (float)y);
+}
+
+void launch_undistort(const Pinhole& cam, const float2* uv, int n, float2* out, cudaStream_t s,
+                      int64_t* launches) {
+  if (n <= 0) return;
+  k_undistort<<<(n + 127) / 128, 128, 0, s>>>(cam, uv, n, out);
+  ++*launches;
+}
+
+}  // namespace esvio

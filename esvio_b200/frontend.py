@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference's front-end interface on top of the C ABI.
+
+`FeatureTracker` keeps the names of the reference class
+(/root/reference/feature_tracker/src/feature_tracker.h:44-135): `trackEvent(cur_time,
+event_left, event_right)` followed by the public result members the node reads
+(`ids, track_cnt, cur_pts, cur_un_pts, pts_velocity, ids_right, cur_right_pts,
+cur_un_right_pts, right_pts_velocity`; stereo_event_tracker_node.cpp:289-323).  All work
+happens in libesvio_fe.so on the GPU; this file only marshals numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import Config, Events, FrontEndError, Pinhole, Tracks
+
+AOS_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("sec", "<u4"), ("nsec", "<u4"), ("p", "u1"),
+                      ("pad", "V3")])
+
+
+def make_config(cfg: dict) -> Config:
+    """dict with the reference's parameter names -> esvio_fe_config."""
+    c = Config()
+    _capi.lib().esvio_fe_default_config(C.byref(c), int(cfg["width"]), int(cfg["height"]))
+    for k in ("max_cnt", "min_dist", "flow_back", "equalize", "ignore_polarity",
+              "median_blur_kernel_size", "do_motion_correction", "device_id",
+              "max_events_per_window", "use_ransac"):
+        if k in cfg:
+            setattr(c, k, int(cfg[k]))
+    for k in ("f_threshold", "ts_lk_threshold", "decay_ms", "feature_filter_threshold",
+              "focal_length"):
+        if k in cfg:
+            setattr(c, k, float(cfg[k]))
+    if "cam" in cfg:
+        for i in range(2):
+            cam = cfg["cam"][i]
+            c.cam[i] = Pinhole(*[float(cam[k]) for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")])
+    return c
+
+
+class _Ev:
+    """Keeps the numpy arrays alive next to the esvio_events struct that points into them."""
+
+    def __init__(self, ev):
+        self.s = Events()
+        self.keep = None
+        if ev is None:
+            return
+        if isinstance(ev, DeviceEvents):
+            self.s.x, self.s.y, self.s.t, self.s.p = ev.x, ev.y, ev.t, ev.p
+            self.s.aos = ev.aos
+            self.s.n = ev.n
+            self.s.on_device = 1
+            return
+        if isinstance(ev, np.ndarray) and ev.dtype == AOS_DTYPE:
+            a = np.ascontiguousarray(ev)
+            self.keep = (a,)
+            self.s.aos = a.ctypes.data
+            self.s.n = len(a)
+            return
+        x, y, t, p = ev[:4]
+        x = np.ascontiguousarray(x, np.uint16)
+        y = np.ascontiguousarray(y, np.uint16)
+        t = np.ascontiguousarray(t, np.float64)
+        p = np.ascontiguousarray(p, np.uint8)
+        self.keep = (x, y, t, p)
+        self.s.x, self.s.y, self.s.t, self.s.p = (a.ctypes.data for a in self.keep)
+        self.s.n = len(x)
+
+
+class DeviceEvents:
+    """One camera's events of one window, resident in HBM (esvio_events.on_device = 1)."""
+
+    def __init__(self, fe: "EventFrontEnd", ev):
+        self.fe = fe
+        self.x = self.y = self.t = self.p = self.aos = None
+        self._ptrs = []
+        if isinstance(ev, np.ndarray) and ev.dtype == AOS_DTYPE:
+            self.n = len(ev)
+            self.aos = self._up(np.ascontiguousarray(ev))
+        else:
+            x, y, t, p = ev[:4]
+            self.n = len(x)
+            self.x = self._up(np.ascontiguousarray(x, np.uint16))
+            self.y = self._up(np.ascontiguousarray(y, np.uint16))
+            self.t = self._up(np.ascontiguousarray(t, np.float64))
+            self.p = self._up(np.ascontiguousarray(p, np.uint8))
+
+    def _up(self, a):
+        ptr = C.c_void_p()
+        self.fe._chk(_capi.lib().esvio_fe_device_alloc(self.fe._h, max(a.nbytes, 1), C.byref(ptr)),
+                     "device_alloc")
+        if a.nbytes:
+            self.fe._chk(_capi.lib().esvio_fe_copy_to_device(self.fe._h, ptr, a.ctypes.data,
+                                                             a.nbytes), "copy_to_device")
+        self._ptrs.append(ptr)
+        return ptr.value
+
+    def free(self):
+        for p in self._ptrs:
+            _capi.lib().esvio_fe_device_free(self.fe._h, p)
+        self._ptrs = []
+
+
+class PinnedEvents:
+    """SoA event arrays in pinned host memory (esvio_fe_host_alloc) viewed as numpy."""
+
+    def __init__(self, ev):
+        x, y, t, p = ev[:4]
+        n = len(x)
+        self.n = n
+        L = _capi.lib()
+        self._raw = []
+
+        def pin(a, dt):
+            a = np.ascontiguousarray(a, dt)
+            ptr = L.esvio_fe_host_alloc(max(a.nbytes, 1))
+            if not ptr:
+                raise MemoryError("esvio_fe_host_alloc failed")
+            self._raw.append(ptr)
+            buf = (C.c_uint8 * max(a.nbytes, 1)).from_address(ptr)
+            v = np.frombuffer(buf, dtype=dt, count=n)
+            v[:] = a
+            return v
+
+        self.arrays = (pin(x, np.uint16), pin(y, np.uint16), pin(t, np.float64), pin(p, np.uint8))
+
+    def __getitem__(self, i):
+        return self.arrays[i]
+
+    def free(self):
+        for p in self._raw:
+            _capi.lib().esvio_fe_host_free(p)
+        self._raw = []
+
+
+class EventFrontEnd:
+    """Thin object wrapper around one `esvio_fe` handle (one stereo event stream)."""
+
+    def __init__(self, cfg: dict):
+        self.cfg = dict(cfg)
+        self._c = make_config(cfg)
+        self.W, self.H, self.M = self._c.width, self._c.height, self._c.max_cnt
+        h = C.c_void_p()
+        st = _capi.lib().esvio_fe_create(C.byref(self._c), C.byref(h))
+        if st != _capi.OK:
+            raise FrontEndError(st, "esvio_fe_create")
+        self._h = h
+        M = self.M
+        self._bufs = {k: np.zeros(M, np.int32) for k in ("id", "track_cnt", "id_right")}
+        self._bufs.update({k: np.zeros(M, np.float32) for k in
+                           ("u", "v", "un_x", "un_y", "vx", "vy", "ru", "rv", "run_x", "run_y",
+                            "rvx", "rvy")})
+        self._t = Tracks()
+        self._t.capacity = M
+        for k, a in self._bufs.items():
+            setattr(self._t, k, a.ctypes.data_as(_capi._pi if a.dtype == np.int32 else _capi._pf))
+        self._inflight = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _capi.lib().esvio_fe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, st, where):
+        if st != _capi.OK:
+            raise FrontEndError(st, where, _capi.lib().esvio_fe_last_error(self._h).decode())
+
+    # ---- hot path
+    def _unpack(self):
+        t, b = self._t, self._bufs
+        nl, nr = t.n_left, t.n_right
+        out = {k: b[k][:nl].copy() for k in ("id", "track_cnt", "u", "v", "un_x", "un_y", "vx", "vy")}
+        out.update({k: b[k][:nr].copy() for k in ("id_right", "ru", "rv", "run_x", "run_y", "rvx", "rvy")})
+        s = t.stats
+        out["stats"] = dict(n_prev=s.n_prev, n_after_temporal=s.n_after_temporal,
+                            n_after_ransac=s.n_after_ransac, n_after_mask=s.n_after_mask,
+                            n_new=s.n_new, ransac_iters=s.ransac_iters)
+        return out
+
+    def track(self, cur_time, left, right, pub_this_frame=True):
+        l, r = _Ev(left), _Ev(right)
+        self._chk(_capi.lib().esvio_fe_track(self._h, float(cur_time), C.byref(l.s), C.byref(r.s),
+                                             int(bool(pub_this_frame)), C.byref(self._t)), "track")
+        return self._unpack()
+
+    def track_raw(self, cur_time, l: _Ev, r: _Ev, pub_this_frame=True):
+        """Same call with pre-built esvio_events structs; returns (n_left, n_right)."""
+        self._chk(_capi.lib().esvio_fe_track(self._h, float(cur_time), C.byref(l.s), C.byref(r.s),
+                                             int(bool(pub_this_frame)), C.byref(self._t)), "track")
+        return self._t.n_left, self._t.n_right
+
+    def submit(self, cur_time, left, right, pub_this_frame=True):
+        l = left if isinstance(left, _Ev) else _Ev(left)
+        r = right if isinstance(right, _Ev) else _Ev(right)
+        self._inflight.append((l, r))
+        self._chk(_capi.lib().esvio_fe_track_submit(self._h, float(cur_time), C.byref(l.s),
+                                                    C.byref(r.s), int(bool(pub_this_frame))),
+                  "track_submit")
+
+    def wait(self, unpack=True):
+        self._chk(_capi.lib().esvio_fe_track_wait(self._h, C.byref(self._t)), "track_wait")
+        self._inflight.pop(0)
+        return self._unpack() if unpack else (self._t.n_left, self._t.n_right)
+
+    def reset(self):
+        self._chk(_capi.lib().esvio_fe_reset(self._h), "reset")
+
+    def time_surface(self, cam):
+        out = np.empty((self.H, self.W), np.uint8)
+        self._chk(_capi.lib().esvio_fe_time_surface(self._h, cam, out.ctypes.data, self.W),
+                  "time_surface")
+        return out
+
+    # ---- profiling / plumbing
+    def set_profiling(self, on=True):
+        self._chk(_capi.lib().esvio_fe_set_profiling(self._h, int(on)), "set_profiling")
+
+    def stage_ms(self):
+        ms = (C.c_float * _capi.NUM_STAGES)()
+        self._chk(_capi.lib().esvio_fe_get_stage_ms(self._h, ms), "get_stage_ms")
+        return dict(zip(_capi.STAGE_NAMES, list(ms)))
+
+    def kernel_launches(self):
+        n = C.c_int64()
+        self._chk(_capi.lib().esvio_fe_kernel_launches(self._h, C.byref(n)), "kernel_launches")
+        return n.value
+
+    def result_device_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._chk(_capi.lib().esvio_fe_result_device_ptr(self._h, C.byref(p), C.byref(n)),
+                  "result_device_ptr")
+        return p.value, n.value
+
+    def stream(self):
+        s = C.c_void_p()
+        self._chk(_capi.lib().esvio_fe_stream(self._h, C.byref(s)), "stream")
+        return s.value or 0
+
+    # ---- stage-level entry points (parity tests)
+    def sae_planes(self, cam):
+        """(sae[0], sae[1], latest[0], latest[1]) as HxW float64."""
+        out = []
+        for plane in range(4):
+            a = np.empty((self.H, self.W), np.float64)
+            self._chk(_capi.lib().esvio_fe_get_sae(self._h, cam, plane, a.ctypes.data), "get_sae")
+            out.append(a)
+        return out
+
+    def stage_update(self, t_ref, left, right):
+        l, r = _Ev(left), _Ev(right)
+        self._chk(_capi.lib().esvio_fe_stage_update(self._h, float(t_ref), C.byref(l.s),
+                                                    C.byref(r.s)), "stage_update")
+
+    def stage_corner_flags(self, left, and_ts_test=False):
+        l = _Ev(left)
+        out = np.zeros(max(l.s.n, 1), np.uint8)
+        self._chk(_capi.lib().esvio_fe_stage_corner_flags(self._h, C.byref(l.s), int(and_ts_test),
+                                                          out.ctypes.data), "stage_corner_flags")
+        return out[:l.s.n]
+
+    def pyramid_level(self, which, level):
+        w, h = C.c_int32(), C.c_int32()
+        self._chk(_capi.lib().esvio_fe_get_pyramid_level(self._h, which, level, None, C.byref(w),
+                                                         C.byref(h)), "get_pyramid_level")
+        out = np.empty((h.value, w.value), np.uint8)
+        self._chk(_capi.lib().esvio_fe_get_pyramid_level(self._h, which, level, out.ctypes.data,
+                                                         C.byref(w), C.byref(h)),
+                  "get_pyramid_level")
+        return out
+
+    def stage_lk(self, prev_img, next_img, prev_pts, next_pts=None, max_level=3):
+        a = np.ascontiguousarray(prev_img, np.uint8)
+        b = np.ascontiguousarray(next_img, np.uint8)
+        assert a.shape == (self.H, self.W) and b.shape == (self.H, self.W)
+        pp = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+        n = len(pp)
+        init = next_pts is not None
+        npts = (np.ascontiguousarray(next_pts, np.float32).reshape(-1, 2).copy() if init
+                else np.zeros((n, 2), np.float32))
+        st = np.zeros(max(n, 1), np.uint8)
+        self._chk(_capi.lib().esvio_fe_stage_lk(self._h, a.ctypes.data, b.ctypes.data,
+                                                pp.ctypes.data, npts.ctypes.data, n,
+                                                st.ctypes.data, max_level, int(init)), "stage_lk")
+        return npts, st[:n]
+
+    def stage_fmat_mask(self, p1, p2, thresh=1.0):
+        p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)
+        p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+        n = len(p1)
+        mask = np.zeros(max(n, 1), np.uint8)
+        it = C.c_int32()
+        self._chk(_capi.lib().esvio_fe_stage_fmat_mask(self._h, p1.ctypes.data, p2.ctypes.data, n,
+                                                       float(thresh), mask.ctypes.data,
+                                                       C.byref(it)), "stage_fmat_mask")
+        return mask[:n], it.value
+
+    def stage_select(self, left, pts, ids, track_cnt):
+        l = _Ev(left)
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        ids = np.ascontiguousarray(ids, np.int32)
+        cnt = np.ascontiguousarray(track_cnt, np.int32)
+        n = len(ids)
+        M = self.M
+        po, io, co = np.zeros((M, 2), np.float32), np.zeros(M, np.int32), np.zeros(M, np.int32)
+        n_out, n_kept = C.c_int32(), C.c_int32()
+        self._chk(_capi.lib().esvio_fe_stage_select(
+            self._h, C.byref(l.s), n, pts.ctypes.data, ids.ctypes.data, cnt.ctypes.data,
+            C.byref(n_out), po.ctypes.data, io.ctypes.data, co.ctypes.data, C.byref(n_kept)),
+            "stage_select")
+        k = n_out.value
+        return po[:k], io[:k], co[:k], n_kept.value
+
+    def stage_undistort(self, cam, uv):
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros_like(uv)
+        self._chk(_capi.lib().esvio_fe_stage_undistort(self._h, cam, uv.ctypes.data, len(uv),
+                                                       out.ctypes.data), "stage_undistort")
+        return out
+
+
+class FeatureTracker:
+    """Drop-in mirror of the reference's `FeatureTracker` for the event path
+    (feature_tracker.h:44-135).  `PUB_THIS_FRAME` is the reference's global of the same name
+    (parameters.h; set by the node at stereo_event_tracker_node.cpp:179,188)."""
+
+    def __init__(self, cfg: dict):
+        self.fe = EventFrontEnd(cfg)
+        self.PUB_THIS_FRAME = True
+        self.cur_time = 0.0
+        self.prev_time = 0.0
+        self.ids = np.zeros(0, np.int32)
+        self.track_cnt = np.zeros(0, np.int32)
+        self.cur_pts = np.zeros((0, 2), np.float32)
+        self.cur_un_pts = np.zeros((0, 2), np.float32)
+        self.pts_velocity = np.zeros((0, 2), np.float32)
+        self.ids_right = np.zeros(0, np.int32)
+        self.cur_right_pts = np.zeros((0, 2), np.float32)
+        self.cur_un_right_pts = np.zeros((0, 2), np.float32)
+        self.right_pts_velocity = np.zeros((0, 2), np.float32)
+        self.stats = {}
+
+    def trackEvent(self, _cur_time, event_left, event_right):
+        r = self.fe.track(_cur_time, event_left, event_right, self.PUB_THIS_FRAME)
+        self.prev_time, self.cur_time = self.cur_time, float(_cur_time)
+        self.ids, self.track_cnt = r["id"], r["track_cnt"]
+        self.cur_pts = np.stack([r["u"], r["v"]], 1)
+        self.cur_un_pts = np.stack([r["un_x"], r["un_y"]], 1)
+        self.pts_velocity = np.stack([r["vx"], r["vy"]], 1)
+        self.ids_right = r["id_right"]
+        self.cur_right_pts = np.stack([r["ru"], r["rv"]], 1)
+        self.cur_un_right_pts = np.stack([r["run_x"], r["run_y"]], 1)
+        self.right_pts_velocity = np.stack([r["rvx"], r["rvy"]], 1)
+        self.stats = r["stats"]
+
+    def gettimesurface(self):
+        """feature_tracker.cpp:894-897"""
+        return self.fe.time_surface(0)
+
+    def feature_point_cloud(self):
+        """Rows of the `feature` sensor_msgs/PointCloud exactly as the node packs them
+        (stereo_event_tracker_node.cpp:268-329): (x, y, z=1, id*2+cam, u, v, vx, vy), left rows
+        with track_cnt > 1 first, then right rows whose id was published on the left."""
+        rows = []
+        pub = set()
+        for j in range(len(self.ids)):
+            if self.track_cnt[j] > 1:
+                pid = int(self.ids[j])
+                pub.add(pid)
+                rows.append((self.cur_un_pts[j, 0], self.cur_un_pts[j, 1], 1.0, pid * 2 + 0,
+                             self.cur_pts[j, 0], self.cur_pts[j, 1], self.pts_velocity[j, 0],
+                             self.pts_velocity[j, 1]))
+        for j in range(len(self.ids_right)):
+            pid = int(self.ids_right[j])
+            if pid in pub:
+                rows.append((self.cur_un_right_pts[j, 0], self.cur_un_right_pts[j, 1], 1.0,
+                             pid * 2 + 1, self.cur_right_pts[j, 0], self.cur_right_pts[j, 1],
+                             self.right_pts_velocity[j, 0], self.right_pts_velocity[j, 1]))
+        return np.asarray(rows, np.float32).reshape(-1, 8)

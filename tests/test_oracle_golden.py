@@ -1,0 +1,93 @@
+"""CPU suite: the oracle's restatement of the OpenCV stages against REAL OpenCV outputs
+(tests/golden/*.npz, produced by tests/golden/make_golden.py with cv2 4.13.0)."""
+import numpy as np
+import pytest
+
+LK_TOL = 1e-3      # px, SURVEY.md section 8c proposed tolerance vs cv2 on identical inputs
+LK_TOL_MAX = 2e-2  # a termination test (|delta|^2 <= 1e-4) may flip on float noise
+
+
+def _cmp_lk(got, st, ref, st_ref, what):
+    st = st.astype(bool)
+    st_ref = st_ref.astype(bool)
+    both = st & st_ref
+    # status may differ only where minEig / the window test sits on its threshold
+    assert (st != st_ref).sum() <= max(1, len(st) // 50), f"{what}: status differs {(st != st_ref).sum()}"
+    d = np.abs(got[both] - ref[both]).max(axis=1)
+    assert (d > LK_TOL).sum() <= max(1, both.sum() // 50), f"{what}: {np.sort(d)[-5:]}"
+    assert d.max() <= LK_TOL_MAX, f"{what}: max {d.max()}"
+
+
+@pytest.mark.parametrize("case", ["noise", "ts", "stereo"])
+def test_lk_matches_cv2(ora, golden_lk, case):
+    g = golden_lk
+    a, b, pts = g[f"{case}_a"], g[f"{case}_b"], g[f"{case}_pts"]
+    fwd, st = ora.calc_optical_flow_pyr_lk(a, b, pts, None, max_level=3)
+    _cmp_lk(fwd, st, g[f"{case}_fwd"], g[f"{case}_st_f"], case + " fwd")
+    # the backward calls start from cv2's forward result so that stages stay isolated
+    rev, st_r = ora.calc_optical_flow_pyr_lk(b, a, g[f"{case}_fwd"], pts.copy(), max_level=1)
+    _cmp_lk(rev, st_r, g[f"{case}_rev"], g[f"{case}_st_r"], case + " rev(init flow)")
+    back, st_b = ora.calc_optical_flow_pyr_lk(b, a, g[f"{case}_fwd"], None, max_level=3)
+    _cmp_lk(back, st_b, g[f"{case}_back"], g[f"{case}_st_b"], case + " back")
+
+
+@pytest.mark.parametrize("name", ["noise", "ts", "vga"])
+def test_pyramid_bit_exact(ora, golden_lk, name):
+    g = golden_lk
+    img = g[f"pyr_{name}_img"]
+    n = int(g[f"pyr_{name}_n"])
+    sizes = ora.pyramid_sizes(img.shape[1], img.shape[0], 3, 21)
+    assert len(sizes) == n
+    levels = ora.build_pyramid(img, 3, 21)
+    for l in range(n):
+        ref = g[f"pyr_{name}_l{l}"]
+        assert levels[l].shape == ref.shape == (sizes[l][1], sizes[l][0])
+        assert np.array_equal(levels[l], ref), f"level {l}"
+
+
+def test_fundamental_mask_matches_cv2(ora, golden_fmat):
+    g = golden_fmat
+    exact = 0
+    for i in g["fm_cases"]:
+        p1, p2, ref = g[f"fm{i}_p1"], g[f"fm{i}_p2"], g[f"fm{i}_mask"]
+        ok, mask = ora.find_fundamental_mask(p1, p2, 1.0, 0.99, 1000)
+        assert ok == bool(g[f"fm{i}_ok"])
+        if len(ref) <= 13:
+            # LMedS with n <= 13: element n/2 of the sorted residuals belongs to one of the 7
+            # sample points, i.e. it is rounding noise (~1e-25); OpenCV keeps exactly the 7
+            # points of whichever sample had the smallest noise.  Only the cardinality is a
+            # reproducible property of the reference here ("F-RANSAC parity").
+            assert mask.sum() == ref.sum() == 7
+            exact += 1
+            continue
+        inter = (mask & ref).sum()
+        union = (mask | ref).sum()
+        jac = inter / union if union else 1.0
+        exact += int(np.array_equal(mask, ref))
+        assert jac >= 0.95, f"case {i} (n={len(ref)}): jaccard {jac:.3f}"
+    # the RNG stream, subset rules and update rules are replicated, so nearly all masks
+    # are identical; a threshold-edge inlier may flip with the null-space solver
+    assert exact >= len(g["fm_cases"]) - 2, exact
+
+
+def test_convert_to_u8(ora, golden_misc):
+    """convertTo(CV_8U) of 255*(m+1)/2 rounds half to even; an empty pixel is 128."""
+    m, ref = golden_misc["cvt_in"], golden_misc["cvt_out"]
+    got = np.clip(np.rint(m * 127.5 + 127.5), 0, 255).astype(np.uint8)
+    assert np.array_equal(got, ref)
+    assert ref[0] == 128
+    # the oracle's time-surface conversion on a pixel that never fired
+    s = ora.Sae(8, 8)
+    assert (s.time_surface(1.0) == 128).all()
+
+
+def test_disc_raster(ora, golden_misc):
+    g = golden_misc
+    for r in list(range(1, 41)) + [64]:
+        assert np.array_equal(ora.disc_half_widths(r), g[f"disc_hw_{r}"]), r
+    hw10 = ora.disc_half_widths(10)
+    assert hw10.tolist() == [10, 10, 10, 10, 9, 9, 8, 7, 6, 4, 0] or int((2 * hw10 + 1).sum() * 2 - (2 * hw10[0] + 1)) == 317
+    m = np.zeros((40, 50), np.uint8)
+    ora.fill_disc(m, 3, 36, 10)
+    ora.fill_disc(m, 48, 2, 10)
+    assert np.array_equal((m == 255).astype(np.uint8), g["disc_clip"])
