@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- Mevents/s through the event front-end (SAE + time surface + Arc* + temporal and
+stereo LK) on synthetic stereo event streams (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (libesvio_fe.so)
+  python bench.py --impl reference --gpus N --steps K ...  the CPU path on the host cores
+
+A "step" is one window (1/30 s of stream time) of one stereo pair: both cameras' events go
+through createSAE/time surface, the left camera through corner detection, then temporal and
+stereo LK (FeatureTracker::trackEvent, feature_tracker/src/feature_tracker.cpp:340-603).
+N > 1: every rank runs its own independent stereo stream (weak scaling, SURVEY.md 8e
+"independent streams") and the ranks all-gather their packed track records once per window
+over NCCL.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from esvio_b200 import synth  # noqa: E402
+
+METRIC = "Mevents/s through time-surface+stereo LK"
+UNIT = "Mevents/s"
+DEFAULT_WORKLOAD = "stereo_davis346_1mevs"  # BASELINE.json configs[1]
+L2_BYTES = 126 * 1024 * 1024
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def workload_cfg(name):
+    w = synth.WORKLOADS[name]
+    cfg = synth.default_config(w["width"], w["height"], max_cnt=w["max_cnt"],
+                               min_dist=w["min_dist"], use_ransac=1)
+    pub_div = int(round(synth.WINDOWS_PER_SEC / w["freq"]))  # freq 15 -> every 2nd window
+    return w, cfg, pub_div
+
+
+def gen_windows(w, stream, n):
+    s = synth.StereoEventStream(w["width"], w["height"], w["rate"], stream=stream, mono=w["mono"])
+    return [s.stereo_window(k) for k in range(n)]
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference C++ with real OpenCV (cv2) for LK/RANSAC
+# ------------------------------------------------------------------------------------------
+def cpu_tracker(cfg, threads):
+    from oracle import oracle as ora  # the only place bench.py touches oracle/: the CPU legs
+    ora.build()
+    use_cv2 = ora.have_cv2()
+    t = ora.OracleTracker(cfg, use_cv2=use_cv2, cv2_threads=threads)
+    kind = "port"
+    desc = ("oracle/ C restatement of event_detector.cc + feature_tracker.cpp, "
+            + ("OpenCV %s calcOpticalFlowPyrLK/findFundamentalMat via cv2" % __import__("cv2").__version__
+               if use_cv2 else "C port of OpenCV LK/RANSAC"))
+    return t, kind, desc
+
+
+def run_cpu(cfg, pub_div, wins, warmup, threads):
+    t, kind, desc = cpu_tracker(cfg, threads)
+    outs = []
+    n_ev = 0
+    t_total = 0.0
+    for k, (L, R, tc) in enumerate(wins):
+        t0 = time.perf_counter()
+        o = t.track(tc, L, R, k % pub_div == 0)
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            t_total += dt
+            n_ev += len(L[0]) + len(R[0])
+        outs.append(o)
+    return n_ev, t_total, outs, kind, desc, t.timers()
+
+
+def main_reference(args):
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    if rank != 0:
+        return
+    w, cfg, pub_div = workload_cfg(args.workload)
+    cores = os.cpu_count() or 1
+    wins = gen_windows(w, 0, args.steps + args.warmup)
+    n_ev, sec, _, kind, desc, timers = run_cpu(cfg, pub_div, wins, args.warmup, cores)
+    val = n_ev / sec / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "width": w["width"], "height": w["height"],
+                   "events_per_window_per_camera": int(round(w["rate"] / synth.WINDOWS_PER_SEC)),
+                   "max_cnt": w["max_cnt"], "min_dist": w["min_dist"], "pub_every": pub_div},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} windows of {args.workload} after {args.warmup} "
+                                   f"warm-up; {desc}; cv2 threads = {cores}; the reference's own "
+                                   "node cannot be built here (needs ROS/OpenCV C++/Eigen)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage_seconds": timers,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+class _CudaArray:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4",
+                                         "data": (ptr, False), "version": 3, "strides": None}
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    from esvio_b200 import frontend
+
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the front-end has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    w, cfg, pub_div = workload_cfg(args.workload)
+    n_per_cam = int(round(w["rate"] / synth.WINDOWS_PER_SEC))
+    cfg = dict(cfg, device_id=local, max_events_per_window=max(n_per_cam + 64, 1024))
+    K, Wm = args.steps, args.warmup
+    wins = gen_windows(w, rank, K + Wm)
+    ev_per_step = sum(len(L[0]) + len(R[0]) for L, R, _ in wins[Wm:]) / max(K, 1)
+
+    # ---------------- device-resident leg: `value` ----------------
+    fe = frontend.EventFrontEnd(cfg)
+    ext = torch.cuda.ExternalStream(fe.stream(), device=dev)
+    dwins = [(frontend._Ev(frontend.DeviceEvents(fe, L)), frontend._Ev(frontend.DeviceEvents(fe, R)), t)
+             for L, R, t in wins]
+    rptr, rbytes = fe.result_device_ptr()
+    res_t = torch.as_tensor(_CudaArray(rptr, rbytes), device=dev)
+    gathered = torch.empty((world, res_t.numel()), dtype=torch.int32, device=dev) if world > 1 else None
+    input_bytes = 13 * ev_per_step * K
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_submit(k):
+        l, r, t = dwins[k]
+        fe.submit(t, l, r, k % pub_div == 0)
+        if world > 1:
+            with torch.cuda.stream(ext):
+                dist.all_gather_into_tensor(gathered, res_t)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(Wm):
+        step_submit(k)
+        fe.wait(unpack=False)
+    flush.fill_(1)  # evict the uploaded windows: every timed step streams its events from HBM
+    fe.set_profiling(True)
+    stage_sum = np.zeros(len(frontend._capi.STAGE_NAMES))
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    launches0 = fe.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    step_submit(Wm)
+    for k in range(Wm + 1, Wm + K):
+        step_submit(k)
+        fe.wait(unpack=False)
+        stage_sum += np.fromiter(fe.stage_ms().values(), float)
+    n_left_last, n_right_last = fe.wait(unpack=False)
+    stage_sum += np.fromiter(fe.stage_ms().values(), float)
+    e1.record(ext)
+    barrier()
+    launches = fe.kernel_launches() - launches0
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    fe.set_profiling(False)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([ev_per_step * K, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms_max = float(t_ms.item())
+    value = float(tot[0].item()) / (ms_max * 1e-3) / 1e6
+    gpu_launches = int(tot[1].item())
+    fe.close()
+
+    # ---------------- end-to-end leg: host buffers through the synchronous C-ABI call ----------
+    fe2 = frontend.EventFrontEnd(cfg)
+    ext2 = torch.cuda.ExternalStream(fe2.stream(), device=dev)
+    pwins = [(frontend._Ev(frontend.PinnedEvents(L)), frontend._Ev(frontend.PinnedEvents(R)), t)
+             for L, R, t in wins]
+    for k in range(Wm):
+        l, r, t = pwins[k]
+        fe2.track_raw(t, l, r, k % pub_div == 0)
+    flush.fill_(2)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(ext2)
+    checksum = 0
+    for k in range(Wm, Wm + K):
+        l, r, t = pwins[k]
+        nl, nr = fe2.track_raw(t, l, r, k % pub_div == 0)   # H2D + kernels + D2H + sync
+        checksum += nl + nr
+        if world > 1:
+            with torch.cuda.stream(ext2):
+                dist.all_gather_into_tensor(gathered, torch.as_tensor(
+                    _CudaArray(*fe2.result_device_ptr()), device=dev))
+    g1.record(ext2)
+    barrier()
+    e2e_ms = g0.elapsed_time(g1)
+    e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = float(tot[0].item()) / (float(e2e_t.item()) * 1e-3) / 1e6
+    h2d = int(round(13 * ev_per_step))
+    d2h = int(rbytes)
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) + parity of the first windows ---------
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_s = min(len(wins), args.cpu_windows)
+        n_ev, sec, outs, kind, desc, _ = run_cpu(workload_cfg(args.workload)[1], pub_div,
+                                                 wins[:n_s], min(Wm, 3), 1)
+        cpu = {"value": n_ev / sec / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"first {n_s} windows of {args.workload} ({n_ev} events timed), single "
+                         f"thread like the reference's worker (stereo_event_tracker_node.cpp:366); {desc}"}
+        fe3 = frontend.EventFrontEnd(cfg)
+        sq, cnt, mx, hor = 0.0, 0, 0.0, 0
+        for k in range(min(n_s, 8)):
+            L, R, t = wins[k]
+            g = fe3.track(t, L, R, k % pub_div == 0)
+            o = outs[k]
+            if not (np.array_equal(g["id"], o["id"]) and np.array_equal(g["id_right"], o["id_right"])):
+                break
+            hor = k + 1
+            for a, b in ((g["u"], o["u"]), (g["v"], o["v"]), (g["ru"], o["ru"]), (g["rv"], o["rv"])):
+                if len(a):
+                    d = np.abs(a - b)
+                    sq += float((d ** 2).sum())
+                    cnt += len(d)
+                    mx = max(mx, float(d.max()))
+        parity = {"tracked_px_rmse_vs_ref": (sq / max(cnt, 1)) ** 0.5, "max_px": mx,
+                  "windows_with_identical_ids": hor, "coords_compared": cnt,
+                  "ref": "oracle with OpenCV LK" if "cv2" in desc else "oracle C LK"}
+        fe3.close()
+    fe2.close()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        W_, H_ = w["width"], w["height"]
+        names = frontend._capi.STAGE_NAMES
+        stage_ms = dict(zip(names, (stage_sum / max(K, 1)).tolist()))
+        k1_ms = stage_ms["sae_update_ts"]
+        alg_bytes = 2 * 17 * W_ * H_ + 45 * ev_per_step   # 17*W*H per camera + 45 B/event
+        achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
+        gpu_ms = sum(v for k_, v in stage_ms.items() if k_ not in ("h2d", "d2h"))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms_max / max(K, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "width": W_, "height": H_,
+                       "events_per_window_per_camera": n_per_cam, "max_cnt": w["max_cnt"],
+                       "min_dist": w["min_dist"], "pub_every": pub_div,
+                       "streams_per_gpu": 1, "parallelism": f"{world} independent stereo streams"
+                       + (", NCCL all-gather of track records per window" if world > 1 else ""),
+                       "l2": "each window's events are read once from HBM: all windows are "
+                             "uploaded, then L2 is flushed with a 512 MiB write before the timed "
+                             "region; the SAE state (the path's persistent working set) stays "
+                             "resident by design",
+                       "timed_input_bytes": int(input_bytes)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": float(e2e_t.item()) / max(K, 1),
+                    "api": "esvio_fe_track (synchronous, pinned host SoA buffers)"},
+            "gpu_launches": gpu_launches,
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "k_sae_update_ts", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "kernel_ms": k1_ms, "share_of_step": k1_ms / gpu_ms if gpu_ms else None,
+                         "peak_source": peak_src,
+                         "note": "state (SAE) is L2-resident; one launch covers both cameras of "
+                                 "one window; LK stages are latency-bound and reported by time"},
+            "stage_ms": stage_ms,
+            "tracks_last_window": {"left": int(n_left_last), "right": int(n_right_last)},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity"] = parity
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--cpu-windows", type=int, default=150)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,8 +15,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libesvio_fe.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "esvio_fe.h")
 
-NUM_STAGES = 8
-STAGE_NAMES = ("h2d", "sae_ts", "pyramid", "corner_flags", "lk_temporal", "select", "lk_stereo",
+NUM_STAGES = 9
+STAGE_NAMES = ("h2d", "bin_events", "sae_update_ts", "pyramid", "corner_flags", "lk_temporal", "select", "lk_stereo",
                "d2h")
 
 OK, EINVAL, ENODEV, ECUDA, ECAPACITY, ESTATE = range(6)

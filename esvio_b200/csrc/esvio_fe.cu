@@ -51,8 +51,10 @@ struct esvio_fe {
   int q_head, q_count;  // in-flight windows (results land in h_result[(q_head + k) & 1])
   cudaEvent_t q_done[2];
   int profiling;
-  cudaEvent_t pev[ESVIO_FE_NUM_STAGES + 1];
-  int pev_valid;
+  cudaEvent_t pev[2][ESVIO_FE_NUM_STAGES + 1];  // one set per in-flight slot
+  int pev_slot;
+  int pev_valid[2];
+  int stage_ms_valid;
   float stage_ms[ESVIO_FE_NUM_STAGES];
 };
 
@@ -182,8 +184,9 @@ static void free_all(esvio_fe* fe) {
   cudaFree(fe->d_scratch_n);
   cudaFree(fe->d_scratch_p0);
   cudaFree(fe->d_scratch_st);
-  for (int i = 0; i <= ESVIO_FE_NUM_STAGES; ++i)
-    if (fe->pev[i]) cudaEventDestroy(fe->pev[i]);
+  for (int k = 0; k < 2; ++k)
+    for (int i = 0; i <= ESVIO_FE_NUM_STAGES; ++i)
+      if (fe->pev[k][i]) cudaEventDestroy(fe->pev[k][i]);
   if (fe->stream) cudaStreamDestroy(fe->stream);
   free(fe);
 }
@@ -200,7 +203,8 @@ static int reset_state(esvio_fe* fe) {
   fe->windows = 0;
   fe->prev_time = 0.0;
   fe->q_head = fe->q_count = 0;
-  fe->pev_valid = 0;
+  fe->pev_valid[0] = fe->pev_valid[1] = 0;
+  fe->stage_ms_valid = 0;
   return ESVIO_FE_OK;
 }
 
@@ -310,7 +314,8 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   CUC(cudaMalloc(&fe->d_scratch_p0, sizeof(float2) * 2 * (size_t)kMaxCnt));
   fe->d_scratch_p1 = fe->d_scratch_p0 + kMaxCnt;
   CUC(cudaMalloc(&fe->d_scratch_st, kMaxCnt));
-  for (int i = 0; i <= ESVIO_FE_NUM_STAGES; ++i) CUC(cudaEventCreate(&fe->pev[i]));
+  for (int k = 0; k < 2; ++k)
+    for (int i = 0; i <= ESVIO_FE_NUM_STAGES; ++i) CUC(cudaEventCreate(&fe->pev[k][i]));
 #undef CUC
 
   TrackParams& P = fe->tp;
@@ -389,13 +394,14 @@ static int stage_events(esvio_fe* fe, int cam, const esvio_events* e, DevEvents*
 }
 
 static void prof_mark(esvio_fe* fe, int i) {
-  if (fe->profiling) cudaEventRecord(fe->pev[i], fe->stream);
+  if (fe->profiling) cudaEventRecord(fe->pev[fe->pev_slot][i], fe->stream);
 }
 
 // createSAE_* + SAEtoTimeSurface_* + pyramids (feature_tracker.cpp:356-368) into the
 // pyramid buffers `left_idx` / right
 static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev[2], int left_idx) {
   launch_bin_events(fe->bl, fe->esb, ev, fe->stream, &fe->launches);
+  prof_mark(fe, 2);
   SaeTsParams sp;
   sp.W = fe->W;
   sp.H = fe->H;
@@ -414,7 +420,7 @@ static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev[2], in
   sp.ts[1] = fe->pyr[2];
   sp.ts_pitch = fe->pd.pitch[0];
   launch_sae_update_ts(sp, fe->map_sae, fe->map_lat, fe->stream, &fe->launches);
-  prof_mark(fe, 2);
+  prof_mark(fe, 3);
   uint8_t* imgs[2] = {fe->pyr[left_idx], fe->pyr[2]};
   launch_pyramids(fe->pd, imgs, 2, fe->stream, &fe->launches);
   CU(cudaGetLastError());
@@ -442,6 +448,8 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   if (fe->q_count >= 2) return fail(fe, ESVIO_FE_ESTATE, "two windows already in flight", cudaSuccess);
   CU(cudaSetDevice(fe->dev));
   cudaStream_t s = fe->stream;
+  const int slot = (fe->q_head + fe->q_count) & 1;
+  fe->pev_slot = slot;
   prof_mark(fe, 0);
   DevEvents ev[2];
   int rc;
@@ -452,11 +460,11 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   const int cur = fe->windows == 0 ? 0 : 1 - fe->cur_left;
   const int prev = fe->windows == 0 ? 0 : fe->cur_left;  // first window: prev_img = cur_img
   if ((rc = run_event_stage(fe, cur_time, ev, cur)) != ESVIO_FE_OK) return rc;
-  prof_mark(fe, 3);
+  prof_mark(fe, 4);
   if (pub_this_frame) {
     launch_corner_flags(corner_params(fe, cur, 1), ev[0], fe->flags, s, &fe->launches);
   }
-  prof_mark(fe, 4);
+  prof_mark(fe, 5);
 
   const TrackBuffers& B = fe->tb;
   const int M = fe->cfg.max_cnt;
@@ -469,12 +477,12 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
               M, 1, 1, s, &fe->launches);
   }
   launch_post_temporal(fe->tp, B, s, &fe->launches);
-  prof_mark(fe, 5);
+  prof_mark(fe, 6);
   if (pub_this_frame) {
     if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s, &fe->launches);
     launch_select(fe->tp, B, ev[0], fe->flags, s, &fe->launches);
   }
-  prof_mark(fe, 6);
+  prof_mark(fe, 7);
   // stereo LK (feature_tracker.cpp:475-510)
   launch_lk(fe->pd, fe->pyr[cur], fe->pyr[2], B.cur_pts, B.right_pts, B.st_sf, &B.st->n_cur, M, 3,
             0, s, &fe->launches);
@@ -482,18 +490,16 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
     launch_lk(fe->pd, fe->pyr[2], fe->pyr[cur], B.right_pts, B.rev_left_pts, B.st_sb,
               &B.st->n_cur, M, 3, 0, s, &fe->launches);
   launch_finalize(fe->tp, B, cur_time, fe->prev_time, s, &fe->launches);
-  prof_mark(fe, 7);
-  const int slot = (fe->q_head + fe->q_count) & 1;
-  CU(cudaMemcpyAsync(fe->h_result[slot], B.result, fe->result_words * 4, cudaMemcpyDeviceToHost, s));
   prof_mark(fe, 8);
+  CU(cudaMemcpyAsync(fe->h_result[slot], B.result, fe->result_words * 4, cudaMemcpyDeviceToHost, s));
+  prof_mark(fe, 9);
   CU(cudaEventRecord(fe->q_done[slot], s));
   CU(cudaGetLastError());
   fe->q_count++;
   fe->cur_left = cur;
   fe->windows++;
   fe->prev_time = cur_time;
-  fe->pev_valid = fe->profiling;
-  (void)left;
+  fe->pev_valid[slot] = fe->profiling;
   return ESVIO_FE_OK;
 }
 
@@ -528,9 +534,11 @@ FE_API int esvio_fe_track_wait(esvio_fe* fe, esvio_tracks* out) {
   s.n_new = r[6];
   s.n_corner_flags = r[7];
   s.ransac_iters = r[8];
-  if (fe->pev_valid && fe->q_count == 0) {
+  if (fe->pev_valid[slot]) {
     for (int i = 0; i < ESVIO_FE_NUM_STAGES; ++i)
-      cudaEventElapsedTime(&fe->stage_ms[i], fe->pev[i], fe->pev[i + 1]);
+      cudaEventElapsedTime(&fe->stage_ms[i], fe->pev[slot][i], fe->pev[slot][i + 1]);
+    fe->stage_ms_valid = 1;
+    fe->pev_valid[slot] = 0;
   }
   return ESVIO_FE_OK;
 }
@@ -601,12 +609,12 @@ FE_API int esvio_fe_stream(esvio_fe* fe, void** cuda_stream) {
 FE_API int esvio_fe_set_profiling(esvio_fe* fe, int32_t on) {
   if (!fe) return ESVIO_FE_EINVAL;
   fe->profiling = on != 0;
-  fe->pev_valid = 0;
+  fe->stage_ms_valid = 0;
   return ESVIO_FE_OK;
 }
 FE_API int esvio_fe_get_stage_ms(esvio_fe* fe, float* ms) {
   if (!fe || !ms) return ESVIO_FE_EINVAL;
-  if (!fe->pev_valid) return fail(fe, ESVIO_FE_ESTATE, "no profiled window", cudaSuccess);
+  if (!fe->stage_ms_valid) return fail(fe, ESVIO_FE_ESTATE, "no profiled window", cudaSuccess);
   memcpy(ms, fe->stage_ms, sizeof(fe->stage_ms));
   return ESVIO_FE_OK;
 }
