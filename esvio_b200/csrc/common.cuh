@@ -206,9 +206,13 @@ void launch_pyramids(const PyrDesc& pd, uint8_t* const pyr[2], int n_img, cudaSt
 
 // cv::calcOpticalFlowPyrLK(I, J, prev, next, status, err, Size(21,21), max_level[, 30/0.01,
 // USE_INITIAL_FLOW]); n is read on the device.
+// mode 0: that call alone.  mode 1: followed, per point and in the same launch, by the
+// temporal backward check (J->I, maxLevel 1, initial flow = prev).  mode 2: followed by the
+// stereo backward check (J->I, same maxLevel, no initial flow).
 void launch_lk(const PyrDesc& pd, const uint8_t* I, const uint8_t* J, const float2* prev_pts,
-               float2* next_pts, uint8_t* status, const int* n_ptr, int n_max, int max_level,
-               int use_initial_flow, cudaStream_t s, int64_t* launches);
+               float2* next_pts, uint8_t* status, float2* rev_pts, uint8_t* rev_status,
+               const int* n_ptr, int n_max, int max_level, int use_initial_flow, int mode,
+               cudaStream_t s, int64_t* launches);
 
 struct TrackBuffers {
   TrackState* st;
@@ -220,6 +224,8 @@ struct TrackBuffers {
   int* prev_un_r_ids;
   float2* prev_un_r;
   int32_t* result;  // kResultHdr ints + kResultArrays * max_cnt words
+  void* rs;                   // RansacScratch (ransac.cu)
+  const uint32_t* rng_draws;  // first ransac_num_draws() raw outputs of cv::RNG(-1)
 };
 
 struct TrackParams {
@@ -237,8 +243,12 @@ void launch_finalize(const TrackParams& P, const TrackBuffers& B, double cur_tim
 void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
                    int64_t* launches);
 // stage entry: F-RANSAC mask on caller points (device pointers)
-void launch_ransac_stage(const float2* p1, const float2* p2, int n, double thresh, uint8_t* mask,
-                         int* iters, cudaStream_t s, int64_t* launches);
+void launch_ransac_stage(const TrackParams& P, const TrackBuffers& B, const float2* p1,
+                         const float2* p2, int n, double thresh, uint8_t* mask, int* iters,
+                         cudaStream_t s, int64_t* launches);
+size_t ransac_scratch_bytes();
+int ransac_num_draws();
+void ransac_fill_draw_table(uint32_t* host_table);
 void launch_undistort(const Pinhole& cam, const float2* uv, int n, float2* out, cudaStream_t s,
                       int64_t* launches);
 

@@ -181,6 +181,8 @@ static void free_all(esvio_fe* fe) {
   cudaFree(fe->tb.ids);
   cudaFree(fe->tb.st_fwd);
   cudaFree(fe->tb.result);
+  cudaFree(fe->tb.rs);
+  cudaFree((void*)fe->tb.rng_draws);
   cudaFree(fe->d_scratch_n);
   cudaFree(fe->d_scratch_p0);
   cudaFree(fe->d_scratch_st);
@@ -309,6 +311,19 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   for (int i = 0; i < 2; ++i) {
     CUC(cudaHostAlloc(&fe->h_result[i], fe->result_words * 4, cudaHostAllocDefault));
     CUC(cudaEventCreateWithFlags(&fe->q_done[i], cudaEventDisableTiming));
+  }
+  CUC(cudaMalloc(&B.rs, ransac_scratch_bytes()));
+  CUC(cudaMemset(B.rs, 0, ransac_scratch_bytes()));
+  {
+    const int nd = ransac_num_draws();
+    uint32_t* tab = (uint32_t*)malloc(sizeof(uint32_t) * nd);
+    ransac_fill_draw_table(tab);
+    uint32_t* dtab = nullptr;
+    cudaError_t ce = cudaMalloc(&dtab, sizeof(uint32_t) * nd);
+    if (ce == cudaSuccess) ce = cudaMemcpy(dtab, tab, sizeof(uint32_t) * nd, cudaMemcpyHostToDevice);
+    free(tab);
+    B.rng_draws = dtab;
+    CUC(ce);
   }
   CUC(cudaMalloc(&fe->d_scratch_n, 64));
   CUC(cudaMalloc(&fe->d_scratch_p0, sizeof(float2) * 2 * (size_t)kMaxCnt));
@@ -469,13 +484,8 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   const TrackBuffers& B = fe->tb;
   const int M = fe->cfg.max_cnt;
   // temporal LK (feature_tracker.cpp:405-437)
-  launch_lk(fe->pd, fe->pyr[prev], fe->pyr[cur], B.prev_pts, B.cur_pts, B.st_fwd, &B.st->n_prev, M,
-            3, 0, s, &fe->launches);
-  if (fe->cfg.flow_back) {
-    CU(cudaMemcpyAsync(B.rev_pts, B.prev_pts, sizeof(float2) * M, cudaMemcpyDeviceToDevice, s));
-    launch_lk(fe->pd, fe->pyr[cur], fe->pyr[prev], B.cur_pts, B.rev_pts, B.st_bwd, &B.st->n_prev,
-              M, 1, 1, s, &fe->launches);
-  }
+  launch_lk(fe->pd, fe->pyr[prev], fe->pyr[cur], B.prev_pts, B.cur_pts, B.st_fwd, B.rev_pts,
+            B.st_bwd, &B.st->n_prev, M, 3, 0, fe->cfg.flow_back ? 1 : 0, s, &fe->launches);
   launch_post_temporal(fe->tp, B, s, &fe->launches);
   prof_mark(fe, 6);
   if (pub_this_frame) {
@@ -484,11 +494,8 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   }
   prof_mark(fe, 7);
   // stereo LK (feature_tracker.cpp:475-510)
-  launch_lk(fe->pd, fe->pyr[cur], fe->pyr[2], B.cur_pts, B.right_pts, B.st_sf, &B.st->n_cur, M, 3,
-            0, s, &fe->launches);
-  if (fe->cfg.flow_back)
-    launch_lk(fe->pd, fe->pyr[2], fe->pyr[cur], B.right_pts, B.rev_left_pts, B.st_sb,
-              &B.st->n_cur, M, 3, 0, s, &fe->launches);
+  launch_lk(fe->pd, fe->pyr[cur], fe->pyr[2], B.cur_pts, B.right_pts, B.st_sf, B.rev_left_pts,
+            B.st_sb, &B.st->n_cur, M, 3, 0, fe->cfg.flow_back ? 2 : 0, s, &fe->launches);
   launch_finalize(fe->tp, B, cur_time, fe->prev_time, s, &fe->launches);
   prof_mark(fe, 8);
   CU(cudaMemcpyAsync(fe->h_result[slot], B.result, fe->result_words * 4, cudaMemcpyDeviceToHost, s));
@@ -704,7 +711,7 @@ FE_API int esvio_fe_stage_lk(esvio_fe* fe, const uint8_t* prev_img, const uint8_
   if (use_initial_flow)
     CU(cudaMemcpyAsync(fe->d_scratch_p1, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
   launch_lk(fe->pd, fe->pyr[3], fe->pyr[4], fe->d_scratch_p0, fe->d_scratch_p1, fe->d_scratch_st,
-            fe->d_scratch_n, n, max_level, use_initial_flow, s, &fe->launches);
+            nullptr, nullptr, fe->d_scratch_n, n, max_level, use_initial_flow, 0, s, &fe->launches);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(next_pts, fe->d_scratch_p1, sizeof(float2) * n, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(status, fe->d_scratch_st, n, cudaMemcpyDeviceToHost, s));
@@ -720,8 +727,8 @@ FE_API int esvio_fe_stage_fmat_mask(esvio_fe* fe, const float* p1, const float* 
   cudaStream_t s = fe->stream;
   CU(cudaMemcpyAsync(fe->d_scratch_p0, p1, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(fe->d_scratch_p1, p2, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
-  launch_ransac_stage(fe->d_scratch_p0, fe->d_scratch_p1, n, thresh, fe->d_scratch_st,
-                      fe->d_scratch_n, s, &fe->launches);
+  launch_ransac_stage(fe->tp, fe->tb, fe->d_scratch_p0, fe->d_scratch_p1, n, thresh,
+                      fe->d_scratch_st, fe->d_scratch_n, s, &fe->launches);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(mask, fe->d_scratch_st, n, cudaMemcpyDeviceToHost, s));
   int it = 0;

@@ -4,32 +4,32 @@
 //
 // OpenCV (modules/calib3d/src/fundam.cpp + ptsetreg.cpp; not in the reference tree) runs a
 // sequential, adaptively shortened loop of 7-point hypotheses driven by cv::RNG(-1); for
-// fewer than 15 points it switches to LMedS.  Here one CTA replays exactly that sequence in
-// rounds of 32 hypotheses: thread 0 draws the 32 subsets from the same RNG stream, 32 lanes
-// solve the 7-point problems, 32 warps score one hypothesis each, and thread 0 folds the
-// scores in iteration order with the same "better than best" and iteration-count update
-// rules, so the surviving model (and hence the inlier mask) is the one the sequential loop
-// picks.  The 2-D null space comes from Gauss-Jordan elimination with complete pivoting
-// instead of an SVD: any basis of the same null space gives the same F matrices.
+// fewer than 15 points it switches to LMedS.  That loop is replayed here in three launches
+// whose result is the model the sequential loop would have picked:
+//   k_ransac_prepare  the RNG stream of cv::RNG(-1) is a constant, so its first 15360 raw
+//                     draws are a table in HBM; one CTA reduces them mod n, finds for every
+//                     stream offset how many draws the "7 distinct indices" rule consumes,
+//                     and chases the offsets to the start of every sample (attempt)
+//   k_ransac_hyp      32 attempts per CTA: degeneracy test + 7-point solve on 32 lanes, then
+//                     one warp per attempt scores its <= 3 models against all points
+//   k_ransac_fold     one CTA: iteration index = prefix count of valid samples, running best
+//                     = prefix max of inlier counts, iteration budget = RANSACUpdateNumIters
+//                     of that prefix max; the first sample past the budget ends the loop; the
+//                     winning model's inlier mask compacts the tracks (reduceVector)
+// The 2-D null space of the 7x9 system comes from Gauss-Jordan elimination with complete
+// pivoting instead of an SVD: any basis of the same null space gives the same F matrices.
 #include <float.h>
 
 #include "common.cuh"
 
 namespace esvio {
 
-constexpr int kRansacThreads = 1024;
-constexpr int kHyp = 32;  // hypotheses per round
 constexpr int kModelPts = 7;
-
-struct CvRng {
-  uint64_t state;
-  __device__ unsigned next() {
-    state = (uint64_t)(unsigned)state * 4164903690ULL + (unsigned)(state >> 32);
-    return (unsigned)state;
-  }
-  __device__ int uniform(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a) + a); }
-};
-
+constexpr int kDrawsPerThread = 15;
+constexpr int kNumDraws = 1024 * kDrawsPerThread;  // 15360 raw draws of cv::RNG(-1)
+constexpr int kMaxLen = 48;                        // cap on draws consumed by one sample
+constexpr int kMaxAttempts = 1280;
+constexpr int kHyp = 32;                           // attempts per CTA in k_ransac_hyp
 // haveCollinearPoints: is the last point collinear with any earlier pair
 __device__ bool collinear_with_last(const float2* m, int count) {
   const int i = count - 1;
@@ -41,28 +41,6 @@ __device__ bool collinear_with_last(const float2* m, int count) {
           (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2)))
         return true;
     }
-  }
-  return false;
-}
-
-// PointSetRegistrator::getSubset
-__device__ bool get_subset7(const float2* p1, const float2* p2, int count, CvRng& rng,
-                            int max_attempts, float2* s1, float2* s2) {
-  int idx[kModelPts];
-  for (int iters = 0; iters < max_attempts; ++iters) {
-    for (int i = 0; i < kModelPts; ++i) {
-      int cand;
-      for (;;) {
-        cand = rng.uniform(0, count);
-        bool dup = false;
-        for (int q = 0; q < i; ++q) dup |= (idx[q] == cand);
-        if (!dup) break;
-      }
-      idx[i] = cand;
-      s1[i] = p1[cand];
-      s2[i] = p2[cand];
-    }
-    if (!collinear_with_last(s1, kModelPts) && !collinear_with_last(s2, kModelPts)) return true;
   }
   return false;
 }
@@ -297,158 +275,36 @@ __device__ int ransac_update_iters(double p, double ep, int model_points, int ma
   return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)llrint(num / denom);
 }
 
-struct RansacShared {
+
+// ------------------------------------------------------------------------------------------
+// scratch shared by the three launches (HBM, one per handle)
+// ------------------------------------------------------------------------------------------
+enum { kModeSkip = 0, kModeRansac = 1, kModeLmeds = 2, kModeSeven = 3, kModeFail = 4 };
+
+struct RansacScratch {
+  int n, mode, n_attempts, pad;
+  double thresh, confidence;
+  int max_iters, pad2;
   float2 p1[kMaxCnt], p2[kMaxCnt];
-  float2 s1[kHyp][kModelPts], s2[kHyp][kModelPts];
-  double F[kHyp][27];
-  int nmodels[kHyp];
-  int sub_ok[kHyp];
-  int good[kHyp][3];
-  float median[kHyp][3];
-  double bestF[9];
-  int have_best, stop, iters_done;
-  uint8_t mask[kMaxCnt];
+  alignas(16) uint16_t idx[kMaxAttempts][8];
+  int valid[kMaxAttempts];
+  int nmodels[kMaxAttempts];
+  int good[kMaxAttempts][3];      // inlier counts (RANSAC)
+  float median[kMaxAttempts][3];  // median residuals (LMedS)
+  double F[kMaxAttempts][27];
 };
 
-// Computes the inlier mask of findFundamentalMat(p1, p2, FM_RANSAC, thresh, 0.99) into
-// S.mask; returns (uniformly) 1 when a model was found.  Called by the whole CTA.
-__device__ int fundamental_mask(RansacShared& S, int n, double thresh, double confidence,
-                                int max_iters, int* iters_out) {
-  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-  if (thresh <= 0) thresh = 3;
-  if (confidence < DBL_EPSILON || confidence > 1 - DBL_EPSILON) confidence = 0.99;
-  __shared__ CvRng s_rng;
-  __shared__ int s_niters, s_iter, s_best;
-  __shared__ double s_min_median;
-  if (tid == 0) {
-    s_rng.state = (uint64_t)-1;
-    s_iter = 0;
-    s_best = 0;
-    S.have_best = 0;
-    S.stop = 0;
-    s_min_median = DBL_MAX;
-  }
-  for (int i = tid; i < n; i += blockDim.x) S.mask[i] = 0;
-  __syncthreads();
-  if (n < 7) return 0;
-  if (n == 7) {  // direct 7-point, every point is an inlier
-    if (tid == 0) S.nmodels[0] = run_7point(S.p1, S.p2, S.F[0]);
-    __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) S.mask[i] = 1;
-    __syncthreads();
-    if (iters_out && tid == 0) *iters_out = 1;
-    return S.nmodels[0] > 0;
-  }
-  const bool ransac = n >= 15;
-  const float t2 = (float)(thresh * thresh);
-  if (tid == 0) {
-    if (ransac) s_niters = max_iters > 1 ? max_iters : 1;
-    else {
-      int it = ransac_update_iters(confidence, 0.45, kModelPts, max_iters);
-      s_niters = it < 3 ? 3 : it;
-    }
-  }
-  __syncthreads();
+size_t ransac_scratch_bytes() { return sizeof(RansacScratch); }
 
-  while (true) {
-    // ---- draw the next kHyp subsets from the RNG stream
-    if (tid == 0) {
-      for (int h = 0; h < kHyp; ++h) {
-        S.sub_ok[h] = 0;
-        if (s_iter + h >= s_niters) break;  // cannot be needed
-        S.sub_ok[h] = get_subset7(S.p1, S.p2, n, s_rng, ransac ? 10000 : 1000, S.s1[h], S.s2[h]) ? 1 : -1;
-        if (S.sub_ok[h] < 0) break;
-      }
-    }
-    __syncthreads();
-    // ---- solve
-    if (tid < kHyp) {
-      S.nmodels[tid] = 0;
-      if (S.sub_ok[tid] > 0) {
-        const int nm = run_7point(S.s1[tid], S.s2[tid], S.F[tid]);
-        S.nmodels[tid] = nm < 0 ? 0 : (nm > 3 ? 3 : nm);
-      }
-    }
-    __syncthreads();
-    // ---- score: warp h scores hypothesis h
-    if (warp < kHyp) {
-      const int nm = S.nmodels[warp];
-      for (int m = 0; m < nm; ++m) {
-        const double* F = S.F[warp] + 9 * m;
-        if (ransac) {
-          int good = 0;
-          for (int i = lane; i < n; i += 32) good += fm_error(F, S.p1[i], S.p2[i]) <= t2;
-          good = __reduce_add_sync(0xffffffffu, good);
-          if (lane == 0) S.good[warp][m] = good;
-        } else {
-          // n < 15: median of the errors = element n/2 of the sorted list
-          const float e = lane < n ? fm_error(F, S.p1[lane], S.p2[lane]) : FLT_MAX;
-          int rank = 0;
-          for (int j = 0; j < n; ++j) {
-            const float o = __shfl_sync(0xffffffffu, e, j);
-            rank += (o < e) || (o == e && j < lane);
-          }
-          if (lane < n && rank == n / 2) S.median[warp][m] = e;
-        }
-      }
-    }
-    __syncthreads();
-    // ---- fold in iteration order
-    if (tid == 0) {
-      int h = 0;
-      for (; h < kHyp; ++h) {
-        if (s_iter >= s_niters) break;
-        if (S.sub_ok[h] <= 0) {  // getSubset failed
-          S.stop = 1;
-          break;
-        }
-        for (int m = 0; m < S.nmodels[h]; ++m) {
-          if (ransac) {
-            const int good = S.good[h][m];
-            if (good > (s_best > kModelPts - 1 ? s_best : kModelPts - 1)) {
-              s_best = good;
-              for (int q = 0; q < 9; ++q) S.bestF[q] = S.F[h][9 * m + q];
-              S.have_best = 1;
-              s_niters = ransac_update_iters(confidence, (double)(n - good) / n, kModelPts, s_niters);
-            }
-          } else {
-            const double med = (double)S.median[h][m];
-            if (med < s_min_median) {
-              s_min_median = med;
-              for (int q = 0; q < 9; ++q) S.bestF[q] = S.F[h][9 * m + q];
-              S.have_best = 1;
-            }
-          }
-        }
-        ++s_iter;
-      }
-      if (s_iter >= s_niters) S.stop = 1;
-    }
-    __syncthreads();
-    if (S.stop) break;
+// cv::RNG(-1): state = (uint64)-1; next(): state = (unsigned)state * 4164903690 + (state >> 32)
+void ransac_fill_draw_table(uint32_t* host_table) {
+  uint64_t state = (uint64_t)-1;
+  for (int i = 0; i < kNumDraws; ++i) {
+    state = (uint64_t)(unsigned)state * 4164903690ULL + (unsigned)(state >> 32);
+    host_table[i] = (unsigned)state;
   }
-  int result = 0;
-  if (S.have_best) {
-    float thr2 = t2;
-    if (!ransac) {
-      double sigma = 2.5 * 1.4826 * (1 + 5. / (n - kModelPts)) * sqrt(s_min_median);
-      sigma = fmax(sigma, 0.001);
-      thr2 = (float)(sigma * sigma);
-    }
-    for (int i = tid; i < n; i += blockDim.x)
-      S.mask[i] = (uint8_t)(fm_error(S.bestF, S.p1[i], S.p2[i]) <= thr2);
-    __syncthreads();
-    if (ransac) result = 1;
-    else {
-      int cnt = 0;
-      for (int i = 0; i < n; ++i) cnt += S.mask[i];
-      result = cnt >= kModelPts;
-    }
-  }
-  __syncthreads();
-  if (iters_out && tid == 0) *iters_out = s_iter;
-  return result;
 }
+int ransac_num_draws() { return kNumDraws; }
 
 __device__ __forceinline__ void lift_pinhole(const Pinhole& c, double u, double v, double& ox,
                                              double& oy) {
@@ -471,38 +327,398 @@ __device__ __forceinline__ void lift_pinhole(const Pinhole& c, double u, double 
   oy = yu;
 }
 
-__global__ void __launch_bounds__(kRansacThreads) k_ransac_tracks(TrackParams P, TrackBuffers B) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  RansacShared& S = *reinterpret_cast<RansacShared*>(s_raw);
-  __shared__ int s_warp[33];
-  TrackState* st = B.st;
-  const int n = st->n_cur;
+// ------------------------------------------------------------------------------------------
+// k_ransac_prepare: points + the start of every sample in the RNG stream
+// ------------------------------------------------------------------------------------------
+struct PrepareArgs {
+  int from_tracks;          // 1: lift B.prev_pts/B.cur_pts (rejectWithF_event); 0: stage points
+  const float2 *p1, *p2;    // stage mode
+  int n;                    // stage mode
+  double thresh;
+  int min_points;           // 8 in the tracker (feature_tracker.cpp:912), 7 for the stage entry
+};
+
+__global__ void __launch_bounds__(1024)
+k_ransac_prepare(TrackParams P, TrackBuffers B, PrepareArgs A, const uint32_t* __restrict__ draws,
+                 RansacScratch* __restrict__ R) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint16_t* s_v = reinterpret_cast<uint16_t*>(s_dyn);  // draws reduced mod n
+  uint16_t* s_hop8 = s_v + kNumDraws;                  // stream offset 8 samples further on
+  uint8_t* s_len = reinterpret_cast<uint8_t*>(s_hop8 + kNumDraws);  // draws one sample consumes
+  __shared__ uint16_t s_start8[kMaxAttempts / 8 + 1];
   const int tid = threadIdx.x;
-  if (n < 8) return;  // cur_pts.size() >= 8 guard (feature_tracker.cpp:912)
+  const int n = A.from_tracks ? B.st->n_cur : A.n;
+  if (tid == 0) {
+    R->n = n;
+    R->thresh = A.thresh <= 0 ? 3.0 : A.thresh;
+    R->confidence = 0.99;
+    R->max_iters = 1000;
+    R->n_attempts = 0;
+    R->mode = n < A.min_points ? (A.from_tracks ? kModeSkip : kModeFail)
+                               : (n == 7 ? kModeSeven : (n >= 15 ? kModeRansac : kModeLmeds));
+  }
+  if (n < A.min_points) return;
+  for (int i = tid; i < n; i += blockDim.x) {
+    if (A.from_tracks) {
+      const float2 pp = B.prev_pts[i], cp = B.cur_pts[i];
+      double x, y;
+      lift_pinhole(P.cam[0], (double)pp.x, (double)pp.y, x, y);
+      R->p1[i] = make_float2((float)(P.focal_length * x + P.W / 2.0),
+                             (float)(P.focal_length * y + P.H / 2.0));
+      lift_pinhole(P.cam[0], (double)cp.x, (double)cp.y, x, y);
+      R->p2[i] = make_float2((float)(P.focal_length * x + P.W / 2.0),
+                             (float)(P.focal_length * y + P.H / 2.0));
+    } else {
+      R->p1[i] = A.p1[i];
+      R->p2[i] = A.p2[i];
+    }
+  }
+  if (n == 7) {
+    if (tid < 8) R->idx[0][tid] = (uint16_t)(tid < 7 ? tid : 0);
+    if (tid == 0) R->n_attempts = 1;
+    return;
+  }
+  // rng.uniform(0, n) == next() % n
+  for (int i = tid; i < kNumDraws; i += blockDim.x) s_v[i] = (uint16_t)(draws[i] % (unsigned)n);
+  __syncthreads();
+  // PointSetRegistrator::getSubset: redraw while the index repeats an earlier one
+  for (int o = tid; o < kNumDraws; o += blockDim.x) {
+    int got = 0, k = 0;
+    uint16_t sel[kModelPts];
+    while (got < kModelPts && k < kMaxLen && o + k < kNumDraws) {
+      const uint16_t c = s_v[o + k++];
+      bool dup = false;
+#pragma unroll
+      for (int q = 0; q < kModelPts; ++q) dup |= (q < got && sel[q] == c);
+      if (!dup) {
+#pragma unroll
+        for (int q = 0; q < kModelPts; ++q)
+          if (q == got) sel[q] = c;
+        ++got;
+      }
+    }
+    s_len[o] = (uint8_t)(got == kModelPts ? k : 0);  // 0: stream exhausted / capped
+  }
+  __syncthreads();
+  // start offsets: thread 0 cannot afford 1280 dependent hops, so first every 8th start is
+  // found with 8-hop jumps computed in parallel for all offsets
+  for (int o = tid; o < kNumDraws; o += blockDim.x) {
+    int p = o;
+    bool ok = true;
+    for (int h = 0; h < 8 && ok; ++h) {
+      const int l = p < kNumDraws ? s_len[p] : 0;
+      if (l == 0) ok = false;
+      else p += l;
+    }
+    s_hop8[o] = (uint16_t)(ok && p < kNumDraws ? p : 0xffff);
+  }
+  __syncthreads();
+  __shared__ int s_groups;
+  if (tid == 0) {
+    int p = 0, g = 0;
+    while (g < kMaxAttempts / 8 && p != 0xffff) {
+      s_start8[g++] = (uint16_t)p;
+      p = s_hop8[p];
+    }
+    s_groups = g;  // complete groups of 8 attempts start at s_start8[0..g-1] (last may be partial)
+  }
+  __syncthreads();
+  const int groups = s_groups;
+  __shared__ int s_natt;
+  if (tid == 0) s_natt = 0;
+  __syncthreads();
+  if (tid < groups) {
+    int p = s_start8[tid];
+    int cnt = 0;
+    for (int h = 0; h < 8; ++h) {
+      const int l = p < kNumDraws ? s_len[p] : 0;
+      if (l == 0) break;
+      // re-derive the 7 distinct indices of the sample starting at p
+      int got = 0, k = 0;
+      const int a = tid * 8 + h;
+      __align__(16) uint16_t sel[8];
+      while (got < kModelPts) {
+        const uint16_t c = s_v[p + k++];
+        bool dup = false;
+#pragma unroll
+        for (int q = 0; q < kModelPts; ++q) dup |= (q < got && sel[q] == c);
+        if (!dup) {
+#pragma unroll
+          for (int q = 0; q < kModelPts; ++q)
+            if (q == got) sel[q] = c;
+          ++got;
+        }
+      }
+      sel[7] = 0;
+      *reinterpret_cast<uint4*>(R->idx[a]) = *reinterpret_cast<const uint4*>(sel);
+      p += l;
+      ++cnt;
+    }
+    if (cnt < 8 || tid == groups - 1) atomicMax(&s_natt, tid * 8 + cnt);
+  }
+  __syncthreads();
+  if (tid == 0) R->n_attempts = s_natt;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_ransac_hyp: solve and score 32 attempts per CTA
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_ransac_hyp(RansacScratch* __restrict__ R) {
+  __shared__ float2 s_p1[kMaxCnt], s_p2[kMaxCnt];
+  __shared__ double s_F[kHyp][27];
+  __shared__ int s_nm[kHyp];
+  const int mode = R->mode;
+  if (mode == kModeSkip || mode == kModeFail) return;
+  const int n = R->n, n_att = R->n_attempts;
+  const int a0 = blockIdx.x * kHyp;
+  if (a0 >= n_att) return;
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  for (int i = tid; i < n; i += blockDim.x) {
+    s_p1[i] = R->p1[i];
+    s_p2[i] = R->p2[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int a = a0 + lane;
+    int nm = 0, valid = 0;
+    if (a < n_att) {
+      float2 m1[kModelPts], m2[kModelPts];
+#pragma unroll
+      for (int q = 0; q < kModelPts; ++q) {
+        const int id = R->idx[a][q];
+        m1[q] = s_p1[id];
+        m2[q] = s_p2[id];
+      }
+      // FMEstimatorCallback::checkSubset
+      valid = (mode == kModeSeven) ||
+              !(collinear_with_last(m1, kModelPts) || collinear_with_last(m2, kModelPts));
+      if (valid) {
+        nm = run_7point(m1, m2, s_F[lane]);
+        nm = nm < 0 ? 0 : (nm > 3 ? 3 : nm);
+      }
+      R->valid[a] = valid;
+      R->nmodels[a] = nm;
+    }
+    s_nm[lane] = nm;
+  }
+  __syncthreads();
+  {
+    const int a = a0 + warp;
+    if (a >= n_att) return;
+    const int nm = s_nm[warp];
+    const float t2 = (float)(R->thresh * R->thresh);
+    for (int m = 0; m < nm; ++m) {
+      const double* F = s_F[warp] + 9 * m;
+      if (lane < 9) R->F[a][9 * m + lane] = F[lane];
+      if (mode == kModeRansac) {
+        int good = 0;
+        for (int i = lane; i < n; i += 32) good += fm_error(F, s_p1[i], s_p2[i]) <= t2;
+        good = __reduce_add_sync(0xffffffffu, good);
+        if (lane == 0) R->good[a][m] = good;
+      } else if (mode == kModeLmeds) {
+        // n < 15: median of the residuals = element n/2 of the sorted list
+        const float e = lane < n ? fm_error(F, s_p1[lane], s_p2[lane]) : FLT_MAX;
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+          const float o = __shfl_sync(0xffffffffu, e, j);
+          rank += (o < e) || (o == e && j < lane);
+        }
+        if (lane < n && rank == n / 2) R->median[a][m] = e;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_ransac_fold: replay the sequential loop's decisions, build the mask, compact the tracks
+// ------------------------------------------------------------------------------------------
+struct FoldArgs {
+  int to_tracks;
+  uint8_t* mask;  // stage mode
+  int* iters;     // stage mode
+};
+
+__global__ void __launch_bounds__(1024)
+k_ransac_fold(TrackParams P, TrackBuffers B, FoldArgs A, RansacScratch* __restrict__ R) {
+  __shared__ int s_warp[33];
+  __shared__ int s_pm[kMaxAttempts];   // per attempt: best inlier count among its models, -1 none
+  __shared__ int s_it[kMaxAttempts];   // iteration index (exclusive prefix count of valid)
+  __shared__ uint8_t s_mask[kMaxCnt];
+  __shared__ double s_bestF[9];
+  __shared__ int s_best_a, s_best_m, s_iters, s_result;
+  __shared__ float s_thr2;
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const int mode = R->mode, n = R->n;
+  if (mode == kModeSkip) return;
+  const int n_att = R->n_attempts;
+  if (tid == 0) {
+    s_best_a = -1;
+    s_best_m = 0;
+    s_iters = 0;
+    s_result = 0;
+    s_thr2 = (float)(R->thresh * R->thresh);
+  }
+  for (int i = tid; i < kMaxCnt; i += blockDim.x) s_mask[i] = 0;
+  __syncthreads();
+  if (mode == kModeSeven) {
+    if (tid == 0) {
+      s_result = R->nmodels[0] > 0;
+      s_iters = 1;
+    }
+    for (int i = tid; i < n; i += blockDim.x) s_mask[i] = 1;
+    __syncthreads();
+  } else if (mode == kModeRansac || mode == kModeLmeds) {
+    // iteration index of every attempt: exclusive prefix count of valid samples.  Done by one
+    // warp over <= 1280 entries (40 strides); the rest is embarrassingly parallel.
+    if (warp == 0) {
+      int carry = 0;
+      for (int base = 0; base < n_att; base += 32) {
+        const int a = base + lane;
+        const int v = a < n_att ? R->valid[a] : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, v);
+        if (a < n_att) s_it[a] = carry + __popc(bal & ((1u << lane) - 1u));
+        carry += __popc(bal);
+      }
+    }
+    __syncthreads();
+    if (mode == kModeRansac) {
+      for (int a = tid; a < n_att; a += blockDim.x) {
+        int best = -1;
+        if (R->valid[a])
+          for (int m = 0; m < R->nmodels[a]; ++m) best = max(best, R->good[a][m]);
+        s_pm[a] = best;
+      }
+      __syncthreads();
+      // sequential semantics: budget after an attempt = RANSACUpdateNumIters of the best count
+      // so far (only counts > 6 update it); an attempt runs iff its iteration index is below
+      // the budget left by its predecessors.  The budget is non-increasing and the index
+      // increasing, so the loop end is the first attempt that fails the test.
+      if (warp == 0) {
+        int run_best = kModelPts - 1, budget = R->max_iters, iters = 0, best_a = -1;
+        bool stop = false;
+        for (int base = 0; base < n_att && !stop; base += 32) {
+          const int a = base + lane;
+          const int g = a < n_att ? s_pm[a] : -1;
+          const int it = a < n_att ? s_it[a] : 0x7fffffff;
+          const int v = a < n_att ? R->valid[a] : 0;
+          // inclusive prefix max inside the stride
+          int pmx = g;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, pmx, d);
+            if (lane >= d) pmx = max(pmx, o);
+          }
+          int excl = __shfl_up_sync(0xffffffffu, pmx, 1);
+          if (lane == 0) excl = -1;
+          const int best_before = max(run_best, excl);
+          const int budget_before =
+              best_before > kModelPts - 1
+                  ? min(budget, ransac_update_iters(R->confidence, (double)(n - best_before) / n,
+                                                    kModelPts, R->max_iters))
+                  : budget;
+          const bool runs = v && it < budget_before;
+          const bool dead = a < n_att && v && !runs;  // first such attempt ends the loop
+          const unsigned dead_bal = __ballot_sync(0xffffffffu, dead);
+          const unsigned live = dead_bal ? ((1u << (__ffs(dead_bal) - 1)) - 1u) : 0xffffffffu;
+          const bool counted = runs && ((live >> lane) & 1u);
+          iters += __popc(__ballot_sync(0xffffffffu, counted));
+          // new best inside the live part: strictly greater than everything before it
+          const bool improves = counted && g > best_before;
+          const unsigned imp = __ballot_sync(0xffffffffu, improves);
+          if (imp) {
+            const int last = 31 - __clz(imp);
+            best_a = base + last;
+            run_best = __shfl_sync(0xffffffffu, g, last);
+          }
+          if (run_best > kModelPts - 1)
+            budget = min(budget, ransac_update_iters(R->confidence, (double)(n - run_best) / n,
+                                                     kModelPts, R->max_iters));
+          if (dead_bal) stop = true;
+        }
+        if (lane == 0) {
+          s_iters = iters;
+          s_best_a = best_a;
+          if (best_a >= 0) {
+            int bm = 0;
+            for (int m = 1; m < R->nmodels[best_a]; ++m)
+              if (R->good[best_a][m] > R->good[best_a][bm]) bm = m;
+            s_best_m = bm;
+            s_result = 1;
+          }
+        }
+      }
+    } else {
+      // LMedS: fixed budget; the smallest median wins, earliest on ties
+      if (warp == 0) {
+        int budget = ransac_update_iters(R->confidence, 0.45, kModelPts, R->max_iters);
+        budget = budget < 3 ? 3 : budget;
+        float best = FLT_MAX;
+        int best_a = -1, best_m = 0, iters = 0;
+        for (int base = 0; base < n_att; base += 32) {
+          const int a = base + lane;
+          const bool runs = a < n_att && R->valid[a] && s_it[a] < budget;
+          iters += __popc(__ballot_sync(0xffffffffu, runs));
+          float mine = FLT_MAX;
+          int mine_m = 0;
+          if (runs)
+            for (int m = 0; m < R->nmodels[a]; ++m)
+              if (R->median[a][m] < mine) mine = R->median[a][m], mine_m = m;
+          // earliest lane holding the stride minimum
+          float mn = mine;
+#pragma unroll
+          for (int d = 16; d; d >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+          const unsigned who = __ballot_sync(0xffffffffu, mine == mn && mine < FLT_MAX);
+          if (who && mn < best) {
+            const int l = __ffs(who) - 1;
+            best = mn;
+            best_a = base + l;
+            best_m = __shfl_sync(0xffffffffu, mine_m, l);
+          }
+        }
+        if (lane == 0) {
+          s_iters = iters;
+          s_best_a = best_a;
+          s_best_m = best_m;
+          if (best_a >= 0) {
+            double sigma = 2.5 * 1.4826 * (1 + 5. / (n - kModelPts)) * sqrt((double)best);
+            sigma = fmax(sigma, 0.001);
+            s_thr2 = (float)(sigma * sigma);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (s_best_a >= 0) {
+      if (tid < 9) s_bestF[tid] = R->F[s_best_a][9 * s_best_m + tid];
+      __syncthreads();
+      for (int i = tid; i < n; i += blockDim.x)
+        s_mask[i] = (uint8_t)(fm_error(s_bestF, R->p1[i], R->p2[i]) <= s_thr2);
+      __syncthreads();
+      if (mode == kModeLmeds && tid == 0) {
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) cnt += s_mask[i];
+        s_result = cnt >= kModelPts;
+      }
+      __syncthreads();
+    }
+  }
+  const int ok = s_result;
+  if (!A.to_tracks) {
+    for (int i = tid; i < n; i += blockDim.x) A.mask[i] = ok ? s_mask[i] : 0;
+    if (tid == 0) *A.iters = s_iters;
+    return;
+  }
+  // reduceVector(prev_pts / cur_pts / ids / track_cnt, status) (feature_tracker.cpp:938-942)
+  TrackState* st = B.st;
   float2 pp = make_float2(0, 0), cp = make_float2(0, 0);
   int id = 0, cnt = 0;
+  const int keep = tid < n ? (ok ? s_mask[tid] : 0) : 0;
   if (tid < n) {
     pp = B.prev_pts[tid];
     cp = B.cur_pts[tid];
     id = B.ids[tid];
     cnt = B.cnt[tid];
-    double x, y;
-    lift_pinhole(P.cam[0], (double)pp.x, (double)pp.y, x, y);
-    S.p1[tid] = make_float2((float)(P.focal_length * x + P.W / 2.0),
-                            (float)(P.focal_length * y + P.H / 2.0));
-    lift_pinhole(P.cam[0], (double)cp.x, (double)cp.y, x, y);
-    S.p2[tid] = make_float2((float)(P.focal_length * x + P.W / 2.0),
-                            (float)(P.focal_length * y + P.H / 2.0));
   }
-  __syncthreads();
-  int iters = 0;
-  __shared__ int s_iters;
-  fundamental_mask(S, n, P.f_threshold, 0.99, 1000, &s_iters);
-  __syncthreads();
-  iters = s_iters;
-  const int keep = tid < n ? S.mask[tid] : 0;
-  // order-preserving compaction (reduceVector)
-  const int lane = lane_id(), warp = tid >> 5;
   const unsigned bal = __ballot_sync(0xffffffffu, keep);
   if (lane == 0) s_warp[warp] = __popc(bal);
   __syncthreads();
@@ -529,51 +745,62 @@ __global__ void __launch_bounds__(kRansacThreads) k_ransac_tracks(TrackParams P,
     st->n_cur = s_warp[32];
     st->stat_after_ransac = s_warp[32];
     st->stat_after_mask = s_warp[32];
-    st->stat_ransac_iters = iters;
+    st->stat_ransac_iters = s_iters;
   }
 }
 
-__global__ void __launch_bounds__(kRansacThreads)
-k_ransac_stage(const float2* __restrict__ p1, const float2* __restrict__ p2, int n, double thresh,
-               uint8_t* __restrict__ mask, int* __restrict__ iters) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  RansacShared& S = *reinterpret_cast<RansacShared*>(s_raw);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    S.p1[i] = p1[i];
-    S.p2[i] = p2[i];
-  }
-  __syncthreads();
-  __shared__ int s_iters;
-  if (threadIdx.x == 0) s_iters = 0;
-  const int ok = fundamental_mask(S, n, thresh, 0.99, 1000, &s_iters);
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) mask[i] = ok ? S.mask[i] : 0;
-  if (threadIdx.x == 0) *iters = s_iters;
-}
+constexpr size_t kPrepareSmem = (size_t)kNumDraws * 5;
 
-static int ransac_configure() {
-  static int done = 0;
-  cudaError_t e = cudaFuncSetAttribute(k_ransac_tracks, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(RansacShared));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_ransac_stage, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(RansacShared));
-  done = e == cudaSuccess;
-  return done ? 0 : -1;
+static void ransac_configure() {
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && done[dev]) return;
+  cudaFuncSetAttribute(k_ransac_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)kPrepareSmem);
+  if (dev >= 0 && dev < 64) done[dev] = true;
 }
 
 void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
                    int64_t* launches) {
   ransac_configure();
-  k_ransac_tracks<<<1, kRansacThreads, sizeof(RansacShared), s>>>(P, B);
-  ++*launches;
+  RansacScratch* R = reinterpret_cast<RansacScratch*>(B.rs);
+  PrepareArgs pa;
+  pa.from_tracks = 1;
+  pa.p1 = pa.p2 = nullptr;
+  pa.n = 0;
+  pa.thresh = P.f_threshold;
+  pa.min_points = 8;
+  k_ransac_prepare<<<1, 1024, kPrepareSmem, s>>>(P, B, pa, B.rng_draws, R);
+  k_ransac_hyp<<<kMaxAttempts / kHyp, 1024, 0, s>>>(R);
+  FoldArgs fa;
+  fa.to_tracks = 1;
+  fa.mask = nullptr;
+  fa.iters = nullptr;
+  k_ransac_fold<<<1, 1024, 0, s>>>(P, B, fa, R);
+  *launches += 3;
 }
 
-void launch_ransac_stage(const float2* p1, const float2* p2, int n, double thresh, uint8_t* mask,
-                         int* iters, cudaStream_t s, int64_t* launches) {
+void launch_ransac_stage(const TrackParams& P, const TrackBuffers& B, const float2* p1,
+                         const float2* p2, int n, double thresh, uint8_t* mask, int* iters,
+                         cudaStream_t s, int64_t* launches) {
+  RansacScratch* R = reinterpret_cast<RansacScratch*>(B.rs);
+  PrepareArgs pa;
+  pa.from_tracks = 0;
+  pa.p1 = p1;
+  pa.p2 = p2;
+  pa.n = n;
+  pa.thresh = thresh;
+  pa.min_points = 7;
   ransac_configure();
-  k_ransac_stage<<<1, kRansacThreads, sizeof(RansacShared), s>>>(p1, p2, n, thresh, mask, iters);
-  ++*launches;
+  k_ransac_prepare<<<1, 1024, kPrepareSmem, s>>>(P, B, pa, B.rng_draws, R);
+  k_ransac_hyp<<<kMaxAttempts / kHyp, 1024, 0, s>>>(R);
+  FoldArgs fa;
+  fa.to_tracks = 0;
+  fa.mask = mask;
+  fa.iters = iters;
+  k_ransac_fold<<<1, 1024, 0, s>>>(P, B, fa, R);
+  *launches += 3;
 }
 
 }  // namespace esvio
