@@ -4,12 +4,12 @@
 //
 // OpenCV (modules/calib3d/src/fundam.cpp + ptsetreg.cpp; not in the reference tree) runs a
 // sequential, adaptively shortened loop of 7-point hypotheses driven by cv::RNG(-1); for
-// fewer than 15 points it switches to LMedS.  That loop is replayed here in three launches
-// whose result is the model the sequential loop would have picked:
-//   k_ransac_prepare  the RNG stream of cv::RNG(-1) is a constant, so its first 15360 raw
-//                     draws are a table in HBM; one CTA reduces them mod n, finds for every
-//                     stream offset how many draws the "7 distinct indices" rule consumes,
-//                     and chases the offsets to the start of every sample (attempt)
+// fewer than 15 points it switches to LMedS.  That loop is replayed here in parallel stages
+// (four launches) whose result is the model the sequential loop would have picked:
+//   k_ransac_len      the RNG stream of cv::RNG(-1) is a constant, so its first 15360 raw
+//                     draws are a table in HBM; reduce them mod n and find for every stream
+//                     offset how many draws the "7 distinct indices" rule consumes
+//   k_ransac_chase    one CTA chases the offsets to the start of every sample (attempt)
 //   k_ransac_hyp      32 attempts per CTA: degeneracy test + 7-point solve on 32 lanes, then
 //                     one warp per attempt scores its <= 3 models against all points
 //   k_ransac_fold     one CTA: iteration index = prefix count of valid samples, running best
@@ -287,6 +287,8 @@ struct RansacScratch {
   int max_iters, pad2;
   float2 p1[kMaxCnt], p2[kMaxCnt];
   alignas(16) uint16_t idx[kMaxAttempts][8];
+  alignas(16) uint16_t v[kNumDraws];  // draws reduced mod n
+  alignas(16) uint8_t len[kNumDraws];  // draws consumed by a sample starting at that offset
   int valid[kMaxAttempts];
   int nmodels[kMaxAttempts];
   int good[kMaxAttempts][3];      // inlier counts (RANSAC)
@@ -338,14 +340,51 @@ struct PrepareArgs {
   int min_points;           // 8 in the tracker (feature_tracker.cpp:912), 7 for the stage entry
 };
 
+// (a) every CTA owns 1024 stream offsets: reduce the draws mod n and find, for every offset, how
+//     many draws the "7 distinct indices" rule of PointSetRegistrator::getSubset consumes
 __global__ void __launch_bounds__(1024)
-k_ransac_prepare(TrackParams P, TrackBuffers B, PrepareArgs A, const uint32_t* __restrict__ draws,
-                 RansacScratch* __restrict__ R) {
+k_ransac_len(TrackBuffers B, PrepareArgs A, const uint32_t* __restrict__ draws,
+             RansacScratch* __restrict__ R) {
+  __shared__ uint16_t s_v[1024 + kMaxLen];
+  const int tid = threadIdx.x;
+  const int n = A.from_tracks ? B.st->n_cur : A.n;
+  if (n < A.min_points || n <= 7) return;
+  const int base = blockIdx.x * 1024;
+  for (int i = tid; i < 1024 + kMaxLen; i += blockDim.x) {
+    const int g = base + i;
+    s_v[i] = g < kNumDraws ? (uint16_t)(draws[g] % (unsigned)n) : (uint16_t)0xffff;
+  }
+  __syncthreads();
+  int got = 0, k = 0;
+  uint16_t sel[kModelPts];
+  while (got < kModelPts && k < kMaxLen) {
+    const uint16_t c = s_v[tid + k++];
+    if (c == 0xffff) break;
+    bool dup = false;
+#pragma unroll
+    for (int q = 0; q < kModelPts; ++q) dup |= (q < got && sel[q] == c);
+    if (!dup) {
+#pragma unroll
+      for (int q = 0; q < kModelPts; ++q)
+        if (q == got) sel[q] = c;
+      ++got;
+    }
+  }
+  R->v[base + tid] = s_v[tid];
+  R->len[base + tid] = (uint8_t)(got == kModelPts ? k : 0);  // 0: stream exhausted / capped
+}
+
+// (b) one CTA: lift the points, then chase the offsets to the start of every sample.  Thread 0
+//     cannot afford 1280 dependent hops, so 8-hop jumps are computed for all offsets in
+//     parallel, thread 0 follows those, and one thread per group of 8 fills in the rest.
+__global__ void __launch_bounds__(1024)
+k_ransac_chase(TrackParams P, TrackBuffers B, PrepareArgs A, RansacScratch* __restrict__ R) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   uint16_t* s_v = reinterpret_cast<uint16_t*>(s_dyn);  // draws reduced mod n
   uint16_t* s_hop8 = s_v + kNumDraws;                  // stream offset 8 samples further on
   uint8_t* s_len = reinterpret_cast<uint8_t*>(s_hop8 + kNumDraws);  // draws one sample consumes
   __shared__ uint16_t s_start8[kMaxAttempts / 8 + 1];
+  __shared__ int s_groups, s_natt;
   const int tid = threadIdx.x;
   const int n = A.from_tracks ? B.st->n_cur : A.n;
   if (tid == 0) {
@@ -378,55 +417,34 @@ k_ransac_prepare(TrackParams P, TrackBuffers B, PrepareArgs A, const uint32_t* _
     if (tid == 0) R->n_attempts = 1;
     return;
   }
-  // rng.uniform(0, n) == next() % n
-  for (int i = tid; i < kNumDraws; i += blockDim.x) s_v[i] = (uint16_t)(draws[i] % (unsigned)n);
+  for (int i = tid; i < kNumDraws / 8; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_v)[i] = reinterpret_cast<const uint4*>(R->v)[i];
+  for (int i = tid; i < kNumDraws / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_len)[i] = reinterpret_cast<const uint4*>(R->len)[i];
   __syncthreads();
-  // PointSetRegistrator::getSubset: redraw while the index repeats an earlier one
-  for (int o = tid; o < kNumDraws; o += blockDim.x) {
-    int got = 0, k = 0;
-    uint16_t sel[kModelPts];
-    while (got < kModelPts && k < kMaxLen && o + k < kNumDraws) {
-      const uint16_t c = s_v[o + k++];
-      bool dup = false;
-#pragma unroll
-      for (int q = 0; q < kModelPts; ++q) dup |= (q < got && sel[q] == c);
-      if (!dup) {
-#pragma unroll
-        for (int q = 0; q < kModelPts; ++q)
-          if (q == got) sel[q] = c;
-        ++got;
-      }
-    }
-    s_len[o] = (uint8_t)(got == kModelPts ? k : 0);  // 0: stream exhausted / capped
-  }
-  __syncthreads();
-  // start offsets: thread 0 cannot afford 1280 dependent hops, so first every 8th start is
-  // found with 8-hop jumps computed in parallel for all offsets
   for (int o = tid; o < kNumDraws; o += blockDim.x) {
     int p = o;
     bool ok = true;
-    for (int h = 0; h < 8 && ok; ++h) {
-      const int l = p < kNumDraws ? s_len[p] : 0;
-      if (l == 0) ok = false;
-      else p += l;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int l = (ok && p < kNumDraws) ? s_len[p] : 0;
+      ok = ok && l != 0;
+      p += l;
     }
     s_hop8[o] = (uint16_t)(ok && p < kNumDraws ? p : 0xffff);
   }
+  if (tid == 0) s_natt = 0;
   __syncthreads();
-  __shared__ int s_groups;
   if (tid == 0) {
     int p = 0, g = 0;
     while (g < kMaxAttempts / 8 && p != 0xffff) {
       s_start8[g++] = (uint16_t)p;
       p = s_hop8[p];
     }
-    s_groups = g;  // complete groups of 8 attempts start at s_start8[0..g-1] (last may be partial)
+    s_groups = g;  // groups of 8 attempts start at s_start8[0..g-1]; only the last may be partial
   }
   __syncthreads();
   const int groups = s_groups;
-  __shared__ int s_natt;
-  if (tid == 0) s_natt = 0;
-  __syncthreads();
   if (tid < groups) {
     int p = s_start8[tid];
     int cnt = 0;
@@ -545,7 +563,7 @@ k_ransac_fold(TrackParams P, TrackBuffers B, FoldArgs A, RansacScratch* __restri
   __shared__ int s_it[kMaxAttempts];   // iteration index (exclusive prefix count of valid)
   __shared__ uint8_t s_mask[kMaxCnt];
   __shared__ double s_bestF[9];
-  __shared__ int s_best_a, s_best_m, s_iters, s_result;
+  __shared__ int s_best_a, s_best_m, s_iters, s_result, s_first_dead;
   __shared__ float s_thr2;
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   const int mode = R->mode, n = R->n;
@@ -556,6 +574,7 @@ k_ransac_fold(TrackParams P, TrackBuffers B, FoldArgs A, RansacScratch* __restri
     s_best_m = 0;
     s_iters = 0;
     s_result = 0;
+    s_first_dead = 0x7fffffff;
     s_thr2 = (float)(R->thresh * R->thresh);
   }
   for (int i = tid; i < kMaxCnt; i += blockDim.x) s_mask[i] = 0;
@@ -570,7 +589,7 @@ k_ransac_fold(TrackParams P, TrackBuffers B, FoldArgs A, RansacScratch* __restri
   } else if (mode == kModeRansac || mode == kModeLmeds) {
     // iteration index of every attempt: exclusive prefix count of valid samples.  Done by one
     // warp over <= 1280 entries (40 strides); the rest is embarrassingly parallel.
-    if (warp == 0) {
+    if (warp == 0 && mode == kModeLmeds) {
       int carry = 0;
       for (int base = 0; base < n_att; base += 32) {
         const int a = base + lane;
@@ -582,70 +601,99 @@ k_ransac_fold(TrackParams P, TrackBuffers B, FoldArgs A, RansacScratch* __restri
     }
     __syncthreads();
     if (mode == kModeRansac) {
-      for (int a = tid; a < n_att; a += blockDim.x) {
-        int best = -1;
-        if (R->valid[a])
-          for (int m = 0; m < R->nmodels[a]; ++m) best = max(best, R->good[a][m]);
-        s_pm[a] = best;
+      // Sequential semantics: the budget after an attempt is RANSACUpdateNumIters of the best
+      // inlier count so far (only counts > 6 update it); an attempt runs iff its iteration
+      // index is below the budget left by its predecessors.  The budget never grows and the
+      // index never shrinks, so the loop ends at the first valid attempt that fails the test.
+      // Every thread owns two consecutive attempts; prefix count / prefix max are block scans.
+      const int a0 = 2 * tid;
+      int v[2], g[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int a = a0 + e;
+        v[e] = a < n_att ? R->valid[a] : 0;
+        g[e] = -1;
+        if (v[e])
+          for (int m = 0; m < R->nmodels[a]; ++m) g[e] = max(g[e], R->good[a][m]);
+      }
+      // exclusive block scan of (count of valid, max of g) over threads
+      int isum = v[0] + v[1], imax = max(g[0], g[1]);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int os = __shfl_up_sync(0xffffffffu, isum, d);
+        const int om = __shfl_up_sync(0xffffffffu, imax, d);
+        if (lane >= d) {
+          isum += os;
+          imax = max(imax, om);
+        }
+      }
+      if (lane == 31) {
+        s_it[warp] = isum;
+        s_pm[warp] = imax;
       }
       __syncthreads();
-      // sequential semantics: budget after an attempt = RANSACUpdateNumIters of the best count
-      // so far (only counts > 6 update it); an attempt runs iff its iteration index is below
-      // the budget left by its predecessors.  The budget is non-increasing and the index
-      // increasing, so the loop end is the first attempt that fails the test.
       if (warp == 0) {
-        int run_best = kModelPts - 1, budget = R->max_iters, iters = 0, best_a = -1;
-        bool stop = false;
-        for (int base = 0; base < n_att && !stop; base += 32) {
-          const int a = base + lane;
-          const int g = a < n_att ? s_pm[a] : -1;
-          const int it = a < n_att ? s_it[a] : 0x7fffffff;
-          const int v = a < n_att ? R->valid[a] : 0;
-          // inclusive prefix max inside the stride
-          int pmx = g;
+        int ws = s_it[lane], wm = s_pm[lane];
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, pmx, d);
-            if (lane >= d) pmx = max(pmx, o);
-          }
-          int excl = __shfl_up_sync(0xffffffffu, pmx, 1);
-          if (lane == 0) excl = -1;
-          const int best_before = max(run_best, excl);
-          const int budget_before =
-              best_before > kModelPts - 1
-                  ? min(budget, ransac_update_iters(R->confidence, (double)(n - best_before) / n,
-                                                    kModelPts, R->max_iters))
-                  : budget;
-          const bool runs = v && it < budget_before;
-          const bool dead = a < n_att && v && !runs;  // first such attempt ends the loop
-          const unsigned dead_bal = __ballot_sync(0xffffffffu, dead);
-          const unsigned live = dead_bal ? ((1u << (__ffs(dead_bal) - 1)) - 1u) : 0xffffffffu;
-          const bool counted = runs && ((live >> lane) & 1u);
-          iters += __popc(__ballot_sync(0xffffffffu, counted));
-          // new best inside the live part: strictly greater than everything before it
-          const bool improves = counted && g > best_before;
-          const unsigned imp = __ballot_sync(0xffffffffu, improves);
-          if (imp) {
-            const int last = 31 - __clz(imp);
-            best_a = base + last;
-            run_best = __shfl_sync(0xffffffffu, g, last);
-          }
-          if (run_best > kModelPts - 1)
-            budget = min(budget, ransac_update_iters(R->confidence, (double)(n - run_best) / n,
-                                                     kModelPts, R->max_iters));
-          if (dead_bal) stop = true;
-        }
-        if (lane == 0) {
-          s_iters = iters;
-          s_best_a = best_a;
-          if (best_a >= 0) {
-            int bm = 0;
-            for (int m = 1; m < R->nmodels[best_a]; ++m)
-              if (R->good[best_a][m] > R->good[best_a][bm]) bm = m;
-            s_best_m = bm;
-            s_result = 1;
+        for (int d = 1; d < 32; d <<= 1) {
+          const int os = __shfl_up_sync(0xffffffffu, ws, d);
+          const int om = __shfl_up_sync(0xffffffffu, wm, d);
+          if (lane >= d) {
+            ws += os;
+            wm = max(wm, om);
           }
         }
+        s_it[32 + lane] = ws;  // inclusive over warps
+        s_pm[32 + lane] = wm;
+      }
+      __syncthreads();
+      int esum = __shfl_up_sync(0xffffffffu, isum, 1), emax = __shfl_up_sync(0xffffffffu, imax, 1);
+      if (lane == 0) {
+        esum = 0;
+        emax = -1;
+      }
+      if (warp > 0) {
+        esum += s_it[32 + warp - 1];
+        emax = max(emax, s_pm[32 + warp - 1]);
+      }
+      const double conf = R->confidence;
+      const int max_it = R->max_iters;
+      int it[2] = {esum, esum + v[0]};
+      int bb[2];
+      bb[0] = max(kModelPts - 1, emax);
+      bb[1] = max(bb[0], g[0]);
+      bool runs[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int budget = bb[e] > kModelPts - 1
+                               ? ransac_update_iters(conf, (double)(n - bb[e]) / n, kModelPts, max_it)
+                               : max_it;
+        runs[e] = v[e] && it[e] < budget;
+        if (v[e] && !runs[e]) atomicMin(&s_first_dead, a0 + e);
+      }
+      __syncthreads();
+      const int first_dead = s_first_dead;
+      int my_iters = 0, my_best = -1;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool counted = runs[e] && (a0 + e) < first_dead;
+        my_iters += counted;
+        if (counted && g[e] > bb[e]) my_best = a0 + e;  // strictly better than all before it
+      }
+      my_iters = __reduce_add_sync(0xffffffffu, my_iters);
+      my_best = __reduce_max_sync(0xffffffffu, my_best);
+      if (lane == 0) {
+        if (my_iters) atomicAdd(&s_iters, my_iters);
+        if (my_best >= 0) atomicMax(&s_best_a, my_best);
+      }
+      __syncthreads();
+      if (tid == 0 && s_best_a >= 0) {
+        const int ba = s_best_a;
+        int bm = 0;
+        for (int m = 1; m < R->nmodels[ba]; ++m)
+          if (R->good[ba][m] > R->good[ba][bm]) bm = m;
+        s_best_m = bm;
+        s_result = 1;
       }
     } else {
       // LMedS: fixed budget; the smallest median wins, earliest on ties
@@ -756,7 +804,7 @@ static void ransac_configure() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && done[dev]) return;
-  cudaFuncSetAttribute(k_ransac_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(k_ransac_chase, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)kPrepareSmem);
   if (dev >= 0 && dev < 64) done[dev] = true;
 }
@@ -771,14 +819,15 @@ void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
   pa.n = 0;
   pa.thresh = P.f_threshold;
   pa.min_points = 8;
-  k_ransac_prepare<<<1, 1024, kPrepareSmem, s>>>(P, B, pa, B.rng_draws, R);
+  k_ransac_len<<<kNumDraws / 1024, 1024, 0, s>>>(B, pa, B.rng_draws, R);
+  k_ransac_chase<<<1, 1024, kPrepareSmem, s>>>(P, B, pa, R);
   k_ransac_hyp<<<kMaxAttempts / kHyp, 1024, 0, s>>>(R);
   FoldArgs fa;
   fa.to_tracks = 1;
   fa.mask = nullptr;
   fa.iters = nullptr;
   k_ransac_fold<<<1, 1024, 0, s>>>(P, B, fa, R);
-  *launches += 3;
+  *launches += 4;
 }
 
 void launch_ransac_stage(const TrackParams& P, const TrackBuffers& B, const float2* p1,
@@ -793,14 +842,15 @@ void launch_ransac_stage(const TrackParams& P, const TrackBuffers& B, const floa
   pa.thresh = thresh;
   pa.min_points = 7;
   ransac_configure();
-  k_ransac_prepare<<<1, 1024, kPrepareSmem, s>>>(P, B, pa, B.rng_draws, R);
+  k_ransac_len<<<kNumDraws / 1024, 1024, 0, s>>>(B, pa, B.rng_draws, R);
+  k_ransac_chase<<<1, 1024, kPrepareSmem, s>>>(P, B, pa, R);
   k_ransac_hyp<<<kMaxAttempts / kHyp, 1024, 0, s>>>(R);
   FoldArgs fa;
   fa.to_tracks = 0;
   fa.mask = mask;
   fa.iters = iters;
   k_ransac_fold<<<1, 1024, 0, s>>>(P, B, fa, R);
-  *launches += 3;
+  *launches += 4;
 }
 
 }  // namespace esvio

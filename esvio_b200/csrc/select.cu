@@ -350,6 +350,18 @@ k_finalize(TrackParams P, TrackBuffers B, double cur_time, double prev_time) {
         *r_rvy = r_rvx + M;
   const double dt = cur_time - prev_time;
   const int np_un = st->n_prev_un, np_un_r = st->n_prev_un_r;
+  // prev_un_pts_map / prev_un_right_pts_map (id -> point) staged in shared memory
+  __shared__ int s_pid[kMaxCnt], s_pid_r[kMaxCnt];
+  __shared__ float2 s_pun[kMaxCnt], s_pun_r[kMaxCnt];
+  if (i < np_un) {
+    s_pid[i] = B.prev_un_ids[i];
+    s_pun[i] = B.prev_un[i];
+  }
+  if (i < np_un_r) {
+    s_pid_r[i] = B.prev_un_r_ids[i];
+    s_pun_r[i] = B.prev_un_r[i];
+  }
+  __syncthreads();
 
   float2 cp = make_float2(0.f, 0.f), un = make_float2(0.f, 0.f);
   int id = -1;
@@ -365,8 +377,8 @@ k_finalize(TrackParams P, TrackBuffers B, double cur_time, double prev_time) {
     float vx = 0.f, vy = 0.f;
     if (np_un > 0 && id != -1) {
       for (int j = 0; j < np_un; ++j)
-        if (B.prev_un_ids[j] == id) {
-          const float2 q = B.prev_un[j];
+        if (s_pid[j] == id) {
+          const float2 q = s_pun[j];
           vx = (float)((double)(un.x - q.x) / dt);
           vy = (float)((double)(un.y - q.y) / dt);
           break;
@@ -402,8 +414,8 @@ k_finalize(TrackParams P, TrackBuffers B, double cur_time, double prev_time) {
     unr = make_float2((float)x, (float)y);
     if (np_un_r > 0 && id != -1) {
       for (int j = 0; j < np_un_r; ++j)
-        if (B.prev_un_r_ids[j] == id) {
-          const float2 q = B.prev_un_r[j];
+        if (s_pid_r[j] == id) {
+          const float2 q = s_pun_r[j];
           rvx = (float)((double)(unr.x - q.x) / dt);
           rvy = (float)((double)(unr.y - q.y) / dt);
           break;
