@@ -24,7 +24,7 @@ namespace esvio {
 constexpr int kWBits = 14;
 constexpr int kLkThreads = 128;
 constexpr int kLkWarps = kLkThreads / 32;
-constexpr int kPxPerThread = (kWin * kWin + kLkThreads - 1) / kLkThreads;  // 4
+constexpr int kPxPerLane = (kWin * kWin + 31) / 32;  // 14
 constexpr int kIP = 24;  // staged intensity patch (window + bilinear tap + Scharr ring)
 constexpr int kDP = 22;  // derivative patch (window + bilinear tap)
 constexpr int kJM = 5;   // margin of the staged search region
@@ -41,216 +41,241 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
 }
 
 struct LkShared {
-  uint8_t I[kIP][kIP];
-  short2 D[kDP][kDP];
-  uint8_t J[kJR][kJR];
-  int red[2][kLkWarps][6];  // double-buffered per-warp (hi, lo) partials of up to 3 sums
+  uint8_t I[kMaxLevels][kIP][kIP];      // template neighbourhoods of all levels
+  short2 D[kMaxLevels][kDP][kDP];       // their Scharr derivatives
+  short Tw[kMaxLevels][kPxPerLane * 32];  // templates: Iw, Ixw, Iyw per window pixel
+  short Tx[kMaxLevels][kPxPerLane * 32];
+  short Ty[kMaxLevels][kPxPerLane * 32];
+  float A[kMaxLevels][3];
+  int flag[kMaxLevels];  // 0 ok, 1 template window outside the image, 2 minEig / det test failed
+  uint8_t J[kJR][kJR];   // search region of the level being iterated
+  float2 np;
+  int st;
 };
 
-// exact CTA-wide sums of NV int32 values per thread; one __syncthreads per call
-template <int NV>
-__device__ __forceinline__ void cta_sum_exact(LkShared& S, int buf, const int (&v)[NV],
-                                              long long (&out)[NV]) {
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int q = 0; q < NV; ++q) {
-    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v[q] & 0xffffu);
-    const int hi = __reduce_add_sync(0xffffffffu, v[q] >> 16);
-    if (lane == 0) {
-      S.red[buf][warp][2 * q] = hi;
-      S.red[buf][warp][2 * q + 1] = (int)lo;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < NV; ++q) {
-    long long acc = 0;
-#pragma unroll
-    for (int w = 0; w < kLkWarps; ++w)
-      acc += ((long long)S.red[buf][w][2 * q] << 16) + (long long)S.red[buf][w][2 * q + 1];
-    out[q] = acc;
-  }
+// exact sum over the warp of one int32 per lane, as int64
+__device__ __forceinline__ long long warp_sum_exact(int v) {
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
+  const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+  return ((long long)hi << 16) + (long long)lo;
 }
 
-// One calcOpticalFlowPyrLK call for one point; every thread of the CTA runs it with the same
-// scalars and returns the same (np, status).
+__device__ __forceinline__ void stage_J(LkShared& S, const uint8_t* __restrict__ Jl, int w, int h,
+                                        int pitch, int rx0, int ry0) {
+  // one warp: lane = column, 32 independent row loads in flight
+  const int lane = lane_id();
+  const int gx = reflect101(rx0 + lane, w);
+#pragma unroll 8
+  for (int r = 0; r < kJR; ++r)
+    S.J[r][lane] = Jl[(size_t)reflect101(ry0 + r, h) * pitch + gx];
+  __syncwarp();
+}
+
+// One calcOpticalFlowPyrLK call for one point, run by the whole CTA:
+//   phase 1-2 (all threads)  stage the 24x24 intensity patches and 22x22 Scharr patches of ALL
+//                            levels at once (they depend only on the point, not on the flow):
+//                            intensities reflect-101 outside the image like the border
+//                            buildOpticalFlowPyramid adds, derivatives zero outside the image
+//                            like the constant border of the derivative buffer
+//   phase 3 (warp L)         template + normal matrix of level L
+//   phase 4 (warp 0)         coarse-to-fine Newton iterations; <= 14 pixels per lane in
+//                            registers, the J search region in shared memory
+// Every thread returns the same (np, status).
 __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restrict__ I,
                          const uint8_t* __restrict__ J, float2 p0, float2 init, int use_init,
                          int top, float2& np_out, int& st_out) {
-  const int tid = threadIdx.x;
-  float2 np = use_init ? init : make_float2(0.f, 0.f);
-  int st = 1;
-  int buf = 0;
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   const float half = (float)kHalfWin;
   const float flt_scale = 1.f / (float)(1 << 20);
-  const double eps2 = 0.01 * 0.01;
-
-  int wx[kPxPerThread], wy[kPxPerThread];
-#pragma unroll
-  for (int j = 0; j < kPxPerThread; ++j) {
-    const int kk = tid + kLkThreads * j;
-    wy[j] = kk / kWin;
-    wx[j] = kk - wy[j] * kWin;
+  const int nlev = top + 1;
+  __syncthreads();  // previous use of S is over
+  // ---- phase 1: intensity patches of all levels
+  for (int i = tid; i < nlev * kIP * kIP; i += kLkThreads) {
+    const int L = i / (kIP * kIP), rem = i - L * (kIP * kIP);
+    const int r = rem / kIP, c = rem - r * kIP;
+    const float sc = 1.f / (float)(1 << L);
+    const int ipx = (int)floorf(p0.x * sc - half), ipy = (int)floorf(p0.y * sc - half);
+    const int w = pd.w[L], h = pd.h[L];
+    uint8_t v = 0;
+    if (!(ipx < -kWin || ipx >= w || ipy < -kWin || ipy >= h))
+      v = I[pd.off[L] + (size_t)reflect101(ipy - 1 + r, h) * pd.pitch[L] + reflect101(ipx - 1 + c, w)];
+    S.I[L][r][c] = v;
   }
-
-  for (int level = top; level >= 0; --level) {
-    const int w = pd.w[level], h = pd.h[level], pitch = pd.pitch[level];
-    const uint8_t* __restrict__ Il = I + pd.off[level];
-    const uint8_t* __restrict__ Jl = J + pd.off[level];
-    const float sc = 1.f / (float)(1 << level);
-    float ppx = p0.x * sc, ppy = p0.y * sc;
-    if (level == top) {
-      if (use_init) {
-        np.x *= sc;
-        np.y *= sc;
-      } else {
-        np.x = ppx;
-        np.y = ppy;
-      }
-    } else {
-      np.x *= 2.f;
-      np.y *= 2.f;
+  __syncthreads();
+  // ---- phase 2: Scharr derivatives
+  for (int i = tid; i < nlev * kDP * kDP; i += kLkThreads) {
+    const int L = i / (kDP * kDP), rem = i - L * (kDP * kDP);
+    const int r = rem / kDP, c = rem - r * kDP;
+    const float sc = 1.f / (float)(1 << L);
+    const int ipx = (int)floorf(p0.x * sc - half), ipy = (int)floorf(p0.y * sc - half);
+    const int gx = ipx + c, gy = ipy + r;
+    short2 d = make_short2(0, 0);
+    if (gx >= 0 && gx < pd.w[L] && gy >= 0 && gy < pd.h[L]) {
+      const uint8_t *up = S.I[L][r], *mid = S.I[L][r + 1], *dn = S.I[L][r + 2];
+      const int t0l = (up[c] + dn[c]) * 3 + mid[c] * 10;
+      const int t0r = (up[c + 2] + dn[c + 2]) * 3 + mid[c + 2] * 10;
+      const int t1l = dn[c] - up[c], t1m = dn[c + 1] - up[c + 1], t1r = dn[c + 2] - up[c + 2];
+      d.x = (short)(t0r - t0l);
+      d.y = (short)((t1r + t1l) * 3 + t1m * 10);
     }
-    ppx -= half;
-    ppy -= half;
+    S.D[L][r][c] = d;
+  }
+  __syncthreads();
+  // ---- phase 3: warp L builds the template of level L
+  if (warp < nlev) {
+    const int L = warp;
+    const float sc = 1.f / (float)(1 << L);
+    const float ppx = p0.x * sc - half, ppy = p0.y * sc - half;
     const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
-    if (ipx < -kWin || ipx >= w || ipy < -kWin || ipy >= h) {
-      if (level == 0) st = 0;
-      continue;
-    }
-    // ---- stage the template neighbourhood (intensities: reflect-101 outside the image like
-    //      the border buildOpticalFlowPyramid adds; derivatives: zero outside the image like
-    //      the constant border of the derivative buffer) and the J search region
-    float npx = np.x - half, npy = np.y - half;
-    int rx0 = (int)floorf(npx) - kJM, ry0 = (int)floorf(npy) - kJM;
-    __syncthreads();
-    for (int i = tid; i < kIP * kIP; i += kLkThreads) {
-      const int r = i / kIP, c = i - r * kIP;
-      S.I[r][c] = Il[(size_t)reflect101(ipy - 1 + r, h) * pitch + reflect101(ipx - 1 + c, w)];
-    }
-    if (rx0 >= -kWin - kJM && rx0 < w && ry0 >= -kWin - kJM && ry0 < h) {
-      for (int i = tid; i < kJR * kJR; i += kLkThreads) {
-        const int r = i / kJR, c = i - r * kJR;
-        S.J[r][c] = Jl[(size_t)reflect101(ry0 + r, h) * pitch + reflect101(rx0 + c, w)];
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < kDP * kDP; i += kLkThreads) {
-      const int r = i / kDP, c = i - r * kDP;
-      const int gx = ipx + c, gy = ipy + r;
-      short2 d = make_short2(0, 0);
-      if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
-        const uint8_t *up = S.I[r], *mid = S.I[r + 1], *dn = S.I[r + 2];
-        const int t0l = (up[c] + dn[c]) * 3 + mid[c] * 10;
-        const int t0r = (up[c + 2] + dn[c + 2]) * 3 + mid[c + 2] * 10;
-        const int t1l = dn[c] - up[c], t1m = dn[c + 1] - up[c + 1], t1r = dn[c + 2] - up[c + 2];
-        d.x = (short)(t0r - t0l);
-        d.y = (short)((t1r + t1l) * 3 + t1m * 10);
-      }
-      S.D[r][c] = d;
-    }
-    __syncthreads();
-
-    float a = ppx - (float)ipx, b = ppy - (float)ipy;
-    int iw00, iw01, iw10, iw11;
-    bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-    int Iw[kPxPerThread], Dx[kPxPerThread], Dy[kPxPerThread];
-    int sA[3] = {0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < kPxPerThread; ++j) {
-      Iw[j] = Dx[j] = Dy[j] = 0;
-      if (tid + kLkThreads * j < kWin * kWin) {
-        const int y = wy[j], x = wx[j];
-        const int iv = descale(S.I[y + 1][x + 1] * iw00 + S.I[y + 1][x + 2] * iw01 +
-                                   S.I[y + 2][x + 1] * iw10 + S.I[y + 2][x + 2] * iw11,
-                               kWBits - 5);
-        const short2 d00 = S.D[y][x], d01 = S.D[y][x + 1], d10 = S.D[y + 1][x],
-                     d11 = S.D[y + 1][x + 1];
-        const int ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, kWBits);
-        const int iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, kWBits);
-        Iw[j] = iv;
-        Dx[j] = ix;
-        Dy[j] = iy;
-        sA[0] += ix * ix;
-        sA[1] += ix * iy;
-        sA[2] += iy * iy;
-      }
-    }
-    long long tA[3];
-    cta_sum_exact<3>(S, buf, sA, tA);
-    buf ^= 1;
-    const float A11 = (float)tA[0] * flt_scale;
-    const float A12 = (float)tA[1] * flt_scale;
-    const float A22 = (float)tA[2] * flt_scale;
-    float D = A11 * A22 - A12 * A12;
-    const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) /
-                          (float)(2 * kWin * kWin);
-    if ((double)min_eig < 1e-4 || D < FLT_EPSILON) {
-      if (level == 0) st = 0;
-      continue;
-    }
-    D = 1.f / D;
-    float pdx = 0.f, pdy = 0.f;
-    for (int it = 0; it < 30; ++it) {
-      const int inx = (int)floorf(npx), iny = (int)floorf(npy);
-      if (inx < -kWin || inx >= w || iny < -kWin || iny >= h) {
-        if (level == 0) st = 0;
-        break;
-      }
-      if (inx < rx0 || iny < ry0 || inx + kWin > rx0 + kJR - 1 || iny + kWin > ry0 + kJR - 1) {
-        // the window left the staged region: re-stage around the current position (all
-        // threads are past the barrier that followed their last read of S.J)
-        rx0 = inx - kJM;
-        ry0 = iny - kJM;
-        for (int i = tid; i < kJR * kJR; i += kLkThreads) {
-          const int r = i / kJR, c = i - r * kJR;
-          S.J[r][c] = Jl[(size_t)reflect101(ry0 + r, h) * pitch + reflect101(rx0 + c, w)];
-        }
-        __syncthreads();
-      }
-      a = npx - (float)inx;
-      b = npy - (float)iny;
+    int flag = 0;
+    if (ipx < -kWin || ipx >= pd.w[L] || ipy < -kWin || ipy >= pd.h[L]) {
+      flag = 1;
+    } else {
+      const float a = ppx - (float)ipx, b = ppy - (float)ipy;
+      int iw00, iw01, iw10, iw11;
       bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-      int sb[2] = {0, 0};
-      const int ox = inx - rx0, oy = iny - ry0;
+      int s11 = 0, s12 = 0, s22 = 0;
 #pragma unroll
-      for (int j = 0; j < kPxPerThread; ++j) {
-        if (tid + kLkThreads * j < kWin * kWin) {
-          const uint8_t* jp = &S.J[oy + wy[j]][ox + wx[j]];
+      for (int j = 0; j < kPxPerLane; ++j) {
+        const int kk = lane + 32 * j;
+        int iv = 0, ix = 0, iy = 0;
+        if (kk < kWin * kWin) {
+          const int y = kk / kWin, x = kk - y * kWin;
+          iv = descale(S.I[L][y + 1][x + 1] * iw00 + S.I[L][y + 1][x + 2] * iw01 +
+                           S.I[L][y + 2][x + 1] * iw10 + S.I[L][y + 2][x + 2] * iw11,
+                       kWBits - 5);
+          const short2 d00 = S.D[L][y][x], d01 = S.D[L][y][x + 1], d10 = S.D[L][y + 1][x],
+                       d11 = S.D[L][y + 1][x + 1];
+          ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, kWBits);
+          iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, kWBits);
+          s11 += ix * ix;
+          s12 += ix * iy;
+          s22 += iy * iy;
+        }
+        S.Tw[L][kk] = (short)iv;
+        S.Tx[L][kk] = (short)ix;
+        S.Ty[L][kk] = (short)iy;
+      }
+      const float A11 = (float)warp_sum_exact(s11) * flt_scale;
+      const float A12 = (float)warp_sum_exact(s12) * flt_scale;
+      const float A22 = (float)warp_sum_exact(s22) * flt_scale;
+      const float D = A11 * A22 - A12 * A12;
+      const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) /
+                            (float)(2 * kWin * kWin);
+      if ((double)min_eig < 1e-4 || D < FLT_EPSILON) flag = 2;
+      if (lane == 0) {
+        S.A[L][0] = A11;
+        S.A[L][1] = A12;
+        S.A[L][2] = A22;
+      }
+    }
+    if (lane == 0) S.flag[L] = flag;
+  }
+  __syncthreads();
+  // ---- phase 4: warp 0 iterates, coarse to fine
+  if (warp == 0) {
+    float2 np = use_init ? init : make_float2(0.f, 0.f);
+    int st = 1;
+    const double eps2 = 0.01 * 0.01;
+    int joff[kPxPerLane];
+#pragma unroll
+    for (int j = 0; j < kPxPerLane; ++j) {
+      const int kk = lane + 32 * j;
+      const int y = kk / kWin, x = kk - y * kWin;
+      joff[j] = kk < kWin * kWin ? y * kJR + x : 0;
+    }
+    for (int level = top; level >= 0; --level) {
+      const int w = pd.w[level], h = pd.h[level], pitch = pd.pitch[level];
+      const uint8_t* __restrict__ Jl = J + pd.off[level];
+      const float sc = 1.f / (float)(1 << level);
+      if (level == top) {
+        if (use_init) {
+          np.x *= sc;
+          np.y *= sc;
+        } else {
+          np.x = p0.x * sc;
+          np.y = p0.y * sc;
+        }
+      } else {
+        np.x *= 2.f;
+        np.y *= 2.f;
+      }
+      if (S.flag[level] != 0) {
+        if (level == 0) st = 0;
+        continue;
+      }
+      const float A11 = S.A[level][0], A12 = S.A[level][1], A22 = S.A[level][2];
+      const float D = 1.f / (A11 * A22 - A12 * A12);
+      int Iw[kPxPerLane], Dx[kPxPerLane], Dy[kPxPerLane];
+#pragma unroll
+      for (int j = 0; j < kPxPerLane; ++j) {
+        const int kk = lane + 32 * j;
+        Iw[j] = S.Tw[level][kk];
+        Dx[j] = S.Tx[level][kk];  // zero beyond the 441st pixel: those lanes add nothing
+        Dy[j] = S.Ty[level][kk];
+      }
+      float npx = np.x - half, npy = np.y - half;
+      int rx0 = 0, ry0 = 0;
+      bool staged = false;
+      float pdx = 0.f, pdy = 0.f;
+      for (int it = 0; it < 30; ++it) {
+        const int inx = (int)floorf(npx), iny = (int)floorf(npy);
+        if (inx < -kWin || inx >= w || iny < -kWin || iny >= h) {
+          if (level == 0) st = 0;
+          break;
+        }
+        if (!staged || inx < rx0 || iny < ry0 || inx + kWin > rx0 + kJR - 1 ||
+            iny + kWin > ry0 + kJR - 1) {
+          rx0 = inx - kJM;
+          ry0 = iny - kJM;
+          __syncwarp();
+          stage_J(S, Jl, w, h, pitch, rx0, ry0);
+          staged = true;
+        }
+        const float a = npx - (float)inx, b = npy - (float)iny;
+        int iw00, iw01, iw10, iw11;
+        bilinear_weights(a, b, iw00, iw01, iw10, iw11);
+        const uint8_t* base = &S.J[iny - ry0][inx - rx0];
+        int sb1 = 0, sb2 = 0;
+#pragma unroll
+        for (int j = 0; j < kPxPerLane; ++j) {
+          const uint8_t* jp = base + joff[j];
           const int v = jp[0] * iw00 + jp[1] * iw01 + jp[kJR] * iw10 + jp[kJR + 1] * iw11;
           const int diff = descale(v, kWBits - 5) - Iw[j];
-          sb[0] += diff * Dx[j];
-          sb[1] += diff * Dy[j];
+          sb1 += diff * Dx[j];
+          sb2 += diff * Dy[j];
         }
+        const float b1 = (float)warp_sum_exact(sb1) * flt_scale;
+        const float b2 = (float)warp_sum_exact(sb2) * flt_scale;
+        const float dx = (A12 * b2 - A22 * b1) * D;
+        const float dy = (A12 * b1 - A11 * b2) * D;
+        npx += dx;
+        npy += dy;
+        np.x = npx + half;
+        np.y = npy + half;
+        if ((double)dx * (double)dx + (double)dy * (double)dy <= eps2) break;
+        if (it > 0 && (double)fabsf(dx + pdx) < 0.01 && (double)fabsf(dy + pdy) < 0.01) {
+          np.x -= dx * 0.5f;
+          np.y -= dy * 0.5f;
+          break;
+        }
+        pdx = dx;
+        pdy = dy;
       }
-      long long tb[2];
-      cta_sum_exact<2>(S, buf, sb, tb);
-      buf ^= 1;
-      const float b1 = (float)tb[0] * flt_scale;
-      const float b2 = (float)tb[1] * flt_scale;
-      const float dx = (A12 * b2 - A22 * b1) * D;
-      const float dy = (A12 * b1 - A11 * b2) * D;
-      npx += dx;
-      npy += dy;
-      np.x = npx + half;
-      np.y = npy + half;
-      if ((double)dx * (double)dx + (double)dy * (double)dy <= eps2) break;
-      if (it > 0 && (double)fabsf(dx + pdx) < 0.01 && (double)fabsf(dy + pdy) < 0.01) {
-        np.x -= dx * 0.5f;
-        np.y -= dy * 0.5f;
-        break;
+      if (st && level == 0) {
+        // the reference passes an `err` vector, so OpenCV re-validates the final window
+        const int inx = (int)floorf(np.x - half), iny = (int)floorf(np.y - half);
+        if (inx < -kWin || inx >= w || iny < -kWin || iny >= h) st = 0;
       }
-      pdx = dx;
-      pdy = dy;
     }
-    if (st && level == 0) {
-      // the reference passes an `err` vector, so OpenCV re-validates the final window
-      const int inx = (int)floorf(np.x - half), iny = (int)floorf(np.y - half);
-      if (inx < -kWin || inx >= w || iny < -kWin || iny >= h) st = 0;
+    if (lane == 0) {
+      S.np = np;
+      S.st = st;
     }
   }
-  np_out = np;
-  st_out = st;
+  __syncthreads();
+  np_out = S.np;
+  st_out = S.st;
 }
 
 // mode 0: forward only (next = LK(I->J, prev[, init = next]))
