@@ -32,13 +32,19 @@ struct esvio_fe {
   double2 *sae, *lat;  // [2][H][W]
   CUtensorMap map_sae, map_lat;
   PyrDesc pd;
-  uint8_t* pyr[5];  // 0/1 left ping-pong, 2 right, 3/4 scratch for esvio_fe_stage_lk
-  int cur_left;     // index of the current left pyramid (0/1); prev = 1 - cur_left
+  // Pyramid buffers: 0..2 left (triple-buffered: window k+1's event stage writes one while
+  // window k's LK still reads the other two), 3..4 right, 5..6 scratch for esvio_fe_stage_lk
+  uint8_t* pyr[7];
+  int cur_left;   // index (0..2) of the newest left pyramid; prev_left is the one before it
+  int prev_left;
+  int cur_right;  // 3 or 4
   int windows;      // windows processed since create/reset
   int cap;          // events per camera per window
-  uint8_t* raw[2];  // 16 B * cap per camera: SoA carve-out or dvs_msgs::Event records
+  uint8_t* raw[2][2];  // [slot][camera] 16 B * cap: SoA carve-out or dvs_msgs::Event records
   EventStageBuffers esb;
-  uint8_t* flags;
+  uint8_t* flags[2];   // [slot] Arc* corner flags of the left events
+  cudaStream_t stream_e;  // event stage (H2D, binning, SAE/TS, pyramids, corner flags)
+  cudaEvent_t e_done[2];  // [slot] event stage of that window finished
   TrackBuffers tb;
   TrackParams tp;
   int32_t* h_result[2];
@@ -51,7 +57,7 @@ struct esvio_fe {
   int q_head, q_count;  // in-flight windows (results land in h_result[(q_head + k) & 1])
   cudaEvent_t q_done[2];
   int profiling;
-  cudaEvent_t pev[2][ESVIO_FE_NUM_STAGES + 1];  // one set per in-flight slot
+  cudaEvent_t pev[2][ESVIO_FE_NUM_STAGES + 2];  // one set per in-flight slot; last = T start
   int pev_slot;
   int pev_valid[2];
   int stage_ms_valid;
@@ -161,12 +167,16 @@ static int make_state_map(esvio_fe* fe, double2* base, CUtensorMap* map) {
 static void free_all(esvio_fe* fe) {
   if (!fe) return;
   cudaSetDevice(fe->dev);
+  if (fe->stream_e) cudaStreamSynchronize(fe->stream_e);
   if (fe->stream) cudaStreamSynchronize(fe->stream);
   cudaFree(fe->sae);
   cudaFree(fe->lat);
-  for (int i = 0; i < 5; ++i) cudaFree(fe->pyr[i]);
+  for (int i = 0; i < 7; ++i) cudaFree(fe->pyr[i]);
   for (int i = 0; i < 2; ++i) {
-    cudaFree(fe->raw[i]);
+    cudaFree(fe->raw[i][0]);
+    cudaFree(fe->raw[i][1]);
+    cudaFree(fe->flags[i]);
+    if (fe->e_done[i]) cudaEventDestroy(fe->e_done[i]);
     cudaFree(fe->esb.bt[i]);
     cudaFree(fe->esb.bk[i]);
     if (fe->h_result[i]) cudaFreeHost(fe->h_result[i]);
@@ -175,7 +185,6 @@ static void free_all(esvio_fe* fe) {
   cudaFree(fe->esb.counts);
   cudaFree(fe->esb.bin_total);
   cudaFree(fe->esb.bin_start);
-  cudaFree(fe->flags);
   cudaFree(fe->tb.st);
   cudaFree(fe->tb.prev_pts);
   cudaFree(fe->tb.ids);
@@ -187,8 +196,9 @@ static void free_all(esvio_fe* fe) {
   cudaFree(fe->d_scratch_p0);
   cudaFree(fe->d_scratch_st);
   for (int k = 0; k < 2; ++k)
-    for (int i = 0; i <= ESVIO_FE_NUM_STAGES; ++i)
+    for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 1; ++i)
       if (fe->pev[k][i]) cudaEventDestroy(fe->pev[k][i]);
+  if (fe->stream_e) cudaStreamDestroy(fe->stream_e);
   if (fe->stream) cudaStreamDestroy(fe->stream);
   free(fe);
 }
@@ -197,11 +207,12 @@ static int reset_state(esvio_fe* fe) {
   const size_t plane = fe->npx * 2 * sizeof(double2);
   CU(cudaMemsetAsync(fe->sae, 0, plane, fe->stream));
   CU(cudaMemsetAsync(fe->lat, 0, plane, fe->stream));
-  for (int i = 0; i < 5; ++i) CU(cudaMemsetAsync(fe->pyr[i], 0, fe->pd.bytes, fe->stream));
+  for (int i = 0; i < 7; ++i) CU(cudaMemsetAsync(fe->pyr[i], 0, fe->pd.bytes, fe->stream));
   CU(cudaMemsetAsync(fe->tb.st, 0, sizeof(TrackState), fe->stream));
   CU(cudaMemsetAsync(fe->tb.result, 0, fe->result_words * 4, fe->stream));
   CU(cudaStreamSynchronize(fe->stream));
-  fe->cur_left = 0;
+  fe->cur_left = fe->prev_left = 0;
+  fe->cur_right = 3;
   fe->windows = 0;
   fe->prev_time = 0.0;
   fe->q_head = fe->q_count = 0;
@@ -254,6 +265,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     return ESVIO_FE_ENODEV;
   }
   CUC(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&fe->stream_e, cudaStreamNonBlocking));
 
   BinLayout& L = fe->bl;
   L.W = fe->W;
@@ -268,16 +280,18 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   CUC(cudaMalloc(&fe->sae, fe->npx * 2 * sizeof(double2)));
   CUC(cudaMalloc(&fe->lat, fe->npx * 2 * sizeof(double2)));
   build_pyr_desc(fe->W, fe->H, &fe->pd);
-  for (int i = 0; i < 5; ++i) CUC(cudaMalloc(&fe->pyr[i], fe->pd.bytes));
+  for (int i = 0; i < 7; ++i) CUC(cudaMalloc(&fe->pyr[i], fe->pd.bytes));
   for (int c = 0; c < 2; ++c) {
-    CUC(cudaMalloc(&fe->raw[c], (size_t)fe->cap * 16));
+    CUC(cudaMalloc(&fe->raw[c][0], (size_t)fe->cap * 16));
+    CUC(cudaMalloc(&fe->raw[c][1], (size_t)fe->cap * 16));
+    CUC(cudaMalloc(&fe->flags[c], (size_t)fe->cap + 16));
+    CUC(cudaEventCreateWithFlags(&fe->e_done[c], cudaEventDisableTiming));
     CUC(cudaMalloc(&fe->esb.bt[c], (size_t)fe->cap * sizeof(double)));
     CUC(cudaMalloc(&fe->esb.bk[c], (size_t)fe->cap * sizeof(uint16_t)));
   }
   CUC(cudaMalloc(&fe->esb.counts, (size_t)2 * nb * L.max_chunks * sizeof(uint32_t)));
   CUC(cudaMalloc(&fe->esb.bin_total, (size_t)2 * nb * sizeof(uint32_t)));
   CUC(cudaMalloc(&fe->esb.bin_start, (size_t)2 * (nb + 1) * sizeof(uint32_t)));
-  CUC(cudaMalloc(&fe->flags, (size_t)fe->cap + 16));
 
   const int M = cfg->max_cnt;
   TrackBuffers& B = fe->tb;
@@ -330,7 +344,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   fe->d_scratch_p1 = fe->d_scratch_p0 + kMaxCnt;
   CUC(cudaMalloc(&fe->d_scratch_st, kMaxCnt));
   for (int k = 0; k < 2; ++k)
-    for (int i = 0; i <= ESVIO_FE_NUM_STAGES; ++i) CUC(cudaEventCreate(&fe->pev[k][i]));
+    for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 1; ++i) CUC(cudaEventCreate(&fe->pev[k][i]));
 #undef CUC
 
   TrackParams& P = fe->tp;
@@ -367,17 +381,23 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
 
 FE_API void esvio_fe_destroy(esvio_fe* fe) { free_all(fe); }
 
+static int sync_all(esvio_fe* fe) {
+  CU(cudaStreamSynchronize(fe->stream_e));
+  CU(cudaStreamSynchronize(fe->stream));
+  return ESVIO_FE_OK;
+}
+
 FE_API int esvio_fe_reset(esvio_fe* fe) {
   if (!fe) return ESVIO_FE_EINVAL;
   CU(cudaSetDevice(fe->dev));
-  CU(cudaStreamSynchronize(fe->stream));
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
   return reset_state(fe);
 }
 
 // ---------------------------------------------------------------------------------------
 // event staging
 // ---------------------------------------------------------------------------------------
-static int stage_events(esvio_fe* fe, int cam, const esvio_events* e, DevEvents* d) {
+static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, DevEvents* d) {
   memset(d, 0, sizeof(*d));
   if (!e || e->n == 0) return ESVIO_FE_OK;
   if (e->n > (size_t)fe->cap) return fail(fe, ESVIO_FE_ECAPACITY, "events > max_events_per_window", cudaSuccess);
@@ -389,33 +409,40 @@ static int stage_events(esvio_fe* fe, int cam, const esvio_events* e, DevEvents*
     else d->x = e->x, d->y = e->y, d->t = e->t, d->p = e->p;
     return ESVIO_FE_OK;
   }
-  uint8_t* raw = fe->raw[cam];
+  uint8_t* raw = fe->raw[slot][cam];
+  cudaStream_t se = fe->stream_e;
   const size_t n = e->n, cap = (size_t)fe->cap;
   if (e->aos) {
-    CU(cudaMemcpyAsync(raw, e->aos, n * 16, cudaMemcpyHostToDevice, fe->stream));
+    CU(cudaMemcpyAsync(raw, e->aos, n * 16, cudaMemcpyHostToDevice, se));
     d->aos = (const uint4*)raw;
   } else {
     uint16_t* dx = (uint16_t*)raw;
     uint16_t* dy = (uint16_t*)(raw + 2 * cap);
     double* dt = (double*)(raw + 4 * cap);
     uint8_t* dp = raw + 12 * cap;
-    CU(cudaMemcpyAsync(dx, e->x, n * 2, cudaMemcpyHostToDevice, fe->stream));
-    CU(cudaMemcpyAsync(dy, e->y, n * 2, cudaMemcpyHostToDevice, fe->stream));
-    CU(cudaMemcpyAsync(dt, e->t, n * 8, cudaMemcpyHostToDevice, fe->stream));
-    CU(cudaMemcpyAsync(dp, e->p, n, cudaMemcpyHostToDevice, fe->stream));
+    CU(cudaMemcpyAsync(dx, e->x, n * 2, cudaMemcpyHostToDevice, se));
+    CU(cudaMemcpyAsync(dy, e->y, n * 2, cudaMemcpyHostToDevice, se));
+    CU(cudaMemcpyAsync(dt, e->t, n * 8, cudaMemcpyHostToDevice, se));
+    CU(cudaMemcpyAsync(dp, e->p, n, cudaMemcpyHostToDevice, se));
     d->x = dx, d->y = dy, d->t = dt, d->p = dp;
   }
   return ESVIO_FE_OK;
 }
 
+// markers 0..5 are recorded on the event-stage stream, ESVIO_FE_NUM_STAGES+1 (start of the
+// tracking stage) and 6..9 on the tracking stream
 static void prof_mark(esvio_fe* fe, int i) {
-  if (fe->profiling) cudaEventRecord(fe->pev[fe->pev_slot][i], fe->stream);
+  if (fe->profiling)
+    cudaEventRecord(fe->pev[fe->pev_slot][i],
+                    (i <= 5) ? fe->stream_e : fe->stream);
 }
 
 // createSAE_* + SAEtoTimeSurface_* + pyramids (feature_tracker.cpp:356-368) into the
 // pyramid buffers `left_idx` / right
-static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev[2], int left_idx) {
-  launch_bin_events(fe->bl, fe->esb, ev, fe->stream, &fe->launches);
+static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev[2], int left_idx,
+                           int right_idx) {
+  cudaStream_t se = fe->stream_e;
+  launch_bin_events(fe->bl, fe->esb, ev, se, &fe->launches);
   prof_mark(fe, 2);
   SaeTsParams sp;
   sp.W = fe->W;
@@ -432,12 +459,12 @@ static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev[2], in
   sp.bk[0] = fe->esb.bk[0];
   sp.bk[1] = fe->esb.bk[1];
   sp.ts[0] = fe->pyr[left_idx];
-  sp.ts[1] = fe->pyr[2];
+  sp.ts[1] = fe->pyr[right_idx];
   sp.ts_pitch = fe->pd.pitch[0];
-  launch_sae_update_ts(sp, fe->map_sae, fe->map_lat, fe->stream, &fe->launches);
+  launch_sae_update_ts(sp, fe->map_sae, fe->map_lat, se, &fe->launches);
   prof_mark(fe, 3);
-  uint8_t* imgs[2] = {fe->pyr[left_idx], fe->pyr[2]};
-  launch_pyramids(fe->pd, imgs, 2, fe->stream, &fe->launches);
+  uint8_t* imgs[2] = {fe->pyr[left_idx], fe->pyr[right_idx]};
+  launch_pyramids(fe->pd, imgs, 2, se, &fe->launches);
   CU(cudaGetLastError());
   return ESVIO_FE_OK;
 }
@@ -462,39 +489,46 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   if (!fe) return ESVIO_FE_EINVAL;
   if (fe->q_count >= 2) return fail(fe, ESVIO_FE_ESTATE, "two windows already in flight", cudaSuccess);
   CU(cudaSetDevice(fe->dev));
-  cudaStream_t s = fe->stream;
+  cudaStream_t se = fe->stream_e, s = fe->stream;
   const int slot = (fe->q_head + fe->q_count) & 1;
   fe->pev_slot = slot;
+  // ---------------- event stage, stream_e: overlaps the tracking stage of the previous window.
+  // Buffer rotation makes that safe with at most two windows in flight: this window writes
+  // raw[slot], flags[slot], left pyramid (cur_left+1)%3 and the other right pyramid, none of
+  // which the previous window's tracking stage reads.
   prof_mark(fe, 0);
   DevEvents ev[2];
   int rc;
-  if ((rc = stage_events(fe, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
-  if ((rc = stage_events(fe, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
+  if ((rc = stage_events(fe, slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
+  if ((rc = stage_events(fe, slot, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
   prof_mark(fe, 1);
-
-  const int cur = fe->windows == 0 ? 0 : 1 - fe->cur_left;
+  const int cur = fe->windows == 0 ? 0 : (fe->cur_left + 1) % 3;
   const int prev = fe->windows == 0 ? 0 : fe->cur_left;  // first window: prev_img = cur_img
-  if ((rc = run_event_stage(fe, cur_time, ev, cur)) != ESVIO_FE_OK) return rc;
+  const int rcur = fe->windows == 0 ? 3 : (fe->cur_right == 3 ? 4 : 3);
+  if ((rc = run_event_stage(fe, cur_time, ev, cur, rcur)) != ESVIO_FE_OK) return rc;
   prof_mark(fe, 4);
-  if (pub_this_frame) {
-    launch_corner_flags(corner_params(fe, cur, 1), ev[0], fe->flags, s, &fe->launches);
-  }
+  if (pub_this_frame)
+    launch_corner_flags(corner_params(fe, cur, 1), ev[0], fe->flags[slot], se, &fe->launches);
   prof_mark(fe, 5);
+  CU(cudaEventRecord(fe->e_done[slot], se));
 
+  // ---------------- tracking stage, stream (in order behind the previous window's)
+  CU(cudaStreamWaitEvent(s, fe->e_done[slot], 0));
+  prof_mark(fe, ESVIO_FE_NUM_STAGES + 1);
   const TrackBuffers& B = fe->tb;
   const int M = fe->cfg.max_cnt;
-  // temporal LK (feature_tracker.cpp:405-437)
+  // temporal LK + backward check (feature_tracker.cpp:405-437)
   launch_lk(fe->pd, fe->pyr[prev], fe->pyr[cur], B.prev_pts, B.cur_pts, B.st_fwd, B.rev_pts,
             B.st_bwd, &B.st->n_prev, M, 3, 0, fe->cfg.flow_back ? 1 : 0, s, &fe->launches);
   launch_post_temporal(fe->tp, B, s, &fe->launches);
   prof_mark(fe, 6);
   if (pub_this_frame) {
     if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s, &fe->launches);
-    launch_select(fe->tp, B, ev[0], fe->flags, s, &fe->launches);
+    launch_select(fe->tp, B, ev[0], fe->flags[slot], s, &fe->launches);
   }
   prof_mark(fe, 7);
-  // stereo LK (feature_tracker.cpp:475-510)
-  launch_lk(fe->pd, fe->pyr[cur], fe->pyr[2], B.cur_pts, B.right_pts, B.st_sf, B.rev_left_pts,
+  // stereo LK + backward check (feature_tracker.cpp:475-510)
+  launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.cur_pts, B.right_pts, B.st_sf, B.rev_left_pts,
             B.st_sb, &B.st->n_cur, M, 3, 0, fe->cfg.flow_back ? 2 : 0, s, &fe->launches);
   launch_finalize(fe->tp, B, cur_time, fe->prev_time, s, &fe->launches);
   prof_mark(fe, 8);
@@ -503,7 +537,9 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   CU(cudaEventRecord(fe->q_done[slot], s));
   CU(cudaGetLastError());
   fe->q_count++;
+  fe->prev_left = prev;
   fe->cur_left = cur;
+  fe->cur_right = rcur;
   fe->windows++;
   fe->prev_time = cur_time;
   fe->pev_valid[slot] = fe->profiling;
@@ -543,7 +579,9 @@ FE_API int esvio_fe_track_wait(esvio_fe* fe, esvio_tracks* out) {
   s.ransac_iters = r[8];
   if (fe->pev_valid[slot]) {
     for (int i = 0; i < ESVIO_FE_NUM_STAGES; ++i)
-      cudaEventElapsedTime(&fe->stage_ms[i], fe->pev[slot][i], fe->pev[slot][i + 1]);
+      cudaEventElapsedTime(&fe->stage_ms[i],
+                           fe->pev[slot][i == 5 ? ESVIO_FE_NUM_STAGES + 1 : i],
+                           fe->pev[slot][i + 1]);
     fe->stage_ms_valid = 1;
     fe->pev_valid[slot] = 0;
   }
@@ -562,7 +600,8 @@ FE_API int esvio_fe_track(esvio_fe* fe, double cur_time, const esvio_events* lef
 FE_API int esvio_fe_time_surface(esvio_fe* fe, int32_t cam, uint8_t* dst, size_t stride) {
   if (!fe || !dst || cam < 0 || cam > 1 || stride < (size_t)fe->W) return ESVIO_FE_EINVAL;
   CU(cudaSetDevice(fe->dev));
-  const uint8_t* src = fe->pyr[cam == 0 ? fe->cur_left : 2];
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
+  const uint8_t* src = fe->pyr[cam == 0 ? fe->cur_left : fe->cur_right];
   CU(cudaMemcpy2DAsync(dst, stride, src, fe->pd.pitch[0], fe->W, fe->H, cudaMemcpyDeviceToHost,
                        fe->stream));
   CU(cudaStreamSynchronize(fe->stream));
@@ -637,7 +676,7 @@ FE_API int esvio_fe_kernel_launches(esvio_fe* fe, int64_t* count) {
 FE_API int esvio_fe_get_sae(esvio_fe* fe, int32_t cam, int32_t plane, double* dst) {
   if (!fe || !dst || cam < 0 || cam > 1 || plane < 0 || plane > 3) return ESVIO_FE_EINVAL;
   CU(cudaSetDevice(fe->dev));
-  CU(cudaStreamSynchronize(fe->stream));
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
   const double2* base = (plane < 2 ? fe->sae : fe->lat) + (size_t)cam * fe->npx;
   const char* src = (const char*)base + (plane & 1) * sizeof(double);
   // strided gather of one double per pixel
@@ -653,10 +692,11 @@ FE_API int esvio_fe_stage_update(esvio_fe* fe, double t_ref, const esvio_events*
   CU(cudaSetDevice(fe->dev));
   DevEvents ev[2];
   int rc;
-  if ((rc = stage_events(fe, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
-  if ((rc = stage_events(fe, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
-  if ((rc = run_event_stage(fe, t_ref, ev, fe->cur_left)) != ESVIO_FE_OK) return rc;
-  CU(cudaStreamSynchronize(fe->stream));
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
+  if ((rc = stage_events(fe, 0, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
+  if ((rc = stage_events(fe, 0, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, t_ref, ev, fe->cur_left, fe->cur_right)) != ESVIO_FE_OK) return rc;
+  CU(cudaStreamSynchronize(fe->stream_e));
   return ESVIO_FE_OK;
 }
 
@@ -667,13 +707,14 @@ FE_API int esvio_fe_stage_corner_flags(esvio_fe* fe, const esvio_events* left, i
   CU(cudaSetDevice(fe->dev));
   DevEvents ev;
   int rc;
-  if ((rc = stage_events(fe, 0, left, &ev)) != ESVIO_FE_OK) return rc;
-  launch_corner_flags(corner_params(fe, fe->cur_left, and_ts_test), ev, fe->flags, fe->stream,
-                      &fe->launches);
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
+  if ((rc = stage_events(fe, 0, 0, left, &ev)) != ESVIO_FE_OK) return rc;
+  launch_corner_flags(corner_params(fe, fe->cur_left, and_ts_test), ev, fe->flags[0],
+                      fe->stream_e, &fe->launches);
   CU(cudaGetLastError());
   if (ev.n > 0)
-    CU(cudaMemcpyAsync(flags, fe->flags, ev.n, cudaMemcpyDeviceToHost, fe->stream));
-  CU(cudaStreamSynchronize(fe->stream));
+    CU(cudaMemcpyAsync(flags, fe->flags[0], ev.n, cudaMemcpyDeviceToHost, fe->stream_e));
+  CU(cudaStreamSynchronize(fe->stream_e));
   return ESVIO_FE_OK;
 }
 
@@ -684,7 +725,8 @@ FE_API int esvio_fe_get_pyramid_level(esvio_fe* fe, int32_t which, int32_t level
   if (w) *w = fe->pd.w[level];
   if (h) *h = fe->pd.h[level];
   if (!dst) return ESVIO_FE_OK;
-  const int idx = which == 0 ? fe->cur_left : (which == 1 ? 2 : 1 - fe->cur_left);
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
+  const int idx = which == 0 ? fe->cur_left : (which == 1 ? fe->cur_right : fe->prev_left);
   CU(cudaMemcpy2DAsync(dst, fe->pd.w[level], fe->pyr[idx] + fe->pd.off[level], fe->pd.pitch[level],
                        fe->pd.w[level], fe->pd.h[level], cudaMemcpyDeviceToHost, fe->stream));
   CU(cudaStreamSynchronize(fe->stream));
@@ -700,17 +742,17 @@ FE_API int esvio_fe_stage_lk(esvio_fe* fe, const uint8_t* prev_img, const uint8_
   if (n == 0) return ESVIO_FE_OK;
   CU(cudaSetDevice(fe->dev));
   cudaStream_t s = fe->stream;
-  CU(cudaMemcpy2DAsync(fe->pyr[3], fe->pd.pitch[0], prev_img, fe->W, fe->W, fe->H,
+  CU(cudaMemcpy2DAsync(fe->pyr[5], fe->pd.pitch[0], prev_img, fe->W, fe->W, fe->H,
                        cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpy2DAsync(fe->pyr[4], fe->pd.pitch[0], next_img, fe->W, fe->W, fe->H,
+  CU(cudaMemcpy2DAsync(fe->pyr[6], fe->pd.pitch[0], next_img, fe->W, fe->W, fe->H,
                        cudaMemcpyHostToDevice, s));
-  uint8_t* imgs[2] = {fe->pyr[3], fe->pyr[4]};
+  uint8_t* imgs[2] = {fe->pyr[5], fe->pyr[6]};
   launch_pyramids(fe->pd, imgs, 2, s, &fe->launches);
   CU(cudaMemcpyAsync(fe->d_scratch_n, &n, sizeof(int), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(fe->d_scratch_p0, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
   if (use_initial_flow)
     CU(cudaMemcpyAsync(fe->d_scratch_p1, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
-  launch_lk(fe->pd, fe->pyr[3], fe->pyr[4], fe->d_scratch_p0, fe->d_scratch_p1, fe->d_scratch_st,
+  launch_lk(fe->pd, fe->pyr[5], fe->pyr[6], fe->d_scratch_p0, fe->d_scratch_p1, fe->d_scratch_st,
             nullptr, nullptr, fe->d_scratch_n, n, max_level, use_initial_flow, 0, s, &fe->launches);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(next_pts, fe->d_scratch_p1, sizeof(float2) * n, cudaMemcpyDeviceToHost, s));
@@ -752,7 +794,9 @@ FE_API int esvio_fe_stage_select(esvio_fe* fe, const esvio_events* left, int32_t
   const TrackBuffers& B = fe->tb;
   DevEvents ev;
   int rc;
-  if ((rc = stage_events(fe, 0, left, &ev)) != ESVIO_FE_OK) return rc;
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
+  if ((rc = stage_events(fe, 0, 0, left, &ev)) != ESVIO_FE_OK) return rc;
+  CU(cudaStreamSynchronize(fe->stream_e));
   TrackState st;
   CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -763,8 +807,8 @@ FE_API int esvio_fe_stage_select(esvio_fe* fe, const esvio_events* left, int32_t
     CU(cudaMemcpyAsync(B.ids, ids, sizeof(int) * n, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(B.cnt, track_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, s));
   }
-  launch_corner_flags(corner_params(fe, fe->cur_left, 1), ev, fe->flags, s, &fe->launches);
-  launch_select(fe->tp, B, ev, fe->flags, s, &fe->launches);
+  launch_corner_flags(corner_params(fe, fe->cur_left, 1), ev, fe->flags[0], s, &fe->launches);
+  launch_select(fe->tp, B, ev, fe->flags[0], s, &fe->launches);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
