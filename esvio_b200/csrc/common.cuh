@@ -26,6 +26,7 @@ constexpr int kMaxLevels = 4;                 // maxLevel = 3 (feature_tracker.c
 constexpr int kWin = 21;                      // cv::Size(21, 21)
 constexpr int kHalfWin = 10;
 constexpr int kMaxCnt = 1024;                 // hard cap on MAX_CNT
+constexpr int kSlots = 3;                     // windows in flight (event / temporal / stereo stage)
 constexpr int kResultHdr = 32;                // int32 words in front of the result arrays
 constexpr int kResultArrays = 15;
 
@@ -224,6 +225,14 @@ struct TrackBuffers {
   int* prev_un_r_ids;
   float2* prev_un_r;
   int32_t* result;  // kResultHdr ints + kResultArrays * max_cnt words
+  // snapshot of (cur_pts, ids, track_cnt, counters) taken at the end of the temporal/selection
+  // stage of a window, one per in-flight slot: the stereo stage of window k reads it while
+  // the temporal stage of window k+1 already rewrites cur_pts / ids / cnt
+  float2* snap_pts;  // [kSlots][max_cnt]
+  int* snap_ids;     // [kSlots][max_cnt]
+  int* snap_cnt;     // [kSlots][max_cnt]
+  int* snap_hdr;     // [kSlots][16]: n, stat_n_prev, after_temporal, after_ransac, after_mask,
+                     //               new, corner_flags, ransac_iters, next_id
   void* rs;                   // RansacScratch (ransac.cu)
   const uint32_t* rng_draws;  // first ransac_num_draws() raw outputs of cv::RNG(-1)
 };
@@ -238,7 +247,9 @@ void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, cudaStrea
                           int64_t* launches);
 void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents& left,
                    const uint8_t* flags, cudaStream_t s, int64_t* launches);
-void launch_finalize(const TrackParams& P, const TrackBuffers& B, double cur_time,
+void launch_snapshot(const TrackParams& P, const TrackBuffers& B, int slot, cudaStream_t s,
+                     int64_t* launches);
+void launch_finalize(const TrackParams& P, const TrackBuffers& B, int slot, double cur_time,
                      double prev_time, cudaStream_t s, int64_t* launches);
 void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
                    int64_t* launches);

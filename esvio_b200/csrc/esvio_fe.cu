@@ -32,34 +32,39 @@ struct esvio_fe {
   double2 *sae, *lat;  // [2][H][W]
   CUtensorMap map_sae, map_lat;
   PyrDesc pd;
-  // Pyramid buffers: 0..2 left (triple-buffered: window k+1's event stage writes one while
-  // window k's LK still reads the other two), 3..4 right, 5..6 scratch for esvio_fe_stage_lk
-  uint8_t* pyr[7];
+  // Pyramid buffers: 0..2 left, 3..5 right (rotating: up to three windows are in flight, one
+  // per pipeline stage), 6..7 scratch for esvio_fe_stage_lk
+  uint8_t* pyr[8];
   int cur_left;   // index (0..2) of the newest left pyramid; prev_left is the one before it
   int prev_left;
-  int cur_right;  // 3 or 4
+  int cur_right;  // 3..5
   int windows;      // windows processed since create/reset
   int cap;          // events per camera per window
-  uint8_t* raw[2][2];  // [slot][camera] 16 B * cap: SoA carve-out or dvs_msgs::Event records
+  uint8_t* raw[kSlots][2];  // [slot][camera] 16 B * cap: SoA carve-out or dvs_msgs::Event records
   EventStageBuffers esb;
-  uint8_t* flags[2];   // [slot] Arc* corner flags of the left events
-  cudaStream_t stream_e;  // event stage (H2D, binning, SAE/TS, pyramids, corner flags)
-  cudaEvent_t e_done[2];  // [slot] event stage of that window finished
+  uint8_t* flags[kSlots];   // [slot] Arc* corner flags of the left events
+  // Three pipeline stages, one stream each; `stream` (stereo stage, results) is the one
+  // esvio_fe_stream() hands out.
+  cudaStream_t stream_e;   // event stage: H2D, binning, SAE/TS, pyramids, corner flags
+  cudaStream_t stream_t1;  // temporal stage: temporal LK, F-RANSAC, selection
+  cudaEvent_t e_done[kSlots];   // [slot] event stage of that window finished
+  cudaEvent_t t1_done[kSlots];  // [slot] temporal stage finished
   TrackBuffers tb;
   TrackParams tp;
-  int32_t* h_result[2];
+  int32_t* h_result[kSlots];
   size_t result_words;
   int* d_scratch_n;
   float2 *d_scratch_p0, *d_scratch_p1;
   uint8_t* d_scratch_st;
   double prev_time;
   int64_t launches;
-  int q_head, q_count;  // in-flight windows (results land in h_result[(q_head + k) & 1])
-  cudaEvent_t q_done[2];
+  int q_head, q_count;  // in-flight windows (results land in h_result[(q_head + k) % kSlots])
+  cudaEvent_t q_done[kSlots];
   int profiling;
-  cudaEvent_t pev[2][ESVIO_FE_NUM_STAGES + 2];  // one set per in-flight slot; last = T start
+  // one set per in-flight slot; [NUM_STAGES+1] = temporal stage start, [+2] = stereo stage start
+  cudaEvent_t pev[kSlots][ESVIO_FE_NUM_STAGES + 3];
   int pev_slot;
-  int pev_valid[2];
+  int pev_valid[kSlots];
   int stage_ms_valid;
   float stage_ms[ESVIO_FE_NUM_STAGES];
 };
@@ -168,20 +173,27 @@ static void free_all(esvio_fe* fe) {
   if (!fe) return;
   cudaSetDevice(fe->dev);
   if (fe->stream_e) cudaStreamSynchronize(fe->stream_e);
+  if (fe->stream_t1) cudaStreamSynchronize(fe->stream_t1);
   if (fe->stream) cudaStreamSynchronize(fe->stream);
   cudaFree(fe->sae);
   cudaFree(fe->lat);
-  for (int i = 0; i < 7; ++i) cudaFree(fe->pyr[i]);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 8; ++i) cudaFree(fe->pyr[i]);
+  for (int i = 0; i < kSlots; ++i) {
     cudaFree(fe->raw[i][0]);
     cudaFree(fe->raw[i][1]);
     cudaFree(fe->flags[i]);
     if (fe->e_done[i]) cudaEventDestroy(fe->e_done[i]);
-    cudaFree(fe->esb.bt[i]);
-    cudaFree(fe->esb.bk[i]);
+    if (fe->t1_done[i]) cudaEventDestroy(fe->t1_done[i]);
     if (fe->h_result[i]) cudaFreeHost(fe->h_result[i]);
     if (fe->q_done[i]) cudaEventDestroy(fe->q_done[i]);
   }
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(fe->esb.bt[i]);
+    cudaFree(fe->esb.bk[i]);
+  }
+  cudaFree(fe->tb.snap_pts);
+  cudaFree(fe->tb.snap_ids);
+  cudaFree(fe->tb.snap_hdr);
   cudaFree(fe->esb.counts);
   cudaFree(fe->esb.bin_total);
   cudaFree(fe->esb.bin_start);
@@ -195,10 +207,11 @@ static void free_all(esvio_fe* fe) {
   cudaFree(fe->d_scratch_n);
   cudaFree(fe->d_scratch_p0);
   cudaFree(fe->d_scratch_st);
-  for (int k = 0; k < 2; ++k)
-    for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 1; ++i)
+  for (int k = 0; k < kSlots; ++k)
+    for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 2; ++i)
       if (fe->pev[k][i]) cudaEventDestroy(fe->pev[k][i]);
   if (fe->stream_e) cudaStreamDestroy(fe->stream_e);
+  if (fe->stream_t1) cudaStreamDestroy(fe->stream_t1);
   if (fe->stream) cudaStreamDestroy(fe->stream);
   free(fe);
 }
@@ -207,7 +220,8 @@ static int reset_state(esvio_fe* fe) {
   const size_t plane = fe->npx * 2 * sizeof(double2);
   CU(cudaMemsetAsync(fe->sae, 0, plane, fe->stream));
   CU(cudaMemsetAsync(fe->lat, 0, plane, fe->stream));
-  for (int i = 0; i < 7; ++i) CU(cudaMemsetAsync(fe->pyr[i], 0, fe->pd.bytes, fe->stream));
+  for (int i = 0; i < 8; ++i) CU(cudaMemsetAsync(fe->pyr[i], 0, fe->pd.bytes, fe->stream));
+  CU(cudaMemsetAsync(fe->tb.snap_hdr, 0, sizeof(int) * 16 * kSlots, fe->stream));
   CU(cudaMemsetAsync(fe->tb.st, 0, sizeof(TrackState), fe->stream));
   CU(cudaMemsetAsync(fe->tb.result, 0, fe->result_words * 4, fe->stream));
   CU(cudaStreamSynchronize(fe->stream));
@@ -216,7 +230,7 @@ static int reset_state(esvio_fe* fe) {
   fe->windows = 0;
   fe->prev_time = 0.0;
   fe->q_head = fe->q_count = 0;
-  fe->pev_valid[0] = fe->pev_valid[1] = 0;
+  for (int k = 0; k < kSlots; ++k) fe->pev_valid[k] = 0;
   fe->stage_ms_valid = 0;
   return ESVIO_FE_OK;
 }
@@ -266,6 +280,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   }
   CUC(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&fe->stream_e, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&fe->stream_t1, cudaStreamNonBlocking));
 
   BinLayout& L = fe->bl;
   L.W = fe->W;
@@ -280,12 +295,15 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   CUC(cudaMalloc(&fe->sae, fe->npx * 2 * sizeof(double2)));
   CUC(cudaMalloc(&fe->lat, fe->npx * 2 * sizeof(double2)));
   build_pyr_desc(fe->W, fe->H, &fe->pd);
-  for (int i = 0; i < 7; ++i) CUC(cudaMalloc(&fe->pyr[i], fe->pd.bytes));
-  for (int c = 0; c < 2; ++c) {
+  for (int i = 0; i < 8; ++i) CUC(cudaMalloc(&fe->pyr[i], fe->pd.bytes));
+  for (int c = 0; c < kSlots; ++c) {
     CUC(cudaMalloc(&fe->raw[c][0], (size_t)fe->cap * 16));
     CUC(cudaMalloc(&fe->raw[c][1], (size_t)fe->cap * 16));
     CUC(cudaMalloc(&fe->flags[c], (size_t)fe->cap + 16));
     CUC(cudaEventCreateWithFlags(&fe->e_done[c], cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&fe->t1_done[c], cudaEventDisableTiming));
+  }
+  for (int c = 0; c < 2; ++c) {
     CUC(cudaMalloc(&fe->esb.bt[c], (size_t)fe->cap * sizeof(double)));
     CUC(cudaMalloc(&fe->esb.bk[c], (size_t)fe->cap * sizeof(uint16_t)));
   }
@@ -320,9 +338,13 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   B.st_bwd = u4 + M;
   B.st_sf = u4 + 2 * M;
   B.st_sb = u4 + 3 * M;
+  CUC(cudaMalloc(&B.snap_pts, sizeof(float2) * (size_t)M * kSlots));
+  CUC(cudaMalloc(&B.snap_ids, sizeof(int) * (size_t)M * kSlots * 2));
+  B.snap_cnt = B.snap_ids + (size_t)M * kSlots;
+  CUC(cudaMalloc(&B.snap_hdr, sizeof(int) * 16 * kSlots));
   fe->result_words = kResultHdr + (size_t)kResultArrays * M;
   CUC(cudaMalloc(&B.result, fe->result_words * 4));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kSlots; ++i) {
     CUC(cudaHostAlloc(&fe->h_result[i], fe->result_words * 4, cudaHostAllocDefault));
     CUC(cudaEventCreateWithFlags(&fe->q_done[i], cudaEventDisableTiming));
   }
@@ -343,8 +365,8 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   CUC(cudaMalloc(&fe->d_scratch_p0, sizeof(float2) * 2 * (size_t)kMaxCnt));
   fe->d_scratch_p1 = fe->d_scratch_p0 + kMaxCnt;
   CUC(cudaMalloc(&fe->d_scratch_st, kMaxCnt));
-  for (int k = 0; k < 2; ++k)
-    for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 1; ++i) CUC(cudaEventCreate(&fe->pev[k][i]));
+  for (int k = 0; k < kSlots; ++k)
+    for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 2; ++i) CUC(cudaEventCreate(&fe->pev[k][i]));
 #undef CUC
 
   TrackParams& P = fe->tp;
@@ -383,6 +405,7 @@ FE_API void esvio_fe_destroy(esvio_fe* fe) { free_all(fe); }
 
 static int sync_all(esvio_fe* fe) {
   CU(cudaStreamSynchronize(fe->stream_e));
+  CU(cudaStreamSynchronize(fe->stream_t1));
   CU(cudaStreamSynchronize(fe->stream));
   return ESVIO_FE_OK;
 }
@@ -429,12 +452,14 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
   return ESVIO_FE_OK;
 }
 
-// markers 0..5 are recorded on the event-stage stream, ESVIO_FE_NUM_STAGES+1 (start of the
-// tracking stage) and 6..9 on the tracking stream
+// markers 0..5: event-stage stream; NUM_STAGES+1 (temporal stage start), 6, 7: temporal
+// stream; NUM_STAGES+2 (stereo stage start), 8, 9: stereo/result stream
 static void prof_mark(esvio_fe* fe, int i) {
-  if (fe->profiling)
-    cudaEventRecord(fe->pev[fe->pev_slot][i],
-                    (i <= 5) ? fe->stream_e : fe->stream);
+  if (!fe->profiling) return;
+  cudaStream_t st = fe->stream;
+  if (i <= 5) st = fe->stream_e;
+  else if (i == 6 || i == 7 || i == ESVIO_FE_NUM_STAGES + 1) st = fe->stream_t1;
+  cudaEventRecord(fe->pev[fe->pev_slot][i], st);
 }
 
 // createSAE_* + SAEtoTimeSurface_* + pyramids (feature_tracker.cpp:356-368) into the
@@ -487,15 +512,18 @@ static CornerParams corner_params(esvio_fe* fe, int left_idx, int and_ts) {
 FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_events* left,
                                  const esvio_events* right, int32_t pub_this_frame) {
   if (!fe) return ESVIO_FE_EINVAL;
-  if (fe->q_count >= 2) return fail(fe, ESVIO_FE_ESTATE, "two windows already in flight", cudaSuccess);
+  if (fe->q_count >= kSlots)
+    return fail(fe, ESVIO_FE_ESTATE, "three windows already in flight", cudaSuccess);
   CU(cudaSetDevice(fe->dev));
-  cudaStream_t se = fe->stream_e, s = fe->stream;
-  const int slot = (fe->q_head + fe->q_count) & 1;
+  cudaStream_t se = fe->stream_e, s1 = fe->stream_t1, s2 = fe->stream;
+  const int slot = (fe->q_head + fe->q_count) % kSlots;
   fe->pev_slot = slot;
-  // ---------------- event stage, stream_e: overlaps the tracking stage of the previous window.
-  // Buffer rotation makes that safe with at most two windows in flight: this window writes
-  // raw[slot], flags[slot], left pyramid (cur_left+1)%3 and the other right pyramid, none of
-  // which the previous window's tracking stage reads.
+  // A window passes through three stages, each on its own stream, so that up to three
+  // consecutive windows overlap:  event stage (k+2) | temporal stage (k+1) | stereo stage (k).
+  // Everything a later stage reads from an earlier one is either per-slot (raw events, flags,
+  // snapshot, result) or rotates over three buffers (pyramids), and a slot is only reused
+  // after esvio_fe_track_wait returned its window.
+  // ---------------- event stage
   prof_mark(fe, 0);
   DevEvents ev[2];
   int rc;
@@ -504,7 +532,7 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   prof_mark(fe, 1);
   const int cur = fe->windows == 0 ? 0 : (fe->cur_left + 1) % 3;
   const int prev = fe->windows == 0 ? 0 : fe->cur_left;  // first window: prev_img = cur_img
-  const int rcur = fe->windows == 0 ? 3 : (fe->cur_right == 3 ? 4 : 3);
+  const int rcur = fe->windows == 0 ? 3 : 3 + (fe->cur_right - 3 + 1) % 3;
   if ((rc = run_event_stage(fe, cur_time, ev, cur, rcur)) != ESVIO_FE_OK) return rc;
   prof_mark(fe, 4);
   if (pub_this_frame)
@@ -512,29 +540,34 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   prof_mark(fe, 5);
   CU(cudaEventRecord(fe->e_done[slot], se));
 
-  // ---------------- tracking stage, stream (in order behind the previous window's)
-  CU(cudaStreamWaitEvent(s, fe->e_done[slot], 0));
+  // ---------------- temporal stage (feature_tracker.cpp:405-468), in order behind window k-1's
+  CU(cudaStreamWaitEvent(s1, fe->e_done[slot], 0));
   prof_mark(fe, ESVIO_FE_NUM_STAGES + 1);
   const TrackBuffers& B = fe->tb;
   const int M = fe->cfg.max_cnt;
-  // temporal LK + backward check (feature_tracker.cpp:405-437)
   launch_lk(fe->pd, fe->pyr[prev], fe->pyr[cur], B.prev_pts, B.cur_pts, B.st_fwd, B.rev_pts,
-            B.st_bwd, &B.st->n_prev, M, 3, 0, fe->cfg.flow_back ? 1 : 0, s, &fe->launches);
-  launch_post_temporal(fe->tp, B, s, &fe->launches);
+            B.st_bwd, &B.st->n_prev, M, 3, 0, fe->cfg.flow_back ? 1 : 0, s1, &fe->launches);
+  launch_post_temporal(fe->tp, B, s1, &fe->launches);
   prof_mark(fe, 6);
   if (pub_this_frame) {
-    if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s, &fe->launches);
-    launch_select(fe->tp, B, ev[0], fe->flags[slot], s, &fe->launches);
+    if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s1, &fe->launches);
+    launch_select(fe->tp, B, ev[0], fe->flags[slot], s1, &fe->launches);
   }
+  launch_snapshot(fe->tp, B, slot, s1, &fe->launches);
   prof_mark(fe, 7);
-  // stereo LK + backward check (feature_tracker.cpp:475-510)
-  launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.cur_pts, B.right_pts, B.st_sf, B.rev_left_pts,
-            B.st_sb, &B.st->n_cur, M, 3, 0, fe->cfg.flow_back ? 2 : 0, s, &fe->launches);
-  launch_finalize(fe->tp, B, cur_time, fe->prev_time, s, &fe->launches);
+  CU(cudaEventRecord(fe->t1_done[slot], s1));
+
+  // ---------------- stereo stage (feature_tracker.cpp:470-590) on the snapshot
+  CU(cudaStreamWaitEvent(s2, fe->t1_done[slot], 0));
+  prof_mark(fe, ESVIO_FE_NUM_STAGES + 2);
+  launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.snap_pts + (size_t)slot * M, B.right_pts,
+            B.st_sf, B.rev_left_pts, B.st_sb, B.snap_hdr + slot * 16, M, 3, 0,
+            fe->cfg.flow_back ? 2 : 0, s2, &fe->launches);
+  launch_finalize(fe->tp, B, slot, cur_time, fe->prev_time, s2, &fe->launches);
   prof_mark(fe, 8);
-  CU(cudaMemcpyAsync(fe->h_result[slot], B.result, fe->result_words * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(fe->h_result[slot], B.result, fe->result_words * 4, cudaMemcpyDeviceToHost, s2));
   prof_mark(fe, 9);
-  CU(cudaEventRecord(fe->q_done[slot], s));
+  CU(cudaEventRecord(fe->q_done[slot], s2));
   CU(cudaGetLastError());
   fe->q_count++;
   fe->prev_left = prev;
@@ -552,7 +585,7 @@ FE_API int esvio_fe_track_wait(esvio_fe* fe, esvio_tracks* out) {
   CU(cudaSetDevice(fe->dev));
   const int slot = fe->q_head;
   CU(cudaEventSynchronize(fe->q_done[slot]));
-  fe->q_head = (fe->q_head + 1) & 1;
+  fe->q_head = (fe->q_head + 1) % kSlots;
   fe->q_count--;
   const int M = fe->cfg.max_cnt;
   if (out->capacity < M) return fail(fe, ESVIO_FE_ECAPACITY, "esvio_tracks.capacity < max_cnt", cudaSuccess);
@@ -580,7 +613,8 @@ FE_API int esvio_fe_track_wait(esvio_fe* fe, esvio_tracks* out) {
   if (fe->pev_valid[slot]) {
     for (int i = 0; i < ESVIO_FE_NUM_STAGES; ++i)
       cudaEventElapsedTime(&fe->stage_ms[i],
-                           fe->pev[slot][i == 5 ? ESVIO_FE_NUM_STAGES + 1 : i],
+                           fe->pev[slot][i == 5 ? ESVIO_FE_NUM_STAGES + 1
+                                                : (i == 7 ? ESVIO_FE_NUM_STAGES + 2 : i)],
                            fe->pev[slot][i + 1]);
     fe->stage_ms_valid = 1;
     fe->pev_valid[slot] = 0;
@@ -742,17 +776,17 @@ FE_API int esvio_fe_stage_lk(esvio_fe* fe, const uint8_t* prev_img, const uint8_
   if (n == 0) return ESVIO_FE_OK;
   CU(cudaSetDevice(fe->dev));
   cudaStream_t s = fe->stream;
-  CU(cudaMemcpy2DAsync(fe->pyr[5], fe->pd.pitch[0], prev_img, fe->W, fe->W, fe->H,
+  CU(cudaMemcpy2DAsync(fe->pyr[6], fe->pd.pitch[0], prev_img, fe->W, fe->W, fe->H,
                        cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpy2DAsync(fe->pyr[6], fe->pd.pitch[0], next_img, fe->W, fe->W, fe->H,
+  CU(cudaMemcpy2DAsync(fe->pyr[7], fe->pd.pitch[0], next_img, fe->W, fe->W, fe->H,
                        cudaMemcpyHostToDevice, s));
-  uint8_t* imgs[2] = {fe->pyr[5], fe->pyr[6]};
+  uint8_t* imgs[2] = {fe->pyr[6], fe->pyr[7]};
   launch_pyramids(fe->pd, imgs, 2, s, &fe->launches);
   CU(cudaMemcpyAsync(fe->d_scratch_n, &n, sizeof(int), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(fe->d_scratch_p0, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
   if (use_initial_flow)
     CU(cudaMemcpyAsync(fe->d_scratch_p1, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
-  launch_lk(fe->pd, fe->pyr[5], fe->pyr[6], fe->d_scratch_p0, fe->d_scratch_p1, fe->d_scratch_st,
+  launch_lk(fe->pd, fe->pyr[6], fe->pyr[7], fe->d_scratch_p0, fe->d_scratch_p1, fe->d_scratch_st,
             nullptr, nullptr, fe->d_scratch_n, n, max_level, use_initial_flow, 0, s, &fe->launches);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(next_pts, fe->d_scratch_p1, sizeof(float2) * n, cudaMemcpyDeviceToHost, s));

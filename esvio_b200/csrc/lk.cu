@@ -23,7 +23,6 @@ namespace esvio {
 
 constexpr int kWBits = 14;
 constexpr int kLkThreads = 128;
-constexpr int kLkWarps = kLkThreads / 32;
 constexpr int kPxPerLane = (kWin * kWin + 31) / 32;  // 14
 constexpr int kIP = 24;  // staged intensity patch (window + bilinear tap + Scharr ring)
 constexpr int kDP = 22;  // derivative patch (window + bilinear tap)

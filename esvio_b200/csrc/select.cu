@@ -332,13 +332,52 @@ void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents&
 // left undistort + velocity, stereo forward/backward check, right undistort + velocity,
 // result packing and the state roll (feature_tracker.cpp:470-473, 496-510, 570-574, 585-590)
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_finalize(TrackParams P, TrackBuffers B, double cur_time, double prev_time) {
-  __shared__ int s_warp[33];
+// End of the temporal/selection stage: freeze what the stereo stage needs and roll
+// prev_pts = cur_pts (feature_tracker.cpp:586) so the next window's temporal LK can start.
+__global__ void __launch_bounds__(1024) k_snapshot(TrackParams P, TrackBuffers B, int slot) {
   TrackState* st = B.st;
   const int i = threadIdx.x;
   const int n = st->n_cur;
   const int M = P.max_cnt;
+  if (i < n) {
+    const float2 cp = B.cur_pts[i];
+    B.snap_pts[slot * M + i] = cp;
+    B.snap_ids[slot * M + i] = B.ids[i];
+    B.snap_cnt[slot * M + i] = B.cnt[i];
+    B.prev_pts[i] = cp;
+  }
+  if (i == 0) {
+    int* h = B.snap_hdr + slot * 16;
+    h[0] = n;
+    h[1] = st->stat_n_prev;
+    h[2] = st->stat_after_temporal;
+    h[3] = st->stat_after_ransac;
+    h[4] = st->stat_after_mask;
+    h[5] = st->stat_new;
+    h[6] = st->stat_corner_flags;
+    h[7] = st->stat_ransac_iters;
+    h[8] = st->next_id;
+    st->n_prev = n;
+  }
+}
+
+void launch_snapshot(const TrackParams& P, const TrackBuffers& B, int slot, cudaStream_t s,
+                     int64_t* launches) {
+  k_snapshot<<<1, 1024, 0, s>>>(P, B, slot);
+  ++*launches;
+}
+
+__global__ void __launch_bounds__(1024)
+k_finalize(TrackParams P, TrackBuffers B, int slot, double cur_time, double prev_time) {
+  __shared__ int s_warp[33];
+  TrackState* st = B.st;
+  const int i = threadIdx.x;
+  const int M = P.max_cnt;
+  const int* hdr = B.snap_hdr + slot * 16;
+  const float2* s_cur = B.snap_pts + slot * M;
+  const int* s_ids = B.snap_ids + slot * M;
+  const int* s_cnt = B.snap_cnt + slot * M;
+  const int n = hdr[0];
   int32_t* res = B.result;
   int32_t* r_id = res + kResultHdr;
   int32_t* r_cnt = r_id + M;
@@ -368,8 +407,8 @@ k_finalize(TrackParams P, TrackBuffers B, double cur_time, double prev_time) {
   int keep = 0;
   float2 rp = make_float2(0.f, 0.f);
   if (i < n) {
-    cp = B.cur_pts[i];
-    id = B.ids[i];
+    cp = s_cur[i];
+    id = s_ids[i];
     double x, y;
     lift_projective(P.cam[0], (double)cp.x, (double)cp.y, x, y);
     un = make_float2((float)x, (float)y);
@@ -385,7 +424,7 @@ k_finalize(TrackParams P, TrackBuffers B, double cur_time, double prev_time) {
         }
     }
     r_id[i] = id;
-    r_cnt[i] = B.cnt[i];
+    r_cnt[i] = s_cnt[i];
     r_u[i] = cp.x;
     r_v[i] = cp.y;
     r_unx[i] = un.x;
@@ -402,7 +441,6 @@ k_finalize(TrackParams P, TrackBuffers B, double cur_time, double prev_time) {
   const int pos = block_excl_scan_1024(keep, s_warp, &total);
   // all reads of prev_un / prev_un_ids are done (barriers inside the scan); roll the state
   if (i < n) {
-    B.prev_pts[i] = cp;
     B.prev_un_ids[i] = id;
     B.prev_un[i] = un;
   }
@@ -436,25 +474,17 @@ k_finalize(TrackParams P, TrackBuffers B, double cur_time, double prev_time) {
   }
   if (i == 0) {
     st->n_right = total;
-    st->n_prev = n;
     st->n_prev_un = n;
     st->n_prev_un_r = total;
     res[0] = n;
     res[1] = total;
-    res[2] = st->stat_n_prev;
-    res[3] = st->stat_after_temporal;
-    res[4] = st->stat_after_ransac;
-    res[5] = st->stat_after_mask;
-    res[6] = st->stat_new;
-    res[7] = st->stat_corner_flags;
-    res[8] = st->stat_ransac_iters;
-    res[9] = st->next_id;
+    for (int q = 1; q <= 8; ++q) res[1 + q] = hdr[q];
   }
 }
 
-void launch_finalize(const TrackParams& P, const TrackBuffers& B, double cur_time,
+void launch_finalize(const TrackParams& P, const TrackBuffers& B, int slot, double cur_time,
                      double prev_time, cudaStream_t s, int64_t* launches) {
-  k_finalize<<<1, 1024, 0, s>>>(P, B, cur_time, prev_time);
+  k_finalize<<<1, 1024, 0, s>>>(P, B, slot, cur_time, prev_time);
   ++*launches;
 }
 

@@ -142,8 +142,10 @@ const char *esvio_fe_last_error(const esvio_fe *fe);
  * Synchronous: returns after the <= 2*max_cnt track records are on the host. */
 int esvio_fe_track(esvio_fe *fe, double cur_time, const esvio_events *left,
                    const esvio_events *right, int32_t pub_this_frame, esvio_tracks *out);
-/* The same call split in two so the host can stage window k+1 while window k
- * runs: at most 2 windows may be in flight; waits return results in order. */
+/* The same call split in two so that consecutive windows overlap on the GPU (event stage
+ * of window k+2 | temporal LK + selection of window k+1 | stereo LK of window k): at most
+ * 3 windows may be in flight; waits return results in order.  Host event buffers passed to
+ * submit must stay valid until the matching wait returns. */
 int esvio_fe_track_submit(esvio_fe *fe, double cur_time, const esvio_events *left,
                           const esvio_events *right, int32_t pub_this_frame);
 int esvio_fe_track_wait(esvio_fe *fe, esvio_tracks *out);

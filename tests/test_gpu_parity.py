@@ -325,12 +325,23 @@ def test_submit_wait_pipeline_equals_sync(fe_mod):
     cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=1 << 18)
     a, b = fe_mod.EventFrontEnd(cfg), fe_mod.EventFrontEnd(cfg)
     s = synth.StereoEventStream(W, H, 1.0e6)
-    wins = [s.stereo_window(k) for k in range(6)]
+    wins = [s.stereo_window(k) for k in range(8)]
     sync = [a.track(t, L, R, k % 2 == 0) for k, (L, R, t) in enumerate(wins)]
+    # three windows in flight: event stage (k+2) | temporal stage (k+1) | stereo stage (k)
     outs = []
-    for k, (L, R, t) in enumerate(wins):
+    b.submit(wins[0][2], wins[0][0], wins[0][1], True)
+    b.submit(wins[1][2], wins[1][0], wins[1][1], False)
+    for k in range(2, len(wins)):
+        L, R, t = wins[k]
         b.submit(t, L, R, k % 2 == 0)
         outs.append(b.wait())
+    outs.append(b.wait())
+    outs.append(b.wait())
+    with pytest.raises(fe_mod.FrontEndError):
+        for _ in range(4):
+            b.submit(wins[0][2], wins[0][0], wins[0][1], True)   # a 4th window in flight is refused
+    for _ in range(3):
+        b.wait()
     for x, y in zip(sync, outs):
         for key in ("id", "u", "v", "id_right", "ru", "rv", "vx", "vy"):
             assert np.array_equal(x[key], y[key]), key
