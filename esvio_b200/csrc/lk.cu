@@ -47,7 +47,9 @@ struct LkShared {
   short Ty[kMaxLevels][kPxPerLane * 32];
   float A[kMaxLevels][3];
   int flag[kMaxLevels];  // 0 ok, 1 template window outside the image, 2 minEig / det test failed
-  uint8_t J[kJR][kJR];   // search region of the level being iterated
+  // search region of the level being iterated, as packed 2x2 neighbourhoods:
+  // Q[r][c] = J(r,c) | J(r,c+1) << 8 | J(r+1,c) << 16 | J(r+1,c+1) << 24
+  uint32_t Q[kJR][kJR];
   float2 np;
   int st;
 };
@@ -59,14 +61,27 @@ __device__ __forceinline__ long long warp_sum_exact(int v) {
   return ((long long)hi << 16) + (long long)lo;
 }
 
+// exact warp sum of one int32 per lane, rounded to float once: the total is hi * 65536 + lo
+// with |hi| < 2^24 and lo < 2^24, so both terms are exact floats and their sum rounds once
+__device__ __forceinline__ float warp_sum_to_float(int v) {
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
+  const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+  return (float)hi * 65536.f + (float)lo;
+}
+
+// one warp: lane = column; the column bytes are loaded with all 32 row loads in flight, paired
+// with the right-hand neighbour's by a shuffle and packed with the row below
 __device__ __forceinline__ void stage_J(LkShared& S, const uint8_t* __restrict__ Jl, int w, int h,
                                         int pitch, int rx0, int ry0) {
-  // one warp: lane = column, 32 independent row loads in flight
   const int lane = lane_id();
   const int gx = reflect101(rx0 + lane, w);
-#pragma unroll 8
-  for (int r = 0; r < kJR; ++r)
-    S.J[r][lane] = Jl[(size_t)reflect101(ry0 + r, h) * pitch + gx];
+  uint32_t col[kJR];
+#pragma unroll
+  for (int r = 0; r < kJR; ++r) col[r] = Jl[(size_t)reflect101(ry0 + r, h) * pitch + gx];
+#pragma unroll
+  for (int r = 0; r < kJR; ++r) col[r] |= __shfl_down_sync(0xffffffffu, col[r], 1) << 8;
+#pragma unroll
+  for (int r = 0; r + 1 < kJR; ++r) S.Q[r][lane] = col[r] | (col[r + 1] << 16);
   __syncwarp();
 }
 
@@ -181,7 +196,7 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
     for (int j = 0; j < kPxPerLane; ++j) {
       const int kk = lane + 32 * j;
       const int y = kk / kWin, x = kk - y * kWin;
-      joff[j] = kk < kWin * kWin ? y * kJR + x : 0;
+      joff[j] = kk < kWin * kWin ? y * kJR + x : 0;  // in 32-bit words
     }
     for (int level = top; level >= 0; --level) {
       const int w = pd.w[level], h = pd.h[level], pitch = pd.pitch[level];
@@ -234,18 +249,23 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
         const float a = npx - (float)inx, b = npy - (float)iny;
         int iw00, iw01, iw10, iw11;
         bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-        const uint8_t* base = &S.J[iny - ry0][inx - rx0];
+        // sum_i pix_i * w_i = 128 * dp4a(pix, w >> 7) + dp4a(pix, w & 127); w <= 2^14
+        const unsigned wh = (unsigned)(iw00 >> 7) | ((unsigned)(iw01 >> 7) << 8) |
+                            ((unsigned)(iw10 >> 7) << 16) | ((unsigned)(iw11 >> 7) << 24);
+        const unsigned wl = (unsigned)(iw00 & 127) | ((unsigned)(iw01 & 127) << 8) |
+                            ((unsigned)(iw10 & 127) << 16) | ((unsigned)(iw11 & 127) << 24);
+        const uint32_t* base = &S.Q[iny - ry0][inx - rx0];
         int sb1 = 0, sb2 = 0;
 #pragma unroll
         for (int j = 0; j < kPxPerLane; ++j) {
-          const uint8_t* jp = base + joff[j];
-          const int v = jp[0] * iw00 + jp[1] * iw01 + jp[kJR] * iw10 + jp[kJR + 1] * iw11;
-          const int diff = descale(v, kWBits - 5) - Iw[j];
+          const unsigned q = base[joff[j]];
+          const unsigned v = (__dp4a(q, wh, 0u) << 7) + __dp4a(q, wl, 1u << (kWBits - 5 - 1));
+          const int diff = (int)(v >> (kWBits - 5)) - Iw[j];
           sb1 += diff * Dx[j];
           sb2 += diff * Dy[j];
         }
-        const float b1 = (float)warp_sum_exact(sb1) * flt_scale;
-        const float b2 = (float)warp_sum_exact(sb2) * flt_scale;
+        const float b1 = warp_sum_to_float(sb1) * flt_scale;
+        const float b2 = warp_sum_to_float(sb2) * flt_scale;
         const float dx = (A12 * b2 - A22 * b1) * D;
         const float dy = (A12 * b1 - A11 * b2) * D;
         npx += dx;
