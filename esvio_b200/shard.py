@@ -1,0 +1,88 @@
+"""Multi-GPU plumbing of the front-end: the path shards by independent
+stereo streams -- one process per GPU, one or more streams per process, no data-path
+collective -- plus ONE all-gather of the packed track records per window so that every rank
+(or rank 0's adapter) can publish the feature clouds of all streams.
+
+Only `torch.distributed` is used here; the same functions run on NCCL (device tensors that
+alias the library's result block) and on gloo (CPU tensors, used by the tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+RESULT_HDR = 32        # int32 words in front of the arrays (csrc/common.cuh kResultHdr)
+RESULT_ARRAYS = 15     # id, cnt, u, v, un_x, un_y, vx, vy | id_r, ru, rv, run_x, run_y, rvx, rvy
+LEFT_FIELDS = ("id", "track_cnt", "u", "v", "un_x", "un_y", "vx", "vy")
+RIGHT_FIELDS = ("id_right", "ru", "rv", "run_x", "run_y", "rvx", "rvy")
+INT_FIELDS = ("id", "track_cnt", "id_right")
+
+
+def result_words(max_cnt: int) -> int:
+    return RESULT_HDR + RESULT_ARRAYS * max_cnt
+
+
+def streams_of_rank(rank: int, world: int, n_streams: int) -> list[int]:
+    """Round-robin assignment of stereo streams to ranks (stream s -> rank s % world)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return [s for s in range(n_streams) if s % world == rank]
+
+
+def pack_result_block(tracks: dict, max_cnt: int) -> np.ndarray:
+    """dict of arrays -> the int32 block layout the library writes (for tests / replay)."""
+    blk = np.zeros(result_words(max_cnt), np.int32)
+    nl, nr = len(tracks["id"]), len(tracks["id_right"])
+    blk[0], blk[1] = nl, nr
+    for k, name in enumerate(LEFT_FIELDS + RIGHT_FIELDS):
+        n = nl if k < len(LEFT_FIELDS) else nr
+        a = np.asarray(tracks[name])
+        a = a.astype(np.int32) if name in INT_FIELDS else a.astype(np.float32).view(np.int32)
+        blk[RESULT_HDR + k * max_cnt: RESULT_HDR + k * max_cnt + n] = a[:n]
+    return blk
+
+
+def unpack_result_block(blk, max_cnt: int) -> dict:
+    """One packed block (int32[result_words]) -> dict of per-feature arrays."""
+    blk = np.asarray(blk, np.int32)
+    nl, nr = int(blk[0]), int(blk[1])
+    if not (0 <= nl <= max_cnt and 0 <= nr <= max_cnt):
+        raise ValueError(f"corrupt result block: n_left={nl} n_right={nr} max_cnt={max_cnt}")
+    out = {}
+    for k, name in enumerate(LEFT_FIELDS + RIGHT_FIELDS):
+        n = nl if k < len(LEFT_FIELDS) else nr
+        a = blk[RESULT_HDR + k * max_cnt: RESULT_HDR + k * max_cnt + n]
+        out[name] = a.copy() if name in INT_FIELDS else a.view(np.float32).copy()
+    out["stats"] = dict(n_prev=int(blk[2]), n_after_temporal=int(blk[3]),
+                        n_after_ransac=int(blk[4]), n_after_mask=int(blk[5]),
+                        n_new=int(blk[6]), ransac_iters=int(blk[8]), next_id=int(blk[9]))
+    return out
+
+
+def all_gather_tracks(local_block, gathered=None):
+    """The per-window collective: every rank contributes its packed block (a torch int32
+    tensor, on the GPU for NCCL / CPU for gloo) and receives all of them, [world, words]."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if gathered is None:
+        gathered = torch.empty((world, local_block.numel()), dtype=local_block.dtype,
+                               device=local_block.device)
+    if world == 1:
+        gathered[0].copy_(local_block)
+    else:
+        dist.all_gather_into_tensor(gathered.view(-1), local_block.view(-1))
+    return gathered
+
+
+def aggregate_throughput(events_local: float, ms_local: float):
+    """Whole-job Mevents/s: events summed over ranks / max over ranks of the timed region."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return events_local / (ms_local * 1e-3) / 1e6, ms_local
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    e = torch.tensor([events_local], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(e, op=dist.ReduceOp.SUM)
+    return float(e.item()) / (float(t.item()) * 1e-3) / 1e6, float(t.item())

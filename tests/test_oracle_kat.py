@@ -1,0 +1,131 @@
+"""CPU suite: hand-written known-answer tests of the oracle's restatement of the
+reference-authored stages."""
+import numpy as np
+
+T0 = 1.7e9
+
+
+def _ev(x, y, t, p):
+    return (np.array(x, np.uint16), np.array(y, np.uint16), np.array(t, np.float64),
+            np.array(p, np.uint8))
+
+
+def test_refractory_filter_and_polarity_rearm(ora):
+    """event_detector.cc:149-166: a same-polarity event within 10 ms is not ACCEPTED unless
+    the opposite polarity fired in between; sae_latest always advances."""
+    s = ora.Sae(32, 32)
+    s.update(*_ev([5, 5], [6, 6], [T0 + 0.100, T0 + 0.105], [1, 1]))
+    sae0, sae1, lat0, lat1 = s.planes()
+    assert sae1[6, 5] == T0 + 0.100 and lat1[6, 5] == T0 + 0.105 and sae0[6, 5] == 0
+    # 20 ms later: accepted again
+    s.update(*_ev([5], [6], [T0 + 0.125], [1]))
+    assert s.planes()[1][6, 5] == T0 + 0.125
+    # opposite polarity re-arms: +, -, + within 2 ms are all accepted
+    s2 = ora.Sae(32, 32)
+    s2.update(*_ev([1, 1, 1], [1, 1, 1], [T0 + 0.200, T0 + 0.201, T0 + 0.202], [1, 0, 1]))
+    p = s2.planes()
+    assert p[1][1, 1] == T0 + 0.202 and p[0][1, 1] == T0 + 0.201
+
+
+def test_time_surface_values(ora):
+    """event_detector.cc:230-267: 255*(+-exp(-dt/20ms)+1)/2 -> u8, empty pixel 128."""
+    s = ora.Sae(16, 16)
+    s.update(*_ev([2, 3, 4], [2, 2, 2], [T0, T0, T0 - 0.020], [1, 0, 1]))
+    ts = s.time_surface(T0)
+    assert ts[0, 0] == 128
+    assert ts[2, 2] == 255 and ts[2, 3] == 0
+    assert ts[2, 4] == int(np.rint(127.5 * np.exp(-1.0) + 127.5))
+    ts_np = s.time_surface(T0, ignore_polarity=1)
+    assert ts_np[0, 0] == 0 and ts_np[2, 2] == 255 and ts_np[2, 3] == 255
+
+
+def _paint(s, pts, t):
+    xs, ys = zip(*pts)
+    s.update(*_ev(xs, ys, [t] * len(xs), [1] * len(xs)))
+
+
+def test_arc_star_corner_vs_edge(ora):
+    """event_detector.cc:308-544 on synthetic SAEs: an L-shaped front is a corner, a straight
+    edge is not, an isolated event is not."""
+    W = H = 64
+    cx = cy = 32
+    # straight vertical edge sweeping right: newest column at x = 32
+    s = ora.Sae(W, H)
+    for k, x in enumerate(range(20, 33)):
+        _paint(s, [(x, y) for y in range(10, 54)], T0 + 0.02 * k)
+    assert not s.is_corner(T0 + 0.02 * 12, cx, cy, 1)
+    # quarter-plane (corner of a square) growing diagonally: fresh pixels form an L
+    s = ora.Sae(W, H)
+    for k, d in enumerate(range(20, 33)):
+        _paint(s, [(d, y) for y in range(10, d + 1)] + [(x, d) for x in range(10, d + 1)], T0 + 0.02 * k)
+    assert s.is_corner(T0 + 0.02 * 12, cx, cy, 1)
+    # isolated event on an empty surface: every ring element is 0 -> not a corner
+    s = ora.Sae(W, H)
+    _paint(s, [(cx, cy)], T0)
+    assert not s.is_corner(T0, cx, cy, 1)
+    # too close to the border (MIN_DIST + 1)
+    assert not s.is_corner(T0, 5, 5, 1)
+    # an event superseded by the opposite polarity at its pixel is rejected first
+    s.update(*_ev([cx], [cy], [T0 + 0.001], [0]))
+    assert not s.is_corner(T0, cx, cy, 1)
+
+
+def test_disc_r10_has_317_pixels(ora):
+    hw = ora.disc_half_widths(10)
+    assert int((2 * hw + 1).sum() * 2 - (2 * hw[0] + 1)) == 317
+    m = np.zeros((41, 41), np.uint8)
+    ora.fill_disc(m, 20, 20, 10)
+    assert int((m == 255).sum()) == 317
+
+
+def test_set_mask_orders_by_track_count(ora):
+    """feature_tracker.cpp:123-151: older tracks win the min-distance conflict."""
+    pts = np.array([[50.0, 50.0], [55.0, 50.0], [100.0, 100.0]], np.float32)
+    ids = np.array([1, 2, 3], np.int32)
+    cnt = np.array([2, 7, 1], np.int32)
+    kp, ki, kc, mask = ora.set_mask(346, 260, 10, pts, ids, cnt)
+    assert ki.tolist() == [2, 3] and kc.tolist() == [7, 1]
+    assert mask[50, 55] == 255 and mask[50, 66] == 0 and mask[100, 100] == 255
+
+
+def test_lk_recovers_subpixel_translation(ora):
+    rng = np.random.default_rng(1)
+    yy, xx = np.mgrid[0:120, 0:160].astype(np.float64)
+    def img(dx, dy):
+        v = 128 + 60 * np.sin((xx - dx) / 7.0) * np.cos((yy - dy) / 9.0) + 40 * np.sin((xx - dx + yy - dy) / 13.0)
+        return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    a, b = img(0, 0), img(1.75, -0.6)
+    pts = np.stack([rng.uniform(30, 130, 20), rng.uniform(30, 90, 20)], 1).astype(np.float32)
+    out, st = ora.calc_optical_flow_pyr_lk(a, b, pts, None, max_level=3)
+    assert st.all()
+    d = out - pts
+    assert np.abs(d[:, 0] - 1.75).max() < 0.08 and np.abs(d[:, 1] + 0.6).max() < 0.08
+
+
+def test_lift_projective_inverts_distortion(ora):
+    from esvio_b200 import synth
+    cam = synth.CAM_DAVIS346[0]
+    # distort a normalised point with the radial-tangential model, project, lift back
+    x, y = 0.21, -0.13
+    r2 = x * x + y * y
+    rad = cam["k1"] * r2 + cam["k2"] * r2 * r2
+    xd = x + x * rad + 2 * cam["p1"] * x * y + cam["p2"] * (r2 + 2 * x * x)
+    yd = y + y * rad + 2 * cam["p2"] * x * y + cam["p1"] * (r2 + 2 * y * y)
+    u, v = cam["fx"] * xd + cam["cx"], cam["fy"] * yd + cam["cy"]
+    lx, ly = ora.lift_projective(cam, u, v)
+    assert abs(lx - x) < 1e-6 and abs(ly - y) < 1e-6
+
+
+def test_oracle_tracker_first_publish_and_ids(ora):
+    from esvio_b200 import synth
+    cfg = synth.default_config(346, 260)
+    t = ora.OracleTracker(cfg, use_cv2=False)
+    s = synth.StereoEventStream(346, 260, 1.0e6)
+    L, R, tr = s.stereo_window(0)
+    o = t.track(tr, L, R, True)
+    assert len(o["id"]) > 0 and (o["track_cnt"] == 1).all() and (o["vx"] == 0).all()
+    assert o["id"].tolist() == list(range(len(o["id"])))      # n_id++ in selection order
+    assert set(o["id_right"]) <= set(o["id"])
+    L, R, tr = s.stereo_window(1)
+    o2 = t.track(tr, L, R, False)
+    assert (o2["track_cnt"] == 2).all() and set(o2["id"]) <= set(o["id"])
