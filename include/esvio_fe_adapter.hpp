@@ -1,0 +1,145 @@
+// esvio_fe_adapter.hpp -- header-only C++ mirror of the reference's FeatureTracker (event path)
+// on top of the C ABI in esvio_fe.h.  It keeps the member names the node reads after
+// trackEvent (feature_tracker/src/feature_tracker.h:126-135; stereo_event_tracker_node.cpp:
+// 289-323), so swapping `FeatureTracker trackerData` for `esvio::GpuFeatureTracker` in
+// stereo_event_tracker_node.cpp:45 leaves handle_stereo_event and the PointCloud packing
+// untouched.  No ROS / OpenCV / Eigen headers are needed: `EventArrayT` is any type with a
+// contiguous `.events` container of 16-byte dvs_msgs::Event records
+// (feature_tracker/src/dvs_msgs/Event.h:42-52), `Point2f` is layout-compatible with
+// cv::Point2f.
+#ifndef ESVIO_FE_ADAPTER_HPP
+#define ESVIO_FE_ADAPTER_HPP
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "esvio_fe.h"
+
+namespace esvio {
+
+struct Point2f {
+  float x, y;
+};
+
+class GpuFeatureTracker {
+ public:
+  // same role as readParameters_event + stereo_readIntrinsicParameter
+  // (feature_tracker/src/parameters.cpp:183-282, feature_tracker.cpp:963-976)
+  explicit GpuFeatureTracker(const esvio_fe_config& cfg) : cfg_(cfg) {
+    const int rc = esvio_fe_create(&cfg_, &fe_);
+    if (rc != ESVIO_FE_OK)
+      throw std::runtime_error(std::string("esvio_fe_create: ") + esvio_fe_strerror(rc));
+    const size_t m = (size_t)cfg_.max_cnt;
+    id_.resize(m), cnt_.resize(m), idr_.resize(m);
+    for (auto* v : {&u_, &v_, &unx_, &uny_, &vx_, &vy_, &ru_, &rv_, &runx_, &runy_, &rvx_, &rvy_})
+      v->resize(m);
+    out_.capacity = cfg_.max_cnt;
+    out_.id = id_.data(), out_.track_cnt = cnt_.data();
+    out_.u = u_.data(), out_.v = v_.data(), out_.un_x = unx_.data(), out_.un_y = uny_.data();
+    out_.vx = vx_.data(), out_.vy = vy_.data();
+    out_.id_right = idr_.data(), out_.ru = ru_.data(), out_.rv = rv_.data();
+    out_.run_x = runx_.data(), out_.run_y = runy_.data(), out_.rvx = rvx_.data(),
+    out_.rvy = rvy_.data();
+  }
+  ~GpuFeatureTracker() { esvio_fe_destroy(fe_); }
+  GpuFeatureTracker(const GpuFeatureTracker&) = delete;
+  GpuFeatureTracker& operator=(const GpuFeatureTracker&) = delete;
+
+  // the reference's global PUB_THIS_FRAME (stereo_event_tracker_node.cpp:179,188)
+  bool PUB_THIS_FRAME = true;
+
+  // FeatureTracker::trackEvent(double, const EventArray&, const EventArray&)
+  // (feature_tracker.h:51; call site stereo_event_tracker_node.cpp:193)
+  template <class EventArrayT>
+  void trackEvent(double _cur_time, const EventArrayT& event_left, const EventArrayT& event_right) {
+    static_assert(sizeof(event_left.events[0]) == 16, "dvs_msgs::Event must be 16 bytes");
+    esvio_events l{}, r{};
+    l.aos = event_left.events.empty() ? nullptr : &event_left.events[0];
+    l.n = event_left.events.size();
+    r.aos = event_right.events.empty() ? nullptr : &event_right.events[0];
+    r.n = event_right.events.size();
+    const int rc = esvio_fe_track(fe_, _cur_time, &l, &r, PUB_THIS_FRAME ? 1 : 0, &out_);
+    if (rc != ESVIO_FE_OK)
+      throw std::runtime_error(std::string("esvio_fe_track: ") + esvio_fe_strerror(rc) + " (" +
+                               esvio_fe_last_error(fe_) + ")");
+    prev_time = cur_time;
+    cur_time = _cur_time;
+    unpack();
+  }
+
+  void reset() { esvio_fe_reset(fe_); }
+
+  // FeatureTracker::gettimesurface() (feature_tracker.cpp:894-897): CV_8U, row-major W x H
+  std::vector<uint8_t> gettimesurface(int cam = 0) {
+    std::vector<uint8_t> img((size_t)cfg_.width * cfg_.height);
+    esvio_fe_time_surface(fe_, cam, img.data(), (size_t)cfg_.width);
+    return img;
+  }
+
+  // public result members, names as in feature_tracker.h:126-135
+  std::vector<int> ids, track_cnt, ids_right;
+  std::vector<Point2f> cur_pts, cur_un_pts, pts_velocity;
+  std::vector<Point2f> cur_right_pts, cur_un_right_pts, right_pts_velocity;
+  double cur_time = 0.0, prev_time = 0.0;
+  esvio_stats stats{};
+
+  esvio_fe* handle() { return fe_; }
+
+ private:
+  void unpack() {
+    const int nl = out_.n_left, nr = out_.n_right;
+    ids.assign(id_.begin(), id_.begin() + nl);
+    track_cnt.assign(cnt_.begin(), cnt_.begin() + nl);
+    ids_right.assign(idr_.begin(), idr_.begin() + nr);
+    cur_pts.resize(nl), cur_un_pts.resize(nl), pts_velocity.resize(nl);
+    for (int i = 0; i < nl; ++i) {
+      cur_pts[i] = {u_[i], v_[i]};
+      cur_un_pts[i] = {unx_[i], uny_[i]};
+      pts_velocity[i] = {vx_[i], vy_[i]};
+    }
+    cur_right_pts.resize(nr), cur_un_right_pts.resize(nr), right_pts_velocity.resize(nr);
+    for (int i = 0; i < nr; ++i) {
+      cur_right_pts[i] = {ru_[i], rv_[i]};
+      cur_un_right_pts[i] = {runx_[i], runy_[i]};
+      right_pts_velocity[i] = {rvx_[i], rvy_[i]};
+    }
+    stats = out_.stats;
+  }
+
+  esvio_fe_config cfg_;
+  esvio_fe* fe_ = nullptr;
+  esvio_tracks out_{};
+  std::vector<int32_t> id_, cnt_, idr_;
+  std::vector<float> u_, v_, unx_, uny_, vx_, vy_, ru_, rv_, runx_, runy_, rvx_, rvy_;
+};
+
+// One row of the `feature` sensor_msgs/PointCloud exactly as the node packs it
+// (stereo_event_tracker_node.cpp:268-329): points[i] = (x, y, 1); channels = {id*2+cam, u, v,
+// vx, vy}.  Left rows with track_cnt > 1 first, then right rows whose id was published left.
+struct FeatureRow {
+  float x, y, z, id_cam, u, v, vx, vy;
+};
+
+inline std::vector<FeatureRow> pack_feature_cloud(const GpuFeatureTracker& t) {
+  std::vector<FeatureRow> rows;
+  std::vector<int> pub;
+  for (size_t j = 0; j < t.ids.size(); ++j)
+    if (t.track_cnt[j] > 1) {
+      pub.push_back(t.ids[j]);
+      rows.push_back({t.cur_un_pts[j].x, t.cur_un_pts[j].y, 1.f, (float)(t.ids[j] * 2 + 0),
+                      t.cur_pts[j].x, t.cur_pts[j].y, t.pts_velocity[j].x, t.pts_velocity[j].y});
+    }
+  for (size_t j = 0; j < t.ids_right.size(); ++j) {
+    bool found = false;
+    for (int id : pub) found |= (id == t.ids_right[j]);
+    if (found)
+      rows.push_back({t.cur_un_right_pts[j].x, t.cur_un_right_pts[j].y, 1.f,
+                      (float)(t.ids_right[j] * 2 + 1), t.cur_right_pts[j].x, t.cur_right_pts[j].y,
+                      t.right_pts_velocity[j].x, t.right_pts_velocity[j].y});
+  }
+  return rows;
+}
+
+}  // namespace esvio
+#endif

@@ -1,0 +1,94 @@
+// Compiles the header-only adapter against a stand-in for dvs_msgs::EventArray (no ROS here) and
+// drives a few windows through it.  Exit code 0: tracked features came back and the PointCloud
+// rows keep the consumer's invariants; 3: no CUDA device (the expected outcome on a CPU box --
+// there is no CPU fallback); anything else is a failure.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "esvio_fe_adapter.hpp"
+
+namespace dvs_msgs {  // layout of feature_tracker/src/dvs_msgs/Event.h:42-52
+struct Time {
+  uint32_t sec, nsec;
+};
+struct Event {
+  uint16_t x, y;
+  Time ts;
+  uint8_t polarity;
+};
+struct EventArray {
+  std::vector<Event> events;
+};
+}  // namespace dvs_msgs
+static_assert(sizeof(dvs_msgs::Event) == 16, "Event layout");
+
+static uint64_t splitmix(uint64_t& s) {
+  uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// a square of side 40 px moving diagonally, seen by both cameras with 6 px disparity
+static void make_window(int k, int cam, dvs_msgs::EventArray& out) {
+  uint64_t seed = 1234 + 77 * k + cam;
+  out.events.clear();
+  const int n = 20000;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t us = (uint32_t)((uint64_t)i * 33333 / n) + 33333u * k;
+    const double tau = us * 1e-6;
+    const double px = 100 + 120 * tau - (cam ? 6 : 0), py = 80 + 90 * tau;
+    const uint64_t r = splitmix(seed);
+    const int edge = r & 3;
+    const double s = ((r >> 8) & 0xffff) / 65536.0 * 40.0;
+    double ex = edge < 2 ? px + s : (edge == 2 ? px : px + 40);
+    double ey = edge >= 2 ? py + s : (edge == 0 ? py : py + 40);
+    dvs_msgs::Event e;
+    e.x = (uint16_t)(ex + 0.5);
+    e.y = (uint16_t)(ey + 0.5);
+    e.ts.sec = 1700000000u + us / 1000000u;
+    e.ts.nsec = (us % 1000000u) * 1000u;
+    e.polarity = (edge == 1 || edge == 3) ? 1 : 0;
+    out.events.push_back(e);
+  }
+}
+
+int main() {
+  esvio_fe_config cfg;
+  esvio_fe_default_config(&cfg, 346, 260);
+  cfg.max_events_per_window = 1 << 16;
+  try {
+    esvio::GpuFeatureTracker trackerData(cfg);
+    dvs_msgs::EventArray L, R;
+    size_t rows_total = 0;
+    for (int k = 0; k < 6; ++k) {
+      make_window(k, 0, L);
+      make_window(k, 1, R);
+      const dvs_msgs::Event& last = L.events.back();
+      const double cur_time = (double)last.ts.sec + 1e-9 * (double)last.ts.nsec;  // node.cpp:190
+      trackerData.PUB_THIS_FRAME = (k % 2 == 0);
+      trackerData.trackEvent(cur_time, L, R);
+      const auto rows = esvio::pack_feature_cloud(trackerData);
+      std::map<int, std::vector<int>> seen;
+      for (const auto& r : rows) {
+        const int v = (int)(r.id_cam + 0.5f);  // stereo_estimator_node.cpp:388-401
+        seen[v / 2].push_back(v % 2);
+        if (r.z != 1.f) return 10;
+      }
+      for (const auto& kv : seen)
+        if (kv.second[0] != 0 || kv.second.size() > 2 || (kv.second.size() == 2 && kv.second[1] != 1))
+          return 11;  // feature_manager.cpp:331-340
+      rows_total += rows.size();
+      std::printf("window %d: %zu left, %zu right, %zu cloud rows\n", k, trackerData.ids.size(),
+                  trackerData.ids_right.size(), rows.size());
+    }
+    if (trackerData.ids.empty() || rows_total == 0) return 12;
+    return 0;
+  } catch (const std::exception& e) {
+    std::printf("%s\n", e.what());
+    return std::strstr(e.what(), "no usable CUDA device") ? 3 : 1;
+  }
+}
