@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from esvio_b200 import synth  # noqa: E402
+from esvio_b200 import shard, synth  # noqa: E402
 
 METRIC = "Mevents/s through time-surface+stereo LK"
 UNIT = "Mevents/s"
@@ -218,8 +218,8 @@ def main_ours(args):
         l, r, t = dwins[k]
         fe.submit(t, l, r, k % pub_div == 0)
         if world > 1:
-            with torch.cuda.stream(ext):
-                dist.all_gather_into_tensor(gathered, res_t)
+            with torch.cuda.stream(ext):   # stream-ordered behind this window's finalize
+                shard.all_gather_tracks(res_t, gathered)
 
     def barrier():
         torch.cuda.synchronize()
@@ -278,7 +278,7 @@ def main_ours(args):
         fe2.submit(t, l, r, k % pub_div == 0)   # H2D of the events is enqueued inside
         if world > 1:
             with torch.cuda.stream(ext2):
-                dist.all_gather_into_tensor(gathered, res2_t)
+                shard.all_gather_tracks(res2_t, gathered)
 
     res2_t = torch.as_tensor(_CudaArray(*fe2.result_device_ptr()), device=dev)
     for k in range(Wm):
