@@ -8,7 +8,8 @@
 //          with prev-left) and cur-right
 // Events of a window sit in HBM either as SoA (x u16, y u16, t f64, p u8) or as the raw
 // 16-byte dvs_msgs::Event records, and are re-ordered once per window into per-tile
-// runs (stable counting sort) so that one warp owns one 32x8 pixel tile in shared memory.
+// runs (stable counting sort by 16x8 fine tile) so that one CTA owns one 32x8 tile in shared
+// memory and each of its warps one fine tile's run.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -16,9 +17,12 @@
 
 namespace esvio {
 
-constexpr int kTileW = 32;                    // pixels per tile row == one warp
-constexpr int kTileH = 8;
-constexpr int kTilePx = kTileW * kTileH;      // 256 pixels, key fits 8 bits
+constexpr int kTileW = 32;                    // 32x8-pixel tile: one TMA box of the SAE state,
+constexpr int kTileH = 8;                     // one CTA of K1
+constexpr int kTilePx = kTileW * kTileH;      // 256 pixels: binned key = local pixel | pol << 8
+constexpr int kPolShift = 8;
+constexpr int kFineW = 16;                    // events are binned by 16x8 fine tile ...
+constexpr int kFine = kTileW / kFineW;        // ... 2 per tile, one warp each in K1
 constexpr int kChunkThreads = 256;
 constexpr int kChunkSteps = 8;                // events per thread in the binning kernels
 constexpr int kChunk = kChunkThreads * kChunkSteps;  // 2048 events per CTA
@@ -162,14 +166,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // launch wrappers implemented in the .cu files
 // ---------------------------------------------------------------------------------
 struct BinLayout {
-  int W, H, tiles_x, tiles_y, n_tiles;  // bin n_tiles collects out-of-range events
-  int max_chunks;                       // row stride of `counts`
+  int W, H, tiles_x, tiles_y, n_tiles;  // coarse 32x8 tiles
+  int n_bins;                           // kFine * n_tiles fine tiles; bin n_bins = out of range
+  int max_chunks;                       // chunk capacity of `counts`
 };
 
 struct EventStageBuffers {
-  uint32_t* counts;     // [2][n_tiles+1][max_chunks]
-  uint32_t* bin_total;  // [2][n_tiles+1]
-  uint32_t* bin_start;  // [2][n_tiles+2]
+  uint32_t* counts;     // [2][max_chunks][n_bins+1]
+  uint32_t* bin_total;  // [2][n_bins+1]
+  uint32_t* bin_start;  // [2][n_bins+2]
+  unsigned int* done_ctr;  // [2] CTAs of k_bin_scan that finished (self-resetting)
   double* bt[2];        // binned event times
   uint16_t* bk[2];      // binned keys: local pixel (8 bits) | polarity << 8
 };
@@ -179,9 +185,9 @@ void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const Dev
 
 struct SaeTsParams {
   int W, H, tiles_x, n_tiles;
-  double t_ref, decay_sec, filter_threshold;
+  double t_ref, decay_sec, inv_decay, filter_threshold;  // inv_decay = RN(1 / decay_sec)
   int ignore_polarity;
-  const uint32_t* bin_start;  // [2][n_tiles+2]
+  const uint32_t* bin_start;  // [2][kFine*n_tiles+2]
   const double* bt[2];
   const uint16_t* bk[2];
   uint8_t* ts[2];  // level-0 images

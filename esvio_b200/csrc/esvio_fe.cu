@@ -16,7 +16,7 @@ using namespace esvio;
 
 namespace esvio {
 int select_configure(int W, int H);
-int bin_configure(int n_tiles);
+int bin_configure(int n_bins);
 }
 
 #define FE_API extern "C" __attribute__((visibility("default")))
@@ -197,6 +197,7 @@ static void free_all(esvio_fe* fe) {
   cudaFree(fe->esb.counts);
   cudaFree(fe->esb.bin_total);
   cudaFree(fe->esb.bin_start);
+  cudaFree(fe->esb.done_ctr);
   cudaFree(fe->tb.st);
   cudaFree(fe->tb.prev_pts);
   cudaFree(fe->tb.ids);
@@ -288,9 +289,10 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   L.tiles_x = (fe->W + kTileW - 1) / kTileW;
   L.tiles_y = (fe->H + kTileH - 1) / kTileH;
   L.n_tiles = L.tiles_x * L.tiles_y;
+  L.n_bins = L.n_tiles * kFine;
   fe->cap = (int)align_up((size_t)cfg->max_events_per_window, 64);
   L.max_chunks = (fe->cap + kChunk - 1) / kChunk;
-  const int nb = L.n_tiles + 1;
+  const int nb = L.n_bins + 1;
 
   CUC(cudaMalloc(&fe->sae, fe->npx * 2 * sizeof(double2)));
   CUC(cudaMalloc(&fe->lat, fe->npx * 2 * sizeof(double2)));
@@ -310,6 +312,8 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   CUC(cudaMalloc(&fe->esb.counts, (size_t)2 * nb * L.max_chunks * sizeof(uint32_t)));
   CUC(cudaMalloc(&fe->esb.bin_total, (size_t)2 * nb * sizeof(uint32_t)));
   CUC(cudaMalloc(&fe->esb.bin_start, (size_t)2 * (nb + 1) * sizeof(uint32_t)));
+  CUC(cudaMalloc(&fe->esb.done_ctr, 2 * sizeof(unsigned int)));
+  CUC(cudaMemset(fe->esb.done_ctr, 0, 2 * sizeof(unsigned int)));
 
   const int M = cfg->max_cnt;
   TrackBuffers& B = fe->tb;
@@ -387,7 +391,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     free_all(fe);
     return rc;
   }
-  if (select_configure(fe->W, fe->H) != 0 || bin_configure(L.n_tiles) != 0) {
+  if (select_configure(fe->W, fe->H) != 0 || bin_configure(L.n_bins) != 0) {
     fprintf(stderr, "esvio_fe_create: sensor too large for the shared-memory mask / histogram\n");
     free_all(fe);
     return ESVIO_FE_EINVAL;
@@ -476,6 +480,7 @@ static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev[2], in
   sp.n_tiles = fe->bl.n_tiles;
   sp.t_ref = t_ref;
   sp.decay_sec = fe->cfg.decay_ms / 1000.0;
+  sp.inv_decay = 1.0 / sp.decay_sec;
   sp.filter_threshold = fe->cfg.feature_filter_threshold;
   sp.ignore_polarity = fe->cfg.ignore_polarity;
   sp.bin_start = fe->esb.bin_start;

@@ -1,34 +1,40 @@
 // events.cu -- per-event stages of the front-end as sm_100a kernels:
-//   K0 bin_events      stable counting sort of a window's events into 32x8-pixel tiles
+//   K0 bin_events      stable counting sort of a window's events into 16x8-pixel fine tiles
 //   K1 sae_update_ts   createSAE_left/right + SAEtoTimeSurface_left/right, fused
 //                      (feature_tracker/src/event_detector/event_detector.cc:149-166,
-//                       212-228, 230-305), one warp per tile, tile state TMA-staged in smem
+//                       212-228, 230-305), one CTA per 32x8 tile, tile state TMA-staged in smem
 //   K2 corner_flags    EventDetector::isCorner (Arc*) for every left event
 //                      (event_detector.cc:308-544)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace esvio {
 
 // =====================================================================================
-// K0: stable counting sort by tile
+// K0: stable counting sort by fine tile
 // =====================================================================================
 // Same-pixel events must be applied in stream order (acceptance of an event depends on
 // the previous same- and opposite-polarity event at its pixel, event_detector.cc:157),
 // so the sort is stable: CTA c owns events [c*2048, (c+1)*2048), warp w of it owns the
 // 256 consecutive events [w*256, (w+1)*256) and walks them 32 at a time.
+// Bins are 16x8-pixel fine tiles, numbered tile*2 + (x%32)/16 so that the two fine tiles of
+// one 32x8 tile (one TMA box of the SAE state) are adjacent runs; bin n_bins collects
+// out-of-range events.
 
-__device__ __forceinline__ int tile_of(const BinLayout& L, int x, int y) {
-  if (x >= L.W || y >= L.H) return L.n_tiles;  // dropped (the reference would index out of range)
-  return (y / kTileH) * L.tiles_x + (x / kTileW);
+__device__ __forceinline__ int bin_of(const BinLayout& L, int x, int y) {
+  if (x >= L.W || y >= L.H) return L.n_bins;  // dropped (the reference would index out of range)
+  return ((y / kTileH) * L.tiles_x + (x / kTileW)) * kFine + ((x % kTileW) / kFineW);
 }
 
+// counts[cam][chunk][bin]: per-chunk histogram, written coalesced
 __global__ void __launch_bounds__(kChunkThreads)
 k_bin_hist(BinLayout L, DevEvents ev0, DevEvents ev1, uint32_t* __restrict__ counts) {
   extern __shared__ uint32_t s_hist[];
   const int cam = blockIdx.y;
   const DevEvents& ev = cam ? ev1 : ev0;
   const int chunk = blockIdx.x;
-  const int nb = L.n_tiles + 1;
+  const int nb = L.n_bins + 1;
   if ((long long)chunk * kChunk >= ev.n) return;
   for (int b = threadIdx.x; b < nb; b += blockDim.x) s_hist[b] = 0;
   __syncthreads();
@@ -46,55 +52,78 @@ k_bin_hist(BinLayout L, DevEvents ev0, DevEvents ev1, uint32_t* __restrict__ cou
         x = __ldg(ev.x + i);
         y = __ldg(ev.y + i);
       }
-      atomicAdd(&s_hist[tile_of(L, x, y)], 1u);
+      atomicAdd(&s_hist[bin_of(L, x, y)], 1u);
     }
   }
   __syncthreads();
-  uint32_t* out = counts + (size_t)cam * nb * L.max_chunks + chunk;
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) out[(size_t)b * L.max_chunks] = s_hist[b];
+  uint32_t* out = counts + ((size_t)cam * L.max_chunks + chunk) * nb;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) out[b] = s_hist[b];
 }
 
-// one warp per bin: exclusive scan of the bin's per-chunk counts, in place
-__global__ void __launch_bounds__(256)
-k_bin_scan_chunks(BinLayout L, int n_chunks0, int n_chunks1, uint32_t* __restrict__ counts,
-                  uint32_t* __restrict__ bin_total) {
-  const int cam = blockIdx.y;
-  const int nb = L.n_tiles + 1;
-  const int bin = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (bin >= nb) return;
-  const int n_chunks = cam ? n_chunks1 : n_chunks0;
-  const int lane = lane_id();
-  uint32_t* row = counts + ((size_t)cam * nb + bin) * L.max_chunks;
-  uint32_t carry = 0;
-  for (int c0 = 0; c0 < n_chunks; c0 += 32) {
-    const int c = c0 + lane;
-    const uint32_t v = c < n_chunks ? row[c] : 0u;
-    uint32_t incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
-    }
-    if (c < n_chunks) row[c] = carry + incl - v;
-    carry += __shfl_sync(0xffffffffu, incl, 31);
-  }
-  if (lane == 0) bin_total[cam * nb + bin] = carry;
-}
+// Exclusive scan of every bin's per-chunk counts, in place.  CTA = 32 adjacent bins x 16
+// chunk phases (all accesses are 128-byte rows of `counts`); the last CTA of a camera to
+// finish then scans the bin totals into bin_start[0..nb].
+constexpr int kScanPhases = 16;
 
-// one CTA per camera: exclusive scan of the bin totals -> bin_start[0..nb]
-__global__ void __launch_bounds__(1024)
-k_bin_scan_bins(BinLayout L, const uint32_t* __restrict__ bin_total,
-                uint32_t* __restrict__ bin_start) {
+__global__ void __launch_bounds__(32 * kScanPhases)
+k_bin_scan(BinLayout L, int n_chunks0, int n_chunks1, uint32_t* __restrict__ counts,
+           uint32_t* __restrict__ bin_total, uint32_t* __restrict__ bin_start,
+           unsigned int* __restrict__ done_ctr) {
+  __shared__ uint32_t s_part[kScanPhases][33];
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
-  const int cam = blockIdx.x;
-  const int nb = L.n_tiles + 1;
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
+  __shared__ bool s_last;
+  const int cam = blockIdx.y;
+  const int nb = L.n_bins + 1;
+  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+  const int bin = blockIdx.x * 32 + lane;
+  const int n_chunks = cam ? n_chunks1 : n_chunks0;
+  const int per = (n_chunks + kScanPhases - 1) / kScanPhases;
+  const int c_lo = min(ph * per, n_chunks), c_hi = min(c_lo + per, n_chunks);
+  uint32_t* col = counts + (size_t)cam * L.max_chunks * nb + bin;
+  uint32_t sum = 0;
+  if (bin < nb) {
+    int c = c_lo;
+    for (; c + 4 <= c_hi; c += 4) {
+      const uint32_t v0 = col[(size_t)c * nb], v1 = col[(size_t)(c + 1) * nb],
+                     v2 = col[(size_t)(c + 2) * nb], v3 = col[(size_t)(c + 3) * nb];
+      sum += v0 + v1 + v2 + v3;
+    }
+    for (; c < c_hi; ++c) sum += col[(size_t)c * nb];
+  }
+  s_part[ph][lane] = sum;
   __syncthreads();
+  uint32_t carry = 0, total = 0;
+#pragma unroll
+  for (int q = 0; q < kScanPhases; ++q) {
+    const uint32_t v = s_part[q][lane];
+    if (q < ph) carry += v;
+    total += v;
+  }
+  if (bin < nb) {
+    for (int c = c_lo; c < c_hi; ++c) {
+      const uint32_t v = col[(size_t)c * nb];
+      col[(size_t)c * nb] = carry;
+      carry += v;
+    }
+    if (ph == 0) bin_total[cam * nb + bin] = total;
+  }
+  // ---- last CTA of this camera: exclusive scan of the totals
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&done_ctr[cam], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    s_carry = 0;
+    done_ctr[cam] = 0;  // ready for the next window
+  }
+  __syncthreads();
+  const int warp = ph;
   for (int b0 = 0; b0 < nb; b0 += blockDim.x) {
     const int b = b0 + threadIdx.x;
-    const uint32_t v = b < nb ? bin_total[cam * nb + b] : 0u;
+    const uint32_t v = b < nb ? __ldcg(bin_total + cam * nb + b) : 0u;
     uint32_t incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -104,20 +133,20 @@ k_bin_scan_bins(BinLayout L, const uint32_t* __restrict__ bin_total,
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-      uint32_t w = s_warp[lane];
+      uint32_t w = lane < kScanPhases ? s_warp[lane] : 0u;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
         if (lane >= d) w += o;
       }
-      s_warp[lane] = w;  // inclusive over warps
+      if (lane < kScanPhases) s_warp[lane] = w;  // inclusive over warps
     }
     __syncthreads();
     const uint32_t warp_off = warp ? s_warp[warp - 1] : 0u;
-    const uint32_t carry = s_carry;
-    if (b < nb) bin_start[cam * (nb + 1) + b] = carry + warp_off + incl - v;
+    const uint32_t base = s_carry;
+    if (b < nb) bin_start[cam * (nb + 1) + b] = base + warp_off + incl - v;
     __syncthreads();
-    if (threadIdx.x == 0) s_carry = carry + s_warp[31];
+    if (threadIdx.x == 0) s_carry = base + s_warp[kScanPhases - 1];
     __syncthreads();
   }
   if (threadIdx.x == 0) bin_start[cam * (nb + 1) + nb] = s_carry;
@@ -127,70 +156,94 @@ __global__ void __launch_bounds__(kChunkThreads)
 k_bin_scatter(BinLayout L, DevEvents ev0, DevEvents ev1, const uint32_t* __restrict__ counts,
               const uint32_t* __restrict__ bin_start, double* __restrict__ bt0,
               uint16_t* __restrict__ bk0, double* __restrict__ bt1, uint16_t* __restrict__ bk1) {
-  extern __shared__ uint32_t s_wh[];  // [8 warps][nb]
+  // s_base[nb]: position of this chunk's first event of each bin; s_wc[8 warps][nb]: events of
+  // the bin in each warp's 256-event slice, then the slice's offset inside the chunk
+  extern __shared__ uint32_t s_dyn[];
   const int cam = blockIdx.y;
   const DevEvents& ev = cam ? ev1 : ev0;
   double* __restrict__ bt = cam ? bt1 : bt0;
   uint16_t* __restrict__ bk = cam ? bk1 : bk0;
   const int chunk = blockIdx.x;
-  const int nb = L.n_tiles + 1;
+  const int nb = L.n_bins + 1;
   if ((long long)chunk * kChunk >= ev.n) return;
+  uint32_t* s_base = s_dyn;
+  uint32_t* s_wc = s_dyn + nb;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int b = threadIdx.x; b < nb * 8; b += blockDim.x) s_wh[b] = 0;
-  __syncthreads();
+  for (int b = threadIdx.x; b < nb * 8; b += blockDim.x) s_wc[b] = 0;
 
-  uint32_t* my = s_wh + warp * nb;
   int bin[kChunkSteps];
-  uint32_t key[kChunkSteps];
+  uint32_t key[kChunkSteps], rank[kChunkSteps];
   double tt[kChunkSteps];
   const int wbase = chunk * kChunk + warp * (32 * kChunkSteps);
 #pragma unroll
   for (int k = 0; k < kChunkSteps; ++k) {
     const int i = wbase + k * 32 + lane;
-    bin[k] = -1 - lane;  // unique per lane: matches nothing
+    bin[k] = -1;
     key[k] = 0;
     tt[k] = 0.0;
     if (i < ev.n) {
       const Ev e = load_event(ev, i);
-      bin[k] = tile_of(L, e.x, e.y);
-      key[k] = (uint32_t)((e.y % kTileH) * kTileW + (e.x % kTileW)) | ((uint32_t)e.p << 8);
+      bin[k] = bin_of(L, e.x, e.y);
+      key[k] = (uint32_t)((e.y % kTileH) * kTileW + (e.x % kTileW)) | ((uint32_t)e.p << kPolShift);
       tt[k] = e.t;
     }
-    const uint32_t m = __match_any_sync(0xffffffffu, bin[k]);
-    if (bin[k] >= 0 && (m & lt_mask) == 0) my[bin[k]] += __popc(m);
+  }
+  // position of this chunk's first event of every bin (independent loads, in flight during
+  // the ranking pass)
+  const uint32_t* cnt_row = counts + ((size_t)cam * L.max_chunks + chunk) * nb;
+#pragma unroll 4
+  for (int b = threadIdx.x; b < nb; b += blockDim.x)
+    s_base[b] = __ldg(bin_start + cam * (nb + 1) + b) + __ldg(cnt_row + b);
+  __syncthreads();
+
+  // Stable rank of every event among the events of its bin in this warp's slice.  A step's
+  // 32 events mostly fall into 32 different bins, where match.any is at its slowest, so the
+  // lanes first count themselves with a shared-memory atomic and only the lanes that share a
+  // bin with another lane of the step (count grew by more than one) sort themselves out.
+  uint32_t* my = s_wc + warp * nb;
+#pragma unroll
+  for (int k = 0; k < kChunkSteps; ++k) {
+    const bool valid = bin[k] >= 0;
+    uint32_t before = 0;
+    if (valid) before = my[bin[k]];
+    __syncwarp();
+    if (valid) atomicAdd(&my[bin[k]], 1u);
+    __syncwarp();
+    const bool shared = valid && my[bin[k]] - before > 1;
+    const uint32_t sh = __ballot_sync(0xffffffffu, shared);
+    rank[k] = before;
+    if (shared) rank[k] += __popc(__match_any_sync(sh, bin[k]) & lt_mask);
     __syncwarp();
   }
   __syncthreads();
-  // per-bin exclusive prefix over the 8 warps, on top of the global offsets
-  const uint32_t* cnt_row = counts + (size_t)cam * nb * L.max_chunks + chunk;
+  // per-bin exclusive prefix over the 8 warps
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-    uint32_t run = bin_start[cam * (nb + 1) + b] + cnt_row[(size_t)b * L.max_chunks];
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      const uint32_t c = s_wh[w * nb + b];
-      s_wh[w * nb + b] = run;
+      const uint32_t c = s_wc[w * nb + b];
+      s_wc[w * nb + b] = run;
       run += c;
     }
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < kChunkSteps; ++k) {
-    const uint32_t m = __match_any_sync(0xffffffffu, bin[k]);
-    uint32_t pos = 0;
-    if (bin[k] >= 0) pos = my[bin[k]] + __popc(m & lt_mask);
-    __syncwarp();
-    if (bin[k] >= 0 && (m & lt_mask) == 0) my[bin[k]] += __popc(m);
-    __syncwarp();
-    if (bin[k] >= 0 && bin[k] < L.n_tiles) {
+    if (bin[k] >= 0 && bin[k] < L.n_bins) {
+      const uint32_t pos = s_base[bin[k]] + my[bin[k]] + rank[k];
       bt[pos] = tt[k];
       bk[pos] = (uint16_t)key[k];
     }
   }
 }
 
-int bin_configure(int n_tiles) {
-  const size_t bytes = (size_t)(n_tiles + 1) * 8 * sizeof(uint32_t);
+static size_t scatter_smem_bytes(int n_bins) {
+  return ((size_t)n_bins + 1) * 9 * sizeof(uint32_t);
+}
+
+int bin_configure(int n_bins) {
+  const size_t bytes = scatter_smem_bytes(n_bins);
   if (bytes > 200 * 1024) return -1;
   return cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)bytes) == cudaSuccess ? 0 : -1;
@@ -198,7 +251,7 @@ int bin_configure(int n_tiles) {
 
 void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents ev[2],
                        cudaStream_t s, int64_t* launches) {
-  const int nb = L.n_tiles + 1;
+  const int nb = L.n_bins + 1;
   const int c0 = (ev[0].n + kChunk - 1) / kChunk, c1 = (ev[1].n + kChunk - 1) / kChunk;
   const int nc = c0 > c1 ? c0 : c1;
   if (nc > 0) {
@@ -206,11 +259,11 @@ void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const Dev
                                                                           B.counts);
     ++*launches;
   }
-  k_bin_scan_chunks<<<dim3((nb + 7) / 8, 2), 256, 0, s>>>(L, c0, c1, B.counts, B.bin_total);
-  k_bin_scan_bins<<<2, 1024, 0, s>>>(L, B.bin_total, B.bin_start);
-  *launches += 2;
+  k_bin_scan<<<dim3((nb + 31) / 32, 2), 32 * kScanPhases, 0, s>>>(L, c0, c1, B.counts, B.bin_total,
+                                                                 B.bin_start, B.done_ctr);
+  ++*launches;
   if (nc > 0) {
-    k_bin_scatter<<<dim3(nc, 2), kChunkThreads, (size_t)nb * 8 * sizeof(uint32_t), s>>>(
+    k_bin_scatter<<<dim3(nc, 2), kChunkThreads, scatter_smem_bytes(L.n_bins), s>>>(
         L, ev[0], ev[1], B.counts, B.bin_start, B.bt[0], B.bk[0], B.bt[1], B.bk[1]);
     ++*launches;
   }
@@ -219,7 +272,15 @@ void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const Dev
 // =====================================================================================
 // K1: fused SAE update + time surface
 // =====================================================================================
-constexpr int kSaeWarps = 4;
+// One CTA (kFine warps) per 32x8 tile of one camera.  The tile's `sae` and `lat` state
+// (2 x 4 KB) arrives by TMA; warp w applies the events of fine tile w (its own 16x8 pixel
+// block, so the warps never touch the same pixel) in stream order, 32 events per step: the
+// lanes of one step that hit the same pixel find their predecessors with match.any / ballot
+// and decide acceptance from them instead of replaying the events one by one.  The time
+// surface is computed from shared memory (4 pixels per thread) and dirty tiles go back by
+// TMA store.
+constexpr int kSaeThreads = 32 * kFine;
+constexpr int kSaeAhead = 4;  // 32-event steps loaded per round trip to L2/HBM
 
 // convertTo(CV_8U) of a double: cvRound (half to even) then saturate
 __device__ __forceinline__ uint8_t sat_u8(double v) {
@@ -229,105 +290,187 @@ __device__ __forceinline__ uint8_t sat_u8(double v) {
 }
 
 struct SaeMaps {
-  CUtensorMap sae, lat;  // f64 [cams][H][2W], box {64, 8, 1}
+  CUtensorMap sae, lat;  // f64 [cams][H][2W], box {2 * kTileW, kTileH, 1}
 };
 
-__global__ void __launch_bounds__(kSaeWarps * 32)
+// 2^(j/32), j = 0..31, rounded to nearest
+__constant__ double c_exp2_32[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577,
+    1.1143867425958924, 1.1387886347566916, 1.1637248587775775, 1.189207115002721,
+    1.215247359980469, 1.241857812073484, 1.2690509571917332, 1.2968395546510096,
+    1.3252366431597413, 1.3542555469368927, 1.383909881963832, 1.4142135623730951,
+    1.4451808069770467, 1.4768261459394993, 1.5091644275934228, 1.5422108254079407,
+    1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429,
+    1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424,
+    1.8741676341103, 1.9152065613971474, 1.9571441241754002};
+
+// exp(a) for a in [-7.5, 8] to < 3 ulp: a = (32 m + j) ln2/32 + r, |r| <= ln2/64;
+// exp(a) = 2^m * 2^(j/32) * P6(r).  Straight-line (no branches) so that the four pixels of a
+// thread interleave.  The CV_8U value derived from it equals the one derived from a
+// correctly rounded exp unless 127.5 * e falls within ~1e-14 of a rounding boundary.
+__device__ __forceinline__ double exp_small(double a, const double* __restrict__ tab) {
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: the sum's low word is rint(a * 32/ln2)
+  const double kf = fma(a, 46.16624130844683, kMagic);
+  const int k = __double2loint(kf);
+  const double kd = kf - kMagic;
+  double r = fma(-kd, 0x1.62e42fefa3000p-6, a);  // ln2/32 hi (40 bits: kd * hi is exact)
+  r = fma(-kd, 0x1.3de6af278ece6p-47, r);         // ln2/32 lo
+  double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double scale = __hiloint2double((1023 + (k >> 5)) << 20, 0);
+  return tab[k & 31] * p * scale;
+}
+
+// SAEtoTimeSurface_* for four adjacent pixels (event_detector.cc:230-267)
+__device__ __forceinline__ uchar4 ts_pixel4(const double2* __restrict__ px, const SaeTsParams& P,
+                                            const double* __restrict__ tab) {
+  double a[4];
+  bool pos[4], hit[4], fresh[4];
+  bool any_fresh = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double2 v = px[i];
+    pos[i] = v.y > v.x;
+    const double stamp = pos[i] ? v.y : v.x;
+    hit[i] = stamp > 0.0;
+    // -dt / decay_sec, correctly rounded (Markstein: q + (n - q*d) * RN(1/d) with FMAs)
+    const double n = -(P.t_ref - stamp);
+    const double q = n * P.inv_decay;
+    a[i] = fma(fma(-q, P.decay_sec, n), P.inv_decay, q);
+    // exp(a) < 1/1024 below -7: 255*e rounds to 0 and 127.5 +- 127.5*e to 128 / 127 whatever
+    // the last bits of exp() are; above 0 the value saturates for any e > 1
+    fresh[i] = hit[i] && a[i] >= -7.0;
+    any_fresh |= fresh[i];
+  }
+  uint8_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    o[i] = !hit[i] ? (P.ignore_polarity ? (uint8_t)0 : (uint8_t)128)
+                   : (P.ignore_polarity ? (uint8_t)0 : (pos[i] ? (uint8_t)128 : (uint8_t)127));
+  if (any_fresh) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double e = exp_small(fmin(fmax(a[i], -7.25), 8.0), tab);
+      if (!P.ignore_polarity && !pos[i]) e = -e;
+      const uint8_t v = sat_u8(P.ignore_polarity ? e * 255.0 : e * 127.5 + 127.5);
+      if (fresh[i]) o[i] = v;
+    }
+  }
+  return make_uchar4(o[0], o[1], o[2], o[3]);
+}
+
+// DBG: perf-experiment switches (0 in the product): 1 skip events, 2 skip TS, 4 skip store
+template <int DBG>
+__global__ void __launch_bounds__(kSaeThreads)
 k_sae_update_ts(const __grid_constant__ SaeMaps maps, SaeTsParams P) {
-  // per warp: sae tile [8][32] double2 (4 KB) + lat tile (4 KB)
-  __shared__ __align__(128) double2 s_tiles[kSaeWarps][2][kTilePx];
-  __shared__ __align__(8) uint64_t s_bar[kSaeWarps];
+  __shared__ __align__(128) double2 s_sae[kTilePx];
+  __shared__ __align__(128) double2 s_lat[kTilePx];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ double s_exp2[32];
 
   const int warp = threadIdx.x >> 5, lane = lane_id();
-  const int task = blockIdx.x * kSaeWarps + warp;
-  if (task >= 2 * P.n_tiles) return;
-  const int cam = task / P.n_tiles, tile = task - cam * P.n_tiles;
-  const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
-  const int x0 = tx * kTileW, y0 = ty * kTileH;
+  const int cam = blockIdx.z, tile = blockIdx.y * P.tiles_x + blockIdx.x;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
 
-  const uint32_t* bs = P.bin_start + cam * (P.n_tiles + 2);
-  const int seg_begin = (int)bs[tile], seg_end = (int)bs[tile + 1];
-  const bool dirty = seg_end > seg_begin;
-
-  double2* s_sae = s_tiles[warp][0];
-  double2* s_lat = s_tiles[warp][1];
-  uint64_t* bar = &s_bar[warp];
-  if (lane == 0) {
-    mbar_init(bar, 1);
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
     mbar_fence_init();
   }
-  __syncwarp();
-  if (lane == 0) {
-    mbar_expect_tx(bar, (dirty ? 2u : 1u) * (uint32_t)(kTilePx * sizeof(double2)));
-    tma_load_3d(s_sae, &maps.sae, bar, 2 * x0, y0, cam);
-    if (dirty) tma_load_3d(s_lat, &maps.lat, bar, 2 * x0, y0, cam);
+  const uint32_t* bs = P.bin_start + cam * (P.n_tiles * kFine + 2) + tile * kFine;
+  const int seg_begin = (int)bs[warp], seg_end = (DBG & 1) ? seg_begin : (int)bs[warp + 1];
+  const bool dirty = bs[kFine] > bs[0];
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&s_bar, (dirty ? 2u : 1u) * (uint32_t)(kTilePx * sizeof(double2)));
+    tma_load_3d(s_sae, &maps.sae, &s_bar, 2 * x0, y0, cam);
+    if (dirty) tma_load_3d(s_lat, &maps.lat, &s_bar, 2 * x0, y0, cam);
   }
-  // overlap the first event batch with the tile load
-  const double* __restrict__ bt = P.bt[cam];
-  const uint16_t* __restrict__ bk = P.bk[cam];
-  double t_next = 0.0;
-  uint32_t k_next = 0;
-  if (seg_begin + lane < seg_end) {
-    t_next = __ldg(bt + seg_begin + lane);
-    k_next = __ldg(bk + seg_begin + lane);
+  // the first events of the run travel while the tile loads
+  const double* __restrict__ bt = cam ? P.bt[1] : P.bt[0];
+  const uint16_t* __restrict__ bk = cam ? P.bk[1] : P.bk[0];
+  double t_nx[kSaeAhead];
+  uint32_t k_nx[kSaeAhead];
+#pragma unroll
+  for (int j = 0; j < kSaeAhead; ++j) {
+    const int i = seg_begin + j * 32 + lane;
+    t_nx[j] = 0.0;
+    k_nx[j] = 0;
+    if (i < seg_end) {
+      t_nx[j] = __ldg(bt + i);
+      k_nx[j] = __ldg(bk + i);
+    }
   }
-  mbar_wait(bar, 0);
+  if (threadIdx.x < 32) s_exp2[threadIdx.x] = c_exp2_32[threadIdx.x];
+  __syncthreads();  // barrier initialised before anybody polls it
+  mbar_wait(&s_bar, 0);
 
   const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int base = seg_begin; base < seg_end; base += 32) {
-    const bool valid = base + lane < seg_end;
-    const double t = t_next;
-    const uint32_t key = k_next;
-    if (base + 32 + lane < seg_end) {
-      t_next = __ldg(bt + base + 32 + lane);
-      k_next = __ldg(bk + base + 32 + lane);
-    }
-    const int pix = key & 0xff, pol = (key >> 8) & 1;
-    // events of one pixel inside this batch are applied in stream order
-    const uint32_t m = __match_any_sync(0xffffffffu, valid ? pix : (0x100 + lane));
-    const int rank = __popc(m & lt_mask);
-    const int max_rank = __reduce_max_sync(0xffffffffu, rank);
-    for (int r = 0; r <= max_rank; ++r) {
-      if (valid && rank == r) {
-        double* lat = reinterpret_cast<double*>(&s_lat[pix]);
-        const double prev_same = lat[pol], prev_opp = lat[1 - pol];
-        if (t > prev_same + P.filter_threshold || prev_opp > prev_same)
-          reinterpret_cast<double*>(&s_sae[pix])[pol] = t;
-        lat[pol] = t;
-      }
-      __syncwarp();
-    }
-  }
-
-  // time surface of the tile straight from shared memory
-  uint8_t* __restrict__ ts = P.ts[cam];
-  const int x = x0 + lane;
+  const uint32_t gt_mask = ~lt_mask & ~(1u << lane);
+  for (int base = seg_begin; base < seg_end; base += 32 * kSaeAhead) {
+    double t_cu[kSaeAhead];
+    uint32_t k_cu[kSaeAhead];
 #pragma unroll
-  for (int r = 0; r < kTileH; ++r) {
-    const double2 v = s_sae[r * kTileW + lane];
-    const bool pos_newer = v.y > v.x;
-    const double stamp = pos_newer ? v.y : v.x;
-    double e = 0.0;
-    if (stamp > 0.0) {
-      const double dt = P.t_ref - stamp;
-      e = exp(-dt / P.decay_sec);
-      if (!P.ignore_polarity && !pos_newer) e = -e;
+    for (int j = 0; j < kSaeAhead; ++j) {
+      t_cu[j] = t_nx[j];
+      k_cu[j] = k_nx[j];
+      const int i = base + (kSaeAhead + j) * 32 + lane;
+      if (i < seg_end) {
+        t_nx[j] = __ldg(bt + i);
+        k_nx[j] = __ldg(bk + i);
+      }
     }
-    const double scaled = P.ignore_polarity ? e * 255.0 : e * 127.5 + 127.5;
+#pragma unroll
+    for (int j = 0; j < kSaeAhead; ++j) {
+      if (base + j * 32 < seg_end) {  // warp-uniform
+        const bool valid = base + j * 32 + lane < seg_end;
+        const double t = t_cu[j];
+        const int pix = k_cu[j] & 0xff, pol = (k_cu[j] >> kPolShift) & 1;
+        // lanes of this step on my pixel, split by polarity (createSAE_*,
+        // event_detector.cc:157: t_last = latest[pol], t_last_inv = latest[!pol] as left by
+        // the events before me)
+        const uint32_t grp = __match_any_sync(0xffffffffu, valid ? pix : (0x100 + lane));
+        const uint32_t pos_lanes = __ballot_sync(0xffffffffu, valid && pol);
+        const uint32_t same = grp & (pol ? pos_lanes : ~pos_lanes);
+        const uint32_t before_same = same & lt_mask, before_opp = grp & ~same & lt_mask;
+        double2 st = make_double2(0.0, 0.0);
+        if (valid) st = s_lat[pix];
+        const double t_bs = __shfl_sync(0xffffffffu, t, before_same ? 31 - __clz(before_same) : lane);
+        const double t_bo = __shfl_sync(0xffffffffu, t, before_opp ? 31 - __clz(before_opp) : lane);
+        const double prev_same = before_same ? t_bs : (pol ? st.y : st.x);
+        const double prev_opp = before_opp ? t_bo : (pol ? st.x : st.y);
+        const bool accept = valid && (t > prev_same + P.filter_threshold || prev_opp > prev_same);
+        const uint32_t acc = __ballot_sync(0xffffffffu, accept);
+        __syncwarp();
+        if (valid && (same & gt_mask) == 0) reinterpret_cast<double*>(&s_lat[pix])[pol] = t;
+        if (accept && (same & acc & gt_mask) == 0) reinterpret_cast<double*>(&s_sae[pix])[pol] = t;
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+
+  // time surface of the tile straight from shared memory: thread -> 4 adjacent pixels.
+  // Columns >= W of the last tile (zero-filled by TMA) land in the row padding of the image.
+  {
+    const int r = threadIdx.x >> 3, c = (threadIdx.x & 7) * 4;
     const int y = y0 + r;
-    if (x < P.W && y < P.H) ts[(size_t)y * P.ts_pitch + x] = sat_u8(scaled);
+    if (y < P.H && !(DBG & 2))
+      *reinterpret_cast<uchar4*>((cam ? P.ts[1] : P.ts[0]) + (size_t)y * P.ts_pitch + x0 + c) =
+          ts_pixel4(&s_sae[r * kTileW + c], P, s_exp2);
   }
 
-  if (dirty) {
+  if (dirty && !(DBG & 4)) {
     fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
       tma_store_3d(&maps.sae, s_sae, 2 * x0, y0, cam);
       tma_store_3d(&maps.lat, s_lat, 2 * x0, y0, cam);
       tma_store_commit();
       tma_store_wait_read0();
     }
-    __syncwarp();
   }
 }
 
@@ -336,8 +479,16 @@ void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
   SaeMaps maps;
   maps.sae = map_sae;
   maps.lat = map_lat;
-  const int tasks = 2 * P.n_tiles;
-  k_sae_update_ts<<<(tasks + kSaeWarps - 1) / kSaeWarps, kSaeWarps * 32, 0, s>>>(maps, P);
+  static const int dbg = getenv("ESVIO_K1_DBG") ? atoi(getenv("ESVIO_K1_DBG")) : 0;
+  const dim3 grid(P.tiles_x, P.n_tiles / P.tiles_x, 2);
+  switch (dbg) {
+    case 1: k_sae_update_ts<1><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
+    case 2: k_sae_update_ts<2><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
+    case 3: k_sae_update_ts<3><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
+    case 4: k_sae_update_ts<4><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
+    case 7: k_sae_update_ts<7><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
+    default: k_sae_update_ts<0><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
+  }
   ++*launches;
 }
 

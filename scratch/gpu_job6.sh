@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/j9_pytest.log
+for d in 0 1 2; do ESVIO_K1_DBG=$d python scratch/stage_times.py stereo_vga_5mevs 40; done 2>&1 | tee gpurun_out/j9_variants.txt
+python scratch/stage_times.py stereo_davis346_1mevs 40 2>&1 | tee -a gpurun_out/j9_variants.txt
+python scratch/stage_times.py stereo_vga_20mevs_burst 30 2>&1 | tee -a gpurun_out/j9_variants.txt
