@@ -6,54 +6,100 @@
 
 namespace esvio {
 
-constexpr int kPyrTW = 32, kPyrTH = 8;  // output tile of one CTA
+// All levels in one launch: a CTA owns an 8x8 tile of level 3 (16x16 of level 2, 32x32 of
+// level 1) and cascades through shared memory: level-0 patch 85x85 -> level-1 patch 41x41
+// -> level-2 patch 19x19 -> level-3 tile 8x8 (every patch carries the halo the next level's
+// 5x5 taps need; the halo pixels are recomputed by the neighbouring CTAs).  Patches are
+// addressed in the image coordinates of their level, so BORDER_REFLECT_101 is applied per
+// level exactly as a level-by-level build would.
+constexpr int kPyrT3 = 8;
+constexpr int kPyrN2 = 2 * kPyrT3 + 3;   // 19
+constexpr int kPyrN1 = 2 * kPyrN2 + 3;   // 41
+constexpr int kPyrN0 = 2 * kPyrN1 + 3;   // 85
+constexpr int kPyrThreads = 256;
 
-// One CTA produces a 32x8 output tile: the (2*32+3) x (2*8+3) input patch is staged in
-// shared memory (reflect-101 applied while staging), filtered horizontally into int rows,
-// then vertically.
-__global__ void __launch_bounds__(kPyrTW* kPyrTH)
-k_pyr_down(const uint8_t* __restrict__ src0, const uint8_t* __restrict__ src1, int sw, int sh,
-           int spitch, uint8_t* __restrict__ dst0, uint8_t* __restrict__ dst1, int dw, int dh,
-           int dpitch) {
-  constexpr int PW = 2 * kPyrTW + 3, PH = 2 * kPyrTH + 3;
-  __shared__ uint8_t s_in[PH][PW + 1];
-  __shared__ int s_row[PH][kPyrTW];
-  const uint8_t* __restrict__ src = blockIdx.z ? src1 : src0;
-  uint8_t* __restrict__ dst = blockIdx.z ? dst1 : dst0;
-  const int ox0 = blockIdx.x * kPyrTW, oy0 = blockIdx.y * kPyrTH;
-  const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
-  const int tid = threadIdx.y * kPyrTW + threadIdx.x;
-  for (int i = tid; i < PW * PH; i += kPyrTW * kPyrTH) {
-    const int py = i / PW, px = i - py * PW;
-    const int gx = reflect101(ix0 + px, sw), gy = reflect101(iy0 + py, sh);
-    s_in[py][px] = src[(size_t)gy * spitch + gx];
+// dst patch (nd x nd at image origin (dx0, dy0), image dw x dh) from src patch (ns x ns at
+// (sx0, sy0), image sw x sh); pixels of the owned rectangle [ox0, ox0+on) x [oy0, oy0+on)
+// also go to global memory.
+template <int NS, int ND>
+__device__ __forceinline__ void pyr_stage(const uint8_t* __restrict__ s_src, int ssp, int sx0,
+                                          int sy0, int sw, int sh, uint16_t* __restrict__ s_row,
+                                          uint8_t* __restrict__ s_dst, int dsp, int dx0, int dy0,
+                                          int dw, int dh, uint8_t* __restrict__ g_dst, int gpitch,
+                                          int ox0, int oy0, int on) {
+  // horizontal [1 4 6 4 1] on every source row of the patch
+  for (int i = threadIdx.x; i < NS * ND; i += kPyrThreads) {
+    const int r = i / ND, c = i - r * ND;
+    const int gx = dx0 + c;
+    uint32_t v = 0;
+    if (gx >= 0 && gx < dw) {
+      const uint8_t* row = s_src + r * ssp;
+      const int x0 = reflect101(2 * gx - 2, sw) - sx0, x1 = reflect101(2 * gx - 1, sw) - sx0,
+                x2 = 2 * gx - sx0, x3 = reflect101(2 * gx + 1, sw) - sx0,
+                x4 = reflect101(2 * gx + 2, sw) - sx0;
+      v = row[x2] * 6 + (row[x1] + row[x3]) * 4 + row[x0] + row[x4];
+    }
+    s_row[r * ND + c] = (uint16_t)v;
   }
   __syncthreads();
-  for (int i = tid; i < PH * kPyrTW; i += kPyrTW * kPyrTH) {
-    const int py = i / kPyrTW, ox = i - py * kPyrTW;
-    const uint8_t* r = &s_in[py][2 * ox];
-    s_row[py][ox] = r[2] * 6 + (r[1] + r[3]) * 4 + r[0] + r[4];
+  for (int i = threadIdx.x; i < ND * ND; i += kPyrThreads) {
+    const int r = i / ND, c = i - r * ND;
+    const int gx = dx0 + c, gy = dy0 + r;
+    if (gx >= 0 && gx < dw && gy >= 0 && gy < dh) {
+      const int y0 = reflect101(2 * gy - 2, sh) - sy0, y1 = reflect101(2 * gy - 1, sh) - sy0,
+                y2 = 2 * gy - sy0, y3 = reflect101(2 * gy + 1, sh) - sy0,
+                y4 = reflect101(2 * gy + 2, sh) - sy0;
+      const int v = s_row[y2 * ND + c] * 6 + (s_row[y1 * ND + c] + s_row[y3 * ND + c]) * 4 +
+                    s_row[y0 * ND + c] + s_row[y4 * ND + c];
+      const uint8_t o = (uint8_t)((v + 128) >> 8);
+      s_dst[r * dsp + c] = o;
+      if (gx >= ox0 && gx < ox0 + on && gy >= oy0 && gy < oy0 + on)
+        g_dst[(size_t)gy * gpitch + gx] = o;
+    }
   }
   __syncthreads();
-  const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
-  if (ox < dw && oy < dh) {
-    const int ly = 2 * threadIdx.y, lx = threadIdx.x;
-    const int v = s_row[ly + 2][lx] * 6 + (s_row[ly + 1][lx] + s_row[ly + 3][lx]) * 4 +
-                  s_row[ly][lx] + s_row[ly + 4][lx];
-    dst[(size_t)oy * dpitch + ox] = (uint8_t)((v + 128) >> 8);
+}
+
+__global__ void __launch_bounds__(kPyrThreads)
+k_pyr_build(PyrDesc pd, uint8_t* __restrict__ img0, uint8_t* __restrict__ img1) {
+  constexpr int SP0 = kPyrN0 + 3, SP1 = kPyrN1 + 3, SP2 = kPyrN2 + 1;
+  __shared__ uint8_t s0[kPyrN0 * SP0];
+  __shared__ uint8_t s1[kPyrN1 * SP1];
+  __shared__ uint8_t s2[kPyrN2 * SP2];
+  __shared__ uint8_t s3[kPyrT3 * kPyrT3];
+  __shared__ uint16_t s_row[kPyrN0 * kPyrN1];
+  uint8_t* __restrict__ img = blockIdx.z ? img1 : img0;
+  const int o3x = blockIdx.x * kPyrT3, o3y = blockIdx.y * kPyrT3;
+  const int p2x = 2 * o3x - 2, p2y = 2 * o3y - 2;
+  const int p1x = 2 * p2x - 2, p1y = 2 * p2y - 2;
+  const int p0x = 2 * p1x - 2, p0y = 2 * p1y - 2;
+  {
+    const uint8_t* __restrict__ src = img + pd.off[0];
+    const int w = pd.w[0], h = pd.h[0], pitch = pd.pitch[0];
+    for (int i = threadIdx.x; i < kPyrN0 * kPyrN0; i += kPyrThreads) {
+      const int r = i / kPyrN0, c = i - r * kPyrN0;
+      const int gx = p0x + c, gy = p0y + r;
+      s0[r * SP0 + c] = (gx >= 0 && gx < w && gy >= 0 && gy < h) ? src[(size_t)gy * pitch + gx] : 0;
+    }
   }
+  __syncthreads();
+  pyr_stage<kPyrN0, kPyrN1>(s0, SP0, p0x, p0y, pd.w[0], pd.h[0], s_row, s1, SP1, p1x, p1y, pd.w[1],
+                            pd.h[1], img + pd.off[1], pd.pitch[1], 4 * o3x, 4 * o3y, 4 * kPyrT3);
+  if (pd.levels > 2)
+    pyr_stage<kPyrN1, kPyrN2>(s1, SP1, p1x, p1y, pd.w[1], pd.h[1], s_row, s2, SP2, p2x, p2y, pd.w[2],
+                              pd.h[2], img + pd.off[2], pd.pitch[2], 2 * o3x, 2 * o3y, 2 * kPyrT3);
+  if (pd.levels > 3)
+    pyr_stage<kPyrN2, kPyrT3>(s2, SP2, p2x, p2y, pd.w[2], pd.h[2], s_row, s3, kPyrT3, o3x, o3y,
+                              pd.w[3], pd.h[3], img + pd.off[3], pd.pitch[3], o3x, o3y, kPyrT3);
 }
 
 void launch_pyramids(const PyrDesc& pd, uint8_t* const pyr[2], int n_img, cudaStream_t s,
                      int64_t* launches) {
-  for (int l = 0; l + 1 < pd.levels; ++l) {
-    dim3 grid((pd.w[l + 1] + kPyrTW - 1) / kPyrTW, (pd.h[l + 1] + kPyrTH - 1) / kPyrTH, n_img);
-    k_pyr_down<<<grid, dim3(kPyrTW, kPyrTH), 0, s>>>(
-        pyr[0] + pd.off[l], pyr[n_img > 1 ? 1 : 0] + pd.off[l], pd.w[l], pd.h[l], pd.pitch[l],
-        pyr[0] + pd.off[l + 1], pyr[n_img > 1 ? 1 : 0] + pd.off[l + 1], pd.w[l + 1], pd.h[l + 1],
-        pd.pitch[l + 1]);
-    ++*launches;
-  }
+  if (pd.levels < 2) return;
+  const dim3 grid((pd.w[1] + 4 * kPyrT3 - 1) / (4 * kPyrT3), (pd.h[1] + 4 * kPyrT3 - 1) / (4 * kPyrT3),
+                  n_img);
+  k_pyr_build<<<grid, kPyrThreads, 0, s>>>(pd, pyr[0], pyr[n_img > 1 ? 1 : 0]);
+  ++*launches;
 }
 
 }  // namespace esvio
