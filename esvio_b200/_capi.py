@@ -96,6 +96,7 @@ SYMBOLS = {
     "esvio_fe_get_pyramid_level": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, _pi, _pi]),
     "esvio_fe_stage_lk": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_int32, C.c_int32]),
+    "esvio_fe_stage_condition": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "esvio_fe_stage_fmat_mask": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
                                            C.c_void_p, _pi]),
     "esvio_fe_stage_select": (C.c_int, [_H, C.POINTER(Events), C.c_int32, C.c_void_p, C.c_void_p,

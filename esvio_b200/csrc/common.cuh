@@ -211,6 +211,14 @@ void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* fl
 void launch_pyramids(const PyrDesc& pd, uint8_t* const pyr[2], int n_img, cudaStream_t s,
                      int64_t* launches);
 
+// optional conditioning of the time surface (imgops.cu)
+void launch_median(const uint8_t* const src[2], uint8_t* const dst[2], int n_img, int W, int H,
+                   int pitch, int ksize, cudaStream_t s, int64_t* launches);
+size_t clahe_lut_bytes();
+void launch_equalize(const uint8_t* const src[2], uint8_t* const tmp[2], uint8_t* const dst[2],
+                     int n_img, int W, int H, int pitch, uint8_t* lut, int* minmax,
+                     cudaStream_t s, int64_t* launches);
+
 // cv::calcOpticalFlowPyrLK(I, J, prev, next, status, err, Size(21,21), max_level[, 30/0.01,
 // USE_INITIAL_FLOW]); n is read on the device.
 // mode 0: that call alone.  mode 1: followed, per point and in the same launch, by the

@@ -35,6 +35,13 @@ struct esvio_fe {
   // Pyramid buffers: 0..2 left, 3..5 right (rotating: up to three windows are in flight, one
   // per pipeline stage), 6..7 scratch for esvio_fe_stage_lk
   uint8_t* pyr[8];
+  // image conditioning (median blur / CLAHE + normalize): [stage][camera] scratch images with
+  // the layout of pyramid level 0; ts_sel[cam] = the time surface the corner selection and
+  // gettimesurface() see (after the median blur, before CLAHE)
+  uint8_t* aux[3][2];
+  uint8_t* clahe_lut;
+  int* clahe_minmax;
+  const uint8_t* ts_sel[2];
   int cur_left;   // index (0..2) of the newest left pyramid; prev_left is the one before it
   int prev_left;
   int cur_right;  // 3..5
@@ -178,6 +185,9 @@ static void free_all(esvio_fe* fe) {
   cudaFree(fe->sae);
   cudaFree(fe->lat);
   for (int i = 0; i < 8; ++i) cudaFree(fe->pyr[i]);
+  for (int i = 0; i < 3; ++i) cudaFree(fe->aux[i][0]), cudaFree(fe->aux[i][1]);
+  cudaFree(fe->clahe_lut);
+  cudaFree(fe->clahe_minmax);
   for (int i = 0; i < kSlots; ++i) {
     cudaFree(fe->raw[i][0]);
     cudaFree(fe->raw[i][1]);
@@ -228,6 +238,7 @@ static int reset_state(esvio_fe* fe) {
   CU(cudaStreamSynchronize(fe->stream));
   fe->cur_left = fe->prev_left = 0;
   fe->cur_right = 3;
+  fe->ts_sel[0] = fe->ts_sel[1] = nullptr;
   fe->windows = 0;
   fe->prev_time = 0.0;
   fe->q_head = fe->q_count = 0;
@@ -243,8 +254,8 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     return ESVIO_FE_EINVAL;
   if (cfg->max_cnt < 1 || cfg->max_cnt > kMaxCnt) return ESVIO_FE_EINVAL;
   if (cfg->min_dist < 1 || cfg->min_dist > 64) return ESVIO_FE_EINVAL;
-  if (cfg->equalize || cfg->median_blur_kernel_size || cfg->do_motion_correction)
-    return ESVIO_FE_EINVAL;  // SURVEY.md section 8f "next" rows, not built yet
+  if (cfg->median_blur_kernel_size < 0 || cfg->median_blur_kernel_size > 7) return ESVIO_FE_EINVAL;
+  if (cfg->do_motion_correction) return ESVIO_FE_EINVAL;  // SURVEY.md 8f rank 2, not built yet
   if (cfg->max_events_per_window < 1) return ESVIO_FE_EINVAL;
   if (!(cfg->decay_ms > 0.0)) return ESVIO_FE_EINVAL;
   int ndev = 0;
@@ -298,6 +309,15 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   CUC(cudaMalloc(&fe->lat, fe->npx * 2 * sizeof(double2)));
   build_pyr_desc(fe->W, fe->H, &fe->pd);
   for (int i = 0; i < 8; ++i) CUC(cudaMalloc(&fe->pyr[i], fe->pd.bytes));
+  if (cfg->equalize || cfg->median_blur_kernel_size) {
+    for (int i = 0; i < 3; ++i)
+      for (int c = 0; c < 2; ++c) {
+        CUC(cudaMalloc(&fe->aux[i][c], fe->pd.bytes));
+        CUC(cudaMemset(fe->aux[i][c], 0, fe->pd.bytes));
+      }
+    CUC(cudaMalloc(&fe->clahe_lut, clahe_lut_bytes()));
+    CUC(cudaMalloc(&fe->clahe_minmax, 4 * sizeof(int)));
+  }
   for (int c = 0; c < kSlots; ++c) {
     CUC(cudaMalloc(&fe->raw[c][0], (size_t)fe->cap * 16));
     CUC(cudaMalloc(&fe->raw[c][1], (size_t)fe->cap * 16));
@@ -488,12 +508,28 @@ static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev[2], in
   sp.bt[1] = fe->esb.bt[1];
   sp.bk[0] = fe->esb.bk[0];
   sp.bk[1] = fe->esb.bk[1];
-  sp.ts[0] = fe->pyr[left_idx];
-  sp.ts[1] = fe->pyr[right_idx];
+  // time surface -> [median blur] -> (selection / gettimesurface see this) -> [CLAHE +
+  // normalize] -> pyramid level 0 (event_detector.cc:260-264, feature_tracker.cpp:370-388)
+  uint8_t* imgs[2] = {fe->pyr[left_idx], fe->pyr[right_idx]};
+  const int med = fe->cfg.median_blur_kernel_size, eq = fe->cfg.equalize;
+  uint8_t* const* a_out = (med || eq) ? fe->aux[0] : imgs;                 // K1 writes here
+  uint8_t* const* b_out = med ? (eq ? fe->aux[1] : imgs) : a_out;          // after the median
+  sp.ts[0] = a_out[0];
+  sp.ts[1] = a_out[1];
   sp.ts_pitch = fe->pd.pitch[0];
   launch_sae_update_ts(sp, fe->map_sae, fe->map_lat, se, &fe->launches);
+  if (med) {
+    const uint8_t* src[2] = {a_out[0], a_out[1]};
+    launch_median(src, b_out, 2, fe->W, fe->H, fe->pd.pitch[0], 2 * med + 1, se, &fe->launches);
+  }
+  fe->ts_sel[0] = b_out[0];
+  fe->ts_sel[1] = b_out[1];
+  if (eq) {
+    const uint8_t* src[2] = {b_out[0], b_out[1]};
+    launch_equalize(src, fe->aux[2], imgs, 2, fe->W, fe->H, fe->pd.pitch[0], fe->clahe_lut,
+                    fe->clahe_minmax, se, &fe->launches);
+  }
   prof_mark(fe, 3);
-  uint8_t* imgs[2] = {fe->pyr[left_idx], fe->pyr[right_idx]};
   launch_pyramids(fe->pd, imgs, 2, se, &fe->launches);
   CU(cudaGetLastError());
   return ESVIO_FE_OK;
@@ -508,7 +544,7 @@ static CornerParams corner_params(esvio_fe* fe, int left_idx, int and_ts) {
   cp.ts_lk_threshold = fe->cfg.ts_lk_threshold;
   cp.sae = fe->sae;
   cp.lat = fe->lat;
-  cp.ts = fe->pyr[left_idx];
+  cp.ts = fe->ts_sel[0] ? fe->ts_sel[0] : fe->pyr[left_idx];
   cp.ts_pitch = fe->pd.pitch[0];
   cp.and_ts_test = and_ts;
   return cp;
@@ -640,7 +676,7 @@ FE_API int esvio_fe_time_surface(esvio_fe* fe, int32_t cam, uint8_t* dst, size_t
   if (!fe || !dst || cam < 0 || cam > 1 || stride < (size_t)fe->W) return ESVIO_FE_EINVAL;
   CU(cudaSetDevice(fe->dev));
   if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
-  const uint8_t* src = fe->pyr[cam == 0 ? fe->cur_left : fe->cur_right];
+  const uint8_t* src = fe->ts_sel[cam] ? fe->ts_sel[cam] : fe->pyr[cam == 0 ? fe->cur_left : fe->cur_right];
   CU(cudaMemcpy2DAsync(dst, stride, src, fe->pd.pitch[0], fe->W, fe->H, cudaMemcpyDeviceToHost,
                        fe->stream));
   CU(cudaStreamSynchronize(fe->stream));
@@ -796,6 +832,39 @@ FE_API int esvio_fe_stage_lk(esvio_fe* fe, const uint8_t* prev_img, const uint8_
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(next_pts, fe->d_scratch_p1, sizeof(float2) * n, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(status, fe->d_scratch_st, n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_stage_condition(esvio_fe* fe, const uint8_t* src, int32_t median_ksize,
+                                    int32_t equalize, uint8_t* dst) {
+  if (!fe || !src || !dst || median_ksize < 0 || median_ksize > 15 ||
+      (median_ksize && !(median_ksize & 1)))
+    return ESVIO_FE_EINVAL;
+  if (!fe->aux[0][0]) return fail(fe, ESVIO_FE_ESTATE, "handle created without equalize / median", cudaSuccess);
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "windows in flight", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
+  cudaStream_t s = fe->stream;
+  const int pitch = fe->pd.pitch[0];
+  CU(cudaMemcpy2DAsync(fe->aux[0][0], pitch, src, fe->W, fe->W, fe->H, cudaMemcpyHostToDevice, s));
+  const uint8_t* cur = fe->aux[0][0];
+  if (median_ksize > 1) {
+    const uint8_t* in[2] = {cur, cur};
+    uint8_t* out[2] = {fe->aux[1][0], fe->aux[1][0]};
+    launch_median(in, out, 1, fe->W, fe->H, pitch, median_ksize, s, &fe->launches);
+    cur = fe->aux[1][0];
+  }
+  if (equalize) {
+    const uint8_t* in[2] = {cur, cur};
+    uint8_t* tmp[2] = {fe->aux[2][0], fe->aux[2][0]};
+    uint8_t* out[2] = {fe->aux[2][1], fe->aux[2][1]};
+    launch_equalize(in, tmp, out, 1, fe->W, fe->H, pitch, fe->clahe_lut, fe->clahe_minmax, s,
+                    &fe->launches);
+    cur = fe->aux[2][1];
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpy2DAsync(dst, fe->W, cur, pitch, fe->W, fe->H, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   return ESVIO_FE_OK;
 }

@@ -289,6 +289,15 @@ class EventFrontEnd:
                                                 st.ctypes.data, max_level, int(init)), "stage_lk")
         return npts, st[:n]
 
+    def stage_condition(self, img, median_ksize=0, equalize=False):
+        a = np.ascontiguousarray(img, np.uint8)
+        assert a.shape == (self.H, self.W)
+        out = np.empty_like(a)
+        self._chk(_capi.lib().esvio_fe_stage_condition(self._h, a.ctypes.data, int(median_ksize),
+                                                       int(bool(equalize)), out.ctypes.data),
+                  "stage_condition")
+        return out
+
     def stage_fmat_mask(self, p1, p2, thresh=1.0):
         p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)
         p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)

@@ -51,12 +51,12 @@ typedef struct esvio_fe_config {
   int32_t max_cnt;                 /* MAX_CNT */
   int32_t min_dist;                /* MIN_DIST */
   int32_t flow_back;               /* FLOW_BACK */
-  int32_t equalize;                /* EQUALIZE (CLAHE + normalize; not in round 1 -> EINVAL if 1) */
+  int32_t equalize;                /* EQUALIZE: CLAHE(40, 8x8) + normalize(0,255,MINMAX) before LK */
   double f_threshold;              /* F_THRESHOLD */
   double ts_lk_threshold;          /* TS_LK_THRESHOLD */
   double decay_ms;                 /* para_decay_ms */
   int32_t ignore_polarity;         /* para_ignore_polarity */
-  int32_t median_blur_kernel_size; /* para_median_blur_kernel_size (must be 0 in round 1) */
+  int32_t median_blur_kernel_size; /* para_median_blur_kernel_size k: medianBlur(2k+1), 0..7 */
   double feature_filter_threshold; /* para_feature_filter_threshold */
   int32_t do_motion_correction;    /* Do_motion_correction (must be 0 in round 1) */
   double focal_length;             /* FOCAL_LENGTH = 460 (parameters.cpp:274) */
@@ -197,6 +197,13 @@ int esvio_fe_get_pyramid_level(esvio_fe *fe, int32_t which, int32_t level, uint8
 int esvio_fe_stage_lk(esvio_fe *fe, const uint8_t *prev_img, const uint8_t *next_img,
                       const float *prev_pts, float *next_pts, int32_t n, uint8_t *status,
                       int32_t max_level, int32_t use_initial_flow);
+/* The optional conditioning of the time surface on a caller image (W*H u8):
+ * cv::medianBlur(src, ksize) when median_ksize > 1 (event_detector.cc:262-264, ksize = 2k+1),
+ * then cv::createCLAHE()->apply + cv::normalize(0,255,NORM_MINMAX) when equalize != 0
+ * (feature_tracker.cpp:375-382).  The handle must have been created with equalize or
+ * median_blur_kernel_size set (that allocates the scratch images). */
+int esvio_fe_stage_condition(esvio_fe *fe, const uint8_t *src, int32_t median_ksize,
+                             int32_t equalize, uint8_t *dst);
 /* cv::findFundamentalMat(p1, p2, FM_RANSAC, thresh, 0.99, status)
  * (feature_tracker.cpp:935) */
 int esvio_fe_stage_fmat_mask(esvio_fe *fe, const float *p1, const float *p2, int32_t n,

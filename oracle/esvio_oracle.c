@@ -990,6 +990,148 @@ ORA_API int ora_find_fundamental_mask(const float *p1, const float *p2, int n, d
 }
 
 /* ======================================================================== */
+/* Optional image conditioning of the time surface (OpenCV imgproc, restated)   */
+/* ======================================================================== */
+
+/* cv::medianBlur(src, dst, ksize) for CV_8U (event_detector.cc:262-264): the exact median of
+ * the ksize x ksize window, BORDER_REPLICATE (every OpenCV code path -- sorting network for 3/5,
+ * histogram for larger -- computes this same value). */
+ORA_API void ora_median_blur_u8(const uint8_t *src, int W, int H, int ksize, uint8_t *dst) {
+  const int r = ksize / 2, half = (ksize * ksize) / 2;
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      int hist[256];
+      memset(hist, 0, sizeof(hist));
+      for (int dy = -r; dy <= r; ++dy) {
+        int yy = y + dy;
+        yy = yy < 0 ? 0 : (yy >= H ? H - 1 : yy);
+        for (int dx = -r; dx <= r; ++dx) {
+          int xx = x + dx;
+          xx = xx < 0 ? 0 : (xx >= W ? W - 1 : xx);
+          hist[src[(size_t)yy * W + xx]]++;
+        }
+      }
+      int acc = 0, v = 0;
+      for (; v < 256; ++v) {
+        acc += hist[v];
+        if (acc > half) break;
+      }
+      dst[(size_t)y * W + x] = (uint8_t)v;
+    }
+}
+
+static int reflect101_i(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+
+static uint8_t sat_u8_f(float v) { /* saturate_cast<uchar>(float): cvRound then clamp */
+  long r = lrintf(v);
+  return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}
+
+/* cv::createCLAHE(clip_limit, Size(tiles, tiles))->apply(src, dst) for CV_8U
+ * (feature_tracker.cpp:377-379 uses the defaults 40.0, 8x8); follows modules/imgproc/src/
+ * clahe.cpp: pad right/bottom with BORDER_REFLECT_101 when either dimension is not a multiple
+ * of the grid (a dimension that IS a multiple is then padded by a whole grid step, as OpenCV
+ * does), per-tile clipped histogram -> LUT, bilinear blend of the four nearest tile LUTs. */
+ORA_API void ora_clahe_u8(const uint8_t *src, int W, int H, double clip_limit_, int tiles,
+                          uint8_t *dst) {
+  const int tx_n = tiles, ty_n = tiles;
+  int EW = W, EH = H;
+  if (W % tx_n != 0 || H % ty_n != 0) {
+    EW = W + (tx_n - W % tx_n);
+    EH = H + (ty_n - H % ty_n);
+  }
+  const int tw = EW / tx_n, th = EH / ty_n;
+  const int area = tw * th;
+  const float lut_scale = (float)255 / area;
+  int clip = 0;
+  if (clip_limit_ > 0.0) {
+    clip = (int)(clip_limit_ * area / 256);
+    if (clip < 1) clip = 1;
+  }
+  uint8_t *lut = (uint8_t *)malloc((size_t)tx_n * ty_n * 256);
+  for (int ty = 0; ty < ty_n; ++ty)
+    for (int tx = 0; tx < tx_n; ++tx) {
+      int hist[256];
+      memset(hist, 0, sizeof(hist));
+      for (int y = ty * th; y < (ty + 1) * th; ++y) {
+        const int sy = reflect101_i(y, H);
+        for (int x = tx * tw; x < (tx + 1) * tw; ++x) hist[src[(size_t)sy * W + reflect101_i(x, W)]]++;
+      }
+      if (clip > 0) {
+        int clipped = 0;
+        for (int i = 0; i < 256; ++i)
+          if (hist[i] > clip) {
+            clipped += hist[i] - clip;
+            hist[i] = clip;
+          }
+        const int batch = clipped / 256;
+        int residual = clipped - batch * 256;
+        for (int i = 0; i < 256; ++i) hist[i] += batch;
+        if (residual != 0) {
+          int step = 256 / residual;
+          if (step < 1) step = 1;
+          for (int i = 0; i < 256 && residual > 0; i += step, --residual) hist[i]++;
+        }
+      }
+      uint8_t *l = lut + ((size_t)ty * tx_n + tx) * 256;
+      int sum = 0;
+      for (int i = 0; i < 256; ++i) {
+        sum += hist[i];
+        l[i] = sat_u8_f((float)sum * lut_scale);
+      }
+    }
+  const float inv_tw = 1.0f / tw, inv_th = 1.0f / th;
+  for (int y = 0; y < H; ++y) {
+    const float tyf = y * inv_th - 0.5f;
+    int ty1 = (int)floorf(tyf), ty2 = ty1 + 1;
+    const float ya = tyf - ty1, ya1 = 1.0f - ya;
+    if (ty1 < 0) ty1 = 0;
+    if (ty2 > ty_n - 1) ty2 = ty_n - 1;
+    for (int x = 0; x < W; ++x) {
+      const float txf = x * inv_tw - 0.5f;
+      int tx1 = (int)floorf(txf), tx2 = tx1 + 1;
+      const float xa = txf - tx1, xa1 = 1.0f - xa;
+      if (tx1 < 0) tx1 = 0;
+      if (tx2 > tx_n - 1) tx2 = tx_n - 1;
+      const int v = src[(size_t)y * W + x];
+      const uint8_t *p1 = lut + ((size_t)ty1 * tx_n) * 256, *p2 = lut + ((size_t)ty2 * tx_n) * 256;
+      const float res = (p1[tx1 * 256 + v] * xa1 + p1[tx2 * 256 + v] * xa) * ya1 +
+                        (p2[tx1 * 256 + v] * xa1 + p2[tx2 * 256 + v] * xa) * ya;
+      dst[(size_t)y * W + x] = sat_u8_f(res);
+    }
+  }
+  free(lut);
+}
+
+/* cv::normalize(src, dst, 0, 255, NORM_MINMAX) for CV_8U (feature_tracker.cpp:380-381):
+ * scale = 255 / (max - min) (0 when max == min), shift = -min * scale in double, then
+ * convertTo's float path: saturate_cast<uchar>(v * (float)scale + (float)shift), evaluated
+ * with one rounding (fused) as OpenCV's AVX2 build does. */
+ORA_API void ora_normalize_minmax_u8(const uint8_t *src, size_t n, uint8_t *dst) {
+  int mn = 255, mx = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (src[i] < mn) mn = src[i];
+    if (src[i] > mx) mx = src[i];
+  }
+  const double scale = 255.0 * ((double)(mx - mn) > 2.220446049250313e-16 ? 1.0 / (mx - mn) : 0.0);
+  const double shift = 0.0 - mn * scale;
+  const float a = (float)scale, b = (float)shift;
+  for (size_t i = 0; i < n; ++i) dst[i] = sat_u8_f(fmaf((float)src[i], a, b));
+}
+
+/* the EQUALIZE branch of trackEvent (feature_tracker.cpp:375-382) */
+ORA_API void ora_equalize_u8(const uint8_t *src, int W, int H, uint8_t *dst) {
+  uint8_t *tmp = (uint8_t *)malloc((size_t)W * H);
+  ora_clahe_u8(src, W, H, 40.0, 8, tmp);
+  ora_normalize_minmax_u8(tmp, (size_t)W * H, dst);
+  free(tmp);
+}
+
+/* ======================================================================== */
 /* Whole-window tracker: FeatureTracker::trackEvent (feature_tracker.cpp:340-603) */
 /* ======================================================================== */
 
@@ -1071,6 +1213,7 @@ ORA_API const ora_sae *ora_tracker_sae(const ora_tracker *t, int cam) { return t
 ORA_API const uint8_t *ora_tracker_time_surface(const ora_tracker *t, int cam) {
   return t->ts[cam];
 }
+ORA_API const uint8_t *ora_tracker_lk_image(const ora_tracker *t, int cam) { return t->img[cam]; }
 ORA_API void ora_tracker_timers(const ora_tracker *t, double *o) {
   memcpy(o, t->timers, sizeof(t->timers));
 }
@@ -1130,8 +1273,14 @@ ORA_API int ora_tracker_track(ora_tracker *t, double cur_time, const uint16_t *l
   /* HOT LOOP B (:367-368) */
   for (int cam = 0; cam < 2; ++cam) {
     ora_time_surface(t->sae[cam], cur_time, c->decay_ms, c->ignore_polarity, t->ts[cam]);
-    if (c->equalize && t->eq) t->eq(t->ts[cam], W, H, t->img[cam]);
-    else
+    if (c->median_blur_kernel_size > 0) { /* event_detector.cc:262-264 */
+      ora_median_blur_u8(t->ts[cam], W, H, 2 * c->median_blur_kernel_size + 1, t->img[cam]);
+      memcpy(t->ts[cam], t->img[cam], N);
+    }
+    if (c->equalize) { /* feature_tracker.cpp:375-382 */
+      if (t->eq) t->eq(t->ts[cam], W, H, t->img[cam]);
+      else ora_equalize_u8(t->ts[cam], W, H, t->img[cam]);
+    } else
       memcpy(t->img[cam], t->ts[cam], N);
   }
   if (!t->have_prev_img) {

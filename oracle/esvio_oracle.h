@@ -15,6 +15,7 @@
  *   feature_tracker/src/feature_tracker.cpp:48-72                          border test / compaction
  *   feature_tracker/src/feature_tracker.cpp:123-151                        min-distance mask
  *   feature_tracker/src/feature_tracker.cpp:340-603                        per-window orchestration
+ *   feature_tracker/src/feature_tracker.cpp:375-382                        CLAHE + normalize (EQUALIZE)
  *   feature_tracker/src/feature_tracker.cpp:910-947                        F-matrix rejection
  *   feature_tracker/src/feature_tracker.cpp:991-1045                       undistort, velocity
  *   camera_model/src/camera_models/PinholeCamera.cc:450-510,646-662        liftProjective
@@ -88,6 +89,16 @@ void ora_calc_optical_flow_pyr_lk(const uint8_t *prev, const uint8_t *next, int 
                                   int win, int max_level, int max_count, double epsilon,
                                   int use_initial_flow, double min_eig_threshold);
 
+/* ---------------- optional image conditioning (OpenCV imgproc) ---------------- */
+/* cv::medianBlur, CV_8U, BORDER_REPLICATE (event_detector.cc:262-264) */
+void ora_median_blur_u8(const uint8_t *src, int W, int H, int ksize, uint8_t *dst);
+/* cv::createCLAHE(clip, Size(tiles,tiles))->apply (feature_tracker.cpp:377-379) */
+void ora_clahe_u8(const uint8_t *src, int W, int H, double clip_limit, int tiles, uint8_t *dst);
+/* cv::normalize(0, 255, NORM_MINMAX), CV_8U (feature_tracker.cpp:380-381) */
+void ora_normalize_minmax_u8(const uint8_t *src, size_t n, uint8_t *dst);
+/* CLAHE defaults (40, 8x8) + normalize: the EQUALIZE branch of trackEvent */
+void ora_equalize_u8(const uint8_t *src, int W, int H, uint8_t *dst);
+
 /* ---------------- camodocal pinhole ---------------- */
 typedef struct ora_pinhole {
   double fx, fy, cx, cy, k1, k2, p1, p2;
@@ -143,6 +154,8 @@ int ora_tracker_track(ora_tracker *t, double cur_time, const uint16_t *lx, const
 /* views of internal state, for stage-level parity checks */
 const ora_sae *ora_tracker_sae(const ora_tracker *t, int cam);
 const uint8_t *ora_tracker_time_surface(const ora_tracker *t, int cam);
+/* the image handed to LK (the time surface after the optional CLAHE + normalize) */
+const uint8_t *ora_tracker_lk_image(const ora_tracker *t, int cam);
 /* stage timers (seconds, accumulated): 0 sae,1 ts,2 temporal lk,3 ransac+mask+select,4 stereo lk,5 other */
 void ora_tracker_timers(const ora_tracker *t, double *out6);
 

@@ -119,6 +119,10 @@ def lib():
         L.ora_find_fundamental_mask.restype = C.c_int
         L.ora_find_fundamental_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                                 C.c_double, C.c_int, C.c_void_p]
+        L.ora_median_blur_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ora_clahe_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
+        L.ora_normalize_minmax_u8.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ora_equalize_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ora_tracker_create.restype = C.c_void_p
         L.ora_tracker_create.argtypes = [C.POINTER(_Config)]
         L.ora_tracker_destroy.argtypes = [C.c_void_p]
@@ -131,6 +135,8 @@ def lib():
         L.ora_tracker_sae.argtypes = [C.c_void_p, C.c_int]
         L.ora_tracker_time_surface.restype = C.POINTER(C.c_uint8)
         L.ora_tracker_time_surface.argtypes = [C.c_void_p, C.c_int]
+        L.ora_tracker_lk_image.restype = C.POINTER(C.c_uint8)
+        L.ora_tracker_lk_image.argtypes = [C.c_void_p, C.c_int]
         L.ora_tracker_timers.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -199,6 +205,35 @@ class Sae:
                                         min_dist, _p(mask), _p(ts), ts_lk_threshold,
                                         filter_threshold, _p(out), _p(mask_out))
         return out[:k].copy(), mask_out
+
+
+# --------------------------------------------------------------------------- image conditioning
+def median_blur(img, ksize):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().ora_median_blur_u8(_p(img), img.shape[1], img.shape[0], int(ksize), _p(out))
+    return out
+
+
+def clahe(img, clip_limit=40.0, tiles=8):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().ora_clahe_u8(_p(img), img.shape[1], img.shape[0], float(clip_limit), int(tiles), _p(out))
+    return out
+
+
+def normalize_minmax(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().ora_normalize_minmax_u8(_p(img), img.size, _p(out))
+    return out
+
+
+def equalize(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().ora_equalize_u8(_p(img), img.shape[1], img.shape[0], _p(out))
+    return out
 
 
 # --------------------------------------------------------------------------- helpers
@@ -417,6 +452,10 @@ class OracleTracker:
 
     def time_surface(self, cam):
         p = lib().ora_tracker_time_surface(self._h, cam)
+        return np.ctypeslib.as_array(p, shape=(self.H, self.W)).copy()
+
+    def lk_image(self, cam):
+        p = lib().ora_tracker_lk_image(self._h, cam)
         return np.ctypeslib.as_array(p, shape=(self.H, self.W)).copy()
 
     def timers(self):

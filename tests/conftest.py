@@ -38,6 +38,11 @@ def golden_misc():
 
 
 @pytest.fixture(scope="session")
+def golden_imgops():
+    return np.load(os.path.join(GOLDEN, "imgops_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def capi():
     """libesvio_fe.so through ctypes; the GPU tests must run on the native library."""
     from esvio_b200 import _capi

@@ -50,9 +50,9 @@ def test_create_rejects_bad_config_or_missing_gpu(capi):
     c.max_cnt = 0
     assert L.esvio_fe_create(C.byref(c), C.byref(h)) == capi.EINVAL and not h.value
     c.max_cnt = 150
-    c.equalize = 1            # SURVEY.md 8f "next": not built yet -> refused, never ignored
+    c.median_blur_kernel_size = 8   # medianBlur(17): beyond what the kernel stages -> refused
     assert L.esvio_fe_create(C.byref(c), C.byref(h)) == capi.EINVAL
-    c.equalize = 0
+    c.median_blur_kernel_size = 0
     assert L.esvio_fe_create(None, C.byref(h)) == capi.EINVAL
     import torch
     if not torch.cuda.is_available():

@@ -91,3 +91,27 @@ def test_disc_raster(ora, golden_misc):
     ora.fill_disc(m, 3, 36, 10)
     ora.fill_disc(m, 48, 2, 10)
     assert np.array_equal((m == 255).astype(np.uint8), g["disc_clip"])
+
+
+# ---- optional image conditioning of the time surface ----
+IMGOPS_IMAGES = ("ts346", "ts640", "noise173", "noise160", "flat_w8", "ramp_h8", "lowrange")
+
+
+@pytest.mark.parametrize("name", IMGOPS_IMAGES)
+def test_median_blur_matches_cv2(ora, golden_imgops, name):
+    """cv::medianBlur(2k+1) (event_detector.cc:262-264), k = 1..3, bit-exact."""
+    g = golden_imgops
+    for k in (3, 5, 7):
+        assert np.array_equal(ora.median_blur(g[name], k), g[f"{name}_median{k}"]), (name, k)
+
+
+@pytest.mark.parametrize("name", IMGOPS_IMAGES)
+def test_clahe_normalize_matches_cv2(ora, golden_imgops, name):
+    """cv::createCLAHE()->apply + cv::normalize(0,255,MINMAX) (feature_tracker.cpp:375-382),
+    bit-exact, incl. sizes that are not multiples of the 8x8 grid (346x260 pads to 352x264;
+    a dimension that is a multiple gets a whole extra grid step, as OpenCV does)."""
+    g = golden_imgops
+    img = g[name]
+    assert np.array_equal(ora.clahe(img), g[name + "_clahe"])
+    assert np.array_equal(ora.normalize_minmax(img), g[name + "_norm"])
+    assert np.array_equal(ora.equalize(img), g[name + "_clahe_norm"])
