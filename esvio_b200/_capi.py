@@ -35,8 +35,16 @@ class Config(C.Structure):
         ("feature_filter_threshold", C.c_double), ("do_motion_correction", C.c_int32),
         ("focal_length", C.c_double), ("cam", Pinhole * 2), ("device_id", C.c_int32),
         ("max_events_per_window", C.c_int32), ("use_ransac", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("reserved0", C.c_int32),
+        ("mc_fx", C.c_double), ("mc_fy", C.c_double), ("mc_cx", C.c_double), ("mc_cy", C.c_double),
+        ("reserved", C.c_int32 * 6),
     ]
+
+
+class Motion(C.Structure):
+    """esvio_motion: the fields of Motion_correction_value the SAE update reads."""
+    _fields_ = [("state_v", C.c_double * 3), ("v_pre", C.c_float * 3), ("accel", C.c_float * 3),
+                ("omega", C.c_float * 3), ("t1", C.c_double)]
 
 
 class Events(C.Structure):
@@ -79,6 +87,10 @@ SYMBOLS = {
     "esvio_fe_track_submit": (C.c_int, [_H, C.c_double, C.POINTER(Events), C.POINTER(Events),
                                         C.c_int32]),
     "esvio_fe_track_wait": (C.c_int, [_H, C.POINTER(Tracks)]),
+    "esvio_fe_track_mc": (C.c_int, [_H, C.c_double, C.POINTER(Events), C.POINTER(Events), C.c_int32,
+                                    C.POINTER(Motion), C.POINTER(Tracks)]),
+    "esvio_fe_track_submit_mc": (C.c_int, [_H, C.c_double, C.POINTER(Events), C.POINTER(Events),
+                                           C.c_int32, C.POINTER(Motion)]),
     "esvio_fe_time_surface": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_size_t]),
     "esvio_fe_host_alloc": (C.c_void_p, [C.c_size_t]),
     "esvio_fe_host_free": (None, [C.c_void_p]),
@@ -92,6 +104,10 @@ SYMBOLS = {
     "esvio_fe_kernel_launches": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "esvio_fe_get_sae": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
     "esvio_fe_stage_update": (C.c_int, [_H, C.c_double, C.POINTER(Events), C.POINTER(Events)]),
+    "esvio_fe_stage_update_mc": (C.c_int, [_H, C.c_double, C.POINTER(Events), C.POINTER(Events),
+                                           C.POINTER(Motion)]),
+    "esvio_fe_stage_motion_correct": (C.c_int, [_H, C.POINTER(Motion), C.c_void_p, C.c_int32,
+                                                C.c_void_p]),
     "esvio_fe_stage_corner_flags": (C.c_int, [_H, C.POINTER(Events), C.c_int32, C.c_void_p]),
     "esvio_fe_get_pyramid_level": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, _pi, _pi]),
     "esvio_fe_stage_lk": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -41,6 +41,11 @@ struct DevEvents {
   const uint8_t* p;
   const uint4* aos;  // dvs_msgs::Event records (feature_tracker/src/dvs_msgs/Event.h:42-52)
   int n;
+  // motion-compensated pixel of every event (k_warp_events); null = use x, y as they are.
+  // Only the SAE update sees these; corner detection keeps the raw coordinates like the
+  // reference (feature_tracker.cpp:740 passes event_left itself).
+  const uint16_t* wx;
+  const uint16_t* wy;
 };
 
 struct Ev {
@@ -63,6 +68,10 @@ __device__ __forceinline__ Ev load_event(const DevEvents& e, int i) {
     r.y = __ldg(e.y + i);
     r.t = __ldg(e.t + i);
     r.p = __ldg(e.p + i) ? 1 : 0;
+  }
+  if (e.wx) {
+    r.x = __ldg(e.wx + i);
+    r.y = __ldg(e.wy + i);
   }
   return r;
 }
@@ -182,6 +191,21 @@ struct EventStageBuffers {
 
 void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents ev[2],
                        cudaStream_t s, int64_t* launches);
+
+// Motion_correction_value (feature_tracker.h:35) as the SAE update reads it
+struct McParams {
+  float v_cur[3], v_pre[3], omega[3];
+  float K[4];   // fx, fy, cx, cy of EventDetector::intrinsics_matrix
+  double t1;    // left header stamp
+  int W, H;
+};
+// createSAE_*(..., measurements) coordinates (event_detector.cc:102-147,168-210,547-591) for
+// both cameras: wx/wy[cam][i]; t0 = time of the first left event
+void launch_warp_events(const McParams& P, const DevEvents ev[2], uint16_t* const wx[2],
+                        uint16_t* const wy[2], cudaStream_t s, int64_t* launches);
+// the warp on caller-supplied (x, y, dt) triples (parity tests)
+void launch_warp_points(const McParams& P, const float* xy_dt, int n, int* out_xy, cudaStream_t s,
+                        int64_t* launches);
 
 struct SaeTsParams {
   int W, H, tiles_x, n_tiles;

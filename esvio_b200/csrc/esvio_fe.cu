@@ -3,6 +3,7 @@
 // FeatureTracker::trackEvent (feature_tracker/src/feature_tracker.cpp:340-603).
 // There is no CPU path in this library: every stage is a kernel from events.cu,
 // pyramid.cu, lk.cu, select.cu, ransac.cu.
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -42,6 +43,8 @@ struct esvio_fe {
   uint8_t* clahe_lut;
   int* clahe_minmax;
   const uint8_t* ts_sel[2];
+  uint16_t* warp_xy[2][2];  // [x|y][camera]: motion-compensated pixels of the window's events
+  float mc_K[4];
   int cur_left;   // index (0..2) of the newest left pyramid; prev_left is the one before it
   int prev_left;
   int cur_right;  // 3..5
@@ -188,6 +191,7 @@ static void free_all(esvio_fe* fe) {
   for (int i = 0; i < 3; ++i) cudaFree(fe->aux[i][0]), cudaFree(fe->aux[i][1]);
   cudaFree(fe->clahe_lut);
   cudaFree(fe->clahe_minmax);
+  for (int i = 0; i < 2; ++i) cudaFree(fe->warp_xy[i][0]), cudaFree(fe->warp_xy[i][1]);
   for (int i = 0; i < kSlots; ++i) {
     cudaFree(fe->raw[i][0]);
     cudaFree(fe->raw[i][1]);
@@ -255,7 +259,6 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   if (cfg->max_cnt < 1 || cfg->max_cnt > kMaxCnt) return ESVIO_FE_EINVAL;
   if (cfg->min_dist < 1 || cfg->min_dist > 64) return ESVIO_FE_EINVAL;
   if (cfg->median_blur_kernel_size < 0 || cfg->median_blur_kernel_size > 7) return ESVIO_FE_EINVAL;
-  if (cfg->do_motion_correction) return ESVIO_FE_EINVAL;  // SURVEY.md 8f rank 2, not built yet
   if (cfg->max_events_per_window < 1) return ESVIO_FE_EINVAL;
   if (!(cfg->decay_ms > 0.0)) return ESVIO_FE_EINVAL;
   int ndev = 0;
@@ -325,6 +328,9 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(cudaEventCreateWithFlags(&fe->e_done[c], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&fe->t1_done[c], cudaEventDisableTiming));
   }
+  if (cfg->do_motion_correction)
+    for (int i = 0; i < 2; ++i)
+      for (int c = 0; c < 2; ++c) CUC(cudaMalloc(&fe->warp_xy[i][c], (size_t)fe->cap * sizeof(uint16_t)));
   for (int c = 0; c < 2; ++c) {
     CUC(cudaMalloc(&fe->esb.bt[c], (size_t)fe->cap * sizeof(double)));
     CUC(cudaMalloc(&fe->esb.bk[c], (size_t)fe->cap * sizeof(uint16_t)));
@@ -393,6 +399,13 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 2; ++i) CUC(cudaEventCreate(&fe->pev[k][i]));
 #undef CUC
 
+  if (cfg->mc_fx > 0.0) {
+    fe->mc_K[0] = (float)cfg->mc_fx, fe->mc_K[1] = (float)cfg->mc_fy;
+    fe->mc_K[2] = (float)cfg->mc_cx, fe->mc_K[3] = (float)cfg->mc_cy;
+  } else {
+    fe->mc_K[0] = (float)cfg->cam[1].fx, fe->mc_K[1] = (float)cfg->cam[1].fy;
+    fe->mc_K[2] = (float)(fe->W / 2), fe->mc_K[3] = (float)(fe->H / 2);
+  }
   TrackParams& P = fe->tp;
   P.W = fe->W;
   P.H = fe->H;
@@ -488,9 +501,35 @@ static void prof_mark(esvio_fe* fe, int i) {
 
 // createSAE_* + SAEtoTimeSurface_* + pyramids (feature_tracker.cpp:356-368) into the
 // pyramid buffers `left_idx` / right
-static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev[2], int left_idx,
-                           int right_idx) {
+static McParams mc_params(const esvio_fe* fe, const esvio_motion* mc) {
+  McParams p;
+  for (int i = 0; i < 3; ++i) {
+    p.v_cur[i] = (float)mc->state_v[i];  // temp_v[i] = State[i] (event_detector.cc:113-116)
+    p.v_pre[i] = mc->v_pre[i];
+    p.omega[i] = mc->omega[i];
+  }
+  for (int i = 0; i < 4; ++i) p.K[i] = fe->mc_K[i];
+  p.t1 = mc->t1;
+  p.W = fe->W;
+  p.H = fe->H;
+  return p;
+}
+
+// sqrt(pow(a0,2) + pow(a1,2) + pow(a2,2)) > a_motion_compensation_threshold
+// (event_detector.cc:125, event_detector.h:51), in double like std::pow(float, int)
+static bool mc_active(const esvio_motion* mc) {
+  const double a0 = mc->accel[0], a1 = mc->accel[1], a2 = mc->accel[2];
+  return sqrt(a0 * a0 + a1 * a1 + a2 * a2) > 5.0;
+}
+
+static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev_in[2], int left_idx,
+                           int right_idx, const esvio_motion* mc = nullptr) {
   cudaStream_t se = fe->stream_e;
+  DevEvents ev[2] = {ev_in[0], ev_in[1]};
+  if (mc && mc_active(mc) && ev[0].n > 0) {
+    launch_warp_events(mc_params(fe, mc), ev_in, fe->warp_xy[0], fe->warp_xy[1], se, &fe->launches);
+    for (int c = 0; c < 2; ++c) ev[c].wx = fe->warp_xy[0][c], ev[c].wy = fe->warp_xy[1][c];
+  }
   launch_bin_events(fe->bl, fe->esb, ev, se, &fe->launches);
   prof_mark(fe, 2);
   SaeTsParams sp;
@@ -552,7 +591,15 @@ static CornerParams corner_params(esvio_fe* fe, int left_idx, int and_ts) {
 
 FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_events* left,
                                  const esvio_events* right, int32_t pub_this_frame) {
+  return esvio_fe_track_submit_mc(fe, cur_time, left, right, pub_this_frame, nullptr);
+}
+
+FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_events* left,
+                                    const esvio_events* right, int32_t pub_this_frame,
+                                    const esvio_motion* mc) {
   if (!fe) return ESVIO_FE_EINVAL;
+  if (mc && !fe->cfg.do_motion_correction)
+    return fail(fe, ESVIO_FE_ESTATE, "motion compensation needs config.do_motion_correction", cudaSuccess);
   if (fe->q_count >= kSlots)
     return fail(fe, ESVIO_FE_ESTATE, "three windows already in flight", cudaSuccess);
   CU(cudaSetDevice(fe->dev));
@@ -574,7 +621,7 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   const int cur = fe->windows == 0 ? 0 : (fe->cur_left + 1) % 3;
   const int prev = fe->windows == 0 ? 0 : fe->cur_left;  // first window: prev_img = cur_img
   const int rcur = fe->windows == 0 ? 3 : 3 + (fe->cur_right - 3 + 1) % 3;
-  if ((rc = run_event_stage(fe, cur_time, ev, cur, rcur)) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, cur_time, ev, cur, rcur, mc)) != ESVIO_FE_OK) return rc;
   prof_mark(fe, 4);
   if (pub_this_frame)
     launch_corner_flags(corner_params(fe, cur, 1), ev[0], fe->flags[slot], se, &fe->launches);
@@ -665,9 +712,15 @@ FE_API int esvio_fe_track_wait(esvio_fe* fe, esvio_tracks* out) {
 
 FE_API int esvio_fe_track(esvio_fe* fe, double cur_time, const esvio_events* left,
                           const esvio_events* right, int32_t pub_this_frame, esvio_tracks* out) {
+  return esvio_fe_track_mc(fe, cur_time, left, right, pub_this_frame, nullptr, out);
+}
+
+FE_API int esvio_fe_track_mc(esvio_fe* fe, double cur_time, const esvio_events* left,
+                             const esvio_events* right, int32_t pub_this_frame,
+                             const esvio_motion* mc, esvio_tracks* out) {
   if (!fe || !out) return ESVIO_FE_EINVAL;
   if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "track while windows are in flight", cudaSuccess);
-  const int rc = esvio_fe_track_submit(fe, cur_time, left, right, pub_this_frame);
+  const int rc = esvio_fe_track_submit_mc(fe, cur_time, left, right, pub_this_frame, mc);
   if (rc != ESVIO_FE_OK) return rc;
   return esvio_fe_track_wait(fe, out);
 }
@@ -762,7 +815,36 @@ FE_API int esvio_fe_get_sae(esvio_fe* fe, int32_t cam, int32_t plane, double* ds
 
 FE_API int esvio_fe_stage_update(esvio_fe* fe, double t_ref, const esvio_events* left,
                                  const esvio_events* right) {
+  return esvio_fe_stage_update_mc(fe, t_ref, left, right, nullptr);
+}
+
+FE_API int esvio_fe_stage_motion_correct(esvio_fe* fe, const esvio_motion* mc, const float* xy_dt,
+                                         int32_t n, int32_t* out_xy) {
+  if (!fe || !mc || !xy_dt || !out_xy || n < 0) return ESVIO_FE_EINVAL;
+  if (n == 0) return ESVIO_FE_OK;
+  CU(cudaSetDevice(fe->dev));
+  cudaStream_t s = fe->stream;
+  float* d_in = nullptr;
+  int* d_out = nullptr;
+  CU(cudaMalloc(&d_in, sizeof(float) * 3 * (size_t)n));
+  cudaError_t ce = cudaMalloc(&d_out, sizeof(int) * 2 * (size_t)n);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_in, xy_dt, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) {
+    launch_warp_points(mc_params(fe, mc), d_in, n, d_out, s, &fe->launches);
+    ce = cudaMemcpyAsync(out_xy, d_out, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  CU(ce);
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_stage_update_mc(esvio_fe* fe, double t_ref, const esvio_events* left,
+                                    const esvio_events* right, const esvio_motion* mc) {
   if (!fe) return ESVIO_FE_EINVAL;
+  if (mc && !fe->cfg.do_motion_correction)
+    return fail(fe, ESVIO_FE_ESTATE, "motion compensation needs config.do_motion_correction", cudaSuccess);
   if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "windows in flight", cudaSuccess);
   CU(cudaSetDevice(fe->dev));
   DevEvents ev[2];
@@ -770,7 +852,7 @@ FE_API int esvio_fe_stage_update(esvio_fe* fe, double t_ref, const esvio_events*
   if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
   if ((rc = stage_events(fe, 0, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
   if ((rc = stage_events(fe, 0, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
-  if ((rc = run_event_stage(fe, t_ref, ev, fe->cur_left, fe->cur_right)) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, t_ref, ev, fe->cur_left, fe->cur_right, mc)) != ESVIO_FE_OK) return rc;
   CU(cudaStreamSynchronize(fe->stream_e));
   return ESVIO_FE_OK;
 }

@@ -12,6 +12,252 @@
 namespace esvio {
 
 // =====================================================================================
+// Motion compensation: EventDetector::motioncorrection (event_detector.cc:547-591)
+// =====================================================================================
+// The reference evaluates this with Eigen fixed-size float types; the order of the float
+// operations below is the oracle's restatement of Eigen 3.3's kernels (oracle/esvio_oracle.c,
+// "Motion-compensated SAE update"), so the two agree bit for bit (-fmad=false).
+__device__ __forceinline__ float dot3f(float a0, float b0, float a1, float b1, float a2, float b2) {
+  return a0 * b0 + (a1 * b1 + a2 * b2);
+}
+__device__ __forceinline__ void mat3_mul_f(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      C[i * 3 + j] = dot3f(A[i * 3], B[j], A[i * 3 + 1], B[3 + j], A[i * 3 + 2], B[6 + j]);
+}
+__device__ __forceinline__ void mat3_vec_f(const float* A, const float* v, float* o) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = dot3f(A[i * 3], v[0], A[i * 3 + 1], v[1], A[i * 3 + 2], v[2]);
+}
+__device__ __forceinline__ float cof3f(const float* m, int i, int j) {
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+}
+__device__ __forceinline__ void mat3_inv_f(const float* m, float* r) {
+  const float c0 = cof3f(m, 0, 0), c1 = cof3f(m, 1, 0), c2 = cof3f(m, 2, 0);
+  const float det = dot3f(c0, m[0], c1, m[3], c2, m[6]);
+  const float invdet = 1.0f / det;
+  r[0] = c0 * invdet;
+  r[1] = c1 * invdet;
+  r[2] = c2 * invdet;
+  r[3] = cof3f(m, 0, 1) * invdet;
+  r[4] = cof3f(m, 1, 1) * invdet;
+  r[5] = cof3f(m, 2, 1) * invdet;
+  r[6] = cof3f(m, 0, 2) * invdet;
+  r[7] = cof3f(m, 1, 2) * invdet;
+  r[8] = cof3f(m, 2, 2) * invdet;
+}
+
+// Matrix3f::exp(): Pade 3/5/7 by L1 norm, scaling and squaring, partial-pivot LU solve
+__device__ void mat3_exp_f(const float* A_in, float* R) {
+  float A[9], A2[9], A4[9], A6[9], tmp[9], U[9], V[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = A_in[i];
+  float l1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float cs = fabsf(A[j]) + (fabsf(A[3 + j]) + fabsf(A[6 + j]));
+    if (cs > l1) l1 = cs;
+  }
+  int squarings = 0;
+  if (l1 < 4.258730016922831e-001f) {
+    mat3_mul_f(A, A, A2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float id = (i % 4 == 0) ? 1.f : 0.f;
+      tmp[i] = 1.f * A2[i] + 60.f * id;
+      V[i] = 12.f * A2[i] + 120.f * id;
+    }
+    mat3_mul_f(A, tmp, U);
+  } else if (l1 < 1.880152677804762e+000f) {
+    mat3_mul_f(A, A, A2);
+    mat3_mul_f(A2, A2, A4);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float id = (i % 4 == 0) ? 1.f : 0.f;
+      tmp[i] = 1.f * A4[i] + 420.f * A2[i] + 15120.f * id;
+      V[i] = 30.f * A4[i] + 3360.f * A2[i] + 30240.f * id;
+    }
+    mat3_mul_f(A, tmp, U);
+  } else {
+    frexpf(l1 / 3.925724783138660f, &squarings);
+    if (squarings < 0) squarings = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = ldexpf(A[i], -squarings);
+    mat3_mul_f(A, A, A2);
+    mat3_mul_f(A2, A2, A4);
+    mat3_mul_f(A4, A2, A6);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float id = (i % 4 == 0) ? 1.f : 0.f;
+      tmp[i] = 1.f * A6[i] + 1512.f * A4[i] + 277200.f * A2[i] + 8648640.f * id;
+      V[i] = 56.f * A6[i] + 25200.f * A4[i] + 1995840.f * A2[i] + 17297280.f * id;
+    }
+    mat3_mul_f(A, tmp, U);
+  }
+  float lu[9], x[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    x[i] = U[i] + V[i];
+    lu[i] = -U[i] + V[i];
+  }
+  int piv[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int best = k;
+    float score = fabsf(lu[k * 3 + k]);
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i)
+      if (fabsf(lu[i * 3 + k]) > score) {
+        score = fabsf(lu[i * 3 + k]);
+        best = i;
+      }
+    piv[k] = best;
+    if (score != 0.f) {
+#pragma unroll
+      for (int i = k + 1; i < 3; ++i)
+        if (best == i) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float t = lu[k * 3 + j];
+            lu[k * 3 + j] = lu[i * 3 + j];
+            lu[i * 3 + j] = t;
+          }
+        }
+#pragma unroll
+      for (int i = k + 1; i < 3; ++i) lu[i * 3 + k] /= lu[k * 3 + k];
+    }
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i)
+#pragma unroll
+      for (int j = k + 1; j < 3; ++j) lu[i * 3 + j] -= lu[i * 3 + k] * lu[k * 3 + j];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i)
+      if (piv[k] == i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float t = x[k * 3 + j];
+          x[k * 3 + j] = x[i * 3 + j];
+          x[i * 3 + j] = t;
+        }
+      }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float b = x[k * 3 + j];
+#pragma unroll
+      for (int i = k + 1; i < 3; ++i) x[i * 3 + j] -= b * lu[i * 3 + k];
+    }
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    const float a = 1.0f / lu[k * 3 + k];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float b = (x[k * 3 + j] *= a);
+#pragma unroll
+      for (int i = 0; i < k; ++i) x[i * 3 + j] -= b * lu[i * 3 + k];
+    }
+  }
+  for (int s = 0; s < squarings; ++s) {
+    float t[9];
+    mat3_mul_f(x, x, t);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = t[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = x[i];
+}
+
+__device__ void motion_correct(const McParams& m, double ex, double ey, double dt, int* ox, int* oy) {
+  *ox = (int)ex;
+  *oy = (int)ey;
+  const int border = 6;
+  if (!(ex > border && ex <= (m.W - border) && ey > border && ey <= (m.H - border))) return;
+  const float fdt = (float)dt;
+  const float rv[3] = {m.omega[0] * fdt, m.omega[1] * fdt, m.omega[2] * fdt};
+  const float skew[9] = {0.f, -rv[2], rv[1], rv[2], 0.f, -rv[0], -rv[1], rv[0], 0.f};
+  const float K[9] = {m.K[0], 0.f, m.K[2], 0.f, m.K[1], m.K[3], 0.f, 0.f, 1.f};
+  float R[9], Rt[9], Kinv[9], KR[9], rotK[9];
+  mat3_exp_f(skew, R);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rt[i * 3 + j] = R[j * 3 + i];
+  mat3_inv_f(K, Kinv);
+  mat3_mul_f(K, Rt, KR);
+  mat3_mul_f(KR, Kinv, rotK);
+  const float c = (float)(0.5 * dt);
+  float tr[3], w[3], nrotK[9], transK[3], o[3];
+  const float ev[3] = {(float)ex, (float)ey, 1.f};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tr[i] = c * (m.v_cur[i] + m.v_pre[i]);
+  mat3_vec_f(Kinv, tr, w);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) nrotK[i] = -rotK[i];
+  mat3_vec_f(nrotK, w, transK);
+  mat3_vec_f(rotK, ev, o);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = o[i] + transK[i];
+  o[0] = o[0] / o[2];
+  o[1] = o[1] / o[2];
+  const int x = (int)floorf(o[0]), y = (int)floorf(o[1]);
+  if (x > 0 && x < m.W - 1 && y > 0 && y < m.H - 1) {
+    *ox = x;
+    *oy = y;
+  }
+}
+
+// trackEvent(..., measurements), feature_tracker.cpp:628-642: an event is warped iff
+// dt_window > 0 and (t - t0) / dt_window < 1 (the |accel| > 5 gate is applied by the caller,
+// which only launches this kernel when it holds)
+__global__ void __launch_bounds__(256)
+k_warp_events(McParams P, DevEvents ev0, DevEvents ev1, uint16_t* __restrict__ wx0,
+              uint16_t* __restrict__ wy0, uint16_t* __restrict__ wx1, uint16_t* __restrict__ wy1) {
+  const int cam = blockIdx.y;
+  const DevEvents& ev = cam ? ev1 : ev0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ev.n) return;
+  const double t0 = load_event(ev0, 0).t;  // first LEFT event, for both cameras
+  const double dtw = P.t1 - t0;
+  const Ev e = load_event(ev, i);
+  int x = e.x, y = e.y;
+  if (dtw > 0 && (e.t - t0) / dtw < 1 && x < P.W && y < P.H) motion_correct(P, x, y, e.t - t0, &x, &y);
+  (cam ? wx1 : wx0)[i] = (uint16_t)x;
+  (cam ? wy1 : wy0)[i] = (uint16_t)y;
+}
+
+void launch_warp_events(const McParams& P, const DevEvents ev[2], uint16_t* const wx[2],
+                        uint16_t* const wy[2], cudaStream_t s, int64_t* launches) {
+  const int n = ev[0].n > ev[1].n ? ev[0].n : ev[1].n;
+  if (n <= 0 || ev[0].n <= 0) return;
+  k_warp_events<<<dim3((n + 255) / 256, 2), 256, 0, s>>>(P, ev[0], ev[1], wx[0], wy[0], wx[1], wy[1]);
+  ++*launches;
+}
+
+__global__ void __launch_bounds__(128)
+k_warp_points(McParams P, const float* __restrict__ xy_dt, int n, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x, y;
+  motion_correct(P, (double)xy_dt[3 * i], (double)xy_dt[3 * i + 1], (double)xy_dt[3 * i + 2], &x, &y);
+  out[2 * i] = x;
+  out[2 * i + 1] = y;
+}
+
+void launch_warp_points(const McParams& P, const float* xy_dt, int n, int* out_xy, cudaStream_t s,
+                        int64_t* launches) {
+  if (n <= 0) return;
+  k_warp_points<<<(n + 127) / 128, 128, 0, s>>>(P, xy_dt, n, out_xy);
+  ++*launches;
+}
+
+// =====================================================================================
 // K0: stable counting sort by fine tile
 // =====================================================================================
 // Same-pixel events must be applied in stream order (acceptance of an event depends on
@@ -44,7 +290,10 @@ k_bin_hist(BinLayout L, DevEvents ev0, DevEvents ev1, uint32_t* __restrict__ cou
     const int i = base + k * kChunkThreads + threadIdx.x;
     if (i < ev.n) {
       int x, y;
-      if (ev.aos) {
+      if (ev.wx) {
+        x = __ldg(ev.wx + i);
+        y = __ldg(ev.wy + i);
+      } else if (ev.aos) {
         const uint32_t xy = __ldg(reinterpret_cast<const uint32_t*>(ev.aos + i));
         x = xy & 0xffffu;
         y = xy >> 16;

@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import Config, Events, FrontEndError, Pinhole, Tracks
+from ._capi import Config, Events, FrontEndError, Motion, Pinhole, Tracks
 
 AOS_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("sec", "<u4"), ("nsec", "<u4"), ("p", "u1"),
                       ("pad", "V3")])
@@ -30,7 +30,7 @@ def make_config(cfg: dict) -> Config:
         if k in cfg:
             setattr(c, k, int(cfg[k]))
     for k in ("f_threshold", "ts_lk_threshold", "decay_ms", "feature_filter_threshold",
-              "focal_length"):
+              "focal_length", "mc_fx", "mc_fy", "mc_cx", "mc_cy"):
         if k in cfg:
             setattr(c, k, float(cfg[k]))
     if "cam" in cfg:
@@ -38,6 +38,19 @@ def make_config(cfg: dict) -> Config:
             cam = cfg["cam"][i]
             c.cam[i] = Pinhole(*[float(cam[k]) for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")])
     return c
+
+
+def make_motion(m) -> Motion:
+    """dict(state_v, v_pre, accel, omega, t1) -> esvio_motion (Motion_correction_value,
+    feature_tracker.h:35)."""
+    if isinstance(m, Motion):
+        return m
+    o = Motion()
+    for k in ("state_v", "v_pre", "accel", "omega"):
+        for i in range(3):
+            getattr(o, k)[i] = float(m[k][i])
+    o.t1 = float(m["t1"])
+    return o
 
 
 class _Ev:
@@ -183,10 +196,13 @@ class EventFrontEnd:
                             n_new=s.n_new, ransac_iters=s.ransac_iters)
         return out
 
-    def track(self, cur_time, left, right, pub_this_frame=True):
+    def track(self, cur_time, left, right, pub_this_frame=True, motion=None):
         l, r = _Ev(left), _Ev(right)
-        self._chk(_capi.lib().esvio_fe_track(self._h, float(cur_time), C.byref(l.s), C.byref(r.s),
-                                             int(bool(pub_this_frame)), C.byref(self._t)), "track")
+        m = make_motion(motion) if motion is not None else None
+        self._chk(_capi.lib().esvio_fe_track_mc(self._h, float(cur_time), C.byref(l.s), C.byref(r.s),
+                                                int(bool(pub_this_frame)),
+                                                C.byref(m) if m is not None else None,
+                                                C.byref(self._t)), "track")
         return self._unpack()
 
     def track_raw(self, cur_time, l: _Ev, r: _Ev, pub_this_frame=True):
@@ -252,10 +268,23 @@ class EventFrontEnd:
             out.append(a)
         return out
 
-    def stage_update(self, t_ref, left, right):
+    def stage_update(self, t_ref, left, right, motion=None):
         l, r = _Ev(left), _Ev(right)
-        self._chk(_capi.lib().esvio_fe_stage_update(self._h, float(t_ref), C.byref(l.s),
-                                                    C.byref(r.s)), "stage_update")
+        m = make_motion(motion) if motion is not None else None
+        self._chk(_capi.lib().esvio_fe_stage_update_mc(self._h, float(t_ref), C.byref(l.s),
+                                                       C.byref(r.s),
+                                                       C.byref(m) if m is not None else None),
+                  "stage_update")
+
+    def stage_motion_correct(self, motion, xy_dt):
+        """EventDetector::motioncorrection on (x, y, dt) triples -> (n, 2) int pixels."""
+        a = np.ascontiguousarray(xy_dt, np.float32).reshape(-1, 3)
+        out = np.zeros((len(a), 2), np.int32)
+        m = make_motion(motion)
+        self._chk(_capi.lib().esvio_fe_stage_motion_correct(self._h, C.byref(m), a.ctypes.data,
+                                                            len(a), out.ctypes.data),
+                  "stage_motion_correct")
+        return out
 
     def stage_corner_flags(self, left, and_ts_test=False):
         l = _Ev(left)
@@ -354,8 +383,10 @@ class FeatureTracker:
         self.right_pts_velocity = np.zeros((0, 2), np.float32)
         self.stats = {}
 
-    def trackEvent(self, _cur_time, event_left, event_right):
-        r = self.fe.track(_cur_time, event_left, event_right, self.PUB_THIS_FRAME)
+    def trackEvent(self, _cur_time, event_left, event_right, measurements=None):
+        """Both overloads of FeatureTracker::trackEvent (feature_tracker.h:51-52):
+        `measurements` is the Motion_correction_value of the motion-compensated one."""
+        r = self.fe.track(_cur_time, event_left, event_right, self.PUB_THIS_FRAME, measurements)
         self.prev_time, self.cur_time = self.cur_time, float(_cur_time)
         self.ids, self.track_cnt = r["id"], r["track_cnt"]
         self.cur_pts = np.stack([r["u"], r["v"]], 1)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ESVIO_FE_ABI_VERSION 1
+#define ESVIO_FE_ABI_VERSION 2
 
 typedef enum esvio_status {
   ESVIO_FE_OK = 0,
@@ -58,14 +58,33 @@ typedef struct esvio_fe_config {
   int32_t ignore_polarity;         /* para_ignore_polarity */
   int32_t median_blur_kernel_size; /* para_median_blur_kernel_size k: medianBlur(2k+1), 0..7 */
   double feature_filter_threshold; /* para_feature_filter_threshold */
-  int32_t do_motion_correction;    /* Do_motion_correction (must be 0 in round 1) */
+  int32_t do_motion_correction;    /* Do_motion_correction: 1 allows esvio_fe_track_mc (allocates the warp scratch) */
   double focal_length;             /* FOCAL_LENGTH = 460 (parameters.cpp:274) */
   esvio_pinhole cam[2];            /* left, right */
   int32_t device_id;
   int32_t max_events_per_window;   /* per camera; staging capacity */
   int32_t use_ransac;              /* 1 = rejectWithF_event enabled (reference behaviour) */
-  int32_t reserved[7];
+  int32_t reserved0;
+  /* EventDetector::intrinsics_matrix of the motion compensation (event_detector.cc:95-97):
+   * the globals fx, fy, cx, cy left by stereo_readIntrinsicParameter
+   * (feature_tracker.cpp:963-976), i.e. the LAST camera's rectified K.  mc_fx <= 0 selects
+   * that default: (float)cam[1].fx, (float)cam[1].fy, width / 2, height / 2 (integer halves,
+   * PinholeCamera.cc:750-767). */
+  double mc_fx, mc_fy, mc_cx, mc_cy;
+  int32_t reserved[6];
 } esvio_fe_config;
+
+/* The fields of the reference's Motion_correction_value (feature_tracker.h:35, packed at
+ * stereo_event_tracker_node.cpp:252) that the SAE update reads. */
+typedef struct esvio_motion {
+  double state_v[3]; /* State_[0..2]: current linear velocity from odometry (node.cpp:209-216) */
+  float v_pre[3];    /* previous velocity (node.cpp:218-220) */
+  float accel[3];    /* temp_a: velocity-differenced acceleration (node.cpp:230-232); the warp
+                      * is applied only when its norm exceeds 5 m/s^2 (event_detector.cc:125) */
+  float omega[3];    /* IMU angular velocity (node.cpp:243-245) */
+  double t1;         /* left EventArray header stamp (feature_tracker.cpp:620); the window's
+                      * first left event time t0 is read from the events themselves (:619) */
+} esvio_motion;
 
 /* One camera's events for one window (dvs_msgs/EventArray.events).
  * Either SoA (x,y,t,p all non-NULL) or AoS (`aos` non-NULL): an array of
@@ -149,6 +168,18 @@ int esvio_fe_track(esvio_fe *fe, double cur_time, const esvio_events *left,
 int esvio_fe_track_submit(esvio_fe *fe, double cur_time, const esvio_events *left,
                           const esvio_events *right, int32_t pub_this_frame);
 int esvio_fe_track_wait(esvio_fe *fe, esvio_tracks *out);
+/* replaces FeatureTracker::trackEvent(cur_time, event_left, event_right, measurements)
+ * (feature_tracker.h:52; feature_tracker.cpp:605-877; call site
+ * stereo_event_tracker_node.cpp:254): the SAE update warps every event of the window back to
+ * the first event's time (EventDetector::motioncorrection, event_detector.cc:547-591) when
+ * |accel| > 5; everything after the SAE update is the plain path.  `mc` == NULL is the plain
+ * call.  Needs config.do_motion_correction = 1. */
+int esvio_fe_track_mc(esvio_fe *fe, double cur_time, const esvio_events *left,
+                      const esvio_events *right, int32_t pub_this_frame, const esvio_motion *mc,
+                      esvio_tracks *out);
+int esvio_fe_track_submit_mc(esvio_fe *fe, double cur_time, const esvio_events *left,
+                             const esvio_events *right, int32_t pub_this_frame,
+                             const esvio_motion *mc);
 
 /* replaces FeatureTracker::gettimesurface() (feature_tracker.cpp:894-897): the
  * CV_8U time surface of the last window; dst has `stride` bytes per row. */
@@ -184,6 +215,13 @@ int esvio_fe_get_sae(esvio_fe *fe, int32_t cam, int32_t plane, double *dst);
 /* createSAE_* + SAEtoTimeSurface_* + pyramids only (feature_tracker.cpp:356-368) */
 int esvio_fe_stage_update(esvio_fe *fe, double t_ref, const esvio_events *left,
                           const esvio_events *right);
+/* createSAE_*(..., measurements) + SAEtoTimeSurface_* + pyramids (feature_tracker.cpp:628-645) */
+int esvio_fe_stage_update_mc(esvio_fe *fe, double t_ref, const esvio_events *left,
+                             const esvio_events *right, const esvio_motion *mc);
+/* EventDetector::motioncorrection (event_detector.cc:547-591) on n caller triples
+ * (x, y, dt): out_xy gets n (x, y) int pairs */
+int esvio_fe_stage_motion_correct(esvio_fe *fe, const esvio_motion *mc, const float *xy_dt,
+                                  int32_t n, int32_t *out_xy);
 /* EventDetector::isCorner for every left event against the current SAE
  * (event_detector.cc:308-544); flags[i] in {0,1}.  If and_ts_test != 0 the
  * TS != TS_LK_threshold test of feature_tracker.cpp:26 is ANDed in. */

@@ -11,6 +11,7 @@
  *   feature_tracker/src/event_detector/event_detector.cc:149-166,212-228  SAE update
  *   feature_tracker/src/event_detector/event_detector.cc:230-305          time surface
  *   feature_tracker/src/event_detector/event_detector.cc:308-544          Arc* corner test
+ *   feature_tracker/src/event_detector/event_detector.cc:102-147,168-210,547-591  motion-compensated SAE
  *   feature_tracker/src/feature_tracker.cpp:13-38                          corner selection
  *   feature_tracker/src/feature_tracker.cpp:48-72                          border test / compaction
  *   feature_tracker/src/feature_tracker.cpp:123-151                        min-distance mask
@@ -63,6 +64,25 @@ int ora_is_corner(const ora_sae *s, double t, int x, int y, int p, double filter
 void ora_corner_flags(const ora_sae *s, const uint16_t *x, const uint16_t *y, const double *t,
                       const uint8_t *p, size_t n, double filter_threshold, int min_dist,
                       uint8_t *flags);
+
+/* ---------------- motion-compensated SAE (event_detector.cc:102-147,168-210,547-591) ------ */
+/* The fields of the reference's Motion_correction_value (feature_tracker.h:35) that the path
+ * reads, plus the detector's intrinsics_matrix (event_detector.cc:95-97). */
+typedef struct ora_motion {
+  double state_v[3]; /* State[0..2]: current velocity (double, cast to float, ed.cc:113-116) */
+  float v_pre[3];    /* previous velocity */
+  float accel[3];    /* "accel_avg_": the velocity-differenced acceleration (node.cpp:230-232) */
+  float omega[3];    /* IMU angular velocity */
+  double t1;         /* left EventArray header stamp (feature_tracker.cpp:620) */
+  float K[4];        /* fx, fy, cx, cy of intrinsics_matrix */
+} ora_motion;
+void ora_mat3_exp_f(const float *A /*9, row-major*/, float *R);
+void ora_motion_correct(const ora_motion *m, int W, int H, double ex, double ey, double dt,
+                        int *ox, int *oy);
+int ora_motion_active(const ora_motion *m);
+void ora_sae_update_mc(ora_sae *s, const uint16_t *x, const uint16_t *y, const double *t,
+                       const uint8_t *p, size_t n, double filter_threshold, const ora_motion *m,
+                       double t0);
 
 /* ---------------- raster helpers (OpenCV drawing.cpp Circle, filled) ---------------- */
 /* half_width[k] for k=0..r : row offset k from the centre is filled on [cx-hw, cx+hw]. */
@@ -151,6 +171,10 @@ int ora_tracker_track(ora_tracker *t, double cur_time, const uint16_t *lx, const
                       const double *lt, const uint8_t *lp, size_t nl, const uint16_t *rx,
                       const uint16_t *ry, const double *rt, const uint8_t *rp, size_t nr,
                       int pub_this_frame, ora_tracks *out);
+int ora_tracker_track_mc(ora_tracker *t, double cur_time, const uint16_t *lx, const uint16_t *ly,
+                         const double *lt, const uint8_t *lp, size_t nl, const uint16_t *rx,
+                         const uint16_t *ry, const double *rt, const uint8_t *rp, size_t nr,
+                         int pub_this_frame, const ora_motion *mc, ora_tracks *out);
 /* views of internal state, for stage-level parity checks */
 const ora_sae *ora_tracker_sae(const ora_tracker *t, int cam);
 const uint8_t *ora_tracker_time_surface(const ora_tracker *t, int cam);

@@ -62,6 +62,23 @@ class _Tracks(C.Structure):
     ]
 
 
+class _Motion(C.Structure):
+    _fields_ = [("state_v", C.c_double * 3), ("v_pre", C.c_float * 3), ("accel", C.c_float * 3),
+                ("omega", C.c_float * 3), ("t1", C.c_double), ("K", C.c_float * 4)]
+
+
+def make_motion(m: dict) -> "_Motion":
+    """dict(state_v, v_pre, accel, omega, t1, K=(fx, fy, cx, cy)) -> ora_motion."""
+    o = _Motion()
+    for k in ("state_v", "v_pre", "accel", "omega"):
+        for i in range(3):
+            getattr(o, k)[i] = float(m[k][i])
+    o.t1 = float(m["t1"])
+    for i in range(4):
+        o.K[i] = float(m["K"][i])
+    return o
+
+
 class _Sae(C.Structure):
     _fields_ = [("W", C.c_int), ("H", C.c_int), ("sae", C.POINTER(C.c_double) * 2),
                 ("latest", C.POINTER(C.c_double) * 2)]
@@ -123,6 +140,17 @@ def lib():
         L.ora_clahe_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
         L.ora_normalize_minmax_u8.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.ora_equalize_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ora_mat3_exp_f.argtypes = [C.c_void_p, C.c_void_p]
+        L.ora_motion_correct.argtypes = [C.POINTER(_Motion), C.c_int, C.c_int, C.c_double, C.c_double,
+                                         C.c_double, _pi, _pi]
+        L.ora_motion_active.restype = C.c_int
+        L.ora_motion_active.argtypes = [C.POINTER(_Motion)]
+        L.ora_sae_update_mc.argtypes = [C.POINTER(_Sae), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_size_t, C.c_double, C.POINTER(_Motion),
+                                        C.c_double]
+        L.ora_tracker_track_mc.restype = C.c_int
+        L.ora_tracker_track_mc.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 4 + [C.c_size_t] + \
+            [C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.POINTER(_Motion), C.POINTER(_Tracks)]
         L.ora_tracker_create.restype = C.c_void_p
         L.ora_tracker_create.argtypes = [C.POINTER(_Config)]
         L.ora_tracker_destroy.argtypes = [C.c_void_p]
@@ -169,6 +197,13 @@ class Sae:
         x, y, t, p = _ev(x, y, t, p)
         lib().ora_sae_update(self._h, _p(x), _p(y), _p(t), _p(p), len(x), filter_threshold)
 
+    def update_mc(self, x, y, t, p, motion: dict, t0, filter_threshold=0.01):
+        """createSAE_*(..., measurements) for every event (feature_tracker.cpp:628-642)."""
+        x, y, t, p = _ev(x, y, t, p)
+        m = make_motion(motion)
+        lib().ora_sae_update_mc(self._h, _p(x), _p(y), _p(t), _p(p), len(x), filter_threshold,
+                                C.byref(m), float(t0))
+
     def planes(self):
         """(sae[0], sae[1], latest[0], latest[1]) as HxW float64 copies."""
         s = self._h.contents
@@ -205,6 +240,26 @@ class Sae:
                                         min_dist, _p(mask), _p(ts), ts_lk_threshold,
                                         filter_threshold, _p(out), _p(mask_out))
         return out[:k].copy(), mask_out
+
+
+# --------------------------------------------------------------------------- motion compensation
+def mat3_exp_f(A):
+    A = np.ascontiguousarray(A, np.float32).reshape(3, 3)
+    R = np.empty((3, 3), np.float32)
+    lib().ora_mat3_exp_f(_p(A), _p(R))
+    return R
+
+
+def motion_correct(motion: dict, W, H, ex, ey, dt):
+    m = make_motion(motion)
+    ox, oy = C.c_int(), C.c_int()
+    lib().ora_motion_correct(C.byref(m), W, H, float(ex), float(ey), float(dt), C.byref(ox), C.byref(oy))
+    return ox.value, oy.value
+
+
+def motion_active(motion: dict) -> bool:
+    m = make_motion(motion)
+    return bool(lib().ora_motion_active(C.byref(m)))
 
 
 # --------------------------------------------------------------------------- image conditioning
@@ -431,12 +486,13 @@ class OracleTracker:
             lib().ora_tracker_destroy(self._h)
             self._h = None
 
-    def track(self, cur_time, left, right, pub_this_frame=True):
+    def track(self, cur_time, left, right, pub_this_frame=True, motion: dict | None = None):
         lx, ly, lt, lp = _ev(*left)
         rx, ry, rt, rp = _ev(*right)
-        lib().ora_tracker_track(self._h, float(cur_time), _p(lx), _p(ly), _p(lt), _p(lp), len(lx),
-                                _p(rx), _p(ry), _p(rt), _p(rp), len(rx), int(pub_this_frame),
-                                C.byref(self._t))
+        m = make_motion(motion) if motion is not None else None
+        lib().ora_tracker_track_mc(self._h, float(cur_time), _p(lx), _p(ly), _p(lt), _p(lp), len(lx),
+                                   _p(rx), _p(ry), _p(rt), _p(rp), len(rx), int(pub_this_frame),
+                                   C.byref(m) if m is not None else None, C.byref(self._t))
         t = self._t
         nl, nr = t.n_left, t.n_right
         b = self._bufs

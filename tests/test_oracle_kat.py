@@ -129,3 +129,71 @@ def test_oracle_tracker_first_publish_and_ids(ora):
     L, R, tr = s.stereo_window(1)
     o2 = t.track(tr, L, R, False)
     assert (o2["track_cnt"] == 2).all() and set(o2["id"]) <= set(o["id"])
+
+
+# ---- motion-compensated SAE (event_detector.cc:102-147,547-591) ----
+MOTION = dict(state_v=(1.0, 0.5, 0.2), v_pre=(0.9, 0.45, 0.25), accel=(4.0, 3.0, 2.0),
+              omega=(0.5, -0.3, 0.8), t1=0.0333, K=(226.38, 226.15, 173.0, 130.0))
+
+
+def test_matrix_exponential_is_a_rotation(ora):
+    """Matrix3f::exp() of a skew matrix = Rodrigues' rotation, through all three Pade branches
+    (L1 norm < 0.426, < 1.88, beyond with squarings)."""
+    rng = np.random.default_rng(5)
+    for scale in (0.05, 0.3, 1.0, 3.0):
+        for _ in range(20):
+            v = rng.normal(size=3) * scale
+            K = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+            th = np.linalg.norm(v)
+            ref = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+            R = ora.mat3_exp_f(K)
+            assert np.abs(R - ref).max() < 2e-6 * max(1.0, scale)
+            assert abs(np.linalg.det(R.astype(np.float64)) - 1.0) < 1e-5
+
+
+def test_motion_correction_kat(ora):
+    W, H = 346, 260
+    m = dict(MOTION)
+    assert ora.motion_active(m)
+    assert not ora.motion_active(dict(m, accel=(3.0, 3.0, 2.0)))      # |a| = 4.69 <= 5
+    # border pixels (<= 6 from the left/top, > W-6 / H-6) are never moved (ed.cc:552-553)
+    for x, y in ((6, 100), (100, 6), (341, 100), (100, 255)):
+        assert ora.motion_correct(m, W, H, x, y, 0.02) == (x, y)
+    # no rotation, no translation: the warp is K * I * K^-1 in float -- it returns the pixel or,
+    # where the float product lands a hair below the integer, its floor neighbour
+    still = dict(m, omega=(0, 0, 0), state_v=(0, 0, 0), v_pre=(0, 0, 0))
+    for x, y in ((50, 60), (173, 130), (300, 200)):
+        ox, oy = ora.motion_correct(still, W, H, x, y, 0.02)
+        assert x - 1 <= ox <= x and y - 1 <= oy <= y
+    # pure roll about the optical axis by w*dt: pixels rotate about (cx, cy) the other way
+    roll = dict(still, omega=(0, 0, 2.0))
+    ox, oy = ora.motion_correct(roll, W, H, 273, 130, 0.05)   # 100 px right of the centre
+    ang = -2.0 * 0.05
+    assert abs(ox - (173 + 100 * np.cos(ang))) <= 1.5 and abs(oy - (130 + 100 * np.sin(ang))) <= 1.5
+    # a warp that leaves the sensor keeps the raw pixel (ed.cc:574-582)
+    far = dict(still, omega=(0, 40.0, 0))
+    assert ora.motion_correct(far, W, H, 300, 130, 0.03) == (300, 130)
+
+
+def test_sae_update_mc_gates(ora):
+    """The warp applies only when dt_window > 0, (t - t0)/dt_window < 1 and |accel| > 5
+    (feature_tracker.cpp:628, event_detector.cc:125); otherwise it is the plain update."""
+    W, H = 346, 260
+    rng = np.random.default_rng(9)
+    n = 4000
+    x = rng.integers(0, W, n).astype(np.uint16)
+    y = rng.integers(0, H, n).astype(np.uint16)
+    t = np.sort(rng.uniform(0.0, 0.0333, n)) + 1000.0
+    p = rng.integers(0, 2, n).astype(np.uint8)
+    plain = ora.Sae(W, H)
+    plain.update(x, y, t, p)
+    for m in (dict(MOTION, t1=1000.0 + 0.0333, accel=(1.0, 1.0, 1.0)),   # below the threshold
+              dict(MOTION, t1=999.0)):                                   # header stamp before t0
+        s = ora.Sae(W, H)
+        s.update_mc(x, y, t, p, m, t[0])
+        assert all(np.array_equal(a, b) for a, b in zip(s.planes(), plain.planes()))
+    s = ora.Sae(W, H)
+    s.update_mc(x, y, t, p, dict(MOTION, t1=1000.0 + 0.0333), t[0])
+    assert not all(np.array_equal(a, b) for a, b in zip(s.planes(), plain.planes()))
+    # same number of events landed, only somewhere else
+    assert (s.planes()[2] > 0).sum() + (s.planes()[3] > 0).sum() > 0
