@@ -68,6 +68,27 @@ class GpuFeatureTracker {
     unpack();
   }
 
+  // FeatureTracker::trackEvent(double, const EventArray&, const EventArray&,
+  // const Motion_correction_value) (feature_tracker.h:52; call site
+  // stereo_event_tracker_node.cpp:254); the handle must have do_motion_correction = 1
+  template <class EventArrayT>
+  void trackEvent(double _cur_time, const EventArrayT& event_left, const EventArrayT& event_right,
+                  const esvio_motion& measurements) {
+    static_assert(sizeof(event_left.events[0]) == 16, "dvs_msgs::Event must be 16 bytes");
+    esvio_events l{}, r{};
+    l.aos = event_left.events.empty() ? nullptr : &event_left.events[0];
+    l.n = event_left.events.size();
+    r.aos = event_right.events.empty() ? nullptr : &event_right.events[0];
+    r.n = event_right.events.size();
+    const int rc = esvio_fe_track_mc(fe_, _cur_time, &l, &r, PUB_THIS_FRAME ? 1 : 0, &measurements, &out_);
+    if (rc != ESVIO_FE_OK)
+      throw std::runtime_error(std::string("esvio_fe_track_mc: ") + esvio_fe_strerror(rc) + " (" +
+                               esvio_fe_last_error(fe_) + ")");
+    prev_time = cur_time;
+    cur_time = _cur_time;
+    unpack();
+  }
+
   void reset() { esvio_fe_reset(fe_); }
 
   // FeatureTracker::gettimesurface() (feature_tracker.cpp:894-897): CV_8U, row-major W x H
