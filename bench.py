@@ -48,6 +48,16 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_sae_update_ts launch, from the
+    committed `ncu --set full` capture of this workload (profiles/r1_k1_ncu_full.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_k1_ncu_full.json")) as f:
+            return int(json.load(f)[workload]["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -389,12 +399,17 @@ def main_ours(args):
             "gpu_launches": gpu_launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_sae_update_ts", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.workload),
                          "algorithmic_bytes_per_launch": int(alg_bytes),
                          "kernel_ms": k1_ms, "share_of_step": k1_ms / gpu_ms if gpu_ms else None,
                          "peak_source": peak_src,
-                         "note": "state (SAE) is L2-resident; one launch covers both cameras of "
-                                 "one window; LK stages are latency-bound and reported by time"},
+                         "note": "one launch covers both cameras of one window; achieved = "
+                                 "algorithmic bytes (SURVEY.md 8d: 17*W*H per camera + 45 B/event) / "
+                                 "CUDA-event time of the launch inside the pipelined timed region "
+                                 "(other stages share the SMs); the SAE state is L2-resident between "
+                                 "windows, `traffic` is the DRAM traffic of one launch under ncu "
+                                 "(caches flushed); LK stages are latency-bound and reported by time"},
             "stage_ms": stage_ms,
             "tracks_last_window": {"left": int(n_left_last), "right": int(n_right_last)},
         }

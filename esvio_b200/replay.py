@@ -1,0 +1,64 @@
+"""Replay harness: a raw stereo event recording -> fixed-rate windows -> left/right pairing ->
+handle_stereo_event -> feature clouds, all through the GPU tracker.
+
+  python -m esvio_b200.replay [--workload stereo_davis346_1mevs] [--windows 30] [--npz rec.npz]
+
+`--npz` replays a recording with arrays lx, ly, lt, lp, rx, ry, rt, rp (time-ascending,
+seconds); without it the synthetic stream of the named workload is used.  Prints one JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import time
+
+import numpy as np
+
+from . import node, synth
+
+
+def synthetic_recording(name: str, windows: int):
+    w = synth.WORKLOADS[name]
+    s = synth.StereoEventStream(w["width"], w["height"], w["rate"], mono=w["mono"])
+    L = [s.window(k, 0) for k in range(windows)]
+    R = [s.window(k, 1) for k in range(windows)]
+    cat = lambda ws: tuple(np.concatenate([q[i] for q in ws]) for i in range(4))
+    return w, cat(L), cat(R)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="stereo_davis346_1mevs", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--windows", type=int, default=30)
+    ap.add_argument("--npz", default=None)
+    ap.add_argument("--frequency", type=float, default=30.0, help="re-windowing rate (EventMessageEditor: 30)")
+    args = ap.parse_args()
+    from . import frontend  # needs libesvio_fe.so and a B200: there is no CPU path
+
+    w, left, right = synthetic_recording(args.workload, args.windows)
+    if args.npz:
+        z = np.load(args.npz)
+        left = tuple(z[k] for k in ("lx", "ly", "lt", "lp"))
+        right = tuple(z[k] for k in ("rx", "ry", "rt", "rp"))
+    cfg = synth.default_config(w["width"], w["height"], max_cnt=w["max_cnt"], min_dist=w["min_dist"],
+                               use_ransac=1)
+    cfg["max_events_per_window"] = max(1 << 16, int(2.5 * w["rate"] / args.frequency))
+    ft = frontend.FeatureTracker(cfg)
+    nd = node.StereoEventNode(ft, w["freq"])
+    t0 = time.perf_counter()
+    lm, rm = node.window_stream(left, args.frequency), node.window_stream(right, args.frequency)
+    t1 = time.perf_counter()
+    clouds, dropped = node.replay(nd, lm, rm)
+    t2 = time.perf_counter()
+    n_ev = sum(len(m) for m in lm) + sum(len(m) for m in rm)
+    print(json.dumps({
+        "workload": args.workload, "messages": [len(lm), len(rm)], "events": n_ev,
+        "windows_tracked": nd.windows_tracked, "clouds_published": len(clouds),
+        "rows_last_cloud": int(len(clouds[-1].rows)) if clouds else 0, "queue_overwrites": dropped,
+        "restarts": nd.restarts, "windowing_s": t1 - t0, "tracking_s": t2 - t1,
+        "mevents_per_s_sync_call": n_ev / max(t2 - t1, 1e-9) / 1e6}))
+    ft.fe.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -511,3 +511,46 @@ def test_track_mc_matches_oracle(fe_mod, ora):
     with pytest.raises(fe_mod.FrontEndError):
         fe2.track(t_ref, L, R, True, motion=dict(MOTION, t1=t_ref))
     fe2.close()
+
+
+# ---- replay harness: raw streams -> windows -> pairing -> handle_stereo_event (8f rank 1) ----
+class _OracleFeatureTracker:
+    """The oracle behind the reference's member names, so the same node code can drive it."""
+
+    def __init__(self, ora, cfg):
+        self.t = ora.OracleTracker(cfg, use_cv2=False)
+        self.PUB_THIS_FRAME = True
+
+    def trackEvent(self, cur_time, left, right, measurements=None):
+        r = self.t.track(cur_time, left, right, self.PUB_THIS_FRAME, motion=measurements)
+        self.ids, self.track_cnt = r["id"], r["track_cnt"]
+        self.cur_pts = np.stack([r["u"], r["v"]], 1)
+        self.cur_un_pts = np.stack([r["un_x"], r["un_y"]], 1)
+        self.pts_velocity = np.stack([r["vx"], r["vy"]], 1)
+        self.ids_right = r["id_right"]
+        self.cur_right_pts = np.stack([r["ru"], r["rv"]], 1)
+        self.cur_un_right_pts = np.stack([r["run_x"], r["run_y"]], 1)
+        self.right_pts_velocity = np.stack([r["rvx"], r["rvy"]], 1)
+
+
+def test_replay_through_node_matches_oracle(fe_mod, ora):
+    from esvio_b200 import node, replay
+    w, left, right = replay.synthetic_recording("stereo_davis346_1mevs", 8)
+    cfg = synth.default_config(346, 260, use_ransac=1, max_events_per_window=1 << 17)
+    lm, rm = node.window_stream(left, 30.0), node.window_stream(right, 30.0)
+    assert len(lm) == 7 and len(rm) == 7       # the open last window is never written
+    ft = fe_mod.FeatureTracker(cfg)
+    gn = node.StereoEventNode(ft, 15)
+    on = node.StereoEventNode(_OracleFeatureTracker(ora, cfg), 15)
+    gc, gd = node.replay(gn, lm, rm)
+    oc, od = node.replay(on, lm, rm)
+    assert gd == od == 0 and gn.windows_tracked == on.windows_tracked == 6
+    assert len(gc) == len(oc) >= 2
+    for a, b in zip(gc[:2], oc[:2]):           # lock-step while no LK rounding flip has occurred
+        assert a.stamp == b.stamp and a.rows.shape == b.rows.shape
+        assert np.array_equal(a.rows[:, 3], b.rows[:, 3])                      # id*2+cam
+        assert np.abs(a.rows[:, 4:6] - b.rows[:, 4:6]).max() <= 0.05           # u, v
+        assert np.abs(a.rows[:, 0:2] - b.rows[:, 0:2]).max() <= 1e-3           # un_x, un_y
+        fid, cam = node.decode_feature_cloud(a.rows)
+        assert set(fid[cam == 1]) <= set(fid[cam == 0])
+    ft.fe.close()
