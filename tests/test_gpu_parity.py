@@ -554,3 +554,21 @@ def test_replay_through_node_matches_oracle(fe_mod, ora):
         fid, cam = node.decode_feature_cloud(a.rows)
         assert set(fid[cam == 1]) <= set(fid[cam == 0])
     ft.fe.close()
+
+
+def test_ignore_polarity_time_surface(fe_mod, ora):
+    """para_ignore_polarity = 1 (event_detector.cc:246-259): the surface is 255 * exp(..),
+    unsigned, an untouched pixel is 0."""
+    W, H = 346, 260
+    fe, cfg = _mk(fe_mod, W, H, ignore_polarity=1)
+    s = synth.StereoEventStream(W, H, 1.0e6)
+    sae = [ora.Sae(W, H), ora.Sae(W, H)]
+    for k in range(2):
+        L, R, t_ref = s.stereo_window(k)
+        fe.stage_update(t_ref, L, R)
+        for cam, ev in enumerate((L, R)):
+            sae[cam].update(*ev)
+            ref = sae[cam].time_surface(t_ref, ignore_polarity=1)
+            _assert_ts_equal(fe.time_surface(cam), ref)
+            assert ref.min() == 0 and ref.max() >= 250
+    fe.close()
