@@ -30,6 +30,7 @@ constexpr int kMaxLevels = 4;                 // maxLevel = 3 (feature_tracker.c
 constexpr int kWin = 21;                      // cv::Size(21, 21)
 constexpr int kHalfWin = 10;
 constexpr int kMaxCnt = 1024;                 // hard cap on MAX_CNT
+constexpr int kMaxCams = 16;                  // cameras per launch: 8 stereo streams of one group
 constexpr int kSlots = 3;                     // windows in flight (event / temporal / stereo stage)
 constexpr int kResultHdr = 32;                // int32 words in front of the result arrays
 constexpr int kResultArrays = 15;
@@ -180,16 +181,28 @@ struct BinLayout {
   int max_chunks;                       // chunk capacity of `counts`
 };
 
+// Every event-stage kernel covers `n_cams` cameras per launch (blockIdx.y / .z = camera): the
+// two cameras of one stereo stream, or the 2S cameras of a group of S streams.
 struct EventStageBuffers {
-  uint32_t* counts;     // [2][max_chunks][n_bins+1]
-  uint32_t* bin_total;  // [2][n_bins+1]
-  uint32_t* bin_start;  // [2][n_bins+2]
-  unsigned int* done_ctr;  // [2] CTAs of k_bin_scan that finished (self-resetting)
-  double* bt[2];        // binned event times
-  uint16_t* bk[2];      // binned keys: local pixel (8 bits) | polarity << 8
+  int n_cams;
+  uint32_t* counts;     // [n_cams][max_chunks][n_bins+1]
+  uint32_t* bin_total;  // [n_cams][n_bins+1]
+  uint32_t* bin_start;  // [n_cams][n_bins+2]
+  unsigned int* done_ctr;  // [n_cams] CTAs of k_bin_scan that finished (self-resetting)
+  double* bt[kMaxCams];    // binned event times
+  uint16_t* bk[kMaxCams];  // binned keys: local pixel (8 bits) | polarity << 8
 };
 
-void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents ev[2],
+// by-value kernel parameter (__grid_constant__: indexed by camera without a local copy)
+struct CamBatch {
+  int n_cams;
+  int n_chunks[kMaxCams];
+  DevEvents ev[kMaxCams];
+  double* bt[kMaxCams];
+  uint16_t* bk[kMaxCams];
+};
+
+void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents* ev,
                        cudaStream_t s, int64_t* launches);
 
 // Motion_correction_value (feature_tracker.h:35) as the SAE update reads it
@@ -208,13 +221,14 @@ void launch_warp_points(const McParams& P, const float* xy_dt, int n, int* out_x
                         int64_t* launches);
 
 struct SaeTsParams {
-  int W, H, tiles_x, n_tiles;
-  double t_ref, decay_sec, inv_decay, filter_threshold;  // inv_decay = RN(1 / decay_sec)
+  int W, H, tiles_x, n_tiles, n_cams;
+  double decay_sec, inv_decay, filter_threshold;  // inv_decay = RN(1 / decay_sec)
   int ignore_polarity;
-  const uint32_t* bin_start;  // [2][kFine*n_tiles+2]
-  const double* bt[2];
-  const uint16_t* bk[2];
-  uint8_t* ts[2];  // level-0 images
+  const uint32_t* bin_start;  // [n_cams][kFine*n_tiles+2]
+  double t_ref[kMaxCams];     // per camera (the two cameras of a stream share theirs)
+  const double* bt[kMaxCams];
+  const uint16_t* bk[kMaxCams];
+  uint8_t* ts[kMaxCams];      // level-0 images
   int ts_pitch;
 };
 void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
@@ -232,7 +246,7 @@ struct CornerParams {
 void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* flags,
                          cudaStream_t s, int64_t* launches);
 
-void launch_pyramids(const PyrDesc& pd, uint8_t* const pyr[2], int n_img, cudaStream_t s,
+void launch_pyramids(const PyrDesc& pd, uint8_t* const* pyr, int n_img, cudaStream_t s,
                      int64_t* launches);
 
 // optional conditioning of the time surface (imgops.cu)

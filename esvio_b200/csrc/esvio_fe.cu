@@ -71,6 +71,7 @@ struct esvio_fe {
   int q_head, q_count;  // in-flight windows (results land in h_result[(q_head + k) % kSlots])
   cudaEvent_t q_done[kSlots];
   int profiling;
+  struct esvio_fe_group* group;  // non-null: the event stage is run by the group, batched
   // one set per in-flight slot; [NUM_STAGES+1] = temporal stage start, [+2] = stereo stage start
   cudaEvent_t pev[kSlots][ESVIO_FE_NUM_STAGES + 3];
   int pev_slot;
@@ -157,13 +158,13 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_state_map(esvio_fe* fe, double2* base, CUtensorMap* map) {
+static int make_state_map(esvio_fe* fe, double2* base, CUtensorMap* map, int n_cams = 2) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
   if (!fn || q != cudaDriverEntryPointSuccess)
     return fail(fe, ESVIO_FE_ECUDA, "cuTensorMapEncodeTiled unavailable", cudaSuccess);
-  const cuuint64_t dims[3] = {(cuuint64_t)fe->W * 2, (cuuint64_t)fe->H, 2};
+  const cuuint64_t dims[3] = {(cuuint64_t)fe->W * 2, (cuuint64_t)fe->H, (cuuint64_t)n_cams};
   const cuuint64_t strides[2] = {(cuuint64_t)fe->W * 16, (cuuint64_t)fe->W * fe->H * 16};
   const cuuint32_t box[3] = {2 * kTileW, kTileH, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
@@ -297,6 +298,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   CUC(cudaStreamCreateWithFlags(&fe->stream_e, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&fe->stream_t1, cudaStreamNonBlocking));
 
+  fe->esb.n_cams = 2;
   BinLayout& L = fe->bl;
   L.W = fe->W;
   L.H = fe->H;
@@ -457,7 +459,8 @@ FE_API int esvio_fe_reset(esvio_fe* fe) {
 // ---------------------------------------------------------------------------------------
 // event staging
 // ---------------------------------------------------------------------------------------
-static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, DevEvents* d) {
+static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, DevEvents* d,
+                        cudaStream_t se = nullptr) {
   memset(d, 0, sizeof(*d));
   if (!e || e->n == 0) return ESVIO_FE_OK;
   if (e->n > (size_t)fe->cap) return fail(fe, ESVIO_FE_ECAPACITY, "events > max_events_per_window", cudaSuccess);
@@ -470,7 +473,7 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
     return ESVIO_FE_OK;
   }
   uint8_t* raw = fe->raw[slot][cam];
-  cudaStream_t se = fe->stream_e;
+  if (!se) se = fe->stream_e;
   const size_t n = e->n, cap = (size_t)fe->cap;
   if (e->aos) {
     CU(cudaMemcpyAsync(raw, e->aos, n * 16, cudaMemcpyHostToDevice, se));
@@ -537,7 +540,11 @@ static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev_in[2],
   sp.H = fe->H;
   sp.tiles_x = fe->bl.tiles_x;
   sp.n_tiles = fe->bl.n_tiles;
-  sp.t_ref = t_ref;
+  sp.n_cams = 2;
+  for (int c = 0; c < kMaxCams; ++c) {
+    sp.t_ref[c] = t_ref;
+    sp.bt[c] = nullptr, sp.bk[c] = nullptr, sp.ts[c] = nullptr;
+  }
   sp.decay_sec = fe->cfg.decay_ms / 1000.0;
   sp.inv_decay = 1.0 / sp.decay_sec;
   sp.filter_threshold = fe->cfg.feature_filter_threshold;
@@ -594,37 +601,30 @@ FE_API int esvio_fe_track_submit(esvio_fe* fe, double cur_time, const esvio_even
   return esvio_fe_track_submit_mc(fe, cur_time, left, right, pub_this_frame, nullptr);
 }
 
-FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_events* left,
-                                    const esvio_events* right, int32_t pub_this_frame,
-                                    const esvio_motion* mc) {
-  if (!fe) return ESVIO_FE_EINVAL;
-  if (mc && !fe->cfg.do_motion_correction)
-    return fail(fe, ESVIO_FE_ESTATE, "motion compensation needs config.do_motion_correction", cudaSuccess);
+// Which buffers a new window uses: its in-flight slot and the rotating pyramid images.
+struct WindowPlan {
+  int slot, cur, prev, rcur;
+};
+
+static int plan_window(esvio_fe* fe, WindowPlan* w) {
   if (fe->q_count >= kSlots)
     return fail(fe, ESVIO_FE_ESTATE, "three windows already in flight", cudaSuccess);
-  CU(cudaSetDevice(fe->dev));
+  w->slot = (fe->q_head + fe->q_count) % kSlots;
+  w->cur = fe->windows == 0 ? 0 : (fe->cur_left + 1) % 3;
+  w->prev = fe->windows == 0 ? 0 : fe->cur_left;  // first window: prev_img = cur_img
+  w->rcur = fe->windows == 0 ? 3 : 3 + (fe->cur_right - 3 + 1) % 3;
+  return ESVIO_FE_OK;
+}
+
+// Everything of a window behind the SAE / time surface / pyramids: corner flags (still on the
+// event-stage stream), then the temporal and the stereo stage on their own streams.
+static int submit_tracking(esvio_fe* fe, const WindowPlan& w, const DevEvents& ev_left,
+                           double cur_time, int32_t pub_this_frame) {
   cudaStream_t se = fe->stream_e, s1 = fe->stream_t1, s2 = fe->stream;
-  const int slot = (fe->q_head + fe->q_count) % kSlots;
-  fe->pev_slot = slot;
-  // A window passes through three stages, each on its own stream, so that up to three
-  // consecutive windows overlap:  event stage (k+2) | temporal stage (k+1) | stereo stage (k).
-  // Everything a later stage reads from an earlier one is either per-slot (raw events, flags,
-  // snapshot, result) or rotates over three buffers (pyramids), and a slot is only reused
-  // after esvio_fe_track_wait returned its window.
-  // ---------------- event stage
-  prof_mark(fe, 0);
-  DevEvents ev[2];
-  int rc;
-  if ((rc = stage_events(fe, slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
-  if ((rc = stage_events(fe, slot, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
-  prof_mark(fe, 1);
-  const int cur = fe->windows == 0 ? 0 : (fe->cur_left + 1) % 3;
-  const int prev = fe->windows == 0 ? 0 : fe->cur_left;  // first window: prev_img = cur_img
-  const int rcur = fe->windows == 0 ? 3 : 3 + (fe->cur_right - 3 + 1) % 3;
-  if ((rc = run_event_stage(fe, cur_time, ev, cur, rcur, mc)) != ESVIO_FE_OK) return rc;
+  const int slot = w.slot, cur = w.cur, prev = w.prev, rcur = w.rcur;
   prof_mark(fe, 4);
   if (pub_this_frame)
-    launch_corner_flags(corner_params(fe, cur, 1), ev[0], fe->flags[slot], se, &fe->launches);
+    launch_corner_flags(corner_params(fe, cur, 1), ev_left, fe->flags[slot], se, &fe->launches);
   prof_mark(fe, 5);
   CU(cudaEventRecord(fe->e_done[slot], se));
 
@@ -639,7 +639,7 @@ FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_e
   prof_mark(fe, 6);
   if (pub_this_frame) {
     if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s1, &fe->launches);
-    launch_select(fe->tp, B, ev[0], fe->flags[slot], s1, &fe->launches);
+    launch_select(fe->tp, B, ev_left, fe->flags[slot], s1, &fe->launches);
   }
   launch_snapshot(fe->tp, B, slot, s1, &fe->launches);
   prof_mark(fe, 7);
@@ -663,7 +663,34 @@ FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_e
   fe->cur_right = rcur;
   fe->windows++;
   fe->prev_time = cur_time;
-  fe->pev_valid[slot] = fe->profiling;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_events* left,
+                                    const esvio_events* right, int32_t pub_this_frame,
+                                    const esvio_motion* mc) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  if (fe->group) return fail(fe, ESVIO_FE_ESTATE, "handle belongs to a group: use esvio_fe_group_track_submit", cudaSuccess);
+  if (mc && !fe->cfg.do_motion_correction)
+    return fail(fe, ESVIO_FE_ESTATE, "motion compensation needs config.do_motion_correction", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  WindowPlan w;
+  int rc;
+  if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
+  fe->pev_slot = w.slot;
+  // A window passes through three stages, each on its own stream, so that up to three
+  // consecutive windows overlap:  event stage (k+2) | temporal stage (k+1) | stereo stage (k).
+  // Everything a later stage reads from an earlier one is either per-slot (raw events, flags,
+  // snapshot, result) or rotates over three buffers (pyramids), and a slot is only reused
+  // after esvio_fe_track_wait returned its window.
+  prof_mark(fe, 0);
+  DevEvents ev[2];
+  if ((rc = stage_events(fe, w.slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
+  if ((rc = stage_events(fe, w.slot, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
+  prof_mark(fe, 1);
+  if ((rc = run_event_stage(fe, cur_time, ev, w.cur, w.rcur, mc)) != ESVIO_FE_OK) return rc;
+  if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame)) != ESVIO_FE_OK) return rc;
+  fe->pev_valid[w.slot] = fe->profiling;
   return ESVIO_FE_OK;
 }
 

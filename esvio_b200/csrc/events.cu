@@ -275,10 +275,10 @@ __device__ __forceinline__ int bin_of(const BinLayout& L, int x, int y) {
 
 // counts[cam][chunk][bin]: per-chunk histogram, written coalesced
 __global__ void __launch_bounds__(kChunkThreads)
-k_bin_hist(BinLayout L, DevEvents ev0, DevEvents ev1, uint32_t* __restrict__ counts) {
+k_bin_hist(BinLayout L, const __grid_constant__ CamBatch B, uint32_t* __restrict__ counts) {
   extern __shared__ uint32_t s_hist[];
   const int cam = blockIdx.y;
-  const DevEvents& ev = cam ? ev1 : ev0;
+  const DevEvents& ev = B.ev[cam];
   const int chunk = blockIdx.x;
   const int nb = L.n_bins + 1;
   if ((long long)chunk * kChunk >= ev.n) return;
@@ -315,7 +315,7 @@ k_bin_hist(BinLayout L, DevEvents ev0, DevEvents ev1, uint32_t* __restrict__ cou
 constexpr int kScanPhases = 16;
 
 __global__ void __launch_bounds__(32 * kScanPhases)
-k_bin_scan(BinLayout L, int n_chunks0, int n_chunks1, uint32_t* __restrict__ counts,
+k_bin_scan(BinLayout L, const __grid_constant__ CamBatch B, uint32_t* __restrict__ counts,
            uint32_t* __restrict__ bin_total, uint32_t* __restrict__ bin_start,
            unsigned int* __restrict__ done_ctr) {
   __shared__ uint32_t s_part[kScanPhases][33];
@@ -326,7 +326,7 @@ k_bin_scan(BinLayout L, int n_chunks0, int n_chunks1, uint32_t* __restrict__ cou
   const int nb = L.n_bins + 1;
   const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
   const int bin = blockIdx.x * 32 + lane;
-  const int n_chunks = cam ? n_chunks1 : n_chunks0;
+  const int n_chunks = B.n_chunks[cam];
   const int per = (n_chunks + kScanPhases - 1) / kScanPhases;
   const int c_lo = min(ph * per, n_chunks), c_hi = min(c_lo + per, n_chunks);
   uint32_t* col = counts + (size_t)cam * L.max_chunks * nb + bin;
@@ -402,16 +402,15 @@ k_bin_scan(BinLayout L, int n_chunks0, int n_chunks1, uint32_t* __restrict__ cou
 }
 
 __global__ void __launch_bounds__(kChunkThreads)
-k_bin_scatter(BinLayout L, DevEvents ev0, DevEvents ev1, const uint32_t* __restrict__ counts,
-              const uint32_t* __restrict__ bin_start, double* __restrict__ bt0,
-              uint16_t* __restrict__ bk0, double* __restrict__ bt1, uint16_t* __restrict__ bk1) {
+k_bin_scatter(BinLayout L, const __grid_constant__ CamBatch B,
+              const uint32_t* __restrict__ counts, const uint32_t* __restrict__ bin_start) {
   // s_base[nb]: position of this chunk's first event of each bin; s_wc[8 warps][nb]: events of
   // the bin in each warp's 256-event slice, then the slice's offset inside the chunk
   extern __shared__ uint32_t s_dyn[];
   const int cam = blockIdx.y;
-  const DevEvents& ev = cam ? ev1 : ev0;
-  double* __restrict__ bt = cam ? bt1 : bt0;
-  uint16_t* __restrict__ bk = cam ? bk1 : bk0;
+  const DevEvents& ev = B.ev[cam];
+  double* __restrict__ bt = B.bt[cam];
+  uint16_t* __restrict__ bk = B.bk[cam];
   const int chunk = blockIdx.x;
   const int nb = L.n_bins + 1;
   if ((long long)chunk * kChunk >= ev.n) return;
@@ -498,22 +497,30 @@ int bin_configure(int n_bins) {
                               (int)bytes) == cudaSuccess ? 0 : -1;
 }
 
-void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents ev[2],
+void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents* ev,
                        cudaStream_t s, int64_t* launches) {
   const int nb = L.n_bins + 1;
-  const int c0 = (ev[0].n + kChunk - 1) / kChunk, c1 = (ev[1].n + kChunk - 1) / kChunk;
-  const int nc = c0 > c1 ? c0 : c1;
+  CamBatch cb;
+  cb.n_cams = B.n_cams;
+  int nc = 0;
+  for (int c = 0; c < kMaxCams; ++c) {
+    const bool on = c < B.n_cams;
+    cb.ev[c] = on ? ev[c] : DevEvents{};
+    cb.bt[c] = on ? B.bt[c] : nullptr;
+    cb.bk[c] = on ? B.bk[c] : nullptr;
+    cb.n_chunks[c] = on ? (ev[c].n + kChunk - 1) / kChunk : 0;
+    if (cb.n_chunks[c] > nc) nc = cb.n_chunks[c];
+  }
   if (nc > 0) {
-    k_bin_hist<<<dim3(nc, 2), kChunkThreads, nb * sizeof(uint32_t), s>>>(L, ev[0], ev[1],
-                                                                          B.counts);
+    k_bin_hist<<<dim3(nc, B.n_cams), kChunkThreads, nb * sizeof(uint32_t), s>>>(L, cb, B.counts);
     ++*launches;
   }
-  k_bin_scan<<<dim3((nb + 31) / 32, 2), 32 * kScanPhases, 0, s>>>(L, c0, c1, B.counts, B.bin_total,
-                                                                 B.bin_start, B.done_ctr);
+  k_bin_scan<<<dim3((nb + 31) / 32, B.n_cams), 32 * kScanPhases, 0, s>>>(L, cb, B.counts, B.bin_total,
+                                                                        B.bin_start, B.done_ctr);
   ++*launches;
   if (nc > 0) {
-    k_bin_scatter<<<dim3(nc, 2), kChunkThreads, scatter_smem_bytes(L.n_bins), s>>>(
-        L, ev[0], ev[1], B.counts, B.bin_start, B.bt[0], B.bk[0], B.bt[1], B.bk[1]);
+    k_bin_scatter<<<dim3(nc, B.n_cams), kChunkThreads, scatter_smem_bytes(L.n_bins), s>>>(
+        L, cb, B.counts, B.bin_start);
     ++*launches;
   }
 }
@@ -576,7 +583,7 @@ __device__ __forceinline__ double exp_small(double a, const double* __restrict__
 
 // SAEtoTimeSurface_* for four adjacent pixels (event_detector.cc:230-267)
 __device__ __forceinline__ uchar4 ts_pixel4(const double2* __restrict__ px, const SaeTsParams& P,
-                                            const double* __restrict__ tab) {
+                                            const double t_ref, const double* __restrict__ tab) {
   double a[4];
   bool pos[4], hit[4], fresh[4];
   bool any_fresh = false;
@@ -587,7 +594,7 @@ __device__ __forceinline__ uchar4 ts_pixel4(const double2* __restrict__ px, cons
     const double stamp = pos[i] ? v.y : v.x;
     hit[i] = stamp > 0.0;
     // -dt / decay_sec, correctly rounded (Markstein: q + (n - q*d) * RN(1/d) with FMAs)
-    const double n = -(P.t_ref - stamp);
+    const double n = -(t_ref - stamp);
     const double q = n * P.inv_decay;
     a[i] = fma(fma(-q, P.decay_sec, n), P.inv_decay, q);
     // exp(a) < 1/1024 below -7: 255*e rounds to 0 and 127.5 +- 127.5*e to 128 / 127 whatever
@@ -615,7 +622,7 @@ __device__ __forceinline__ uchar4 ts_pixel4(const double2* __restrict__ px, cons
 // DBG: perf-experiment switches (0 in the product): 1 skip events, 2 skip TS, 4 skip store
 template <int DBG>
 __global__ void __launch_bounds__(kSaeThreads)
-k_sae_update_ts(const __grid_constant__ SaeMaps maps, SaeTsParams P) {
+k_sae_update_ts(const __grid_constant__ SaeMaps maps, const __grid_constant__ SaeTsParams P) {
   __shared__ __align__(128) double2 s_sae[kTilePx];
   __shared__ __align__(128) double2 s_lat[kTilePx];
   __shared__ __align__(8) uint64_t s_bar;
@@ -638,8 +645,8 @@ k_sae_update_ts(const __grid_constant__ SaeMaps maps, SaeTsParams P) {
     if (dirty) tma_load_3d(s_lat, &maps.lat, &s_bar, 2 * x0, y0, cam);
   }
   // the first events of the run travel while the tile loads
-  const double* __restrict__ bt = cam ? P.bt[1] : P.bt[0];
-  const uint16_t* __restrict__ bk = cam ? P.bk[1] : P.bk[0];
+  const double* __restrict__ bt = P.bt[cam];
+  const uint16_t* __restrict__ bk = P.bk[cam];
   double t_nx[kSaeAhead];
   uint32_t k_nx[kSaeAhead];
 #pragma unroll
@@ -707,8 +714,8 @@ k_sae_update_ts(const __grid_constant__ SaeMaps maps, SaeTsParams P) {
     const int r = threadIdx.x >> 3, c = (threadIdx.x & 7) * 4;
     const int y = y0 + r;
     if (y < P.H && !(DBG & 2))
-      *reinterpret_cast<uchar4*>((cam ? P.ts[1] : P.ts[0]) + (size_t)y * P.ts_pitch + x0 + c) =
-          ts_pixel4(&s_sae[r * kTileW + c], P, s_exp2);
+      *reinterpret_cast<uchar4*>(P.ts[cam] + (size_t)y * P.ts_pitch + x0 + c) =
+          ts_pixel4(&s_sae[r * kTileW + c], P, P.t_ref[cam], s_exp2);
   }
 
   if (dirty && !(DBG & 4)) {
@@ -729,7 +736,7 @@ void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
   maps.sae = map_sae;
   maps.lat = map_lat;
   static const int dbg = getenv("ESVIO_K1_DBG") ? atoi(getenv("ESVIO_K1_DBG")) : 0;
-  const dim3 grid(P.tiles_x, P.n_tiles / P.tiles_x, 2);
+  const dim3 grid(P.tiles_x, P.n_tiles / P.tiles_x, P.n_cams);
   switch (dbg) {
     case 1: k_sae_update_ts<1><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
     case 2: k_sae_update_ts<2><<<grid, kSaeThreads, 0, s>>>(maps, P); break;

@@ -60,15 +60,19 @@ __device__ __forceinline__ void pyr_stage(const uint8_t* __restrict__ s_src, int
   __syncthreads();
 }
 
+struct PyrImages {
+  uint8_t* img[kMaxCams];
+};
+
 __global__ void __launch_bounds__(kPyrThreads)
-k_pyr_build(PyrDesc pd, uint8_t* __restrict__ img0, uint8_t* __restrict__ img1) {
+k_pyr_build(PyrDesc pd, const __grid_constant__ PyrImages imgs) {
   constexpr int SP0 = kPyrN0 + 3, SP1 = kPyrN1 + 3, SP2 = kPyrN2 + 1;
   __shared__ uint8_t s0[kPyrN0 * SP0];
   __shared__ uint8_t s1[kPyrN1 * SP1];
   __shared__ uint8_t s2[kPyrN2 * SP2];
   __shared__ uint8_t s3[kPyrT3 * kPyrT3];
   __shared__ uint16_t s_row[kPyrN0 * kPyrN1];
-  uint8_t* __restrict__ img = blockIdx.z ? img1 : img0;
+  uint8_t* __restrict__ img = imgs.img[blockIdx.z];
   const int o3x = blockIdx.x * kPyrT3, o3y = blockIdx.y * kPyrT3;
   const int p2x = 2 * o3x - 2, p2y = 2 * o3y - 2;
   const int p1x = 2 * p2x - 2, p1y = 2 * p2y - 2;
@@ -93,12 +97,14 @@ k_pyr_build(PyrDesc pd, uint8_t* __restrict__ img0, uint8_t* __restrict__ img1) 
                               pd.w[3], pd.h[3], img + pd.off[3], pd.pitch[3], o3x, o3y, kPyrT3);
 }
 
-void launch_pyramids(const PyrDesc& pd, uint8_t* const pyr[2], int n_img, cudaStream_t s,
+void launch_pyramids(const PyrDesc& pd, uint8_t* const* pyr, int n_img, cudaStream_t s,
                      int64_t* launches) {
-  if (pd.levels < 2) return;
+  if (pd.levels < 2 || n_img < 1 || n_img > kMaxCams) return;
+  PyrImages imgs;
+  for (int i = 0; i < kMaxCams; ++i) imgs.img[i] = i < n_img ? pyr[i] : nullptr;
   const dim3 grid((pd.w[1] + 4 * kPyrT3 - 1) / (4 * kPyrT3), (pd.h[1] + 4 * kPyrT3 - 1) / (4 * kPyrT3),
                   n_img);
-  k_pyr_build<<<grid, kPyrThreads, 0, s>>>(pd, pyr[0], pyr[n_img > 1 ? 1 : 0]);
+  k_pyr_build<<<grid, kPyrThreads, 0, s>>>(pd, imgs);
   ++*launches;
 }
 
