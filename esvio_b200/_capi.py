@@ -91,6 +91,16 @@ SYMBOLS = {
                                     C.POINTER(Motion), C.POINTER(Tracks)]),
     "esvio_fe_track_submit_mc": (C.c_int, [_H, C.c_double, C.POINTER(Events), C.POINTER(Events),
                                            C.c_int32, C.POINTER(Motion)]),
+    "esvio_fe_group_create": (C.c_int, [C.POINTER(Config), C.c_int32, C.POINTER(_H)]),
+    "esvio_fe_group_destroy": (None, [_H]),
+    "esvio_fe_group_member": (_H, [_H, C.c_int32]),
+    "esvio_fe_group_track": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(Events), C.POINTER(Events),
+                                       C.POINTER(C.c_int32), C.POINTER(Tracks)]),
+    "esvio_fe_group_track_submit": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(Events),
+                                              C.POINTER(Events), C.POINTER(C.c_int32)]),
+    "esvio_fe_group_track_wait": (C.c_int, [_H, C.POINTER(Tracks)]),
+    "esvio_fe_group_kernel_launches": (C.c_int, [_H, C.POINTER(C.c_int64)]),
+    "esvio_fe_group_sae_ts_ms": (C.c_int, [_H, _pf]),
     "esvio_fe_time_surface": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_size_t]),
     "esvio_fe_host_alloc": (C.c_void_p, [C.c_size_t]),
     "esvio_fe_host_free": (None, [C.c_void_p]),

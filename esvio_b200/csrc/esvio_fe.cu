@@ -440,7 +440,10 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   return ESVIO_FE_OK;
 }
 
-FE_API void esvio_fe_destroy(esvio_fe* fe) { free_all(fe); }
+FE_API void esvio_fe_destroy(esvio_fe* fe) {
+  if (fe && fe->group) return;  // owned by its group: esvio_fe_group_destroy
+  free_all(fe);
+}
 
 static int sync_all(esvio_fe* fe) {
   CU(cudaStreamSynchronize(fe->stream_e));
@@ -688,6 +691,8 @@ FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_e
   if ((rc = stage_events(fe, w.slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
   if ((rc = stage_events(fe, w.slot, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
   prof_mark(fe, 1);
+  // pyr[w.cur] was the PREVIOUS image of window k-2, whose temporal LK may still be reading it
+  if (fe->windows >= 2) CU(cudaStreamWaitEvent(fe->stream_e, fe->t1_done[(w.slot + 1) % kSlots], 0));
   if ((rc = run_event_stage(fe, cur_time, ev, w.cur, w.rcur, mc)) != ESVIO_FE_OK) return rc;
   if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame)) != ESVIO_FE_OK) return rc;
   fe->pev_valid[w.slot] = fe->profiling;
@@ -760,6 +765,233 @@ FE_API int esvio_fe_time_surface(esvio_fe* fe, int32_t cam, uint8_t* dst, size_t
   CU(cudaMemcpy2DAsync(dst, stride, src, fe->pd.pitch[0], fe->W, fe->H, cudaMemcpyDeviceToHost,
                        fe->stream));
   CU(cudaStreamSynchronize(fe->stream));
+  return ESVIO_FE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// groups: S independent stereo streams whose event stage runs as ONE batched launch sequence
+// ---------------------------------------------------------------------------------------
+// SURVEY.md 8e "independent streams" on one GPU (BASELINE configs[4]: 4 stereo pairs): binning,
+// SAE update + time surface and the pyramids of all 2S cameras share their launches (one
+// k_sae_update_ts per window for the whole group), the per-stream tracking stages then run
+// concurrently on the members' own streams.  Results are identical to S separate handles.
+struct esvio_fe_group {
+  int S, dev;
+  esvio_fe* m[kMaxCams / 2];
+  double2 *sae, *lat;                                 // [2S][H][W]
+  double2 *own_sae[kMaxCams / 2], *own_lat[kMaxCams / 2];  // the members' own planes (unused)
+  CUtensorMap map_sae, map_lat;
+  EventStageBuffers esb;
+  BinLayout bl;
+  cudaStream_t stream_e;
+  cudaEvent_t g_done[kSlots];
+  cudaEvent_t k1_beg[kSlots], k1_end[kSlots];
+  int k1_slot_valid[kSlots];
+  float k1_ms;
+  int k1_ms_valid;
+  int64_t launches;
+};
+
+FE_API void esvio_fe_group_destroy(esvio_fe_group* g) {
+  if (!g) return;
+  cudaSetDevice(g->dev);
+  if (g->stream_e) cudaStreamSynchronize(g->stream_e);
+  for (int i = 0; i < g->S; ++i)
+    if (g->m[i]) {
+      sync_all(g->m[i]);
+      g->m[i]->sae = g->own_sae[i];
+      g->m[i]->lat = g->own_lat[i];
+      g->m[i]->group = nullptr;
+      free_all(g->m[i]);
+    }
+  cudaFree(g->sae);
+  cudaFree(g->lat);
+  for (int c = 0; c < kMaxCams; ++c) {
+    cudaFree(g->esb.bt[c]);
+    cudaFree(g->esb.bk[c]);
+  }
+  cudaFree(g->esb.counts);
+  cudaFree(g->esb.bin_total);
+  cudaFree(g->esb.bin_start);
+  cudaFree(g->esb.done_ctr);
+  for (int k = 0; k < kSlots; ++k) {
+    if (g->g_done[k]) cudaEventDestroy(g->g_done[k]);
+    if (g->k1_beg[k]) cudaEventDestroy(g->k1_beg[k]);
+    if (g->k1_end[k]) cudaEventDestroy(g->k1_end[k]);
+  }
+  if (g->stream_e) cudaStreamDestroy(g->stream_e);
+  free(g);
+}
+
+FE_API int esvio_fe_group_create(const esvio_fe_config* cfg, int32_t n_streams,
+                                 esvio_fe_group** out) {
+  if (!cfg || !out || n_streams < 1 || n_streams > kMaxCams / 2) return ESVIO_FE_EINVAL;
+  *out = nullptr;
+  if (cfg->equalize || cfg->median_blur_kernel_size || cfg->do_motion_correction)
+    return ESVIO_FE_EINVAL;  // the batched event stage covers the plain path only
+  esvio_fe_group* g = (esvio_fe_group*)calloc(1, sizeof(esvio_fe_group));
+  if (!g) return ESVIO_FE_EINVAL;
+  g->S = n_streams;
+  g->dev = cfg->device_id;
+  for (int i = 0; i < n_streams; ++i) {
+    const int rc = esvio_fe_create(cfg, &g->m[i]);
+    if (rc != ESVIO_FE_OK) {
+      g->S = i;
+      esvio_fe_group_destroy(g);
+      return rc;
+    }
+    g->own_sae[i] = g->m[i]->sae;
+    g->own_lat[i] = g->m[i]->lat;
+  }
+  esvio_fe* f0 = g->m[0];
+  const int NC = 2 * n_streams;
+  const size_t npx = f0->npx;
+  g->bl = f0->bl;
+  const int nb = g->bl.n_bins + 1;
+  cudaError_t ce = cudaSetDevice(g->dev);
+#define GC(call) if (ce == cudaSuccess) ce = (call)
+  GC(cudaStreamCreateWithFlags(&g->stream_e, cudaStreamNonBlocking));
+  GC(cudaMalloc(&g->sae, npx * NC * sizeof(double2)));
+  GC(cudaMalloc(&g->lat, npx * NC * sizeof(double2)));
+  GC(cudaMemset(g->sae, 0, npx * NC * sizeof(double2)));
+  GC(cudaMemset(g->lat, 0, npx * NC * sizeof(double2)));
+  g->esb.n_cams = NC;
+  for (int c = 0; c < NC; ++c) {
+    GC(cudaMalloc(&g->esb.bt[c], (size_t)f0->cap * sizeof(double)));
+    GC(cudaMalloc(&g->esb.bk[c], (size_t)f0->cap * sizeof(uint16_t)));
+  }
+  GC(cudaMalloc(&g->esb.counts, (size_t)NC * nb * g->bl.max_chunks * sizeof(uint32_t)));
+  GC(cudaMalloc(&g->esb.bin_total, (size_t)NC * nb * sizeof(uint32_t)));
+  GC(cudaMalloc(&g->esb.bin_start, (size_t)NC * (nb + 1) * sizeof(uint32_t)));
+  GC(cudaMalloc(&g->esb.done_ctr, NC * sizeof(unsigned int)));
+  GC(cudaMemset(g->esb.done_ctr, 0, NC * sizeof(unsigned int)));
+  for (int k = 0; k < kSlots; ++k) {
+    GC(cudaEventCreateWithFlags(&g->g_done[k], cudaEventDisableTiming));
+    GC(cudaEventCreate(&g->k1_beg[k]));
+    GC(cudaEventCreate(&g->k1_end[k]));
+  }
+  GC(cudaDeviceSynchronize());
+#undef GC
+  int rc = ce == cudaSuccess ? ESVIO_FE_OK : ESVIO_FE_ECUDA;
+  if (rc == ESVIO_FE_OK) rc = make_state_map(f0, g->sae, &g->map_sae, NC);
+  if (rc == ESVIO_FE_OK) rc = make_state_map(f0, g->lat, &g->map_lat, NC);
+  if (rc != ESVIO_FE_OK) {
+    fprintf(stderr, "esvio_fe_group_create: %s\n", ce != cudaSuccess ? cudaGetErrorString(ce) : f0->err);
+    esvio_fe_group_destroy(g);
+    return rc;
+  }
+  for (int i = 0; i < n_streams; ++i) {  // the members see their slice of the group's state
+    g->m[i]->sae = g->sae + (size_t)2 * i * npx;
+    g->m[i]->lat = g->lat + (size_t)2 * i * npx;
+    g->m[i]->group = g;
+  }
+  *out = g;
+  return ESVIO_FE_OK;
+}
+
+FE_API esvio_fe* esvio_fe_group_member(esvio_fe_group* g, int32_t i) {
+  return (g && i >= 0 && i < g->S) ? g->m[i] : nullptr;
+}
+
+FE_API int esvio_fe_group_track_submit(esvio_fe_group* g, const double* cur_time,
+                                       const esvio_events* left, const esvio_events* right,
+                                       const int32_t* pub_this_frame) {
+  if (!g || !cur_time || !left || !right || !pub_this_frame) return ESVIO_FE_EINVAL;
+  esvio_fe* fe = g->m[0];  // error text lands on member 0
+  CU(cudaSetDevice(g->dev));
+  const int S = g->S;
+  WindowPlan w[kMaxCams / 2];
+  DevEvents ev[kMaxCams];
+  int rc;
+  for (int i = 0; i < S; ++i)
+    if ((rc = plan_window(g->m[i], &w[i])) != ESVIO_FE_OK) return rc;
+  cudaStream_t se = g->stream_e;
+  const int slot = w[0].slot;  // members are always submitted and waited together
+  // the previous window's corner flags read the SAE this window is about to change
+  // and pyr[cur] was the previous image of window k-2, whose temporal LK may still read it
+  for (int i = 0; i < S; ++i) {
+    if (g->m[i]->windows > 0) CU(cudaStreamWaitEvent(se, g->m[i]->e_done[(w[i].slot + kSlots - 1) % kSlots], 0));
+    if (g->m[i]->windows >= 2) CU(cudaStreamWaitEvent(se, g->m[i]->t1_done[(w[i].slot + 1) % kSlots], 0));
+  }
+  for (int i = 0; i < S; ++i) {
+    if ((rc = stage_events(g->m[i], w[i].slot, 0, &left[i], &ev[2 * i], se)) != ESVIO_FE_OK) return rc;
+    if ((rc = stage_events(g->m[i], w[i].slot, 1, &right[i], &ev[2 * i + 1], se)) != ESVIO_FE_OK) return rc;
+  }
+  launch_bin_events(g->bl, g->esb, ev, se, &g->launches);
+  SaeTsParams sp;
+  sp.W = fe->W;
+  sp.H = fe->H;
+  sp.tiles_x = g->bl.tiles_x;
+  sp.n_tiles = g->bl.n_tiles;
+  sp.n_cams = 2 * S;
+  sp.decay_sec = fe->cfg.decay_ms / 1000.0;
+  sp.inv_decay = 1.0 / sp.decay_sec;
+  sp.filter_threshold = fe->cfg.feature_filter_threshold;
+  sp.ignore_polarity = fe->cfg.ignore_polarity;
+  sp.bin_start = g->esb.bin_start;
+  sp.ts_pitch = fe->pd.pitch[0];
+  uint8_t* imgs[kMaxCams];
+  for (int c = 0; c < kMaxCams; ++c) {
+    const bool on = c < 2 * S;
+    const int i = c / 2;
+    sp.t_ref[c] = on ? cur_time[i] : 0.0;
+    sp.bt[c] = on ? g->esb.bt[c] : nullptr;
+    sp.bk[c] = on ? g->esb.bk[c] : nullptr;
+    imgs[c] = on ? g->m[i]->pyr[(c & 1) ? w[i].rcur : w[i].cur] : nullptr;
+    sp.ts[c] = imgs[c];
+  }
+  CU(cudaEventRecord(g->k1_beg[slot], se));
+  launch_sae_update_ts(sp, g->map_sae, g->map_lat, se, &g->launches);
+  CU(cudaEventRecord(g->k1_end[slot], se));
+  g->k1_slot_valid[slot] = 1;
+  launch_pyramids(fe->pd, imgs, 2 * S, se, &g->launches);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(g->g_done[slot], se));
+  for (int i = 0; i < S; ++i) {
+    esvio_fe* m = g->m[i];
+    m->ts_sel[0] = m->pyr[w[i].cur];
+    m->ts_sel[1] = m->pyr[w[i].rcur];
+    m->pev_valid[w[i].slot] = 0;
+    CU(cudaStreamWaitEvent(m->stream_e, g->g_done[slot], 0));
+    if ((rc = submit_tracking(m, w[i], ev[2 * i], cur_time[i], pub_this_frame[i])) != ESVIO_FE_OK) return rc;
+  }
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_group_track_wait(esvio_fe_group* g, esvio_tracks* out) {
+  if (!g || !out) return ESVIO_FE_EINVAL;
+  const int slot = g->m[0]->q_head;
+  for (int i = 0; i < g->S; ++i) {
+    const int rc = esvio_fe_track_wait(g->m[i], &out[i]);
+    if (rc != ESVIO_FE_OK) return rc;
+  }
+  if (g->k1_slot_valid[slot]) {
+    g->k1_ms_valid = cudaEventElapsedTime(&g->k1_ms, g->k1_beg[slot], g->k1_end[slot]) == cudaSuccess;
+    g->k1_slot_valid[slot] = 0;
+  }
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_group_track(esvio_fe_group* g, const double* cur_time, const esvio_events* left,
+                                const esvio_events* right, const int32_t* pub_this_frame,
+                                esvio_tracks* out) {
+  const int rc = esvio_fe_group_track_submit(g, cur_time, left, right, pub_this_frame);
+  if (rc != ESVIO_FE_OK) return rc;
+  return esvio_fe_group_track_wait(g, out);
+}
+
+FE_API int esvio_fe_group_kernel_launches(esvio_fe_group* g, int64_t* count) {
+  if (!g || !count) return ESVIO_FE_EINVAL;
+  int64_t n = g->launches;
+  for (int i = 0; i < g->S; ++i) n += g->m[i]->launches;
+  *count = n;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_group_sae_ts_ms(esvio_fe_group* g, float* ms) {
+  if (!g || !ms) return ESVIO_FE_EINVAL;
+  if (!g->k1_ms_valid) return ESVIO_FE_ESTATE;
+  *ms = g->k1_ms;
   return ESVIO_FE_OK;
 }
 
@@ -870,6 +1102,7 @@ FE_API int esvio_fe_stage_motion_correct(esvio_fe* fe, const esvio_motion* mc, c
 FE_API int esvio_fe_stage_update_mc(esvio_fe* fe, double t_ref, const esvio_events* left,
                                     const esvio_events* right, const esvio_motion* mc) {
   if (!fe) return ESVIO_FE_EINVAL;
+  if (fe->group) return fail(fe, ESVIO_FE_ESTATE, "handle belongs to a group", cudaSuccess);
   if (mc && !fe->cfg.do_motion_correction)
     return fail(fe, ESVIO_FE_ESTATE, "motion compensation needs config.do_motion_correction", cudaSuccess);
   if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "windows in flight", cudaSuccess);

@@ -362,6 +362,97 @@ class EventFrontEnd:
         return out
 
 
+class _MemberView(EventFrontEnd):
+    """Read-only view of a group member (time surface, SAE planes, pyramids)."""
+
+    def __init__(self, handle, cfg_struct):
+        self._c = cfg_struct
+        self.W, self.H, self.M = cfg_struct.width, cfg_struct.height, cfg_struct.max_cnt
+        self._h = C.c_void_p(handle)
+        self._inflight = []
+
+    def close(self):
+        self._h = None
+
+
+class EventFrontEndGroup:
+    """`esvio_fe_group`: S independent stereo streams of one configuration whose event stage
+    runs batched (one k_sae_update_ts launch per window for all 2S cameras)."""
+
+    def __init__(self, cfg: dict, n_streams: int):
+        self.S = int(n_streams)
+        self._c = make_config(cfg)
+        self.M = self._c.max_cnt
+        h = C.c_void_p()
+        st = _capi.lib().esvio_fe_group_create(C.byref(self._c), self.S, C.byref(h))
+        if st != _capi.OK:
+            raise FrontEndError(st, "esvio_fe_group_create")
+        self._h = h
+        self._tracks = (Tracks * self.S)()
+        self._bufs = []
+        for i in range(self.S):
+            b = {k: np.zeros(self.M, np.int32) for k in ("id", "track_cnt", "id_right")}
+            b.update({k: np.zeros(self.M, np.float32) for k in
+                      ("u", "v", "un_x", "un_y", "vx", "vy", "ru", "rv", "run_x", "run_y", "rvx", "rvy")})
+            self._tracks[i].capacity = self.M
+            for k, a in b.items():
+                setattr(self._tracks[i], k, a.ctypes.data_as(_capi._pi if a.dtype == np.int32 else _capi._pf))
+            self._bufs.append(b)
+        self._inflight = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _capi.lib().esvio_fe_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def member(self, i) -> EventFrontEnd:
+        return _MemberView(_capi.lib().esvio_fe_group_member(self._h, int(i)), self._c)
+
+    def _chk(self, st, where):
+        if st != _capi.OK:
+            m = _capi.lib().esvio_fe_group_member(self._h, 0)
+            raise FrontEndError(st, where, _capi.lib().esvio_fe_last_error(m).decode())
+
+    def submit(self, cur_times, lefts, rights, pubs):
+        ls = [l if isinstance(l, _Ev) else _Ev(l) for l in lefts]
+        rs = [r if isinstance(r, _Ev) else _Ev(r) for r in rights]
+        la, ra = (Events * self.S)(*[e.s for e in ls]), (Events * self.S)(*[e.s for e in rs])
+        ct = (C.c_double * self.S)(*[float(t) for t in cur_times])
+        pb = (C.c_int32 * self.S)(*[int(bool(p)) for p in pubs])
+        self._inflight.append((ls, rs, la, ra))
+        self._chk(_capi.lib().esvio_fe_group_track_submit(self._h, ct, la, ra, pb), "group_track_submit")
+
+    def wait(self, unpack=True):
+        self._chk(_capi.lib().esvio_fe_group_track_wait(self._h, self._tracks), "group_track_wait")
+        self._inflight.pop(0)
+        if not unpack:
+            return [(t.n_left, t.n_right) for t in self._tracks]
+        out = []
+        for t, b in zip(self._tracks, self._bufs):
+            nl, nr = t.n_left, t.n_right
+            o = {k: b[k][:nl].copy() for k in ("id", "track_cnt", "u", "v", "un_x", "un_y", "vx", "vy")}
+            o.update({k: b[k][:nr].copy() for k in ("id_right", "ru", "rv", "run_x", "run_y", "rvx", "rvy")})
+            out.append(o)
+        return out
+
+    def track(self, cur_times, lefts, rights, pubs):
+        self.submit(cur_times, lefts, rights, pubs)
+        return self.wait()
+
+    def kernel_launches(self):
+        n = C.c_int64()
+        self._chk(_capi.lib().esvio_fe_group_kernel_launches(self._h, C.byref(n)), "group_kernel_launches")
+        return n.value
+
+    def sae_ts_ms(self):
+        ms = C.c_float()
+        self._chk(_capi.lib().esvio_fe_group_sae_ts_ms(self._h, C.byref(ms)), "group_sae_ts_ms")
+        return ms.value
+
+
 class FeatureTracker:
     """Drop-in mirror of the reference's `FeatureTracker` for the event path
     (feature_tracker.h:44-135).  `PUB_THIS_FRAME` is the reference's global of the same name

@@ -181,6 +181,30 @@ int esvio_fe_track_submit_mc(esvio_fe *fe, double cur_time, const esvio_events *
                              const esvio_events *right, int32_t pub_this_frame,
                              const esvio_motion *mc);
 
+/* ---- groups: several independent stereo streams on one GPU ---- */
+/* S handles of the same configuration whose event stage (binning, SAE update + time surface,
+ * pyramids) runs as one batched launch sequence per window -- one k_sae_update_ts launch covers
+ * all 2S cameras -- while the per-stream tracking stages run concurrently on the members' own
+ * streams (SURVEY.md 8e "independent streams"; BASELINE configs[4]).  Results are identical to
+ * S separate handles.  The reference would need one process per stream (its tracker state is
+ * global, feature_tracker.cpp:7-9).  1 <= n_streams <= 8; equalize / median blur / motion
+ * compensation are not available in a group.  All arrays below have n_streams entries. */
+typedef struct esvio_fe_group esvio_fe_group;
+int esvio_fe_group_create(const esvio_fe_config *cfg, int32_t n_streams, esvio_fe_group **out);
+void esvio_fe_group_destroy(esvio_fe_group *g);
+/* member i, for the read-only queries (esvio_fe_time_surface, esvio_fe_get_sae, ...) */
+esvio_fe *esvio_fe_group_member(esvio_fe_group *g, int32_t i);
+int esvio_fe_group_track(esvio_fe_group *g, const double *cur_time, const esvio_events *left,
+                         const esvio_events *right, const int32_t *pub_this_frame,
+                         esvio_tracks *out);
+int esvio_fe_group_track_submit(esvio_fe_group *g, const double *cur_time,
+                                const esvio_events *left, const esvio_events *right,
+                                const int32_t *pub_this_frame);
+int esvio_fe_group_track_wait(esvio_fe_group *g, esvio_tracks *out);
+int esvio_fe_group_kernel_launches(esvio_fe_group *g, int64_t *count);
+/* CUDA-event milliseconds of the batched k_sae_update_ts launch of the last completed window */
+int esvio_fe_group_sae_ts_ms(esvio_fe_group *g, float *ms);
+
 /* replaces FeatureTracker::gettimesurface() (feature_tracker.cpp:894-897): the
  * CV_8U time surface of the last window; dst has `stride` bytes per row. */
 int esvio_fe_time_surface(esvio_fe *fe, int32_t cam, uint8_t *dst, size_t stride);

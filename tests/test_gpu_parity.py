@@ -572,3 +572,42 @@ def test_ignore_polarity_time_surface(fe_mod, ora):
             _assert_ts_equal(fe.time_surface(cam), ref)
             assert ref.min() == 0 and ref.max() >= 250
     fe.close()
+
+
+# ---- groups: S streams, one batched event stage (SURVEY.md 8e "independent streams") ----
+@pytest.mark.parametrize("W,H,rate,S", [(346, 260, 1.0e6, 3), (640, 480, 5.0e6, 2)])
+def test_group_equals_separate_handles(fe_mod, W, H, rate, S):
+    """A group of S streams returns, stream by stream, exactly what S separate handles return
+    (same kernels, the event stage merely shares its launches), pipelined 3 deep."""
+    cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=int(rate / 30) + 1024)
+    streams = [synth.StereoEventStream(W, H, rate, stream=i) for i in range(S)]
+    n_win = 7
+    wins = [[st.stereo_window(k) for k in range(n_win)] for st in streams]
+    singles = [fe_mod.EventFrontEnd(cfg) for _ in range(S)]
+    ref = [[singles[i].track(wins[i][k][2], wins[i][k][0], wins[i][k][1], k % 2 == 0) for k in range(n_win)]
+           for i in range(S)]
+    grp = fe_mod.EventFrontEndGroup(cfg, S)
+    got = [[] for _ in range(S)]
+    def sub(k):
+        grp.submit([wins[i][k][2] for i in range(S)], [wins[i][k][0] for i in range(S)],
+                   [wins[i][k][1] for i in range(S)], [k % 2 == 0] * S)
+    def take():
+        for i, o in enumerate(grp.wait()):
+            got[i].append(o)
+    sub(0); sub(1)
+    for k in range(2, n_win):
+        sub(k); take()
+    take(); take()
+    for i in range(S):
+        for k in range(n_win):
+            for key in ("id", "track_cnt", "u", "v", "un_x", "un_y", "vx", "vy", "id_right", "ru", "rv"):
+                assert np.array_equal(got[i][k][key], ref[i][k][key]), (i, k, key)
+        m = grp.member(i)
+        for cam in (0, 1):
+            assert np.array_equal(m.time_surface(cam), singles[i].time_surface(cam))
+            for a, b in zip(m.sae_planes(cam), singles[i].sae_planes(cam)):
+                assert np.array_equal(a, b)
+    assert grp.sae_ts_ms() > 0 and grp.kernel_launches() > 0
+    grp.close()
+    for f in singles:
+        f.close()
