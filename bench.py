@@ -329,6 +329,63 @@ def main_ours(args):
             fe4.track_raw(t, l, r, k % pub_div == 0)
         sync_ms = (time.perf_counter() - t0) * 1e3 / n_sync
         fe4.close()
+    # ---------------- batched leg (N = 1): S streams of this workload in one group ----------
+    # SURVEY.md 8d caveat: one window of one stream moves 6-25 MB per k_sae_update_ts launch,
+    # i.e. 1-4 us at the HBM peak -- the roofline of that kernel only means something when a
+    # launch covers several streams (BASELINE configs[4], esvio_fe_group_*).
+    batched = None
+    if world == 1 and args.batch_streams > 1:
+        S = args.batch_streams
+        Kb = min(K, args.batch_steps)
+        nb_w = Wm + Kb
+        grp = frontend.EventFrontEndGroup(cfg, S)
+        m0 = grp.member(0)
+        bw = []
+        for i in range(S):
+            ws = wins[:nb_w] if i == 0 else gen_windows(w, 100 + i, nb_w)
+            bw.append([(frontend._Ev(frontend.DeviceEvents(m0, L)), frontend._Ev(frontend.DeviceEvents(m0, R)), t,
+                        len(L[0]) + len(R[0])) for L, R, t in ws])
+        def gsub(k):
+            grp.submit([bw[i][k][2] for i in range(S)], [bw[i][k][0] for i in range(S)],
+                       [bw[i][k][1] for i in range(S)], [k % pub_div == 0] * S)
+        for k in range(Wm):
+            gsub(k)
+            grp.wait(unpack=False)
+        flush.fill_(3)
+        torch.cuda.synchronize()
+        k1_ms = []
+        t0 = time.perf_counter()
+        gsub(Wm)
+        if Kb > 1:
+            gsub(Wm + 1)
+        done = 0
+        for k in range(Wm + 2, Wm + Kb):
+            gsub(k)
+            grp.wait(unpack=False)
+            done += 1
+            k1_ms.append(grp.sae_ts_ms())
+        while done < Kb:
+            grp.wait(unpack=False)
+            done += 1
+            k1_ms.append(grp.sae_ts_ms())
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        n_ev_b = sum(bw[i][k][3] for i in range(S) for k in range(Wm, Wm + Kb))
+        k1 = float(np.mean(k1_ms))
+        alg = S * 2 * 17 * w["width"] * w["height"] + 45 * n_ev_b / Kb
+        peak_b, _ = peaks()
+        batched = {"streams": S, "steps": Kb, "value": n_ev_b / (wall_ms * 1e-3) / 1e6, "unit": UNIT,
+                   "ms_per_step": wall_ms / Kb, "timing": "host wall clock around submit/wait with "
+                   "synchronize on both sides, events device-resident, 3 windows in flight",
+                   "gpu_launches": grp.kernel_launches(),
+                   "roofline": {"bound": "hbm", "kernel": "k_sae_update_ts", "kernel_ms": k1,
+                                "algorithmic_bytes_per_launch": int(alg),
+                                "achieved": alg / (k1 * 1e-3) / 1e9, "peak": peak_b, "unit": "GB/s",
+                                "frac": alg / (k1 * 1e-3) / 1e9 / peak_b,
+                                "note": "one launch covers the 2*S cameras of the group; CUDA events "
+                                        "around the launch on the group's event-stage stream, other "
+                                        "stages of other windows share the SMs"}}
+        grp.close()
     e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -413,6 +470,8 @@ def main_ours(args):
             "stage_ms": stage_ms,
             "tracks_last_window": {"left": int(n_left_last), "right": int(n_right_last)},
         }
+        if batched is not None:
+            line["batched"] = batched
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if parity is not None:
@@ -431,6 +490,9 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(synth.WORKLOADS))
     ap.add_argument("--cpu-windows", type=int, default=150)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--batch-streams", type=int, default=8,
+                    help="streams of the extra batched leg at N=1 (esvio_fe_group); 1 disables it")
+    ap.add_argument("--batch-steps", type=int, default=60)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -22,6 +22,9 @@ int bin_configure(int n_bins);
 
 #define FE_API extern "C" __attribute__((visibility("default")))
 
+constexpr int kLeftBufs = 4, kRightBufs = 3, kRightBase = kLeftBufs, kScratchBase = kLeftBufs + kRightBufs,
+              kNumPyr = kScratchBase + 2;
+
 struct esvio_fe {
   esvio_fe_config cfg;
   int dev;
@@ -33,9 +36,13 @@ struct esvio_fe {
   double2 *sae, *lat;  // [2][H][W]
   CUtensorMap map_sae, map_lat;
   PyrDesc pd;
-  // Pyramid buffers: 0..2 left, 3..5 right (rotating: up to three windows are in flight, one
-  // per pipeline stage), 6..7 scratch for esvio_fe_stage_lk
-  uint8_t* pyr[8];
+  // Pyramid buffers: 0..3 left, 4..6 right, 7..8 scratch for esvio_fe_stage_lk.  Up to three
+  // windows are in flight, one per pipeline stage.  The left image of window k is read by the
+  // temporal LK of k (as cur) and of k+1 (as prev) and by the stereo LK of k; when window k+4
+  // overwrites it, windows <= k+1 have been waited for -- hence four left buffers (three would
+  // let the event stage of k+3 overwrite what the temporal LK of k+1 may still read).  The
+  // right image of window k is only read by its own stereo LK: three buffers.
+  uint8_t* pyr[kNumPyr];
   // image conditioning (median blur / CLAHE + normalize): [stage][camera] scratch images with
   // the layout of pyramid level 0; ts_sel[cam] = the time surface the corner selection and
   // gettimesurface() see (after the median blur, before CLAHE)
@@ -188,7 +195,7 @@ static void free_all(esvio_fe* fe) {
   if (fe->stream) cudaStreamSynchronize(fe->stream);
   cudaFree(fe->sae);
   cudaFree(fe->lat);
-  for (int i = 0; i < 8; ++i) cudaFree(fe->pyr[i]);
+  for (int i = 0; i < kNumPyr; ++i) cudaFree(fe->pyr[i]);
   for (int i = 0; i < 3; ++i) cudaFree(fe->aux[i][0]), cudaFree(fe->aux[i][1]);
   cudaFree(fe->clahe_lut);
   cudaFree(fe->clahe_minmax);
@@ -236,13 +243,13 @@ static int reset_state(esvio_fe* fe) {
   const size_t plane = fe->npx * 2 * sizeof(double2);
   CU(cudaMemsetAsync(fe->sae, 0, plane, fe->stream));
   CU(cudaMemsetAsync(fe->lat, 0, plane, fe->stream));
-  for (int i = 0; i < 8; ++i) CU(cudaMemsetAsync(fe->pyr[i], 0, fe->pd.bytes, fe->stream));
+  for (int i = 0; i < kNumPyr; ++i) CU(cudaMemsetAsync(fe->pyr[i], 0, fe->pd.bytes, fe->stream));
   CU(cudaMemsetAsync(fe->tb.snap_hdr, 0, sizeof(int) * 16 * kSlots, fe->stream));
   CU(cudaMemsetAsync(fe->tb.st, 0, sizeof(TrackState), fe->stream));
   CU(cudaMemsetAsync(fe->tb.result, 0, fe->result_words * 4, fe->stream));
   CU(cudaStreamSynchronize(fe->stream));
   fe->cur_left = fe->prev_left = 0;
-  fe->cur_right = 3;
+  fe->cur_right = kRightBase;
   fe->ts_sel[0] = fe->ts_sel[1] = nullptr;
   fe->windows = 0;
   fe->prev_time = 0.0;
@@ -313,7 +320,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   CUC(cudaMalloc(&fe->sae, fe->npx * 2 * sizeof(double2)));
   CUC(cudaMalloc(&fe->lat, fe->npx * 2 * sizeof(double2)));
   build_pyr_desc(fe->W, fe->H, &fe->pd);
-  for (int i = 0; i < 8; ++i) CUC(cudaMalloc(&fe->pyr[i], fe->pd.bytes));
+  for (int i = 0; i < kNumPyr; ++i) CUC(cudaMalloc(&fe->pyr[i], fe->pd.bytes));
   if (cfg->equalize || cfg->median_blur_kernel_size) {
     for (int i = 0; i < 3; ++i)
       for (int c = 0; c < 2; ++c) {
@@ -613,9 +620,9 @@ static int plan_window(esvio_fe* fe, WindowPlan* w) {
   if (fe->q_count >= kSlots)
     return fail(fe, ESVIO_FE_ESTATE, "three windows already in flight", cudaSuccess);
   w->slot = (fe->q_head + fe->q_count) % kSlots;
-  w->cur = fe->windows == 0 ? 0 : (fe->cur_left + 1) % 3;
+  w->cur = fe->windows == 0 ? 0 : (fe->cur_left + 1) % kLeftBufs;
   w->prev = fe->windows == 0 ? 0 : fe->cur_left;  // first window: prev_img = cur_img
-  w->rcur = fe->windows == 0 ? 3 : 3 + (fe->cur_right - 3 + 1) % 3;
+  w->rcur = fe->windows == 0 ? kRightBase : kRightBase + (fe->cur_right - kRightBase + 1) % kRightBufs;
   return ESVIO_FE_OK;
 }
 
@@ -691,8 +698,6 @@ FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_e
   if ((rc = stage_events(fe, w.slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
   if ((rc = stage_events(fe, w.slot, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
   prof_mark(fe, 1);
-  // pyr[w.cur] was the PREVIOUS image of window k-2, whose temporal LK may still be reading it
-  if (fe->windows >= 2) CU(cudaStreamWaitEvent(fe->stream_e, fe->t1_done[(w.slot + 1) % kSlots], 0));
   if ((rc = run_event_stage(fe, cur_time, ev, w.cur, w.rcur, mc)) != ESVIO_FE_OK) return rc;
   if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame)) != ESVIO_FE_OK) return rc;
   fe->pev_valid[w.slot] = fe->profiling;
@@ -908,11 +913,8 @@ FE_API int esvio_fe_group_track_submit(esvio_fe_group* g, const double* cur_time
   cudaStream_t se = g->stream_e;
   const int slot = w[0].slot;  // members are always submitted and waited together
   // the previous window's corner flags read the SAE this window is about to change
-  // and pyr[cur] was the previous image of window k-2, whose temporal LK may still read it
-  for (int i = 0; i < S; ++i) {
+  for (int i = 0; i < S; ++i)
     if (g->m[i]->windows > 0) CU(cudaStreamWaitEvent(se, g->m[i]->e_done[(w[i].slot + kSlots - 1) % kSlots], 0));
-    if (g->m[i]->windows >= 2) CU(cudaStreamWaitEvent(se, g->m[i]->t1_done[(w[i].slot + 1) % kSlots], 0));
-  }
   for (int i = 0; i < S; ++i) {
     if ((rc = stage_events(g->m[i], w[i].slot, 0, &left[i], &ev[2 * i], se)) != ESVIO_FE_OK) return rc;
     if ((rc = stage_events(g->m[i], w[i].slot, 1, &right[i], &ev[2 * i + 1], se)) != ESVIO_FE_OK) return rc;
@@ -1159,17 +1161,17 @@ FE_API int esvio_fe_stage_lk(esvio_fe* fe, const uint8_t* prev_img, const uint8_
   if (n == 0) return ESVIO_FE_OK;
   CU(cudaSetDevice(fe->dev));
   cudaStream_t s = fe->stream;
-  CU(cudaMemcpy2DAsync(fe->pyr[6], fe->pd.pitch[0], prev_img, fe->W, fe->W, fe->H,
+  CU(cudaMemcpy2DAsync(fe->pyr[kScratchBase], fe->pd.pitch[0], prev_img, fe->W, fe->W, fe->H,
                        cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpy2DAsync(fe->pyr[7], fe->pd.pitch[0], next_img, fe->W, fe->W, fe->H,
+  CU(cudaMemcpy2DAsync(fe->pyr[kScratchBase + 1], fe->pd.pitch[0], next_img, fe->W, fe->W, fe->H,
                        cudaMemcpyHostToDevice, s));
-  uint8_t* imgs[2] = {fe->pyr[6], fe->pyr[7]};
+  uint8_t* imgs[2] = {fe->pyr[kScratchBase], fe->pyr[kScratchBase + 1]};
   launch_pyramids(fe->pd, imgs, 2, s, &fe->launches);
   CU(cudaMemcpyAsync(fe->d_scratch_n, &n, sizeof(int), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(fe->d_scratch_p0, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
   if (use_initial_flow)
     CU(cudaMemcpyAsync(fe->d_scratch_p1, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
-  launch_lk(fe->pd, fe->pyr[6], fe->pyr[7], fe->d_scratch_p0, fe->d_scratch_p1, fe->d_scratch_st,
+  launch_lk(fe->pd, fe->pyr[kScratchBase], fe->pyr[kScratchBase + 1], fe->d_scratch_p0, fe->d_scratch_p1, fe->d_scratch_st,
             nullptr, nullptr, fe->d_scratch_n, n, max_level, use_initial_flow, 0, s, &fe->launches);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(next_pts, fe->d_scratch_p1, sizeof(float2) * n, cudaMemcpyDeviceToHost, s));
