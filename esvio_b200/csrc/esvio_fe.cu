@@ -302,7 +302,13 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     return ESVIO_FE_ENODEV;
   }
   CUC(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
-  CUC(cudaStreamCreateWithFlags(&fe->stream_e, cudaStreamNonBlocking));
+  {
+    // the event stage is short, wide and latency-bound: let its CTAs go first when the long
+    // single-CTA-per-point LK kernels of the other stages are also pending
+    int prio_lo = 0, prio_hi = 0;
+    CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUC(cudaStreamCreateWithPriority(&fe->stream_e, cudaStreamNonBlocking, prio_hi));
+  }
   CUC(cudaStreamCreateWithFlags(&fe->stream_t1, cudaStreamNonBlocking));
 
   fe->esb.n_cams = 2;
@@ -855,7 +861,11 @@ FE_API int esvio_fe_group_create(const esvio_fe_config* cfg, int32_t n_streams,
   const int nb = g->bl.n_bins + 1;
   cudaError_t ce = cudaSetDevice(g->dev);
 #define GC(call) if (ce == cudaSuccess) ce = (call)
-  GC(cudaStreamCreateWithFlags(&g->stream_e, cudaStreamNonBlocking));
+  {
+    int prio_lo = 0, prio_hi = 0;
+    GC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    GC(cudaStreamCreateWithPriority(&g->stream_e, cudaStreamNonBlocking, prio_hi));
+  }
   GC(cudaMalloc(&g->sae, npx * NC * sizeof(double2)));
   GC(cudaMalloc(&g->lat, npx * NC * sizeof(double2)));
   GC(cudaMemset(g->sae, 0, npx * NC * sizeof(double2)));

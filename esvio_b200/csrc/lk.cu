@@ -103,17 +103,32 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
   const float flt_scale = 1.f / (float)(1 << 20);
   const int nlev = top + 1;
   __syncthreads();  // previous use of S is over
-  // ---- phase 1: intensity patches of all levels
-  for (int i = tid; i < nlev * kIP * kIP; i += kLkThreads) {
-    const int L = i / (kIP * kIP), rem = i - L * (kIP * kIP);
-    const int r = rem / kIP, c = rem - r * kIP;
-    const float sc = 1.f / (float)(1 << L);
-    const int ipx = (int)floorf(p0.x * sc - half), ipy = (int)floorf(p0.y * sc - half);
-    const int w = pd.w[L], h = pd.h[L];
-    uint8_t v = 0;
-    if (!(ipx < -kWin || ipx >= w || ipy < -kWin || ipy >= h))
-      v = I[pd.off[L] + (size_t)reflect101(ipy - 1 + r, h) * pd.pitch[L] + reflect101(ipx - 1 + c, w)];
-    S.I[L][r][c] = v;
+  // ---- phase 1: intensity patches of all levels.  All of a thread's (<= 18) global loads are
+  // issued before the first store, so they share one round trip to L2 instead of queueing
+  // one behind the other.
+  {
+    constexpr int kPerThread = (kMaxLevels * kIP * kIP + kLkThreads - 1) / kLkThreads;  // 18
+    uint8_t v[kPerThread];
+#pragma unroll
+    for (int q = 0; q < kPerThread; ++q) {
+      const int i = tid + q * kLkThreads;
+      v[q] = 0;
+      if (i < nlev * kIP * kIP) {
+        const int L = i / (kIP * kIP), rem = i - L * (kIP * kIP);
+        const int r = rem / kIP, c = rem - r * kIP;
+        const float sc = 1.f / (float)(1 << L);
+        const int ipx = (int)floorf(p0.x * sc - half), ipy = (int)floorf(p0.y * sc - half);
+        const int w = pd.w[L], h = pd.h[L];
+        if (!(ipx < -kWin || ipx >= w || ipy < -kWin || ipy >= h))
+          v[q] = __ldg(I + pd.off[L] + (size_t)reflect101(ipy - 1 + r, h) * pd.pitch[L] +
+                       reflect101(ipx - 1 + c, w));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kPerThread; ++q) {
+      const int i = tid + q * kLkThreads;
+      if (i < nlev * kIP * kIP) (&S.I[0][0][0])[i] = v[q];
+    }
   }
   __syncthreads();
   // ---- phase 2: Scharr derivatives
@@ -302,7 +317,7 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
 //         backward J->I from the forward result with initial flow = prev, maxLevel 1
 // mode 2: stereo pair (:490,495): forward, then backward J->I, both maxLevel `top`, no init
 __global__ void __launch_bounds__(kLkThreads)
-k_lk(PyrDesc pd, const uint8_t* __restrict__ I, const uint8_t* __restrict__ J,
+k_lk(const __grid_constant__ PyrDesc pd, const uint8_t* __restrict__ I, const uint8_t* __restrict__ J,
      const float2* __restrict__ prev_pts, float2* __restrict__ next_pts,
      uint8_t* __restrict__ status, float2* __restrict__ rev_pts, uint8_t* __restrict__ rev_status,
      const int* __restrict__ n_ptr, int top, int use_init, int mode) {

@@ -169,7 +169,49 @@ size_t select_smem_bytes(int W, int H) { return (size_t)H * ((W + 31) / 32) * si
 
 constexpr int kSelThreads = 1024;
 constexpr int kSelPerThread = 4;
+constexpr int kSelFast = 256;  // tracked points the bit-matrix path of Event_setMask handles
 
+// the pixel (bx, by) lies inside OpenCV's filled circle of radius r around (ax, ay)
+__device__ __forceinline__ bool in_disc(int ax, int ay, int bx, int by, int r, const int* hw) {
+  const int dy = by > ay ? by - ay : ay - by;
+  if (dy > r) return false;
+  const int dx = bx > ax ? bx - ax : ax - bx;
+  return dx <= hw[dy];
+}
+
+// any warp: rows over lanes, atomicOr because several warps fill at once
+__device__ __forceinline__ void fill_disc_warp_atomic(uint32_t* mask, int words, int W, int H,
+                                                      int cx, int cy, int r, const int* hw) {
+  for (int k = lane_id() - r; k <= r; k += 32) {
+    const int yy = cy + k;
+    if (yy < 0 || yy >= H) continue;
+    const int h = hw[k < 0 ? -k : k];
+    if (h < 0) continue;
+    int x0 = cx - h, x1 = cx + h;
+    if (x0 < 0) x0 = 0;
+    if (x1 > W - 1) x1 = W - 1;
+    if (x0 > x1) continue;
+    uint32_t* row = mask + (size_t)yy * words;
+    const int w0 = x0 >> 5, w1 = x1 >> 5;
+    for (int w = w0; w <= w1; ++w) {
+      uint32_t bits = 0xffffffffu;
+      if (w == w0) bits &= 0xffffffffu << (x0 & 31);
+      if (w == w1) bits &= 0xffffffffu >> (31 - (x1 & 31));
+      atomicOr(&row[w], bits);
+    }
+  }
+}
+
+// Event_setMask + Event_FeaturesToTrack + id assignment.
+//  (1) Event_setMask (feature_tracker.cpp:123-151): points are visited by track_cnt descending
+//      (ties keep their order); a point survives iff no surviving earlier point's filled circle
+//      covers its rounded pixel.  "Covers" is evaluated pairwise for all pairs in parallel (bit
+//      matrix, <= 256 points), the greedy pass then only ANDs bit rows, and all surviving discs
+//      are rastered into the bit mask at once.  More than 256 points: the serial mask walk.
+//  (2) Event_FeaturesToTrack (:13-38): the left events are taken 4096 at a time in stream
+//      order; flagged events (Arc* corner on a live time-surface pixel) that are not yet
+//      masked are compacted, one warp then serves them first come, first served, and the walk
+//      stops as soon as MAX_CNT is reached (usually within the first steps).
 __global__ void __launch_bounds__(kSelThreads)
 k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict__ flags) {
   extern __shared__ uint32_t s_mask[];
@@ -178,6 +220,9 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
   __shared__ int s_order[kMaxCnt];
   __shared__ float2 s_pts[kMaxCnt];
   __shared__ int s_ids[kMaxCnt], s_cnt[kMaxCnt];
+  __shared__ uint32_t s_conf[kSelFast][kSelFast / 32];  // [b][a/32]: a (earlier) covers b
+  __shared__ short2 s_px[kSelFast];
+  __shared__ uint32_t s_keptbits[kSelFast / 32];
   __shared__ uint32_t s_cand[kSelThreads * kSelPerThread];
   __shared__ int s_kept, s_found;
 
@@ -191,8 +236,6 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
     s_kept = 0;
     s_found = 0;
   }
-  // ---- Event_setMask: visit by track_cnt descending (ties keep their order), keep a
-  //      point iff its rounded pixel is still free, then blank a disc of MIN_DIST
   if (tid < n) {
     s_pts[tid] = B.cur_pts[tid];
     s_ids[tid] = B.ids[tid];
@@ -206,7 +249,56 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
     s_order[rank] = tid;
   }
   __syncthreads();
-  if (warp == 0) {
+  if (n <= kSelFast) {
+    // ---- (1) bit-matrix path
+    if (tid < n) {
+      const float2 p = s_pts[s_order[tid]];
+      s_px[tid] = make_short2((short)max(-30000, min(30000, cv_round(p.x))),
+                              (short)max(-30000, min(30000, cv_round(p.y))));
+    }
+    __syncthreads();
+    const int nw = (n + 31) >> 5;
+    for (int i = tid; i < n * nw; i += blockDim.x) {
+      const int b = i / nw, aw = i - b * nw;
+      const short2 pb = s_px[b];
+      uint32_t bits = 0;
+      for (int k = 0; k < 32; ++k) {
+        const int a = aw * 32 + k;
+        if (a < b) {
+          const short2 pa = s_px[a];
+          if (in_disc(pa.x, pa.y, pb.x, pb.y, P.min_dist, s_hw)) bits |= 1u << k;
+        }
+      }
+      s_conf[b][aw] = bits;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t kept_w = 0;  // lane w: survivors among order positions [32w, 32w+32)
+      int kept = 0;
+      for (int b = 0; b < n; ++b) {
+        const short2 pb = s_px[b];
+        const bool inside = pb.x >= 0 && pb.x < W && pb.y >= 0 && pb.y < H;
+        const uint32_t hit = lane < nw ? (s_conf[b][lane] & kept_w) : 0u;
+        if (inside && !__any_sync(0xffffffffu, hit != 0)) {
+          if (lane == (b >> 5)) kept_w |= 1u << (b & 31);
+          if (lane == 0) {
+            const int i = s_order[b];
+            B.cur_pts[kept] = s_pts[i];
+            B.ids[kept] = s_ids[i];
+            B.cnt[kept] = s_cnt[i];
+          }
+          ++kept;
+        }
+      }
+      if (lane < kSelFast / 32) s_keptbits[lane] = kept_w;
+      if (lane == 0) s_kept = kept;
+    }
+    __syncthreads();
+    for (int b = warp; b < n; b += kSelThreads / 32)
+      if ((s_keptbits[b >> 5] >> (b & 31)) & 1u)
+        fill_disc_warp_atomic(s_mask, words, W, H, s_px[b].x, s_px[b].y, P.min_dist, s_hw);
+  } else if (warp == 0) {
+    // ---- (1) serial walk over the mask
     int kept = 0;
     for (int k = 0; k < n; ++k) {
       const int i = s_order[k];

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-T=j19
+T=j20
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/${T}_pytest.log
 timeout 400 python bench.py --steps 100 --warmup 10 --cpu-windows 20 > gpurun_out/${T}_bench_davis.json 2> gpurun_out/${T}_bench_davis.err
 timeout 400 python bench.py --steps 100 --warmup 10 --workload stereo_vga_5mevs --cpu-windows 12 --batch-streams 4 > gpurun_out/${T}_bench_vga.json 2> gpurun_out/${T}_bench_vga.err

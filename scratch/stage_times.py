@@ -10,6 +10,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 w = synth.WORKLOADS[name]
 cfg = synth.default_config(w["width"], w["height"], max_cnt=w["max_cnt"], min_dist=w["min_dist"])
 cfg["max_events_per_window"] = int(w["rate"] / synth.WINDOWS_PER_SEC) + 1024
+cfg["use_ransac"] = int(os.environ.get("USE_RANSAC", "1"))
 pub_div = int(round(synth.WINDOWS_PER_SEC / w["freq"]))
 fe = frontend.EventFrontEnd(cfg)
 s = synth.StereoEventStream(w["width"], w["height"], w["rate"], mono=w["mono"])
