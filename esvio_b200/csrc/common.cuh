@@ -295,12 +295,12 @@ struct TrackParams {
   Pinhole cam[2];
 };
 
-void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
-                          int64_t* launches);
+// snap_slot >= 0: the kernel is the last one of the window's temporal stage and also takes the
+// per-slot snapshot (cur_pts, ids, track_cnt, counters) the stereo stage works from
+void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, int snap_slot,
+                          cudaStream_t s, int64_t* launches);
 void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents& left,
-                   const uint8_t* flags, cudaStream_t s, int64_t* launches);
-void launch_snapshot(const TrackParams& P, const TrackBuffers& B, int slot, cudaStream_t s,
-                     int64_t* launches);
+                   const uint8_t* flags, int snap_slot, cudaStream_t s, int64_t* launches);
 void launch_finalize(const TrackParams& P, const TrackBuffers& B, int slot, double cur_time,
                      double prev_time, cudaStream_t s, int64_t* launches);
 void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,

@@ -651,13 +651,12 @@ static int submit_tracking(esvio_fe* fe, const WindowPlan& w, const DevEvents& e
   const int M = fe->cfg.max_cnt;
   launch_lk(fe->pd, fe->pyr[prev], fe->pyr[cur], B.prev_pts, B.cur_pts, B.st_fwd, B.rev_pts,
             B.st_bwd, &B.st->n_prev, M, 3, 0, fe->cfg.flow_back ? 1 : 0, s1, &fe->launches);
-  launch_post_temporal(fe->tp, B, s1, &fe->launches);
+  launch_post_temporal(fe->tp, B, pub_this_frame ? -1 : slot, s1, &fe->launches);
   prof_mark(fe, 6);
   if (pub_this_frame) {
     if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s1, &fe->launches);
-    launch_select(fe->tp, B, ev_left, fe->flags[slot], s1, &fe->launches);
+    launch_select(fe->tp, B, ev_left, fe->flags[slot], slot, s1, &fe->launches);
   }
-  launch_snapshot(fe->tp, B, slot, s1, &fe->launches);
   prof_mark(fe, 7);
   CU(cudaEventRecord(fe->t1_done[slot], s1));
 
@@ -1270,7 +1269,7 @@ FE_API int esvio_fe_stage_select(esvio_fe* fe, const esvio_events* left, int32_t
     CU(cudaMemcpyAsync(B.cnt, track_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, s));
   }
   launch_corner_flags(corner_params(fe, fe->cur_left, 1), ev, fe->flags[0], s, &fe->launches);
-  launch_select(fe->tp, B, ev, fe->flags[0], s, &fe->launches);
+  launch_select(fe->tp, B, ev, fe->flags[0], -1, s, &fe->launches);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));

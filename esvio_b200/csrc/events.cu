@@ -735,8 +735,9 @@ void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
   SaeMaps maps;
   maps.sae = map_sae;
   maps.lat = map_lat;
-  static const int dbg = getenv("ESVIO_K1_DBG") ? atoi(getenv("ESVIO_K1_DBG")) : 0;
   const dim3 grid(P.tiles_x, P.n_tiles / P.tiles_x, P.n_cams);
+#ifdef ESVIO_K1_EXPERIMENTS  // perf experiments only (scratch/stage_times.py); never in the product build
+  static const int dbg = getenv("ESVIO_K1_DBG") ? atoi(getenv("ESVIO_K1_DBG")) : 0;
   switch (dbg) {
     case 1: k_sae_update_ts<1><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
     case 2: k_sae_update_ts<2><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
@@ -745,6 +746,9 @@ void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
     case 7: k_sae_update_ts<7><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
     default: k_sae_update_ts<0><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
   }
+#else
+  k_sae_update_ts<0><<<grid, kSaeThreads, 0, s>>>(maps, P);
+#endif
   ++*launches;
 }
 

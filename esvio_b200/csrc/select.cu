@@ -68,10 +68,43 @@ __device__ int block_excl_scan_1024(int flag, int* s_warp /*33 ints*/, int* tota
   return r;
 }
 
+// End of the temporal/selection stage: freeze what the stereo stage needs and roll
+// prev_pts = cur_pts (feature_tracker.cpp:586) so the next window's temporal LK can start.
+// Called by all 1024 threads of the stage's last kernel, after a __syncthreads() behind the
+// writes of cur_pts / ids / cnt and of the counters.
+__device__ __forceinline__ void snapshot_tracks(const TrackParams& P, const TrackBuffers& B, int slot,
+                                                int n) {
+  TrackState* st = B.st;
+  const int i = threadIdx.x;
+  const int M = P.max_cnt;
+  if (i < n) {
+    const float2 cp = B.cur_pts[i];
+    B.snap_pts[slot * M + i] = cp;
+    B.snap_ids[slot * M + i] = B.ids[i];
+    B.snap_cnt[slot * M + i] = B.cnt[i];
+    B.prev_pts[i] = cp;
+  }
+  if (i == 0) {
+    int* h = B.snap_hdr + slot * 16;
+    h[0] = n;
+    h[1] = st->stat_n_prev;
+    h[2] = st->stat_after_temporal;
+    h[3] = st->stat_after_ransac;
+    h[4] = st->stat_after_mask;
+    h[5] = st->stat_new;
+    h[6] = st->stat_corner_flags;
+    h[7] = st->stat_ransac_iters;
+    h[8] = st->next_id;
+    st->n_prev = n;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // after temporal forward + backward LK (feature_tracker.cpp:419-440)
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_post_temporal(TrackParams P, TrackBuffers B) {
+// snap_slot >= 0: nothing else follows in this window's temporal stage (not a publish window),
+// so the snapshot is taken here as well
+__global__ void __launch_bounds__(1024) k_post_temporal(TrackParams P, TrackBuffers B, int snap_slot) {
   __shared__ int s_warp[33];
   TrackState* st = B.st;
   const int n = st->n_prev;
@@ -105,11 +138,15 @@ __global__ void __launch_bounds__(1024) k_post_temporal(TrackParams P, TrackBuff
     st->stat_new = 0;
     st->stat_ransac_iters = 0;
   }
+  if (snap_slot >= 0) {
+    __syncthreads();
+    snapshot_tracks(P, B, snap_slot, total);
+  }
 }
 
-void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
-                          int64_t* launches) {
-  k_post_temporal<<<1, 1024, 0, s>>>(P, B);
+void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, int snap_slot,
+                          cudaStream_t s, int64_t* launches) {
+  k_post_temporal<<<1, 1024, 0, s>>>(P, B, snap_slot);
   ++*launches;
 }
 
@@ -213,7 +250,8 @@ __device__ __forceinline__ void fill_disc_warp_atomic(uint32_t* mask, int words,
 //      masked are compacted, one warp then serves them first come, first served, and the walk
 //      stops as soon as MAX_CNT is reached (usually within the first steps).
 __global__ void __launch_bounds__(kSelThreads)
-k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict__ flags) {
+k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict__ flags,
+         int snap_slot) {
   extern __shared__ uint32_t s_mask[];
   __shared__ int s_hw[kMaxDiscR + 1];
   __shared__ int s_warp[33];
@@ -403,6 +441,10 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
     st->n_cur = kept + found;
     st->next_id += found;
   }
+  if (snap_slot >= 0) {  // the publish window's temporal stage ends here
+    __syncthreads();
+    snapshot_tracks(P, B, snap_slot, s_kept + s_found);
+  }
 }
 
 int select_configure(int W, int H) {
@@ -415,8 +457,8 @@ int select_configure(int W, int H) {
 }
 
 void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents& left,
-                   const uint8_t* flags, cudaStream_t s, int64_t* launches) {
-  k_select<<<1, kSelThreads, select_smem_bytes(P.W, P.H), s>>>(P, B, left, flags);
+                   const uint8_t* flags, int snap_slot, cudaStream_t s, int64_t* launches) {
+  k_select<<<1, kSelThreads, select_smem_bytes(P.W, P.H), s>>>(P, B, left, flags, snap_slot);
   ++*launches;
 }
 
@@ -424,41 +466,6 @@ void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents&
 // left undistort + velocity, stereo forward/backward check, right undistort + velocity,
 // result packing and the state roll (feature_tracker.cpp:470-473, 496-510, 570-574, 585-590)
 // ------------------------------------------------------------------------------------
-// End of the temporal/selection stage: freeze what the stereo stage needs and roll
-// prev_pts = cur_pts (feature_tracker.cpp:586) so the next window's temporal LK can start.
-__global__ void __launch_bounds__(1024) k_snapshot(TrackParams P, TrackBuffers B, int slot) {
-  TrackState* st = B.st;
-  const int i = threadIdx.x;
-  const int n = st->n_cur;
-  const int M = P.max_cnt;
-  if (i < n) {
-    const float2 cp = B.cur_pts[i];
-    B.snap_pts[slot * M + i] = cp;
-    B.snap_ids[slot * M + i] = B.ids[i];
-    B.snap_cnt[slot * M + i] = B.cnt[i];
-    B.prev_pts[i] = cp;
-  }
-  if (i == 0) {
-    int* h = B.snap_hdr + slot * 16;
-    h[0] = n;
-    h[1] = st->stat_n_prev;
-    h[2] = st->stat_after_temporal;
-    h[3] = st->stat_after_ransac;
-    h[4] = st->stat_after_mask;
-    h[5] = st->stat_new;
-    h[6] = st->stat_corner_flags;
-    h[7] = st->stat_ransac_iters;
-    h[8] = st->next_id;
-    st->n_prev = n;
-  }
-}
-
-void launch_snapshot(const TrackParams& P, const TrackBuffers& B, int slot, cudaStream_t s,
-                     int64_t* launches) {
-  k_snapshot<<<1, 1024, 0, s>>>(P, B, slot);
-  ++*launches;
-}
-
 __global__ void __launch_bounds__(1024)
 k_finalize(TrackParams P, TrackBuffers B, int slot, double cur_time, double prev_time) {
   __shared__ int s_warp[33];

@@ -611,3 +611,77 @@ def test_group_equals_separate_handles(fe_mod, W, H, rate, S):
     grp.close()
     for f in singles:
         f.close()
+
+
+def test_mono_config1_matches_oracle(fe_mod, ora):
+    """BASELINE configs[0]: mono DAVIS346, 100 000 events in 3 windows, right stream empty:
+    SAE + time surface + Arc* selection only (no right matches)."""
+    W, H = 346, 260
+    fe, cfg = _mk(fe_mod, W, H, use_ransac=1)
+    ot = ora.OracleTracker(cfg, use_cv2=False)
+    s = synth.StereoEventStream(W, H, 1.0e6, mono=True)
+    total = 0
+    for k in range(3):
+        L, R, t_ref = s.stereo_window(k)
+        assert len(R[0]) == 0
+        total += len(L[0])
+        g = fe.track(t_ref, L, R, True)
+        o = ot.track(t_ref, L, R, True)
+        for a, b in zip(fe.sae_planes(0), ot.sae(0).planes()):
+            assert np.array_equal(a, b)
+        assert np.array_equal(fe.time_surface(0), ot.time_surface(0))
+        assert (fe.time_surface(1) == 128).all()
+        assert len(g["id_right"]) == 0 == len(o["id_right"])
+        _assert_tracks_agree(g, o, k)
+    assert total == 99999 or total == 100000
+    fe.close()
+
+
+def test_capacity_and_state_errors(fe_mod):
+    W, H = 346, 260
+    fe, _ = _mk(fe_mod, W, H, max_events_per_window=1024)
+    s = synth.StereoEventStream(W, H, 1.0e6)
+    L, R, t_ref = s.stereo_window(0)
+    with pytest.raises(fe_mod.FrontEndError) as e:      # 33 333 events > capacity 1024
+        fe.track(t_ref, L, R, True)
+    assert e.value.status == fe_mod._capi.ECAPACITY
+    small = tuple(a[:1000] for a in L)
+    for _ in range(3):
+        fe.submit(t_ref, small, small, True)
+    with pytest.raises(fe_mod.FrontEndError) as e:      # a fourth window in flight
+        fe.submit(t_ref, small, small, True)
+    assert e.value.status == fe_mod._capi.ESTATE
+    for _ in range(3):
+        fe.wait()
+    with pytest.raises(fe_mod.FrontEndError) as e:      # nothing left to wait for
+        fe.wait()
+    assert e.value.status == fe_mod._capi.ESTATE
+    fe.close()
+
+
+def test_group_with_empty_and_ragged_windows(fe_mod):
+    """Members of a group may see empty or very different windows; each still equals its own
+    separate handle."""
+    W, H = 346, 260
+    cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=1 << 16)
+    s = [synth.StereoEventStream(W, H, 1.0e6, stream=i) for i in range(3)]
+    empty = (np.zeros(0, np.uint16), np.zeros(0, np.uint16), np.zeros(0), np.zeros(0, np.uint8))
+    singles = [fe_mod.EventFrontEnd(cfg) for _ in range(3)]
+    grp = fe_mod.EventFrontEndGroup(cfg, 3)
+    for k in range(4):
+        wins = [st.stereo_window(k) for st in s]
+        lefts = [wins[0][0], empty if k == 1 else wins[1][0], tuple(a[:777] for a in wins[2][0])]
+        rights = [wins[0][1], wins[1][1], empty]
+        times = [wins[0][2], wins[1][2], wins[2][2]]
+        got = grp.track(times, lefts, rights, [True, k % 2 == 0, False])
+        for i in range(3):
+            ref = singles[i].track(times[i], lefts[i], rights[i], [True, k % 2 == 0, False][i])
+            for key in ("id", "track_cnt", "u", "v", "id_right", "ru", "rv"):
+                assert np.array_equal(got[i][key], ref[key]), (k, i, key)
+    for i in range(3):
+        for cam in (0, 1):
+            for a, b in zip(grp.member(i).sae_planes(cam), singles[i].sae_planes(cam)):
+                assert np.array_equal(a, b)
+    grp.close()
+    for f in singles:
+        f.close()
