@@ -173,6 +173,40 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ---------------------------------------------------------------------------------
+// Programmatic dependent launch: a window is a chain of ~17 short kernels on three streams, and
+// the hand-over from one kernel to the next (drain, launch latency, first instruction) costs as
+// much as many of them run.  Every kernel of the chain releases its successor right away
+// (pdl_launch_dependents) and waits for its predecessor's completion and memory flush
+// (pdl_wait) before it touches anything, so the successor's launch overlaps the predecessor's
+// execution while the data dependencies stay exactly those of plain stream order.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#define PDL_PROLOGUE()       \
+  do {                       \
+    pdl_launch_dependents(); \
+    pdl_wait();              \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------
 // launch wrappers implemented in the .cu files
 // ---------------------------------------------------------------------------------
 struct BinLayout {

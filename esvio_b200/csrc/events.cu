@@ -276,6 +276,7 @@ __device__ __forceinline__ int bin_of(const BinLayout& L, int x, int y) {
 // counts[cam][chunk][bin]: per-chunk histogram, written coalesced
 __global__ void __launch_bounds__(kChunkThreads)
 k_bin_hist(BinLayout L, const __grid_constant__ CamBatch B, uint32_t* __restrict__ counts) {
+  PDL_PROLOGUE();
   extern __shared__ uint32_t s_hist[];
   const int cam = blockIdx.y;
   const DevEvents& ev = B.ev[cam];
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(32 * kScanPhases)
 k_bin_scan(BinLayout L, const __grid_constant__ CamBatch B, uint32_t* __restrict__ counts,
            uint32_t* __restrict__ bin_total, uint32_t* __restrict__ bin_start,
            unsigned int* __restrict__ done_ctr) {
+  PDL_PROLOGUE();
   __shared__ uint32_t s_part[kScanPhases][33];
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
@@ -404,6 +406,7 @@ k_bin_scan(BinLayout L, const __grid_constant__ CamBatch B, uint32_t* __restrict
 __global__ void __launch_bounds__(kChunkThreads)
 k_bin_scatter(BinLayout L, const __grid_constant__ CamBatch B,
               const uint32_t* __restrict__ counts, const uint32_t* __restrict__ bin_start) {
+  PDL_PROLOGUE();
   // s_base[nb]: position of this chunk's first event of each bin; s_wc[8 warps][nb]: events of
   // the bin in each warp's 256-event slice, then the slice's offset inside the chunk
   extern __shared__ uint32_t s_dyn[];
@@ -512,15 +515,15 @@ void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const Dev
     if (cb.n_chunks[c] > nc) nc = cb.n_chunks[c];
   }
   if (nc > 0) {
-    k_bin_hist<<<dim3(nc, B.n_cams), kChunkThreads, nb * sizeof(uint32_t), s>>>(L, cb, B.counts);
+    launch_pdl(k_bin_hist, dim3(nc, B.n_cams), dim3(kChunkThreads), nb * sizeof(uint32_t), s, L, cb, B.counts);
     ++*launches;
   }
-  k_bin_scan<<<dim3((nb + 31) / 32, B.n_cams), 32 * kScanPhases, 0, s>>>(L, cb, B.counts, B.bin_total,
-                                                                        B.bin_start, B.done_ctr);
+  launch_pdl(k_bin_scan, dim3((nb + 31) / 32, B.n_cams), dim3(32 * kScanPhases), 0, s, L, cb, B.counts,
+             B.bin_total, B.bin_start, B.done_ctr);
   ++*launches;
   if (nc > 0) {
-    k_bin_scatter<<<dim3(nc, B.n_cams), kChunkThreads, scatter_smem_bytes(L.n_bins), s>>>(
-        L, cb, B.counts, B.bin_start);
+    launch_pdl(k_bin_scatter, dim3(nc, B.n_cams), dim3(kChunkThreads), scatter_smem_bytes(L.n_bins), s, L, cb,
+               B.counts, B.bin_start);
     ++*launches;
   }
 }
@@ -623,6 +626,7 @@ __device__ __forceinline__ uchar4 ts_pixel4(const double2* __restrict__ px, cons
 template <int DBG>
 __global__ void __launch_bounds__(kSaeThreads)
 k_sae_update_ts(const __grid_constant__ SaeMaps maps, const __grid_constant__ SaeTsParams P) {
+  PDL_PROLOGUE();
   __shared__ __align__(128) double2 s_sae[kTilePx];
   __shared__ __align__(128) double2 s_lat[kTilePx];
   __shared__ __align__(8) uint64_t s_bar;
@@ -747,7 +751,7 @@ void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
     default: k_sae_update_ts<0><<<grid, kSaeThreads, 0, s>>>(maps, P); break;
   }
 #else
-  k_sae_update_ts<0><<<grid, kSaeThreads, 0, s>>>(maps, P);
+  launch_pdl(k_sae_update_ts<0>, grid, dim3(kSaeThreads), 0, s, maps, P);
 #endif
   ++*launches;
 }
@@ -802,6 +806,7 @@ __device__ __forceinline__ bool arc_ring_valid(const double* ring) {
 
 __global__ void __launch_bounds__(128)
 k_corner_flags(CornerParams P, DevEvents ev, uint8_t* __restrict__ flags) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ev.n) return;
   const Ev e = load_event(ev, i);
@@ -833,7 +838,7 @@ k_corner_flags(CornerParams P, DevEvents ev, uint8_t* __restrict__ flags) {
 void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* flags,
                          cudaStream_t s, int64_t* launches) {
   if (ev.n <= 0) return;
-  k_corner_flags<<<(ev.n + 127) / 128, 128, 0, s>>>(P, ev, flags);
+  launch_pdl(k_corner_flags, dim3((ev.n + 127) / 128), dim3(128), 0, s, P, ev, flags);
   ++*launches;
 }
 

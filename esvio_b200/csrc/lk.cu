@@ -321,6 +321,7 @@ k_lk(const __grid_constant__ PyrDesc pd, const uint8_t* __restrict__ I, const ui
      const float2* __restrict__ prev_pts, float2* __restrict__ next_pts,
      uint8_t* __restrict__ status, float2* __restrict__ rev_pts, uint8_t* __restrict__ rev_status,
      const int* __restrict__ n_ptr, int top, int use_init, int mode) {
+  PDL_PROLOGUE();
   __shared__ LkShared S;
   const int k = blockIdx.x;
   if (k >= *n_ptr) return;
@@ -356,8 +357,8 @@ void launch_lk(const PyrDesc& pd, const uint8_t* I, const uint8_t* J, const floa
   if (n_max <= 0) return;
   int top = pd.levels - 1;
   if (top > max_level) top = max_level;
-  k_lk<<<n_max, kLkThreads, 0, s>>>(pd, I, J, prev_pts, next_pts, status, rev_pts, rev_status,
-                                    n_ptr, top, use_initial_flow, mode);
+  launch_pdl(k_lk, dim3(n_max), dim3(kLkThreads), 0, s, pd, I, J, prev_pts, next_pts, status, rev_pts,
+             rev_status, n_ptr, top, use_initial_flow, mode);
   ++*launches;
 }
 

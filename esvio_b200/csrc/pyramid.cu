@@ -66,6 +66,7 @@ struct PyrImages {
 
 __global__ void __launch_bounds__(kPyrThreads)
 k_pyr_build(PyrDesc pd, const __grid_constant__ PyrImages imgs) {
+  PDL_PROLOGUE();
   constexpr int SP0 = kPyrN0 + 3, SP1 = kPyrN1 + 3, SP2 = kPyrN2 + 1;
   __shared__ uint8_t s0[kPyrN0 * SP0];
   __shared__ uint8_t s1[kPyrN1 * SP1];
@@ -104,7 +105,7 @@ void launch_pyramids(const PyrDesc& pd, uint8_t* const* pyr, int n_img, cudaStre
   for (int i = 0; i < kMaxCams; ++i) imgs.img[i] = i < n_img ? pyr[i] : nullptr;
   const dim3 grid((pd.w[1] + 4 * kPyrT3 - 1) / (4 * kPyrT3), (pd.h[1] + 4 * kPyrT3 - 1) / (4 * kPyrT3),
                   n_img);
-  k_pyr_build<<<grid, kPyrThreads, 0, s>>>(pd, imgs);
+  launch_pdl(k_pyr_build, grid, dim3(kPyrThreads), 0, s, pd, imgs);
   ++*launches;
 }
 

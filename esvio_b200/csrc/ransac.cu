@@ -345,6 +345,7 @@ struct PrepareArgs {
 __global__ void __launch_bounds__(1024)
 k_ransac_len(TrackBuffers B, PrepareArgs A, const uint32_t* __restrict__ draws,
              RansacScratch* __restrict__ R) {
+  PDL_PROLOGUE();
   __shared__ uint16_t s_v[1024 + kMaxLen];
   const int tid = threadIdx.x;
   const int n = A.from_tracks ? B.st->n_cur : A.n;
@@ -379,6 +380,7 @@ k_ransac_len(TrackBuffers B, PrepareArgs A, const uint32_t* __restrict__ draws,
 //     parallel, thread 0 follows those, and one thread per group of 8 fills in the rest.
 __global__ void __launch_bounds__(1024)
 k_ransac_chase(TrackParams P, TrackBuffers B, PrepareArgs A, RansacScratch* __restrict__ R) {
+  PDL_PROLOGUE();
   extern __shared__ __align__(16) unsigned char s_dyn[];
   uint16_t* s_v = reinterpret_cast<uint16_t*>(s_dyn);  // draws reduced mod n
   uint16_t* s_hop8 = s_v + kNumDraws;                  // stream offset 8 samples further on
@@ -482,6 +484,7 @@ k_ransac_chase(TrackParams P, TrackBuffers B, PrepareArgs A, RansacScratch* __re
 // k_ransac_hyp: solve and score 32 attempts per CTA
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_ransac_hyp(RansacScratch* __restrict__ R) {
+  PDL_PROLOGUE();
   __shared__ float2 s_p1[kMaxCnt], s_p2[kMaxCnt];
   __shared__ double s_F[kHyp][27];
   __shared__ int s_nm[kHyp];
@@ -558,6 +561,7 @@ struct FoldArgs {
 
 __global__ void __launch_bounds__(1024)
 k_ransac_fold(TrackParams P, TrackBuffers B, FoldArgs A, RansacScratch* __restrict__ R) {
+  PDL_PROLOGUE();
   __shared__ int s_warp[33];
   __shared__ int s_pm[kMaxAttempts];   // per attempt: best inlier count among its models, -1 none
   __shared__ int s_it[kMaxAttempts];   // iteration index (exclusive prefix count of valid)
@@ -819,14 +823,14 @@ void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
   pa.n = 0;
   pa.thresh = P.f_threshold;
   pa.min_points = 8;
-  k_ransac_len<<<kNumDraws / 1024, 1024, 0, s>>>(B, pa, B.rng_draws, R);
-  k_ransac_chase<<<1, 1024, kPrepareSmem, s>>>(P, B, pa, R);
-  k_ransac_hyp<<<kMaxAttempts / kHyp, 1024, 0, s>>>(R);
+  launch_pdl(k_ransac_len, dim3(kNumDraws / 1024), dim3(1024), 0, s, B, pa, B.rng_draws, R);
+  launch_pdl(k_ransac_chase, dim3(1), dim3(1024), kPrepareSmem, s, P, B, pa, R);
+  launch_pdl(k_ransac_hyp, dim3(kMaxAttempts / kHyp), dim3(1024), 0, s, R);
   FoldArgs fa;
   fa.to_tracks = 1;
   fa.mask = nullptr;
   fa.iters = nullptr;
-  k_ransac_fold<<<1, 1024, 0, s>>>(P, B, fa, R);
+  launch_pdl(k_ransac_fold, dim3(1), dim3(1024), 0, s, P, B, fa, R);
   *launches += 4;
 }
 
@@ -842,14 +846,14 @@ void launch_ransac_stage(const TrackParams& P, const TrackBuffers& B, const floa
   pa.thresh = thresh;
   pa.min_points = 7;
   ransac_configure();
-  k_ransac_len<<<kNumDraws / 1024, 1024, 0, s>>>(B, pa, B.rng_draws, R);
-  k_ransac_chase<<<1, 1024, kPrepareSmem, s>>>(P, B, pa, R);
-  k_ransac_hyp<<<kMaxAttempts / kHyp, 1024, 0, s>>>(R);
+  launch_pdl(k_ransac_len, dim3(kNumDraws / 1024), dim3(1024), 0, s, B, pa, B.rng_draws, R);
+  launch_pdl(k_ransac_chase, dim3(1), dim3(1024), kPrepareSmem, s, P, B, pa, R);
+  launch_pdl(k_ransac_hyp, dim3(kMaxAttempts / kHyp), dim3(1024), 0, s, R);
   FoldArgs fa;
   fa.to_tracks = 0;
   fa.mask = mask;
   fa.iters = iters;
-  k_ransac_fold<<<1, 1024, 0, s>>>(P, B, fa, R);
+  launch_pdl(k_ransac_fold, dim3(1), dim3(1024), 0, s, P, B, fa, R);
   *launches += 4;
 }
 

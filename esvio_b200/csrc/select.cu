@@ -105,6 +105,7 @@ __device__ __forceinline__ void snapshot_tracks(const TrackParams& P, const Trac
 // snap_slot >= 0: nothing else follows in this window's temporal stage (not a publish window),
 // so the snapshot is taken here as well
 __global__ void __launch_bounds__(1024) k_post_temporal(TrackParams P, TrackBuffers B, int snap_slot) {
+  PDL_PROLOGUE();
   __shared__ int s_warp[33];
   TrackState* st = B.st;
   const int n = st->n_prev;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(1024) k_post_temporal(TrackParams P, TrackBuff
 
 void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, int snap_slot,
                           cudaStream_t s, int64_t* launches) {
-  k_post_temporal<<<1, 1024, 0, s>>>(P, B, snap_slot);
+  launch_pdl(k_post_temporal, dim3(1), dim3(1024), 0, s, P, B, snap_slot);
   ++*launches;
 }
 
@@ -252,6 +253,7 @@ __device__ __forceinline__ void fill_disc_warp_atomic(uint32_t* mask, int words,
 __global__ void __launch_bounds__(kSelThreads)
 k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict__ flags,
          int snap_slot) {
+  PDL_PROLOGUE();
   extern __shared__ uint32_t s_mask[];
   __shared__ int s_hw[kMaxDiscR + 1];
   __shared__ int s_warp[33];
@@ -458,7 +460,7 @@ int select_configure(int W, int H) {
 
 void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents& left,
                    const uint8_t* flags, int snap_slot, cudaStream_t s, int64_t* launches) {
-  k_select<<<1, kSelThreads, select_smem_bytes(P.W, P.H), s>>>(P, B, left, flags, snap_slot);
+  launch_pdl(k_select, dim3(1), dim3(kSelThreads), select_smem_bytes(P.W, P.H), s, P, B, left, flags, snap_slot);
   ++*launches;
 }
 
@@ -468,6 +470,7 @@ void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents&
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 k_finalize(TrackParams P, TrackBuffers B, int slot, double cur_time, double prev_time) {
+  PDL_PROLOGUE();
   __shared__ int s_warp[33];
   TrackState* st = B.st;
   const int i = threadIdx.x;
@@ -583,7 +586,7 @@ k_finalize(TrackParams P, TrackBuffers B, int slot, double cur_time, double prev
 
 void launch_finalize(const TrackParams& P, const TrackBuffers& B, int slot, double cur_time,
                      double prev_time, cudaStream_t s, int64_t* launches) {
-  k_finalize<<<1, 1024, 0, s>>>(P, B, slot, cur_time, prev_time);
+  launch_pdl(k_finalize, dim3(1), dim3(1024), 0, s, P, B, slot, cur_time, prev_time);
   ++*launches;
 }
 

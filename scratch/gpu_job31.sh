@@ -1,0 +1,14 @@
+mkdir -p gpurun_out
+T=j31
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/${T}_pytest.log
+python scratch/stage_times.py stereo_davis346_1mevs 40 2>&1 | tee gpurun_out/${T}_stage.txt
+python scratch/stage_times.py stereo_vga_5mevs 40 2>&1 | tee -a gpurun_out/${T}_stage.txt
+timeout 400 python bench.py --steps 100 --warmup 10 --cpu-windows 20 > gpurun_out/${T}_bench_davis.json 2> gpurun_out/${T}_bench_davis.err
+timeout 400 python bench.py --steps 100 --warmup 10 --workload stereo_vga_5mevs --cpu-windows 12 --batch-streams 4 > gpurun_out/${T}_bench_vga.json 2> gpurun_out/${T}_bench_vga.err
+python -c "
+import json
+for f in ('gpurun_out/${T}_bench_davis.json','gpurun_out/${T}_bench_vga.json'):
+    try:
+        d=json.load(open(f)); print(f, d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['sync_call_ms_per_step']); b=d.get('batched'); print(' batched', b['value'], b['ms_per_step'], b['roofline']['kernel_ms'], b['roofline']['frac'])
+    except Exception as e: print(f, 'ERR', e)
+"
