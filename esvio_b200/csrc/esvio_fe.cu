@@ -62,7 +62,10 @@ struct esvio_fe {
   uint8_t* flags[kSlots];   // [slot] Arc* corner flags of the left events
   // Three pipeline stages, one stream each; `stream` (stereo stage, results) is the one
   // esvio_fe_stream() hands out.
-  cudaStream_t stream_e;   // event stage: H2D, binning, SAE/TS, pyramids, corner flags
+  cudaStream_t stream_c;   // host -> device copies of a window's events (overlap the event stage
+                           // of the window before)
+  cudaEvent_t c_done[kSlots];
+  cudaStream_t stream_e;   // event stage: binning, SAE/TS, pyramids, corner flags
   cudaStream_t stream_t1;  // temporal stage: temporal LK, F-RANSAC, selection
   cudaEvent_t e_done[kSlots];   // [slot] event stage of that window finished
   cudaEvent_t t1_done[kSlots];  // [slot] temporal stage finished
@@ -190,6 +193,7 @@ static int make_state_map(esvio_fe* fe, double2* base, CUtensorMap* map, int n_c
 static void free_all(esvio_fe* fe) {
   if (!fe) return;
   cudaSetDevice(fe->dev);
+  if (fe->stream_c) cudaStreamSynchronize(fe->stream_c);
   if (fe->stream_e) cudaStreamSynchronize(fe->stream_e);
   if (fe->stream_t1) cudaStreamSynchronize(fe->stream_t1);
   if (fe->stream) cudaStreamSynchronize(fe->stream);
@@ -205,6 +209,7 @@ static void free_all(esvio_fe* fe) {
     cudaFree(fe->raw[i][1]);
     cudaFree(fe->flags[i]);
     if (fe->e_done[i]) cudaEventDestroy(fe->e_done[i]);
+    if (fe->c_done[i]) cudaEventDestroy(fe->c_done[i]);
     if (fe->t1_done[i]) cudaEventDestroy(fe->t1_done[i]);
     if (fe->h_result[i]) cudaFreeHost(fe->h_result[i]);
     if (fe->q_done[i]) cudaEventDestroy(fe->q_done[i]);
@@ -233,6 +238,7 @@ static void free_all(esvio_fe* fe) {
   for (int k = 0; k < kSlots; ++k)
     for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 2; ++i)
       if (fe->pev[k][i]) cudaEventDestroy(fe->pev[k][i]);
+  if (fe->stream_c) cudaStreamDestroy(fe->stream_c);
   if (fe->stream_e) cudaStreamDestroy(fe->stream_e);
   if (fe->stream_t1) cudaStreamDestroy(fe->stream_t1);
   if (fe->stream) cudaStreamDestroy(fe->stream);
@@ -310,6 +316,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(cudaStreamCreateWithPriority(&fe->stream_e, cudaStreamNonBlocking, prio_hi));
   }
   CUC(cudaStreamCreateWithFlags(&fe->stream_t1, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&fe->stream_c, cudaStreamNonBlocking));
 
   fe->esb.n_cams = 2;
   BinLayout& L = fe->bl;
@@ -341,6 +348,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(cudaMalloc(&fe->raw[c][1], (size_t)fe->cap * 16));
     CUC(cudaMalloc(&fe->flags[c], (size_t)fe->cap + 16));
     CUC(cudaEventCreateWithFlags(&fe->e_done[c], cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&fe->c_done[c], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&fe->t1_done[c], cudaEventDisableTiming));
   }
   if (cfg->do_motion_correction)
@@ -459,6 +467,7 @@ FE_API void esvio_fe_destroy(esvio_fe* fe) {
 }
 
 static int sync_all(esvio_fe* fe) {
+  CU(cudaStreamSynchronize(fe->stream_c));
   CU(cudaStreamSynchronize(fe->stream_e));
   CU(cudaStreamSynchronize(fe->stream_t1));
   CU(cudaStreamSynchronize(fe->stream));
@@ -475,8 +484,7 @@ FE_API int esvio_fe_reset(esvio_fe* fe) {
 // ---------------------------------------------------------------------------------------
 // event staging
 // ---------------------------------------------------------------------------------------
-static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, DevEvents* d,
-                        cudaStream_t se = nullptr) {
+static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, DevEvents* d) {
   memset(d, 0, sizeof(*d));
   if (!e || e->n == 0) return ESVIO_FE_OK;
   if (e->n > (size_t)fe->cap) return fail(fe, ESVIO_FE_ECAPACITY, "events > max_events_per_window", cudaSuccess);
@@ -489,7 +497,7 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
     return ESVIO_FE_OK;
   }
   uint8_t* raw = fe->raw[slot][cam];
-  if (!se) se = fe->stream_e;
+  cudaStream_t se = fe->stream_c;
   const size_t n = e->n, cap = (size_t)fe->cap;
   if (e->aos) {
     CU(cudaMemcpyAsync(raw, e->aos, n * 16, cudaMemcpyHostToDevice, se));
@@ -505,6 +513,14 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
     CU(cudaMemcpyAsync(dp, e->p, n, cudaMemcpyHostToDevice, se));
     d->x = dx, d->y = dy, d->t = dt, d->p = dp;
   }
+  return ESVIO_FE_OK;
+}
+
+// the copies of a window's events were enqueued on the copy stream: `consumer` may go on once
+// they have landed
+static int staging_done(esvio_fe* fe, int slot, cudaStream_t consumer) {
+  CU(cudaEventRecord(fe->c_done[slot], fe->stream_c));
+  CU(cudaStreamWaitEvent(consumer, fe->c_done[slot], 0));
   return ESVIO_FE_OK;
 }
 
@@ -702,6 +718,7 @@ FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_e
   DevEvents ev[2];
   if ((rc = stage_events(fe, w.slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
   if ((rc = stage_events(fe, w.slot, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
+  if ((rc = staging_done(fe, w.slot, fe->stream_e)) != ESVIO_FE_OK) return rc;
   prof_mark(fe, 1);
   if ((rc = run_event_stage(fe, cur_time, ev, w.cur, w.rcur, mc)) != ESVIO_FE_OK) return rc;
   if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame)) != ESVIO_FE_OK) return rc;
@@ -925,8 +942,9 @@ FE_API int esvio_fe_group_track_submit(esvio_fe_group* g, const double* cur_time
   for (int i = 0; i < S; ++i)
     if (g->m[i]->windows > 0) CU(cudaStreamWaitEvent(se, g->m[i]->e_done[(w[i].slot + kSlots - 1) % kSlots], 0));
   for (int i = 0; i < S; ++i) {
-    if ((rc = stage_events(g->m[i], w[i].slot, 0, &left[i], &ev[2 * i], se)) != ESVIO_FE_OK) return rc;
-    if ((rc = stage_events(g->m[i], w[i].slot, 1, &right[i], &ev[2 * i + 1], se)) != ESVIO_FE_OK) return rc;
+    if ((rc = stage_events(g->m[i], w[i].slot, 0, &left[i], &ev[2 * i])) != ESVIO_FE_OK) return rc;
+    if ((rc = stage_events(g->m[i], w[i].slot, 1, &right[i], &ev[2 * i + 1])) != ESVIO_FE_OK) return rc;
+    if ((rc = staging_done(g->m[i], w[i].slot, se)) != ESVIO_FE_OK) return rc;
   }
   launch_bin_events(g->bl, g->esb, ev, se, &g->launches);
   SaeTsParams sp;
@@ -1123,6 +1141,7 @@ FE_API int esvio_fe_stage_update_mc(esvio_fe* fe, double t_ref, const esvio_even
   if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
   if ((rc = stage_events(fe, 0, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
   if ((rc = stage_events(fe, 0, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
+  if ((rc = staging_done(fe, 0, fe->stream_e)) != ESVIO_FE_OK) return rc;
   if ((rc = run_event_stage(fe, t_ref, ev, fe->cur_left, fe->cur_right, mc)) != ESVIO_FE_OK) return rc;
   CU(cudaStreamSynchronize(fe->stream_e));
   return ESVIO_FE_OK;
@@ -1137,6 +1156,7 @@ FE_API int esvio_fe_stage_corner_flags(esvio_fe* fe, const esvio_events* left, i
   int rc;
   if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
   if ((rc = stage_events(fe, 0, 0, left, &ev)) != ESVIO_FE_OK) return rc;
+  if ((rc = staging_done(fe, 0, fe->stream_e)) != ESVIO_FE_OK) return rc;
   launch_corner_flags(corner_params(fe, fe->cur_left, and_ts_test), ev, fe->flags[0],
                       fe->stream_e, &fe->launches);
   CU(cudaGetLastError());
@@ -1257,7 +1277,7 @@ FE_API int esvio_fe_stage_select(esvio_fe* fe, const esvio_events* left, int32_t
   int rc;
   if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
   if ((rc = stage_events(fe, 0, 0, left, &ev)) != ESVIO_FE_OK) return rc;
-  CU(cudaStreamSynchronize(fe->stream_e));
+  CU(cudaStreamSynchronize(fe->stream_c));
   TrackState st;
   CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));

@@ -226,7 +226,7 @@ int esvio_fe_stream(esvio_fe *fe, void **cuda_stream);
 /* ---- profiling ---- */
 #define ESVIO_FE_NUM_STAGES 9
 /* CUDA-event milliseconds of the last completed window when profiling is on:
- * 0 h2d, 1 bin_events (4 kernels), 2 sae_update_ts (1 kernel), 3 pyramid, 4 corner flags,
+ * 0 wait for the h2d copies (own stream), 1 bin_events (3 kernels), 2 sae_update_ts (1 kernel), 3 pyramid, 4 corner flags,
  * 5 temporal LK + filter, 6 select (ransac+mask+corners), 7 stereo LK + pack, 8 d2h */
 int esvio_fe_set_profiling(esvio_fe *fe, int32_t on);
 int esvio_fe_get_stage_ms(esvio_fe *fe, float *ms /* ESVIO_FE_NUM_STAGES */);
