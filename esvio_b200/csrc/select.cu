@@ -415,19 +415,31 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
       for (int k = 0; k < nc; ++k) s_cand[pos + k] = cand[k];
       __syncthreads();
       if (warp == 0) {
+        // 32 candidates at a time: the lowest lane whose pixel is still free is the next corner
+        // in stream order (everything before it is masked, and the mask only grows); its disc
+        // is filled and the remaining lanes are tested again
         int found = s_found;
-        for (int c = 0; c < total && found < want; ++c) {
-          const uint32_t xy = s_cand[c];
+        const int next_id = st->next_id;
+        for (int c0 = 0; c0 < total && found < want; c0 += 32) {
+          const bool have = c0 + lane < total;
+          const uint32_t xy = have ? s_cand[c0 + lane] : 0u;
           const int x = xy & 0xffff, y = xy >> 16;
-          if (mask_test(s_mask, words, x, y)) continue;
-          if (lane == 0) {
-            B.cur_pts[kept + found] = make_float2((float)x, (float)y);
-            B.ids[kept + found] = st->next_id + found;
-            B.cnt[kept + found] = 1;
+          uint32_t alive = __ballot_sync(0xffffffffu, have);
+          while (found < want) {
+            const bool free_px = ((alive >> lane) & 1u) && !mask_test(s_mask, words, x, y);
+            const uint32_t fr = __ballot_sync(0xffffffffu, free_px);
+            if (!fr) break;
+            const int l = __ffs(fr) - 1;
+            const int ax = __shfl_sync(0xffffffffu, x, l), ay = __shfl_sync(0xffffffffu, y, l);
+            if (lane == 0) {
+              B.cur_pts[kept + found] = make_float2((float)ax, (float)ay);
+              B.ids[kept + found] = next_id + found;
+              B.cnt[kept + found] = 1;
+            }
+            ++found;
+            alive &= ~((2u << l) - 1u);  // lanes up to l are settled
+            fill_disc_warp(s_mask, words, W, H, ax, ay, P.min_dist, s_hw);
           }
-          ++found;
-          __syncwarp();
-          fill_disc_warp(s_mask, words, W, H, x, y, P.min_dist, s_hw);
         }
         if (lane == 0) s_found = found;
       }
