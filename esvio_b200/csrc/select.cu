@@ -240,6 +240,28 @@ __device__ __forceinline__ void fill_disc_warp_atomic(uint32_t* mask, int words,
   }
 }
 
+// r <= 15: lane l owns row cy + l - r of the disc (half width my_hw, -1 = no row), which spans at
+// most 31 pixels, i.e. one or two mask words.  Executed by one full warp.
+__device__ __forceinline__ void fill_disc_rows(uint32_t* mask, int words, int W, int H, int cx,
+                                               int cy, int my_k, int my_hw) {
+  const int yy = cy + my_k;
+  if (my_hw >= 0 && yy >= 0 && yy < H) {
+    const int x0 = max(cx - my_hw, 0), x1 = min(cx + my_hw, W - 1);
+    if (x0 <= x1) {
+      uint32_t* row = mask + (size_t)yy * words;
+      const int w0 = x0 >> 5, w1 = x1 >> 5;
+      const uint32_t lo = 0xffffffffu << (x0 & 31), hi = 0xffffffffu >> (31 - (x1 & 31));
+      if (w0 == w1) {
+        row[w0] |= lo & hi;
+      } else {
+        row[w0] |= lo;
+        row[w1] |= hi;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // Event_setMask + Event_FeaturesToTrack + id assignment.
 //  (1) Event_setMask (feature_tracker.cpp:123-151): points are visited by track_cnt descending
 //      (ties keep their order); a point survives iff no surviving earlier point's filled circle
@@ -321,12 +343,6 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
         const uint32_t hit = lane < nw ? (s_conf[b][lane] & kept_w) : 0u;
         if (inside && !__any_sync(0xffffffffu, hit != 0)) {
           if (lane == (b >> 5)) kept_w |= 1u << (b & 31);
-          if (lane == 0) {
-            const int i = s_order[b];
-            B.cur_pts[kept] = s_pts[i];
-            B.ids[kept] = s_ids[i];
-            B.cnt[kept] = s_cnt[i];
-          }
           ++kept;
         }
       }
@@ -334,6 +350,15 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
       if (lane == 0) s_kept = kept;
     }
     __syncthreads();
+    if (tid < n && ((s_keptbits[tid >> 5] >> (tid & 31)) & 1u)) {
+      // survivors keep their visiting order: position = survivors before me
+      int pos = __popc(s_keptbits[tid >> 5] & ((1u << (tid & 31)) - 1u));
+      for (int w = 0; w < (tid >> 5); ++w) pos += __popc(s_keptbits[w]);
+      const int i = s_order[tid];
+      B.cur_pts[pos] = s_pts[i];
+      B.ids[pos] = s_ids[i];
+      B.cnt[pos] = s_cnt[i];
+    }
     for (int b = warp; b < n; b += kSelThreads / 32)
       if ((s_keptbits[b >> 5] >> (b & 31)) & 1u)
         fill_disc_warp_atomic(s_mask, words, W, H, s_px[b].x, s_px[b].y, P.min_dist, s_hw);
@@ -361,6 +386,7 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
   __syncthreads();
   const int kept = s_kept;
   const int want = P.max_cnt - kept;
+  uint32_t* s_new = &s_conf[0][0];  // the bit matrix is done with: accepted corners, x | y << 16
 
   // ---- Event_FeaturesToTrack: first come, first served in stream order
   if (want > 0) {
@@ -419,7 +445,9 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
         // in stream order (everything before it is masked, and the mask only grows); its disc
         // is filled and the remaining lanes are tested again
         int found = s_found;
-        const int next_id = st->next_id;
+        const int r = P.min_dist;
+        const int my_k = lane - r;
+        const int my_hw = (r <= 15 && lane <= 2 * r) ? s_hw[my_k < 0 ? -my_k : my_k] : -1;
         for (int c0 = 0; c0 < total && found < want; c0 += 32) {
           const bool have = c0 + lane < total;
           const uint32_t xy = have ? s_cand[c0 + lane] : 0u;
@@ -431,14 +459,11 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
             if (!fr) break;
             const int l = __ffs(fr) - 1;
             const int ax = __shfl_sync(0xffffffffu, x, l), ay = __shfl_sync(0xffffffffu, y, l);
-            if (lane == 0) {
-              B.cur_pts[kept + found] = make_float2((float)ax, (float)ay);
-              B.ids[kept + found] = next_id + found;
-              B.cnt[kept + found] = 1;
-            }
+            if (lane == 0) s_new[found] = (uint32_t)ax | ((uint32_t)ay << 16);
             ++found;
             alive &= ~((2u << l) - 1u);  // lanes up to l are settled
-            fill_disc_warp(s_mask, words, W, H, ax, ay, P.min_dist, s_hw);
+            if (r <= 15) fill_disc_rows(s_mask, words, W, H, ax, ay, my_k, my_hw);
+            else fill_disc_warp(s_mask, words, W, H, ax, ay, r, s_hw);
           }
         }
         if (lane == 0) s_found = found;
@@ -446,6 +471,13 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
       __syncthreads();
       if (s_found >= want) break;
     }
+  }
+  __syncthreads();
+  for (int i = tid; i < s_found; i += blockDim.x) {  // new points: ids from n_id++, track_cnt 1
+    const uint32_t xy = s_new[i];
+    B.cur_pts[kept + i] = make_float2((float)(xy & 0xffff), (float)(xy >> 16));
+    B.ids[kept + i] = st->next_id + i;
+    B.cnt[kept + i] = 1;
   }
   __syncthreads();
   if (tid == 0) {
