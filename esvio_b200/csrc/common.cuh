@@ -321,6 +321,12 @@ struct TrackBuffers {
                      //               new, corner_flags, ransac_iters, next_id
   void* rs;                   // RansacScratch (ransac.cu)
   const uint32_t* rng_draws;  // first ransac_num_draws() raw outputs of cv::RNG(-1)
+  // the 7 sample indices of every RANSAC attempt for every point count rs_cache_lo..max_cnt
+  // (they depend on the count only): [n - rs_cache_lo][1280 attempts][8] u16, and the number of
+  // attempts the draw table affords
+  const uint16_t* rs_idx_cache;
+  const int* rs_natt_cache;
+  int rs_cache_lo;
 };
 
 struct TrackParams {
@@ -344,6 +350,9 @@ void launch_ransac_stage(const TrackParams& P, const TrackBuffers& B, const floa
                          const float2* p2, int n, double thresh, uint8_t* mask, int* iters,
                          cudaStream_t s, int64_t* launches);
 size_t ransac_scratch_bytes();
+size_t ransac_cache_idx_bytes(int n_lo, int n_hi);
+int ransac_build_cache(const TrackParams& P, const TrackBuffers& B, const float2* dummy, int n_lo,
+                       int n_hi, uint16_t* cache_idx, int* cache_natt, cudaStream_t s);
 int ransac_num_draws();
 void ransac_fill_draw_table(uint32_t* host_table);
 void launch_undistort(const Pinhole& cam, const float2* uv, int n, float2* out, cudaStream_t s,

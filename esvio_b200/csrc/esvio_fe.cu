@@ -232,6 +232,8 @@ static void free_all(esvio_fe* fe) {
   cudaFree(fe->tb.result);
   cudaFree(fe->tb.rs);
   cudaFree((void*)fe->tb.rng_draws);
+  cudaFree((void*)fe->tb.rs_idx_cache);
+  cudaFree((void*)fe->tb.rs_natt_cache);
   cudaFree(fe->d_scratch_n);
   cudaFree(fe->d_scratch_p0);
   cudaFree(fe->d_scratch_st);
@@ -456,6 +458,26 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     fprintf(stderr, "esvio_fe_create: %s\n", fe->err);
     free_all(fe);
     return rc;
+  }
+  if (cfg->use_ransac && M >= 8) {
+    // the sample indices of every RANSAC attempt, for every track count this handle can see
+    uint16_t* c_idx = nullptr;
+    int* c_natt = nullptr;
+    cudaError_t ce = cudaMalloc(&c_idx, ransac_cache_idx_bytes(8, M));
+    if (ce == cudaSuccess) ce = cudaMalloc(&c_natt, sizeof(int) * (size_t)(M - 8 + 1));
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(fe->d_scratch_p0, 0, sizeof(float2) * 2 * (size_t)kMaxCnt, fe->stream);
+    fe->tb.rs_idx_cache = c_idx;
+    fe->tb.rs_natt_cache = c_natt;
+    fe->tb.rs_cache_lo = 8;
+    if (ce == cudaSuccess &&
+        ransac_build_cache(fe->tp, fe->tb, fe->d_scratch_p0, 8, M, c_idx, c_natt, fe->stream) != 0)
+      ce = cudaErrorUnknown;
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(fe->stream);
+    if (ce != cudaSuccess) {
+      fprintf(stderr, "esvio_fe_create: RANSAC sample cache: %s\n", cudaGetErrorString(ce));
+      free_all(fe);
+      return ESVIO_FE_ECUDA;
+    }
   }
   *out = fe;
   return ESVIO_FE_OK;

@@ -480,6 +480,61 @@ k_ransac_chase(TrackParams P, TrackBuffers B, PrepareArgs A, RansacScratch* __re
   if (tid == 0) R->n_attempts = s_natt;
 }
 
+// (c) The 7 indices of every attempt depend on the point count n and on nothing else: the
+//     draws of cv::RNG(-1) are a constant and getSubset only rejects duplicates.  A handle
+//     therefore runs (a) + (b) once per n when it is created (ransac_build_cache) and a window
+//     just copies the row of its n -- 20 KB -- next to lifting its points.
+__global__ void __launch_bounds__(1024)
+k_ransac_prepare_cached(TrackParams P, TrackBuffers B, PrepareArgs A,
+                        RansacScratch* __restrict__ R) {
+  PDL_PROLOGUE();
+  const int tid = threadIdx.x;
+  const int n = A.from_tracks ? B.st->n_cur : A.n;
+  if (tid == 0) {
+    R->n = n;
+    R->thresh = A.thresh <= 0 ? 3.0 : A.thresh;
+    R->confidence = 0.99;
+    R->max_iters = 1000;
+    R->n_attempts = 0;
+    R->mode = n < A.min_points ? (A.from_tracks ? kModeSkip : kModeFail)
+                               : (n == 7 ? kModeSeven : (n >= 15 ? kModeRansac : kModeLmeds));
+  }
+  if (n < A.min_points) return;
+  for (int i = tid; i < n; i += blockDim.x) {
+    if (A.from_tracks) {
+      const float2 pp = B.prev_pts[i], cp = B.cur_pts[i];
+      double x, y;
+      lift_pinhole(P.cam[0], (double)pp.x, (double)pp.y, x, y);
+      R->p1[i] = make_float2((float)(P.focal_length * x + P.W / 2.0),
+                             (float)(P.focal_length * y + P.H / 2.0));
+      lift_pinhole(P.cam[0], (double)cp.x, (double)cp.y, x, y);
+      R->p2[i] = make_float2((float)(P.focal_length * x + P.W / 2.0),
+                             (float)(P.focal_length * y + P.H / 2.0));
+    } else {
+      R->p1[i] = A.p1[i];
+      R->p2[i] = A.p2[i];
+    }
+  }
+  if (n == 7) {
+    if (tid < 8) R->idx[0][tid] = (uint16_t)(tid < 7 ? tid : 0);
+    if (tid == 0) R->n_attempts = 1;
+    return;
+  }
+  const uint4* __restrict__ src =
+      reinterpret_cast<const uint4*>(B.rs_idx_cache) + (size_t)(n - B.rs_cache_lo) * kMaxAttempts;
+  uint4* dst = reinterpret_cast<uint4*>(&R->idx[0][0]);
+  for (int a = tid; a < kMaxAttempts; a += blockDim.x) dst[a] = __ldg(src + a);
+  __syncthreads();
+  if (tid == 0) R->n_attempts = B.rs_natt_cache[n - B.rs_cache_lo];
+}
+
+__global__ void k_ransac_cache_row(const RansacScratch* __restrict__ R, uint4* __restrict__ idx_row,
+                                   int* __restrict__ natt) {
+  const uint4* src = reinterpret_cast<const uint4*>(&R->idx[0][0]);
+  for (int a = threadIdx.x; a < kMaxAttempts; a += blockDim.x) idx_row[a] = src[a];
+  if (threadIdx.x == 0) *natt = R->n_attempts;
+}
+
 // ------------------------------------------------------------------------------------------
 // k_ransac_hyp: solve and score 32 attempts per CTA
 // ------------------------------------------------------------------------------------------
@@ -823,15 +878,40 @@ void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
   pa.n = 0;
   pa.thresh = P.f_threshold;
   pa.min_points = 8;
-  launch_pdl(k_ransac_len, dim3(kNumDraws / 1024), dim3(1024), 0, s, B, pa, B.rng_draws, R);
-  launch_pdl(k_ransac_chase, dim3(1), dim3(1024), kPrepareSmem, s, P, B, pa, R);
+  launch_pdl(k_ransac_prepare_cached, dim3(1), dim3(1024), 0, s, P, B, pa, R);
   launch_pdl(k_ransac_hyp, dim3(kMaxAttempts / kHyp), dim3(1024), 0, s, R);
   FoldArgs fa;
   fa.to_tracks = 1;
   fa.mask = nullptr;
   fa.iters = nullptr;
   launch_pdl(k_ransac_fold, dim3(1), dim3(1024), 0, s, P, B, fa, R);
-  *launches += 4;
+  *launches += 3;
+}
+
+size_t ransac_cache_idx_bytes(int n_lo, int n_hi) {
+  return (size_t)(n_hi - n_lo + 1) * kMaxAttempts * 8 * sizeof(uint16_t);
+}
+
+// attempt indices of every point count n_lo..n_hi (see k_ransac_prepare_cached); `dummy` =
+// any n_hi float2 on the device
+int ransac_build_cache(const TrackParams& P, const TrackBuffers& B, const float2* dummy, int n_lo,
+                       int n_hi, uint16_t* cache_idx, int* cache_natt, cudaStream_t s) {
+  RansacScratch* R = reinterpret_cast<RansacScratch*>(B.rs);
+  ransac_configure();
+  for (int n = n_lo; n <= n_hi; ++n) {
+    PrepareArgs pa;
+    pa.from_tracks = 0;
+    pa.p1 = pa.p2 = dummy;
+    pa.n = n;
+    pa.thresh = 1.0;
+    pa.min_points = 7;
+    k_ransac_len<<<kNumDraws / 1024, 1024, 0, s>>>(B, pa, B.rng_draws, R);
+    k_ransac_chase<<<1, 1024, kPrepareSmem, s>>>(P, B, pa, R);
+    k_ransac_cache_row<<<1, 256, 0, s>>>(
+        R, reinterpret_cast<uint4*>(cache_idx) + (size_t)(n - n_lo) * kMaxAttempts,
+        cache_natt + (n - n_lo));
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 void launch_ransac_stage(const TrackParams& P, const TrackBuffers& B, const float2* p1,
