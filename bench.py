@@ -318,6 +318,7 @@ def main_ours(args):
     e2e_ms = g0.elapsed_time(g1)
     # the same windows once more through the synchronous drop-in call, for reference
     sync_ms = None
+    k1_alone = []
     if world == 1:
         fe4 = frontend.EventFrontEnd(cfg)
         n_sync = min(K, 60)
@@ -325,10 +326,12 @@ def main_ours(args):
             l, r, t = pwins[k]
             fe4.track_raw(t, l, r, k % pub_div == 0)
         torch.cuda.synchronize()
+        fe4.set_profiling(True)   # one window at a time: the kernels run without neighbours
         t0 = time.perf_counter()
         for k in range(Wm, Wm + n_sync):
             l, r, t = pwins[k]
             fe4.track_raw(t, l, r, k % pub_div == 0)
+            k1_alone.append(fe4.stage_ms()["sae_update_ts"])
         sync_ms = (time.perf_counter() - t0) * 1e3 / n_sync
         fe4.close()
     # ---------------- batched leg (N = 1): S streams of this workload in one group ----------
@@ -462,11 +465,16 @@ def main_ours(args):
                          "traffic": ncu_traffic(args.workload),
                          "algorithmic_bytes_per_launch": int(alg_bytes),
                          "kernel_ms": k1_ms, "share_of_step": k1_ms / gpu_ms if gpu_ms else None,
+                         "kernel_ms_alone": float(np.mean(k1_alone)) if k1_alone else None,
+                         "frac_alone": (alg_bytes / (float(np.mean(k1_alone)) * 1e-3) / 1e9 / peak)
+                         if k1_alone else None,
                          "peak_source": peak_src,
                          "note": "one launch covers both cameras of one window; achieved = "
                                  "algorithmic bytes (SURVEY.md 8d: 17*W*H per camera + 45 B/event) / "
                                  "CUDA-event time of the launch inside the pipelined timed region "
-                                 "(other stages share the SMs); the SAE state is L2-resident between "
+                                 "(the LK / selection kernels of two other windows share the SMs; "
+                                 "`kernel_ms_alone` / `frac_alone`: the same launch in the synchronous "
+                                 "call, nothing else on the GPU); the SAE state is L2-resident between "
                                  "windows, `traffic` is the DRAM traffic of one launch under ncu "
                                  "(caches flushed); LK stages are latency-bound and reported by time"},
             "stage_ms": stage_ms,
