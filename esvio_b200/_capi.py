@@ -102,6 +102,7 @@ SYMBOLS = {
     "esvio_fe_group_kernel_launches": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "esvio_fe_group_sae_ts_ms": (C.c_int, [_H, _pf]),
     "esvio_fe_time_surface": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_size_t]),
+    "esvio_fe_soa_layout": (None, [C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "esvio_fe_host_alloc": (C.c_void_p, [C.c_size_t]),
     "esvio_fe_host_free": (None, [C.c_void_p]),
     "esvio_fe_device_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -144,6 +144,16 @@ FE_API void esvio_fe_default_config(esvio_fe_config* c, int32_t width, int32_t h
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+FE_API void esvio_fe_soa_layout(size_t n, size_t* offsets, size_t* total_bytes) {
+  size_t o = 0;
+  const size_t w[4] = {2, 2, 8, 1};
+  for (int i = 0; i < 4; ++i) {
+    if (offsets) offsets[i] = o;
+    o = align_up(o + w[i] * n, 16);
+  }
+  if (total_bytes) *total_bytes = o;
+}
+
 static void build_pyr_desc(int W, int H, PyrDesc* pd) {
   int w = W, h = H;
   size_t off = 0;
@@ -525,15 +535,26 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
     CU(cudaMemcpyAsync(raw, e->aos, n * 16, cudaMemcpyHostToDevice, se));
     d->aos = (const uint4*)raw;
   } else {
-    uint16_t* dx = (uint16_t*)raw;
-    uint16_t* dy = (uint16_t*)(raw + 2 * cap);
-    double* dt = (double*)(raw + 4 * cap);
-    uint8_t* dp = raw + 12 * cap;
-    CU(cudaMemcpyAsync(dx, e->x, n * 2, cudaMemcpyHostToDevice, se));
-    CU(cudaMemcpyAsync(dy, e->y, n * 2, cudaMemcpyHostToDevice, se));
-    CU(cudaMemcpyAsync(dt, e->t, n * 8, cudaMemcpyHostToDevice, se));
-    CU(cudaMemcpyAsync(dp, e->p, n, cudaMemcpyHostToDevice, se));
-    d->x = dx, d->y = dy, d->t = dt, d->p = dp;
+    size_t off[4], total;
+    esvio_fe_soa_layout(n, off, &total);
+    const uint8_t* hx = (const uint8_t*)e->x;
+    if ((const uint8_t*)e->y == hx + off[1] && (const uint8_t*)e->t == hx + off[2] &&
+        (const uint8_t*)e->p == hx + off[3]) {
+      // the four arrays sit in one block laid out by esvio_fe_soa_layout: one copy
+      CU(cudaMemcpyAsync(raw, hx, total, cudaMemcpyHostToDevice, se));
+      d->x = (uint16_t*)raw, d->y = (uint16_t*)(raw + off[1]), d->t = (double*)(raw + off[2]),
+      d->p = raw + off[3];
+    } else {
+      uint16_t* dx = (uint16_t*)raw;
+      uint16_t* dy = (uint16_t*)(raw + 2 * cap);
+      double* dt = (double*)(raw + 4 * cap);
+      uint8_t* dp = raw + 12 * cap;
+      CU(cudaMemcpyAsync(dx, e->x, n * 2, cudaMemcpyHostToDevice, se));
+      CU(cudaMemcpyAsync(dy, e->y, n * 2, cudaMemcpyHostToDevice, se));
+      CU(cudaMemcpyAsync(dt, e->t, n * 8, cudaMemcpyHostToDevice, se));
+      CU(cudaMemcpyAsync(dp, e->p, n, cudaMemcpyHostToDevice, se));
+      d->x = dx, d->y = dy, d->t = dt, d->p = dp;
+    }
   }
   return ESVIO_FE_OK;
 }

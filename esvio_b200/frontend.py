@@ -118,27 +118,28 @@ class DeviceEvents:
 
 
 class PinnedEvents:
-    """SoA event arrays in pinned host memory (esvio_fe_host_alloc) viewed as numpy."""
+    """SoA event arrays in ONE block of pinned host memory (esvio_fe_host_alloc) laid out by
+    esvio_fe_soa_layout, viewed as numpy: the window crosses PCIe as a single copy."""
 
     def __init__(self, ev):
         x, y, t, p = ev[:4]
         n = len(x)
         self.n = n
         L = _capi.lib()
-        self._raw = []
-
-        def pin(a, dt):
-            a = np.ascontiguousarray(a, dt)
-            ptr = L.esvio_fe_host_alloc(max(a.nbytes, 1))
-            if not ptr:
-                raise MemoryError("esvio_fe_host_alloc failed")
-            self._raw.append(ptr)
-            buf = (C.c_uint8 * max(a.nbytes, 1)).from_address(ptr)
-            v = np.frombuffer(buf, dtype=dt, count=n)
-            v[:] = a
-            return v
-
-        self.arrays = (pin(x, np.uint16), pin(y, np.uint16), pin(t, np.float64), pin(p, np.uint8))
+        off = (C.c_size_t * 4)()
+        total = C.c_size_t()
+        L.esvio_fe_soa_layout(n, off, C.byref(total))
+        ptr = L.esvio_fe_host_alloc(max(total.value, 16))
+        if not ptr:
+            raise MemoryError("esvio_fe_host_alloc failed")
+        self._raw = [ptr]
+        self._buf = (C.c_uint8 * max(total.value, 16)).from_address(ptr)
+        views = []
+        for a, dt, o in zip((x, y, t, p), (np.uint16, np.uint16, np.float64, np.uint8), off):
+            v = np.frombuffer(self._buf, dtype=dt, count=n, offset=o)
+            v[:] = np.ascontiguousarray(a, dt)
+            views.append(v)
+        self.arrays = tuple(views)
 
     def __getitem__(self, i):
         return self.arrays[i]

@@ -210,6 +210,10 @@ int esvio_fe_group_sae_ts_ms(esvio_fe_group *g, float *ms);
 int esvio_fe_time_surface(esvio_fe *fe, int32_t cam, uint8_t *dst, size_t stride);
 
 /* ---- memory helpers ---- */
+/* Byte offsets of x, y, t, p inside ONE block that holds the four SoA arrays of n events (each
+ * array 16-byte aligned).  SoA events whose host pointers follow this layout cross PCIe as a
+ * single copy; any other placement is copied array by array. */
+void esvio_fe_soa_layout(size_t n, size_t *offsets /* 4 */, size_t *total_bytes);
 void *esvio_fe_host_alloc(size_t bytes); /* pinned host memory for event staging */
 void esvio_fe_host_free(void *p);
 int esvio_fe_device_alloc(esvio_fe *fe, size_t bytes, void **out);

@@ -685,3 +685,26 @@ def test_group_with_empty_and_ragged_windows(fe_mod):
     grp.close()
     for f in singles:
         f.close()
+
+
+def test_single_copy_soa_block_equals_separate_arrays(fe_mod):
+    """Events laid out by esvio_fe_soa_layout in one pinned block (one H2D copy) give the same
+    result as four separate arrays (four copies)."""
+    W, H = 346, 260
+    fa, _ = _mk(fe_mod, W, H, use_ransac=1)
+    fb, _ = _mk(fe_mod, W, H, use_ransac=1)
+    s = synth.StereoEventStream(W, H, 1.0e6)
+    for k in range(3):
+        L, R, t_ref = s.stereo_window(k)
+        if k == 2:
+            L = tuple(a[:12345] for a in L)        # odd length: the block's paddings matter
+        pl, pr = fe_mod.PinnedEvents(L), fe_mod.PinnedEvents(R)
+        a = fa.track(t_ref, L, R, k % 2 == 0)
+        b = fb.track(t_ref, pl, pr, k % 2 == 0)
+        for key in ("id", "u", "v", "id_right", "ru", "rv"):
+            assert np.array_equal(a[key], b[key]), (k, key)
+        for cam in (0, 1):
+            for x, y in zip(fa.sae_planes(cam), fb.sae_planes(cam)):
+                assert np.array_equal(x, y)
+        pl.free(); pr.free()
+    fa.close(); fb.close()
