@@ -93,6 +93,7 @@ SYMBOLS = {
                                            C.c_int32, C.POINTER(Motion)]),
     "esvio_fe_group_create": (C.c_int, [C.POINTER(Config), C.c_int32, C.POINTER(_H)]),
     "esvio_fe_group_destroy": (None, [_H]),
+    "esvio_fe_group_reset": (C.c_int, [_H]),
     "esvio_fe_group_member": (_H, [_H, C.c_int32]),
     "esvio_fe_group_track": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(Events), C.POINTER(Events),
                                        C.POINTER(C.c_int32), C.POINTER(Tracks)]),

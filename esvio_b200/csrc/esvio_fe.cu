@@ -508,6 +508,7 @@ static int sync_all(esvio_fe* fe) {
 
 FE_API int esvio_fe_reset(esvio_fe* fe) {
   if (!fe) return ESVIO_FE_EINVAL;
+  if (fe->group) return fail(fe, ESVIO_FE_ESTATE, "handle belongs to a group: use esvio_fe_group_reset", cudaSuccess);
   CU(cudaSetDevice(fe->dev));
   if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
   return reset_state(fe);
@@ -960,6 +961,21 @@ FE_API int esvio_fe_group_create(const esvio_fe_config* cfg, int32_t n_streams,
     g->m[i]->group = g;
   }
   *out = g;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_group_reset(esvio_fe_group* g) {
+  if (!g) return ESVIO_FE_EINVAL;
+  esvio_fe* fe = g->m[0];
+  CU(cudaSetDevice(g->dev));
+  CU(cudaStreamSynchronize(g->stream_e));
+  for (int i = 0; i < g->S; ++i) {
+    int rc = sync_all(g->m[i]);
+    if (rc == ESVIO_FE_OK) rc = reset_state(g->m[i]);  // clears the member's slice of the SAE too
+    if (rc != ESVIO_FE_OK) return rc;
+  }
+  for (int k = 0; k < kSlots; ++k) g->k1_slot_valid[k] = 0;
+  g->k1_ms_valid = 0;
   return ESVIO_FE_OK;
 }
 

@@ -409,6 +409,9 @@ class EventFrontEndGroup:
     def __del__(self):
         self.close()
 
+    def reset(self):
+        self._chk(_capi.lib().esvio_fe_group_reset(self._h), "group_reset")
+
     def member(self, i) -> EventFrontEnd:
         return _MemberView(_capi.lib().esvio_fe_group_member(self._h, int(i)), self._c)
 

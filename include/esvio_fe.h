@@ -192,6 +192,7 @@ int esvio_fe_track_submit_mc(esvio_fe *fe, double cur_time, const esvio_events *
 typedef struct esvio_fe_group esvio_fe_group;
 int esvio_fe_group_create(const esvio_fe_config *cfg, int32_t n_streams, esvio_fe_group **out);
 void esvio_fe_group_destroy(esvio_fe_group *g);
+int esvio_fe_group_reset(esvio_fe_group *g); /* esvio_fe_reset for every member */
 /* member i, for the read-only queries (esvio_fe_time_surface, esvio_fe_get_sae, ...) */
 esvio_fe *esvio_fe_group_member(esvio_fe_group *g, int32_t i);
 int esvio_fe_group_track(esvio_fe_group *g, const double *cur_time, const esvio_events *left,

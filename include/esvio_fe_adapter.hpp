@@ -135,6 +135,89 @@ class GpuFeatureTracker {
   std::vector<float> u_, v_, unx_, uny_, vx_, vy_, ru_, rv_, runx_, runy_, rvx_, rvy_;
 };
 
+// Several independent stereo streams on one GPU (esvio_fe_group_*): the event stage of all
+// streams shares its launches, results are those of separate trackers.  `tracker(i)` exposes the
+// reference's member names for stream i after trackEvents().
+class GpuFeatureTrackerGroup {
+ public:
+  struct Stream {
+    bool PUB_THIS_FRAME = true;
+    std::vector<int> ids, track_cnt, ids_right;
+    std::vector<Point2f> cur_pts, cur_un_pts, pts_velocity;
+    std::vector<Point2f> cur_right_pts, cur_un_right_pts, right_pts_velocity;
+    esvio_tracks out{};
+    std::vector<int32_t> id_, cnt_, idr_;
+    std::vector<float> f_[12];
+  };
+  GpuFeatureTrackerGroup(const esvio_fe_config& cfg, int n_streams) : streams_(n_streams) {
+    const int rc = esvio_fe_group_create(&cfg, n_streams, &g_);
+    if (rc != ESVIO_FE_OK)
+      throw std::runtime_error(std::string("esvio_fe_group_create: ") + esvio_fe_strerror(rc));
+    const size_t m = (size_t)cfg.max_cnt;
+    for (auto& s : streams_) {
+      s.id_.resize(m), s.cnt_.resize(m), s.idr_.resize(m);
+      for (auto& v : s.f_) v.resize(m);
+      esvio_tracks& o = s.out;
+      o.capacity = cfg.max_cnt;
+      o.id = s.id_.data(), o.track_cnt = s.cnt_.data(), o.id_right = s.idr_.data();
+      float** dst[12] = {&o.u, &o.v, &o.un_x, &o.un_y, &o.vx, &o.vy, &o.ru, &o.rv, &o.run_x, &o.run_y, &o.rvx, &o.rvy};
+      for (int k = 0; k < 12; ++k) *dst[k] = s.f_[k].data();
+    }
+  }
+  ~GpuFeatureTrackerGroup() { esvio_fe_group_destroy(g_); }
+  GpuFeatureTrackerGroup(const GpuFeatureTrackerGroup&) = delete;
+  GpuFeatureTrackerGroup& operator=(const GpuFeatureTrackerGroup&) = delete;
+
+  Stream& tracker(int i) { return streams_[(size_t)i]; }
+  int size() const { return (int)streams_.size(); }
+
+  // one window of every stream: cur_time[i], left[i], right[i] as for trackEvent
+  template <class EventArrayT>
+  void trackEvents(const std::vector<double>& cur_time, const std::vector<EventArrayT>& left,
+                   const std::vector<EventArrayT>& right) {
+    const size_t S = streams_.size();
+    std::vector<esvio_events> l(S), r(S);
+    std::vector<int32_t> pub(S);
+    std::vector<esvio_tracks> out(S);
+    for (size_t i = 0; i < S; ++i) {
+      l[i] = esvio_events{}, r[i] = esvio_events{};
+      l[i].aos = left[i].events.empty() ? nullptr : &left[i].events[0];
+      l[i].n = left[i].events.size();
+      r[i].aos = right[i].events.empty() ? nullptr : &right[i].events[0];
+      r[i].n = right[i].events.size();
+      pub[i] = streams_[i].PUB_THIS_FRAME ? 1 : 0;
+      out[i] = streams_[i].out;
+    }
+    const int rc = esvio_fe_group_track(g_, cur_time.data(), l.data(), r.data(), pub.data(), out.data());
+    if (rc != ESVIO_FE_OK)
+      throw std::runtime_error(std::string("esvio_fe_group_track: ") + esvio_fe_strerror(rc));
+    for (size_t i = 0; i < S; ++i) {
+      Stream& s = streams_[i];
+      s.out = out[i];
+      const int nl = s.out.n_left, nr = s.out.n_right;
+      s.ids.assign(s.id_.begin(), s.id_.begin() + nl);
+      s.track_cnt.assign(s.cnt_.begin(), s.cnt_.begin() + nl);
+      s.ids_right.assign(s.idr_.begin(), s.idr_.begin() + nr);
+      s.cur_pts.resize(nl), s.cur_un_pts.resize(nl), s.pts_velocity.resize(nl);
+      for (int k = 0; k < nl; ++k) {
+        s.cur_pts[k] = {s.f_[0][k], s.f_[1][k]};
+        s.cur_un_pts[k] = {s.f_[2][k], s.f_[3][k]};
+        s.pts_velocity[k] = {s.f_[4][k], s.f_[5][k]};
+      }
+      s.cur_right_pts.resize(nr), s.cur_un_right_pts.resize(nr), s.right_pts_velocity.resize(nr);
+      for (int k = 0; k < nr; ++k) {
+        s.cur_right_pts[k] = {s.f_[6][k], s.f_[7][k]};
+        s.cur_un_right_pts[k] = {s.f_[8][k], s.f_[9][k]};
+        s.right_pts_velocity[k] = {s.f_[10][k], s.f_[11][k]};
+      }
+    }
+  }
+
+ private:
+  esvio_fe_group* g_ = nullptr;
+  std::vector<Stream> streams_;
+};
+
 // One row of the `feature` sensor_msgs/PointCloud exactly as the node packs it
 // (stereo_event_tracker_node.cpp:268-329): points[i] = (x, y, 1); channels = {id*2+cam, u, v,
 // vx, vy}.  Left rows with track_cnt > 1 first, then right rows whose id was published left.

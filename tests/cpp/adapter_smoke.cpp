@@ -86,6 +86,27 @@ int main() {
                   trackerData.ids_right.size(), rows.size());
     }
     if (trackerData.ids.empty() || rows_total == 0) return 12;
+    // a group of two streams fed the same data must reproduce the single tracker, stream by stream
+    esvio::GpuFeatureTracker single(cfg);
+    esvio::GpuFeatureTrackerGroup group(cfg, 2);
+    for (int k = 0; k < 4; ++k) {
+      make_window(k, 0, L);
+      make_window(k, 1, R);
+      const dvs_msgs::Event& last = L.events.back();
+      const double cur_time = (double)last.ts.sec + 1e-9 * (double)last.ts.nsec;
+      single.PUB_THIS_FRAME = (k % 2 == 0);
+      single.trackEvent(cur_time, L, R);
+      group.tracker(0).PUB_THIS_FRAME = group.tracker(1).PUB_THIS_FRAME = (k % 2 == 0);
+      group.trackEvents(std::vector<double>{cur_time, cur_time}, std::vector<dvs_msgs::EventArray>{L, L},
+                        std::vector<dvs_msgs::EventArray>{R, R});
+      for (int i = 0; i < 2; ++i) {
+        const auto& t = group.tracker(i);
+        if (t.ids != single.ids || t.ids_right != single.ids_right) return 13;
+        for (size_t j = 0; j < t.cur_pts.size(); ++j)
+          if (t.cur_pts[j].x != single.cur_pts[j].x || t.cur_pts[j].y != single.cur_pts[j].y) return 14;
+      }
+    }
+    std::printf("group of 2 == single tracker\n");
     return 0;
   } catch (const std::exception& e) {
     std::printf("%s\n", e.what());
