@@ -360,4 +360,7 @@ void launch_undistort(const Pinhole& cam, const float2* uv, int n, float2* out, 
 
 size_t select_smem_bytes(int W, int H);
 
+void prefer_shared_lk();  // k_lk's shared-memory carve-out preference (lk.cu)
+void prefer_shared_events();   // the same for k_sae_update_ts (events.cu)
+
 }  // namespace esvio

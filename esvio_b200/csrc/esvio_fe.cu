@@ -459,6 +459,9 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     free_all(fe);
     return rc;
   }
+  prefer_shared_lk();
+  prefer_shared_events();
+  cudaGetLastError();
   if (select_configure(fe->W, fe->H) != 0 || bin_configure(L.n_bins) != 0) {
     fprintf(stderr, "esvio_fe_create: sensor too large for the shared-memory mask / histogram\n");
     free_all(fe);

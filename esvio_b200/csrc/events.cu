@@ -842,4 +842,10 @@ void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* fl
   ++*launches;
 }
 
+// see prefer_shared_lk (lk.cu): kernels that are to share an SM have to ask for the same
+// shared-memory carve-out
+void prefer_shared_events() {
+  cudaFuncSetAttribute(k_sae_update_ts<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+}
+
 }  // namespace esvio

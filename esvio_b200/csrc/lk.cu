@@ -377,4 +377,16 @@ void launch_lk(const PyrDesc& pd, const uint8_t* I, const uint8_t* J, const floa
   ++*launches;
 }
 
+// Up to three windows run concurrently on three streams, and the LK kernels sit on every SM for
+// most of a step.  Kernels that are to share an SM have to ask for the same L1/shared-memory
+// carve-out: with the driver's per-kernel defaults (small for k_lk, large for the many small
+// CTAs of k_sae_update_ts) the SAE kernel of the next window gets one CTA per SM next to two LK
+// kernels and takes twice as long (measured at 346x260: 23 us instead of 12 us; MaxShared on
+// both fixes that too but starves the gather-heavy kernels on those SMs of L1: -5..9 %
+// throughput at 640x480).  Both ask for half of the array: room for 2-3 LK CTAs plus 6 SAE
+// CTAs per SM, 114 KB of L1 left.
+void prefer_shared_lk() {
+  cudaFuncSetAttribute(k_lk, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+}
+
 }  // namespace esvio
