@@ -190,6 +190,147 @@ class _CudaArray:
                                          "data": (ptr, False), "version": 3, "strides": None}
 
 
+def init_nccl(local, p2p_peer=None):
+    """NCCL prints its version banner to stdout when the first communicator comes up; stdout
+    must carry exactly one JSON line, so fd 1 points at stderr until that has happened."""
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        warm = torch.zeros(1, device=torch.device("cuda", local))
+        dist.all_reduce(warm)
+        if p2p_peer is not None:        # the send/recv communicator comes up lazily as well
+            if dist.get_rank() < p2p_peer:
+                dist.recv(warm, src=p2p_peer)
+            else:
+                dist.send(warm, dst=p2p_peer)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
+
+
+def main_split(args):
+    """--split-lr, 2 ranks: ONE stereo stream with the right camera's SAE / time surface /
+    pyramid on rank 1 and everything else on rank 0 (SURVEY.md 8e row 2, 8d config 3 "then 2
+    GPUs with L/R split"); the right image block crosses NVLink once per window (NCCL
+    send/recv).  Strong scaling of one stream; rank 0 also runs the same windows on one handle
+    and reports that throughput and whether the results are identical."""
+    import torch
+    import torch.distributed as dist
+    from esvio_b200 import frontend
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != 2:
+        raise SystemExit("bench.py --split-lr needs exactly 2 ranks (torchrun --nproc-per-node 2)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the front-end has no CPU fallback")
+    torch.cuda.set_device(local)
+    init_nccl(local, p2p_peer=1 - rank)
+    dev = torch.device("cuda", local)
+    w, cfg, pub_div = workload_cfg(args.workload)
+    n_per_cam = int(round(w["rate"] / synth.WINDOWS_PER_SEC))
+    cfg = dict(cfg, device_id=local, max_events_per_window=max(n_per_cam + 64, 1024))
+    K, Wm = args.steps, args.warmup
+    wins = gen_windows(w, 0, K + Wm)                 # both ranks see the same stereo stream
+    fe = frontend.EventFrontEnd(cfg)
+    sp = shard.LeftRightSplit(fe, rank)
+    mine = [frontend._Ev(frontend.DeviceEvents(fe, (L, R)[rank])) for L, R, _ in wins]
+    n_ev_local = float(sum(len((L, R)[rank][0]) for L, R, _ in wins[Wm:]))
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    DEPTH = 3
+
+    def run(k0, n, sink):
+        waited = 0
+        for k in range(k0, k0 + n):
+            sp.step(wins[k][2], mine[k], k % pub_div == 0)
+            if rank == shard.LEFT_RANK and k - k0 >= DEPTH - 1:
+                sink.append(sp.wait(unpack=False))
+                waited += 1
+        while rank == shard.LEFT_RANK and waited < n:
+            sink.append(sp.wait(unpack=False))
+            waited += 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    counts = []
+    run(0, Wm, counts)
+    flush.fill_(1)
+    cur = torch.cuda.current_stream()
+    tstream = torch.cuda.ExternalStream(fe.stream(), device=dev) if rank == shard.LEFT_RANK else cur
+    barrier()
+    launches0 = fe.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(tstream)
+    run(Wm, K, counts)
+    e1.record(tstream)
+    barrier()
+    launches = fe.kernel_launches() - launches0
+    value, ms = shard.aggregate_throughput(n_ev_local, e0.elapsed_time(e1))
+    nl = torch.tensor([launches], dtype=torch.int64, device=dev)
+    dist.all_reduce(nl)
+    img_bytes = fe.split_right_buffer()[1] if rank == shard.LEFT_RANK else 0
+
+    one = None
+    if rank == shard.LEFT_RANK:       # the same windows on one handle, same pipelining
+        fe1 = frontend.EventFrontEnd(cfg)
+        dw = [(frontend._Ev(frontend.DeviceEvents(fe1, L)), frontend._Ev(frontend.DeviceEvents(fe1, R)), t)
+              for L, R, t in wins]
+        ext1 = torch.cuda.ExternalStream(fe1.stream(), device=dev)
+        ref_counts = []
+
+        def run1(k0, n):
+            waited = 0
+            for k in range(k0, k0 + n):
+                fe1.submit(dw[k][2], dw[k][0], dw[k][1], k % pub_div == 0)
+                if k - k0 >= DEPTH - 1:
+                    ref_counts.append(fe1.wait(unpack=False))
+                    waited += 1
+            while waited < n:
+                ref_counts.append(fe1.wait(unpack=False))
+                waited += 1
+
+        run1(0, Wm)
+        flush.fill_(2)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(ext1)
+        run1(Wm, K)
+        f1.record(ext1)
+        torch.cuda.synchronize()
+        ms1 = f0.elapsed_time(f1)
+        n_ev = float(sum(len(L[0]) + len(R[0]) for L, R, _ in wins[Wm:]))
+        # last window in full, every window by its feature counts
+        a, b = fe._unpack(), fe1._unpack()
+        same = ref_counts == counts and all(np.array_equal(a[k], b[k]) for k in a if k != "stats")
+        one = {"value": n_ev / (ms1 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms1 / K,
+               "identical_results": bool(same)}
+        fe1.close()
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 2, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64 SAE / u8 time surface / f32 LK", "data": "synthetic",
+            "config": {"workload": args.workload, "parallelism": "lr_split: rank 0 left camera + "
+                       "tracking, rank 1 right camera SAE/time surface/pyramid",
+                       "inputs": "resident in HBM on the rank that consumes them",
+                       "windows_in_flight": DEPTH},
+            "exchange": {"what": "right pyramid block, NCCL send/recv per window",
+                         "bytes_per_step": int(img_bytes)},
+            "gpu_launches": int(nl.item()), "one_gpu_same_run": one}))
+    fe.close()
+    dist.destroy_process_group()
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -202,21 +343,7 @@ def main_ours(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner to stdout when the first communicator comes up; stdout
-        # must carry exactly one JSON line, so fd 1 points at stderr until that has happened
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            warm = torch.zeros(1, device=torch.device("cuda", local))
-            dist.all_reduce(warm)
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+        init_nccl(local)
     dev = torch.device("cuda", local)
 
     w, cfg, pub_div = workload_cfg(args.workload)
@@ -542,10 +669,14 @@ def main():
     ap.add_argument("--batch-streams", type=int, default=8,
                     help="streams of the extra batched leg at N=1 (esvio_fe_group); 1 disables it")
     ap.add_argument("--batch-steps", type=int, default=60)
+    ap.add_argument("--split-lr", action="store_true",
+                    help="2 ranks: one stereo stream split by camera (SURVEY.md 8e row 2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         main_reference(args)
+    elif args.split_lr:
+        main_split(args)
     else:
         main_ours(args)
 

@@ -65,6 +65,7 @@ struct esvio_fe {
   cudaStream_t stream_c;   // host -> device copies of a window's events (overlap the event stage
                            // of the window before)
   cudaEvent_t c_done[kSlots];
+  cudaEvent_t x_ready[kSlots];  // left/right split: marks on the caller's exchange stream
   cudaStream_t stream_e;   // event stage: binning, SAE/TS, pyramids, corner flags
   cudaStream_t stream_t1;  // temporal stage: temporal LK, F-RANSAC, selection
   cudaEvent_t e_done[kSlots];   // [slot] event stage of that window finished
@@ -220,6 +221,7 @@ static void free_all(esvio_fe* fe) {
     cudaFree(fe->flags[i]);
     if (fe->e_done[i]) cudaEventDestroy(fe->e_done[i]);
     if (fe->c_done[i]) cudaEventDestroy(fe->c_done[i]);
+    if (fe->x_ready[i]) cudaEventDestroy(fe->x_ready[i]);
     if (fe->t1_done[i]) cudaEventDestroy(fe->t1_done[i]);
     if (fe->h_result[i]) cudaFreeHost(fe->h_result[i]);
     if (fe->q_done[i]) cudaEventDestroy(fe->q_done[i]);
@@ -361,6 +363,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(cudaMalloc(&fe->flags[c], (size_t)fe->cap + 16));
     CUC(cudaEventCreateWithFlags(&fe->e_done[c], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&fe->c_done[c], cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&fe->x_ready[c], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&fe->t1_done[c], cudaEventDisableTiming));
   }
   if (cfg->do_motion_correction)
@@ -604,22 +607,26 @@ static bool mc_active(const esvio_motion* mc) {
   return sqrt(a0 * a0 + a1 * a1 + a2 * a2) > 5.0;
 }
 
+// n_cams = 1 (left/right split over two GPUs): only camera 0 of this handle -- ev_in[0], state
+// plane 0, image `left_idx` -- is processed.
 static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev_in[2], int left_idx,
-                           int right_idx, const esvio_motion* mc = nullptr) {
+                           int right_idx, const esvio_motion* mc = nullptr, int n_cams = 2) {
   cudaStream_t se = fe->stream_e;
-  DevEvents ev[2] = {ev_in[0], ev_in[1]};
-  if (mc && mc_active(mc) && ev[0].n > 0) {
+  DevEvents ev[2] = {ev_in[0], n_cams == 2 ? ev_in[1] : DevEvents{}};
+  if (mc && n_cams == 2 && mc_active(mc) && ev[0].n > 0) {
     launch_warp_events(mc_params(fe, mc), ev_in, fe->warp_xy[0], fe->warp_xy[1], se, &fe->launches);
     for (int c = 0; c < 2; ++c) ev[c].wx = fe->warp_xy[0][c], ev[c].wy = fe->warp_xy[1][c];
   }
-  launch_bin_events(fe->bl, fe->esb, ev, se, &fe->launches);
+  EventStageBuffers esb = fe->esb;
+  esb.n_cams = n_cams;
+  launch_bin_events(fe->bl, esb, ev, se, &fe->launches);
   prof_mark(fe, 2);
   SaeTsParams sp;
   sp.W = fe->W;
   sp.H = fe->H;
   sp.tiles_x = fe->bl.tiles_x;
   sp.n_tiles = fe->bl.n_tiles;
-  sp.n_cams = 2;
+  sp.n_cams = n_cams;
   for (int c = 0; c < kMaxCams; ++c) {
     sp.t_ref[c] = t_ref;
     sp.bt[c] = nullptr, sp.bk[c] = nullptr, sp.ts[c] = nullptr;
@@ -645,17 +652,17 @@ static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev_in[2],
   launch_sae_update_ts(sp, fe->map_sae, fe->map_lat, se, &fe->launches);
   if (med) {
     const uint8_t* src[2] = {a_out[0], a_out[1]};
-    launch_median(src, b_out, 2, fe->W, fe->H, fe->pd.pitch[0], 2 * med + 1, se, &fe->launches);
+    launch_median(src, b_out, n_cams, fe->W, fe->H, fe->pd.pitch[0], 2 * med + 1, se, &fe->launches);
   }
   fe->ts_sel[0] = b_out[0];
-  fe->ts_sel[1] = b_out[1];
+  if (n_cams == 2) fe->ts_sel[1] = b_out[1];
   if (eq) {
     const uint8_t* src[2] = {b_out[0], b_out[1]};
-    launch_equalize(src, fe->aux[2], imgs, 2, fe->W, fe->H, fe->pd.pitch[0], fe->clahe_lut,
+    launch_equalize(src, fe->aux[2], imgs, n_cams, fe->W, fe->H, fe->pd.pitch[0], fe->clahe_lut,
                     fe->clahe_minmax, se, &fe->launches);
   }
   prof_mark(fe, 3);
-  launch_pyramids(fe->pd, imgs, 2, se, &fe->launches);
+  launch_pyramids(fe->pd, imgs, n_cams, se, &fe->launches);
   CU(cudaGetLastError());
   return ESVIO_FE_OK;
 }
@@ -829,6 +836,90 @@ FE_API int esvio_fe_track_mc(esvio_fe* fe, double cur_time, const esvio_events* 
   const int rc = esvio_fe_track_submit_mc(fe, cur_time, left, right, pub_this_frame, mc);
   if (rc != ESVIO_FE_OK) return rc;
   return esvio_fe_track_wait(fe, out);
+}
+
+// ---------------------------------------------------------------------------------------
+// left/right split over two GPUs
+// ---------------------------------------------------------------------------------------
+// The right camera only feeds its pyramid to the stereo LK (feature_tracker.cpp:475-495), so
+// it can live on another GPU: that GPU runs createSAE_right / SAEtoTimeSurface_right and the
+// pyramid (esvio_fe_split_image_submit), the caller moves the image block (NCCL send/recv or a
+// peer copy on a stream of its own) into the buffer esvio_fe_split_right_buffer names, and the
+// left GPU tracks with it (esvio_fe_track_submit_split).  Ordering against the caller's
+// exchange stream is by events recorded on / waited for by that stream, never by host syncs
+// (exchange_stream is a cudaStream_t; 0 = the legacy default stream, which is what
+// torch.cuda.current_stream().cuda_stream is unless the caller switched streams).
+static int split_ok(esvio_fe* fe) {
+  if (fe->group) return fail(fe, ESVIO_FE_ESTATE, "handle belongs to a group", cudaSuccess);
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_split_image_submit(esvio_fe* fe, double cur_time, const esvio_events* ev,
+                                       void* exchange_stream, void** image, size_t* bytes) {
+  if (!fe || !image || !bytes) return ESVIO_FE_EINVAL;
+  int rc;
+  if ((rc = split_ok(fe)) != ESVIO_FE_OK) return rc;
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "split image while windows are in flight", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  cudaStream_t xs = (cudaStream_t)exchange_stream;
+  const int slot = fe->windows % kSlots;
+  const int idx = fe->windows == 0 ? kRightBase : kRightBase + (fe->cur_right - kRightBase + 1) % kRightBufs;
+  // the staging buffer of this slot was last read by the event stage three windows ago
+  CU(cudaStreamWaitEvent(fe->stream_c, fe->e_done[slot], 0));
+  // sends of earlier windows enqueued on the exchange stream have read the image buffers
+  CU(cudaEventRecord(fe->x_ready[slot], xs));
+  CU(cudaStreamWaitEvent(fe->stream_e, fe->x_ready[slot], 0));
+  DevEvents d[2];
+  memset(d, 0, sizeof(d));
+  if ((rc = stage_events(fe, slot, 0, ev, &d[0])) != ESVIO_FE_OK) return rc;
+  if ((rc = staging_done(fe, slot, fe->stream_e)) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, cur_time, d, idx, idx, nullptr, 1)) != ESVIO_FE_OK) return rc;
+  CU(cudaEventRecord(fe->e_done[slot], fe->stream_e));
+  CU(cudaStreamWaitEvent(xs, fe->e_done[slot], 0));
+  fe->cur_right = idx;
+  fe->windows++;
+  fe->prev_time = cur_time;
+  *image = fe->pyr[idx];
+  *bytes = fe->pd.bytes;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_split_right_buffer(esvio_fe* fe, void** image, size_t* bytes) {
+  if (!fe || !image || !bytes) return ESVIO_FE_EINVAL;
+  int rc;
+  if ((rc = split_ok(fe)) != ESVIO_FE_OK) return rc;
+  WindowPlan w;
+  // with fewer than three windows in flight the stereo LK that last read this buffer (three
+  // windows ago) has been waited for
+  if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
+  *image = fe->pyr[w.rcur];
+  *bytes = fe->pd.bytes;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_track_submit_split(esvio_fe* fe, double cur_time, const esvio_events* left,
+                                       int32_t pub_this_frame, void* exchange_stream) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  int rc;
+  if ((rc = split_ok(fe)) != ESVIO_FE_OK) return rc;
+  CU(cudaSetDevice(fe->dev));
+  WindowPlan w;
+  if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
+  fe->pev_slot = w.slot;
+  prof_mark(fe, 0);
+  DevEvents ev[2];
+  memset(ev, 0, sizeof(ev));
+  if ((rc = stage_events(fe, w.slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
+  if ((rc = staging_done(fe, w.slot, fe->stream_e)) != ESVIO_FE_OK) return rc;
+  prof_mark(fe, 1);
+  if ((rc = run_event_stage(fe, cur_time, ev, w.cur, w.rcur, nullptr, 1)) != ESVIO_FE_OK) return rc;
+  // the stereo stage reads the right image the caller wrote on its exchange stream
+  cudaStream_t xs = (cudaStream_t)exchange_stream;
+  CU(cudaEventRecord(fe->x_ready[w.slot], xs));
+  CU(cudaStreamWaitEvent(fe->stream, fe->x_ready[w.slot], 0));
+  if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame)) != ESVIO_FE_OK) return rc;
+  fe->pev_valid[w.slot] = fe->profiling;
+  return ESVIO_FE_OK;
 }
 
 FE_API int esvio_fe_time_surface(esvio_fe* fe, int32_t cam, uint8_t* dst, size_t stride) {

@@ -225,6 +225,34 @@ class EventFrontEnd:
         self._inflight.pop(0)
         return self._unpack() if unpack else (self._t.n_left, self._t.n_right)
 
+    # ---- left/right split over two GPUs (include/esvio_fe.h "Left/right split")
+    def split_image_submit(self, cur_time, events, exchange_stream=0):
+        """Right GPU: SAE update + time surface + pyramid of this handle's one camera; returns
+        (device pointer, bytes) of the image block, ready on `exchange_stream` (cudaStream_t)."""
+        e = events if isinstance(events, _Ev) else _Ev(events)
+        self._split_keep = getattr(self, "_split_keep", [])[-2:] + [e]   # host buffers of 3 windows
+        p, n = C.c_void_p(), C.c_size_t()
+        self._chk(_capi.lib().esvio_fe_split_image_submit(self._h, float(cur_time), C.byref(e.s),
+                                                          C.c_void_p(exchange_stream), C.byref(p),
+                                                          C.byref(n)), "split_image_submit")
+        return p.value, n.value
+
+    def split_right_buffer(self):
+        """Left GPU: (device pointer, bytes) the next window's right image must be written to."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._chk(_capi.lib().esvio_fe_split_right_buffer(self._h, C.byref(p), C.byref(n)),
+                  "split_right_buffer")
+        return p.value, n.value
+
+    def submit_split(self, cur_time, left, pub_this_frame=True, exchange_stream=0):
+        """Left GPU: track_submit with the right image taken from split_right_buffer()."""
+        l = left if isinstance(left, _Ev) else _Ev(left)
+        self._inflight.append((l, None))
+        self._chk(_capi.lib().esvio_fe_track_submit_split(self._h, float(cur_time), C.byref(l.s),
+                                                          int(bool(pub_this_frame)),
+                                                          C.c_void_p(exchange_stream)),
+                  "track_submit_split")
+
     def reset(self):
         self._chk(_capi.lib().esvio_fe_reset(self._h), "reset")
 

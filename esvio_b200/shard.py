@@ -86,3 +86,76 @@ def aggregate_throughput(events_local: float, ms_local: float):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(e, op=dist.ReduceOp.SUM)
     return float(e.item()) / (float(t.item()) * 1e-3) / 1e6, float(t.item())
+
+
+# ---------------------------------------------------------------------------------------
+# left/right split of ONE stereo stream over two ranks
+# ---------------------------------------------------------------------------------------
+LEFT_RANK, RIGHT_RANK = 0, 1
+
+
+class _DeviceBytes:
+    """A raw device pointer seen as a uint8 vector through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                         "data": (int(ptr), False), "version": 3}
+
+
+def device_bytes(ptr: int, nbytes: int):
+    """torch uint8 tensor aliasing `nbytes` of device memory at `ptr` (no copy)."""
+    import torch
+    return torch.as_tensor(_DeviceBytes(ptr, nbytes), device="cuda")
+
+
+def exchange_right_image(rank: int, image, group=None):
+    """The one data-path exchange of the split: the right rank sends its image block (all
+    pyramid levels of the right time surface), the left rank receives it in place.  `image` is
+    a uint8 tensor (device for NCCL, CPU for gloo); runs on the caller's current stream."""
+    import torch.distributed as dist
+    if rank == RIGHT_RANK:
+        dist.send(image, dst=LEFT_RANK, group=group)
+    elif rank == LEFT_RANK:
+        dist.recv(image, src=RIGHT_RANK, group=group)
+    else:
+        raise ValueError("the left/right split uses ranks 0 (left) and 1 (right)")
+    return image
+
+
+class LeftRightSplit:
+    """One stereo stream on two GPUs: rank 1 owns the right camera's SAE / time surface /
+    pyramid, rank 0 everything else (the right camera has no detector and no temporal tracker
+    in the reference, feature_tracker.cpp:475-575, so rank 1 is lightly loaded by construction).
+    `fe` is this rank's EventFrontEnd; per window call `step(cur_time, events, pub)` with the
+    left events on rank 0 and the right events on rank 1, then `wait()` on rank 0."""
+
+    def __init__(self, fe, rank: int, exchange_stream=None, view=device_bytes):
+        if rank not in (LEFT_RANK, RIGHT_RANK):
+            raise ValueError("the left/right split uses ranks 0 (left) and 1 (right)")
+        self.fe, self.rank = fe, rank
+        if exchange_stream is None:
+            import torch
+            exchange_stream = torch.cuda.current_stream().cuda_stream
+        self._stream = exchange_stream
+        self._make_view = view        # (pointer, bytes) -> uint8 tensor; the tests use CPU tensors
+        self._views = {}
+
+    def _view(self, ptr, nbytes):
+        v = self._views.get(ptr)
+        if v is None:
+            v = self._views[ptr] = self._make_view(ptr, nbytes)
+        return v
+
+    def step(self, cur_time, events, pub_this_frame=True):
+        if self.rank == RIGHT_RANK:
+            ptr, n = self.fe.split_image_submit(cur_time, events, self._stream)
+            exchange_right_image(self.rank, self._view(ptr, n))
+        else:
+            ptr, n = self.fe.split_right_buffer()
+            exchange_right_image(self.rank, self._view(ptr, n))
+            self.fe.submit_split(cur_time, events, pub_this_frame, self._stream)
+
+    def wait(self, unpack=True):
+        if self.rank != LEFT_RANK:
+            return None
+        return self.fe.wait(unpack)

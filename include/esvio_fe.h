@@ -228,6 +228,26 @@ int esvio_fe_copy_to_device(esvio_fe *fe, void *dst, const void *src, size_t byt
 int esvio_fe_result_device_ptr(esvio_fe *fe, void **ptr, size_t *bytes);
 int esvio_fe_stream(esvio_fe *fe, void **cuda_stream);
 
+/* Left/right split of ONE stereo stream over two GPUs.  The right camera
+ * only feeds its pyramid to the stereo LK (feature_tracker.cpp:475-495), so its createSAE_right /
+ * SAEtoTimeSurface_right / pyramid (feature_tracker.cpp:358-368) can run on a second GPU:
+ *   right GPU:  esvio_fe_split_image_submit(fe_r, t, &right_events, xs, &img, &n)
+ *               then send the n bytes at img (NCCL send / peer copy) on stream xs
+ *   left GPU:   esvio_fe_split_right_buffer(fe_l, &buf, &n); receive into buf on stream xs;
+ *               esvio_fe_track_submit_split(fe_l, t, &left_events, pub, xs); esvio_fe_track_wait
+ * `exchange_stream` is the cudaStream_t (0 = legacy default stream) the caller moves the image
+ * on: the library orders its own streams against it with CUDA events, no host synchronisation.
+ * The image block holds all pyramid levels (level 0 = the CV_8U time surface, row pitch
+ * 32-byte aligned); both handles must have the same width/height.  The right handle keeps the
+ * camera in its plane 0 (esvio_fe_get_sae(fe_r, 0, ...)); its cam[0] calibration is unused
+ * (undistortion of the right points happens on the left GPU with cam[1]).  Results are
+ * identical to esvio_fe_track on one GPU.  Motion compensation is not available in a split. */
+int esvio_fe_split_image_submit(esvio_fe *fe, double cur_time, const esvio_events *events,
+                                void *exchange_stream, void **image, size_t *bytes);
+int esvio_fe_split_right_buffer(esvio_fe *fe, void **image, size_t *bytes);
+int esvio_fe_track_submit_split(esvio_fe *fe, double cur_time, const esvio_events *left,
+                                int32_t pub_this_frame, void *exchange_stream);
+
 /* ---- profiling ---- */
 #define ESVIO_FE_NUM_STAGES 9
 /* CUDA-event milliseconds of the last completed window when profiling is on:

@@ -708,3 +708,56 @@ def test_single_copy_soa_block_equals_separate_arrays(fe_mod):
                 assert np.array_equal(x, y)
         pl.free(); pr.free()
     fa.close(); fb.close()
+
+
+@pytest.mark.parametrize("W,H,rate,depth", [(346, 260, 1.0e6, 1), (640, 480, 5.0e6, 3)])
+def test_left_right_split_equals_one_handle(fe_mod, W, H, rate, depth):
+    """SURVEY.md 8e row 2 through the C ABI: the right camera's SAE / time surface / pyramid on
+    one handle (the 'right GPU'), the image block moved on the caller's stream, tracking on the
+    other handle -- bit-identical to esvio_fe_track on one handle.  Both handles live on this
+    one GPU here and the exchange is a device copy on torch's current stream; across two GPUs
+    the same calls bracket an NCCL send/recv (esvio_b200/shard.py LeftRightSplit)."""
+    import torch
+    from esvio_b200 import shard
+    cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=1 << 19)
+    ref, left, right = (fe_mod.EventFrontEnd(cfg) for _ in range(3))
+    s = synth.StereoEventStream(W, H, rate)
+    n_win = 7
+    wins = [s.stereo_window(k) for k in range(n_win)]
+    expect = [ref.track(t, L, R, k % 2 == 0) for k, (L, R, t) in enumerate(wins)]
+    xs = torch.cuda.current_stream().cuda_stream
+    got = []
+
+    def submit(k):
+        L, R, t = wins[k]
+        src, n = right.split_image_submit(t, R, xs)
+        dst, m = left.split_right_buffer()
+        assert n == m
+        shard.device_bytes(dst, m).copy_(shard.device_bytes(src, n))   # the "exchange"
+        left.submit_split(t, L, k % 2 == 0, xs)
+
+    for k in range(n_win):
+        submit(k)
+        if k >= depth - 1:
+            got.append(left.wait())
+    while len(got) < n_win:
+        got.append(left.wait())
+    for k, (x, y) in enumerate(zip(expect, got)):
+        for key in ("id", "track_cnt", "u", "v", "un_x", "un_y", "vx", "vy",
+                    "id_right", "ru", "rv", "run_x", "run_y", "rvx", "rvy"):
+            assert np.array_equal(x[key], y[key]), (k, key)
+    assert sum(len(x["id_right"]) for x in expect) > 0
+    for a, b in zip(ref.sae_planes(1), right.sae_planes(0)):
+        assert np.array_equal(a, b)
+    for a, b in zip(ref.sae_planes(0), left.sae_planes(0)):
+        assert np.array_equal(a, b)
+    assert np.array_equal(ref.time_surface(0), left.time_surface(0))
+    # a 4th window in flight is refused before anything is written
+    for k in range(3):
+        submit(k)
+    with pytest.raises(fe_mod.FrontEndError):
+        left.split_right_buffer()
+    for _ in range(3):
+        left.wait()
+    for f in (ref, left, right):
+        f.close()

@@ -142,3 +142,76 @@ def test_all_gather_tracks_gloo_world2():
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True]
     assert res[0][2] == [0, 2] and res[1][2] == [1, 3]
+
+
+class _FakeSplitFrontEnd:
+    """Stands in for EventFrontEnd in the split protocol test: 'images' are rows of a CPU
+    tensor pool addressed by fake pointers, rotating over three buffers like the library."""
+
+    def __init__(self, nbytes):
+        import torch
+        self.pool = torch.zeros((3, nbytes), dtype=torch.uint8)
+        self.k = 0
+        self.log = []
+
+    def view(self, ptr, nbytes):
+        return self.pool[ptr - 100][:nbytes]
+
+    def split_image_submit(self, cur_time, events, stream):
+        i = self.k % 3
+        self.pool[i] = int(events) % 251          # the "image" of this window
+        self.k += 1
+        self.log.append(("image", cur_time))
+        return 100 + i, self.pool.shape[1]
+
+    def split_right_buffer(self):
+        return 100 + self.k % 3, self.pool.shape[1]
+
+    def submit_split(self, cur_time, left, pub, stream):
+        self.log.append(("submit", cur_time, int(self.pool[self.k % 3][0]), int(self.pool[self.k % 3][-1]), pub))
+        self.k += 1
+
+    def wait(self, unpack=True):
+        self.log.append(("wait",))
+        return {"id": np.arange(3)}
+
+
+def _split_worker(rank, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    try:
+        fe = _FakeSplitFrontEnd(4096)
+        sp = shard.LeftRightSplit(fe, rank, exchange_stream=0, view=fe.view)
+        outs = []
+        for k in range(5):
+            sp.step(1.0 + k, 7 * k + 3, k % 2 == 0)     # "events" = a number that seeds the image
+            outs.append(sp.wait())
+        q.put((rank, fe.log, [o is not None for o in outs]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_left_right_split_protocol_gloo_world2():
+    """SURVEY.md 8e row 2, host side: rank 1 produces the right image and sends it, rank 0
+    receives it into the buffer the library names BEFORE it submits the window."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_split_worker, args=(r, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, left_log, left_outs), (_, right_log, right_outs) = res
+    assert left_outs == [True] * 5 and right_outs == [False] * 5
+    assert right_log == [("image", 1.0 + k) for k in range(5)]
+    submits = [e for e in left_log if e[0] == "submit"]
+    assert submits == [("submit", 1.0 + k, (7 * k + 3) % 251, (7 * k + 3) % 251, k % 2 == 0)
+                       for k in range(5)]
+    with pytest.raises(ValueError):
+        shard.LeftRightSplit(None, 2, exchange_stream=0)
