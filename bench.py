@@ -11,6 +11,9 @@ stereo LK (FeatureTracker::trackEvent, feature_tracker/src/feature_tracker.cpp:3
 N > 1: every rank runs its own independent stereo stream (weak scaling, SURVEY.md 8e
 "independent streams") and the ranks all-gather their packed track records once per window
 over NCCL.  One JSON line is printed by rank 0.
+
+  torchrun --nproc-per-node 2 bench.py --split-lr [--workload W]   one stream split by camera
+      over 2 GPUs, with the same windows on one GPU timed beside it
 """
 from __future__ import annotations
 
