@@ -166,3 +166,30 @@ WORKLOADS = {
     "stereo_vga_20mevs_burst": dict(width=640, height=480, rate=20.0e6, mono=False, max_cnt=200, min_dist=10, freq=10),
     "stereo_vga_10mevs": dict(width=640, height=480, rate=10.0e6, mono=False, max_cnt=150, min_dist=10, freq=10),
 }
+
+
+# ---------------------------------------------------------------------------------------
+# frame path (FeatureTracker::trackImage): synthetic intensity images
+# ---------------------------------------------------------------------------------------
+def frame_texture(W, H, seed):
+    """Smooth random texture with corners, built with integer arithmetic only: random blocks
+    plus a 5x5 box blur by integer cumulative sums."""
+    rng = np.random.default_rng(seed)
+    coarse = rng.integers(0, 256, ((H + 15) // 8 + 2, (W + 15) // 8 + 2), dtype=np.int64)
+    img = np.kron(coarse, np.ones((8, 8), np.int64))[:H + 4, :W + 4]
+    img = img + rng.integers(0, 24, img.shape, dtype=np.int64)
+    c = np.cumsum(np.cumsum(np.pad(img, ((1, 0), (1, 0))), axis=0), axis=1)
+    box = c[5:, 5:] - c[:-5, 5:] - c[5:, :-5] + c[:-5, :-5]
+    return ((box + 12) // 25).clip(0, 255).astype(np.uint8)[:H, :W]
+
+
+def stereo_frame_sequence(W, H, n_frames, seed=5):
+    """Frames cropped from one big texture at integer offsets: camera pans (3, 2) px per
+    frame, the right camera sees the scene 6 px further left."""
+    big = frame_texture(W + 8 * n_frames + 32, H + 8 * n_frames + 32, seed)
+    out = []
+    for k in range(n_frames):
+        ox, oy = 8 + 3 * k, 8 + 2 * k
+        out.append((np.ascontiguousarray(big[oy:oy + H, ox:ox + W]),
+                    np.ascontiguousarray(big[oy:oy + H, ox + 6:ox + 6 + W])))
+    return out

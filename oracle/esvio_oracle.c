@@ -1338,6 +1338,160 @@ ORA_API void ora_equalize_u8(const uint8_t *src, int W, int H, uint8_t *dst) {
 }
 
 /* ======================================================================== */
+/* cv::goodFeaturesToTrack as trackImage calls it (feature_tracker.cpp:228):   */
+/* minimum-eigenvalue corners, blockSize 3, Sobel aperture 3, quality 0.01     */
+/* ======================================================================== */
+/* OpenCV modules/imgproc/src/corner.cpp (cornerEigenValsVecs + calcMinEigenVal) and
+ * featureselect.cpp -- sources not under /root/reference; restated from the published
+ * algorithm and pinned bit for bit against cv2 4.13.0 (AVX2/FMA3 dispatch) in
+ * tests/test_oracle_golden.py.  The float operation order below is the one that build
+ * executes:
+ *   Dx = Sobel(1,0): row pass [-1 0 1] exact, column pass fma(S0+S2, k, S1*2k), k = 1/3060;
+ *   Dy = Sobel(0,1): row pass k*A, fma(2k,B,.), fma(k,C,.) in the 32-pixel vector body and plain
+ *        multiply/add in the row tail (x >= 32*(W/32)), column pass S2 - S0;
+ *   cov = (Dx*Dx, Dx*Dy, Dy*Dy) in f32, 3x3 unnormalised box sums in f64 (running column sums);
+ *   minEig = (a + c) - sqrt((a - c)^2 + b*b) with a = cov0/2, c = cov2/2, no fma.
+ * All borders are BORDER_REFLECT_101. */
+static inline float sobel_src(const uint8_t *img, int W, int H, int y, int x) {
+  return (float)img[(size_t)reflect101(y, H) * W + reflect101(x, W)];
+}
+
+ORA_API void ora_corner_min_eigen_val_u8(const uint8_t *img, int W, int H, float *eig) {
+  const size_t N = (size_t)W * H;
+  const float k1 = (float)(1.0 / 3060.0), k0 = (float)(2.0 * (1.0 / 3060.0));
+  float *dx = (float *)malloc(sizeof(float) * N * 5), *dy = dx + N;
+  float *cxx = dy + N, *cxy = cxx + N, *cyy = cxy + N;
+  const int nv = (W / 32) * 32;
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      float d[3], s[3];
+      for (int r = 0; r < 3; ++r) {
+        const float a = sobel_src(img, W, H, y - 1 + r, x - 1), b = sobel_src(img, W, H, y - 1 + r, x),
+                    cc = sobel_src(img, W, H, y - 1 + r, x + 1);
+        d[r] = cc - a;
+        if (x < nv) s[r] = fmaf(cc, k1, fmaf(b, k0, a * k1));
+        else s[r] = (a * k1 + b * k0) + cc * k1;
+      }
+      const float gx = fmaf(d[0] + d[2], k1, d[1] * k0), gy = s[2] - s[0];
+      const size_t i = (size_t)y * W + x;
+      dx[i] = gx;
+      dy[i] = gy;
+      cxx[i] = gx * gx;
+      cxy[i] = gx * gy;
+      cyy[i] = gy * gy;
+    }
+  /* boxFilter(3x3, normalize=false) on CV_32F: row sums (S0 + S1) + S2 in f64 (RowSum, ksize 3),
+   * then ONE running column sum per pixel column in f64 down the whole image (ColumnSum:
+   * s = SUM + row[y+1]; out = (float)s; SUM = s - row[y-1]) -- its rounding history is part of
+   * the result, so it is restated literally. */
+  double *sum = (double *)calloc((size_t)W * 3, sizeof(double));
+  double *ring = (double *)malloc(sizeof(double) * (size_t)W * 3 * 3); /* row sums of y-1, y, y+1 */
+  const float *plane[3] = {cxx, cxy, cyy};
+#define ROWSUM(dst, yy)                                                                   \
+  do {                                                                                    \
+    const size_t row_ = (size_t)reflect101((yy), H) * W;                                  \
+    for (int ch_ = 0; ch_ < 3; ++ch_)                                                     \
+      for (int x_ = 0; x_ < W; ++x_)                                                      \
+        (dst)[(size_t)ch_ * W + x_] = ((double)plane[ch_][row_ + reflect101(x_ - 1, W)] +  \
+                                       (double)plane[ch_][row_ + x_]) +                   \
+                                      (double)plane[ch_][row_ + reflect101(x_ + 1, W)];   \
+  } while (0)
+  double *r0 = ring, *r1 = ring + (size_t)W * 3, *r2 = ring + (size_t)W * 6;
+  ROWSUM(r0, -1);
+  ROWSUM(r1, 0);
+  for (size_t i = 0; i < (size_t)W * 3; ++i) sum[i] = (0.0 + r0[i]) + r1[i];
+  for (int y = 0; y < H; ++y) {
+    ROWSUM(r2, y + 1);
+    for (int x = 0; x < W; ++x) {
+      float cv[3];
+      for (int ch = 0; ch < 3; ++ch) {
+        const size_t i = (size_t)ch * W + x;
+        const double s0 = sum[i] + r2[i];
+        cv[ch] = (float)s0;
+        sum[i] = s0 - r0[i];
+      }
+      const float a = cv[0] * 0.5f, b = cv[1], c = cv[2] * 0.5f;
+      const float tt = a - c;
+      eig[(size_t)y * W + x] = (a + c) - sqrtf(tt * tt + b * b);
+    }
+    double *tmp = r0;
+    r0 = r1, r1 = r2, r2 = tmp;
+  }
+#undef ROWSUM
+  free(sum);
+  free(ring);
+  free(dx);
+}
+
+typedef struct gf_cand {
+  float v;
+  int idx;
+} gf_cand;
+/* featureselect.cpp greaterThanPtr: value descending, then address (= pixel index) descending */
+static int gf_cmp(const void *pa, const void *pb) {
+  const gf_cand *a = (const gf_cand *)pa, *b = (const gf_cand *)pb;
+  if (a->v > b->v) return -1;
+  if (a->v < b->v) return 1;
+  return a->idx > b->idx ? -1 : (a->idx < b->idx ? 1 : 0);
+}
+
+/* mask: NULL or W*H bytes, non-zero = allowed.  Writes <= max_corners (x, y) pairs in the
+ * order cv2 returns them; returns their number. */
+ORA_API int ora_good_features_to_track(const uint8_t *img, int W, int H, const uint8_t *mask,
+                                       int max_corners, double quality, double min_distance,
+                                       float *out_xy) {
+  if (W < 3 || H < 3) return 0;
+  const size_t N = (size_t)W * H;
+  float *eig = (float *)malloc(sizeof(float) * N);
+  ora_corner_min_eigen_val_u8(img, W, H, eig);
+  /* minMaxLoc under the mask, threshold(THRESH_TOZERO) on the whole image */
+  double max_val = 0;
+  int any = 0;
+  for (size_t i = 0; i < N; ++i)
+    if (!mask || mask[i]) {
+      if (!any || eig[i] > max_val) max_val = eig[i];
+      any = 1;
+    }
+  if (!any) max_val = 0; /* minMaxLoc leaves maxVal 0 under an all-zero mask */
+  const float thr = (float)(max_val * quality);
+  for (size_t i = 0; i < N; ++i)
+    if (!(eig[i] > thr)) eig[i] = 0.f;
+  /* local maxima of the 3x3 dilation (pixels outside the image do not take part) */
+  gf_cand *cand = (gf_cand *)malloc(sizeof(gf_cand) * N);
+  size_t nc = 0;
+  for (int y = 1; y < H - 1; ++y)
+    for (int x = 1; x < W - 1; ++x) {
+      const size_t i = (size_t)y * W + x;
+      const float v = eig[i];
+      if (v == 0.f || (mask && !mask[i])) continue;
+      float m = v;
+      for (int r = -1; r <= 1; ++r)
+        for (int q = -1; q <= 1; ++q) {
+          const float w = eig[i + (ptrdiff_t)r * W + q];
+          if (w > m) m = w;
+        }
+      if (v == m) cand[nc].v = v, cand[nc].idx = (int)i, ++nc;
+    }
+  qsort(cand, nc, sizeof(gf_cand), gf_cmp);
+  /* greedy minimum-distance filter in that order (the grid of the original only speeds it up) */
+  int n = 0;
+  const float md2 = (float)(min_distance * min_distance);
+  for (size_t k = 0; k < nc && (max_corners <= 0 || n < max_corners); ++k) {
+    const float x = (float)(cand[k].idx % W), y = (float)(cand[k].idx / W);
+    int good = 1;
+    if (min_distance >= 1)
+      for (int j = 0; j < n && good; ++j) {
+        const float dx = x - out_xy[2 * j], dy = y - out_xy[2 * j + 1];
+        if (dx * dx + dy * dy < md2) good = 0;
+      }
+    if (good) out_xy[2 * n] = x, out_xy[2 * n + 1] = y, ++n;
+  }
+  free(cand);
+  free(eig);
+  return n;
+}
+
+/* ======================================================================== */
 /* Whole-window tracker: FeatureTracker::trackEvent (feature_tracker.cpp:340-603) */
 /* ======================================================================== */
 
@@ -1461,6 +1615,25 @@ static void velocity(const int *ids, const float *un, int n, const int *pids, co
   }
 }
 
+static int track_tail(ora_tracker *t, double cur_time, int pub, int image_mode, int have_right,
+                      const uint16_t *lx, const uint16_t *ly, const double *lt,
+                      const uint8_t *lp, size_t nl, ora_tracks *out);
+
+/* FeatureTracker::trackImage (feature_tracker.cpp:164-338): cfg.max_cnt / cfg.min_dist play
+ * MAX_CNT_IMG / MIN_DIST_IMG, cfg.width / height play COL / ROW.  right == NULL: img_right.empty() */
+ORA_API int ora_tracker_track_image(ora_tracker *t, double cur_time, const uint8_t *left,
+                                    const uint8_t *right, int pub, ora_tracks *out) {
+  const size_t N = (size_t)t->cfg.width * t->cfg.height;
+  memcpy(t->img[0], left, N);
+  memcpy(t->ts[0], left, N);
+  if (right) memcpy(t->img[1], right, N), memcpy(t->ts[1], right, N);
+  if (!t->have_prev_img) { /* :172-174 */
+    memcpy(t->prev_img, t->img[0], N);
+    t->have_prev_img = 1;
+  }
+  return track_tail(t, cur_time, pub, 1, right != NULL, NULL, NULL, NULL, NULL, 0, out);
+}
+
 ORA_API int ora_tracker_track(ora_tracker *t, double cur_time, const uint16_t *lx,
                               const uint16_t *ly, const double *lt, const uint8_t *lp, size_t nl,
                               const uint16_t *rx, const uint16_t *ry, const double *rt,
@@ -1509,7 +1682,20 @@ ORA_API int ora_tracker_track_mc(ora_tracker *t, double cur_time, const uint16_t
   }
   t1 = now_sec();
   t->timers[1] += t1 - t0;
-  t0 = t1;
+  return track_tail(t, cur_time, pub, 0, 1, lx, ly, lt, lp, nl, out);
+}
+
+/* Everything of trackEvent behind the images (feature_tracker.cpp:405-603), and -- with
+ * image_mode -- of trackImage (:178-338): there the backward temporal LK is a full 4-level
+ * call without initial flow (:190), there is no F-RANSAC, and new points come from
+ * goodFeaturesToTrack under the Image_setMask mask (:213-237). */
+static int track_tail(ora_tracker *t, double cur_time, int pub, int image_mode, int have_right,
+                      const uint16_t *lx, const uint16_t *ly, const double *lt,
+                      const uint8_t *lp, size_t nl, ora_tracks *out) {
+  const ora_config *c = &t->cfg;
+  const int W = c->width, H = c->height, M = c->max_cnt;
+  const size_t N = (size_t)W * H;
+  double t0 = now_sec(), t1;
 
   float *cur = (float *)malloc(sizeof(float) * 2 * (M + 1));
   float *rev = (float *)malloc(sizeof(float) * 2 * (M + 1));
@@ -1523,7 +1709,8 @@ ORA_API int ora_tracker_track_mc(ora_tracker *t, double cur_time, const uint16_t
     run_lk(t, t->prev_img, t->img[0], t->prev_pts, cur, n, st, 3, 0);
     if (c->flow_back) {
       memcpy(rev, t->prev_pts, sizeof(float) * 2 * n);
-      run_lk(t, t->img[0], t->prev_img, cur, rev, n, st2, 1, 1);
+      if (image_mode) run_lk(t, t->img[0], t->prev_img, cur, rev, n, st2, 3, 0);
+      else run_lk(t, t->img[0], t->prev_img, cur, rev, n, st2, 1, 1);
       for (int i = 0; i < n; ++i)
         st[i] = st[i] && st2[i] &&
                 pt_dist(t->prev_pts[2 * i], t->prev_pts[2 * i + 1], rev[2 * i], rev[2 * i + 1]) <= 0.5;
@@ -1554,7 +1741,7 @@ ORA_API int ora_tracker_track_mc(ora_tracker *t, double cur_time, const uint16_t
   out->n_new = 0;
   if (pub) {
     /* rejectWithF_event (:910-947) */
-    if (n >= 8 && !t->ransac_disabled) {
+    if (n >= 8 && !t->ransac_disabled && !image_mode) {
       float *a = (float *)malloc(sizeof(float) * 4 * n), *b = a + 2 * n;
       for (int i = 0; i < n; ++i) {
         double x, y;
@@ -1587,9 +1774,16 @@ ORA_API int ora_tracker_track_mc(ora_tracker *t, double cur_time, const uint16_t
     const int want = M - n;
     if (want > 0) {
       float *np = (float *)malloc(sizeof(float) * 2 * want);
-      const int k = ora_features_to_track(t->sae[0], lx, ly, lt, lp, nl, want, c->min_dist, t->mask,
-                                          t->ts[0], c->ts_lk_threshold,
-                                          c->feature_filter_threshold, np, NULL);
+      int k;
+      if (image_mode) { /* goodFeaturesToTrack wants 255 = allowed; ora_set_mask marks blocked */
+        uint8_t *allow = (uint8_t *)malloc(N);
+        for (size_t i = 0; i < N; ++i) allow[i] = t->mask[i] ? 0 : 255;
+        k = ora_good_features_to_track(t->img[0], W, H, allow, want, 0.01, (double)c->min_dist, np);
+        free(allow);
+      } else
+        k = ora_features_to_track(t->sae[0], lx, ly, lt, lp, nl, want, c->min_dist, t->mask,
+                                  t->ts[0], c->ts_lk_threshold, c->feature_filter_threshold, np,
+                                  NULL);
       for (int i = 0; i < k; ++i) {
         cur[2 * n] = np[2 * i];
         cur[2 * n + 1] = np[2 * i + 1];
@@ -1632,7 +1826,7 @@ ORA_API int ora_tracker_track_mc(ora_tracker *t, double cur_time, const uint16_t
   int nrgt = 0;
   float *unr = (float *)malloc(sizeof(float) * 2 * (M + 1));
   int *idr = (int *)malloc(sizeof(int) * (M + 1));
-  if (n > 0) {
+  if (n > 0 && have_right) {
     float *rpts = (float *)malloc(sizeof(float) * 2 * n);
     run_lk(t, t->img[0], t->img[1], cur, rpts, n, st, 3, 0);
     if (c->flow_back) {

@@ -119,6 +119,15 @@ void ora_normalize_minmax_u8(const uint8_t *src, size_t n, uint8_t *dst);
 /* CLAHE defaults (40, 8x8) + normalize: the EQUALIZE branch of trackEvent */
 void ora_equalize_u8(const uint8_t *src, int W, int H, uint8_t *dst);
 
+/* ---------------- cv::goodFeaturesToTrack (frame path, feature_tracker.cpp:228) ---------------- */
+/* cv::cornerMinEigenVal(img, blockSize 3, ksize 3), CV_8U -> CV_32F, BORDER_REFLECT_101 */
+void ora_corner_min_eigen_val_u8(const uint8_t *img, int W, int H, float *eig);
+/* cv::goodFeaturesToTrack(img, maxCorners, quality, minDistance, mask, blockSize 3, Harris off);
+ * mask NULL or W*H (non-zero = allowed); returns the number of (x, y) pairs written */
+int ora_good_features_to_track(const uint8_t *img, int W, int H, const uint8_t *mask,
+                               int max_corners, double quality, double min_distance,
+                               float *out_xy);
+
 /* ---------------- camodocal pinhole ---------------- */
 typedef struct ora_pinhole {
   double fx, fy, cx, cy, k1, k2, p1, p2;
@@ -175,6 +184,10 @@ int ora_tracker_track_mc(ora_tracker *t, double cur_time, const uint16_t *lx, co
                          const double *lt, const uint8_t *lp, size_t nl, const uint16_t *rx,
                          const uint16_t *ry, const double *rt, const uint8_t *rp, size_t nr,
                          int pub_this_frame, const ora_motion *mc, ora_tracks *out);
+/* FeatureTracker::trackImage (feature_tracker.cpp:164-338) on the same tracker state:
+ * cfg.max_cnt / min_dist play MAX_CNT_IMG / MIN_DIST_IMG; right == NULL: img_right.empty() */
+int ora_tracker_track_image(ora_tracker *t, double cur_time, const uint8_t *left,
+                            const uint8_t *right, int pub, ora_tracks *out);
 /* views of internal state, for stage-level parity checks */
 const ora_sae *ora_tracker_sae(const ora_tracker *t, int cam);
 const uint8_t *ora_tracker_time_surface(const ora_tracker *t, int cam);

@@ -140,6 +140,13 @@ def lib():
         L.ora_clahe_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
         L.ora_normalize_minmax_u8.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.ora_equalize_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ora_corner_min_eigen_val_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ora_good_features_to_track.restype = C.c_int
+        L.ora_good_features_to_track.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                 C.c_double, C.c_double, C.c_void_p]
+        L.ora_tracker_track_image.restype = C.c_int
+        L.ora_tracker_track_image.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.POINTER(_Tracks)]
         L.ora_mat3_exp_f.argtypes = [C.c_void_p, C.c_void_p]
         L.ora_motion_correct.argtypes = [C.POINTER(_Motion), C.c_int, C.c_int, C.c_double, C.c_double,
                                          C.c_double, _pi, _pi]
@@ -282,6 +289,25 @@ def normalize_minmax(img):
     out = np.empty_like(img)
     lib().ora_normalize_minmax_u8(_p(img), img.size, _p(out))
     return out
+
+
+def corner_min_eigen_val(img):
+    """cv2.cornerMinEigenVal(img, 3, ksize=3) on CV_8U."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(img.shape, np.float32)
+    lib().ora_corner_min_eigen_val_u8(_p(img), img.shape[1], img.shape[0], _p(out))
+    return out
+
+
+def good_features_to_track(img, max_corners, quality=0.01, min_distance=30.0, mask=None):
+    """cv2.goodFeaturesToTrack(img, max_corners, quality, min_distance, mask=mask) -> (n, 2) f32."""
+    img = np.ascontiguousarray(img, np.uint8)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    out = np.zeros((max(int(max_corners), 1) if max_corners > 0 else img.size, 2), np.float32)
+    n = lib().ora_good_features_to_track(_p(img), img.shape[1], img.shape[0],
+                                         _p(m) if m is not None else None, int(max_corners),
+                                         float(quality), float(min_distance), _p(out))
+    return out[:n].copy()
 
 
 def equalize(img):
@@ -502,6 +528,28 @@ class OracleTracker:
                             n_after_ransac=t.n_after_ransac, n_after_mask=t.n_after_mask,
                             n_new=t.n_new)
         return out
+
+    def _unpack(self):
+        t = self._t
+        nl, nr = t.n_left, t.n_right
+        b = self._bufs
+        out = {k: b[k][:nl].copy() for k in ("id", "track_cnt", "u", "v", "un_x", "un_y", "vx", "vy")}
+        out.update({k: b[k][:nr].copy() for k in ("id_right", "ru", "rv", "run_x", "run_y", "rvx", "rvy")})
+        out["stats"] = dict(n_prev=t.n_prev, n_after_temporal=t.n_after_temporal,
+                            n_after_ransac=t.n_after_ransac, n_after_mask=t.n_after_mask,
+                            n_new=t.n_new)
+        return out
+
+    def track_image(self, cur_time, img_left, img_right=None, pub_this_frame=True):
+        """FeatureTracker::trackImage (feature_tracker.cpp:164-338); cfg max_cnt / min_dist are
+        MAX_CNT_IMG / MIN_DIST_IMG."""
+        a = np.ascontiguousarray(img_left, np.uint8)
+        assert a.shape == (self.H, self.W)
+        b = None if img_right is None else np.ascontiguousarray(img_right, np.uint8)
+        lib().ora_tracker_track_image(self._h, float(cur_time), _p(a),
+                                      _p(b) if b is not None else None, int(pub_this_frame),
+                                      C.byref(self._t))
+        return self._unpack()
 
     def sae(self, cam):
         return Sae(self.W, self.H, _borrow=lib().ora_tracker_sae(self._h, cam))

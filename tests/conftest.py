@@ -43,6 +43,11 @@ def golden_imgops():
 
 
 @pytest.fixture(scope="session")
+def golden_frames():
+    return np.load(os.path.join(GOLDEN, "frames_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def capi():
     """libesvio_fe.so through ctypes; the GPU tests must run on the native library."""
     from esvio_b200 import _capi

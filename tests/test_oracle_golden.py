@@ -115,3 +115,64 @@ def test_clahe_normalize_matches_cv2(ora, golden_imgops, name):
     assert np.array_equal(ora.clahe(img), g[name + "_clahe"])
     assert np.array_equal(ora.normalize_minmax(img), g[name + "_norm"])
     assert np.array_equal(ora.equalize(img), g[name + "_clahe_norm"])
+
+
+# ---- frame path: goodFeaturesToTrack + trackImage ----
+FRAME_SEQ = dict(W=240, H=180, n_frames=6, max_cnt=60, min_dist=14)     # = make_golden_frames.SEQ
+FRAME_CAM = [dict(fx=260.0, fy=261.0, cx=121.5, cy=88.0, k1=-0.05, k2=0.02, p1=1e-3, p2=-5e-4),
+             dict(fx=259.0, fy=260.5, cx=119.0, cy=90.5, k1=-0.04, k2=0.015, p1=-8e-4, p2=3e-4)]
+
+
+def frame_input(g, name):
+    from esvio_b200 import synth
+    return {"tex346": lambda: synth.frame_texture(346, 260, 11),
+            "tex640": lambda: synth.frame_texture(640, 480, 12),
+            "noise173": lambda: g["noise173_in"],
+            "tiny": lambda: synth.frame_texture(7, 5, 13),
+            "flat": lambda: np.full((64, 96), 77, np.uint8)}[name]()
+
+
+@pytest.mark.parametrize("name", ["tex346", "tex640", "noise173", "tiny", "flat"])
+def test_min_eigen_val_and_good_features_match_cv2(ora, golden_frames, name):
+    """cv::cornerMinEigenVal(3, 3) bit for bit (f32 plane) and cv::goodFeaturesToTrack with the
+    arguments of feature_tracker.cpp:228 (quality 0.01, mask, min distance) -- same corners in
+    the same order, incl. a width that is not a multiple of 32 (Sobel row tail), maxCorners 0
+    (unlimited), min distance < 1 (no spacing) and images without any corner."""
+    import hashlib
+    g = golden_frames
+    img = frame_input(g, name)
+    eig = ora.corner_min_eigen_val(img)
+    assert np.array_equal(np.frombuffer(hashlib.sha256(eig.tobytes()).digest(), np.uint8),
+                          g[f"{name}_eig_sha"])
+    if f"{name}_eig" in g.files:
+        assert np.array_equal(eig, g[f"{name}_eig"])
+    else:
+        assert np.array_equal(eig[::7], g[f"{name}_eig_rows"])
+    mask = g[f"{name}_mask"]
+    for tag, (n, md, m) in dict(a=(100, 30.0, None), b=(150, 10.0, mask), c=(0, 1.0, None),
+                                d=(40, 0.5, mask)).items():
+        got = ora.good_features_to_track(img, n, 0.01, md, m)
+        assert np.array_equal(got, g[f"{name}_gftt_{tag}"]), (name, tag)
+
+
+def test_track_image_matches_cv2_sequence(ora, golden_frames):
+    """FeatureTracker::trackImage (feature_tracker.cpp:164-338) over six stereo frames, one of
+    them without a right image, against the same control flow run on real OpenCV
+    (tests/golden/make_golden_frames.py).  Oracle LK = the C restatement, so (u, v) agree to the
+    LK tolerance and ids / counts exactly."""
+    from esvio_b200 import synth
+    g, s = golden_frames, FRAME_SEQ
+    cfg = synth.default_config(s["W"], s["H"], max_cnt=s["max_cnt"], min_dist=s["min_dist"])
+    cfg["cam"] = FRAME_CAM
+    trk = ora.OracleTracker(cfg)
+    for k, (L, R) in enumerate(synth.stereo_frame_sequence(s["W"], s["H"], s["n_frames"])):
+        out = trk.track_image(1.0 + k / 20.0, L, R if k != 3 else None, k % 2 == 0)
+        for key in ("id", "track_cnt", "id_right"):
+            assert np.array_equal(out[key], g[f"seq{k}_{key}"]), (k, key)
+        for key in ("u", "v", "ru", "rv"):
+            assert np.abs(out[key] - g[f"seq{k}_{key}"]).max(initial=0) <= 1e-3, (k, key)
+        for key in ("un_x", "un_y"):
+            assert np.abs(out[key] - g[f"seq{k}_{key}"]).max(initial=0) <= 1e-5, (k, key)
+        if k == 3:
+            assert len(out["id_right"]) == 0
+    assert len(g["seq5_id"]) > 40 and g["seq5_track_cnt"].max() == 6
