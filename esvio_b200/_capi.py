@@ -116,6 +116,12 @@ SYMBOLS = {
     "esvio_fe_split_right_buffer": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "esvio_fe_track_submit_split": (C.c_int, [_H, C.c_double, C.POINTER(Events), C.c_int32,
                                               C.c_void_p]),
+    "esvio_fe_track_image": (C.c_int, [_H, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p,
+                                       C.c_size_t, C.c_int32, C.POINTER(Tracks)]),
+    "esvio_fe_track_image_submit": (C.c_int, [_H, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p,
+                                              C.c_size_t, C.c_int32]),
+    "esvio_fe_stage_good_features": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
+                                               C.c_void_p, C.c_int32, _pi, C.c_void_p]),
     "esvio_fe_set_profiling": (C.c_int, [_H, C.c_int32]),
     "esvio_fe_get_stage_ms": (C.c_int, [_H, _pf]),
     "esvio_fe_kernel_launches": (C.c_int, [_H, C.POINTER(C.c_int64)]),

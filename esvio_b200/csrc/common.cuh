@@ -335,6 +335,42 @@ struct TrackParams {
   Pinhole cam[2];
 };
 
+// frame path: scratch of cv::goodFeaturesToTrack (frames.cu), allocated on first use
+struct GfttBuffers {
+  float* cov[3];                 // Dx*Dx, Dx*Dy, Dy*Dy                      [H][W]
+  float* eig;                    // cornerMinEigenVal                        [H][W]
+  uint32_t* blocked;             // 1 bit per pixel: mask == 0               [H][(W+31)/32]
+  float* thr;                    // maxVal * qualityLevel
+  unsigned long long* keys;      // float_order(eig) << 32 | pixel, 0 = none [H*W]
+  unsigned long long* keys_sorted;
+  void* sort_temp;
+  size_t sort_temp_bytes;
+  float2* out_xy;                // stage entry: picked corners              [H*W] (capacity)
+  int* out_n;
+};
+size_t gftt_sort_temp_bytes(int n);
+void launch_gftt_eig(const GfttBuffers& G, const uint8_t* img, int pitch, int W, int H,
+                     cudaStream_t s, int64_t* launches);
+void launch_gftt_thr(const GfttBuffers& G, int W, int H, bool use_mask, cudaStream_t s,
+                     int64_t* launches);
+int launch_gftt_candidates(const GfttBuffers& G, int W, int H, bool use_mask, cudaStream_t s,
+                           int64_t* launches);
+// Image_setMask (feature_tracker.cpp:91-121): survivors compacted in place, their discs
+// rastered into G.blocked
+void launch_image_set_mask(const TrackParams& P, const TrackBuffers& B, const GfttBuffers& G,
+                           cudaStream_t s, int64_t* launches);
+// greedy minimum-distance pick over G.keys_sorted.  Tracker form: appends up to
+// max_cnt - n_cur new points (ids from next_id, track_cnt 1), updates the counters and takes
+// the snapshot of slot `snap_slot`.  Stage form: writes up to max_corners (<= 0: all) corners
+// to G.out_xy / G.out_n.
+void launch_gftt_pick_tracks(const TrackParams& P, const TrackBuffers& B, const GfttBuffers& G,
+                             int snap_slot, cudaStream_t s, int64_t* launches);
+void launch_gftt_pick_stage(const GfttBuffers& G, int W, int H, int max_corners,
+                            double min_distance, cudaStream_t s, int64_t* launches);
+// the right-camera velocity map survives a frame without a right image
+// (feature_tracker.cpp:245: the whole block is skipped): stash / restore its size
+void launch_right_map_keep(const TrackBuffers& B, int restore, cudaStream_t s, int64_t* launches);
+
 // snap_slot >= 0: the kernel is the last one of the window's temporal stage and also takes the
 // per-slot snapshot (cur_pts, ids, track_cnt, counters) the stereo stage works from
 void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, int snap_slot,

@@ -52,6 +52,8 @@ struct esvio_fe {
   const uint8_t* ts_sel[2];
   uint16_t* warp_xy[2][2];  // [x|y][camera]: motion-compensated pixels of the window's events
   float mc_K[4];
+  GfttBuffers gftt;  // frame path (esvio_fe_track_image): allocated on first use
+  void* gftt_block;
   int cur_left;   // index (0..2) of the newest left pyramid; prev_left is the one before it
   int prev_left;
   int cur_right;  // 3..5
@@ -214,6 +216,7 @@ static void free_all(esvio_fe* fe) {
   for (int i = 0; i < 3; ++i) cudaFree(fe->aux[i][0]), cudaFree(fe->aux[i][1]);
   cudaFree(fe->clahe_lut);
   cudaFree(fe->clahe_minmax);
+  cudaFree(fe->gftt_block);
   for (int i = 0; i < 2; ++i) cudaFree(fe->warp_xy[i][0]), cudaFree(fe->warp_xy[i][1]);
   for (int i = 0; i < kSlots; ++i) {
     cudaFree(fe->raw[i][0]);
@@ -919,6 +922,183 @@ FE_API int esvio_fe_track_submit_split(esvio_fe* fe, double cur_time, const esvi
   CU(cudaStreamWaitEvent(fe->stream, fe->x_ready[w.slot], 0));
   if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame)) != ESVIO_FE_OK) return rc;
   fe->pev_valid[w.slot] = fe->profiling;
+  return ESVIO_FE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// frame path: FeatureTracker::trackImage (feature_tracker.cpp:164-338)
+// ---------------------------------------------------------------------------------------
+// One allocation for the scratch of goodFeaturesToTrack (frames.cu), made on the first frame.
+static int ensure_gftt(esvio_fe* fe) {
+  if (fe->gftt_block) return ESVIO_FE_OK;
+  const size_t N = fe->npx, words = (size_t)fe->H * ((fe->W + 31) / 32);
+  const size_t temp = gftt_sort_temp_bytes((int)N);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t o_cov = take(3 * N * 4), o_eig = take(N * 4), o_blk = take(words * 4),
+               o_thr = take(256), o_keys = take(N * 8), o_sorted = take(N * 8),
+               o_temp = take(temp), o_xy = take(N * 8), o_n = take(256);
+  uint8_t* base = nullptr;
+  CU(cudaMalloc(&base, off));
+  CU(cudaMemset(base, 0, off));
+  GfttBuffers& G = fe->gftt;
+  for (int c = 0; c < 3; ++c) G.cov[c] = (float*)(base + o_cov) + (size_t)c * N;
+  G.eig = (float*)(base + o_eig);
+  G.blocked = (uint32_t*)(base + o_blk);
+  G.thr = (float*)(base + o_thr);
+  G.keys = (unsigned long long*)(base + o_keys);
+  G.keys_sorted = (unsigned long long*)(base + o_sorted);
+  G.sort_temp = base + o_temp;
+  G.sort_temp_bytes = temp;
+  G.out_xy = (float2*)(base + o_xy);
+  G.out_n = (int*)(base + o_n);
+  fe->gftt_block = base;
+  return ESVIO_FE_OK;
+}
+
+// The frame counterpart of esvio_fe_track_submit.  cfg.max_cnt / cfg.min_dist play MAX_CNT_IMG /
+// MIN_DIST_IMG, cfg.width / height COL / ROW.  right == NULL: img_right.empty() (mono).
+FE_API int esvio_fe_track_image_submit(esvio_fe* fe, double cur_time, const uint8_t* left,
+                                       size_t left_stride, const uint8_t* right,
+                                       size_t right_stride, int32_t pub_this_frame) {
+  if (!fe || !left || left_stride < (size_t)fe->W || (right && right_stride < (size_t)fe->W))
+    return ESVIO_FE_EINVAL;
+  if (fe->group) return fail(fe, ESVIO_FE_ESTATE, "handle belongs to a group", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  int rc;
+  if ((rc = ensure_gftt(fe)) != ESVIO_FE_OK) return rc;
+  WindowPlan w;
+  if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
+  fe->pev_slot = w.slot;
+  cudaStream_t sc = fe->stream_c, se = fe->stream_e, s1 = fe->stream_t1, s2 = fe->stream;
+  const int slot = w.slot, cur = w.cur, prev = w.prev, rcur = w.rcur, pitch = fe->pd.pitch[0];
+  const int M = fe->cfg.max_cnt;
+  const TrackBuffers& B = fe->tb;
+  const GfttBuffers& G = fe->gftt;
+  // ---- image stage: the frames into pyramid level 0, then the pyramids
+  prof_mark(fe, 0);
+  CU(cudaMemcpy2DAsync(fe->pyr[cur], pitch, left, left_stride, fe->W, fe->H, cudaMemcpyHostToDevice, sc));
+  if (right)
+    CU(cudaMemcpy2DAsync(fe->pyr[rcur], pitch, right, right_stride, fe->W, fe->H, cudaMemcpyHostToDevice, sc));
+  if ((rc = staging_done(fe, slot, se)) != ESVIO_FE_OK) return rc;
+  prof_mark(fe, 1);
+  prof_mark(fe, 2);
+  prof_mark(fe, 3);
+  uint8_t* imgs[2] = {fe->pyr[cur], fe->pyr[rcur]};
+  launch_pyramids(fe->pd, imgs, right ? 2 : 1, se, &fe->launches);
+  fe->ts_sel[0] = fe->ts_sel[1] = nullptr;
+  prof_mark(fe, 4);
+  prof_mark(fe, 5);
+  CU(cudaEventRecord(fe->e_done[slot], se));
+  // ---- temporal stage (:178-237): forward + full backward LK, Image_setMask, goodFeaturesToTrack
+  CU(cudaStreamWaitEvent(s1, fe->e_done[slot], 0));
+  prof_mark(fe, ESVIO_FE_NUM_STAGES + 1);
+  launch_lk(fe->pd, fe->pyr[prev], fe->pyr[cur], B.prev_pts, B.cur_pts, B.st_fwd, B.rev_pts,
+            B.st_bwd, &B.st->n_prev, M, 3, 0, fe->cfg.flow_back ? 2 : 0, s1, &fe->launches);
+  launch_post_temporal(fe->tp, B, pub_this_frame ? -1 : slot, s1, &fe->launches);
+  prof_mark(fe, 6);
+  if (pub_this_frame) {
+    // the scratch of goodFeaturesToTrack is only touched on this stream, so windows in flight
+    // cannot collide on it
+    launch_image_set_mask(fe->tp, B, G, s1, &fe->launches);
+    launch_gftt_eig(G, fe->pyr[cur], pitch, fe->W, fe->H, s1, &fe->launches);
+    launch_gftt_thr(G, fe->W, fe->H, true, s1, &fe->launches);
+    if (launch_gftt_candidates(G, fe->W, fe->H, true, s1, &fe->launches) != 0)
+      return fail(fe, ESVIO_FE_ECUDA, "radix sort of the corner candidates", cudaGetLastError());
+    launch_gftt_pick_tracks(fe->tp, B, G, slot, s1, &fe->launches);
+  }
+  prof_mark(fe, 7);
+  CU(cudaEventRecord(fe->t1_done[slot], s1));
+  // ---- stereo stage (:245-322)
+  CU(cudaStreamWaitEvent(s2, fe->t1_done[slot], 0));
+  prof_mark(fe, ESVIO_FE_NUM_STAGES + 2);
+  if (right) {
+    launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.snap_pts + (size_t)slot * M, B.right_pts,
+              B.st_sf, B.rev_left_pts, B.st_sb, B.snap_hdr + slot * 16, M, 3, 0,
+              fe->cfg.flow_back ? 2 : 0, s2, &fe->launches);
+    launch_finalize(fe->tp, B, slot, cur_time, fe->prev_time, s2, &fe->launches);
+  } else {
+    // no right image: no right points, and prev_un_right_pts_map stays as it is (:245)
+    CU(cudaMemsetAsync(B.st_sf, 0, M, s2));
+    launch_right_map_keep(B, 0, s2, &fe->launches);
+    launch_finalize(fe->tp, B, slot, cur_time, fe->prev_time, s2, &fe->launches);
+    launch_right_map_keep(B, 1, s2, &fe->launches);
+  }
+  prof_mark(fe, 8);
+  CU(cudaMemcpyAsync(fe->h_result[slot], B.result, fe->result_words * 4, cudaMemcpyDeviceToHost, s2));
+  prof_mark(fe, 9);
+  CU(cudaEventRecord(fe->q_done[slot], s2));
+  CU(cudaGetLastError());
+  fe->q_count++;
+  fe->prev_left = prev;
+  fe->cur_left = cur;
+  fe->cur_right = rcur;
+  fe->windows++;
+  fe->prev_time = cur_time;
+  fe->pev_valid[slot] = fe->profiling;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_track_image(esvio_fe* fe, double cur_time, const uint8_t* left,
+                                size_t left_stride, const uint8_t* right, size_t right_stride,
+                                int32_t pub_this_frame, esvio_tracks* out) {
+  if (!fe || !out) return ESVIO_FE_EINVAL;
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "track while windows are in flight", cudaSuccess);
+  const int rc = esvio_fe_track_image_submit(fe, cur_time, left, left_stride, right, right_stride,
+                                             pub_this_frame);
+  if (rc != ESVIO_FE_OK) return rc;
+  return esvio_fe_track_wait(fe, out);
+}
+
+// stage entry: cv::goodFeaturesToTrack(img, max_corners, 0.01, min_distance, mask) on a host
+// image (W x H, contiguous); mask NULL or W x H bytes, non-zero = allowed.  out_xy has room for
+// `capacity` corners; eig (nullable) receives the cornerMinEigenVal plane.
+FE_API int esvio_fe_stage_good_features(esvio_fe* fe, const uint8_t* img, const uint8_t* mask,
+                                        int32_t max_corners, double min_distance, float* out_xy,
+                                        int32_t capacity, int32_t* out_n, float* eig) {
+  if (!fe || !img || !out_xy || !out_n || capacity < 0) return ESVIO_FE_EINVAL;
+  if (min_distance > 1.0 && (max_corners <= 0 || max_corners > kMaxCnt))
+    return fail(fe, ESVIO_FE_EINVAL, "spaced corners: 1 <= max_corners <= 1024", cudaSuccess);
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "windows in flight", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  int rc;
+  if ((rc = ensure_gftt(fe)) != ESVIO_FE_OK) return rc;
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
+  cudaStream_t s = fe->stream;
+  const GfttBuffers& G = fe->gftt;
+  const int W = fe->W, H = fe->H, pitch = fe->pd.pitch[0], words = (W + 31) / 32;
+  uint8_t* d_img = fe->pyr[kScratchBase];
+  CU(cudaMemcpy2DAsync(d_img, pitch, img, W, W, H, cudaMemcpyHostToDevice, s));
+  uint32_t* h_blk = nullptr;
+  if (mask) {
+    h_blk = (uint32_t*)calloc((size_t)H * words, 4);
+    if (!h_blk) return fail(fe, ESVIO_FE_ECUDA, "out of host memory", cudaSuccess);
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x)
+        if (!mask[(size_t)y * W + x]) h_blk[(size_t)y * words + (x >> 5)] |= 1u << (x & 31);
+    const cudaError_t e = cudaMemcpyAsync(G.blocked, h_blk, (size_t)H * words * 4, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+      free(h_blk);
+      return fail(fe, ESVIO_FE_ECUDA, "mask upload", e);
+    }
+  }
+  launch_gftt_eig(G, d_img, pitch, W, H, s, &fe->launches);
+  launch_gftt_thr(G, W, H, mask != nullptr, s, &fe->launches);
+  const int sort_rc = launch_gftt_candidates(G, W, H, mask != nullptr, s, &fe->launches);
+  launch_gftt_pick_stage(G, W, H, max_corners, min_distance, s, &fe->launches);
+  int n = 0;
+  cudaError_t e = cudaMemcpyAsync(&n, G.out_n, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  free(h_blk);
+  if (sort_rc != 0 || e != cudaSuccess) return fail(fe, ESVIO_FE_ECUDA, "good features", e);
+  *out_n = n;
+  const int m = n < capacity ? n : capacity;
+  if (m > 0) CU(cudaMemcpy(out_xy, G.out_xy, sizeof(float2) * m, cudaMemcpyDeviceToHost));
+  if (eig) CU(cudaMemcpy(eig, G.eig, sizeof(float) * (size_t)W * H, cudaMemcpyDeviceToHost));
   return ESVIO_FE_OK;
 }
 

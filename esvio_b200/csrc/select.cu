@@ -650,4 +650,226 @@ void launch_undistort(const Pinhole& cam, const float2* uv, int n, float2* out, 
   ++*launches;
 }
 
+// =====================================================================================
+// frame path (FeatureTracker::trackImage, feature_tracker.cpp:164-338)
+// =====================================================================================
+// Image_setMask (feature_tracker.cpp:91-121): points are visited by track_cnt descending (ties
+// keep their order, as in Event_setMask above); a point survives iff its rounded pixel is
+// still free, and then blocks the filled circle of radius MIN_DIST_IMG around it.  Survivors
+// are compacted in place; the mask (1 bit per pixel, 1 = blocked) goes to global memory for
+// goodFeaturesToTrack.
+__global__ void __launch_bounds__(kSelThreads)
+k_image_set_mask(TrackParams P, TrackBuffers B, uint32_t* __restrict__ blocked) {
+  PDL_PROLOGUE();
+  extern __shared__ uint32_t s_mask[];
+  __shared__ int s_hw[kMaxDiscR + 1];
+  __shared__ int s_order[kMaxCnt];
+  __shared__ float2 s_pts[kMaxCnt];
+  __shared__ int s_ids[kMaxCnt], s_cnt[kMaxCnt];
+  __shared__ int s_kept;
+  TrackState* st = B.st;
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const int W = P.W, H = P.H, words = (W + 31) / 32;
+  const int n = st->n_cur;
+  for (int i = tid; i < H * words; i += blockDim.x) s_mask[i] = 0;
+  if (tid == 0) {
+    disc_half_widths(P.min_dist, s_hw);
+    s_kept = 0;
+  }
+  if (tid < n) {
+    s_pts[tid] = B.cur_pts[tid];
+    s_ids[tid] = B.ids[tid];
+    s_cnt[tid] = B.cnt[tid];
+  }
+  __syncthreads();
+  if (tid < n) {
+    const int c = s_cnt[tid];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (s_cnt[j] > c) || (s_cnt[j] == c && j < tid);
+    s_order[rank] = tid;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int kept = 0;
+    for (int k = 0; k < n; ++k) {
+      const int i = s_order[k];
+      const float2 p = s_pts[i];
+      const int cx = cv_round(p.x), cy = cv_round(p.y);
+      if (cx < 0 || cx >= W || cy < 0 || cy >= H) continue;  // cannot happen after inBorder
+      if (!mask_test(s_mask, words, cx, cy)) {
+        if (lane == 0) {
+          B.cur_pts[kept] = p;
+          B.ids[kept] = s_ids[i];
+          B.cnt[kept] = s_cnt[i];
+        }
+        ++kept;
+        __syncwarp();
+        fill_disc_warp(s_mask, words, W, H, cx, cy, P.min_dist, s_hw);
+      }
+    }
+    if (lane == 0) s_kept = kept;
+  }
+  __syncthreads();
+  for (int i = tid; i < H * words; i += blockDim.x) blocked[i] = s_mask[i];
+  if (tid == 0) {
+    st->n_cur = s_kept;
+    st->stat_after_mask = s_kept;
+  }
+}
+
+void launch_image_set_mask(const TrackParams& P, const TrackBuffers& B, const GfttBuffers& G,
+                           cudaStream_t s, int64_t* launches) {
+  static bool configured = false;
+  if (!configured) {  // the bit mask of the largest supported frame (227 KB budget)
+    cudaFuncSetAttribute(k_image_set_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    configured = true;
+  }
+  launch_pdl(k_image_set_mask, dim3(1), dim3(kSelThreads), select_smem_bytes(P.W, P.H), s, P, B,
+             G.blocked);
+  ++*launches;
+}
+
+// goodFeaturesToTrack's minimum-distance pass (featureselect.cpp): the candidates come best
+// first (keys sorted descending, key 0 = end); one is accepted iff no corner accepted before it
+// lies closer than minDistance (Euclidean, on integer pixel coordinates), until maxCorners.
+// 1024 candidates at a time: all threads test theirs against the corners accepted so far, the
+// ones still alive are compacted in order and warp 0 settles them 32 at a time (the lowest
+// alive lane is accepted, the others are tested against it, and so on).
+// TRACKS: append to the track arrays (ids from next_id, track_cnt 1), update the counters and
+// take the snapshot; otherwise write the corners to out_xy / out_n.
+template <bool TRACKS>
+__global__ void __launch_bounds__(1024)
+k_gftt_pick(TrackParams P, TrackBuffers B, int snap_slot, const unsigned long long* __restrict__ keys,
+            int n_keys, int W, int max_corners, float md2, int spaced, float2* __restrict__ out_xy,
+            int* __restrict__ out_n) {
+  PDL_PROLOGUE();
+  __shared__ int s_warp[33];
+  __shared__ float2 s_acc[kMaxCnt];       // accepted corners (TRACKS: at most max_cnt)
+  __shared__ uint32_t s_cand[1024];
+  __shared__ int s_found, s_end;
+  TrackState* st = B.st;
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const int kept = TRACKS ? st->n_cur : 0;
+  // stage form: max_corners <= 0 = unlimited, which the spaced pass serves up to kMaxCnt
+  int want = TRACKS ? P.max_cnt - kept : (max_corners > 0 ? max_corners : n_keys);
+  if (spaced && want > kMaxCnt) want = kMaxCnt;  // capacity of s_acc (the ABI refuses more)
+  if (tid == 0) s_found = 0, s_end = 0;
+  __syncthreads();
+  if (want > 0) {
+    for (int base = 0; base < n_keys; base += 1024) {
+      const int found0 = s_found;
+      const unsigned long long key = base + tid < n_keys ? keys[base + tid] : 0ull;
+      const bool valid = key != 0ull;
+      const int idx = (int)(key & 0xffffffffull);
+      const int yi = idx / W, xi = idx - yi * W;
+      const float x = (float)xi, y = (float)yi;
+      bool alive = valid;
+      if (alive && spaced) {
+        const int lim = found0 < kMaxCnt ? found0 : kMaxCnt;
+        for (int j = 0; j < lim; ++j) {
+          const float dx = x - s_acc[j].x, dy = y - s_acc[j].y;
+          if (dx * dx + dy * dy < md2) {
+            alive = false;
+            break;
+          }
+        }
+      }
+      int total;
+      const int pos = block_excl_scan_1024(alive ? 1 : 0, s_warp, &total);
+      if (alive) s_cand[pos] = (uint32_t)xi | ((uint32_t)yi << 16);
+      if (!valid && tid == 0) s_end = 1;  // keys are sorted: a zero key ends the candidates
+      if (tid == 1023 && !valid) s_end = 1;
+      __syncthreads();
+      if (warp == 0) {
+        int found = found0;
+        for (int c0 = 0; c0 < total && found < want; c0 += 32) {
+          const bool have = c0 + lane < total;
+          const uint32_t xy = have ? s_cand[c0 + lane] : 0u;
+          const float cx = (float)(xy & 0xffff), cy = (float)(xy >> 16);
+          bool ok = have;
+          if (ok && spaced)  // against the corners accepted earlier in this batch
+            for (int j = found0; j < found && j < kMaxCnt; ++j) {
+              const float dx = cx - s_acc[j].x, dy = cy - s_acc[j].y;
+              if (dx * dx + dy * dy < md2) {
+                ok = false;
+                break;
+              }
+            }
+          uint32_t live = __ballot_sync(0xffffffffu, ok);
+          while (live && found < want) {
+            const int l = __ffs(live) - 1;
+            const float ax = __shfl_sync(0xffffffffu, cx, l), ay = __shfl_sync(0xffffffffu, cy, l);
+            if (lane == 0) {
+              if (found < kMaxCnt) s_acc[found] = make_float2(ax, ay);
+              if (TRACKS) {
+                B.cur_pts[kept + found] = make_float2(ax, ay);
+                B.ids[kept + found] = st->next_id + found;
+                B.cnt[kept + found] = 1;
+              } else {
+                out_xy[found] = make_float2(ax, ay);
+              }
+            }
+            ++found;
+            __syncwarp();
+            bool still = ((live >> lane) & 1u) && lane > l;
+            if (still && spaced) {
+              const float dx = cx - ax, dy = cy - ay;
+              if (dx * dx + dy * dy < md2) still = false;
+            }
+            live = __ballot_sync(0xffffffffu, still);
+          }
+        }
+        if (lane == 0) s_found = found;
+      }
+      __syncthreads();
+      if (s_found >= want || s_end) break;
+    }
+  }
+  __syncthreads();
+  const int found = s_found;
+  if (TRACKS) {
+    if (tid == 0) {
+      st->stat_new = found;
+      st->n_cur = kept + found;
+      st->next_id += found;
+    }
+    if (snap_slot >= 0) {
+      __syncthreads();
+      snapshot_tracks(P, B, snap_slot, kept + found);
+    }
+  } else if (tid == 0) {
+    *out_n = found;
+  }
+}
+
+void launch_gftt_pick_tracks(const TrackParams& P, const TrackBuffers& B, const GfttBuffers& G,
+                             int snap_slot, cudaStream_t s, int64_t* launches) {
+  const float md = (float)P.min_dist;
+  launch_pdl(k_gftt_pick<true>, dim3(1), dim3(1024), 0, s, P, B, snap_slot,
+             (const unsigned long long*)G.keys_sorted, P.W * P.H, P.W, 0, md * md,
+             P.min_dist > 1 ? 1 : 0, (float2*)nullptr, (int*)nullptr);  // distance 1: distinct
+                                                                          // pixels never clash
+  ++*launches;
+}
+
+void launch_gftt_pick_stage(const GfttBuffers& G, int W, int H, int max_corners,
+                            double min_distance, cudaStream_t s, int64_t* launches) {
+  TrackParams P{};
+  TrackBuffers B{};
+  launch_pdl(k_gftt_pick<false>, dim3(1), dim3(1024), 0, s, P, B, -1,
+             (const unsigned long long*)G.keys_sorted, W * H, W, max_corners,
+             (float)(min_distance * min_distance), min_distance > 1.0 ? 1 : 0, G.out_xy, G.out_n);
+  ++*launches;
+}
+
+__global__ void k_right_map_keep(TrackState* st, int restore) {
+  if (restore) st->n_prev_un_r = st->pad[0];
+  else st->pad[0] = st->n_prev_un_r;
+}
+
+void launch_right_map_keep(const TrackBuffers& B, int restore, cudaStream_t s, int64_t* launches) {
+  k_right_map_keep<<<1, 1, 0, s>>>(B.st, restore);
+  ++*launches;
+}
+
 }  // namespace esvio

@@ -253,6 +253,43 @@ class EventFrontEnd:
                                                           C.c_void_p(exchange_stream)),
                   "track_submit_split")
 
+    # ---- frame path (FeatureTracker::trackImage)
+    def _img(self, a):
+        a = np.ascontiguousarray(a, np.uint8)
+        if a.shape != (self.H, self.W):
+            raise ValueError(f"image must be {self.H}x{self.W} uint8")
+        return a
+
+    def track_image(self, cur_time, img_left, img_right=None, pub_this_frame=True):
+        l = self._img(img_left)
+        r = self._img(img_right) if img_right is not None else None
+        self._chk(_capi.lib().esvio_fe_track_image(
+            self._h, float(cur_time), l.ctypes.data, self.W, r.ctypes.data if r is not None else None,
+            self.W, int(bool(pub_this_frame)), C.byref(self._t)), "track_image")
+        return self._unpack()
+
+    def submit_image(self, cur_time, img_left, img_right=None, pub_this_frame=True):
+        l = self._img(img_left)
+        r = self._img(img_right) if img_right is not None else None
+        self._inflight.append((l, r))       # the host frames stay alive until the wait
+        self._chk(_capi.lib().esvio_fe_track_image_submit(
+            self._h, float(cur_time), l.ctypes.data, self.W, r.ctypes.data if r is not None else None,
+            self.W, int(bool(pub_this_frame))), "track_image_submit")
+
+    def stage_good_features(self, img, max_corners, min_distance, mask=None, want_eig=False):
+        a = self._img(img)
+        m = self._img(mask) if mask is not None else None
+        cap = max_corners if max_corners > 0 else self.W * self.H
+        out = np.zeros((max(cap, 1), 2), np.float32)
+        n = C.c_int32()
+        eig = np.empty((self.H, self.W), np.float32) if want_eig else None
+        self._chk(_capi.lib().esvio_fe_stage_good_features(
+            self._h, a.ctypes.data, m.ctypes.data if m is not None else None, int(max_corners),
+            float(min_distance), out.ctypes.data, cap, C.byref(n),
+            eig.ctypes.data if eig is not None else None), "stage_good_features")
+        pts = out[:min(n.value, cap)].copy()
+        return (pts, eig) if want_eig else pts
+
     def reset(self):
         self._chk(_capi.lib().esvio_fe_reset(self._h), "reset")
 

@@ -181,6 +181,23 @@ int esvio_fe_track_submit_mc(esvio_fe *fe, double cur_time, const esvio_events *
                              const esvio_events *right, int32_t pub_this_frame,
                              const esvio_motion *mc);
 
+/* ---- the frame front-end ---- */
+/* replaces FeatureTracker::trackImage(cur_time, img_left, img_right)
+ * (feature_tracker.h:49; feature_tracker.cpp:164-338; call site
+ * stereo_image_tracker_node.cpp:99): forward + full backward pyramidal LK on the previous
+ * frame, Image_setMask (:91-121), cv::goodFeaturesToTrack(img, MAX_CNT_IMG - n, 0.01,
+ * MIN_DIST_IMG, mask) (:228), stereo LK against the right frame, undistortion, velocities.
+ * Images are CV_8UC1, width x height of the config, `stride` bytes per row; config.max_cnt /
+ * min_dist play MAX_CNT_IMG / MIN_DIST_IMG.  right == NULL is img_right.empty() (mono).
+ * Use a handle of its own for frames (the reference runs them in a separate node,
+ * stereo_image_tracker_node.cpp:45).  Results come back through esvio_fe_track_wait. */
+int esvio_fe_track_image(esvio_fe *fe, double cur_time, const uint8_t *left, size_t left_stride,
+                         const uint8_t *right, size_t right_stride, int32_t pub_this_frame,
+                         esvio_tracks *out);
+int esvio_fe_track_image_submit(esvio_fe *fe, double cur_time, const uint8_t *left,
+                                size_t left_stride, const uint8_t *right, size_t right_stride,
+                                int32_t pub_this_frame);
+
 /* ---- groups: several independent stereo streams on one GPU ---- */
 /* S handles of the same configuration whose event stage (binning, SAE update + time surface,
  * pyramids) runs as one batched launch sequence per window -- one k_sae_update_ts launch covers
@@ -291,6 +308,14 @@ int esvio_fe_stage_lk(esvio_fe *fe, const uint8_t *prev_img, const uint8_t *next
  * median_blur_kernel_size set (that allocates the scratch images). */
 int esvio_fe_stage_condition(esvio_fe *fe, const uint8_t *src, int32_t median_ksize,
                              int32_t equalize, uint8_t *dst);
+/* cv::goodFeaturesToTrack(img, max_corners, 0.01, min_distance, mask, blockSize 3) on a host
+ * image (width x height, contiguous); mask NULL or width x height bytes (non-zero = allowed).
+ * *out_n = corners found, the first min(*out_n, capacity) (x, y) pairs go to out_xy; eig
+ * (nullable) receives the cv::cornerMinEigenVal plane.  min_distance > 1 needs
+ * 1 <= max_corners <= 1024. */
+int esvio_fe_stage_good_features(esvio_fe *fe, const uint8_t *img, const uint8_t *mask,
+                                 int32_t max_corners, double min_distance, float *out_xy,
+                                 int32_t capacity, int32_t *out_n, float *eig);
 /* cv::findFundamentalMat(p1, p2, FM_RANSAC, thresh, 0.99, status)
  * (feature_tracker.cpp:935) */
 int esvio_fe_stage_fmat_mask(esvio_fe *fe, const float *p1, const float *p2, int32_t n,

@@ -1859,10 +1859,14 @@ static int track_tail(ora_tracker *t, double cur_time, int pub, int image_mode, 
              out->rvy);
   }
   out->n_right = nrgt;
-  /* prev_un_right_pts_map = cur_un_right_pts_map (:574) -- empty when no left points */
-  t->n_prev_un_r = nrgt;
-  memcpy(t->prev_un_r_ids, idr, sizeof(int) * nrgt);
-  memcpy(t->prev_un_r, unr, sizeof(float) * 2 * nrgt);
+  /* prev_un_right_pts_map = cur_un_right_pts_map (:574) -- empty when no left points; the
+   * whole block is skipped when trackImage gets no right image (:245, :322), which leaves the
+   * map as it was */
+  if (have_right) {
+    t->n_prev_un_r = nrgt;
+    memcpy(t->prev_un_r_ids, idr, sizeof(int) * nrgt);
+    memcpy(t->prev_un_r, unr, sizeof(float) * 2 * nrgt);
+  }
 
   /* state roll (:585-590) */
   memcpy(t->prev_img, t->img[0], N);

@@ -761,3 +761,93 @@ def test_left_right_split_equals_one_handle(fe_mod, W, H, rate, depth):
         left.wait()
     for f in (ref, left, right):
         f.close()
+
+
+# ---- frame path: goodFeaturesToTrack + trackImage ----
+FRAME_SEQ = dict(W=240, H=180, n_frames=6, max_cnt=60, min_dist=14)
+FRAME_CAM = [dict(fx=260.0, fy=261.0, cx=121.5, cy=88.0, k1=-0.05, k2=0.02, p1=1e-3, p2=-5e-4),
+             dict(fx=259.0, fy=260.5, cx=119.0, cy=90.5, k1=-0.04, k2=0.015, p1=-8e-4, p2=3e-4)]
+
+
+def _frame_input(g, name):
+    return {"tex346": lambda: synth.frame_texture(346, 260, 11),
+            "tex640": lambda: synth.frame_texture(640, 480, 12),
+            "noise173": lambda: g["noise173_in"],
+            "flat": lambda: np.full((64, 96), 77, np.uint8)}[name]()
+
+
+@pytest.mark.parametrize("name", ["tex346", "tex640", "noise173", "flat"])
+def test_good_features_match_cv2_golden(fe_mod, ora, golden_frames, name):
+    """cv::cornerMinEigenVal plane bit for bit and cv::goodFeaturesToTrack corner lists (same
+    corners, same order) against the committed cv2 outputs and the oracle."""
+    g = golden_frames
+    img = _frame_input(g, name)
+    H, W = img.shape
+    fe, _ = _mk(fe_mod, W, H)
+    mask = g[f"{name}_mask"]
+    pts, eig = fe.stage_good_features(img, 100, 30.0, None, want_eig=True)
+    ref = ora.corner_min_eigen_val(img)
+    assert np.array_equal(eig, ref), (name, int((eig != ref).sum()))
+    assert np.array_equal(pts, g[f"{name}_gftt_a"]), (name, "a", len(pts))
+    for tag, (n, md, m) in dict(b=(150, 10.0, mask), c=(0, 1.0, None), d=(40, 0.5, mask)).items():
+        got = fe.stage_good_features(img, n, md, m)
+        exp = g[f"{name}_gftt_{tag}"]
+        assert got.shape == exp.shape and np.array_equal(got, exp), (name, tag, got.shape, exp.shape)
+    with pytest.raises(fe_mod.FrontEndError):
+        fe.stage_good_features(img, 0, 5.0)          # spaced and unlimited: refused
+    fe.close()
+
+
+def test_track_image_matches_oracle(fe_mod, ora):
+    """FeatureTracker::trackImage (feature_tracker.cpp:164-338) over six stereo frames (one
+    without a right image) against the oracle, which tests/test_oracle_golden.py pins on the
+    same sequence run through real OpenCV."""
+    s = FRAME_SEQ
+    cfg = synth.default_config(s["W"], s["H"], max_cnt=s["max_cnt"], min_dist=s["min_dist"])
+    cfg["cam"] = FRAME_CAM
+    fe = fe_mod.EventFrontEnd(dict(cfg, max_events_per_window=1024))
+    trk = ora.OracleTracker(cfg)
+    n_right = 0
+    for k, (L, R) in enumerate(synth.stereo_frame_sequence(s["W"], s["H"], s["n_frames"])):
+        right = R if k != 3 else None
+        t = 1.0 + k / 20.0
+        g = fe.track_image(t, L, right, k % 2 == 0)
+        o = trk.track_image(t, L, right, k % 2 == 0)
+        _assert_tracks_agree(g, o, k)
+        assert abs(len(g["id_right"]) - len(o["id_right"])) <= 3, k
+        if k == 3:
+            assert len(g["id_right"]) == 0
+        if k < 2:
+            for key in ("track_cnt", "id_right"):
+                assert np.array_equal(g[key], o[key]), (k, key)
+            for key in ("un_x", "un_y", "ru", "rv"):
+                assert np.abs(g[key] - o[key]).max(initial=0) <= 1e-3, (k, key)
+            assert g["stats"]["n_new"] == o["stats"]["n_new"]
+        n_right += len(g["id_right"])
+        assert np.array_equal(fe.time_surface(0), L)        # the image getter shows the frame
+    assert n_right > 100 and g["track_cnt"].max() == 6
+    fe.close()
+
+
+def test_track_image_pipeline_equals_sync(fe_mod):
+    """Three frames in flight give the results of the synchronous call, bit for bit."""
+    s = FRAME_SEQ
+    cfg = synth.default_config(s["W"], s["H"], max_cnt=s["max_cnt"], min_dist=s["min_dist"],
+                               max_events_per_window=1024)
+    cfg["cam"] = FRAME_CAM
+    a, b = fe_mod.EventFrontEnd(cfg), fe_mod.EventFrontEnd(cfg)
+    frames = synth.stereo_frame_sequence(s["W"], s["H"], 8)
+    sync = [a.track_image(1.0 + k / 20.0, L, R, k % 2 == 0) for k, (L, R) in enumerate(frames)]
+    outs = []
+    for k, (L, R) in enumerate(frames):
+        b.submit_image(1.0 + k / 20.0, L, R, k % 2 == 0)
+        if k >= 2:
+            outs.append(b.wait())
+    outs.append(b.wait())
+    outs.append(b.wait())
+    for k, (x, y) in enumerate(zip(sync, outs)):
+        for key in ("id", "track_cnt", "u", "v", "vx", "vy", "id_right", "ru", "rv", "rvx", "rvy"):
+            assert np.array_equal(x[key], y[key]), (k, key)
+    assert len(sync[-1]["id"]) > 30
+    a.close()
+    b.close()
