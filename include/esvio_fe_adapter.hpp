@@ -89,6 +89,25 @@ class GpuFeatureTracker {
     unpack();
   }
 
+  // FeatureTracker::trackImage(double, const cv::Mat&, const cv::Mat&) (feature_tracker.h:49;
+  // call site stereo_image_tracker_node.cpp:99).  MatT is cv::Mat or anything with
+  // data / step / empty() of a CV_8UC1 image of the configured size; an empty right image is
+  // the mono case (feature_tracker.cpp:245).  Use a tracker object of its own for frames, as
+  // the reference's image node does.
+  template <class MatT>
+  void trackImage(double _cur_time, const MatT& img_left, const MatT& img_right) {
+    const uint8_t* r = img_right.empty() ? nullptr : (const uint8_t*)img_right.data;
+    const int rc = esvio_fe_track_image(fe_, _cur_time, (const uint8_t*)img_left.data,
+                                        (size_t)img_left.step, r, r ? (size_t)img_right.step : 0,
+                                        PUB_THIS_FRAME ? 1 : 0, &out_);
+    if (rc != ESVIO_FE_OK)
+      throw std::runtime_error(std::string("esvio_fe_track_image: ") + esvio_fe_strerror(rc) +
+                               " (" + esvio_fe_last_error(fe_) + ")");
+    prev_time = cur_time;
+    cur_time = _cur_time;
+    unpack();
+  }
+
   void reset() { esvio_fe_reset(fe_); }
 
   // FeatureTracker::gettimesurface() (feature_tracker.cpp:894-897): CV_8U, row-major W x H

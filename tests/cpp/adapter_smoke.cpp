@@ -107,6 +107,35 @@ int main() {
       }
     }
     std::printf("group of 2 == single tracker\n");
+    // frame path: FeatureTracker::trackImage through the same mirror (a tracker of its own, as
+    // in stereo_image_tracker_node.cpp:45), on a blocky texture panning 2 px per frame
+    struct Mat8 {  // the three members of cv::Mat the adapter touches
+      uint8_t* data;
+      size_t step;
+      bool empty() const { return data == nullptr; }
+    };
+    esvio_fe_config icfg = cfg;
+    icfg.max_cnt = 80, icfg.min_dist = 20;
+    esvio::GpuFeatureTracker imageTracker(icfg);
+    const int W = icfg.width, H = icfg.height, BW = W + 64;
+    std::vector<uint8_t> big((size_t)BW * (H + 64));
+    for (int y = 0; y < H + 64; ++y)
+      for (int x = 0; x < BW; ++x) {
+        uint32_t h = (uint32_t)(x / 12) * 2654435761u ^ (uint32_t)(y / 12) * 40503u;
+        h ^= h >> 13, h *= 0x5bd1e995u, h ^= h >> 15;
+        big[(size_t)y * BW + x] = (uint8_t)(40 + h % 180);
+      }
+    for (int k = 0; k < 3; ++k) {
+      Mat8 left{&big[(size_t)(8 + 2 * k) * BW + 8 + 2 * k], (size_t)BW};
+      Mat8 right{&big[(size_t)(8 + 2 * k) * BW + 12 + 2 * k], (size_t)BW};
+      Mat8 none{nullptr, 0};
+      imageTracker.PUB_THIS_FRAME = true;
+      imageTracker.trackImage(0.05 * (k + 1), left, k == 1 ? none : right);
+      if (k == 1 && !imageTracker.ids_right.empty()) return 16;
+    }
+    if (imageTracker.ids.empty()) return 15;
+    std::printf("trackImage: %zu left / %zu right features\n", imageTracker.ids.size(),
+                imageTracker.ids_right.size());
     return 0;
   } catch (const std::exception& e) {
     std::printf("%s\n", e.what());
