@@ -547,6 +547,17 @@ class FeatureTracker:
         """Both overloads of FeatureTracker::trackEvent (feature_tracker.h:51-52):
         `measurements` is the Motion_correction_value of the motion-compensated one."""
         r = self.fe.track(_cur_time, event_left, event_right, self.PUB_THIS_FRAME, measurements)
+        self._take(_cur_time, r)
+
+    def trackImage(self, _cur_time, img_left, img_right=None):
+        """FeatureTracker::trackImage (feature_tracker.h:49): CV_8UC1 frames of the configured
+        size; img_right None (or empty) is the mono case.  Use a tracker of its own for frames."""
+        if img_right is not None and np.size(img_right) == 0:
+            img_right = None
+        r = self.fe.track_image(_cur_time, img_left, img_right, self.PUB_THIS_FRAME)
+        self._take(_cur_time, r)
+
+    def _take(self, _cur_time, r):
         self.prev_time, self.cur_time = self.cur_time, float(_cur_time)
         self.ids, self.track_cnt = r["id"], r["track_cnt"]
         self.cur_pts = np.stack([r["u"], r["v"]], 1)

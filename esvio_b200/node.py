@@ -275,6 +275,104 @@ class StereoEventNode:
         return cloud
 
 
+class ImagePairer(EventPairer):
+    """The depth-1 queues of img_callback_left/right (stereo_image_tracker_node.cpp:36-52) and
+    the pairing step of the image node's sync_process (:217-241): +-1 s, and a left frame EXACTLY
+    one second older than the right one is already thrown (`<=`, unlike the event node's `<`)."""
+
+    def __init__(self, tolerance: float = 1.0):
+        super().__init__(tolerance)
+
+    def poll(self):
+        if not self.left or not self.right:
+            return None
+        tl, tr = self.left[0].stamp, self.right[0].stamp
+        if tl <= tr - self.tol:
+            self.left.popleft()
+            return None
+        if tl > tr + self.tol:
+            self.right.popleft()
+            return None
+        l, r = self.left.popleft(), self.right.popleft()
+        return l, r, l.stamp
+
+
+class ImageMsg:
+    """header.stamp + the CV_8UC1 frame of one sensor_msgs/Image (after getImageFromMsg)."""
+
+    def __init__(self, stamp: float, image):
+        self.stamp = float(stamp)
+        self.image = image
+
+
+class StereoImageNode(StereoEventNode):
+    """handle_stereo_image (stereo_image_tracker_node.cpp:54-183) around any tracker with the
+    reference's names: the same first-frame skip, restart rule, publish-rate gate, cloud
+    packing and first-publish suppression as the event node; the tracker call is
+    trackImage(msg_timestamp, img_left, img_right) (:99).  The node's own CLAHE (`EQUALIZE`,
+    :93-97) is not mirrored."""
+
+    def __init__(self, tracker, freq: int):
+        super().__init__(tracker, freq)
+
+    def handle_stereo_image(self, img_left, img_right, msg_timestamp: float):
+        """Returns the FeatureCloud published for this pair, or None."""
+        if self.first_image_flag:                         # :58-64
+            self.first_image_flag = False
+            self.first_image_time = msg_timestamp
+            self.last_image_time = msg_timestamp
+            return None
+        if msg_timestamp - self.last_image_time > 1.0 or msg_timestamp < self.last_image_time:
+            self.first_image_flag = True                  # :66-76
+            self.last_image_time = 0.0
+            self.pub_count = 1
+            self.restarts += 1
+            return None
+        self.last_image_time = msg_timestamp
+        span = msg_timestamp - self.first_image_time      # frequency control :80-91
+        rate = 1.0 * self.pub_count / span if span != 0.0 else math.inf
+        if round_half_away(rate) <= self.FREQ:
+            pub = True
+            if abs(rate - self.FREQ) < 0.01 * self.FREQ:
+                self.first_image_time = msg_timestamp
+                self.pub_count = 0
+        else:
+            pub = False
+        self.t.PUB_THIS_FRAME = pub
+        self.t.trackImage(msg_timestamp, img_left, img_right)      # :99
+        self.windows_tracked += 1
+        if not pub:
+            return None
+        self.pub_count += 1                               # :113
+        cloud = FeatureCloud(msg_timestamp, pack_feature_cloud(self.t))
+        if not self.init_pub:                             # :172-177
+            self.init_pub = True
+            return None
+        return cloud
+
+
+def replay_images(node: StereoImageNode, left_msgs, right_msgs):
+    """Plays two ImageMsg lists through the image node's queues and pairing step in stamp
+    order (ties: left first), polling after every arrival.  Returns (clouds, overwritten)."""
+    pairer = ImagePairer()
+    clouds = []
+    order = sorted([(m.stamp, 0, i) for i, m in enumerate(left_msgs)]
+                   + [(m.stamp, 1, i) for i, m in enumerate(right_msgs)])
+    for _, side, i in order:
+        if side == 0:
+            pairer.push_left(left_msgs[i])
+        else:
+            pairer.push_right(right_msgs[i])
+        while pairer.left and pairer.right:
+            pair = pairer.poll()
+            if pair is None:
+                continue
+            c = node.handle_stereo_image(pair[0].image, pair[1].image, pair[2])
+            if c is not None:
+                clouds.append(c)
+    return clouds, pairer.dropped
+
+
 def round_half_away(v: float) -> float:
     """C round(): half away from zero (Python's round() is half-to-even)."""
     if math.isinf(v) or math.isnan(v):

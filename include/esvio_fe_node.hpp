@@ -260,5 +260,119 @@ class StereoEventNode {
   int pub_count_ = 1;
 };
 
+// The depth-1 queues of img_callback_left/right (stereo_image_tracker_node.cpp:36-52) and the
+// pairing step of the image node's sync_process (:217-241): +-1 s; a left frame exactly one
+// second older than the right one is already thrown (`<=`, unlike the event node's `<`).
+// MsgT needs a `double stamp`.
+template <class MsgT>
+class ImagePairer {
+ public:
+  void pushLeft(MsgT m) { push(left_, std::move(m)); }
+  void pushRight(MsgT m) { push(right_, std::move(m)); }
+  bool ready() const { return !left_.empty() && !right_.empty(); }
+  bool poll(MsgT* l, MsgT* r, double* msg_timestamp) {
+    if (!ready()) return false;
+    const double tl = left_.front().stamp, tr = right_.front().stamp;
+    if (tl <= tr - 1) {
+      left_.pop_front();
+      return false;
+    }
+    if (tl > tr + 1) {
+      right_.pop_front();
+      return false;
+    }
+    *msg_timestamp = tl;
+    *l = std::move(left_.front());
+    left_.pop_front();
+    *r = std::move(right_.front());
+    right_.pop_front();
+    return true;
+  }
+  int dropped = 0;
+
+ private:
+  void push(std::deque<MsgT>& q, MsgT m) {
+    if (!q.empty()) {
+      q.pop_front();
+      ++dropped;
+    }
+    q.push_back(std::move(m));
+  }
+  std::deque<MsgT> left_, right_;
+};
+
+// handle_stereo_image (stereo_image_tracker_node.cpp:54-183): the same first-frame skip,
+// restart rule, publish-rate gate, cloud packing and first-publish suppression as the event
+// node around trackerData.trackImage(msg_timestamp, img_left, img_right) (:99).  The node's
+// own CLAHE (EQUALIZE, :93-97) is not mirrored.
+template <class TrackerT>
+class StereoImageNode {
+ public:
+  StereoImageNode(TrackerT& tracker, int freq) : t_(tracker), freq_(freq) {}
+  int restarts = 0, frames_tracked = 0;
+
+  template <class MatT>
+  bool handle_stereo_image(const MatT& img_left, const MatT& img_right, double msg_timestamp,
+                           FeatureCloud* cloud) {
+    if (first_image_flag_) {
+      first_image_flag_ = false;
+      first_image_time_ = msg_timestamp;
+      last_image_time_ = msg_timestamp;
+      return false;
+    }
+    if (msg_timestamp - last_image_time_ > 1.0 || msg_timestamp < last_image_time_) {
+      first_image_flag_ = true;
+      last_image_time_ = 0;
+      pub_count_ = 1;
+      ++restarts;
+      return false;
+    }
+    last_image_time_ = msg_timestamp;
+    bool pub;
+    if (std::round(1.0 * pub_count_ / (msg_timestamp - first_image_time_)) <= freq_) {
+      pub = true;
+      if (std::fabs(1.0 * pub_count_ / (msg_timestamp - first_image_time_) - freq_) < 0.01 * freq_) {
+        first_image_time_ = msg_timestamp;
+        pub_count_ = 0;
+      }
+    } else {
+      pub = false;
+    }
+    t_.PUB_THIS_FRAME = pub;
+    t_.trackImage(msg_timestamp, img_left, img_right);
+    ++frames_tracked;
+    if (!pub) return false;
+    ++pub_count_;
+    cloud->stamp = msg_timestamp;
+    cloud->rows.clear();
+    std::set<int> hash_ids;
+    for (size_t j = 0; j < t_.ids.size(); ++j)
+      if (t_.track_cnt[j] > 1) {
+        hash_ids.insert(t_.ids[j]);
+        cloud->rows.push_back({t_.cur_un_pts[j].x, t_.cur_un_pts[j].y, 1.f,
+                               (float)(t_.ids[j] * 2 + 0), t_.cur_pts[j].x, t_.cur_pts[j].y,
+                               t_.pts_velocity[j].x, t_.pts_velocity[j].y});
+      }
+    for (size_t j = 0; j < t_.ids_right.size(); ++j)
+      if (hash_ids.count(t_.ids_right[j]))
+        cloud->rows.push_back({t_.cur_un_right_pts[j].x, t_.cur_un_right_pts[j].y, 1.f,
+                               (float)(t_.ids_right[j] * 2 + 1), t_.cur_right_pts[j].x,
+                               t_.cur_right_pts[j].y, t_.right_pts_velocity[j].x,
+                               t_.right_pts_velocity[j].y});
+    if (!init_pub_) {  // :172-177
+      init_pub_ = true;
+      return false;
+    }
+    return true;
+  }
+
+ private:
+  TrackerT& t_;
+  int freq_;
+  bool first_image_flag_ = true, init_pub_ = false;
+  double first_image_time_ = 0.0, last_image_time_ = 0.0;
+  int pub_count_ = 1;
+};
+
 }  // namespace esvio
 #endif

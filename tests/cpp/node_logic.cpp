@@ -52,6 +52,10 @@ struct StubTracker {
     }
     std::printf("T %.9f nl=%zu nr=%zu pub=%d\n", t, nl, nr, PUB_THIS_FRAME ? 1 : 0);
   }
+  template <class ImgT>
+  void trackImage(double t, const ImgT& l, const ImgT& r) {
+    fill(t, (size_t)l.tag, (size_t)r.tag);
+  }
   void trackEvent(double t, const dvs_msgs::EventArray& l, const dvs_msgs::EventArray& r) {
     fill(t, l.events.size(), r.events.size());
   }
@@ -82,7 +86,56 @@ static std::vector<dvs_msgs::Event> make_stream(uint32_t sec0, uint32_t us0, int
   return v;
 }
 
+// stand-in for one sensor_msgs/Image after getImageFromMsg: a stamp and a tag
+struct ImageMsg {
+  double stamp = 0.0;
+  int tag = 0;
+};
+
+// image node script: 20 Hz stereo frames; right frame 7 is lost; left frame 30 arrives exactly
+// 1 s older than the waiting right frame (thrown by the `<=` rule); a 1.5 s hole after frame 40
+// restarts the node; the last frame goes back in time (second restart)
+static int image_script() {
+  StubTracker trk;
+  esvio::StereoImageNode<StubTracker> node(trk, 10);
+  esvio::ImagePairer<ImageMsg> pairer;
+  const double t0 = 1700000000.0;
+  auto step = [&](bool left, double stamp, int tag) {
+    ImageMsg m;
+    m.stamp = stamp, m.tag = tag;
+    if (left) pairer.pushLeft(m);
+    else pairer.pushRight(m);
+    while (pairer.ready()) {
+      ImageMsg l, r;
+      double ts;
+      if (!pairer.poll(&l, &r, &ts)) {
+        std::printf("D\n");
+        continue;
+      }
+      esvio::FeatureCloud cloud;
+      const bool pub = node.handle_stereo_image(l, r, ts, &cloud);
+      std::printf("H %.9f l=%d r=%d published=%d rows=%zu restarts=%d", ts, l.tag, r.tag, pub ? 1 : 0,
+                  pub ? cloud.rows.size() : 0, node.restarts);
+      if (pub)
+        for (const auto& row : cloud.rows) std::printf(" %g:%g", row.id_cam, row.u);
+      std::printf("\n");
+    }
+  };
+  for (int k = 0; k < 60; ++k) {
+    double tl = t0 + 0.05 * k + (k > 40 ? 1.5 : 0.0);
+    double tr = tl + 0.002;
+    if (k == 30) tr = tl + 1.0;  // left exactly 1 s older than right: left is thrown
+    if (k == 59) tl = tr = t0 + 0.05 * 50;  // back in time
+    step(true, tl, 1000 + k);
+    if (k != 7) step(false, tr, 2000 + k);
+  }
+  std::printf("END dropped=%d restarts=%d tracked=%d\n", pairer.dropped, node.restarts,
+              node.frames_tracked);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'i') return image_script();
   const bool mc = argc > 1 && argv[1][0] == 'm';
   using EA = dvs_msgs::EventArray;
   std::vector<EA> lm, rm;

@@ -39,6 +39,9 @@ class StubTracker:
         self.calls = 0
         self.log = log
 
+    def trackImage(self, t, img_left, img_right):
+        self.trackEvent(t, ([0] * img_left,), ([0] * img_right,))
+
     def trackEvent(self, t, left, right, measurements=None):
         if measurements is not None:
             m = measurements
@@ -165,3 +168,56 @@ def test_cloud_rows_decode_like_the_estimator():
     assert set(fid[cam == 1]) <= set(fid[cam == 0])
     assert (np.diff(np.flatnonzero(cam == 0)) == 1).all() and cam[0] == 0
     assert (np.asarray(t.track_cnt)[np.isin(t.ids, fid[cam == 0])] > 1).all()
+
+
+def _py_image_trace():
+    log = []
+    trk = StubTracker(log)
+    nd = node.StereoImageNode(trk, 10)
+    pairer = node.ImagePairer()
+    t0 = 1700000000.0
+
+    def step(left, stamp, tag):
+        m = node.ImageMsg(stamp, tag)           # the stand-in "image" is its tag
+        (pairer.push_left if left else pairer.push_right)(m)
+        while pairer.left and pairer.right:
+            pair = pairer.poll()
+            if pair is None:
+                log.append("D")
+                continue
+            l, r, ts = pair
+            c = nd.handle_stereo_image(l.image, r.image, ts)
+            line = "H %.9f l=%d r=%d published=%d rows=%d restarts=%d" % (
+                ts, l.image, r.image, int(c is not None), len(c.rows) if c is not None else 0, nd.restarts)
+            if c is not None:
+                line += "".join(" %g:%g" % (row[3], row[4]) for row in c.rows)
+            log.append(line)
+
+    for k in range(60):
+        tl = t0 + 0.05 * k + (1.5 if k > 40 else 0.0)
+        tr = tl + 0.002
+        if k == 30:
+            tr = tl + 1.0
+        if k == 59:
+            tl = tr = t0 + 0.05 * 50
+        step(True, tl, 1000 + k)
+        if k != 7:
+            step(False, tr, 2000 + k)
+    log.append("END dropped=%d restarts=%d tracked=%d" % (pairer.dropped, nd.restarts, nd.windows_tracked))
+    return log
+
+
+def test_cpp_and_python_image_node_agree():
+    """handle_stereo_image + the image node's pairing step (stereo_image_tracker_node.cpp:54-183,
+    217-241): the C++ header and the Python twin print the same decision trace on a scripted
+    stream with a lost right frame, a left frame exactly 1 s older than the right one (thrown by
+    the image node's `<=`), a 1.5 s hole (restart) and a frame that goes back in time."""
+    cpp = [l for l in _cpp_trace("i") if not l.startswith("T ")]
+    py = [l for l in _py_image_trace() if not l.startswith("T ")]
+    assert len(cpp) == len(py), (len(cpp), len(py), cpp[:5], py[:5])
+    for a, b in zip(cpp, py):
+        assert a == b, (a, b)
+    assert sum(l == "D" for l in py) >= 1                     # the `<=` throw happened
+    assert py[-1].startswith("END") and "restarts=2" in py[-1]
+    hs = [l for l in py if l.startswith("H ")]
+    assert "published=0" in hs[0] and sum("published=1" in l for l in hs) >= 15
