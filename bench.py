@@ -12,6 +12,9 @@ N > 1: every rank runs its own independent stereo stream (weak scaling, SURVEY.m
 "independent streams") and the ranks all-gather their packed track records once per window
 over NCCL.  One JSON line is printed by rank 0.
 
+At N = 1 the line also carries `batched` (a group of streams on the one GPU) and `frames`
+(FeatureTracker::trackImage on synthetic stereo frames, SURVEY.md 8f rank 4).
+
   torchrun --nproc-per-node 2 bench.py --split-lr [--workload W]   one stream split by camera
       over 2 GPUs, with the same windows on one GPU timed beside it
 """
@@ -334,6 +337,70 @@ def main_split(args):
     dist.destroy_process_group()
 
 
+def frames_leg(width, height, device_id, n_frames=48, cpu_frames=16):
+    """Extra record at N = 1: FeatureTracker::trackImage (SURVEY.md 8f rank 4) on synthetic stereo
+    frames of the workload's resolution through esvio_fe_track_image_submit / _wait, three frames
+    in flight, host frames copied inside the timed region; every 2nd frame is a publish frame
+    (Image_setMask + goodFeaturesToTrack).  CPU beside it: the oracle's trackImage with OpenCV
+    LK, 1 thread.  Never raises: a failure is reported in the record."""
+    rec = {"what": "trackImage, stereo frames/s", "width": width, "height": height}
+    try:
+        import torch
+        from esvio_b200 import frontend
+        mc, md = (150, 10) if width < 600 else (175, 40)   # config/esvio, config/esvio_DSEC
+        cfg = synth.default_config(width, height, max_cnt=mc, min_dist=md)
+        rec.update(max_cnt_img=mc, min_dist_img=md, frames=n_frames, pub_every=2)
+        warm = 4
+        frames = synth.stereo_frame_sequence(width, height, n_frames + warm)
+        fe = frontend.EventFrontEnd(dict(cfg, device_id=device_id, max_events_per_window=1024))
+        ext = torch.cuda.ExternalStream(fe.stream(), device=torch.device("cuda", device_id))
+        for k in range(warm):
+            fe.track_image(1.0 + k / 20.0, frames[k][0], frames[k][1], k % 2 == 0)
+        torch.cuda.synchronize()
+        launches0 = fe.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(ext)
+        waited, last = 0, (0, 0)
+        for k in range(warm, warm + n_frames):
+            fe.submit_image(1.0 + k / 20.0, frames[k][0], frames[k][1], k % 2 == 0)
+            if k - warm >= 2:
+                last = fe.wait(unpack=False)
+                waited += 1
+        while waited < n_frames:
+            last = fe.wait(unpack=False)
+            waited += 1
+        e1.record(ext)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        rec.update(value=n_frames / (ms * 1e-3), unit="stereo frames/s", ms_per_frame=ms / n_frames,
+                   wall_ms_per_frame=wall_ms / n_frames,
+                   gpu_launches=int(fe.kernel_launches() - launches0),
+                   h2d_bytes_per_frame=2 * width * height,
+                   tracks_last_frame={"left": int(last[0]), "right": int(last[1])})
+        fe.close()
+        try:
+            from oracle import oracle as ora   # CPU leg of the bench: the checker as a baseline
+            ora.build()
+            trk = ora.OracleTracker(cfg, use_cv2=True, cv2_threads=1)
+            n_cpu = min(cpu_frames, n_frames)
+            for k in range(2):
+                trk.track_image(1.0 + k / 20.0, frames[k][0], frames[k][1], k % 2 == 0)
+            t0 = time.perf_counter()
+            for k in range(2, 2 + n_cpu):
+                trk.track_image(1.0 + k / 20.0, frames[k][0], frames[k][1], k % 2 == 0)
+            dt = time.perf_counter() - t0
+            rec["cpu_baseline"] = {"value": n_cpu / dt, "unit": "stereo frames/s", "cores": 1,
+                                   "kind": "port", "sample": f"{n_cpu} frames, oracle trackImage "
+                                   "(C goodFeaturesToTrack restatement + cv2 LK)"}
+        except Exception as e:  # noqa: BLE001
+            rec["cpu_baseline"] = {"error": repr(e)[:200]}
+    except Exception as e:  # noqa: BLE001
+        rec["error"] = repr(e)[:300]
+    return rec
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -651,6 +718,8 @@ def main_ours(args):
         }
         if batched is not None:
             line["batched"] = batched
+        if world == 1 and not args.no_frames:
+            line["frames"] = frames_leg(W_, H_, local)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if parity is not None:
@@ -672,6 +741,7 @@ def main():
     ap.add_argument("--batch-streams", type=int, default=8,
                     help="streams of the extra batched leg at N=1 (esvio_fe_group); 1 disables it")
     ap.add_argument("--batch-steps", type=int, default=60)
+    ap.add_argument("--no-frames", action="store_true", help="skip the trackImage record")
     ap.add_argument("--split-lr", action="store_true",
                     help="2 ranks: one stereo stream split by camera (SURVEY.md 8e row 2)")
     args = ap.parse_args()
