@@ -197,3 +197,46 @@ def test_sae_update_mc_gates(ora):
     assert not all(np.array_equal(a, b) for a, b in zip(s.planes(), plain.planes()))
     # same number of events landed, only somewhere else
     assert (s.planes()[2] > 0).sum() + (s.planes()[3] > 0).sum() > 0
+
+
+# ---- cv::goodFeaturesToTrack restatement (frame path) ----
+def _square_image(size=48, squares=((12, 12, 12, 200),)):
+    img = np.zeros((size, size), np.uint8)
+    for x0, y0, s, v in squares:
+        img[y0:y0 + s, x0:x0 + s] = v
+    return img
+
+
+def test_good_features_find_the_corners_of_a_square(ora):
+    """A bright square on black has exactly four minimum-eigenvalue maxima, one per corner;
+    edges (one large eigenvalue only) and flat areas give nothing."""
+    img = _square_image()
+    pts = ora.good_features_to_track(img, 10, 0.01, 5.0)
+    assert len(pts) == 4
+    want = np.array([[11.5, 11.5], [23.5, 11.5], [11.5, 23.5], [23.5, 23.5]])
+    d = np.abs(pts[:, None, :] - want[None, :, :]).max(2)          # Chebyshev distance
+    assert (d.min(0) <= 1.0).all() and (d.min(1) <= 1.0).all()
+    eig = ora.corner_min_eigen_val(img)
+    assert eig[18, 12] < 1e-3 * eig.max() and eig[5, 5] == 0.0      # edge midpoint, flat area
+    assert len(ora.good_features_to_track(np.full((40, 40), 9, np.uint8), 10, 0.01, 5.0)) == 0
+
+
+def test_good_features_mask_quality_cap_and_spacing(ora):
+    img = _square_image(64, ((8, 8, 12, 200), (40, 40, 12, 12)))     # strong and weak square
+    strong = ora.good_features_to_track(img, 0, 0.01, 1.0)
+    # quality 0.01: the weak square's corners ((12/200)^2 of the strong ones) stay below 1 % of max
+    assert len(strong) == 4 and strong.max() < 30
+    both = ora.good_features_to_track(img, 0, 1e-5, 1.0)
+    assert len(both) == 8 and (both[:4].max() < 30) and (both[4:].min() > 30)   # best first
+    # mask: only pixels with a non-zero mask may become corners, and the maximum is taken
+    # under the mask, so the weak square alone passes the 1 % test again
+    mask = np.zeros_like(img)
+    mask[32:, 32:] = 255
+    weak = ora.good_features_to_track(img, 0, 0.01, 1.0, mask)
+    assert len(weak) == 4 and weak.min() > 30
+    # maxCorners cuts the sorted list; a large minimum distance keeps one corner per square
+    assert np.array_equal(ora.good_features_to_track(img, 2, 1e-5, 1.0), both[:2])
+    far = ora.good_features_to_track(img, 0, 1e-5, 20.0)
+    assert len(far) == 2 and np.array_equal(far[0], both[0])
+    # min distance < 1: no spacing rule at all
+    assert np.array_equal(ora.good_features_to_track(img, 0, 1e-5, 0.5), both)
