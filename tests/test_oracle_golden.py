@@ -176,3 +176,56 @@ def test_track_image_matches_cv2_sequence(ora, golden_frames):
         if k == 3:
             assert len(out["id_right"]) == 0
     assert len(g["seq5_id"]) > 40 and g["seq5_track_cnt"].max() == 6
+
+
+def test_good_features_random_images_match_live_cv2(ora):
+    """Beyond the committed goldens: where cv2 is importable (it is in this image), the oracle's
+    goodFeaturesToTrack is compared with it on seeded random images of awkward sizes, with random
+    masks, minimum distances and corner caps.  Skipped without cv2."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4242)
+    for trial in range(24):
+        H, W = int(rng.integers(8, 140)), int(rng.integers(8, 200))
+        img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        if trial % 3:
+            img = cv2.GaussianBlur(img, (5, 5), 1.0 + trial % 4)
+        mask = None
+        if trial % 2:
+            mask = np.full((H, W), 255, np.uint8)
+            for _ in range(6):
+                cv2.circle(mask, (int(rng.integers(0, W)), int(rng.integers(0, H))), 7, 0, -1)
+        md = float(rng.choice([0.5, 1.0, 3.0, 10.0, 25.0]))
+        n = int(rng.choice([0, 5, 50, 150]))
+        assert np.array_equal(ora.corner_min_eigen_val(img), cv2.cornerMinEigenVal(img, 3, ksize=3)), trial
+        ref = cv2.goodFeaturesToTrack(img, n, 0.01, md, mask=mask)
+        ref = np.zeros((0, 2), np.float32) if ref is None else ref.reshape(-1, 2)
+        got = ora.good_features_to_track(img, n, 0.01, md, mask)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (trial, H, W, md, n)
+
+
+@pytest.mark.parametrize("W,H,seed,max_cnt,min_dist", [(346, 260, 21, 150, 10), (200, 152, 22, 40, 25)])
+def test_track_image_other_sequences_match_live_cv2(ora, W, H, seed, max_cnt, min_dist):
+    """trackImage on further sequences (the shipped 346x260 / 150 / 10 configuration among them)
+    against the cv2-driven control flow of tests/golden/make_golden_frames.py.  Skipped without
+    cv2."""
+    pytest.importorskip("cv2")
+    import importlib.util
+    import os
+    from esvio_b200 import synth
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_frames.py")
+    spec = importlib.util.spec_from_file_location("make_golden_frames", path)
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    cfg = synth.default_config(W, H, max_cnt=max_cnt, min_dist=min_dist)
+    cfg["cam"] = FRAME_CAM
+    ref = mg.TrackImageCv2(W, H, max_cnt, min_dist, FRAME_CAM)
+    trk = ora.OracleTracker(cfg)
+    for k, (L, R) in enumerate(synth.stereo_frame_sequence(W, H, 7, seed=seed)):
+        right = None if k == 4 else R
+        exp = ref.track(L, right, pub=(k % 3 != 1))
+        out = trk.track_image(2.0 + k / 30.0, L, right, k % 3 != 1)
+        for key in ("id", "track_cnt", "id_right"):
+            assert np.array_equal(out[key], exp[key]), (k, key)
+        for key in ("u", "v", "ru", "rv"):
+            assert np.abs(out[key] - exp[key]).max(initial=0) <= 1e-3, (k, key)
+    assert len(out["id"]) > max_cnt // 2
