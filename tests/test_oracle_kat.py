@@ -240,3 +240,69 @@ def test_good_features_mask_quality_cap_and_spacing(ora):
     assert len(far) == 2 and np.array_equal(far[0], both[0])
     # min distance < 1: no spacing rule at all
     assert np.array_equal(ora.good_features_to_track(img, 0, 1e-5, 0.5), both)
+
+
+def test_time_window_shard_rule_reproduces_the_sequential_sae(ora):
+    """SURVEY.md 8e row 3 (time-window shard), stated and checked on the oracle: the acceptance
+    test of createSAE (event_detector.cc:157) reads only `sae_latest`, and `sae_latest` after a
+    window is "last event time per pixel and polarity".  So window k can be processed on its
+    own rank from a carry-in of `sae_latest` alone (an exclusive "last non-empty" scan of the
+    ranks' local last-event planes), and `sae` follows by an inclusive scan of the per-window
+    accepted times.  The planes and the time surface after every window must equal the
+    sequential ones."""
+    from esvio_b200 import synth
+    W, H, n_win = 346, 260, 4
+    s = synth.StereoEventStream(W, H, 1.0e6)
+    wins = [s.stereo_window(k)[0] for k in range(n_win)]
+    n = W * H
+
+    def view(sae, which, k):
+        arr = getattr(sae._h.contents, which)[k]
+        return np.ctypeslib.as_array(arr, shape=(n,))
+
+    # sequential reference
+    seq = ora.Sae(W, H)
+    seq_states = []
+    for x, y, t, p in (w[:4] for w in wins):
+        seq.update(x, y, t, p)
+        seq_states.append((seq.planes(), seq.time_surface(float(t[-1]))))
+
+    # phase A (every rank on its own): local last-event time per pixel and polarity
+    local_latest = []
+    for x, y, t, p in (w[:4] for w in wins):
+        ll = np.zeros((2, n))
+        idx = y.astype(np.int64) * W + x
+        for pol in (0, 1):
+            m = p == pol
+            np.maximum.at(ll[pol], idx[m], t[m])          # times ascend: max = last
+        local_latest.append(ll)
+    # phase B: exclusive "last non-empty" scan -> carry-in of sae_latest for every rank
+    carry, acc = [], np.zeros((2, n))
+    for ll in local_latest:
+        carry.append(acc.copy())
+        acc = np.where(ll > 0, ll, acc)
+    # phase C (every rank on its own): the normal update from (latest = carry, sae = sentinel)
+    SENT = -1.0
+    accepted = []
+    for k, (x, y, t, p) in enumerate(w[:4] for w in wins):
+        r = ora.Sae(W, H)
+        for pol in (0, 1):
+            view(r, "latest", pol)[:] = carry[k][pol]
+            view(r, "sae", pol)[:] = SENT
+        r.update(x, y, t, p)
+        pl = r.planes()
+        accepted.append(np.stack([pl[0].ravel(), pl[1].ravel()]))
+        # sae_latest after the window needs no further exchange
+        for pol in (0, 1):
+            assert np.array_equal(pl[2 + pol], seq_states[k][0][2 + pol]), (k, pol)
+    # phase D: inclusive scan of the accepted times -> sae after every window, then the surface
+    sae_acc = np.zeros((2, n))
+    for k in range(n_win):
+        sae_acc = np.where(accepted[k] != SENT, accepted[k], sae_acc)
+        for pol in (0, 1):
+            assert np.array_equal(sae_acc[pol].reshape(H, W), seq_states[k][0][pol]), (k, pol)
+        r = ora.Sae(W, H)
+        for pol in (0, 1):
+            view(r, "sae", pol)[:] = sae_acc[pol]
+        t_ref = float(wins[k][2][-1])
+        assert np.array_equal(r.time_surface(t_ref), seq_states[k][1]), k
