@@ -2,9 +2,13 @@
 handle_stereo_event -> feature clouds, all through the GPU tracker.
 
   python -m esvio_b200.replay [--workload stereo_davis346_1mevs] [--windows 30] [--npz rec.npz]
+  python -m esvio_b200.replay --frames [--windows 40] [--npz frames.npz]
 
 `--npz` replays a recording with arrays lx, ly, lt, lp, rx, ry, rt, rp (time-ascending,
-seconds); without it the synthetic stream of the named workload is used.  Prints one JSON line.
+seconds); without it the synthetic stream of the named workload is used.  `--frames` replays
+stereo frames instead (image pairing step -> handle_stereo_image -> trackImage, SURVEY.md 8f rank
+4): arrays left[k], right[k] (uint8, H x W), stamps_left, stamps_right, or synthetic frames at
+20 Hz of the workload's resolution.  Prints one JSON line.
 """
 from __future__ import annotations
 
@@ -26,15 +30,56 @@ def synthetic_recording(name: str, windows: int):
     return w, cat(L), cat(R)
 
 
+def frame_messages(args):
+    """(width, height, freq, left ImageMsg list, right ImageMsg list)"""
+    w = synth.WORKLOADS[args.workload]
+    if args.npz:
+        z = np.load(args.npz)
+        L, R = z["left"], z["right"]
+        tl, tr = z["stamps_left"], z["stamps_right"]
+        H, W = L.shape[1:]
+    else:
+        W, H = w["width"], w["height"]
+        seq = synth.stereo_frame_sequence(W, H, args.windows)
+        L, R = [f[0] for f in seq], [f[1] for f in seq]
+        tl = 1.7e9 + 0.05 * np.arange(len(L))
+        tr = tl + 0.002
+    lm = [node.ImageMsg(t, img) for t, img in zip(tl, L)]
+    rm = [node.ImageMsg(t, img) for t, img in zip(tr, R)]
+    return W, H, w["freq"], lm, rm
+
+
+def replay_frames(args, frontend):
+    W, H, freq, lm, rm = frame_messages(args)
+    mc, md = (150, 10) if W < 600 else (175, 40)     # config/esvio, config/esvio_DSEC
+    cfg = synth.default_config(W, H, max_cnt=mc, min_dist=md)
+    cfg["max_events_per_window"] = 1024
+    ft = frontend.FeatureTracker(cfg)
+    nd = node.StereoImageNode(ft, freq)
+    t0 = time.perf_counter()
+    clouds, dropped = node.replay_images(nd, lm, rm)
+    dt = time.perf_counter() - t0
+    print(json.dumps({
+        "frames": [len(lm), len(rm)], "width": W, "height": H, "frames_tracked": nd.windows_tracked,
+        "clouds_published": len(clouds),
+        "rows_last_cloud": int(len(clouds[-1].rows)) if clouds else 0, "queue_overwrites": dropped,
+        "restarts": nd.restarts, "tracking_s": dt,
+        "frames_per_s_sync_call": nd.windows_tracked / max(dt, 1e-9)}))
+    ft.fe.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="stereo_davis346_1mevs", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--windows", type=int, default=30)
     ap.add_argument("--npz", default=None)
     ap.add_argument("--frequency", type=float, default=30.0, help="re-windowing rate (EventMessageEditor: 30)")
+    ap.add_argument("--frames", action="store_true", help="replay stereo frames through trackImage")
     args = ap.parse_args()
     from . import frontend  # needs libesvio_fe.so and a B200: there is no CPU path
 
+    if args.frames:
+        return replay_frames(args, frontend)
     w, left, right = synthetic_recording(args.workload, args.windows)
     if args.npz:
         z = np.load(args.npz)

@@ -221,3 +221,27 @@ def test_cpp_and_python_image_node_agree():
     assert py[-1].startswith("END") and "restarts=2" in py[-1]
     hs = [l for l in py if l.startswith("H ")]
     assert "published=0" in hs[0] and sum("published=1" in l for l in hs) >= 15
+
+
+def test_replay_frames_host_logic_with_a_stub_tracker():
+    """esvio_b200.replay --frames without a GPU: the message builder and replay_images around a
+    stub tracker (every frame reaches trackImage once, in order; first pair only arms the node)."""
+    import argparse
+    from esvio_b200 import replay
+    args = argparse.Namespace(workload="stereo_davis346_1mevs", npz=None, windows=12)
+    W, H, freq, lm, rm = replay.frame_messages(args)
+    assert (W, H, freq) == (346, 260, 15) and len(lm) == len(rm) == 12
+    assert lm[0].image.shape == (260, 346) and lm[0].image.dtype == np.uint8
+
+    class Stub(StubTracker):
+        def trackImage(self, t, img_left, img_right):
+            assert img_left.shape == (260, 346) and img_right.shape == (260, 346)
+            self.trackEvent(t, ([0] * 7,), ([0] * 5,))
+
+    log = []
+    nd = node.StereoImageNode(Stub(log), freq)
+    clouds, dropped = node.replay_images(nd, lm, rm)
+    assert dropped == 0 and nd.windows_tracked == 11 and nd.restarts == 0
+    stamps = [float(l.split()[1]) for l in log if l.startswith("T ")]
+    assert stamps == sorted(stamps) and len(stamps) == 11
+    assert 4 <= len(clouds) <= 10 and all(c.rows.shape[1] == 8 for c in clouds)
