@@ -719,13 +719,15 @@ k_image_set_mask(TrackParams P, TrackBuffers B, uint32_t* __restrict__ blocked) 
 
 void launch_image_set_mask(const TrackParams& P, const TrackBuffers& B, const GfttBuffers& G,
                            cudaStream_t s, int64_t* launches) {
-  static bool configured = false;
-  if (!configured) {  // the bit mask of the largest supported frame (227 KB budget)
-    cudaFuncSetAttribute(k_image_set_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    configured = true;
-  }
-  launch_pdl(k_image_set_mask, dim3(1), dim3(kSelThreads), select_smem_bytes(P.W, P.H), s, P, B,
-             G.blocked);
+  // the W x H bit mask lives in dynamic shared memory (38 KB at 640x480); raise the kernel's
+  // limit when a larger frame than any before comes along
+  static size_t configured = 48 * 1024 - 24 * 1024;  // default limit minus the static arrays
+  const size_t bytes = select_smem_bytes(P.W, P.H);
+  if (bytes > configured &&
+      cudaFuncSetAttribute(k_image_set_mask, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)bytes) == cudaSuccess)
+    configured = bytes;
+  launch_pdl(k_image_set_mask, dim3(1), dim3(kSelThreads), bytes, s, P, B, G.blocked);
   ++*launches;
 }
 
