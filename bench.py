@@ -353,6 +353,21 @@ def frames_leg(width, height, device_id, n_frames=48, cpu_frames=16):
         warm = 4
         frames = synth.stereo_frame_sequence(width, height, n_frames + warm)
         fe = frontend.EventFrontEnd(dict(cfg, device_id=device_id, max_events_per_window=1024))
+        # host frames in pinned memory (esvio_fe_host_alloc), as a driver's DMA buffers would be
+        import ctypes
+        lib, pinned = frontend._capi.lib(), []
+
+        def pin(a):
+            ptr = lib.esvio_fe_host_alloc(a.nbytes)
+            if not ptr:
+                return a
+            pinned.append(ptr)
+            v = np.frombuffer((ctypes.c_uint8 * a.nbytes).from_address(ptr), np.uint8).reshape(a.shape)
+            v[:] = a
+            return v
+
+        frames = [(pin(l), pin(r)) for l, r in frames]
+        rec["host_frames"] = "pinned" if pinned else "pageable"
         ext = torch.cuda.ExternalStream(fe.stream(), device=torch.device("cuda", device_id))
         for k in range(warm):
             fe.track_image(1.0 + k / 20.0, frames[k][0], frames[k][1], k % 2 == 0)
@@ -380,6 +395,9 @@ def frames_leg(width, height, device_id, n_frames=48, cpu_frames=16):
                    h2d_bytes_per_frame=2 * width * height,
                    tracks_last_frame={"left": int(last[0]), "right": int(last[1])})
         fe.close()
+        frames = [(np.array(l), np.array(r)) for l, r in frames]   # the CPU leg reads copies
+        for ptr in pinned:
+            lib.esvio_fe_host_free(ptr)
         try:
             from oracle import oracle as ora   # CPU leg of the bench: the checker as a baseline
             ora.build()
