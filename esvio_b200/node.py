@@ -263,7 +263,8 @@ class StereoEventNode:
             self.t.trackEvent(t_last, event_left.events, event_right.events)          # :193
         else:
             m = self.motion.assemble(float(event_left.t[0]), event_left.stamp)       # :195-252
-            self.t.trackEvent(msg_timestamp, event_left.events, event_right.events, m)  # :254
+            # :254 passes msg_timestamp_left (= t_last, :190); the header stamp is only m["t1"]
+            self.t.trackEvent(t_last, event_left.events, event_right.events, m)
         self.windows_tracked += 1
         if not pub:
             return None

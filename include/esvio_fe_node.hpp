@@ -244,9 +244,11 @@ class StereoEventNode {
 
  private:
   template <class EA, class T = TrackerT>
-  auto track_mc(double, double msg_timestamp, const EA& l, const EA& r, const esvio_motion& mc, int)
+  auto track_mc(double t_last, double, const EA& l, const EA& r, const esvio_motion& mc, int)
       -> decltype(std::declval<T&>().trackEvent(0.0, l, r, mc), void()) {
-    t_.trackEvent(msg_timestamp, l, r, mc);  // node.cpp:254 passes the header stamp here
+    // stereo_event_tracker_node.cpp:190,254: msg_timestamp_left = events.back().ts, the same
+    // clock as the plain call; the header stamp only travels inside mc.t1 (:197,202)
+    t_.trackEvent(t_last, l, r, mc);
   }
   template <class EA>
   void track_mc(double t_last, double, const EA& l, const EA& r, const esvio_motion&, long) {

@@ -245,3 +245,40 @@ def test_replay_frames_host_logic_with_a_stub_tracker():
     stamps = [float(l.split()[1]) for l in log if l.startswith("T ")]
     assert stamps == sorted(stamps) and len(stamps) == 11
     assert 4 <= len(clouds) <= 10 and all(c.rows.shape[1] == 8 for c in clouds)
+
+
+@pytest.mark.parametrize("mc", [False, True])
+def test_track_event_clock_is_the_last_left_event(mc):
+    """Written from the reference, not from the other twin: stereo_event_tracker_node.cpp:190
+    `msg_timestamp_left = event_left.events.back().ts.toSec()` is what BOTH trackEvent calls get
+    (:193 and :254); the header stamp only travels as t_left_1 inside the measurements
+    (:197,202) and as the cloud's stamp (:280)."""
+    log = []
+    trk = StubTracker(log)
+    nd = node.StereoEventNode(trk, 15, do_motion_correction=mc)
+    if mc:
+        nd.motion.push_imu(node.Imu(1700000000.0, (0.1, 0.2, 0.3), (0, 0, 0)))
+    x, y, t, p = _stream(1700000000, 100, 4000, 25, 10 ** 9, 0)
+    stamps, lasts = [], []
+    for k in range(4):
+        sl = slice(1000 * k, 1000 * (k + 1))
+        stamp = float(t[sl][-1]) + 0.004            # header stamp = window end, after the last event
+        msg = node.EventArray(stamp, x[sl], y[sl], t[sl], p[sl])
+        nd.handle_stereo_event(msg, msg, stamp)
+        if k:                                       # the first pair only arms the node
+            stamps.append(stamp)
+            lasts.append(float(t[sl][-1]))
+    times = [float(l.split()[1]) for l in log if l.startswith("T ")]
+    assert times == pytest.approx(lasts, abs=1e-9) and len(times) == 3
+    assert all(abs(a - b) > 1e-3 for a, b in zip(times, stamps))
+    if mc:
+        t1 = [float(l.split("t1=")[1]) for l in log if l.startswith("M ")]
+        assert t1 == pytest.approx(stamps, abs=1e-9)
+
+
+def test_cpp_node_hands_the_same_clock_with_and_without_motion_compensation():
+    """The C++ twin on the same script: the `T <time>` lines (the clock trackEvent got) must not
+    depend on Do_motion_correction (node.cpp:190 feeds both :193 and :254)."""
+    plain = [l.split()[1] for l in _cpp_trace(None) if l.startswith("T ")]
+    mc = [l.split()[1] for l in _cpp_trace("m") if l.startswith("T ")]
+    assert plain == mc and len(plain) > 20
