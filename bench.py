@@ -8,12 +8,19 @@ stereo LK) on synthetic stereo event streams (BASELINE.json metric).
 A "step" is one window (1/30 s of stream time) of one stereo pair: both cameras' events go
 through createSAE/time surface, the left camera through corner detection, then temporal and
 stereo LK (FeatureTracker::trackEvent, feature_tracker/src/feature_tracker.cpp:340-603).
-N > 1: every rank runs its own independent stereo stream (weak scaling, SURVEY.md 8e
-"independent streams") and the ranks all-gather their packed track records once per window
-over NCCL.  One JSON line is printed by rank 0.
 
-At N = 1 the line also carries `batched` (a group of streams on the one GPU) and `frames`
-(FeatureTracker::trackImage on synthetic stereo frames, SURVEY.md 8f rank 4).
+Workload: N = 1 runs BASELINE.json configs[2] (stereo 640x480 @ 5 Mev/s per camera, the
+configuration north_star quotes its target on); N > 1 runs configs[4]'s stream (640x480 @
+10 Mev/s per camera), one independent stereo stream per rank (weak scaling, SURVEY.md 8e
+"independent streams"), the packed track records all-gathered over NCCL on publish windows.
+One JSON line is printed by rank 0.  `config` is identical in both arms.
+
+Extra records on the N = 1 line: `rigid_scene` (the same workload on a scene with ONE epipolar
+geometry, both arms: the survey's scene of 64 independent movers makes the CPU arm's F-RANSAC
+run its full iteration budget), `sync` (the synchronous drop-in call), `secondary`
+(configs[1]) and `scale_base` (configs[4]'s stream on one GPU: the denominator of the scaling
+curve), `batched` (a group of streams on the one GPU, where the roofline kernel is measured),
+`frames` (FeatureTracker::trackImage, SURVEY.md 8f rank 4).
 
   torchrun --nproc-per-node 2 bench.py --split-lr [--workload W]   one stream split by camera
       over 2 GPUs, with the same windows on one GPU timed beside it
@@ -38,12 +45,18 @@ from esvio_b200 import shard, synth  # noqa: E402
 
 METRIC = "Mevents/s through time-surface+stereo LK"
 UNIT = "Mevents/s"
-DEFAULT_WORKLOAD = "stereo_davis346_1mevs"  # BASELINE.json configs[1]
-L2_BYTES = 126 * 1024 * 1024
+WORKLOAD_N1 = "stereo_vga_5mevs"      # BASELINE.json configs[2]: the north-star configuration
+WORKLOAD_NX = "stereo_vga_10mevs"     # configs[4]: one of the 8 streams, per rank
+WORKLOAD_SECONDARY = "stereo_davis346_1mevs"  # configs[1]
+DEPTH = 3  # windows in flight: event stage | temporal stage | stereo stage
 
 
 def env_int(k, d):
     return int(os.environ.get(k, d))
+
+
+def default_workload(world):
+    return WORKLOAD_N1 if world == 1 else WORKLOAD_NX
 
 
 def peaks():
@@ -54,14 +67,16 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
+def ncu_traffic(key):
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_sae_update_ts launch, from the
-    committed `ncu --set full` capture of this workload (profiles/r1_k1_ncu_full.json)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_k1_ncu_full.json")) as f:
-            return int(json.load(f)[workload]["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    committed `ncu --set full` capture (profiles/r2_k1_ncu_full.json, else round 1's)."""
+    for name in ("r2_k1_ncu_full.json", "r1_k1_ncu_full.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return int(json.load(f)[key]["traffic_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -77,7 +92,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -85,7 +100,7 @@ class ClockSampler:
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -120,13 +135,27 @@ def workload_cfg(name):
     w = synth.WORKLOADS[name]
     cfg = synth.default_config(w["width"], w["height"], max_cnt=w["max_cnt"],
                                min_dist=w["min_dist"], use_ransac=1)
-    pub_div = int(round(synth.WINDOWS_PER_SEC / w["freq"]))  # freq 15 -> every 2nd window
+    pub_div = int(round(synth.WINDOWS_PER_SEC / w["freq"]))  # freq 10 -> every 3rd window
     return w, cfg, pub_div
 
 
-def gen_windows(w, stream, n):
-    s = synth.StereoEventStream(w["width"], w["height"], w["rate"], stream=stream, mono=w["mono"])
+def config_of(name, scene="survey"):
+    """The `config` object of the JSON line -- the same in both arms."""
+    w, _, pub_div = workload_cfg(name)
+    return {"workload": name, "width": w["width"], "height": w["height"],
+            "events_per_window_per_camera": int(round(w["rate"] / synth.WINDOWS_PER_SEC)),
+            "max_cnt": w["max_cnt"], "min_dist": w["min_dist"], "pub_every": pub_div,
+            "scene": scene}
+
+
+def gen_windows(w, stream, n, scene="survey"):
+    s = synth.StereoEventStream(w["width"], w["height"], w["rate"], stream=stream, mono=w["mono"],
+                                rigid=(scene == "rigid"))
     return [s.stereo_window(k) for k in range(n)]
+
+
+def n_events(wins):
+    return float(sum(len(L[0]) + len(R[0]) for L, R, _ in wins))
 
 
 # ------------------------------------------------------------------------------------------
@@ -144,12 +173,14 @@ def cpu_tracker(cfg, threads):
     return t, kind, desc
 
 
-def run_cpu(cfg, pub_div, wins, warmup, threads):
+def run_cpu(cfg, pub_div, wins, warmup, threads, barrier=None):
     t, kind, desc = cpu_tracker(cfg, threads)
     outs = []
     n_ev = 0
     t_total = 0.0
     for k, (L, R, tc) in enumerate(wins):
+        if k == warmup and barrier is not None:
+            barrier.wait()
         t0 = time.perf_counter()
         o = t.track(tc, L, R, k % pub_div == 0)
         dt = time.perf_counter() - t0
@@ -160,30 +191,82 @@ def run_cpu(cfg, pub_div, wins, warmup, threads):
     return n_ev, t_total, outs, kind, desc, t.timers()
 
 
+def _ref_stream_worker(workload, scene, stream, steps, warmup, threads, barrier, q):
+    """One CPU stream of the reference arm at N > 1 (its own process, `threads` OpenCV threads)."""
+    try:
+        w, cfg, pub_div = workload_cfg(workload)
+        wins = gen_windows(w, stream, steps + warmup, scene)
+        n_ev, sec, _, kind, desc, timers = run_cpu(cfg, pub_div, wins, warmup, threads, barrier)
+        q.put((stream, n_ev, sec, kind, desc, timers))
+    except Exception as e:  # noqa: BLE001
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+        q.put((stream, 0, 0.0, "error", repr(e)[:200], {}))
+
+
+def reference_measure(workload, scene, n_streams, steps, warmup, cores):
+    """(Mevents/s, seconds, kind, desc, timers, threads per stream): n_streams CPU streams side
+    by side on `cores` host threads; value = all events / the slowest stream's timed seconds."""
+    if n_streams == 1:
+        w, cfg, pub_div = workload_cfg(workload)
+        wins = gen_windows(w, 0, steps + warmup, scene)
+        n_ev, sec, _, kind, desc, timers = run_cpu(cfg, pub_div, wins, warmup, cores)
+        return n_ev / sec / 1e6, sec, kind, desc, timers, cores
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    threads = max(1, cores // n_streams)
+    barrier = ctx.Barrier(n_streams)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ref_stream_worker,
+                         args=(workload, scene, s, steps, warmup, threads, barrier, q))
+             for s in range(n_streams)]
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    bad = [r for r in res if r[3] == "error"]
+    if bad:
+        raise RuntimeError("reference stream failed: " + bad[0][4])
+    n_ev = sum(r[1] for r in res)
+    sec = max(r[2] for r in res)
+    return n_ev / sec / 1e6, sec, res[0][3], res[0][4], res[0][5], threads
+
+
 def main_reference(args):
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     if rank != 0:
         return
-    w, cfg, pub_div = workload_cfg(args.workload)
+    n_streams = max(1, args.gpus)
+    workload = args.workload or default_workload(n_streams)
     cores = os.cpu_count() or 1
-    wins = gen_windows(w, 0, args.steps + args.warmup)
-    n_ev, sec, _, kind, desc, timers = run_cpu(cfg, pub_div, wins, args.warmup, cores)
-    val = n_ev / sec / 1e6
+    val, sec, kind, desc, timers, threads = reference_measure(workload, "survey", n_streams,
+                                                              args.steps, args.warmup, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(args.steps, 1),
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sec / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": args.workload, "width": w["width"], "height": w["height"],
-                   "events_per_window_per_camera": int(round(w["rate"] / synth.WINDOWS_PER_SEC)),
-                   "max_cnt": w["max_cnt"], "min_dist": w["min_dist"], "pub_every": pub_div},
+        "data": "synthetic", "config": config_of(workload),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{args.steps} windows of {args.workload} after {args.warmup} "
-                                   f"warm-up; {desc}; cv2 threads = {cores}; the reference's own "
-                                   "node cannot be built here (needs ROS/OpenCV C++/Eigen)"},
+                         "sample": f"{n_streams} stream(s) x {args.steps} windows of {workload} after "
+                                   f"{args.warmup} warm-up; {desc}; {threads} OpenCV threads per stream"
+                                   + (", one process per stream" if n_streams > 1 else "")
+                                   + "; the reference's own node cannot be built here (needs "
+                                     "ROS/OpenCV C++/Eigen), its event_detector.cc pins the oracle "
+                                     "(oracle/_ref)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "stage_seconds": timers,
     }
+    if n_streams == 1 and not args.no_rigid:
+        rv, rsec, _, _, rtimers, _ = reference_measure(workload, "rigid", 1, args.steps,
+                                                       args.warmup, cores)
+        line["rigid_scene"] = {"config": config_of(workload, "rigid"), "value": rv, "unit": UNIT,
+                               "e2e": {"value": rv, "unit": UNIT},
+                               "ms_per_step": 1e3 * rsec / max(args.steps, 1),
+                               "stage_seconds": rtimers}
     print(json.dumps(line))
 
 
@@ -221,120 +304,260 @@ def init_nccl(local, p2p_peer=None):
         os.close(saved_fd)
 
 
-def main_split(args):
-    """--split-lr, 2 ranks: ONE stereo stream with the right camera's SAE / time surface /
-    pyramid on rank 1 and everything else on rank 0 (SURVEY.md 8e row 2, 8d config 3 "then 2
-    GPUs with L/R split"); the right image block crosses NVLink once per window (NCCL
-    send/recv).  Strong scaling of one stream; rank 0 also runs the same windows on one handle
-    and reports that throughput and whether the results are identical."""
-    import torch
-    import torch.distributed as dist
-    from esvio_b200 import frontend
+class TrackGather:
+    """The per-publish-window collective of the replica mode: every rank's
+    packed track block, all-gathered so that any rank can publish all clouds.  It runs on a
+    stream of its own behind esvio_fe_result_acquire / _release -- the tracking streams never
+    wait for NCCL -- into one of two rotating receive buffers, and only on publish windows (the
+    reference publishes nothing on the others, stereo_event_tracker_node.cpp:268)."""
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if world != 2:
-        raise SystemExit("bench.py --split-lr needs exactly 2 ranks (torchrun --nproc-per-node 2)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the front-end has no CPU fallback")
-    torch.cuda.set_device(local)
-    init_nccl(local, p2p_peer=1 - rank)
-    dev = torch.device("cuda", local)
-    w, cfg, pub_div = workload_cfg(args.workload)
+    def __init__(self, torch, dev, world, words):
+        self.torch, self.dev, self.world = torch, dev, world
+        self.stream = torch.cuda.Stream(device=dev)
+        self.bufs = [torch.empty((world, words), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.views = {}
+        self.n = 0
+
+    def after_submit(self, fe):
+        ptr, nbytes = fe.result_acquire(self.stream.cuda_stream)
+        v = self.views.get(ptr)
+        if v is None:
+            v = self.views[ptr] = self.torch.as_tensor(_CudaArray(ptr, nbytes), device=self.dev)
+        with self.torch.cuda.stream(self.stream):
+            shard.all_gather_tracks(v, self.bufs[self.n & 1])
+        fe.result_release(self.stream.cuda_stream)
+        self.n += 1
+
+
+def run_pipelined(fe, wins, k0, n, pub_div, gather=None, collect=None):
+    """n windows from k0 through submit/wait, three in flight; `wins[k]` = (left, right, t) as
+    esvio_events wrappers.  Returns (n_left, n_right) of the last one and their sum over all."""
+    last, checksum, waited = (0, 0), 0, 0
+    for k in range(k0, k0 + n):
+        l, r, t = wins[k]
+        pub = k % pub_div == 0
+        fe.submit(t, l, r, pub)
+        if gather is not None and pub:
+            gather.after_submit(fe)
+        if k - k0 >= DEPTH - 1:
+            last = fe.wait(unpack=False)
+            checksum += last[0] + last[1]
+            waited += 1
+            if collect is not None:
+                collect(fe.stage_ms())
+    while waited < n:
+        last = fe.wait(unpack=False)
+        checksum += last[0] + last[1]
+        waited += 1
+        if collect is not None:
+            collect(fe.stage_ms())
+    return last, checksum
+
+
+class StreamBench:
+    """One stereo stream on this rank's GPU: the device-resident leg (`value`), the host-buffer
+    leg through submit/wait (`e2e`), the synchronous drop-in call and the per-stage profile."""
+
+    def __init__(self, torch, dev, local, workload, scene, stream_id, K, Wm, world=1):
+        from esvio_b200 import frontend
+        self.torch, self.dev, self.fr = torch, dev, frontend
+        self.w, cfg, self.pub_div = workload_cfg(workload)
+        self.n_per_cam = int(round(self.w["rate"] / synth.WINDOWS_PER_SEC))
+        self.cfg = dict(cfg, device_id=local, max_events_per_window=max(self.n_per_cam + 64, 1024))
+        self.K, self.Wm, self.world = K, Wm, world
+        self.wins = gen_windows(self.w, stream_id, K + Wm, scene)
+        self.ev_timed = n_events(self.wins[Wm:])
+        self.ev_per_step = self.ev_timed / max(K, 1)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _timed(self, fe, wins, gather, flush, fill):
+        torch = self.torch
+        ext = torch.cuda.ExternalStream(fe.stream(), device=self.dev)
+        for k in range(self.Wm):
+            l, r, t = wins[k]
+            pub = k % self.pub_div == 0
+            fe.submit(t, l, r, pub)
+            if gather is not None and pub:
+                gather.after_submit(fe)
+            fe.wait(unpack=False)
+        flush.fill_(fill)   # evict the uploaded windows: every timed step streams its events from HBM
+        self.barrier()
+        launches0 = fe.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        last, checksum = run_pipelined(fe, wins, self.Wm, self.K, self.pub_div, gather)
+        if gather is not None:
+            ext.wait_stream(gather.stream)   # the timed region ends when the last gather has
+        e1.record(ext)
+        self.barrier()
+        return e0.elapsed_time(e1), fe.kernel_launches() - launches0, last, checksum
+
+    def device_leg(self, flush, gather=None, profile=False):
+        fr = self.fr
+        fe = fr.EventFrontEnd(self.cfg)
+        held = [(fr.DeviceEvents(fe, L), fr.DeviceEvents(fe, R)) for L, R, _ in self.wins]
+        dw = [(fr._Ev(a), fr._Ev(b), w[2]) for (a, b), w in zip(held, self.wins)]
+        ms, launches, last, _ = self._timed(fe, dw, gather, flush, 1)
+        out = {"ms": ms, "launches": launches, "last": last, "result_bytes": fe.result_device_ptr()[1]}
+        if profile:
+            # second pipelined pass over the same windows with the per-stage CUDA events on:
+            # stage_ms and the SAE kernel's launch duration.  The events sit between the kernels
+            # and switch off their programmatic launch overlap, so they stay out of the pass
+            # that yields `value`.
+            fe.reset()
+            for k in range(self.Wm):
+                l, r, t = dw[k]
+                fe.submit(t, l, r, k % self.pub_div == 0)
+                fe.wait(unpack=False)
+            flush.fill_(4)
+            fe.set_profiling(True)
+            acc = np.zeros(len(fr._capi.STAGE_NAMES))
+
+            def collect(d):
+                acc[:] += np.fromiter(d.values(), float)
+
+            self.barrier()
+            run_pipelined(fe, dw, self.Wm, self.K, self.pub_div, None, collect)
+            self.barrier()
+            fe.set_profiling(False)
+            out["stage_ms"] = dict(zip(fr._capi.STAGE_NAMES, (acc / max(self.K, 1)).tolist()))
+        for a, b in held:
+            a.free()
+            b.free()
+        fe.close()
+        return out
+
+    def host_leg(self, flush, gather=None, sync=False):
+        """e2e: pinned host SoA buffers through esvio_fe_track_submit / _wait (H2D of the events
+        and D2H of the track records inside the timed region); `sync`: the same windows once
+        more through the synchronous esvio_fe_track, host wall clock."""
+        fr = self.fr
+        fe = fr.EventFrontEnd(self.cfg)
+        pw = [(fr._Ev(fr.PinnedEvents(L)), fr._Ev(fr.PinnedEvents(R)), t) for L, R, t in self.wins]
+        ms, launches, last, checksum = self._timed(fe, pw, gather, flush, 2)
+        out = {"ms": ms, "launches": launches, "last": last, "checksum": checksum}
+        fe.close()
+        if sync:
+            fe = fr.EventFrontEnd(self.cfg)
+            for k in range(self.Wm):
+                l, r, t = pw[k]
+                fe.track_raw(t, l, r, k % self.pub_div == 0)
+            self.torch.cuda.synchronize()
+            fe.set_profiling(True)   # one window at a time: the kernels run without neighbours
+            k1 = []
+            t0 = time.perf_counter()
+            for k in range(self.Wm, self.Wm + self.K):
+                l, r, t = pw[k]
+                fe.track_raw(t, l, r, k % self.pub_div == 0)
+                k1.append(fe.stage_ms()["sae_update_ts"])
+            out["sync_ms_per_step"] = (time.perf_counter() - t0) * 1e3 / self.K
+            out["k1_alone_ms"] = float(np.mean(k1))
+            fe.close()
+        return out
+
+    def mev(self, ms):
+        return self.ev_timed / (ms * 1e-3) / 1e6
+
+
+def quick_record(torch, dev, local, workload, scene, K, Wm, flush, sync=False):
+    """value + e2e (+ sync) of one more workload / scene on this GPU, as a record."""
+    sb = StreamBench(torch, dev, local, workload, scene, 0, K, Wm)
+    d = sb.device_leg(flush)
+    h = sb.host_leg(flush, sync=sync)
+    rec = {"config": config_of(workload, scene), "value": sb.mev(d["ms"]), "unit": UNIT,
+           "ms_per_step": d["ms"] / K,
+           "e2e": {"value": sb.mev(h["ms"]), "unit": UNIT, "ms_per_step": h["ms"] / K,
+                   "h2d_bytes_per_step": int(round(13 * sb.ev_per_step)),
+                   "d2h_bytes_per_step": int(d["result_bytes"])},
+           "tracks_last_window": {"left": int(d["last"][0]), "right": int(d["last"][1])}}
+    if sync:
+        rec["sync"] = {"value": sb.ev_per_step / (h["sync_ms_per_step"] * 1e-3) / 1e6, "unit": UNIT,
+                       "ms_per_step": h["sync_ms_per_step"]}
+    return rec
+
+
+def batched_leg(torch, dev, local, workload, S, K, Wm, flush):
+    """S streams of the workload in one esvio_fe_group on this GPU (BASELINE configs[4] on one
+    GPU): ONE k_sae_update_ts launch per window covers the 2S cameras.  This is where the
+    roofline of that kernel is measured (SURVEY.md 8d caveat: one window of one stream moves
+    6-25 MB per launch, i.e. 1-4 us at the HBM peak): CUDA events around the launch on the
+    group's event-stage stream while the tracking stages of two other windows x S streams share
+    the SMs; whole-group throughput by CUDA events as well."""
+    from esvio_b200 import frontend
+    w, cfg, pub_div = workload_cfg(workload)
     n_per_cam = int(round(w["rate"] / synth.WINDOWS_PER_SEC))
     cfg = dict(cfg, device_id=local, max_events_per_window=max(n_per_cam + 64, 1024))
-    K, Wm = args.steps, args.warmup
-    wins = gen_windows(w, 0, K + Wm)                 # both ranks see the same stereo stream
-    fe = frontend.EventFrontEnd(cfg)
-    sp = shard.LeftRightSplit(fe, rank)
-    mine = [frontend._Ev(frontend.DeviceEvents(fe, (L, R)[rank])) for L, R, _ in wins]
-    n_ev_local = float(sum(len((L, R)[rank][0]) for L, R, _ in wins[Wm:]))
-    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    DEPTH = 3
+    grp = frontend.EventFrontEndGroup(cfg, S)
+    m0 = grp.member(0)
+    nb_w = Wm + K
+    bw, n_ev, held = [], 0.0, []
+    for i in range(S):
+        ws = gen_windows(w, 100 + i, nb_w)
+        n_ev += n_events(ws[Wm:])
+        row = []
+        for L, R, t in ws:
+            a, b = frontend.DeviceEvents(m0, L), frontend.DeviceEvents(m0, R)
+            held += [a, b]
+            row.append((frontend._Ev(a), frontend._Ev(b), t))
+        bw.append(row)
 
-    def run(k0, n, sink):
-        waited = 0
-        for k in range(k0, k0 + n):
-            sp.step(wins[k][2], mine[k], k % pub_div == 0)
-            if rank == shard.LEFT_RANK and k - k0 >= DEPTH - 1:
-                sink.append(sp.wait(unpack=False))
-                waited += 1
-        while rank == shard.LEFT_RANK and waited < n:
-            sink.append(sp.wait(unpack=False))
-            waited += 1
+    def gsub(k):
+        grp.submit([bw[i][k][2] for i in range(S)], [bw[i][k][0] for i in range(S)],
+                   [bw[i][k][1] for i in range(S)], [k % pub_div == 0] * S)
 
-    def barrier():
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    counts = []
-    run(0, Wm, counts)
-    flush.fill_(1)
-    cur = torch.cuda.current_stream()
-    tstream = torch.cuda.ExternalStream(fe.stream(), device=dev) if rank == shard.LEFT_RANK else cur
-    barrier()
-    launches0 = fe.kernel_launches()
+    for k in range(Wm):
+        gsub(k)
+        grp.wait(unpack=False)
+    flush.fill_(3)
+    torch.cuda.synchronize()
+    ext = torch.cuda.ExternalStream(m0.stream(), device=dev)   # member 0's result stream
+    k1_ms = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(tstream)
-    run(Wm, K, counts)
-    e1.record(tstream)
-    barrier()
-    launches = fe.kernel_launches() - launches0
-    value, ms = shard.aggregate_throughput(n_ev_local, e0.elapsed_time(e1))
-    nl = torch.tensor([launches], dtype=torch.int64, device=dev)
-    dist.all_reduce(nl)
-    img_bytes = fe.split_right_buffer()[1] if rank == shard.LEFT_RANK else 0
-
-    one = None
-    if rank == shard.LEFT_RANK:       # the same windows on one handle, same pipelining
-        fe1 = frontend.EventFrontEnd(cfg)
-        dw = [(frontend._Ev(frontend.DeviceEvents(fe1, L)), frontend._Ev(frontend.DeviceEvents(fe1, R)), t)
-              for L, R, t in wins]
-        ext1 = torch.cuda.ExternalStream(fe1.stream(), device=dev)
-        ref_counts = []
-
-        def run1(k0, n):
-            waited = 0
-            for k in range(k0, k0 + n):
-                fe1.submit(dw[k][2], dw[k][0], dw[k][1], k % pub_div == 0)
-                if k - k0 >= DEPTH - 1:
-                    ref_counts.append(fe1.wait(unpack=False))
-                    waited += 1
-            while waited < n:
-                ref_counts.append(fe1.wait(unpack=False))
-                waited += 1
-
-        run1(0, Wm)
-        flush.fill_(2)
-        torch.cuda.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(ext1)
-        run1(Wm, K)
-        f1.record(ext1)
-        torch.cuda.synchronize()
-        ms1 = f0.elapsed_time(f1)
-        n_ev = float(sum(len(L[0]) + len(R[0]) for L, R, _ in wins[Wm:]))
-        # last window in full, every window by its feature counts
-        a, b = fe._unpack(), fe1._unpack()
-        same = ref_counts == counts and all(np.array_equal(a[k], b[k]) for k in a if k != "stats")
-        one = {"value": n_ev / (ms1 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms1 / K,
-               "identical_results": bool(same)}
-        fe1.close()
-    dist.barrier()
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 2, "steps": K, "warmup": Wm,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64 SAE / u8 time surface / f32 LK", "data": "synthetic",
-            "config": {"workload": args.workload, "parallelism": "lr_split: rank 0 left camera + "
-                       "tracking, rank 1 right camera SAE/time surface/pyramid",
-                       "inputs": "resident in HBM on the rank that consumes them",
-                       "windows_in_flight": DEPTH},
-            "exchange": {"what": "right pyramid block, NCCL send/recv per window",
-                         "bytes_per_step": int(img_bytes)},
-            "gpu_launches": int(nl.item()), "one_gpu_same_run": one}))
-    fe.close()
-    dist.destroy_process_group()
+    t0 = time.perf_counter()
+    e0.record(ext)
+    waited = 0
+    for k in range(Wm, Wm + K):
+        gsub(k)
+        if k - Wm >= DEPTH - 1:
+            grp.wait(unpack=False)
+            waited += 1
+            k1_ms.append(grp.sae_ts_ms())
+    while waited < K:
+        grp.wait(unpack=False)
+        waited += 1
+        k1_ms.append(grp.sae_ts_ms())
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    k1 = float(np.mean(k1_ms))
+    alg = S * 2 * 17 * w["width"] * w["height"] + 45 * n_ev / K
+    peak, peak_src = peaks()
+    rec = {"streams": S, "steps": K, "config": config_of(workload),
+           "value": n_ev / (wall_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wall_ms / K,
+           "timing": "host wall clock around submit/wait with synchronize on both sides, events "
+                     "device-resident, 3 windows in flight",
+           "gpu_launches": grp.kernel_launches()}
+    roof = {"bound": "hbm", "kernel": "k_sae_update_ts", "achieved": alg / (k1 * 1e-3) / 1e9,
+            "peak": peak, "unit": "GB/s", "frac": alg / (k1 * 1e-3) / 1e9 / peak,
+            "traffic": ncu_traffic(f"{workload}_x{S}"),
+            "algorithmic_bytes_per_launch": int(alg), "kernel_ms": k1,
+            "share_of_step": k1 / (wall_ms / K), "peak_source": peak_src,
+            "launch_covers": f"{2 * S} cameras = {S} stereo streams of {workload} in one esvio_fe_group",
+            "note": "achieved = algorithmic bytes (SURVEY.md 8d: 17*W*H per camera + 45 B/event, "
+                    "summed over the cameras of the launch) / CUDA-event time of the launch, "
+                    "measured inside the 3-deep pipeline (the LK / selection kernels of two other "
+                    "windows x S streams share the SMs); the group's SAE state (S x 19.7 MB at "
+                    "640x480) exceeds what stays in L2 next to the event buffers, so the launch "
+                    "streams from HBM"}
+    for a in held:
+        a.free()
+    grp.close()
+    return rec, roof
 
 
 def frames_leg(width, height, device_id, n_frames=48, cpu_frames=16):
@@ -419,6 +642,31 @@ def frames_leg(width, height, device_id, n_frames=48, cpu_frames=16):
     return rec
 
 
+def parity_record(frontend, cfg, pub_div, wins, outs, desc):
+    """Tracked-px RMSE of the first windows against the CPU arm's outputs (lock-step windows)."""
+    fe = frontend.EventFrontEnd(cfg)
+    sq, cnt, mx, hor = 0.0, 0, 0.0, 0
+    for k in range(min(len(outs), 8)):
+        L, R, t = wins[k]
+        g = fe.track(t, L, R, k % pub_div == 0)
+        o = outs[k]
+        if not (np.array_equal(g["id"], o["id"]) and np.array_equal(g["id_right"], o["id_right"])):
+            break
+        hor = k + 1
+        for a, b in ((g["u"], o["u"]), (g["v"], o["v"]), (g["ru"], o["ru"]), (g["rv"], o["rv"])):
+            if len(a):
+                d = np.abs(a - b)
+                sq += float((d ** 2).sum())
+                cnt += len(d)
+                mx = max(mx, float(d.max()))
+    fe.close()
+    return {"tracked_px_rmse_vs_ref": (sq / max(cnt, 1)) ** 0.5, "max_px": mx,
+            "windows_with_identical_ids": hor, "coords_compared": cnt,
+            "ref": "oracle with OpenCV LK" if "cv2" in desc else "oracle C LK",
+            "all_windows": "tests/test_gpu_parity.py::test_teacher_forced_every_window compares every "
+                           "window of the run, restarted from the reference state each window"}
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -433,332 +681,262 @@ def main_ours(args):
     if world > 1:
         init_nccl(local)
     dev = torch.device("cuda", local)
-
-    w, cfg, pub_div = workload_cfg(args.workload)
-    n_per_cam = int(round(w["rate"] / synth.WINDOWS_PER_SEC))
-    cfg = dict(cfg, device_id=local, max_events_per_window=max(n_per_cam + 64, 1024))
+    workload = args.workload or default_workload(world)
     K, Wm = args.steps, args.warmup
-    wins = gen_windows(w, rank, K + Wm)
-    ev_per_step = sum(len(L[0]) + len(R[0]) for L, R, _ in wins[Wm:]) / max(K, 1)
-
-    # ---------------- device-resident leg: `value` ----------------
-    fe = frontend.EventFrontEnd(cfg)
-    ext = torch.cuda.ExternalStream(fe.stream(), device=dev)
-    dwins = [(frontend._Ev(frontend.DeviceEvents(fe, L)), frontend._Ev(frontend.DeviceEvents(fe, R)), t)
-             for L, R, t in wins]
-    rptr, rbytes = fe.result_device_ptr()
-    res_t = torch.as_tensor(_CudaArray(rptr, rbytes), device=dev)
-    gathered = torch.empty((world, res_t.numel()), dtype=torch.int32, device=dev) if world > 1 else None
-    input_bytes = 13 * ev_per_step * K
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def step_submit(k):
-        l, r, t = dwins[k]
-        fe.submit(t, l, r, k % pub_div == 0)
-        if world > 1:
-            with torch.cuda.stream(ext):   # stream-ordered behind this window's finalize
-                shard.all_gather_tracks(res_t, gathered)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for k in range(Wm):
-        step_submit(k)
-        fe.wait(unpack=False)
-    DEPTH = 3  # windows in flight: event stage | temporal stage | stereo stage
-
-    def run_pipelined(k0, n, collect=None):
-        """n windows from k0, three in flight; returns the (n_left, n_right) of the last one."""
-        last = (0, 0)
-        for k in range(k0, min(k0 + DEPTH - 1, k0 + n)):
-            step_submit(k)
-        waited = 0
-        for k in range(k0 + DEPTH - 1, k0 + n):
-            step_submit(k)
-            last = fe.wait(unpack=False)
-            waited += 1
-            if collect is not None:
-                collect(fe.stage_ms())
-        while waited < n:
-            last = fe.wait(unpack=False)
-            waited += 1
-            if collect is not None:
-                collect(fe.stage_ms())
-        return last
-
-    flush.fill_(1)  # evict the uploaded windows: every timed step streams its events from HBM
+    sb = StreamBench(torch, dev, local, workload, "survey", rank, K, Wm, world)
+    gather = None
+    if world > 1:
+        gather = TrackGather(torch, dev, world, shard.result_words(sb.cfg["max_cnt"]))
     clocks = ClockSampler(local)
-    barrier()
     clocks.start()
-    launches0 = fe.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
-    n_left_last, n_right_last = run_pipelined(Wm, K)
-    e1.record(ext)
-    barrier()
-    launches = fe.kernel_launches() - launches0
-    ms = e0.elapsed_time(e1)
+    d = sb.device_leg(flush, gather, profile=True)
+    h = sb.host_leg(flush, gather, sync=(world == 1))
     clk = clocks.stop()
-    # second pipelined pass over the head of the same windows with the per-stage CUDA events
-    # on: stage_ms and the roofline kernel's launch duration.  The events sit between the
-    # kernels and switch off their programmatic launch overlap, so they stay out of the pass
-    # that yields `value`.
-    fe.reset()
-    Kp = min(K, 100)
-    for k in range(Wm):
-        step_submit(k)
-        fe.wait(unpack=False)
-    flush.fill_(4)
-    fe.set_profiling(True)
-    stage_sum = np.zeros(len(frontend._capi.STAGE_NAMES))
 
-    def collect(d):
-        nonlocal stage_sum
-        stage_sum += np.fromiter(d.values(), float)
-
-    barrier()
-    run_pipelined(Wm, Kp, collect)
-    barrier()
-    fe.set_profiling(False)
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([ev_per_step * K, float(launches)], dtype=torch.float64, device=dev)
+    red = torch.tensor([d["ms"], h["ms"]], dtype=torch.float64, device=dev)
+    tot = torch.tensor([sb.ev_timed, float(d["launches"])], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
-    ms_max = float(t_ms.item())
-    value = float(tot[0].item()) / (ms_max * 1e-3) / 1e6
-    gpu_launches = int(tot[1].item())
-    fe.close()
+    ms_max, e2e_ms = float(red[0].item()), float(red[1].item())
+    ev_all = float(tot[0].item())
+    value = ev_all / (ms_max * 1e-3) / 1e6
+    e2e_value = ev_all / (e2e_ms * 1e-3) / 1e6
 
-    # ---------------- end-to-end leg: host buffers through the synchronous C-ABI call ----------
-    fe2 = frontend.EventFrontEnd(cfg)
-    ext2 = torch.cuda.ExternalStream(fe2.stream(), device=dev)
-    pwins = [(frontend._Ev(frontend.PinnedEvents(L)), frontend._Ev(frontend.PinnedEvents(R)), t)
-             for L, R, t in wins]
-    def e2e_submit(k):
-        l, r, t = pwins[k]
-        fe2.submit(t, l, r, k % pub_div == 0)   # H2D of the events is enqueued inside
-        if world > 1:
-            with torch.cuda.stream(ext2):
-                shard.all_gather_tracks(res2_t, gathered)
-
-    res2_t = torch.as_tensor(_CudaArray(*fe2.result_device_ptr()), device=dev)
-    for k in range(Wm):
-        e2e_submit(k)
-        fe2.wait(unpack=False)
-    flush.fill_(2)
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record(ext2)
-    checksum = 0
-    for k in range(Wm, min(Wm + DEPTH - 1, Wm + K)):
-        e2e_submit(k)
-    waited = 0
-    for k in range(Wm + DEPTH - 1, Wm + K):
-        e2e_submit(k)                     # window k's copies + event stage overlap earlier LK
-        nl, nr = fe2.wait(unpack=False)   # D2H of the track records + host sync
-        checksum += nl + nr
-        waited += 1
-    while waited < K:
-        nl, nr = fe2.wait(unpack=False)
-        checksum += nl + nr
-        waited += 1
-    g1.record(ext2)
-    barrier()
-    e2e_ms = g0.elapsed_time(g1)
-    # the same windows once more through the synchronous drop-in call, for reference
-    sync_ms = None
-    k1_alone = []
-    if world == 1:
-        fe4 = frontend.EventFrontEnd(cfg)
-        n_sync = min(K, 60)
-        for k in range(Wm):
-            l, r, t = pwins[k]
-            fe4.track_raw(t, l, r, k % pub_div == 0)
-        torch.cuda.synchronize()
-        fe4.set_profiling(True)   # one window at a time: the kernels run without neighbours
-        t0 = time.perf_counter()
-        for k in range(Wm, Wm + n_sync):
-            l, r, t = pwins[k]
-            fe4.track_raw(t, l, r, k % pub_div == 0)
-            k1_alone.append(fe4.stage_ms()["sae_update_ts"])
-        sync_ms = (time.perf_counter() - t0) * 1e3 / n_sync
-        fe4.close()
-    # ---------------- batched leg (N = 1): S streams of this workload in one group ----------
-    # SURVEY.md 8d caveat: one window of one stream moves 6-25 MB per k_sae_update_ts launch,
-    # i.e. 1-4 us at the HBM peak -- the roofline of that kernel only means something when a
-    # launch covers several streams (BASELINE configs[4], esvio_fe_group_*).
-    batched = None
-    if world == 1 and args.batch_streams > 1:
-        S = args.batch_streams
-        Kb = min(K, args.batch_steps)
-        nb_w = Wm + Kb
-        grp = frontend.EventFrontEndGroup(cfg, S)
-        m0 = grp.member(0)
-        bw = []
-        for i in range(S):
-            ws = wins[:nb_w] if i == 0 else gen_windows(w, 100 + i, nb_w)
-            bw.append([(frontend._Ev(frontend.DeviceEvents(m0, L)), frontend._Ev(frontend.DeviceEvents(m0, R)), t,
-                        len(L[0]) + len(R[0])) for L, R, t in ws])
-        def gsub(k):
-            grp.submit([bw[i][k][2] for i in range(S)], [bw[i][k][0] for i in range(S)],
-                       [bw[i][k][1] for i in range(S)], [k % pub_div == 0] * S)
-        for k in range(Wm):
-            gsub(k)
-            grp.wait(unpack=False)
-        flush.fill_(3)
-        torch.cuda.synchronize()
-        k1_ms = []
-        t0 = time.perf_counter()
-        gsub(Wm)
-        if Kb > 1:
-            gsub(Wm + 1)
-        done = 0
-        for k in range(Wm + 2, Wm + Kb):
-            gsub(k)
-            grp.wait(unpack=False)
-            done += 1
-            k1_ms.append(grp.sae_ts_ms())
-        while done < Kb:
-            grp.wait(unpack=False)
-            done += 1
-            k1_ms.append(grp.sae_ts_ms())
-        torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        n_ev_b = sum(bw[i][k][3] for i in range(S) for k in range(Wm, Wm + Kb))
-        k1 = float(np.mean(k1_ms))
-        alg = S * 2 * 17 * w["width"] * w["height"] + 45 * n_ev_b / Kb
-        peak_b, _ = peaks()
-        batched = {"streams": S, "steps": Kb, "value": n_ev_b / (wall_ms * 1e-3) / 1e6, "unit": UNIT,
-                   "ms_per_step": wall_ms / Kb, "timing": "host wall clock around submit/wait with "
-                   "synchronize on both sides, events device-resident, 3 windows in flight",
-                   "gpu_launches": grp.kernel_launches(),
-                   "roofline": {"bound": "hbm", "kernel": "k_sae_update_ts", "kernel_ms": k1,
-                                "algorithmic_bytes_per_launch": int(alg),
-                                "achieved": alg / (k1 * 1e-3) / 1e9, "peak": peak_b, "unit": "GB/s",
-                                "frac": alg / (k1 * 1e-3) / 1e9 / peak_b,
-                                "note": "one launch covers the 2*S cameras of the group; CUDA events "
-                                        "around the launch on the group's event-stage stream, other "
-                                        "stages of other windows share the SMs"}}
-        grp.close()
-    e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    # N > 1: the same stream alone on rank 0's GPU while the other ranks idle -- the one-GPU
+    # figure of THIS workload in THIS run (the N = 1 line runs configs[2])
+    one_gpu = None
     if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = float(tot[0].item()) / (float(e2e_t.item()) * 1e-3) / 1e6
-    h2d = int(round(13 * ev_per_step))
-    d2h = int(rbytes)
+        if rank == 0:
+            sb1 = StreamBench(torch, dev, local, workload, "survey", 0, K, Wm, 1)
+            one_gpu = {"value": sb1.mev(sb1.device_leg(flush)["ms"]), "unit": UNIT,
+                       "what": "rank 0's stream alone, no collective, same run"}
+        dist.barrier()
 
-    # ---------------- CPU baseline (rank 0, N = 1 only) + parity of the first windows ---------
-    cpu = None
-    parity = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        n_s = min(len(wins), args.cpu_windows)
-        n_ev, sec, outs, kind, desc, _ = run_cpu(workload_cfg(args.workload)[1], pub_div,
-                                                 wins[:n_s], min(Wm, 3), 1)
-        cpu = {"value": n_ev / sec / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
-               "sample": f"first {n_s} windows of {args.workload} ({n_ev} events timed), single "
-                         f"thread like the reference's worker (stereo_event_tracker_node.cpp:366); {desc}"}
-        fe3 = frontend.EventFrontEnd(cfg)
-        sq, cnt, mx, hor = 0.0, 0, 0.0, 0
-        for k in range(min(n_s, 8)):
-            L, R, t = wins[k]
-            g = fe3.track(t, L, R, k % pub_div == 0)
-            o = outs[k]
-            if not (np.array_equal(g["id"], o["id"]) and np.array_equal(g["id_right"], o["id_right"])):
-                break
-            hor = k + 1
-            for a, b in ((g["u"], o["u"]), (g["v"], o["v"]), (g["ru"], o["ru"]), (g["rv"], o["rv"])):
-                if len(a):
-                    d = np.abs(a - b)
-                    sq += float((d ** 2).sum())
-                    cnt += len(d)
-                    mx = max(mx, float(d.max()))
-        parity = {"tracked_px_rmse_vs_ref": (sq / max(cnt, 1)) ** 0.5, "max_px": mx,
-                  "windows_with_identical_ids": hor, "coords_compared": cnt,
-                  "ref": "oracle with OpenCV LK" if "cv2" in desc else "oracle C LK"}
-        fe3.close()
-    fe2.close()
+    extra = {}
+    if rank == 0 and world == 1:
+        if not args.no_rigid:
+            extra["rigid_scene"] = quick_record(torch, dev, local, workload, "rigid", K, Wm, flush, sync=True)
+        if not args.no_secondary:
+            if workload != WORKLOAD_SECONDARY:
+                extra["secondary"] = quick_record(torch, dev, local, WORKLOAD_SECONDARY, "survey", K, Wm, flush)
+            if workload != WORKLOAD_NX:
+                extra["scale_base"] = quick_record(torch, dev, local, WORKLOAD_NX, "survey", K, Wm, flush)
+        roof_group = None
+        if args.batch_streams > 1:
+            try:
+                extra["batched"], roof_group = batched_leg(torch, dev, local, workload, args.batch_streams,
+                                                           min(K, args.batch_steps), Wm, flush)
+            except Exception as e:  # noqa: BLE001
+                extra["batched"] = {"error": repr(e)[:300]}
+        if not args.no_frames:
+            extra["frames"] = frames_leg(sb.w["width"], sb.w["height"], local)
+        if not args.no_cpu:
+            _, cfg0, pub_div = workload_cfg(workload)
+            n_s = min(len(sb.wins), args.cpu_windows)
+            n_ev, sec, outs, kind, desc, _ = run_cpu(cfg0, pub_div, sb.wins[:n_s], min(Wm, 3), 1)
+            extra["cpu_baseline"] = {
+                "value": n_ev / sec / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
+                "sample": f"first {n_s} windows of {workload} ({n_ev} events timed), single thread "
+                          f"like the reference's worker (stereo_event_tracker_node.cpp:366); {desc}"}
+            extra["parity"] = parity_record(frontend, sb.cfg, pub_div, sb.wins, outs, desc)
 
     if rank == 0:
         peak, peak_src = peaks()
-        W_, H_ = w["width"], w["height"]
-        names = frontend._capi.STAGE_NAMES
-        stage_ms = dict(zip(names, (stage_sum / max(Kp, 1)).tolist()))
+        W_, H_ = sb.w["width"], sb.w["height"]
+        stage_ms = d["stage_ms"]
         k1_ms = stage_ms["sae_update_ts"]
-        alg_bytes = 2 * 17 * W_ * H_ + 45 * ev_per_step   # SURVEY.md 8d: 17*W*H per camera + 45 B/event
+        alg_bytes = 2 * 17 * W_ * H_ + 45 * sb.ev_per_step   # 17*W*H per camera + 45 B/event
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
         gpu_ms = sum(v for k_, v in stage_ms.items() if k_ not in ("h2d", "d2h"))
+        roof_single = {
+            "bound": "hbm", "kernel": "k_sae_update_ts", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(workload),
+            "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": k1_ms,
+            "share_of_step": k1_ms / gpu_ms if gpu_ms else None,
+            "kernel_ms_alone": h.get("k1_alone_ms"),
+            "frac_alone": (alg_bytes / (h["k1_alone_ms"] * 1e-3) / 1e9 / peak) if h.get("k1_alone_ms") else None,
+            "peak_source": peak_src, "launch_covers": "the 2 cameras of one window of one stream",
+            "note": "one window of one stream moves 1-4 us worth of bytes at the HBM peak, less "
+                    "than a kernel launch costs (SURVEY.md 8d caveat); see `roofline` for the "
+                    "launch that covers a group of streams"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_max / max(K, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "width": W_, "height": H_,
-                       "events_per_window_per_camera": n_per_cam, "max_cnt": w["max_cnt"],
-                       "min_dist": w["min_dist"], "pub_every": pub_div,
-                       "streams_per_gpu": 1, "parallelism": f"{world} independent stereo streams"
-                       + (", NCCL all-gather of track records per window" if world > 1 else ""),
-                       "l2": "each window's events are read once from HBM: all windows are "
-                             "uploaded, then L2 is flushed with a 512 MiB write before the timed "
-                             "region; the SAE state (the path's persistent working set) stays "
-                             "resident by design",
-                       "timed_input_bytes": int(input_bytes)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": float(e2e_t.item()) / max(K, 1),
+            "config": config_of(workload),
+            "run": {"streams_per_gpu": 1, "parallelism": f"{world} independent stereo streams"
+                    + (", NCCL all-gather of the packed track records on publish windows, on a "
+                       "stream of its own" if world > 1 else ""),
+                    "windows_in_flight": DEPTH,
+                    "l2": "each window's events are read once from HBM: all windows are uploaded, "
+                          "then L2 is flushed with a 512 MiB write before the timed region; the SAE "
+                          "state (the path's persistent working set) stays resident by design",
+                    "timed_input_bytes": int(13 * sb.ev_timed)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(round(13 * sb.ev_per_step)),
+                    "d2h_bytes_per_step": int(d["result_bytes"]), "ms_per_step": e2e_ms / max(K, 1),
                     "api": "esvio_fe_track_submit / esvio_fe_track_wait on pinned host SoA "
                            "buffers, three windows in flight (H2D + event stage of window k+2 | "
                            "temporal LK + selection of k+1 | stereo LK of k)",
-                    "sync_call_ms_per_step": sync_ms},
-            "gpu_launches": gpu_launches,
+                    "sync_call_ms_per_step": h.get("sync_ms_per_step")},
+            "gpu_launches": int(tot[1].item()),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "k_sae_update_ts", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload),
-                         "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "kernel_ms": k1_ms, "share_of_step": k1_ms / gpu_ms if gpu_ms else None,
-                         "kernel_ms_alone": float(np.mean(k1_alone)) if k1_alone else None,
-                         "frac_alone": (alg_bytes / (float(np.mean(k1_alone)) * 1e-3) / 1e9 / peak)
-                         if k1_alone else None,
-                         "peak_source": peak_src,
-                         "note": "one launch covers both cameras of one window; achieved = "
-                                 "algorithmic bytes (SURVEY.md 8d: 17*W*H per camera + 45 B/event) / "
-                                 "CUDA-event time of the launch in a second pipelined pass over the same windows "
-                                 "with the per-stage events on "
-                                 "(the LK / selection kernels of two other windows share the SMs; "
-                                 "`kernel_ms_alone` / `frac_alone`: the same launch in the synchronous "
-                                 "call, nothing else on the GPU); the SAE state is L2-resident between "
-                                 "windows, `traffic` is the DRAM traffic of one launch under ncu "
-                                 "(caches flushed); LK stages are latency-bound and reported by time"},
             "stage_ms": stage_ms,
-            "tracks_last_window": {"left": int(n_left_last), "right": int(n_right_last)},
+            "tracks_last_window": {"left": int(d["last"][0]), "right": int(d["last"][1])},
         }
-        if batched is not None:
-            line["batched"] = batched
-        if world == 1 and not args.no_frames:
-            line["frames"] = frames_leg(W_, H_, local)
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
-        if parity is not None:
-            line["parity"] = parity
+        if h.get("sync_ms_per_step"):
+            line["sync"] = {"value": sb.ev_per_step / (h["sync_ms_per_step"] * 1e-3) / 1e6, "unit": UNIT,
+                            "ms_per_step": h["sync_ms_per_step"],
+                            "api": "esvio_fe_track: the synchronous call the reference node makes "
+                                   "(stereo_event_tracker_node.cpp:193), pinned host buffers, host "
+                                   "wall clock"}
+        if world == 1 and extra.get("batched") and "error" not in extra["batched"] and roof_group:
+            line["roofline"] = roof_group
+            line["roofline_single_stream"] = roof_single
+        else:
+            line["roofline"] = roof_single
+        if one_gpu is not None:
+            line["one_gpu_same_workload"] = one_gpu
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def main_split(args):
+    """--split-lr, 2 ranks: ONE stereo stream with the right camera's SAE / time surface /
+    pyramid on rank 1 and everything else on rank 0 (SURVEY.md 8e row 2, 8d config 3 "then 2
+    GPUs with L/R split"); the right image block crosses NVLink once per window (NCCL
+    send/recv).  Strong scaling of one stream; rank 0 also runs the same windows on one handle
+    and reports that throughput and whether the results are identical."""
+    import torch
+    import torch.distributed as dist
+    from esvio_b200 import frontend
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != 2:
+        raise SystemExit("bench.py --split-lr needs exactly 2 ranks (torchrun --nproc-per-node 2)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the front-end has no CPU fallback")
+    torch.cuda.set_device(local)
+    init_nccl(local, p2p_peer=1 - rank)
+    dev = torch.device("cuda", local)
+    workload = args.workload or WORKLOAD_N1
+    w, cfg, pub_div = workload_cfg(workload)
+    n_per_cam = int(round(w["rate"] / synth.WINDOWS_PER_SEC))
+    cfg = dict(cfg, device_id=local, max_events_per_window=max(n_per_cam + 64, 1024))
+    K, Wm = args.steps, args.warmup
+    wins = gen_windows(w, 0, K + Wm)                 # both ranks see the same stereo stream
+    fe = frontend.EventFrontEnd(cfg)
+    sp = shard.LeftRightSplit(fe, rank)
+    mine = [frontend._Ev(frontend.DeviceEvents(fe, (L, R)[rank])) for L, R, _ in wins]
+    n_ev_local = float(sum(len((L, R)[rank][0]) for L, R, _ in wins[Wm:]))
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def run(k0, n, sink):
+        waited = 0
+        for k in range(k0, k0 + n):
+            sp.step(wins[k][2], mine[k], k % pub_div == 0)
+            if rank == shard.LEFT_RANK and k - k0 >= DEPTH - 1:
+                sink.append(sp.wait(unpack=False))
+                waited += 1
+        while rank == shard.LEFT_RANK and waited < n:
+            sink.append(sp.wait(unpack=False))
+            waited += 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    counts = []
+    run(0, Wm, counts)
+    flush.fill_(1)
+    cur = torch.cuda.current_stream()
+    tstream = torch.cuda.ExternalStream(fe.stream(), device=dev) if rank == shard.LEFT_RANK else cur
+    barrier()
+    launches0 = fe.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(tstream)
+    run(Wm, K, counts)
+    e1.record(tstream)
+    barrier()
+    launches = fe.kernel_launches() - launches0
+    value, ms = shard.aggregate_throughput(n_ev_local, e0.elapsed_time(e1))
+    nl = torch.tensor([launches], dtype=torch.int64, device=dev)
+    dist.all_reduce(nl)
+    img_bytes = fe.split_right_buffer()[1] if rank == shard.LEFT_RANK else 0
+
+    one = None
+    if rank == shard.LEFT_RANK:       # the same windows on one handle, same pipelining
+        fe1 = frontend.EventFrontEnd(cfg)
+        dw = [(frontend._Ev(frontend.DeviceEvents(fe1, L)), frontend._Ev(frontend.DeviceEvents(fe1, R)), t)
+              for L, R, t in wins]
+        ext1 = torch.cuda.ExternalStream(fe1.stream(), device=dev)
+        ref_counts = []
+
+        def run1(k0, n):
+            waited = 0
+            for k in range(k0, k0 + n):
+                fe1.submit(dw[k][2], dw[k][0], dw[k][1], k % pub_div == 0)
+                if k - k0 >= DEPTH - 1:
+                    ref_counts.append(fe1.wait(unpack=False))
+                    waited += 1
+            while waited < n:
+                ref_counts.append(fe1.wait(unpack=False))
+                waited += 1
+
+        run1(0, Wm)
+        flush.fill_(2)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(ext1)
+        run1(Wm, K)
+        f1.record(ext1)
+        torch.cuda.synchronize()
+        ms1 = f0.elapsed_time(f1)
+        n_ev = n_events(wins[Wm:])
+        # last window in full, every window by its feature counts
+        a, b = fe._unpack(), fe1._unpack()
+        same = ref_counts == counts and all(np.array_equal(a[k], b[k]) for k in a if k != "stats")
+        one = {"value": n_ev / (ms1 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms1 / K,
+               "identical_results": bool(same)}
+        fe1.close()
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 2, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(workload),
+            "run": {"parallelism": "lr_split: rank 0 left camera + tracking, rank 1 right camera "
+                                   "SAE/time surface/pyramid",
+                    "inputs": "resident in HBM on the rank that consumes them",
+                    "windows_in_flight": DEPTH},
+            "exchange": {"what": "right pyramid block, NCCL send/recv per window",
+                         "bytes_per_step": int(img_bytes)},
+            "gpu_launches": int(nl.item()), "one_gpu_same_run": one}))
+    fe.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(synth.WORKLOADS))
-    ap.add_argument("--cpu-windows", type=int, default=150)
+    ap.add_argument("--workload", default=None, choices=sorted(synth.WORKLOADS),
+                    help=f"default: {WORKLOAD_N1} at N = 1, {WORKLOAD_NX} at N > 1")
+    ap.add_argument("--cpu-windows", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-rigid", action="store_true", help="skip the rigid-scene record")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[1] / configs[4] records")
     ap.add_argument("--batch-streams", type=int, default=8,
-                    help="streams of the extra batched leg at N=1 (esvio_fe_group); 1 disables it")
-    ap.add_argument("--batch-steps", type=int, default=60)
+                    help="streams of the batched leg at N=1 (esvio_fe_group); 1 disables it")
+    ap.add_argument("--batch-steps", type=int, default=30)
     ap.add_argument("--no-frames", action="store_true", help="skip the trackImage record")
     ap.add_argument("--split-lr", action="store_true",
                     help="2 ranks: one stereo stream split by camera (SURVEY.md 8e row 2)")

@@ -110,6 +110,8 @@ SYMBOLS = {
     "esvio_fe_device_free": (C.c_int, [_H, C.c_void_p]),
     "esvio_fe_copy_to_device": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_size_t]),
     "esvio_fe_result_device_ptr": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "esvio_fe_result_acquire": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "esvio_fe_result_release": (C.c_int, [_H, C.c_void_p]),
     "esvio_fe_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "esvio_fe_split_image_submit": (C.c_int, [_H, C.c_double, C.POINTER(Events), C.c_void_p,
                                               C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),

@@ -310,7 +310,10 @@ struct TrackBuffers {
   float2* prev_un;
   int* prev_un_r_ids;
   float2* prev_un_r;
-  int32_t* result;  // kResultHdr ints + kResultArrays * max_cnt words
+  int32_t* result;  // [kSlots] blocks of kResultHdr ints + kResultArrays * max_cnt words: window k
+                    // packs into block k % kSlots, so a consumer on another stream (the
+                    // all-gather) can still read it while the next windows finalize
+  int result_words;
   // snapshot of (cur_pts, ids, track_cnt, counters) taken at the end of the temporal/selection
   // stage of a window, one per in-flight slot: the stereo stage of window k reads it while
   // the temporal stage of window k+1 already rewrites cur_pts / ids / cnt

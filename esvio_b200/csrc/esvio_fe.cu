@@ -83,6 +83,11 @@ struct esvio_fe {
   int64_t launches;
   int q_head, q_count;  // in-flight windows (results land in h_result[(q_head + k) % kSlots])
   cudaEvent_t q_done[kSlots];
+  // esvio_fe_result_acquire / _release: a consumer stream (the per-window all-gather) reads
+  // the device result block of slot `last_slot`; the slot's next finalize waits for r_free
+  int last_slot;
+  cudaEvent_t r_free[kSlots];
+  int r_held[kSlots];
   int profiling;
   struct esvio_fe_group* group;  // non-null: the event stage is run by the group, batched
   // one set per in-flight slot; [NUM_STAGES+1] = temporal stage start, [+2] = stereo stage start
@@ -228,6 +233,7 @@ static void free_all(esvio_fe* fe) {
     if (fe->t1_done[i]) cudaEventDestroy(fe->t1_done[i]);
     if (fe->h_result[i]) cudaFreeHost(fe->h_result[i]);
     if (fe->q_done[i]) cudaEventDestroy(fe->q_done[i]);
+    if (fe->r_free[i]) cudaEventDestroy(fe->r_free[i]);
   }
   for (int i = 0; i < 2; ++i) {
     cudaFree(fe->esb.bt[i]);
@@ -269,7 +275,7 @@ static int reset_state(esvio_fe* fe) {
   for (int i = 0; i < kNumPyr; ++i) CU(cudaMemsetAsync(fe->pyr[i], 0, fe->pd.bytes, fe->stream));
   CU(cudaMemsetAsync(fe->tb.snap_hdr, 0, sizeof(int) * 16 * kSlots, fe->stream));
   CU(cudaMemsetAsync(fe->tb.st, 0, sizeof(TrackState), fe->stream));
-  CU(cudaMemsetAsync(fe->tb.result, 0, fe->result_words * 4, fe->stream));
+  CU(cudaMemsetAsync(fe->tb.result, 0, fe->result_words * 4 * kSlots, fe->stream));
   CU(cudaStreamSynchronize(fe->stream));
   fe->cur_left = fe->prev_left = 0;
   fe->cur_right = kRightBase;
@@ -277,7 +283,8 @@ static int reset_state(esvio_fe* fe) {
   fe->windows = 0;
   fe->prev_time = 0.0;
   fe->q_head = fe->q_count = 0;
-  for (int k = 0; k < kSlots; ++k) fe->pev_valid[k] = 0;
+  fe->last_slot = -1;
+  for (int k = 0; k < kSlots; ++k) fe->pev_valid[k] = 0, fe->r_held[k] = 0;
   fe->stage_ms_valid = 0;
   return ESVIO_FE_OK;
 }
@@ -414,10 +421,12 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   B.snap_cnt = B.snap_ids + (size_t)M * kSlots;
   CUC(cudaMalloc(&B.snap_hdr, sizeof(int) * 16 * kSlots));
   fe->result_words = kResultHdr + (size_t)kResultArrays * M;
-  CUC(cudaMalloc(&B.result, fe->result_words * 4));
+  B.result_words = (int)fe->result_words;
+  CUC(cudaMalloc(&B.result, fe->result_words * 4 * kSlots));
   for (int i = 0; i < kSlots; ++i) {
     CUC(cudaHostAlloc(&fe->h_result[i], fe->result_words * 4, cudaHostAllocDefault));
     CUC(cudaEventCreateWithFlags(&fe->q_done[i], cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&fe->r_free[i], cudaEventDisableTiming));
   }
   CUC(cudaMalloc(&B.rs, ransac_scratch_bytes()));
   CUC(cudaMemset(B.rs, 0, ransac_scratch_bytes()));
@@ -735,17 +744,23 @@ static int submit_tracking(esvio_fe* fe, const WindowPlan& w, const DevEvents& e
 
   // ---------------- stereo stage (feature_tracker.cpp:470-590) on the snapshot
   CU(cudaStreamWaitEvent(s2, fe->t1_done[slot], 0));
+  if (fe->r_held[slot]) {  // a consumer stream may still read this slot's previous block
+    CU(cudaStreamWaitEvent(s2, fe->r_free[slot], 0));
+    fe->r_held[slot] = 0;
+  }
   prof_mark(fe, ESVIO_FE_NUM_STAGES + 2);
   launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.snap_pts + (size_t)slot * M, B.right_pts,
             B.st_sf, B.rev_left_pts, B.st_sb, B.snap_hdr + slot * 16, M, 3, 0,
             fe->cfg.flow_back ? 2 : 0, s2, &fe->launches);
   launch_finalize(fe->tp, B, slot, cur_time, fe->prev_time, s2, &fe->launches);
   prof_mark(fe, 8);
-  CU(cudaMemcpyAsync(fe->h_result[slot], B.result, fe->result_words * 4, cudaMemcpyDeviceToHost, s2));
+  CU(cudaMemcpyAsync(fe->h_result[slot], B.result + (size_t)slot * fe->result_words, fe->result_words * 4,
+                     cudaMemcpyDeviceToHost, s2));
   prof_mark(fe, 9);
   CU(cudaEventRecord(fe->q_done[slot], s2));
   CU(cudaGetLastError());
   fe->q_count++;
+  fe->last_slot = slot;
   fe->prev_left = prev;
   fe->cur_left = cur;
   fe->cur_right = rcur;
@@ -786,13 +801,14 @@ FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_e
 FE_API int esvio_fe_track_wait(esvio_fe* fe, esvio_tracks* out) {
   if (!fe || !out) return ESVIO_FE_EINVAL;
   if (fe->q_count <= 0) return fail(fe, ESVIO_FE_ESTATE, "wait without submit", cudaSuccess);
+  const int M = fe->cfg.max_cnt;
+  // checked before the window is dequeued: a too-small `out` leaves it waitable
+  if (out->capacity < M) return fail(fe, ESVIO_FE_ECAPACITY, "esvio_tracks.capacity < max_cnt", cudaSuccess);
   CU(cudaSetDevice(fe->dev));
   const int slot = fe->q_head;
   CU(cudaEventSynchronize(fe->q_done[slot]));
   fe->q_head = (fe->q_head + 1) % kSlots;
   fe->q_count--;
-  const int M = fe->cfg.max_cnt;
-  if (out->capacity < M) return fail(fe, ESVIO_FE_ECAPACITY, "esvio_tracks.capacity < max_cnt", cudaSuccess);
   const int32_t* r = fe->h_result[slot];
   const int nl = r[0], nr = r[1];
   out->n_left = nl;
@@ -1015,6 +1031,10 @@ FE_API int esvio_fe_track_image_submit(esvio_fe* fe, double cur_time, const uint
   CU(cudaEventRecord(fe->t1_done[slot], s1));
   // ---- stereo stage (:245-322)
   CU(cudaStreamWaitEvent(s2, fe->t1_done[slot], 0));
+  if (fe->r_held[slot]) {
+    CU(cudaStreamWaitEvent(s2, fe->r_free[slot], 0));
+    fe->r_held[slot] = 0;
+  }
   prof_mark(fe, ESVIO_FE_NUM_STAGES + 2);
   if (right) {
     launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.snap_pts + (size_t)slot * M, B.right_pts,
@@ -1029,11 +1049,13 @@ FE_API int esvio_fe_track_image_submit(esvio_fe* fe, double cur_time, const uint
     launch_right_map_keep(B, 1, s2, &fe->launches);
   }
   prof_mark(fe, 8);
-  CU(cudaMemcpyAsync(fe->h_result[slot], B.result, fe->result_words * 4, cudaMemcpyDeviceToHost, s2));
+  CU(cudaMemcpyAsync(fe->h_result[slot], B.result + (size_t)slot * fe->result_words, fe->result_words * 4,
+                     cudaMemcpyDeviceToHost, s2));
   prof_mark(fe, 9);
   CU(cudaEventRecord(fe->q_done[slot], s2));
   CU(cudaGetLastError());
   fe->q_count++;
+  fe->last_slot = slot;
   fe->prev_left = prev;
   fe->cur_left = cur;
   fe->cur_right = rcur;
@@ -1392,8 +1414,29 @@ FE_API int esvio_fe_copy_to_device(esvio_fe* fe, void* dst, const void* src, siz
 }
 FE_API int esvio_fe_result_device_ptr(esvio_fe* fe, void** ptr, size_t* bytes) {
   if (!fe || !ptr || !bytes) return ESVIO_FE_EINVAL;
-  *ptr = fe->tb.result;
+  const int slot = fe->last_slot < 0 ? 0 : fe->last_slot;
+  *ptr = fe->tb.result + (size_t)slot * fe->result_words;
   *bytes = fe->result_words * 4;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_result_acquire(esvio_fe* fe, void* consumer_stream, void** ptr, size_t* bytes) {
+  if (!fe || !ptr || !bytes) return ESVIO_FE_EINVAL;
+  if (fe->last_slot < 0) return fail(fe, ESVIO_FE_ESTATE, "no window submitted yet", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  const int slot = fe->last_slot;
+  CU(cudaStreamWaitEvent((cudaStream_t)consumer_stream, fe->q_done[slot], 0));
+  *ptr = fe->tb.result + (size_t)slot * fe->result_words;
+  *bytes = fe->result_words * 4;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_result_release(esvio_fe* fe, void* consumer_stream) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  if (fe->last_slot < 0) return fail(fe, ESVIO_FE_ESTATE, "no window submitted yet", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  CU(cudaEventRecord(fe->r_free[fe->last_slot], (cudaStream_t)consumer_stream));
+  fe->r_held[fe->last_slot] = 1;
   return ESVIO_FE_OK;
 }
 FE_API int esvio_fe_stream(esvio_fe* fe, void** cuda_stream) {

@@ -524,7 +524,7 @@ k_finalize(TrackParams P, TrackBuffers B, int slot, double cur_time, double prev
   const int* s_ids = B.snap_ids + slot * M;
   const int* s_cnt = B.snap_cnt + slot * M;
   const int n = hdr[0];
-  int32_t* res = B.result;
+  int32_t* res = B.result + (size_t)slot * B.result_words;
   int32_t* r_id = res + kResultHdr;
   int32_t* r_cnt = r_id + M;
   float* r_u = reinterpret_cast<float*>(r_cnt + M);

@@ -319,6 +319,18 @@ class EventFrontEnd:
                   "result_device_ptr")
         return p.value, n.value
 
+    def result_acquire(self, consumer_stream=0):
+        """(device pointer, bytes) of the last submitted window's packed records, ordered on
+        `consumer_stream` (cudaStream_t); pair with result_release()."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._chk(_capi.lib().esvio_fe_result_acquire(self._h, C.c_void_p(consumer_stream),
+                                                      C.byref(p), C.byref(n)), "result_acquire")
+        return p.value, n.value
+
+    def result_release(self, consumer_stream=0):
+        self._chk(_capi.lib().esvio_fe_result_release(self._h, C.c_void_p(consumer_stream)),
+                  "result_release")
+
     def stream(self):
         s = C.c_void_p()
         self._chk(_capi.lib().esvio_fe_stream(self._h, C.byref(s)), "stream")

@@ -38,10 +38,17 @@ def _u01(bits: np.ndarray) -> np.ndarray:
 
 
 class Scene:
-    """64 rectangles: side 12-40 px, velocity in [-150, 150] px/s, disparity 2-20 px."""
+    """64 rectangles: side 12-40 px, velocity in [-150, 150] px/s, disparity 2-20 px.
+
+    `rigid=True` is the second scene of the benchmarks: the same rectangles as a STATIC world
+    seen by a camera that translates parallel to its image plane, so every rectangle moves in
+    one common direction with a speed proportional to its disparity (inverse depth).  All
+    correspondences then share one epipolar geometry, as on a real sequence, and
+    cv::findFundamentalMat (feature_tracker.cpp:935) exits early instead of running its full
+    iteration budget the way it does on 64 independently moving objects."""
 
     def __init__(self, width: int, height: int, seed: int = 42, n_rect: int = 64,
-                 max_speed: float = 150.0):
+                 max_speed: float = 150.0, rigid: bool = False):
         self.W, self.H, self.n = width, height, n_rect
         r = _u01(splitmix64(seed, np.arange(n_rect * 7))).reshape(n_rect, 7)
         self.w = 12.0 + 28.0 * r[:, 0]
@@ -51,6 +58,12 @@ class Scene:
         self.vx = (2.0 * r[:, 4] - 1.0) * max_speed
         self.vy = (2.0 * r[:, 5] - 1.0) * max_speed
         self.disp = 2.0 + 18.0 * r[:, 6]
+        self.rigid = bool(rigid)
+        if rigid:
+            theta = 2.0 * np.pi * float(_u01(splitmix64(seed ^ 0x5EED, np.arange(1)))[0])
+            speed = max_speed * self.disp / 20.0
+            self.vx = speed * np.cos(theta)
+            self.vy = speed * np.sin(theta)
 
 
 class StereoEventStream:
@@ -58,12 +71,12 @@ class StereoEventStream:
 
     def __init__(self, width: int, height: int, rate: float, stream: int = 0,
                  scene_seed: int = 42, noise: float = 0.1, mono: bool = False,
-                 max_speed: float = 150.0):
+                 max_speed: float = 150.0, rigid: bool = False):
         self.W, self.H = width, height
         self.rate = float(rate)
         self.mono = mono
         self.noise = noise
-        self.scene = Scene(width, height, scene_seed + 10 * stream, max_speed=max_speed)
+        self.scene = Scene(width, height, scene_seed + 10 * stream, max_speed=max_speed, rigid=rigid)
         self.seeds = (1001 + 10 * stream, 2002 + 10 * stream)
         self.events_per_window = int(round(self.rate / WINDOWS_PER_SEC))
 
@@ -157,6 +170,8 @@ def default_config(width: int, height: int, **kw) -> dict:
     cfg.update(kw)
     return cfg
 
+
+SCENES = ("survey", "rigid")   # SURVEY.md 8d's 64 independent movers | one rigid world (Scene)
 
 # BASELINE.json configs
 WORKLOADS = {

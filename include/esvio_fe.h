@@ -244,6 +244,14 @@ int esvio_fe_copy_to_device(esvio_fe *fe, void *dst, const void *src, size_t byt
  * (all-gather) per window; and the handle's cudaStream_t. */
 int esvio_fe_result_device_ptr(esvio_fe *fe, void **ptr, size_t *bytes);
 int esvio_fe_stream(esvio_fe *fe, void **cuda_stream);
+/* The same block for a consumer on a stream of its own (the all-gather of a publish window,
+ * kept off the tracking streams): _acquire makes `consumer_stream` (cudaStream_t) wait for the
+ * most recently submitted window's packed records and returns their device address (every
+ * in-flight window has its own block); after enqueuing its reads the caller calls _release on
+ * the same stream, and the block is not rewritten (three windows later) before those reads
+ * have finished.  No host synchronisation on either side. */
+int esvio_fe_result_acquire(esvio_fe *fe, void *consumer_stream, void **ptr, size_t *bytes);
+int esvio_fe_result_release(esvio_fe *fe, void *consumer_stream);
 
 /* Left/right split of ONE stereo stream over two GPUs.  The right camera
  * only feeds its pyramid to the stereo LK (feature_tracker.cpp:475-495), so its createSAE_right /
