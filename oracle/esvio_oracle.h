@@ -28,9 +28,21 @@
  * the build container by tests/golden/make_golden.py).
  *
  * Parity status: the reference ships no tests, fixtures or golden vectors for
- * this path, so parity of the reference-authored stages is
- * UNPINNED by reference tests; the OpenCV-derived stages are pinned against
- * real OpenCV (cv2) outputs committed under tests/golden/.
+ * this path.  What pins this oracle instead:
+ *   - SAE update, time surface, Arc* and the motion-compensated update are checked
+ *     against the REFERENCE'S OWN CODE: oracle/_ref/libesvio_ref.so is
+ *     event_detector.cc compiled unmodified from /root/reference against stand-in
+ *     Eigen/OpenCV/ROS headers (oracle/ref_shim/, recipe in oracle/Makefile);
+ *     tests/test_oracle_ref.py demands identical planes, time surfaces and corner
+ *     decisions on the synthetic streams.  (For motion compensation the stand-in's
+ *     Matrix3f arithmetic is this file's statement of Eigen's kernels, so there the
+ *     reference's control flow is pinned and Eigen's float kernels are not.)
+ *   - the OpenCV-derived stages are pinned against real OpenCV (cv2) outputs
+ *     committed under tests/golden/.
+ *   - the bookkeeping of feature_tracker.cpp (mask, selection order, compaction,
+ *     velocity, packing) has no compilable reference here (it needs OpenCV C++ and
+ *     camodocal): PARITY UNPINNED for those, beyond hand-written known answers
+ *     (tests/test_oracle_kat.py).
  */
 #ifndef ESVIO_ORACLE_H
 #define ESVIO_ORACLE_H
