@@ -112,6 +112,18 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
+// The same fold without a loop, for |overshoot| < 2n - 2 (two folds): LK only ever reaches at
+// most 43 pixels beyond an image whose sides are >= 22.  Being branch-free matters: a batch of
+// loads whose addresses go through reflect101()'s loop is issued one by one behind the loop's
+// branches, each paying its own trip to L2 (measured: 32 staging loads took 9 800 cycles,
+// profiles/r2_lk_phases.txt).
+__device__ __forceinline__ int reflect101_nb(int i, int n) {
+  int a = abs(i);
+  a = min(a, 2 * n - 2 - a);
+  a = abs(a);
+  return min(a, 2 * n - 2 - a);
+}
+
 // cvRound(float): round half to even
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 

@@ -96,6 +96,8 @@ struct esvio_fe {
   int pev_valid[kSlots];
   int stage_ms_valid;
   float stage_ms[ESVIO_FE_NUM_STAGES];
+  cudaEvent_t pev_ref;  // recorded by esvio_fe_set_profiling(on): origin of stage_marks
+  float stage_marks[ESVIO_FE_NUM_MARKS];
 };
 
 static int fail(esvio_fe* fe, int code, const char* what, cudaError_t ce) {
@@ -261,6 +263,7 @@ static void free_all(esvio_fe* fe) {
   for (int k = 0; k < kSlots; ++k)
     for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 2; ++i)
       if (fe->pev[k][i]) cudaEventDestroy(fe->pev[k][i]);
+  if (fe->pev_ref) cudaEventDestroy(fe->pev_ref);
   if (fe->stream_c) cudaStreamDestroy(fe->stream_c);
   if (fe->stream_e) cudaStreamDestroy(fe->stream_e);
   if (fe->stream_t1) cudaStreamDestroy(fe->stream_t1);
@@ -447,6 +450,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   CUC(cudaMalloc(&fe->d_scratch_st, kMaxCnt));
   for (int k = 0; k < kSlots; ++k)
     for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 2; ++i) CUC(cudaEventCreate(&fe->pev[k][i]));
+  CUC(cudaEventCreate(&fe->pev_ref));
 #undef CUC
 
   if (cfg->mc_fx > 0.0) {
@@ -836,6 +840,11 @@ FE_API int esvio_fe_track_wait(esvio_fe* fe, esvio_tracks* out) {
                            fe->pev[slot][i == 5 ? ESVIO_FE_NUM_STAGES + 1
                                                 : (i == 7 ? ESVIO_FE_NUM_STAGES + 2 : i)],
                            fe->pev[slot][i + 1]);
+    for (int i = 0; i < ESVIO_FE_NUM_MARKS; ++i)
+      if (cudaEventElapsedTime(&fe->stage_marks[i], fe->pev_ref, fe->pev[slot][i]) != cudaSuccess) {
+        fe->stage_marks[i] = -1.f;
+        cudaGetLastError();
+      }
     fe->stage_ms_valid = 1;
     fe->pev_valid[slot] = 0;
   }
@@ -1448,6 +1457,16 @@ FE_API int esvio_fe_set_profiling(esvio_fe* fe, int32_t on) {
   if (!fe) return ESVIO_FE_EINVAL;
   fe->profiling = on != 0;
   fe->stage_ms_valid = 0;
+  if (on) {
+    CU(cudaSetDevice(fe->dev));
+    CU(cudaEventRecord(fe->pev_ref, fe->stream));
+  }
+  return ESVIO_FE_OK;
+}
+FE_API int esvio_fe_get_stage_marks(esvio_fe* fe, float* ms) {
+  if (!fe || !ms) return ESVIO_FE_EINVAL;
+  if (!fe->stage_ms_valid) return fail(fe, ESVIO_FE_ESTATE, "no profiled window", cudaSuccess);
+  memcpy(ms, fe->stage_marks, sizeof(fe->stage_marks));
   return ESVIO_FE_OK;
 }
 FE_API int esvio_fe_get_stage_ms(esvio_fe* fe, float* ms) {

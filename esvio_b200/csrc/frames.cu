@@ -31,12 +31,12 @@ k_gftt_cov(const uint8_t* __restrict__ img, int pitch, int W, int H, float* __re
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= W || y >= H) return;
   const float k1 = (float)(1.0 / 3060.0), k0 = (float)(2.0 * (1.0 / 3060.0));
-  const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+  const int xm = reflect101_nb(x - 1, W), xp = reflect101_nb(x + 1, W);
   const bool body = x < (W / 32) * 32;
   float d[3], s[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const uint8_t* row = img + (size_t)reflect101(y - 1 + r, H) * pitch;
+    const uint8_t* row = img + (size_t)reflect101_nb(y - 1 + r, H) * pitch;
     const float a = (float)row[xm], b = (float)row[x], c = (float)row[xp];
     d[r] = c - a;
     s[r] = body ? fmaf(c, k1, fmaf(b, k0, a * k1)) : (a * k1 + b * k0) + c * k1;
@@ -66,11 +66,11 @@ k_gftt_eig(const float* __restrict__ cxx, const float* __restrict__ cxy,
            const float* __restrict__ cyy, int W, int H, float* __restrict__ eig) {
   const int x = blockIdx.x * kEigThreads + threadIdx.x;
   if (x >= W) return;
-  const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+  const int xm = reflect101_nb(x - 1, W), xp = reflect101_nb(x + 1, W);
   const float* pl[3] = {cxx, cxy, cyy};
   double r0[3], r1[3], sum[3];
   {
-    const size_t ra = (size_t)reflect101(-1, H) * W, rb = 0;
+    const size_t ra = (size_t)reflect101_nb(-1, H) * W, rb = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       r0[c] = row_sum3(pl[c], ra, xm, x, xp);
@@ -80,7 +80,7 @@ k_gftt_eig(const float* __restrict__ cxx, const float* __restrict__ cxy,
   }
 #pragma unroll 4
   for (int y = 0; y < H; ++y) {
-    const size_t rn = (size_t)reflect101(y + 1, H) * W;
+    const size_t rn = (size_t)reflect101_nb(y + 1, H) * W;
     float cv[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

@@ -108,7 +108,7 @@ k_clahe_lut(ClaheGeom g, const uint8_t* __restrict__ src0, const uint8_t* __rest
   __syncthreads();
   for (int i = tid; i < g.tw * g.th; i += 256) {
     const int py = i / g.tw, px = i - py * g.tw;
-    const int sx = reflect101(tx * g.tw + px, g.W), sy = reflect101(ty * g.th + py, g.H);
+    const int sx = reflect101_nb(tx * g.tw + px, g.W), sy = reflect101_nb(ty * g.th + py, g.H);
     atomicAdd(&s_hist[src[(size_t)sy * g.pitch + sx]], 1);
   }
   __syncthreads();

@@ -6,28 +6,61 @@
 // modules/video/src/lkpyramid.cpp -- not part of the reference tree; arithmetic spec in
 // SURVEY.md section 8a).
 //
-// One CTA of 128 threads tracks one point through all pyramid levels, forward and (when
-// asked) straight on into the backward check, inside a single launch.  Per level the
-// template neighbourhood (24x24 intensities, 22x22 Scharr derivatives) and a 32x32 search
-// region of J are staged in shared memory, so the <= 30 Newton iterations touch no global
-// memory; the region is re-staged only if the window walks out of it.  The template
-// (Iw, Ixw, Iyw) lives in registers, <= 4 pixels per thread; the normal-equation sums
-// A11,A12,A22 and b1,b2 are accumulated as exact integers (redux.sync inside a warp,
-// shared memory across the 4 warps) and rounded to float once -- OpenCV accumulates the
-// same integers in float, so results agree to float rounding (~1e-4 px).
+// One CTA of 256 threads tracks one point through all pyramid levels, forward and (when
+// asked) straight on into the backward check, inside a single launch.  The kernel is
+// latency-bound (a point is one dependent chain of <= 4 levels x 30 Newton iterations, and a
+// launch is as slow as its slowest point), so everything is organised around the length of
+// that chain:
+//   * set-up (all 8 warps): the 24x24 intensity patches of ALL levels and the search region of
+//     the top level are fetched in ONE batch of independent loads (addresses are branch-free:
+//     reflect101_nb), then the Scharr patches and the templates of all levels are built, two
+//     warps per level;
+//   * Newton iterations (warps 0-3, the "N group"): the 441 window pixels are split over 128
+//     threads (<= 4 each, template in registers, search region in shared memory as packed 2x2
+//     neighbourhoods + dp4a); the sums are exact integers: redux.sync inside a warp, one
+//     16-byte shared-memory slot per warp, ONE named barrier per iteration, after which every
+//     thread adds the four partials and runs the same 2x2 solve and stopping rules;
+//   * staging (warps 4-7, the "S group"): while the N group iterates on level L, the S group
+//     fetches the search region of level L-1 around the predicted position 2*p into the other
+//     buffer, so the trip to L2 hides behind the iterations; a level only re-stages when the
+//     prediction misses by more than the 5-pixel margin.
+// OpenCV accumulates the same integers in float, so results agree to float rounding
+// (~1e-4 px); against the round-1 kernel (one warp iterating) they are bit-identical.
 #include <float.h>
 
 #include "common.cuh"
 
 namespace esvio {
 
+#ifdef ESVIO_LK_CLOCKS  // scratch builds only (make EXTRA=-DESVIO_LK_CLOCKS): per-phase clock64 of every CTA
+__device__ long long g_lk_clk[1024][2][24];
+#define LK_CLK(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_lk_clk[blockIdx.x][clk_call][i] = clock64(); } while (0)
+#define LK_VAL(i, v) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_lk_clk[blockIdx.x][clk_call][i] = (v); } while (0)
+extern "C" __attribute__((visibility("default"))) int esvio_dbg_lk_clocks(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_lk_clk, sizeof(g_lk_clk));
+}
+#else
+#define LK_CLK(i)
+#define LK_VAL(i, v)
+#endif
+
 constexpr int kWBits = 14;
-constexpr int kLkThreads = 128;
-constexpr int kPxPerLane = (kWin * kWin + 31) / 32;  // 14
+constexpr int kLkThreads = 256;
+constexpr int kLkWarps = kLkThreads / 32;
+constexpr int kNThreads = 128;                     // Newton group: warps 0-3
+constexpr int kNWarps = kNThreads / 32;
+constexpr int kPxN = (kWin * kWin + kNThreads - 1) / kNThreads;  // 4 window pixels per thread
+constexpr int kTplWarps = 2;                       // warps per level in the template phase
+constexpr int kPxT = (kWin * kWin + 32 * kTplWarps - 1) / (32 * kTplWarps);  // 7
+constexpr int kTplLen = 32 * kTplWarps * kPxT;     // 448 template slots per level
 constexpr int kIP = 24;  // staged intensity patch (window + bilinear tap + Scharr ring)
 constexpr int kDP = 22;  // derivative patch (window + bilinear tap)
 constexpr int kJM = 5;   // margin of the staged search region
 constexpr int kJR = kWin + 1 + 2 * kJM;  // 32
+// Row stride of the search region in 32-bit words: 21 (mod 32), so that the word of window
+// pixel k = 21 * y + x sits in bank (k + const) % 32 and 32 consecutive pixels never collide.
+constexpr int kQS = 53;
+static_assert(kMaxLevels * kTplWarps == kLkWarps, "two warps per level in the template phase");
 
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
@@ -42,16 +75,17 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
 struct LkShared {
   uint8_t I[kMaxLevels][kIP][kIP];      // template neighbourhoods of all levels
   short2 D[kMaxLevels][kDP][kDP];       // their Scharr derivatives
-  short Tw[kMaxLevels][kPxPerLane * 32];  // templates: Iw, Ixw, Iyw per window pixel
-  short Tx[kMaxLevels][kPxPerLane * 32];
-  short Ty[kMaxLevels][kPxPerLane * 32];
-  float A[kMaxLevels][3];
-  int flag[kMaxLevels];  // 0 ok, 1 template window outside the image, 2 minEig / det test failed
-  // search region of the level being iterated, as packed 2x2 neighbourhoods:
+  short Tw[kMaxLevels][kTplLen];        // templates: Iw, Ixw, Iyw per window pixel
+  short Tx[kMaxLevels][kTplLen];
+  short Ty[kMaxLevels][kTplLen];
+  long long Apart[kMaxLevels][kTplWarps][3];  // per-warp sums of Ixw^2, Ixw*Iyw, Iyw^2
+  int flag_win[kMaxLevels];             // 1: template window outside the image
+  // search regions (current level / prefetched next level) as packed 2x2 neighbourhoods:
   // Q[r][c] = J(r,c) | J(r,c+1) << 8 | J(r+1,c) << 16 | J(r+1,c+1) << 24
-  uint32_t Q[kJR][kJR];
-  float2 np;
-  int st;
+  uint32_t Q[2][kJR][kQS];
+  longlong2 part[2][kNWarps];           // per-iteration partial sums (b1, b2) of the N-group warps
+  float2 np[2];                         // result of a level, slot = Newton levels run so far & 1
+  int st[2];
 };
 
 // exact sum over the warp of one int32 per lane, as int64
@@ -61,53 +95,79 @@ __device__ __forceinline__ long long warp_sum_exact(int v) {
   return ((long long)hi << 16) + (long long)lo;
 }
 
-// exact warp sum of one int32 per lane, rounded to float once: the total is hi * 65536 + lo
-// with |hi| < 2^24 and lo < 2^24, so both terms are exact floats and their sum rounds once
-__device__ __forceinline__ float warp_sum_to_float(int v) {
-  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
-  const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
-  return (float)hi * 65536.f + (float)lo;
-}
+// barrier of the 128 threads of the N group (barrier 0 is __syncthreads of the whole CTA)
+__device__ __forceinline__ void bar_newton() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// one warp: lane = column; the column bytes are loaded with all 32 row loads in flight, paired
-// with the right-hand neighbour's by a shuffle and packed with the row below
-__device__ __forceinline__ void stage_J(LkShared& S, const uint8_t* __restrict__ Jl, int w, int h,
-                                        int pitch, int rx0, int ry0) {
+// Stage the kJR x kJR search region with origin (rx0, ry0) of one level of J into Q.  Warp
+// `wi` of NW cooperating warps owns kJR / NW rows: lane = column; every lane issues its row
+// loads back to back (one trip to L2 for the lot), pairs each byte with the right-hand
+// neighbour's by a shuffle and packs it with the row below.
+template <int NW>
+__device__ __forceinline__ void stage_J(uint32_t (*Q)[kQS], const uint8_t* __restrict__ Jl, int w,
+                                        int h, int pitch, int rx0, int ry0, int wi) {
+  constexpr int kRows = kJR / NW;
   const int lane = lane_id();
-  const int gx = reflect101(rx0 + lane, w);
-  uint32_t col[kJR];
+  const int gx = reflect101_nb(rx0 + lane, w);
+  const int r0 = wi * kRows;
+  uint32_t col[kRows + 1];
 #pragma unroll
-  for (int r = 0; r < kJR; ++r) col[r] = Jl[(size_t)reflect101(ry0 + r, h) * pitch + gx];
+  for (int r = 0; r <= kRows; ++r)
+    col[r] = __ldg(Jl + (size_t)reflect101_nb(ry0 + r0 + r, h) * pitch + gx);
 #pragma unroll
-  for (int r = 0; r < kJR; ++r) col[r] |= __shfl_down_sync(0xffffffffu, col[r], 1) << 8;
+  for (int r = 0; r <= kRows; ++r) col[r] |= __shfl_down_sync(0xffffffffu, col[r], 1) << 8;
 #pragma unroll
-  for (int r = 0; r + 1 < kJR; ++r) S.Q[r][lane] = col[r] | (col[r + 1] << 16);
-  __syncwarp();
+  for (int r = 0; r < kRows; ++r) Q[r0 + r][lane] = col[r] | (col[r + 1] << 16);
 }
 
-// One calcOpticalFlowPyrLK call for one point, run by the whole CTA:
-//   phase 1-2 (all threads)  stage the 24x24 intensity patches and 22x22 Scharr patches of ALL
-//                            levels at once (they depend only on the point, not on the flow):
-//                            intensities reflect-101 outside the image like the border
-//                            buildOpticalFlowPyramid adds, derivatives zero outside the image
-//                            like the constant border of the derivative buffer
-//   phase 3 (warp L)         template + normal matrix of level L
-//   phase 4 (warp 0)         coarse-to-fine Newton iterations; <= 14 pixels per lane in
-//                            registers, the J search region in shared memory
-// Every thread returns the same (np, status).
+struct Region {
+  int level, rx0, ry0;  // level -1: nothing staged
+};
+
+__device__ __forceinline__ bool region_covers(const Region& g, int level, int inx, int iny) {
+  return g.level == level && inx >= g.rx0 && iny >= g.ry0 && inx + kWin <= g.rx0 + kJR - 1 &&
+         iny + kWin <= g.ry0 + kJR - 1;
+}
+
+// the region of level `level` (image w x h) around window origin floor(p - half); level -1
+// if that window lies outside the image (OpenCV then gives up on the level)
+__device__ __forceinline__ Region region_around(int level, int w, int h, float px, float py) {
+  const int inx = (int)floorf(px - (float)kHalfWin), iny = (int)floorf(py - (float)kHalfWin);
+  Region g;
+  g.level = (inx < -kWin || inx >= w || iny < -kWin || iny >= h) ? -1 : level;
+  g.rx0 = inx - kJM;
+  g.ry0 = iny - kJM;
+  return g;
+}
+
+// One calcOpticalFlowPyrLK call for one point, run by the whole CTA.  Every thread returns
+// the same (np, status).
 __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restrict__ I,
                          const uint8_t* __restrict__ J, float2 p0, float2 init, int use_init,
-                         int top, float2& np_out, int& st_out) {
+                         int top, float2& np_out, int& st_out, int clk_call = 0) {
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   const float half = (float)kHalfWin;
   const float flt_scale = 1.f / (float)(1 << 20);
   const int nlev = top + 1;
-  __syncthreads();  // previous use of S is over
-  // ---- phase 1: intensity patches of all levels.  All of a thread's (<= 18) global loads are
-  // issued before the first store, so they share one round trip to L2 instead of queueing
-  // one behind the other.
+  const bool n_group = tid < kNThreads;
+
+  // position at the top level (OpenCV: nextPt = prevPt, or the initial flow, scaled)
+  float2 np;
   {
-    constexpr int kPerThread = (kMaxLevels * kIP * kIP + kLkThreads - 1) / kLkThreads;  // 18
+    const float sc = 1.f / (float)(1 << top);
+    np = use_init ? make_float2(init.x * sc, init.y * sc) : make_float2(p0.x * sc, p0.y * sc);
+  }
+  // what the two search-region buffers hold: rc = S.Q[cur] (the level being iterated), rn =
+  // S.Q[cur ^ 1] (the prefetched next level)
+  Region rc = region_around(top, pd.w[top], pd.h[top], np.x, np.y), rn;
+  rn.level = -1;
+  __syncthreads();  // previous use of S is over
+  LK_CLK(0);
+
+  // ---- phase 1: ONE batch of loads: the intensity patches of all levels (they depend on the
+  // point only, not on the flow) and the search region of the top level around `np`.
+  // Intensities reflect-101 outside the image like the border buildOpticalFlowPyramid adds.
+  {
+    constexpr int kPerThread = (kMaxLevels * kIP * kIP + kLkThreads - 1) / kLkThreads;  // 9
     uint8_t v[kPerThread];
 #pragma unroll
     for (int q = 0; q < kPerThread; ++q) {
@@ -120,10 +180,13 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
         const int ipx = (int)floorf(p0.x * sc - half), ipy = (int)floorf(p0.y * sc - half);
         const int w = pd.w[L], h = pd.h[L];
         if (!(ipx < -kWin || ipx >= w || ipy < -kWin || ipy >= h))
-          v[q] = __ldg(I + pd.off[L] + (size_t)reflect101(ipy - 1 + r, h) * pd.pitch[L] +
-                       reflect101(ipx - 1 + c, w));
+          v[q] = __ldg(I + pd.off[L] + (size_t)reflect101_nb(ipy - 1 + r, h) * pd.pitch[L] +
+                       reflect101_nb(ipx - 1 + c, w));
       }
     }
+    if (rc.level >= 0)
+      stage_J<kLkWarps>(S.Q[0], J + pd.off[top], pd.w[top], pd.h[top], pd.pitch[top], rc.rx0,
+                        rc.ry0, warp);
 #pragma unroll
     for (int q = 0; q < kPerThread; ++q) {
       const int i = tid + q * kLkThreads;
@@ -131,7 +194,10 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
     }
   }
   __syncthreads();
-  // ---- phase 2: Scharr derivatives
+  LK_CLK(1);
+  // ---- phase 2: Scharr derivatives, zero outside the image like the constant border of
+  // OpenCV's derivative buffer
+#pragma unroll 4
   for (int i = tid; i < nlev * kDP * kDP; i += kLkThreads) {
     const int L = i / (kDP * kDP), rem = i - L * (kDP * kDP);
     const int r = rem / kDP, c = rem - r * kDP;
@@ -150,116 +216,141 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
     S.D[L][r][c] = d;
   }
   __syncthreads();
-  // ---- phase 3: warp L builds the template of level L
-  if (warp < nlev) {
-    const int L = warp;
-    const float sc = 1.f / (float)(1 << L);
-    const float ppx = p0.x * sc - half, ppy = p0.y * sc - half;
-    const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
-    int flag = 0;
-    if (ipx < -kWin || ipx >= pd.w[L] || ipy < -kWin || ipy >= pd.h[L]) {
-      flag = 1;
-    } else {
-      const float a = ppx - (float)ipx, b = ppy - (float)ipy;
-      int iw00, iw01, iw10, iw11;
-      bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-      int s11 = 0, s12 = 0, s22 = 0;
+  LK_CLK(2);
+  // ---- phase 3: warps 2L and 2L+1 build the template of level L
+  {
+    const int L = warp / kTplWarps, sub = warp % kTplWarps;
+    if (L < nlev) {
+      const float sc = 1.f / (float)(1 << L);
+      const float ppx = p0.x * sc - half, ppy = p0.y * sc - half;
+      const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
+      const bool outside = ipx < -kWin || ipx >= pd.w[L] || ipy < -kWin || ipy >= pd.h[L];
+      if (sub == 0 && lane == 0) S.flag_win[L] = outside ? 1 : 0;
+      if (!outside) {
+        const float a = ppx - (float)ipx, b = ppy - (float)ipy;
+        int iw00, iw01, iw10, iw11;
+        bilinear_weights(a, b, iw00, iw01, iw10, iw11);
+        int s11 = 0, s12 = 0, s22 = 0;
 #pragma unroll
-      for (int j = 0; j < kPxPerLane; ++j) {
-        const int kk = lane + 32 * j;
-        int iv = 0, ix = 0, iy = 0;
-        if (kk < kWin * kWin) {
-          const int y = kk / kWin, x = kk - y * kWin;
-          iv = descale(S.I[L][y + 1][x + 1] * iw00 + S.I[L][y + 1][x + 2] * iw01 +
-                           S.I[L][y + 2][x + 1] * iw10 + S.I[L][y + 2][x + 2] * iw11,
-                       kWBits - 5);
-          const short2 d00 = S.D[L][y][x], d01 = S.D[L][y][x + 1], d10 = S.D[L][y + 1][x],
-                       d11 = S.D[L][y + 1][x + 1];
-          ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, kWBits);
-          iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, kWBits);
-          s11 += ix * ix;
-          s12 += ix * iy;
-          s22 += iy * iy;
+        for (int j = 0; j < kPxT; ++j) {
+          const int kk = sub * 32 + lane + 32 * kTplWarps * j;
+          int iv = 0, ix = 0, iy = 0;
+          if (kk < kWin * kWin) {
+            const int y = kk / kWin, x = kk - y * kWin;
+            iv = descale(S.I[L][y + 1][x + 1] * iw00 + S.I[L][y + 1][x + 2] * iw01 +
+                             S.I[L][y + 2][x + 1] * iw10 + S.I[L][y + 2][x + 2] * iw11,
+                         kWBits - 5);
+            const short2 d00 = S.D[L][y][x], d01 = S.D[L][y][x + 1], d10 = S.D[L][y + 1][x],
+                         d11 = S.D[L][y + 1][x + 1];
+            ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, kWBits);
+            iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, kWBits);
+            s11 += ix * ix;
+            s12 += ix * iy;
+            s22 += iy * iy;
+          }
+          S.Tw[L][kk] = (short)iv;
+          S.Tx[L][kk] = (short)ix;
+          S.Ty[L][kk] = (short)iy;
         }
-        S.Tw[L][kk] = (short)iv;
-        S.Tx[L][kk] = (short)ix;
-        S.Ty[L][kk] = (short)iy;
-      }
-      const float A11 = (float)warp_sum_exact(s11) * flt_scale;
-      const float A12 = (float)warp_sum_exact(s12) * flt_scale;
-      const float A22 = (float)warp_sum_exact(s22) * flt_scale;
-      const float D = A11 * A22 - A12 * A12;
-      const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) /
-                            (float)(2 * kWin * kWin);
-      if ((double)min_eig < 1e-4 || D < FLT_EPSILON) flag = 2;
-      if (lane == 0) {
-        S.A[L][0] = A11;
-        S.A[L][1] = A12;
-        S.A[L][2] = A22;
+        const long long t11 = warp_sum_exact(s11), t12 = warp_sum_exact(s12),
+                        t22 = warp_sum_exact(s22);
+        if (lane == 0) {
+          S.Apart[L][sub][0] = t11;
+          S.Apart[L][sub][1] = t12;
+          S.Apart[L][sub][2] = t22;
+        }
       }
     }
-    if (lane == 0) S.flag[L] = flag;
   }
   __syncthreads();
-  // ---- phase 4: warp 0 iterates, coarse to fine
-  if (warp == 0) {
-    float2 np = use_init ? init : make_float2(0.f, 0.f);
-    int st = 1;
-    const double eps2 = 0.01 * 0.01;
-    int joff[kPxPerLane];
+  LK_CLK(3);
+
+  // ---- phase 4: coarse to fine.  The N group iterates, the S group prefetches the next level.
+  int st = 1;
+  int cur = 0;       // which Q buffer holds the level being iterated
+  int n_newton = 0;  // levels iterated so far (slot of S.np / S.st)
+  const double eps2 = 0.01 * 0.01;
+  int joff[kPxN];
 #pragma unroll
-    for (int j = 0; j < kPxPerLane; ++j) {
-      const int kk = lane + 32 * j;
-      const int y = kk / kWin, x = kk - y * kWin;
-      joff[j] = kk < kWin * kWin ? y * kJR + x : 0;  // in 32-bit words
+  for (int j = 0; j < kPxN; ++j) {
+    const int kk = tid + kNThreads * j;
+    const int y = kk / kWin, x = kk - y * kWin;
+    joff[j] = (n_group && kk < kWin * kWin) ? y * kQS + x : 0;  // in 32-bit words
+  }
+  for (int level = top; level >= 0; --level) {
+    const int w = pd.w[level], h = pd.h[level], pitch = pd.pitch[level];
+    const uint8_t* __restrict__ Jl = J + pd.off[level];
+    if (level != top) {
+      np.x *= 2.f;
+      np.y *= 2.f;
     }
-    for (int level = top; level >= 0; --level) {
-      const int w = pd.w[level], h = pd.h[level], pitch = pd.pitch[level];
-      const uint8_t* __restrict__ Jl = J + pd.off[level];
-      const float sc = 1.f / (float)(1 << level);
-      if (level == top) {
-        if (use_init) {
-          np.x *= sc;
-          np.y *= sc;
-        } else {
-          np.x = p0.x * sc;
-          np.y = p0.y * sc;
-        }
-      } else {
-        np.x *= 2.f;
-        np.y *= 2.f;
+    // normal matrix of the level: every thread, from the exact integer sums
+    float A11 = 0.f, A12 = 0.f, A22 = 0.f;
+    int flag = S.flag_win[level];
+    if (!flag) {
+      A11 = (float)(S.Apart[level][0][0] + S.Apart[level][1][0]) * flt_scale;
+      A12 = (float)(S.Apart[level][0][1] + S.Apart[level][1][1]) * flt_scale;
+      A22 = (float)(S.Apart[level][0][2] + S.Apart[level][1][2]) * flt_scale;
+      const float det = A11 * A22 - A12 * A12;
+      const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) /
+                            (float)(2 * kWin * kWin);
+      if ((double)min_eig < 1e-4 || det < FLT_EPSILON) flag = 2;
+    }
+    if (flag != 0) {  // template window outside the image, or minEig / determinant test failed
+      if (level == 0) st = 0;
+      continue;
+    }
+    const float D = 1.f / (A11 * A22 - A12 * A12);
+    LK_CLK(4 + 4 * level);
+    // the current buffer must hold this level around the start position (it does when the
+    // prefetch of the level above predicted well, and for the top level from phase 1)
+    {
+      const Region want = region_around(level, w, h, np.x, np.y);
+      if (want.level >= 0 && !region_covers(rc, level, want.rx0 + kJM, want.ry0 + kJM)) {
+        rc = want;
+        stage_J<kLkWarps>(S.Q[cur], Jl, w, h, pitch, want.rx0, want.ry0, warp);
+        __syncthreads();
       }
-      if (S.flag[level] != 0) {
-        if (level == 0) st = 0;
-        continue;
-      }
-      const float A11 = S.A[level][0], A12 = S.A[level][1], A22 = S.A[level][2];
-      const float D = 1.f / (A11 * A22 - A12 * A12);
-      int Iw[kPxPerLane], Dx[kPxPerLane], Dy[kPxPerLane];
+    }
+    LK_CLK(5 + 4 * level);
+    // the next level's region around the predicted position 2 * np
+    rn.level = -1;
+    if (level > 0)
+      rn = region_around(level - 1, pd.w[level - 1], pd.h[level - 1], 2.f * np.x, 2.f * np.y);
+    const int slot = n_newton & 1;
+    if (!n_group) {
+      if (rn.level >= 0)
+        stage_J<kLkWarps - kNWarps>(S.Q[cur ^ 1], J + pd.off[level - 1], pd.w[level - 1],
+                                    pd.h[level - 1], pd.pitch[level - 1], rn.rx0, rn.ry0,
+                                    warp - kNWarps);
+    } else {
+      int Iw[kPxN], Dx[kPxN], Dy[kPxN];
 #pragma unroll
-      for (int j = 0; j < kPxPerLane; ++j) {
-        const int kk = lane + 32 * j;
-        Iw[j] = S.Tw[level][kk];
-        Dx[j] = S.Tx[level][kk];  // zero beyond the 441st pixel: those lanes add nothing
-        Dy[j] = S.Ty[level][kk];
+      for (int j = 0; j < kPxN; ++j) {
+        const int kk = tid + kNThreads * j;
+        const bool on = kk < kWin * kWin;
+        Iw[j] = on ? S.Tw[level][kk] : 0;
+        Dx[j] = on ? S.Tx[level][kk] : 0;  // zero in the unused slots: they add nothing
+        Dy[j] = on ? S.Ty[level][kk] : 0;
       }
       float npx = np.x - half, npy = np.y - half;
-      int rx0 = 0, ry0 = 0;
-      bool staged = false;
+      int rx0 = rc.rx0, ry0 = rc.ry0;
       float pdx = 0.f, pdy = 0.f;
+      int n_it = 0;
       for (int it = 0; it < 30; ++it) {
+        ++n_it;
         const int inx = (int)floorf(npx), iny = (int)floorf(npy);
         if (inx < -kWin || inx >= w || iny < -kWin || iny >= h) {
           if (level == 0) st = 0;
           break;
         }
-        if (!staged || inx < rx0 || iny < ry0 || inx + kWin > rx0 + kJR - 1 ||
-            iny + kWin > ry0 + kJR - 1) {
+        if (inx < rx0 || iny < ry0 || inx + kWin > rx0 + kJR - 1 || iny + kWin > ry0 + kJR - 1) {
+          // the window walked out of the staged region (rare): the N group re-stages it
           rx0 = inx - kJM;
           ry0 = iny - kJM;
-          __syncwarp();
-          stage_J(S, Jl, w, h, pitch, rx0, ry0);
-          staged = true;
+          bar_newton();  // everybody is done reading the old region
+          stage_J<kNWarps>(S.Q[cur], Jl, w, h, pitch, rx0, ry0, warp);
+          bar_newton();
         }
         const float a = npx - (float)inx, b = npy - (float)iny;
         int iw00, iw01, iw10, iw11;
@@ -269,23 +360,30 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
                             ((unsigned)(iw10 >> 7) << 16) | ((unsigned)(iw11 >> 7) << 24);
         const unsigned wl = (unsigned)(iw00 & 127) | ((unsigned)(iw01 & 127) << 8) |
                             ((unsigned)(iw10 & 127) << 16) | ((unsigned)(iw11 & 127) << 24);
-        const uint32_t* base = &S.Q[iny - ry0][inx - rx0];
-        int sb1 = 0, sb2 = 0, sc1 = 0, sc2 = 0;  // two accumulation chains each
+        const uint32_t* base = &S.Q[cur][iny - ry0][inx - rx0];
+        int sb1 = 0, sb2 = 0;
 #pragma unroll
-        for (int j = 0; j < kPxPerLane; ++j) {
+        for (int j = 0; j < kPxN; ++j) {
           const unsigned q = base[joff[j]];
           const unsigned v = (__dp4a(q, wh, 0u) << 7) + __dp4a(q, wl, 1u << (kWBits - 5 - 1));
           const int diff = (int)(v >> (kWBits - 5)) - Iw[j];
-          if (j & 1) {
-            sc1 += diff * Dx[j];
-            sc2 += diff * Dy[j];
-          } else {
-            sb1 += diff * Dx[j];
-            sb2 += diff * Dy[j];
-          }
+          sb1 += diff * Dx[j];
+          sb2 += diff * Dy[j];
         }
-        const float b1 = warp_sum_to_float(sb1 + sc1) * flt_scale;
-        const float b2 = warp_sum_to_float(sb2 + sc2) * flt_scale;
+        const long long w1 = warp_sum_exact(sb1), w2 = warp_sum_exact(sb2);
+        longlong2* part = S.part[it & 1];
+        if (lane == 0) part[warp] = make_longlong2(w1, w2);
+        bar_newton();
+        long long t1 = 0, t2 = 0;
+#pragma unroll
+        for (int q = 0; q < kNWarps; ++q) {
+          const longlong2 p = part[q];
+          t1 += p.x;
+          t2 += p.y;
+        }
+        // the exact totals, rounded to float once
+        const float b1 = __ll2float_rn(t1) * flt_scale;
+        const float b2 = __ll2float_rn(t2) * flt_scale;
         const float dx = (A12 * b2 - A22 * b1) * D;
         const float dy = (A12 * b1 - A11 * b2) * D;
         npx += dx;
@@ -316,15 +414,23 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
         const int inx = (int)floorf(np.x - half), iny = (int)floorf(np.y - half);
         if (inx < -kWin || inx >= w || iny < -kWin || iny >= h) st = 0;
       }
+      LK_CLK(6 + 4 * level);
+      LK_VAL(7 + 4 * level, n_it);
+      if (tid == 0) {
+        S.np[slot] = np;
+        S.st[slot] = st;
+      }
     }
-    if (lane == 0) {
-      S.np = np;
-      S.st = st;
-    }
+    __syncthreads();  // level done: its result and the prefetched region are visible to all
+    np = S.np[slot];
+    st = S.st[slot];
+    ++n_newton;
+    cur ^= 1;
+    rc = rn;
   }
-  __syncthreads();
-  np_out = S.np;
-  st_out = S.st;
+  LK_CLK(20);
+  np_out = np;
+  st_out = st;
 }
 
 // mode 0: forward only (next = LK(I->J, prev[, init = next]))
@@ -337,7 +443,7 @@ k_lk(const __grid_constant__ PyrDesc pd, const uint8_t* __restrict__ I, const ui
      uint8_t* __restrict__ status, float2* __restrict__ rev_pts, uint8_t* __restrict__ rev_status,
      const int* __restrict__ n_ptr, int top, int use_init, int mode) {
   PDL_PROLOGUE();
-  __shared__ LkShared S;
+  __shared__ __align__(16) LkShared S;
   const int k = blockIdx.x;
   if (k >= *n_ptr) return;
   const float2 p0 = prev_pts[k];
@@ -355,9 +461,9 @@ k_lk(const __grid_constant__ PyrDesc pd, const uint8_t* __restrict__ I, const ui
   int rst;
   if (mode == 1) {
     const int top_b = top < 1 ? top : 1;
-    lk_point(S, pd, J, I, np, p0, 1, top_b, rp, rst);
+    lk_point(S, pd, J, I, np, p0, 1, top_b, rp, rst, 1);
   } else {
-    lk_point(S, pd, J, I, np, init, 0, top, rp, rst);
+    lk_point(S, pd, J, I, np, init, 0, top, rp, rst, 1);
   }
   if (threadIdx.x == 0) {
     rev_pts[k] = rp;
@@ -383,7 +489,7 @@ void launch_lk(const PyrDesc& pd, const uint8_t* I, const uint8_t* J, const floa
 // CTAs of k_sae_update_ts) the SAE kernel of the next window gets one CTA per SM next to two LK
 // kernels and takes twice as long (measured at 346x260: 23 us instead of 12 us; MaxShared on
 // both fixes that too but starves the gather-heavy kernels on those SMs of L1: -5..9 %
-// throughput at 640x480).  Both ask for half of the array: room for 2-3 LK CTAs plus 6 SAE
+// throughput at 640x480).  Both ask for half of the array: room for 3 LK CTAs plus 6 SAE
 // CTAs per SM, 114 KB of L1 left.
 void prefer_shared_lk() {
   cudaFuncSetAttribute(k_lk, cudaFuncAttributePreferredSharedMemoryCarveout, 50);

@@ -34,9 +34,9 @@ __device__ __forceinline__ void pyr_stage(const uint8_t* __restrict__ s_src, int
     uint32_t v = 0;
     if (gx >= 0 && gx < dw) {
       const uint8_t* row = s_src + r * ssp;
-      const int x0 = reflect101(2 * gx - 2, sw) - sx0, x1 = reflect101(2 * gx - 1, sw) - sx0,
-                x2 = 2 * gx - sx0, x3 = reflect101(2 * gx + 1, sw) - sx0,
-                x4 = reflect101(2 * gx + 2, sw) - sx0;
+      const int x0 = reflect101_nb(2 * gx - 2, sw) - sx0, x1 = reflect101_nb(2 * gx - 1, sw) - sx0,
+                x2 = 2 * gx - sx0, x3 = reflect101_nb(2 * gx + 1, sw) - sx0,
+                x4 = reflect101_nb(2 * gx + 2, sw) - sx0;
       v = row[x2] * 6 + (row[x1] + row[x3]) * 4 + row[x0] + row[x4];
     }
     s_row[r * ND + c] = (uint16_t)v;
@@ -46,9 +46,9 @@ __device__ __forceinline__ void pyr_stage(const uint8_t* __restrict__ s_src, int
     const int r = i / ND, c = i - r * ND;
     const int gx = dx0 + c, gy = dy0 + r;
     if (gx >= 0 && gx < dw && gy >= 0 && gy < dh) {
-      const int y0 = reflect101(2 * gy - 2, sh) - sy0, y1 = reflect101(2 * gy - 1, sh) - sy0,
-                y2 = 2 * gy - sy0, y3 = reflect101(2 * gy + 1, sh) - sy0,
-                y4 = reflect101(2 * gy + 2, sh) - sy0;
+      const int y0 = reflect101_nb(2 * gy - 2, sh) - sy0, y1 = reflect101_nb(2 * gy - 1, sh) - sy0,
+                y2 = 2 * gy - sy0, y3 = reflect101_nb(2 * gy + 1, sh) - sy0,
+                y4 = reflect101_nb(2 * gy + 2, sh) - sy0;
       const int v = s_row[y2 * ND + c] * 6 + (s_row[y1 * ND + c] + s_row[y3 * ND + c]) * 4 +
                     s_row[y0 * ND + c] + s_row[y4 * ND + c];
       const uint8_t o = (uint8_t)((v + 128) >> 8);

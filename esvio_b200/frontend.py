@@ -308,6 +308,13 @@ class EventFrontEnd:
         self._chk(_capi.lib().esvio_fe_get_stage_ms(self._h, ms), "get_stage_ms")
         return dict(zip(_capi.STAGE_NAMES, list(ms)))
 
+    def stage_marks(self):
+        """Timeline of the last profiled window: ms since set_profiling(True) of the 12 markers
+        (include/esvio_fe.h)."""
+        ms = (C.c_float * 12)()
+        self._chk(_capi.lib().esvio_fe_get_stage_marks(self._h, ms), "get_stage_marks")
+        return list(ms)
+
     def kernel_launches(self):
         n = C.c_int64()
         self._chk(_capi.lib().esvio_fe_kernel_launches(self._h, C.byref(n)), "kernel_launches")

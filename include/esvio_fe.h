@@ -280,6 +280,12 @@ int esvio_fe_track_submit_split(esvio_fe *fe, double cur_time, const esvio_event
  * 5 temporal LK + filter, 6 select (ransac+mask+corners), 7 stereo LK + pack, 8 d2h */
 int esvio_fe_set_profiling(esvio_fe *fe, int32_t on);
 int esvio_fe_get_stage_ms(esvio_fe *fe, float *ms /* ESVIO_FE_NUM_STAGES */);
+/* The same window as a timeline: milliseconds since esvio_fe_set_profiling(fe, 1) of the 12
+ * markers  0 submit, 1 events landed, 2 binned, 3 time surface done, 4 pyramids done, 5 corner
+ * flags done (event stage, own stream) | 6 temporal LK + filter done, 7 selection done, 10 start
+ * (temporal stream) | 8 stereo LK + pack done, 9 result on the host, 11 start (stereo stream). */
+#define ESVIO_FE_NUM_MARKS 12
+int esvio_fe_get_stage_marks(esvio_fe *fe, float *ms /* ESVIO_FE_NUM_MARKS */);
 int esvio_fe_kernel_launches(esvio_fe *fe, int64_t *count); /* kernels launched so far */
 
 /* ---- stage-level entry points (used by the parity tests) ---- */
