@@ -48,7 +48,7 @@ UNIT = "Mevents/s"
 WORKLOAD_N1 = "stereo_vga_5mevs"      # BASELINE.json configs[2]: the north-star configuration
 WORKLOAD_NX = "stereo_vga_10mevs"     # configs[4]: one of the 8 streams, per rank
 WORKLOAD_SECONDARY = "stereo_davis346_1mevs"  # configs[1]
-DEPTH = 3  # windows in flight: event stage | temporal stage | stereo stage
+DEPTH = 3  # windows in flight; set to esvio_fe_pipeline_depth() once the library is loaded
 
 
 def env_int(k, d):
@@ -540,7 +540,7 @@ def batched_leg(torch, dev, local, workload, S, K, Wm, flush):
     rec = {"streams": S, "steps": K, "config": config_of(workload),
            "value": n_ev / (wall_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wall_ms / K,
            "timing": "host wall clock around submit/wait with synchronize on both sides, events "
-                     "device-resident, 3 windows in flight",
+                     f"device-resident, {DEPTH} windows in flight",
            "gpu_launches": grp.kernel_launches()}
     roof = {"bound": "hbm", "kernel": "k_sae_update_ts", "achieved": alg / (k1 * 1e-3) / 1e9,
             "peak": peak, "unit": "GB/s", "frac": alg / (k1 * 1e-3) / 1e9 / peak,
@@ -550,7 +550,7 @@ def batched_leg(torch, dev, local, workload, S, K, Wm, flush):
             "launch_covers": f"{2 * S} cameras = {S} stereo streams of {workload} in one esvio_fe_group",
             "note": "achieved = algorithmic bytes (SURVEY.md 8d: 17*W*H per camera + 45 B/event, "
                     "summed over the cameras of the launch) / CUDA-event time of the launch, "
-                    "measured inside the 3-deep pipeline (the LK / selection kernels of two other "
+                    "measured inside the pipeline (the LK / selection kernels of two other "
                     "windows x S streams share the SMs); the group's SAE state (S x 19.7 MB at "
                     "640x480) exceeds what stays in L2 next to the event buffers, so the launch "
                     "streams from HBM"}
@@ -562,8 +562,8 @@ def batched_leg(torch, dev, local, workload, S, K, Wm, flush):
 
 def frames_leg(width, height, device_id, n_frames=48, cpu_frames=16):
     """Extra record at N = 1: FeatureTracker::trackImage (SURVEY.md 8f rank 4) on synthetic stereo
-    frames of the workload's resolution through esvio_fe_track_image_submit / _wait, three frames
-    in flight, host frames copied inside the timed region; every 2nd frame is a publish frame
+    frames of the workload's resolution through esvio_fe_track_image_submit / _wait, a pipeline
+    depth of frames in flight, host frames copied inside the timed region; every 2nd frame is a publish frame
     (Image_setMask + goodFeaturesToTrack).  CPU beside it: the oracle's trackImage with OpenCV
     LK, 1 thread.  Never raises: a failure is reported in the record."""
     rec = {"what": "trackImage, stereo frames/s", "width": width, "height": height}
@@ -602,7 +602,7 @@ def frames_leg(width, height, device_id, n_frames=48, cpu_frames=16):
         waited, last = 0, (0, 0)
         for k in range(warm, warm + n_frames):
             fe.submit_image(1.0 + k / 20.0, frames[k][0], frames[k][1], k % 2 == 0)
-            if k - warm >= 2:
+            if k - warm >= frontend.pipeline_depth() - 1:
                 last = fe.wait(unpack=False)
                 waited += 1
         while waited < n_frames:
@@ -672,6 +672,8 @@ def main_ours(args):
     import torch.distributed as dist
     from esvio_b200 import frontend
 
+    global DEPTH
+    DEPTH = frontend.pipeline_depth()
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local = env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
@@ -778,8 +780,8 @@ def main_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(round(13 * sb.ev_per_step)),
                     "d2h_bytes_per_step": int(d["result_bytes"]), "ms_per_step": e2e_ms / max(K, 1),
                     "api": "esvio_fe_track_submit / esvio_fe_track_wait on pinned host SoA "
-                           "buffers, three windows in flight (H2D + event stage of window k+2 | "
-                           "temporal LK + selection of k+1 | stereo LK of k)",
+                           f"buffers, {DEPTH} windows in flight (the windows' copies and kernels "
+                           "overlap on several streams)",
                     "sync_call_ms_per_step": h.get("sync_ms_per_step")},
             "gpu_launches": int(tot[1].item()),
             "clocks": clk,
@@ -815,6 +817,8 @@ def main_split(args):
     import torch.distributed as dist
     from esvio_b200 import frontend
 
+    global DEPTH
+    DEPTH = frontend.pipeline_depth()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world != 2:
         raise SystemExit("bench.py --split-lr needs exactly 2 ranks (torchrun --nproc-per-node 2)")

@@ -31,7 +31,8 @@ constexpr int kWin = 21;                      // cv::Size(21, 21)
 constexpr int kHalfWin = 10;
 constexpr int kMaxCnt = 1024;                 // hard cap on MAX_CNT
 constexpr int kMaxCams = 16;                  // cameras per launch: 8 stereo streams of one group
-constexpr int kSlots = 3;                     // windows in flight (event / temporal / stereo stage)
+constexpr int kSlots = 6;                     // windows in flight: a window is a ~0.4 ms chain of short
+                                              // kernels, a new one can start every ~0.08 ms
 constexpr int kResultHdr = 32;                // int32 words in front of the result arrays
 constexpr int kResultArrays = 15;
 
@@ -315,7 +316,10 @@ void launch_lk(const PyrDesc& pd, const uint8_t* I, const uint8_t* J, const floa
 
 struct TrackBuffers {
   TrackState* st;
-  float2 *prev_pts, *cur_pts, *rev_pts, *right_pts, *rev_left_pts;
+  float2 *prev_pts, *cur_pts, *rev_pts;
+  // stereo LK outputs, one set per in-flight slot ([kSlots][max_cnt]): the stereo LK of window
+  // k+1 runs while window k is still being packed
+  float2 *right_pts, *rev_left_pts;
   int *ids, *cnt;
   uint8_t *st_fwd, *st_bwd, *st_sf, *st_sb;
   int* prev_un_ids;

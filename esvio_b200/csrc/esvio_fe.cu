@@ -22,7 +22,7 @@ int bin_configure(int n_bins);
 
 #define FE_API extern "C" __attribute__((visibility("default")))
 
-constexpr int kLeftBufs = 4, kRightBufs = 3, kRightBase = kLeftBufs, kScratchBase = kLeftBufs + kRightBufs,
+constexpr int kLeftBufs = kSlots + 1, kRightBufs = kSlots, kRightBase = kLeftBufs, kScratchBase = kLeftBufs + kRightBufs,
               kNumPyr = kScratchBase + 2;
 
 struct esvio_fe {
@@ -36,12 +36,11 @@ struct esvio_fe {
   double2 *sae, *lat;  // [2][H][W]
   CUtensorMap map_sae, map_lat;
   PyrDesc pd;
-  // Pyramid buffers: 0..3 left, 4..6 right, 7..8 scratch for esvio_fe_stage_lk.  Up to three
-  // windows are in flight, one per pipeline stage.  The left image of window k is read by the
-  // temporal LK of k (as cur) and of k+1 (as prev) and by the stereo LK of k; when window k+4
-  // overwrites it, windows <= k+1 have been waited for -- hence four left buffers (three would
-  // let the event stage of k+3 overwrite what the temporal LK of k+1 may still read).  The
-  // right image of window k is only read by its own stereo LK: three buffers.
+  // Pyramid buffers: kLeftBufs left, kRightBufs right, 2 scratch for esvio_fe_stage_lk.  Up to
+  // kSlots windows are in flight.  The left image of window k is read by the temporal LK of k
+  // (as cur) and of k+1 (as prev) and by the stereo LK of k; when window k+kSlots+1 overwrites
+  // it, windows <= k+1 have been waited for -- hence kSlots+1 left buffers.  The right image of
+  // window k is only read by its own stereo LK: kSlots buffers.
   uint8_t* pyr[kNumPyr];
   // image conditioning (median blur / CLAHE + normalize): [stage][camera] scratch images with
   // the layout of pyramid level 0; ts_sel[cam] = the time surface the corner selection and
@@ -54,24 +53,41 @@ struct esvio_fe {
   float mc_K[4];
   GfttBuffers gftt;  // frame path (esvio_fe_track_image): allocated on first use
   void* gftt_block;
-  int cur_left;   // index (0..2) of the newest left pyramid; prev_left is the one before it
+  int cur_left;   // index of the newest left pyramid; prev_left is the one before it
   int prev_left;
-  int cur_right;  // 3..5
+  int cur_right;
   int windows;      // windows processed since create/reset
   int cap;          // events per camera per window
   uint8_t* raw[kSlots][2];  // [slot][camera] 16 B * cap: SoA carve-out or dvs_msgs::Event records
-  EventStageBuffers esb;
+  EventStageBuffers esb[2];  // binned events of even / odd windows: binning of window k+1 runs
+                             // while the SAE kernel of window k still reads window k's
   uint8_t* flags[kSlots];   // [slot] Arc* corner flags of the left events
-  // Three pipeline stages, one stream each; `stream` (stereo stage, results) is the one
-  // esvio_fe_stream() hands out.
-  cudaStream_t stream_c;   // host -> device copies of a window's events (overlap the event stage
-                           // of the window before)
-  cudaEvent_t c_done[kSlots];
+  // A window is a graph of short kernels; every node that has no data dependency on another
+  // gets its own stream, and windows overlap wherever the data allow it (dependencies are
+  // CUDA events, never host synchronisation):
+  //   copy  -> bin (K0) -> SAE + time surface (K1) -+-> pyramids ------> temporal LK -> filter
+  //                                                 +-> corner flags -.              [-> F-RANSAC]
+  //                                                                    `-----------> [-> selection]
+  //   -> stereo LK (two alternating streams) -> pack + D2H (`stream`, the one esvio_fe_stream()
+  //   hands out).  Across windows only three chains are serial: K1 (the SAE state; K1 of k+1
+  //   also waits for the corner flags of k, which read that state), the temporal chain
+  //   (prev_pts = cur_pts) and the packing (velocity maps).
+  cudaStream_t stream_c;   // host -> device copies of a window's events
+  cudaStream_t stream_b;   // K0: binning (+ the motion-compensation warp)
+  cudaStream_t stream_e;   // K1: SAE update + time surface (+ median / CLAHE)
+  cudaStream_t stream_p;   // pyramids
+  cudaStream_t stream_f;   // Arc* corner flags (publish windows)
+  cudaStream_t stream_t1;  // temporal chain: temporal LK, filter, F-RANSAC, selection
+  cudaStream_t stream_s[2];  // stereo LK of even / odd slots
+  cudaEvent_t c_done[kSlots];   // [slot] events landed
+  cudaEvent_t b_done[kSlots];   // binned
+  cudaEvent_t k1_done[kSlots];  // SAE + time surface (+ conditioning) done
+  cudaEvent_t p_done[kSlots];   // pyramids done
+  cudaEvent_t f_done[kSlots];   // corner flags done
+  cudaEvent_t t1_done[kSlots];  // temporal chain done (snapshot taken)
+  cudaEvent_t s_done[kSlots];   // stereo LK done
   cudaEvent_t x_ready[kSlots];  // left/right split: marks on the caller's exchange stream
-  cudaStream_t stream_e;   // event stage: binning, SAE/TS, pyramids, corner flags
-  cudaStream_t stream_t1;  // temporal stage: temporal LK, F-RANSAC, selection
-  cudaEvent_t e_done[kSlots];   // [slot] event stage of that window finished
-  cudaEvent_t t1_done[kSlots];  // [slot] temporal stage finished
+  int f_pending;                // slot whose corner flags the next K1 has to wait for, or -1
   TrackBuffers tb;
   TrackParams tp;
   int32_t* h_result[kSlots];
@@ -90,8 +106,8 @@ struct esvio_fe {
   int r_held[kSlots];
   int profiling;
   struct esvio_fe_group* group;  // non-null: the event stage is run by the group, batched
-  // one set per in-flight slot; [NUM_STAGES+1] = temporal stage start, [+2] = stereo stage start
-  cudaEvent_t pev[kSlots][ESVIO_FE_NUM_STAGES + 3];
+  // one set of markers per in-flight slot (ESVIO_FE_NUM_MARKS, include/esvio_fe.h)
+  cudaEvent_t pev[kSlots][ESVIO_FE_NUM_MARKS];
   int pev_slot;
   int pev_valid[kSlots];
   int stage_ms_valid;
@@ -111,6 +127,7 @@ static int fail(esvio_fe* fe, int code, const char* what, cudaError_t ce) {
   } while (0)
 
 FE_API int esvio_fe_abi_version(void) { return ESVIO_FE_ABI_VERSION; }
+FE_API int esvio_fe_pipeline_depth(void) { return kSlots; }
 
 FE_API const char* esvio_fe_strerror(int s) {
   switch (s) {
@@ -213,10 +230,9 @@ static int make_state_map(esvio_fe* fe, double2* base, CUtensorMap* map, int n_c
 static void free_all(esvio_fe* fe) {
   if (!fe) return;
   cudaSetDevice(fe->dev);
-  if (fe->stream_c) cudaStreamSynchronize(fe->stream_c);
-  if (fe->stream_e) cudaStreamSynchronize(fe->stream_e);
-  if (fe->stream_t1) cudaStreamSynchronize(fe->stream_t1);
-  if (fe->stream) cudaStreamSynchronize(fe->stream);
+  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_f,
+                          fe->stream_t1, fe->stream_s[0], fe->stream_s[1], fe->stream})
+    if (st) cudaStreamSynchronize(st);
   cudaFree(fe->sae);
   cudaFree(fe->lat);
   for (int i = 0; i < kNumPyr; ++i) cudaFree(fe->pyr[i]);
@@ -229,26 +245,28 @@ static void free_all(esvio_fe* fe) {
     cudaFree(fe->raw[i][0]);
     cudaFree(fe->raw[i][1]);
     cudaFree(fe->flags[i]);
-    if (fe->e_done[i]) cudaEventDestroy(fe->e_done[i]);
-    if (fe->c_done[i]) cudaEventDestroy(fe->c_done[i]);
-    if (fe->x_ready[i]) cudaEventDestroy(fe->x_ready[i]);
-    if (fe->t1_done[i]) cudaEventDestroy(fe->t1_done[i]);
+    for (cudaEvent_t ev : {fe->c_done[i], fe->b_done[i], fe->k1_done[i], fe->p_done[i], fe->f_done[i],
+                           fe->t1_done[i], fe->s_done[i], fe->x_ready[i]})
+      if (ev) cudaEventDestroy(ev);
     if (fe->h_result[i]) cudaFreeHost(fe->h_result[i]);
     if (fe->q_done[i]) cudaEventDestroy(fe->q_done[i]);
     if (fe->r_free[i]) cudaEventDestroy(fe->r_free[i]);
   }
-  for (int i = 0; i < 2; ++i) {
-    cudaFree(fe->esb.bt[i]);
-    cudaFree(fe->esb.bk[i]);
+  for (int b = 0; b < 2; ++b) {
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(fe->esb[b].bt[i]);
+      cudaFree(fe->esb[b].bk[i]);
+    }
+    cudaFree(fe->esb[b].counts);
+    cudaFree(fe->esb[b].bin_total);
+    cudaFree(fe->esb[b].bin_start);
+    cudaFree(fe->esb[b].done_ctr);
   }
   cudaFree(fe->tb.snap_pts);
   cudaFree(fe->tb.snap_ids);
   cudaFree(fe->tb.snap_hdr);
-  cudaFree(fe->esb.counts);
-  cudaFree(fe->esb.bin_total);
-  cudaFree(fe->esb.bin_start);
-  cudaFree(fe->esb.done_ctr);
   cudaFree(fe->tb.st);
+  cudaFree(fe->tb.right_pts);
   cudaFree(fe->tb.prev_pts);
   cudaFree(fe->tb.ids);
   cudaFree(fe->tb.st_fwd);
@@ -261,13 +279,12 @@ static void free_all(esvio_fe* fe) {
   cudaFree(fe->d_scratch_p0);
   cudaFree(fe->d_scratch_st);
   for (int k = 0; k < kSlots; ++k)
-    for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 2; ++i)
+    for (int i = 0; i < ESVIO_FE_NUM_MARKS; ++i)
       if (fe->pev[k][i]) cudaEventDestroy(fe->pev[k][i]);
   if (fe->pev_ref) cudaEventDestroy(fe->pev_ref);
-  if (fe->stream_c) cudaStreamDestroy(fe->stream_c);
-  if (fe->stream_e) cudaStreamDestroy(fe->stream_e);
-  if (fe->stream_t1) cudaStreamDestroy(fe->stream_t1);
-  if (fe->stream) cudaStreamDestroy(fe->stream);
+  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_f,
+                          fe->stream_t1, fe->stream_s[0], fe->stream_s[1], fe->stream})
+    if (st) cudaStreamDestroy(st);
   free(fe);
 }
 
@@ -287,6 +304,7 @@ static int reset_state(esvio_fe* fe) {
   fe->prev_time = 0.0;
   fe->q_head = fe->q_count = 0;
   fe->last_slot = -1;
+  fe->f_pending = -1;
   for (int k = 0; k < kSlots; ++k) fe->pev_valid[k] = 0, fe->r_held[k] = 0;
   fe->stage_ms_valid = 0;
   return ESVIO_FE_OK;
@@ -336,16 +354,21 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   }
   CUC(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
   {
-    // the event stage is short, wide and latency-bound: let its CTAs go first when the long
-    // single-CTA-per-point LK kernels of the other stages are also pending
+    // the event-stage kernels are short, wide and latency-bound: let their CTAs go first when
+    // the long one-CTA-per-point LK kernels of other windows are also pending
     int prio_lo = 0, prio_hi = 0;
     CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUC(cudaStreamCreateWithPriority(&fe->stream_b, cudaStreamNonBlocking, prio_hi));
     CUC(cudaStreamCreateWithPriority(&fe->stream_e, cudaStreamNonBlocking, prio_hi));
+    CUC(cudaStreamCreateWithPriority(&fe->stream_p, cudaStreamNonBlocking, prio_hi));
+    CUC(cudaStreamCreateWithPriority(&fe->stream_f, cudaStreamNonBlocking, prio_hi));
   }
   CUC(cudaStreamCreateWithFlags(&fe->stream_t1, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&fe->stream_s[0], cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&fe->stream_s[1], cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&fe->stream_c, cudaStreamNonBlocking));
 
-  fe->esb.n_cams = 2;
+  fe->esb[0].n_cams = fe->esb[1].n_cams = 2;
   BinLayout& L = fe->bl;
   L.W = fe->W;
   L.H = fe->H;
@@ -374,37 +397,42 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(cudaMalloc(&fe->raw[c][0], (size_t)fe->cap * 16));
     CUC(cudaMalloc(&fe->raw[c][1], (size_t)fe->cap * 16));
     CUC(cudaMalloc(&fe->flags[c], (size_t)fe->cap + 16));
-    CUC(cudaEventCreateWithFlags(&fe->e_done[c], cudaEventDisableTiming));
-    CUC(cudaEventCreateWithFlags(&fe->c_done[c], cudaEventDisableTiming));
-    CUC(cudaEventCreateWithFlags(&fe->x_ready[c], cudaEventDisableTiming));
-    CUC(cudaEventCreateWithFlags(&fe->t1_done[c], cudaEventDisableTiming));
+    for (cudaEvent_t* ev : {&fe->c_done[c], &fe->b_done[c], &fe->k1_done[c], &fe->p_done[c], &fe->f_done[c],
+                            &fe->t1_done[c], &fe->s_done[c], &fe->x_ready[c]})
+      CUC(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
   if (cfg->do_motion_correction)
     for (int i = 0; i < 2; ++i)
       for (int c = 0; c < 2; ++c) CUC(cudaMalloc(&fe->warp_xy[i][c], (size_t)fe->cap * sizeof(uint16_t)));
-  for (int c = 0; c < 2; ++c) {
-    CUC(cudaMalloc(&fe->esb.bt[c], (size_t)fe->cap * sizeof(double)));
-    CUC(cudaMalloc(&fe->esb.bk[c], (size_t)fe->cap * sizeof(uint16_t)));
+  for (int b = 0; b < 2; ++b) {
+    EventStageBuffers& E = fe->esb[b];
+    for (int c = 0; c < 2; ++c) {
+      CUC(cudaMalloc(&E.bt[c], (size_t)fe->cap * sizeof(double)));
+      CUC(cudaMalloc(&E.bk[c], (size_t)fe->cap * sizeof(uint16_t)));
+    }
+    CUC(cudaMalloc(&E.counts, (size_t)2 * nb * L.max_chunks * sizeof(uint32_t)));
+    CUC(cudaMalloc(&E.bin_total, (size_t)2 * nb * sizeof(uint32_t)));
+    CUC(cudaMalloc(&E.bin_start, (size_t)2 * (nb + 1) * sizeof(uint32_t)));
+    CUC(cudaMalloc(&E.done_ctr, 2 * sizeof(unsigned int)));
+    CUC(cudaMemset(E.done_ctr, 0, 2 * sizeof(unsigned int)));
   }
-  CUC(cudaMalloc(&fe->esb.counts, (size_t)2 * nb * L.max_chunks * sizeof(uint32_t)));
-  CUC(cudaMalloc(&fe->esb.bin_total, (size_t)2 * nb * sizeof(uint32_t)));
-  CUC(cudaMalloc(&fe->esb.bin_start, (size_t)2 * (nb + 1) * sizeof(uint32_t)));
-  CUC(cudaMalloc(&fe->esb.done_ctr, 2 * sizeof(unsigned int)));
-  CUC(cudaMemset(fe->esb.done_ctr, 0, 2 * sizeof(unsigned int)));
 
   const int M = cfg->max_cnt;
   TrackBuffers& B = fe->tb;
   CUC(cudaMalloc(&B.st, sizeof(TrackState)));
   float2* f2 = nullptr;
-  CUC(cudaMalloc(&f2, sizeof(float2) * (size_t)M * 7));
-  CUC(cudaMemset(f2, 0, sizeof(float2) * (size_t)M * 7));
+  CUC(cudaMalloc(&f2, sizeof(float2) * (size_t)M * 5));
+  CUC(cudaMemset(f2, 0, sizeof(float2) * (size_t)M * 5));
   B.prev_pts = f2;
   B.cur_pts = f2 + M;
   B.rev_pts = f2 + 2 * M;
-  B.right_pts = f2 + 3 * M;
-  B.rev_left_pts = f2 + 4 * M;
-  B.prev_un = f2 + 5 * M;
-  B.prev_un_r = f2 + 6 * M;
+  B.prev_un = f2 + 3 * M;
+  B.prev_un_r = f2 + 4 * M;
+  CUC(cudaMalloc(&B.right_pts, (sizeof(float2) * 2 + 2) * (size_t)M * kSlots));
+  CUC(cudaMemset(B.right_pts, 0, (sizeof(float2) * 2 + 2) * (size_t)M * kSlots));
+  B.rev_left_pts = B.right_pts + (size_t)M * kSlots;
+  B.st_sf = reinterpret_cast<uint8_t*>(B.rev_left_pts + (size_t)M * kSlots);
+  B.st_sb = B.st_sf + (size_t)M * kSlots;
   int* i4 = nullptr;
   CUC(cudaMalloc(&i4, sizeof(int) * (size_t)M * 4));
   CUC(cudaMemset(i4, 0, sizeof(int) * (size_t)M * 4));
@@ -413,12 +441,10 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   B.prev_un_ids = i4 + 2 * M;
   B.prev_un_r_ids = i4 + 3 * M;
   uint8_t* u4 = nullptr;
-  CUC(cudaMalloc(&u4, (size_t)M * 4));
-  CUC(cudaMemset(u4, 0, (size_t)M * 4));
+  CUC(cudaMalloc(&u4, (size_t)M * 2));
+  CUC(cudaMemset(u4, 0, (size_t)M * 2));
   B.st_fwd = u4;
   B.st_bwd = u4 + M;
-  B.st_sf = u4 + 2 * M;
-  B.st_sb = u4 + 3 * M;
   CUC(cudaMalloc(&B.snap_pts, sizeof(float2) * (size_t)M * kSlots));
   CUC(cudaMalloc(&B.snap_ids, sizeof(int) * (size_t)M * kSlots * 2));
   B.snap_cnt = B.snap_ids + (size_t)M * kSlots;
@@ -449,7 +475,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   fe->d_scratch_p1 = fe->d_scratch_p0 + kMaxCnt;
   CUC(cudaMalloc(&fe->d_scratch_st, kMaxCnt));
   for (int k = 0; k < kSlots; ++k)
-    for (int i = 0; i <= ESVIO_FE_NUM_STAGES + 2; ++i) CUC(cudaEventCreate(&fe->pev[k][i]));
+    for (int i = 0; i < ESVIO_FE_NUM_MARKS; ++i) CUC(cudaEventCreate(&fe->pev[k][i]));
   CUC(cudaEventCreate(&fe->pev_ref));
 #undef CUC
 
@@ -521,10 +547,9 @@ FE_API void esvio_fe_destroy(esvio_fe* fe) {
 }
 
 static int sync_all(esvio_fe* fe) {
-  CU(cudaStreamSynchronize(fe->stream_c));
-  CU(cudaStreamSynchronize(fe->stream_e));
-  CU(cudaStreamSynchronize(fe->stream_t1));
-  CU(cudaStreamSynchronize(fe->stream));
+  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_f,
+                          fe->stream_t1, fe->stream_s[0], fe->stream_s[1], fe->stream})
+    CU(cudaStreamSynchronize(st));
   return ESVIO_FE_OK;
 }
 
@@ -582,21 +607,19 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
   return ESVIO_FE_OK;
 }
 
-// the copies of a window's events were enqueued on the copy stream: `consumer` may go on once
-// they have landed
-static int staging_done(esvio_fe* fe, int slot, cudaStream_t consumer) {
+// the copies of a window's events were enqueued on the copy stream: mark where they end
+static int staging_done(esvio_fe* fe, int slot) {
   CU(cudaEventRecord(fe->c_done[slot], fe->stream_c));
-  CU(cudaStreamWaitEvent(consumer, fe->c_done[slot], 0));
   return ESVIO_FE_OK;
 }
 
-// markers 0..5: event-stage stream; NUM_STAGES+1 (temporal stage start), 6, 7: temporal
-// stream; NUM_STAGES+2 (stereo stage start), 8, 9: stereo/result stream
-static void prof_mark(esvio_fe* fe, int i) {
+// profiling markers (include/esvio_fe.h, ESVIO_FE_NUM_MARKS), each recorded on the stream whose
+// progress it reports
+enum { kMarkSubmit = 0, kMarkLanded = 1, kMarkK1Start = 2, kMarkK1Done = 3, kMarkPyrDone = 4,
+       kMarkFlagsDone = 5, kMarkTemporalLk = 6, kMarkSelect = 7, kMarkPacked = 8, kMarkResult = 9,
+       kMarkTemporalStart = 10, kMarkStereoStart = 11, kMarkBinned = 12 };
+static void prof_mark(esvio_fe* fe, int i, cudaStream_t st) {
   if (!fe->profiling) return;
-  cudaStream_t st = fe->stream;
-  if (i <= 5) st = fe->stream_e;
-  else if (i == 6 || i == 7 || i == ESVIO_FE_NUM_STAGES + 1) st = fe->stream_t1;
   cudaEventRecord(fe->pev[fe->pev_slot][i], st);
 }
 
@@ -623,20 +646,36 @@ static bool mc_active(const esvio_motion* mc) {
   return sqrt(a0 * a0 + a1 * a1 + a2 * a2) > 5.0;
 }
 
-// n_cams = 1 (left/right split over two GPUs): only camera 0 of this handle -- ev_in[0], state
-// plane 0, image `left_idx` -- is processed.
-static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev_in[2], int left_idx,
+// createSAE_* + SAEtoTimeSurface_* + pyramids (feature_tracker.cpp:356-368) of the window in
+// `slot` into the pyramid buffers `left_idx` / `right_idx`: binning on stream_b behind the
+// window's copies, K1 (+ conditioning) on stream_e, pyramids on stream_p; records b_done,
+// k1_done and p_done of the slot.  n_cams = 1 (left/right split over two GPUs): only camera 0
+// of this handle -- ev_in[0], state plane 0, image `left_idx` -- is processed.
+static int run_event_stage(esvio_fe* fe, int slot, double t_ref, const DevEvents ev_in[2], int left_idx,
                            int right_idx, const esvio_motion* mc = nullptr, int n_cams = 2) {
-  cudaStream_t se = fe->stream_e;
+  cudaStream_t sb = fe->stream_b, se = fe->stream_e, s_pyr = fe->stream_p;
   DevEvents ev[2] = {ev_in[0], n_cams == 2 ? ev_in[1] : DevEvents{}};
+  // ---- K0 on stream_b.  The binned-event buffers alternate between even and odd slots; the
+  // set of this slot was last read by the K1 two windows back.
+  EventStageBuffers esb = fe->esb[slot & 1];
+  esb.n_cams = n_cams;
+  CU(cudaStreamWaitEvent(sb, fe->c_done[slot], 0));
+  CU(cudaStreamWaitEvent(sb, fe->k1_done[(slot + kSlots - 2) % kSlots], 0));
   if (mc && n_cams == 2 && mc_active(mc) && ev[0].n > 0) {
-    launch_warp_events(mc_params(fe, mc), ev_in, fe->warp_xy[0], fe->warp_xy[1], se, &fe->launches);
+    launch_warp_events(mc_params(fe, mc), ev_in, fe->warp_xy[0], fe->warp_xy[1], sb, &fe->launches);
     for (int c = 0; c < 2; ++c) ev[c].wx = fe->warp_xy[0][c], ev[c].wy = fe->warp_xy[1][c];
   }
-  EventStageBuffers esb = fe->esb;
-  esb.n_cams = n_cams;
-  launch_bin_events(fe->bl, esb, ev, se, &fe->launches);
-  prof_mark(fe, 2);
+  launch_bin_events(fe->bl, esb, ev, sb, &fe->launches);
+  prof_mark(fe, kMarkBinned, sb);
+  CU(cudaEventRecord(fe->b_done[slot], sb));
+  // ---- K1 on stream_e: behind the binning, and behind the corner flags of the window before,
+  // which read the SAE state this launch rewrites
+  CU(cudaStreamWaitEvent(se, fe->b_done[slot], 0));
+  if (fe->f_pending >= 0) {
+    CU(cudaStreamWaitEvent(se, fe->f_done[fe->f_pending], 0));
+    fe->f_pending = -1;
+  }
+  prof_mark(fe, kMarkK1Start, se);
   SaeTsParams sp;
   sp.W = fe->W;
   sp.H = fe->H;
@@ -651,11 +690,11 @@ static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev_in[2],
   sp.inv_decay = 1.0 / sp.decay_sec;
   sp.filter_threshold = fe->cfg.feature_filter_threshold;
   sp.ignore_polarity = fe->cfg.ignore_polarity;
-  sp.bin_start = fe->esb.bin_start;
-  sp.bt[0] = fe->esb.bt[0];
-  sp.bt[1] = fe->esb.bt[1];
-  sp.bk[0] = fe->esb.bk[0];
-  sp.bk[1] = fe->esb.bk[1];
+  sp.bin_start = esb.bin_start;
+  sp.bt[0] = esb.bt[0];
+  sp.bt[1] = esb.bt[1];
+  sp.bk[0] = esb.bk[0];
+  sp.bk[1] = esb.bk[1];
   // time surface -> [median blur] -> (selection / gettimesurface see this) -> [CLAHE +
   // normalize] -> pyramid level 0 (event_detector.cc:260-264, feature_tracker.cpp:370-388)
   uint8_t* imgs[2] = {fe->pyr[left_idx], fe->pyr[right_idx]};
@@ -677,8 +716,13 @@ static int run_event_stage(esvio_fe* fe, double t_ref, const DevEvents ev_in[2],
     launch_equalize(src, fe->aux[2], imgs, n_cams, fe->W, fe->H, fe->pd.pitch[0], fe->clahe_lut,
                     fe->clahe_minmax, se, &fe->launches);
   }
-  prof_mark(fe, 3);
-  launch_pyramids(fe->pd, imgs, n_cams, se, &fe->launches);
+  prof_mark(fe, kMarkK1Done, se);
+  CU(cudaEventRecord(fe->k1_done[slot], se));
+  // ---- pyramids on stream_p
+  CU(cudaStreamWaitEvent(s_pyr, fe->k1_done[slot], 0));
+  launch_pyramids(fe->pd, imgs, n_cams, s_pyr, &fe->launches);
+  prof_mark(fe, kMarkPyrDone, s_pyr);
+  CU(cudaEventRecord(fe->p_done[slot], s_pyr));
   CU(cudaGetLastError());
   return ESVIO_FE_OK;
 }
@@ -710,7 +754,7 @@ struct WindowPlan {
 
 static int plan_window(esvio_fe* fe, WindowPlan* w) {
   if (fe->q_count >= kSlots)
-    return fail(fe, ESVIO_FE_ESTATE, "three windows already in flight", cudaSuccess);
+    return fail(fe, ESVIO_FE_ESTATE, "too many windows in flight (esvio_fe_pipeline_depth)", cudaSuccess);
   w->slot = (fe->q_head + fe->q_count) % kSlots;
   w->cur = fe->windows == 0 ? 0 : (fe->cur_left + 1) % kLeftBufs;
   w->prev = fe->windows == 0 ? 0 : fe->cur_left;  // first window: prev_img = cur_img
@@ -718,49 +762,67 @@ static int plan_window(esvio_fe* fe, WindowPlan* w) {
   return ESVIO_FE_OK;
 }
 
-// Everything of a window behind the SAE / time surface / pyramids: corner flags (still on the
-// event-stage stream), then the temporal and the stereo stage on their own streams.
+// Everything of a window behind the SAE / time surface / pyramids.  `after_k1` / `after_pyr`:
+// the events that mark the window's time surface + SAE state and its pyramids as ready (the
+// handle's own k1_done / p_done, or its group's).  `wait_exchange`: the stereo LK also waits
+// for x_ready[slot] (left/right split: the right image arrives on the caller's stream).
 static int submit_tracking(esvio_fe* fe, const WindowPlan& w, const DevEvents& ev_left,
-                           double cur_time, int32_t pub_this_frame) {
-  cudaStream_t se = fe->stream_e, s1 = fe->stream_t1, s2 = fe->stream;
+                           double cur_time, int32_t pub_this_frame, cudaEvent_t after_k1,
+                           cudaEvent_t after_pyr, bool wait_exchange = false) {
+  cudaStream_t sf = fe->stream_f, s1 = fe->stream_t1, ss = fe->stream_s[w.slot & 1], s2 = fe->stream;
   const int slot = w.slot, cur = w.cur, prev = w.prev, rcur = w.rcur;
-  prof_mark(fe, 4);
-  if (pub_this_frame)
-    launch_corner_flags(corner_params(fe, cur, 1), ev_left, fe->flags[slot], se, &fe->launches);
-  prof_mark(fe, 5);
-  CU(cudaEventRecord(fe->e_done[slot], se));
-
-  // ---------------- temporal stage (feature_tracker.cpp:405-468), in order behind window k-1's
-  CU(cudaStreamWaitEvent(s1, fe->e_done[slot], 0));
-  prof_mark(fe, ESVIO_FE_NUM_STAGES + 1);
   const TrackBuffers& B = fe->tb;
   const int M = fe->cfg.max_cnt;
+  // ---------------- Arc* corner flags (feature_tracker.cpp:458 -> event_detector.cc:308), off the
+  // LK path: selection is their only reader
+  if (pub_this_frame) {
+    CU(cudaStreamWaitEvent(sf, after_k1, 0));
+    launch_corner_flags(corner_params(fe, cur, 1), ev_left, fe->flags[slot], sf, &fe->launches);
+    prof_mark(fe, kMarkFlagsDone, sf);
+    CU(cudaEventRecord(fe->f_done[slot], sf));
+    fe->f_pending = slot;
+  } else {
+    prof_mark(fe, kMarkFlagsDone, fe->stream_e);
+  }
+
+  // ---------------- temporal chain (feature_tracker.cpp:405-468), in order behind window k-1's
+  CU(cudaStreamWaitEvent(s1, after_pyr, 0));
+  prof_mark(fe, kMarkTemporalStart, s1);
   launch_lk(fe->pd, fe->pyr[prev], fe->pyr[cur], B.prev_pts, B.cur_pts, B.st_fwd, B.rev_pts,
             B.st_bwd, &B.st->n_prev, M, 3, 0, fe->cfg.flow_back ? 1 : 0, s1, &fe->launches);
   launch_post_temporal(fe->tp, B, pub_this_frame ? -1 : slot, s1, &fe->launches);
-  prof_mark(fe, 6);
+  prof_mark(fe, kMarkTemporalLk, s1);
   if (pub_this_frame) {
     if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s1, &fe->launches);
+    CU(cudaStreamWaitEvent(s1, fe->f_done[slot], 0));
     launch_select(fe->tp, B, ev_left, fe->flags[slot], slot, s1, &fe->launches);
   }
-  prof_mark(fe, 7);
+  prof_mark(fe, kMarkSelect, s1);
   CU(cudaEventRecord(fe->t1_done[slot], s1));
 
-  // ---------------- stereo stage (feature_tracker.cpp:470-590) on the snapshot
-  CU(cudaStreamWaitEvent(s2, fe->t1_done[slot], 0));
+  // ---------------- stereo LK (feature_tracker.cpp:490,495) on the snapshot; consecutive windows
+  // alternate between two streams, so their stereo LKs overlap
+  CU(cudaStreamWaitEvent(ss, fe->t1_done[slot], 0));
+  if (wait_exchange) CU(cudaStreamWaitEvent(ss, fe->x_ready[slot], 0));
+  prof_mark(fe, kMarkStereoStart, ss);
+  launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.snap_pts + (size_t)slot * M,
+            B.right_pts + (size_t)slot * M, B.st_sf + (size_t)slot * M,
+            B.rev_left_pts + (size_t)slot * M, B.st_sb + (size_t)slot * M, B.snap_hdr + slot * 16, M, 3,
+            0, fe->cfg.flow_back ? 2 : 0, ss, &fe->launches);
+  CU(cudaEventRecord(fe->s_done[slot], ss));
+
+  // ---------------- stereo check, undistortion, velocities, packing (:470-473, 496-590): in
+  // window order on the result stream (the velocity maps roll from window to window)
+  CU(cudaStreamWaitEvent(s2, fe->s_done[slot], 0));
   if (fe->r_held[slot]) {  // a consumer stream may still read this slot's previous block
     CU(cudaStreamWaitEvent(s2, fe->r_free[slot], 0));
     fe->r_held[slot] = 0;
   }
-  prof_mark(fe, ESVIO_FE_NUM_STAGES + 2);
-  launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.snap_pts + (size_t)slot * M, B.right_pts,
-            B.st_sf, B.rev_left_pts, B.st_sb, B.snap_hdr + slot * 16, M, 3, 0,
-            fe->cfg.flow_back ? 2 : 0, s2, &fe->launches);
   launch_finalize(fe->tp, B, slot, cur_time, fe->prev_time, s2, &fe->launches);
-  prof_mark(fe, 8);
+  prof_mark(fe, kMarkPacked, s2);
   CU(cudaMemcpyAsync(fe->h_result[slot], B.result + (size_t)slot * fe->result_words, fe->result_words * 4,
                      cudaMemcpyDeviceToHost, s2));
-  prof_mark(fe, 9);
+  prof_mark(fe, kMarkResult, s2);
   CU(cudaEventRecord(fe->q_done[slot], s2));
   CU(cudaGetLastError());
   fe->q_count++;
@@ -785,19 +847,19 @@ FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_e
   int rc;
   if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
   fe->pev_slot = w.slot;
-  // A window passes through three stages, each on its own stream, so that up to three
-  // consecutive windows overlap:  event stage (k+2) | temporal stage (k+1) | stereo stage (k).
-  // Everything a later stage reads from an earlier one is either per-slot (raw events, flags,
-  // snapshot, result) or rotates over three buffers (pyramids), and a slot is only reused
-  // after esvio_fe_track_wait returned its window.
-  prof_mark(fe, 0);
+  // Everything a later node of the window's graph reads from an earlier one is either per-slot
+  // (raw events, flags, snapshot, stereo outputs, result) or rotates (pyramids, binned events),
+  // and a slot is only reused after esvio_fe_track_wait returned its window.
+  prof_mark(fe, kMarkSubmit, fe->stream_c);
   DevEvents ev[2];
   if ((rc = stage_events(fe, w.slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
   if ((rc = stage_events(fe, w.slot, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
-  if ((rc = staging_done(fe, w.slot, fe->stream_e)) != ESVIO_FE_OK) return rc;
-  prof_mark(fe, 1);
-  if ((rc = run_event_stage(fe, cur_time, ev, w.cur, w.rcur, mc)) != ESVIO_FE_OK) return rc;
-  if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame)) != ESVIO_FE_OK) return rc;
+  prof_mark(fe, kMarkLanded, fe->stream_c);
+  if ((rc = staging_done(fe, w.slot)) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, w.slot, cur_time, ev, w.cur, w.rcur, mc)) != ESVIO_FE_OK) return rc;
+  if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame, fe->k1_done[w.slot],
+                            fe->p_done[w.slot])) != ESVIO_FE_OK)
+    return rc;
   fe->pev_valid[w.slot] = fe->profiling;
   return ESVIO_FE_OK;
 }
@@ -835,11 +897,16 @@ FE_API int esvio_fe_track_wait(esvio_fe* fe, esvio_tracks* out) {
   s.n_corner_flags = r[7];
   s.ransac_iters = r[8];
   if (fe->pev_valid[slot]) {
+    // h2d, bin_events, sae_update_ts, pyramid, corner_flags, lk_temporal, select, lk_stereo, d2h
+    static const int kFrom[ESVIO_FE_NUM_STAGES] = {kMarkSubmit, kMarkLanded, kMarkK1Start, kMarkK1Done, kMarkK1Done,
+                                                   kMarkTemporalStart, kMarkTemporalLk, kMarkStereoStart, kMarkPacked};
+    static const int kTo[ESVIO_FE_NUM_STAGES] = {kMarkLanded, kMarkBinned, kMarkK1Done, kMarkPyrDone, kMarkFlagsDone,
+                                                 kMarkTemporalLk, kMarkSelect, kMarkPacked, kMarkResult};
     for (int i = 0; i < ESVIO_FE_NUM_STAGES; ++i)
-      cudaEventElapsedTime(&fe->stage_ms[i],
-                           fe->pev[slot][i == 5 ? ESVIO_FE_NUM_STAGES + 1
-                                                : (i == 7 ? ESVIO_FE_NUM_STAGES + 2 : i)],
-                           fe->pev[slot][i + 1]);
+      if (cudaEventElapsedTime(&fe->stage_ms[i], fe->pev[slot][kFrom[i]], fe->pev[slot][kTo[i]]) != cudaSuccess) {
+        fe->stage_ms[i] = 0.f;
+        cudaGetLastError();
+      }
     for (int i = 0; i < ESVIO_FE_NUM_MARKS; ++i)
       if (cudaEventElapsedTime(&fe->stage_marks[i], fe->pev_ref, fe->pev[slot][i]) != cudaSuccess) {
         fe->stage_marks[i] = -1.f;
@@ -892,18 +959,19 @@ FE_API int esvio_fe_split_image_submit(esvio_fe* fe, double cur_time, const esvi
   cudaStream_t xs = (cudaStream_t)exchange_stream;
   const int slot = fe->windows % kSlots;
   const int idx = fe->windows == 0 ? kRightBase : kRightBase + (fe->cur_right - kRightBase + 1) % kRightBufs;
-  // the staging buffer of this slot was last read by the event stage three windows ago
-  CU(cudaStreamWaitEvent(fe->stream_c, fe->e_done[slot], 0));
-  // sends of earlier windows enqueued on the exchange stream have read the image buffers
+  // nobody waits for results on this GPU, so buffer reuse is ordered by events: the staging
+  // buffer of this slot was last read by the binning kSlots windows ago ...
+  CU(cudaStreamWaitEvent(fe->stream_c, fe->b_done[slot], 0));
+  // ... and the sends of earlier windows, enqueued on the exchange stream, have read the image
+  // buffers before K1 writes the next time surface into one of them
   CU(cudaEventRecord(fe->x_ready[slot], xs));
   CU(cudaStreamWaitEvent(fe->stream_e, fe->x_ready[slot], 0));
   DevEvents d[2];
   memset(d, 0, sizeof(d));
   if ((rc = stage_events(fe, slot, 0, ev, &d[0])) != ESVIO_FE_OK) return rc;
-  if ((rc = staging_done(fe, slot, fe->stream_e)) != ESVIO_FE_OK) return rc;
-  if ((rc = run_event_stage(fe, cur_time, d, idx, idx, nullptr, 1)) != ESVIO_FE_OK) return rc;
-  CU(cudaEventRecord(fe->e_done[slot], fe->stream_e));
-  CU(cudaStreamWaitEvent(xs, fe->e_done[slot], 0));
+  if ((rc = staging_done(fe, slot)) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, slot, cur_time, d, idx, idx, nullptr, 1)) != ESVIO_FE_OK) return rc;
+  CU(cudaStreamWaitEvent(xs, fe->p_done[slot], 0));
   fe->cur_right = idx;
   fe->windows++;
   fe->prev_time = cur_time;
@@ -917,8 +985,7 @@ FE_API int esvio_fe_split_right_buffer(esvio_fe* fe, void** image, size_t* bytes
   int rc;
   if ((rc = split_ok(fe)) != ESVIO_FE_OK) return rc;
   WindowPlan w;
-  // with fewer than three windows in flight the stereo LK that last read this buffer (three
-  // windows ago) has been waited for
+  // the stereo LK that last read this buffer (kSlots windows ago) has been waited for
   if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
   *image = fe->pyr[w.rcur];
   *bytes = fe->pd.bytes;
@@ -934,18 +1001,19 @@ FE_API int esvio_fe_track_submit_split(esvio_fe* fe, double cur_time, const esvi
   WindowPlan w;
   if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
   fe->pev_slot = w.slot;
-  prof_mark(fe, 0);
+  prof_mark(fe, kMarkSubmit, fe->stream_c);
   DevEvents ev[2];
   memset(ev, 0, sizeof(ev));
   if ((rc = stage_events(fe, w.slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
-  if ((rc = staging_done(fe, w.slot, fe->stream_e)) != ESVIO_FE_OK) return rc;
-  prof_mark(fe, 1);
-  if ((rc = run_event_stage(fe, cur_time, ev, w.cur, w.rcur, nullptr, 1)) != ESVIO_FE_OK) return rc;
-  // the stereo stage reads the right image the caller wrote on its exchange stream
+  prof_mark(fe, kMarkLanded, fe->stream_c);
+  if ((rc = staging_done(fe, w.slot)) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, w.slot, cur_time, ev, w.cur, w.rcur, nullptr, 1)) != ESVIO_FE_OK) return rc;
+  // the stereo LK reads the right image the caller wrote on its exchange stream
   cudaStream_t xs = (cudaStream_t)exchange_stream;
   CU(cudaEventRecord(fe->x_ready[w.slot], xs));
-  CU(cudaStreamWaitEvent(fe->stream, fe->x_ready[w.slot], 0));
-  if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame)) != ESVIO_FE_OK) return rc;
+  if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame, fe->k1_done[w.slot], fe->p_done[w.slot],
+                            true)) != ESVIO_FE_OK)
+    return rc;
   fe->pev_valid[w.slot] = fe->profiling;
   return ESVIO_FE_OK;
 }
@@ -999,68 +1067,81 @@ FE_API int esvio_fe_track_image_submit(esvio_fe* fe, double cur_time, const uint
   WindowPlan w;
   if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
   fe->pev_slot = w.slot;
-  cudaStream_t sc = fe->stream_c, se = fe->stream_e, s1 = fe->stream_t1, s2 = fe->stream;
+  cudaStream_t sc = fe->stream_c, sp = fe->stream_p, s1 = fe->stream_t1, ss = fe->stream_s[w.slot & 1],
+               s2 = fe->stream;
   const int slot = w.slot, cur = w.cur, prev = w.prev, rcur = w.rcur, pitch = fe->pd.pitch[0];
   const int M = fe->cfg.max_cnt;
   const TrackBuffers& B = fe->tb;
   const GfttBuffers& G = fe->gftt;
-  // ---- image stage: the frames into pyramid level 0, then the pyramids
-  prof_mark(fe, 0);
+  // ---- image stage: the frames into pyramid level 0 (copy stream), then the pyramids
+  prof_mark(fe, kMarkSubmit, sc);
   CU(cudaMemcpy2DAsync(fe->pyr[cur], pitch, left, left_stride, fe->W, fe->H, cudaMemcpyHostToDevice, sc));
   if (right)
     CU(cudaMemcpy2DAsync(fe->pyr[rcur], pitch, right, right_stride, fe->W, fe->H, cudaMemcpyHostToDevice, sc));
-  if ((rc = staging_done(fe, slot, se)) != ESVIO_FE_OK) return rc;
-  prof_mark(fe, 1);
-  prof_mark(fe, 2);
-  prof_mark(fe, 3);
+  prof_mark(fe, kMarkLanded, sc);
+  if ((rc = staging_done(fe, slot)) != ESVIO_FE_OK) return rc;
+  CU(cudaStreamWaitEvent(sp, fe->c_done[slot], 0));
+  prof_mark(fe, kMarkBinned, sp);
+  prof_mark(fe, kMarkK1Start, sp);
+  prof_mark(fe, kMarkK1Done, sp);
   uint8_t* imgs[2] = {fe->pyr[cur], fe->pyr[rcur]};
-  launch_pyramids(fe->pd, imgs, right ? 2 : 1, se, &fe->launches);
+  launch_pyramids(fe->pd, imgs, right ? 2 : 1, sp, &fe->launches);
   fe->ts_sel[0] = fe->ts_sel[1] = nullptr;
-  prof_mark(fe, 4);
-  prof_mark(fe, 5);
-  CU(cudaEventRecord(fe->e_done[slot], se));
-  // ---- temporal stage (:178-237): forward + full backward LK, Image_setMask, goodFeaturesToTrack
-  CU(cudaStreamWaitEvent(s1, fe->e_done[slot], 0));
-  prof_mark(fe, ESVIO_FE_NUM_STAGES + 1);
+  prof_mark(fe, kMarkPyrDone, sp);
+  prof_mark(fe, kMarkFlagsDone, sp);
+  CU(cudaEventRecord(fe->p_done[slot], sp));
+  // ---- temporal chain (:178-237): forward + full backward LK, Image_setMask, goodFeaturesToTrack
+  CU(cudaStreamWaitEvent(s1, fe->p_done[slot], 0));
+  prof_mark(fe, kMarkTemporalStart, s1);
   launch_lk(fe->pd, fe->pyr[prev], fe->pyr[cur], B.prev_pts, B.cur_pts, B.st_fwd, B.rev_pts,
             B.st_bwd, &B.st->n_prev, M, 3, 0, fe->cfg.flow_back ? 2 : 0, s1, &fe->launches);
   launch_post_temporal(fe->tp, B, pub_this_frame ? -1 : slot, s1, &fe->launches);
-  prof_mark(fe, 6);
+  prof_mark(fe, kMarkTemporalLk, s1);
   if (pub_this_frame) {
     // the scratch of goodFeaturesToTrack is only touched on this stream, so windows in flight
     // cannot collide on it
     launch_image_set_mask(fe->tp, B, G, s1, &fe->launches);
     launch_gftt_eig(G, fe->pyr[cur], pitch, fe->W, fe->H, s1, &fe->launches);
     launch_gftt_thr(G, fe->W, fe->H, true, s1, &fe->launches);
-    if (launch_gftt_candidates(G, fe->W, fe->H, true, s1, &fe->launches) != 0)
-      return fail(fe, ESVIO_FE_ECUDA, "radix sort of the corner candidates", cudaGetLastError());
+    if (launch_gftt_candidates(G, fe->W, fe->H, true, s1, &fe->launches) != 0) {
+      // nothing of this frame has been booked yet: drain what was enqueued and drop the frame
+      const cudaError_t ce = cudaGetLastError();
+      sync_all(fe);
+      return fail(fe, ESVIO_FE_ECUDA, "sort of the corner candidates (frame dropped)", ce);
+    }
     launch_gftt_pick_tracks(fe->tp, B, G, slot, s1, &fe->launches);
   }
-  prof_mark(fe, 7);
+  prof_mark(fe, kMarkSelect, s1);
   CU(cudaEventRecord(fe->t1_done[slot], s1));
-  // ---- stereo stage (:245-322)
-  CU(cudaStreamWaitEvent(s2, fe->t1_done[slot], 0));
+  // ---- stereo LK (:245-322) on one of the two alternating streams
+  CU(cudaStreamWaitEvent(ss, fe->t1_done[slot], 0));
+  prof_mark(fe, kMarkStereoStart, ss);
+  if (right)
+    launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.snap_pts + (size_t)slot * M,
+              B.right_pts + (size_t)slot * M, B.st_sf + (size_t)slot * M,
+              B.rev_left_pts + (size_t)slot * M, B.st_sb + (size_t)slot * M, B.snap_hdr + slot * 16, M,
+              3, 0, fe->cfg.flow_back ? 2 : 0, ss, &fe->launches);
+  else  // no right image: no right points
+    CU(cudaMemsetAsync(B.st_sf + (size_t)slot * M, 0, M, ss));
+  CU(cudaEventRecord(fe->s_done[slot], ss));
+  // ---- packing, in frame order on the result stream
+  CU(cudaStreamWaitEvent(s2, fe->s_done[slot], 0));
   if (fe->r_held[slot]) {
     CU(cudaStreamWaitEvent(s2, fe->r_free[slot], 0));
     fe->r_held[slot] = 0;
   }
-  prof_mark(fe, ESVIO_FE_NUM_STAGES + 2);
   if (right) {
-    launch_lk(fe->pd, fe->pyr[cur], fe->pyr[rcur], B.snap_pts + (size_t)slot * M, B.right_pts,
-              B.st_sf, B.rev_left_pts, B.st_sb, B.snap_hdr + slot * 16, M, 3, 0,
-              fe->cfg.flow_back ? 2 : 0, s2, &fe->launches);
     launch_finalize(fe->tp, B, slot, cur_time, fe->prev_time, s2, &fe->launches);
   } else {
-    // no right image: no right points, and prev_un_right_pts_map stays as it is (:245)
-    CU(cudaMemsetAsync(B.st_sf, 0, M, s2));
+    // prev_un_right_pts_map stays as it is (:245: the whole block is skipped)
     launch_right_map_keep(B, 0, s2, &fe->launches);
     launch_finalize(fe->tp, B, slot, cur_time, fe->prev_time, s2, &fe->launches);
     launch_right_map_keep(B, 1, s2, &fe->launches);
   }
-  prof_mark(fe, 8);
+  prof_mark(fe, kMarkPacked, s2);
   CU(cudaMemcpyAsync(fe->h_result[slot], B.result + (size_t)slot * fe->result_words, fe->result_words * 4,
                      cudaMemcpyDeviceToHost, s2));
-  prof_mark(fe, 9);
+  prof_mark(fe, kMarkResult, s2);
   CU(cudaEventRecord(fe->q_done[slot], s2));
   CU(cudaGetLastError());
   fe->q_count++;
@@ -1157,11 +1238,11 @@ struct esvio_fe_group {
   double2 *sae, *lat;                                 // [2S][H][W]
   double2 *own_sae[kMaxCams / 2], *own_lat[kMaxCams / 2];  // the members' own planes (unused)
   CUtensorMap map_sae, map_lat;
-  EventStageBuffers esb;
+  EventStageBuffers esb[2];  // even / odd windows, as in esvio_fe
   BinLayout bl;
-  cudaStream_t stream_e;
-  cudaEvent_t g_done[kSlots];
-  cudaEvent_t k1_beg[kSlots], k1_end[kSlots];
+  cudaStream_t stream_b, stream_e, stream_p;  // batched K0 | K1 | pyramids of all 2S cameras
+  cudaEvent_t b_done[kSlots], p_done[kSlots];
+  cudaEvent_t k1_beg[kSlots], k1_end[kSlots];  // timed; k1_end doubles as "SAE + time surface done"
   int k1_slot_valid[kSlots];
   float k1_ms;
   int k1_ms_valid;
@@ -1171,7 +1252,8 @@ struct esvio_fe_group {
 FE_API void esvio_fe_group_destroy(esvio_fe_group* g) {
   if (!g) return;
   cudaSetDevice(g->dev);
-  if (g->stream_e) cudaStreamSynchronize(g->stream_e);
+  for (cudaStream_t st : {g->stream_b, g->stream_e, g->stream_p})
+    if (st) cudaStreamSynchronize(st);
   for (int i = 0; i < g->S; ++i)
     if (g->m[i]) {
       sync_all(g->m[i]);
@@ -1182,20 +1264,21 @@ FE_API void esvio_fe_group_destroy(esvio_fe_group* g) {
     }
   cudaFree(g->sae);
   cudaFree(g->lat);
-  for (int c = 0; c < kMaxCams; ++c) {
-    cudaFree(g->esb.bt[c]);
-    cudaFree(g->esb.bk[c]);
+  for (int b = 0; b < 2; ++b) {
+    for (int c = 0; c < kMaxCams; ++c) {
+      cudaFree(g->esb[b].bt[c]);
+      cudaFree(g->esb[b].bk[c]);
+    }
+    cudaFree(g->esb[b].counts);
+    cudaFree(g->esb[b].bin_total);
+    cudaFree(g->esb[b].bin_start);
+    cudaFree(g->esb[b].done_ctr);
   }
-  cudaFree(g->esb.counts);
-  cudaFree(g->esb.bin_total);
-  cudaFree(g->esb.bin_start);
-  cudaFree(g->esb.done_ctr);
-  for (int k = 0; k < kSlots; ++k) {
-    if (g->g_done[k]) cudaEventDestroy(g->g_done[k]);
-    if (g->k1_beg[k]) cudaEventDestroy(g->k1_beg[k]);
-    if (g->k1_end[k]) cudaEventDestroy(g->k1_end[k]);
-  }
-  if (g->stream_e) cudaStreamDestroy(g->stream_e);
+  for (int k = 0; k < kSlots; ++k)
+    for (cudaEvent_t ev : {g->b_done[k], g->p_done[k], g->k1_beg[k], g->k1_end[k]})
+      if (ev) cudaEventDestroy(ev);
+  for (cudaStream_t st : {g->stream_b, g->stream_e, g->stream_p})
+    if (st) cudaStreamDestroy(st);
   free(g);
 }
 
@@ -1229,24 +1312,30 @@ FE_API int esvio_fe_group_create(const esvio_fe_config* cfg, int32_t n_streams,
   {
     int prio_lo = 0, prio_hi = 0;
     GC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    GC(cudaStreamCreateWithPriority(&g->stream_b, cudaStreamNonBlocking, prio_hi));
     GC(cudaStreamCreateWithPriority(&g->stream_e, cudaStreamNonBlocking, prio_hi));
+    GC(cudaStreamCreateWithPriority(&g->stream_p, cudaStreamNonBlocking, prio_hi));
   }
   GC(cudaMalloc(&g->sae, npx * NC * sizeof(double2)));
   GC(cudaMalloc(&g->lat, npx * NC * sizeof(double2)));
   GC(cudaMemset(g->sae, 0, npx * NC * sizeof(double2)));
   GC(cudaMemset(g->lat, 0, npx * NC * sizeof(double2)));
-  g->esb.n_cams = NC;
-  for (int c = 0; c < NC; ++c) {
-    GC(cudaMalloc(&g->esb.bt[c], (size_t)f0->cap * sizeof(double)));
-    GC(cudaMalloc(&g->esb.bk[c], (size_t)f0->cap * sizeof(uint16_t)));
+  for (int b = 0; b < 2; ++b) {
+    EventStageBuffers& E = g->esb[b];
+    E.n_cams = NC;
+    for (int c = 0; c < NC; ++c) {
+      GC(cudaMalloc(&E.bt[c], (size_t)f0->cap * sizeof(double)));
+      GC(cudaMalloc(&E.bk[c], (size_t)f0->cap * sizeof(uint16_t)));
+    }
+    GC(cudaMalloc(&E.counts, (size_t)NC * nb * g->bl.max_chunks * sizeof(uint32_t)));
+    GC(cudaMalloc(&E.bin_total, (size_t)NC * nb * sizeof(uint32_t)));
+    GC(cudaMalloc(&E.bin_start, (size_t)NC * (nb + 1) * sizeof(uint32_t)));
+    GC(cudaMalloc(&E.done_ctr, NC * sizeof(unsigned int)));
+    GC(cudaMemset(E.done_ctr, 0, NC * sizeof(unsigned int)));
   }
-  GC(cudaMalloc(&g->esb.counts, (size_t)NC * nb * g->bl.max_chunks * sizeof(uint32_t)));
-  GC(cudaMalloc(&g->esb.bin_total, (size_t)NC * nb * sizeof(uint32_t)));
-  GC(cudaMalloc(&g->esb.bin_start, (size_t)NC * (nb + 1) * sizeof(uint32_t)));
-  GC(cudaMalloc(&g->esb.done_ctr, NC * sizeof(unsigned int)));
-  GC(cudaMemset(g->esb.done_ctr, 0, NC * sizeof(unsigned int)));
   for (int k = 0; k < kSlots; ++k) {
-    GC(cudaEventCreateWithFlags(&g->g_done[k], cudaEventDisableTiming));
+    GC(cudaEventCreateWithFlags(&g->b_done[k], cudaEventDisableTiming));
+    GC(cudaEventCreateWithFlags(&g->p_done[k], cudaEventDisableTiming));
     GC(cudaEventCreate(&g->k1_beg[k]));
     GC(cudaEventCreate(&g->k1_end[k]));
   }
@@ -1273,7 +1362,7 @@ FE_API int esvio_fe_group_reset(esvio_fe_group* g) {
   if (!g) return ESVIO_FE_EINVAL;
   esvio_fe* fe = g->m[0];
   CU(cudaSetDevice(g->dev));
-  CU(cudaStreamSynchronize(g->stream_e));
+  for (cudaStream_t st : {g->stream_b, g->stream_e, g->stream_p}) CU(cudaStreamSynchronize(st));
   for (int i = 0; i < g->S; ++i) {
     int rc = sync_all(g->m[i]);
     if (rc == ESVIO_FE_OK) rc = reset_state(g->m[i]);  // clears the member's slice of the SAE too
@@ -1300,17 +1389,27 @@ FE_API int esvio_fe_group_track_submit(esvio_fe_group* g, const double* cur_time
   int rc;
   for (int i = 0; i < S; ++i)
     if ((rc = plan_window(g->m[i], &w[i])) != ESVIO_FE_OK) return rc;
-  cudaStream_t se = g->stream_e;
+  cudaStream_t sb = g->stream_b, se = g->stream_e, s_pyr = g->stream_p;
   const int slot = w[0].slot;  // members are always submitted and waited together
-  // the previous window's corner flags read the SAE this window is about to change
-  for (int i = 0; i < S; ++i)
-    if (g->m[i]->windows > 0) CU(cudaStreamWaitEvent(se, g->m[i]->e_done[(w[i].slot + kSlots - 1) % kSlots], 0));
+  // ---- K0 of all 2S cameras on the group's binning stream, behind the members' copies and the
+  // K1 that last read this set of binned-event buffers (two windows back)
+  const EventStageBuffers& esb = g->esb[slot & 1];
   for (int i = 0; i < S; ++i) {
     if ((rc = stage_events(g->m[i], w[i].slot, 0, &left[i], &ev[2 * i])) != ESVIO_FE_OK) return rc;
     if ((rc = stage_events(g->m[i], w[i].slot, 1, &right[i], &ev[2 * i + 1])) != ESVIO_FE_OK) return rc;
-    if ((rc = staging_done(g->m[i], w[i].slot, se)) != ESVIO_FE_OK) return rc;
+    if ((rc = staging_done(g->m[i], w[i].slot)) != ESVIO_FE_OK) return rc;
+    CU(cudaStreamWaitEvent(sb, g->m[i]->c_done[w[i].slot], 0));
   }
-  launch_bin_events(g->bl, g->esb, ev, se, &g->launches);
+  CU(cudaStreamWaitEvent(sb, g->k1_end[(slot + kSlots - 2) % kSlots], 0));
+  launch_bin_events(g->bl, esb, ev, sb, &g->launches);
+  CU(cudaEventRecord(g->b_done[slot], sb));
+  // ---- ONE K1 launch for the group, behind the members' corner flags of the window before
+  CU(cudaStreamWaitEvent(se, g->b_done[slot], 0));
+  for (int i = 0; i < S; ++i)
+    if (g->m[i]->f_pending >= 0) {
+      CU(cudaStreamWaitEvent(se, g->m[i]->f_done[g->m[i]->f_pending], 0));
+      g->m[i]->f_pending = -1;
+    }
   SaeTsParams sp;
   sp.W = fe->W;
   sp.H = fe->H;
@@ -1321,15 +1420,15 @@ FE_API int esvio_fe_group_track_submit(esvio_fe_group* g, const double* cur_time
   sp.inv_decay = 1.0 / sp.decay_sec;
   sp.filter_threshold = fe->cfg.feature_filter_threshold;
   sp.ignore_polarity = fe->cfg.ignore_polarity;
-  sp.bin_start = g->esb.bin_start;
+  sp.bin_start = esb.bin_start;
   sp.ts_pitch = fe->pd.pitch[0];
   uint8_t* imgs[kMaxCams];
   for (int c = 0; c < kMaxCams; ++c) {
     const bool on = c < 2 * S;
     const int i = c / 2;
     sp.t_ref[c] = on ? cur_time[i] : 0.0;
-    sp.bt[c] = on ? g->esb.bt[c] : nullptr;
-    sp.bk[c] = on ? g->esb.bk[c] : nullptr;
+    sp.bt[c] = on ? esb.bt[c] : nullptr;
+    sp.bk[c] = on ? esb.bk[c] : nullptr;
     imgs[c] = on ? g->m[i]->pyr[(c & 1) ? w[i].rcur : w[i].cur] : nullptr;
     sp.ts[c] = imgs[c];
   }
@@ -1337,16 +1436,19 @@ FE_API int esvio_fe_group_track_submit(esvio_fe_group* g, const double* cur_time
   launch_sae_update_ts(sp, g->map_sae, g->map_lat, se, &g->launches);
   CU(cudaEventRecord(g->k1_end[slot], se));
   g->k1_slot_valid[slot] = 1;
-  launch_pyramids(fe->pd, imgs, 2 * S, se, &g->launches);
+  // ---- pyramids of all cameras
+  CU(cudaStreamWaitEvent(s_pyr, g->k1_end[slot], 0));
+  launch_pyramids(fe->pd, imgs, 2 * S, s_pyr, &g->launches);
   CU(cudaGetLastError());
-  CU(cudaEventRecord(g->g_done[slot], se));
+  CU(cudaEventRecord(g->p_done[slot], s_pyr));
   for (int i = 0; i < S; ++i) {
     esvio_fe* m = g->m[i];
     m->ts_sel[0] = m->pyr[w[i].cur];
     m->ts_sel[1] = m->pyr[w[i].rcur];
     m->pev_valid[w[i].slot] = 0;
-    CU(cudaStreamWaitEvent(m->stream_e, g->g_done[slot], 0));
-    if ((rc = submit_tracking(m, w[i], ev[2 * i], cur_time[i], pub_this_frame[i])) != ESVIO_FE_OK) return rc;
+    if ((rc = submit_tracking(m, w[i], ev[2 * i], cur_time[i], pub_this_frame[i], g->k1_end[slot],
+                              g->p_done[slot])) != ESVIO_FE_OK)
+      return rc;
   }
   return ESVIO_FE_OK;
 }
@@ -1536,10 +1638,9 @@ FE_API int esvio_fe_stage_update_mc(esvio_fe* fe, double t_ref, const esvio_even
   if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
   if ((rc = stage_events(fe, 0, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
   if ((rc = stage_events(fe, 0, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
-  if ((rc = staging_done(fe, 0, fe->stream_e)) != ESVIO_FE_OK) return rc;
-  if ((rc = run_event_stage(fe, t_ref, ev, fe->cur_left, fe->cur_right, mc)) != ESVIO_FE_OK) return rc;
-  CU(cudaStreamSynchronize(fe->stream_e));
-  return ESVIO_FE_OK;
+  if ((rc = staging_done(fe, 0)) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, 0, t_ref, ev, fe->cur_left, fe->cur_right, mc)) != ESVIO_FE_OK) return rc;
+  return sync_all(fe);
 }
 
 FE_API int esvio_fe_stage_corner_flags(esvio_fe* fe, const esvio_events* left, int32_t and_ts_test,
@@ -1551,7 +1652,8 @@ FE_API int esvio_fe_stage_corner_flags(esvio_fe* fe, const esvio_events* left, i
   int rc;
   if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
   if ((rc = stage_events(fe, 0, 0, left, &ev)) != ESVIO_FE_OK) return rc;
-  if ((rc = staging_done(fe, 0, fe->stream_e)) != ESVIO_FE_OK) return rc;
+  if ((rc = staging_done(fe, 0)) != ESVIO_FE_OK) return rc;
+  CU(cudaStreamWaitEvent(fe->stream_e, fe->c_done[0], 0));
   launch_corner_flags(corner_params(fe, fe->cur_left, and_ts_test), ev, fe->flags[0],
                       fe->stream_e, &fe->launches);
   CU(cudaGetLastError());

@@ -578,10 +578,11 @@ k_finalize(TrackParams P, TrackBuffers B, int slot, double cur_time, double prev
     r_vx[i] = vx;
     r_vy[i] = vy;
     // stereo check
-    rp = B.right_pts[i];
-    keep = B.st_sf[i] != 0;
+    rp = B.right_pts[slot * M + i];
+    keep = B.st_sf[slot * M + i] != 0;
     if (P.flow_back)
-      keep = keep && B.st_sb[i] && in_border(P.W, P.H, rp) && pt_dist(cp, B.rev_left_pts[i]) <= 0.5;
+      keep = keep && B.st_sb[slot * M + i] && in_border(P.W, P.H, rp) &&
+             pt_dist(cp, B.rev_left_pts[slot * M + i]) <= 0.5;
   }
   int total;
   const int pos = block_excl_scan_1024(keep, s_warp, &total);

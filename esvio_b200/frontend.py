@@ -20,6 +20,11 @@ AOS_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("sec", "<u4"), ("nsec", "<u4"
                       ("pad", "V3")])
 
 
+def pipeline_depth() -> int:
+    """Windows that may be in flight between submit() and wait() (esvio_fe_pipeline_depth)."""
+    return int(_capi.lib().esvio_fe_pipeline_depth())
+
+
 def make_config(cfg: dict) -> Config:
     """dict with the reference's parameter names -> esvio_fe_config."""
     c = Config()
@@ -230,7 +235,7 @@ class EventFrontEnd:
         """Right GPU: SAE update + time surface + pyramid of this handle's one camera; returns
         (device pointer, bytes) of the image block, ready on `exchange_stream` (cudaStream_t)."""
         e = events if isinstance(events, _Ev) else _Ev(events)
-        self._split_keep = getattr(self, "_split_keep", [])[-2:] + [e]   # host buffers of 3 windows
+        self._split_keep = getattr(self, "_split_keep", [])[-(pipeline_depth() - 1):] + [e]   # host buffers of the windows in flight
         p, n = C.c_void_p(), C.c_size_t()
         self._chk(_capi.lib().esvio_fe_split_image_submit(self._h, float(cur_time), C.byref(e.s),
                                                           C.c_void_p(exchange_stream), C.byref(p),
@@ -311,7 +316,7 @@ class EventFrontEnd:
     def stage_marks(self):
         """Timeline of the last profiled window: ms since set_profiling(True) of the 12 markers
         (include/esvio_fe.h)."""
-        ms = (C.c_float * 12)()
+        ms = (C.c_float * 13)()
         self._chk(_capi.lib().esvio_fe_get_stage_marks(self._h, ms), "get_stage_marks")
         return list(ms)
 

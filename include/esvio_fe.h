@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ESVIO_FE_ABI_VERSION 2
+#define ESVIO_FE_ABI_VERSION 3
 
 typedef enum esvio_status {
   ESVIO_FE_OK = 0,
@@ -161,10 +161,13 @@ const char *esvio_fe_last_error(const esvio_fe *fe);
  * Synchronous: returns after the <= 2*max_cnt track records are on the host. */
 int esvio_fe_track(esvio_fe *fe, double cur_time, const esvio_events *left,
                    const esvio_events *right, int32_t pub_this_frame, esvio_tracks *out);
-/* The same call split in two so that consecutive windows overlap on the GPU (event stage
- * of window k+2 | temporal LK + selection of window k+1 | stereo LK of window k): at most
- * 3 windows may be in flight; waits return results in order.  Host event buffers passed to
- * submit must stay valid until the matching wait returns. */
+/* The same call split in two so that consecutive windows overlap on the GPU (a window is a
+ * graph of short kernels on several streams; only the SAE update, the temporal chain and the
+ * packing are serial from window to window): at most esvio_fe_pipeline_depth() windows may be
+ * in flight; waits return results in order.  Host event buffers passed to submit must stay
+ * valid and unmodified until the matching wait returns (the copy is asynchronous).  A wait
+ * whose `out` is too small (ESVIO_FE_ECAPACITY) leaves the window waitable. */
+int esvio_fe_pipeline_depth(void);
 int esvio_fe_track_submit(esvio_fe *fe, double cur_time, const esvio_events *left,
                           const esvio_events *right, int32_t pub_this_frame);
 int esvio_fe_track_wait(esvio_fe *fe, esvio_tracks *out);
@@ -190,7 +193,9 @@ int esvio_fe_track_submit_mc(esvio_fe *fe, double cur_time, const esvio_events *
  * Images are CV_8UC1, width x height of the config, `stride` bytes per row; config.max_cnt /
  * min_dist play MAX_CNT_IMG / MIN_DIST_IMG.  right == NULL is img_right.empty() (mono).
  * Use a handle of its own for frames (the reference runs them in a separate node,
- * stereo_image_tracker_node.cpp:45).  Results come back through esvio_fe_track_wait. */
+ * stereo_image_tracker_node.cpp:45).  Results come back through esvio_fe_track_wait.  The
+ * submit form copies the frames asynchronously: they must stay valid and unmodified until the
+ * matching esvio_fe_track_wait returns. */
 int esvio_fe_track_image(esvio_fe *fe, double cur_time, const uint8_t *left, size_t left_stride,
                          const uint8_t *right, size_t right_stride, int32_t pub_this_frame,
                          esvio_tracks *out);
@@ -248,7 +253,7 @@ int esvio_fe_stream(esvio_fe *fe, void **cuda_stream);
  * kept off the tracking streams): _acquire makes `consumer_stream` (cudaStream_t) wait for the
  * most recently submitted window's packed records and returns their device address (every
  * in-flight window has its own block); after enqueuing its reads the caller calls _release on
- * the same stream, and the block is not rewritten (three windows later) before those reads
+ * the same stream, and the block is not rewritten (a pipeline depth later) before those reads
  * have finished.  No host synchronisation on either side. */
 int esvio_fe_result_acquire(esvio_fe *fe, void *consumer_stream, void **ptr, size_t *bytes);
 int esvio_fe_result_release(esvio_fe *fe, void *consumer_stream);
@@ -280,11 +285,12 @@ int esvio_fe_track_submit_split(esvio_fe *fe, double cur_time, const esvio_event
  * 5 temporal LK + filter, 6 select (ransac+mask+corners), 7 stereo LK + pack, 8 d2h */
 int esvio_fe_set_profiling(esvio_fe *fe, int32_t on);
 int esvio_fe_get_stage_ms(esvio_fe *fe, float *ms /* ESVIO_FE_NUM_STAGES */);
-/* The same window as a timeline: milliseconds since esvio_fe_set_profiling(fe, 1) of the 12
- * markers  0 submit, 1 events landed, 2 binned, 3 time surface done, 4 pyramids done, 5 corner
- * flags done (event stage, own stream) | 6 temporal LK + filter done, 7 selection done, 10 start
- * (temporal stream) | 8 stereo LK + pack done, 9 result on the host, 11 start (stereo stream). */
-#define ESVIO_FE_NUM_MARKS 12
+/* The same window as a timeline: milliseconds since esvio_fe_set_profiling(fe, 1) of the
+ * markers, each on the stream it reports on:  0 submit, 1 events landed (copy stream) | 12
+ * binned | 2 SAE kernel start, 3 time surface done | 4 pyramids done | 5 corner flags done |
+ * 10 temporal chain start, 6 temporal LK + filter done, 7 selection done | 11 stereo LK start
+ * | 8 packed, 9 result on the host (result stream). */
+#define ESVIO_FE_NUM_MARKS 13
 int esvio_fe_get_stage_marks(esvio_fe *fe, float *ms /* ESVIO_FE_NUM_MARKS */);
 int esvio_fe_kernel_launches(esvio_fe *fe, int64_t *count); /* kernels launched so far */
 

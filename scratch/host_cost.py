@@ -1,4 +1,4 @@
-"""Host-side cost of one window: perf_counter around submit() and wait() in the 3-deep loop,
+"""Host-side cost of one window: perf_counter around submit() and wait() in the pipelined loop,
 next to the CUDA-event time of the same loop."""
 import sys, time, os
 import numpy as np
@@ -28,7 +28,7 @@ for k in range(Wm, Wm + K):
     fe.submit(dw[k][2], dw[k][0], dw[k][1], k % pub_div == 0)
     t1 = time.perf_counter()
     ts.append((t1 - t0, k % pub_div == 0))
-    if k - Wm >= 2:
+    if k - Wm >= frontend.pipeline_depth() - 1:
         fe.wait(unpack=False)
         tw.append(time.perf_counter() - t1)
 while len(tw) < K:

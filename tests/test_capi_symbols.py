@@ -75,7 +75,7 @@ def test_header_is_plain_c99(tmp_path):
     src = tmp_path / "hdr.c"
     src.write_text('#include "esvio_fe.h"\n'
                    "int main(void) { esvio_fe_config c; esvio_tracks t; esvio_events e; esvio_motion m;\n"
-                   "  (void)c; (void)t; (void)e; (void)m; return ESVIO_FE_ABI_VERSION == 2 ? 0 : 1; }\n")
+                   "  (void)c; (void)t; (void)e; (void)m; return ESVIO_FE_ABI_VERSION == 3 ? 0 : 1; }\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I",
                            os.path.join(root, "include"), "-c", str(src), "-o", str(tmp_path / "hdr.o")])

@@ -327,20 +327,21 @@ def test_submit_wait_pipeline_equals_sync(fe_mod):
     s = synth.StereoEventStream(W, H, 1.0e6)
     wins = [s.stereo_window(k) for k in range(8)]
     sync = [a.track(t, L, R, k % 2 == 0) for k, (L, R, t) in enumerate(wins)]
-    # three windows in flight: event stage (k+2) | temporal stage (k+1) | stereo stage (k)
+    # as many windows in flight as the library takes: their kernels overlap on several streams
+    depth = fe_mod.pipeline_depth()
+    assert depth >= 3
     outs = []
-    b.submit(wins[0][2], wins[0][0], wins[0][1], True)
-    b.submit(wins[1][2], wins[1][0], wins[1][1], False)
-    for k in range(2, len(wins)):
+    for k in range(len(wins)):
         L, R, t = wins[k]
         b.submit(t, L, R, k % 2 == 0)
+        if k >= depth - 1:
+            outs.append(b.wait())
+    while len(outs) < len(wins):
         outs.append(b.wait())
-    outs.append(b.wait())
-    outs.append(b.wait())
     with pytest.raises(fe_mod.FrontEndError):
-        for _ in range(4):
-            b.submit(wins[0][2], wins[0][0], wins[0][1], True)   # a 4th window in flight is refused
-    for _ in range(3):
+        for _ in range(depth + 1):
+            b.submit(wins[0][2], wins[0][0], wins[0][1], True)   # one window too many is refused
+    for _ in range(depth):
         b.wait()
     for x, y in zip(sync, outs):
         for key in ("id", "u", "v", "id_right", "ru", "rv", "vx", "vy"):
@@ -646,12 +647,13 @@ def test_capacity_and_state_errors(fe_mod):
         fe.track(t_ref, L, R, True)
     assert e.value.status == fe_mod._capi.ECAPACITY
     small = tuple(a[:1000] for a in L)
-    for _ in range(3):
+    depth = fe_mod.pipeline_depth()
+    for _ in range(depth):
         fe.submit(t_ref, small, small, True)
-    with pytest.raises(fe_mod.FrontEndError) as e:      # a fourth window in flight
+    with pytest.raises(fe_mod.FrontEndError) as e:      # one window too many in flight
         fe.submit(t_ref, small, small, True)
     assert e.value.status == fe_mod._capi.ESTATE
-    for _ in range(3):
+    for _ in range(depth):
         fe.wait()
     with pytest.raises(fe_mod.FrontEndError) as e:      # nothing left to wait for
         fe.wait()
@@ -710,7 +712,7 @@ def test_single_copy_soa_block_equals_separate_arrays(fe_mod):
     fa.close(); fb.close()
 
 
-@pytest.mark.parametrize("W,H,rate,depth", [(346, 260, 1.0e6, 1), (640, 480, 5.0e6, 3)])
+@pytest.mark.parametrize("W,H,rate,depth", [(346, 260, 1.0e6, 1), (640, 480, 5.0e6, 3), (346, 260, 1.0e6, 6)])
 def test_left_right_split_equals_one_handle(fe_mod, W, H, rate, depth):
     """SURVEY.md 8e row 2 through the C ABI: the right camera's SAE / time surface / pyramid on
     one handle (the 'right GPU'), the image block moved on the caller's stream, tracking on the
@@ -752,12 +754,12 @@ def test_left_right_split_equals_one_handle(fe_mod, W, H, rate, depth):
     for a, b in zip(ref.sae_planes(0), left.sae_planes(0)):
         assert np.array_equal(a, b)
     assert np.array_equal(ref.time_surface(0), left.time_surface(0))
-    # a 4th window in flight is refused before anything is written
-    for k in range(3):
+    # one window too many in flight is refused before anything is written
+    for k in range(fe_mod.pipeline_depth()):
         submit(k)
     with pytest.raises(fe_mod.FrontEndError):
         left.split_right_buffer()
-    for _ in range(3):
+    for _ in range(fe_mod.pipeline_depth()):
         left.wait()
     for f in (ref, left, right):
         f.close()
