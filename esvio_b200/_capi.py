@@ -128,6 +128,8 @@ SYMBOLS = {
     "esvio_fe_get_stage_ms": (C.c_int, [_H, _pf]),
     "esvio_fe_get_stage_marks": (C.c_int, [_H, _pf]),
     "esvio_fe_pipeline_depth": (C.c_int, []),
+    "esvio_fe_stage_set_tracks": (C.c_int, [_H, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "esvio_fe_kernel_launches": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "esvio_fe_get_sae": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
     "esvio_fe_stage_update": (C.c_int, [_H, C.c_double, C.POINTER(Events), C.POINTER(Events)]),

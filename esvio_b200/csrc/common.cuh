@@ -33,6 +33,7 @@ constexpr int kMaxCnt = 1024;                 // hard cap on MAX_CNT
 constexpr int kMaxCams = 16;                  // cameras per launch: 8 stereo streams of one group
 constexpr int kSlots = 6;                     // windows in flight: a window is a ~0.4 ms chain of short
                                               // kernels, a new one can start every ~0.08 ms
+constexpr int kCornerBlock = 128;             // events per CTA of k_corner_flags = per candidate list
 constexpr int kResultHdr = 32;                // int32 words in front of the result arrays
 constexpr int kResultArrays = 15;
 
@@ -289,6 +290,10 @@ struct CornerParams {
   const uint8_t* ts;   // left level-0 image (may be null when and_ts_test == 0)
   int ts_pitch;
   int and_ts_test;
+  // per CTA of kCornerBlock events: the flagged events' pixels (x | y << 16) in stream order
+  // and their number; null = flags only
+  uint32_t* cand;   // [ceil(n / kCornerBlock) * kCornerBlock]
+  int* cand_cnt;    // [ceil(n / kCornerBlock)]
 };
 void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* flags,
                          cudaStream_t s, int64_t* launches);
@@ -394,8 +399,9 @@ void launch_right_map_keep(const TrackBuffers& B, int restore, cudaStream_t s, i
 // per-slot snapshot (cur_pts, ids, track_cnt, counters) the stereo stage works from
 void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, int snap_slot,
                           cudaStream_t s, int64_t* launches);
-void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents& left,
-                   const uint8_t* flags, int snap_slot, cudaStream_t s, int64_t* launches);
+// cand / cand_cnt: the candidate lists k_corner_flags left for the window's n_events left events
+void launch_select(const TrackParams& P, const TrackBuffers& B, int n_events, const uint32_t* cand,
+                   const int* cand_cnt, int snap_slot, cudaStream_t s, int64_t* launches);
 void launch_finalize(const TrackParams& P, const TrackBuffers& B, int slot, double cur_time,
                      double prev_time, cudaStream_t s, int64_t* launches);
 void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,

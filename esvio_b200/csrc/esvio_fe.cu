@@ -62,6 +62,8 @@ struct esvio_fe {
   EventStageBuffers esb[2];  // binned events of even / odd windows: binning of window k+1 runs
                              // while the SAE kernel of window k still reads window k's
   uint8_t* flags[kSlots];   // [slot] Arc* corner flags of the left events
+  uint32_t* cand[kSlots];   // [slot] the flagged events' pixels, one list per kCornerBlock events
+  int* cand_cnt[kSlots];
   // A window is a graph of short kernels; every node that has no data dependency on another
   // gets its own stream, and windows overlap wherever the data allow it (dependencies are
   // CUDA events, never host synchronisation):
@@ -245,6 +247,8 @@ static void free_all(esvio_fe* fe) {
     cudaFree(fe->raw[i][0]);
     cudaFree(fe->raw[i][1]);
     cudaFree(fe->flags[i]);
+    cudaFree(fe->cand[i]);
+    cudaFree(fe->cand_cnt[i]);
     for (cudaEvent_t ev : {fe->c_done[i], fe->b_done[i], fe->k1_done[i], fe->p_done[i], fe->f_done[i],
                            fe->t1_done[i], fe->s_done[i], fe->x_ready[i]})
       if (ev) cudaEventDestroy(ev);
@@ -397,6 +401,8 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(cudaMalloc(&fe->raw[c][0], (size_t)fe->cap * 16));
     CUC(cudaMalloc(&fe->raw[c][1], (size_t)fe->cap * 16));
     CUC(cudaMalloc(&fe->flags[c], (size_t)fe->cap + 16));
+    CUC(cudaMalloc(&fe->cand[c], ((size_t)fe->cap + kCornerBlock) * sizeof(uint32_t)));
+    CUC(cudaMalloc(&fe->cand_cnt[c], ((size_t)fe->cap / kCornerBlock + 2) * sizeof(int)));
     for (cudaEvent_t* ev : {&fe->c_done[c], &fe->b_done[c], &fe->k1_done[c], &fe->p_done[c], &fe->f_done[c],
                             &fe->t1_done[c], &fe->s_done[c], &fe->x_ready[c]})
       CUC(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
@@ -727,7 +733,7 @@ static int run_event_stage(esvio_fe* fe, int slot, double t_ref, const DevEvents
   return ESVIO_FE_OK;
 }
 
-static CornerParams corner_params(esvio_fe* fe, int left_idx, int and_ts) {
+static CornerParams corner_params(esvio_fe* fe, int left_idx, int and_ts, int slot) {
   CornerParams cp;
   cp.W = fe->W;
   cp.H = fe->H;
@@ -739,6 +745,8 @@ static CornerParams corner_params(esvio_fe* fe, int left_idx, int and_ts) {
   cp.ts = fe->ts_sel[0] ? fe->ts_sel[0] : fe->pyr[left_idx];
   cp.ts_pitch = fe->pd.pitch[0];
   cp.and_ts_test = and_ts;
+  cp.cand = fe->cand[slot];
+  cp.cand_cnt = fe->cand_cnt[slot];
   return cp;
 }
 
@@ -777,7 +785,7 @@ static int submit_tracking(esvio_fe* fe, const WindowPlan& w, const DevEvents& e
   // LK path: selection is their only reader
   if (pub_this_frame) {
     CU(cudaStreamWaitEvent(sf, after_k1, 0));
-    launch_corner_flags(corner_params(fe, cur, 1), ev_left, fe->flags[slot], sf, &fe->launches);
+    launch_corner_flags(corner_params(fe, cur, 1, slot), ev_left, fe->flags[slot], sf, &fe->launches);
     prof_mark(fe, kMarkFlagsDone, sf);
     CU(cudaEventRecord(fe->f_done[slot], sf));
     fe->f_pending = slot;
@@ -795,7 +803,7 @@ static int submit_tracking(esvio_fe* fe, const WindowPlan& w, const DevEvents& e
   if (pub_this_frame) {
     if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s1, &fe->launches);
     CU(cudaStreamWaitEvent(s1, fe->f_done[slot], 0));
-    launch_select(fe->tp, B, ev_left, fe->flags[slot], slot, s1, &fe->launches);
+    launch_select(fe->tp, B, ev_left.n, fe->cand[slot], fe->cand_cnt[slot], slot, s1, &fe->launches);
   }
   prof_mark(fe, kMarkSelect, s1);
   CU(cudaEventRecord(fe->t1_done[slot], s1));
@@ -1654,7 +1662,7 @@ FE_API int esvio_fe_stage_corner_flags(esvio_fe* fe, const esvio_events* left, i
   if ((rc = stage_events(fe, 0, 0, left, &ev)) != ESVIO_FE_OK) return rc;
   if ((rc = staging_done(fe, 0)) != ESVIO_FE_OK) return rc;
   CU(cudaStreamWaitEvent(fe->stream_e, fe->c_done[0], 0));
-  launch_corner_flags(corner_params(fe, fe->cur_left, and_ts_test), ev, fe->flags[0],
+  launch_corner_flags(corner_params(fe, fe->cur_left, and_ts_test, 0), ev, fe->flags[0],
                       fe->stream_e, &fe->launches);
   CU(cudaGetLastError());
   if (ev.n > 0)
@@ -1785,8 +1793,8 @@ FE_API int esvio_fe_stage_select(esvio_fe* fe, const esvio_events* left, int32_t
     CU(cudaMemcpyAsync(B.ids, ids, sizeof(int) * n, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(B.cnt, track_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, s));
   }
-  launch_corner_flags(corner_params(fe, fe->cur_left, 1), ev, fe->flags[0], s, &fe->launches);
-  launch_select(fe->tp, B, ev, fe->flags[0], -1, s, &fe->launches);
+  launch_corner_flags(corner_params(fe, fe->cur_left, 1, 0), ev, fe->flags[0], s, &fe->launches);
+  launch_select(fe->tp, B, ev.n, fe->cand[0], fe->cand_cnt[0], -1, s, &fe->launches);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -1798,6 +1806,43 @@ FE_API int esvio_fe_stage_select(esvio_fe* fe, const esvio_events* left, int32_t
     CU(cudaMemcpyAsync(track_cnt_out, B.cnt, sizeof(int) * st.n_cur, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
   }
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_stage_set_tracks(esvio_fe* fe, double prev_time, int32_t next_id, int32_t n,
+                                     const float* pts, const int32_t* ids, const int32_t* track_cnt,
+                                     const float* un, int32_t n_r, const int32_t* ids_r,
+                                     const float* un_r) {
+  if (!fe || n < 0 || n > fe->cfg.max_cnt || n_r < 0 || n_r > fe->cfg.max_cnt) return ESVIO_FE_EINVAL;
+  if (n > 0 && (!pts || !ids || !track_cnt || !un)) return ESVIO_FE_EINVAL;
+  if (n_r > 0 && (!ids_r || !un_r)) return ESVIO_FE_EINVAL;
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "windows in flight", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  if (sync_all(fe) != ESVIO_FE_OK) return ESVIO_FE_ECUDA;
+  cudaStream_t s = fe->stream;
+  const TrackBuffers& B = fe->tb;
+  TrackState st;
+  CU(cudaMemcpyAsync(&st, B.st, sizeof(st), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  st.n_prev = st.n_cur = n;
+  st.n_right = n_r;
+  st.next_id = next_id;
+  st.n_prev_un = n;
+  st.n_prev_un_r = n_r;
+  CU(cudaMemcpyAsync(B.st, &st, sizeof(st), cudaMemcpyHostToDevice, s));
+  if (n > 0) {
+    CU(cudaMemcpyAsync(B.prev_pts, pts, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(B.ids, ids, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(B.cnt, track_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(B.prev_un_ids, ids, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(B.prev_un, un, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
+  }
+  if (n_r > 0) {
+    CU(cudaMemcpyAsync(B.prev_un_r_ids, ids_r, sizeof(int) * n_r, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(B.prev_un_r, un_r, sizeof(float2) * n_r, cudaMemcpyHostToDevice, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  fe->prev_time = prev_time;
   return ESVIO_FE_OK;
 }
 

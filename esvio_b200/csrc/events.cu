@@ -804,41 +804,66 @@ __device__ __forceinline__ bool arc_ring_valid(const double* ring) {
   return seg_len <= HI || (seg_len >= N - HI && seg_len <= N - LO);
 }
 
-__global__ void __launch_bounds__(128)
+// Besides the flag of every event the kernel leaves, per CTA of kCornerBlock consecutive
+// events, the flagged events' pixels compacted in stream order (cand[block * kCornerBlock + j],
+// x | y << 16) and their number: the selection kernel then walks a few thousand candidates
+// instead of re-reading the whole window.
+__global__ void __launch_bounds__(kCornerBlock)
 k_corner_flags(CornerParams P, DevEvents ev, uint8_t* __restrict__ flags) {
   PDL_PROLOGUE();
+  __shared__ int s_wc[kCornerBlock / 32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ev.n) return;
-  const Ev e = load_event(ev, i);
   uint8_t out = 0;
-  do {
-    if (e.x >= P.W || e.y >= P.H) break;
-    const size_t px = (size_t)e.x + (size_t)e.y * P.W;
-    if (P.and_ts_test && (double)P.ts[(size_t)e.y * P.ts_pitch + e.x] == P.ts_lk_threshold) break;
-    const double2 l = P.lat[px];
-    const double last_same = e.p ? l.y : l.x, last_opp = e.p ? l.x : l.y;
-    if (e.t > last_same + P.filter_threshold || last_opp > last_same) break;
-    const int border = P.min_dist + 1;
-    if (e.x < border || e.x >= P.W - border || e.y < border || e.y >= P.H - border) break;
-    const double* S = reinterpret_cast<const double*>(P.sae) + e.p;
-    double ring[20];
+  Ev e;
+  e.x = e.y = e.p = 0;
+  e.t = 0.0;
+  if (i < ev.n) {
+    e = load_event(ev, i);
+    do {
+      if (e.x >= P.W || e.y >= P.H) break;
+      const size_t px = (size_t)e.x + (size_t)e.y * P.W;
+      if (P.and_ts_test && (double)P.ts[(size_t)e.y * P.ts_pitch + e.x] == P.ts_lk_threshold) break;
+      const double2 l = P.lat[px];
+      const double last_same = e.p ? l.y : l.x, last_opp = e.p ? l.x : l.y;
+      if (e.t > last_same + P.filter_threshold || last_opp > last_same) break;
+      const int border = P.min_dist + 1;
+      if (e.x < border || e.x >= P.W - border || e.y < border || e.y >= P.H - border) break;
+      const double* S = reinterpret_cast<const double*>(P.sae) + e.p;
+      double ring[20];
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-      ring[k] = S[2 * ((size_t)(e.x + c_ring3[k][0]) + (size_t)(e.y + c_ring3[k][1]) * P.W)];
-    if (!arc_ring_valid<16, 4, 6>(ring)) break;
+      for (int k = 0; k < 16; ++k)
+        ring[k] = S[2 * ((size_t)(e.x + c_ring3[k][0]) + (size_t)(e.y + c_ring3[k][1]) * P.W)];
+      if (!arc_ring_valid<16, 4, 6>(ring)) break;
 #pragma unroll
-    for (int k = 0; k < 20; ++k)
-      ring[k] = S[2 * ((size_t)(e.x + c_ring4[k][0]) + (size_t)(e.y + c_ring4[k][1]) * P.W)];
-    if (!arc_ring_valid<20, 5, 8>(ring)) break;
-    out = 1;
-  } while (0);
-  flags[i] = out;
+      for (int k = 0; k < 20; ++k)
+        ring[k] = S[2 * ((size_t)(e.x + c_ring4[k][0]) + (size_t)(e.y + c_ring4[k][1]) * P.W)];
+      if (!arc_ring_valid<20, 5, 8>(ring)) break;
+      out = 1;
+    } while (0);
+    flags[i] = out;
+  }
+  if (P.cand == nullptr) return;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t m = __ballot_sync(0xffffffffu, out != 0);
+  if (lane == 0) s_wc[warp] = __popc(m);
+  __syncthreads();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kCornerBlock / 32; ++w) {
+    if (w < warp) off += s_wc[w];
+    total += s_wc[w];
+  }
+  if (out)
+    P.cand[(size_t)blockIdx.x * kCornerBlock + off + __popc(m & ((1u << lane) - 1u))] =
+        (uint32_t)e.x | ((uint32_t)e.y << 16);
+  if (threadIdx.x == 0) P.cand_cnt[blockIdx.x] = total;
 }
 
 void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* flags,
                          cudaStream_t s, int64_t* launches) {
   if (ev.n <= 0) return;
-  launch_pdl(k_corner_flags, dim3((ev.n + 127) / 128), dim3(128), 0, s, P, ev, flags);
+  launch_pdl(k_corner_flags, dim3((ev.n + kCornerBlock - 1) / kCornerBlock), dim3(kCornerBlock), 0, s, P, ev,
+             flags);
   ++*launches;
 }
 

@@ -205,6 +205,16 @@ __device__ __forceinline__ bool mask_test(const uint32_t* mask, int words, int x
 
 size_t select_smem_bytes(int W, int H) { return (size_t)H * ((W + 31) / 32) * sizeof(uint32_t); }
 
+#ifdef ESVIO_LK_CLOCKS  // scratch builds only: phase clocks of the last k_select launch
+__device__ long long g_sel_clk[16];
+#define SEL_CLK(i) do { if (threadIdx.x == 0) g_sel_clk[i] = clock64(); } while (0)
+extern "C" __attribute__((visibility("default"))) int esvio_dbg_select_clocks(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_sel_clk, sizeof(g_sel_clk));
+}
+#else
+#define SEL_CLK(i)
+#endif
+
 constexpr int kSelThreads = 1024;
 constexpr int kSelPerThread = 4;
 constexpr int kSelFast = 256;  // tracked points the bit-matrix path of Event_setMask handles
@@ -268,13 +278,14 @@ __device__ __forceinline__ void fill_disc_rows(uint32_t* mask, int words, int W,
 //      covers its rounded pixel.  "Covers" is evaluated pairwise for all pairs in parallel (bit
 //      matrix, <= 256 points), the greedy pass then only ANDs bit rows, and all surviving discs
 //      are rastered into the bit mask at once.  More than 256 points: the serial mask walk.
-//  (2) Event_FeaturesToTrack (:13-38): the left events are taken 4096 at a time in stream
-//      order; flagged events (Arc* corner on a live time-surface pixel) that are not yet
-//      masked are compacted, one warp then serves them first come, first served, and the walk
-//      stops as soon as MAX_CNT is reached (usually within the first steps).
+//  (2) Event_FeaturesToTrack (:13-38): k_corner_flags left the flagged events (Arc* corner on
+//      a live time-surface pixel) as one short list per 128 events, in stream order.  The
+//      lists of up to 1024 consecutive event blocks are gathered into shared memory (those
+//      already masked by a track are dropped on the way), one warp then serves them first
+//      come, first served, and the walk stops as soon as MAX_CNT is reached.
 __global__ void __launch_bounds__(kSelThreads)
-k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict__ flags,
-         int snap_slot) {
+k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict__ cand,
+         const int* __restrict__ cand_cnt, int snap_slot) {
   PDL_PROLOGUE();
   extern __shared__ uint32_t s_mask[];
   __shared__ int s_hw[kMaxDiscR + 1];
@@ -292,6 +303,7 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   const int W = P.W, H = P.H, words = (W + 31) / 32;
   const int n = st->n_cur;
+  SEL_CLK(0);
   for (int i = tid; i < H * words; i += blockDim.x) s_mask[i] = 0;
   if (tid == 0) {
     disc_half_widths(P.min_dist, s_hw);
@@ -311,6 +323,7 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
     s_order[rank] = tid;
   }
   __syncthreads();
+  SEL_CLK(1);
   if (n <= kSelFast) {
     // ---- (1) bit-matrix path
     if (tid < n) {
@@ -334,6 +347,7 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
       s_conf[b][aw] = bits;
     }
     __syncthreads();
+    SEL_CLK(2);
     if (warp == 0) {
       uint32_t kept_w = 0;  // lane w: survivors among order positions [32w, 32w+32)
       int kept = 0;
@@ -350,6 +364,7 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
       if (lane == 0) s_kept = kept;
     }
     __syncthreads();
+    SEL_CLK(3);
     if (tid < n && ((s_keptbits[tid >> 5] >> (tid & 31)) & 1u)) {
       // survivors keep their visiting order: position = survivors before me
       int pos = __popc(s_keptbits[tid >> 5] & ((1u << (tid & 31)) - 1u));
@@ -384,63 +399,57 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
     if (lane == 0) s_kept = kept;
   }
   __syncthreads();
+  SEL_CLK(4);
   const int kept = s_kept;
   const int want = P.max_cnt - kept;
   uint32_t* s_new = &s_conf[0][0];  // the bit matrix is done with: accepted corners, x | y << 16
 
   // ---- Event_FeaturesToTrack: first come, first served in stream order
-  if (want > 0) {
-    const int step = kSelThreads * kSelPerThread;
-    for (int base = 0; base < ev.n; base += step) {
-      const int i0 = base + tid * kSelPerThread;
-      uint32_t f4 = 0;
-      if (i0 + kSelPerThread <= ev.n) {
-        f4 = *reinterpret_cast<const uint32_t*>(flags + i0);
-      } else {
-        for (int k = 0; k < kSelPerThread; ++k)
-          if (i0 + k < ev.n) f4 |= (uint32_t)flags[i0 + k] << (8 * k);
-      }
-      uint32_t cand[kSelPerThread];
-      int nc = 0;
-      if (f4) {
-        for (int k = 0; k < kSelPerThread; ++k) {
-          if ((f4 >> (8 * k)) & 0xff) {
-            const Ev e = load_event(ev, i0 + k);
-            if (!mask_test(s_mask, words, e.x, e.y)) cand[nc++] = (uint32_t)e.x | ((uint32_t)e.y << 16);
-          }
-        }
-      }
-      if (!__syncthreads_or(nc)) continue;
-      // stable compaction of this step's candidates
-      int total = 0, pos = 0;
-      {
-        // exclusive scan of nc over the block
-        int incl = nc;
+  if (want > 0 && n_events > 0) {
+    constexpr uint32_t kNone = 0xffffffffu;
+    constexpr int kCap = kSelThreads * kSelPerThread;
+    const int n_blk = (n_events + kCornerBlock - 1) / kCornerBlock;
+    int b0 = 0;
+    while (b0 < n_blk) {
+      // thread t takes event block b0 + t: inclusive scan of the list lengths
+      const int blk = b0 + tid;
+      const bool real = blk < n_blk;
+      const int c = real ? __ldg(cand_cnt + blk) : 0;
+      int incl = c;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int o = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-          const int v = s_warp[lane];
-          int w = v;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, w, d);
-            if (lane >= d) w += o;
-          }
-          s_warp[lane] = w - v;
-          if (lane == 31) s_warp[32] = w;
-        }
-        __syncthreads();
-        pos = s_warp[warp] + incl - nc;
-        total = s_warp[32];
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
       }
-      for (int k = 0; k < nc; ++k) s_cand[pos + k] = cand[k];
+      if (lane == 31) s_warp[warp] = incl;
       __syncthreads();
       if (warp == 0) {
+        const int v = s_warp[lane];
+        int w = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, w, d);
+          if (lane >= d) w += o;
+        }
+        s_warp[lane] = w - v;
+      }
+      __syncthreads();
+      incl += s_warp[warp];
+      // the lists that fit the shared-memory buffer are a prefix of the blocks (a list holds at
+      // most kCornerBlock entries, so at least one always fits)
+      const bool fits = real && incl <= kCap;
+      const int n_fit = __syncthreads_count(fits);
+      if (fits) {
+        const uint32_t* src = cand + (size_t)blk * kCornerBlock;
+        for (int j = 0; j < c; ++j) {
+          const uint32_t xy = __ldg(src + j);
+          s_cand[incl - c + j] = mask_test(s_mask, words, xy & 0xffff, xy >> 16) ? kNone : xy;
+        }
+        if (tid == n_fit - 1) s_warp[32] = incl;
+      }
+      __syncthreads();
+      const int total = s_warp[32];
+      if (warp == 0 && total > 0) {
         // 32 candidates at a time: the lowest lane whose pixel is still free is the next corner
         // in stream order (everything before it is masked, and the mask only grows); its disc
         // is filled and the remaining lanes are tested again
@@ -449,10 +458,9 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
         const int my_k = lane - r;
         const int my_hw = (r <= 15 && lane <= 2 * r) ? s_hw[my_k < 0 ? -my_k : my_k] : -1;
         for (int c0 = 0; c0 < total && found < want; c0 += 32) {
-          const bool have = c0 + lane < total;
-          const uint32_t xy = have ? s_cand[c0 + lane] : 0u;
+          const uint32_t xy = c0 + lane < total ? s_cand[c0 + lane] : kNone;
           const int x = xy & 0xffff, y = xy >> 16;
-          uint32_t alive = __ballot_sync(0xffffffffu, have);
+          uint32_t alive = __ballot_sync(0xffffffffu, xy != kNone);
           while (found < want) {
             const bool free_px = ((alive >> lane) & 1u) && !mask_test(s_mask, words, x, y);
             const uint32_t fr = __ballot_sync(0xffffffffu, free_px);
@@ -470,9 +478,11 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
       }
       __syncthreads();
       if (s_found >= want) break;
+      b0 += n_fit;
     }
   }
   __syncthreads();
+  SEL_CLK(5);
   for (int i = tid; i < s_found; i += blockDim.x) {  // new points: ids from n_id++, track_cnt 1
     const uint32_t xy = s_new[i];
     B.cur_pts[kept + i] = make_float2((float)(xy & 0xffff), (float)(xy >> 16));
@@ -491,6 +501,7 @@ k_select(TrackParams P, TrackBuffers B, DevEvents ev, const uint8_t* __restrict_
     __syncthreads();
     snapshot_tracks(P, B, snap_slot, s_kept + s_found);
   }
+  SEL_CLK(6);
 }
 
 int select_configure(int W, int H) {
@@ -502,9 +513,10 @@ int select_configure(int W, int H) {
                               (int)bytes) == cudaSuccess ? 0 : -1;
 }
 
-void launch_select(const TrackParams& P, const TrackBuffers& B, const DevEvents& left,
-                   const uint8_t* flags, int snap_slot, cudaStream_t s, int64_t* launches) {
-  launch_pdl(k_select, dim3(1), dim3(kSelThreads), select_smem_bytes(P.W, P.H), s, P, B, left, flags, snap_slot);
+void launch_select(const TrackParams& P, const TrackBuffers& B, int n_events, const uint32_t* cand,
+                   const int* cand_cnt, int snap_slot, cudaStream_t s, int64_t* launches) {
+  launch_pdl(k_select, dim3(1), dim3(kSelThreads), select_smem_bytes(P.W, P.H), s, P, B, n_events, cand,
+             cand_cnt, snap_slot);
   ++*launches;
 }
 

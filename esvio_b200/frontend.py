@@ -444,6 +444,20 @@ class EventFrontEnd:
         k = n_out.value
         return po[:k], io[:k], co[:k], n_kept.value
 
+    def stage_set_tracks(self, prev_time, next_id, tracks):
+        """Teacher forcing: the tracker's carried state becomes `tracks` (a result dict of this
+        class or of the oracle: id, track_cnt, u, v, un_x, un_y, id_right, run_x, run_y)."""
+        n, nr = len(tracks["id"]), len(tracks["id_right"])
+        pts = np.ascontiguousarray(np.stack([tracks["u"], tracks["v"]], 1), np.float32)
+        un = np.ascontiguousarray(np.stack([tracks["un_x"], tracks["un_y"]], 1), np.float32)
+        unr = np.ascontiguousarray(np.stack([tracks["run_x"], tracks["run_y"]], 1), np.float32)
+        ids = np.ascontiguousarray(tracks["id"], np.int32)
+        cnt = np.ascontiguousarray(tracks["track_cnt"], np.int32)
+        idr = np.ascontiguousarray(tracks["id_right"], np.int32)
+        self._chk(_capi.lib().esvio_fe_stage_set_tracks(
+            self._h, float(prev_time), int(next_id), n, pts.ctypes.data, ids.ctypes.data,
+            cnt.ctypes.data, un.ctypes.data, nr, idr.ctypes.data, unr.ctypes.data), "stage_set_tracks")
+
     def stage_undistort(self, cam, uv):
         uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
         out = np.zeros_like(uv)

@@ -2,7 +2,12 @@
 handle_stereo_event -> feature clouds, all through the GPU tracker.
 
   python -m esvio_b200.replay [--workload stereo_davis346_1mevs] [--windows 30] [--npz rec.npz]
+                              [--config config/esvio_DSEC]
   python -m esvio_b200.replay --frames [--windows 40] [--npz frames.npz]
+
+`--config` takes a configuration set of the reference (a directory with es*io.yaml and the two
+event calibrations, or the yaml itself): resolution, MAX_CNT, MIN_DIST, FREQ, EQUALIZE, ... and
+the pinhole models come from it exactly as readParameters_event reads them (esvio_b200/config.py).
 
 `--npz` replays a recording with arrays lx, ly, lt, lp, rx, ry, rt, rp (time-ascending,
 seconds); without it the synthetic stream of the named workload is used.  `--frames` replays
@@ -18,6 +23,7 @@ import time
 
 import numpy as np
 
+from . import config as config_sets
 from . import node, synth
 
 
@@ -75,6 +81,8 @@ def main():
     ap.add_argument("--npz", default=None)
     ap.add_argument("--frequency", type=float, default=30.0, help="re-windowing rate (EventMessageEditor: 30)")
     ap.add_argument("--frames", action="store_true", help="replay stereo frames through trackImage")
+    ap.add_argument("--config", default=None,
+                    help="reference configuration set: directory with es*io.yaml, or the yaml")
     args = ap.parse_args()
     from . import frontend  # needs libesvio_fe.so and a B200: there is no CPU path
 
@@ -87,9 +95,18 @@ def main():
         right = tuple(z[k] for k in ("rx", "ry", "rt", "rp"))
     cfg = synth.default_config(w["width"], w["height"], max_cnt=w["max_cnt"], min_dist=w["min_dist"],
                                use_ransac=1)
+    freq, do_mc = w["freq"], False
+    if args.config:
+        import os
+        f = config_sets.find_config(args.config) if os.path.isdir(args.config) else args.config
+        cfg, nparams = config_sets.read_parameters_event(f)
+        if (cfg["width"], cfg["height"]) != (w["width"], w["height"]) and not args.npz:
+            raise SystemExit(f"--config is {cfg['width']}x{cfg['height']}, the synthetic workload "
+                             f"{args.workload} is {w['width']}x{w['height']}: pick a matching --workload")
+        freq, do_mc = nparams["freq"], bool(cfg["do_motion_correction"])
     cfg["max_events_per_window"] = max(1 << 16, int(2.5 * w["rate"] / args.frequency))
     ft = frontend.FeatureTracker(cfg)
-    nd = node.StereoEventNode(ft, w["freq"])
+    nd = node.StereoEventNode(ft, freq, do_motion_correction=do_mc)
     t0 = time.perf_counter()
     lm, rm = node.window_stream(left, args.frequency), node.window_stream(right, args.frequency)
     t1 = time.perf_counter()
@@ -97,7 +114,8 @@ def main():
     t2 = time.perf_counter()
     n_ev = sum(len(m) for m in lm) + sum(len(m) for m in rm)
     print(json.dumps({
-        "workload": args.workload, "messages": [len(lm), len(rm)], "events": n_ev,
+        "workload": args.workload, "config": args.config, "max_cnt": cfg["max_cnt"], "min_dist": cfg["min_dist"],
+        "freq": freq, "messages": [len(lm), len(rm)], "events": n_ev,
         "windows_tracked": nd.windows_tracked, "clouds_published": len(clouds),
         "rows_last_cloud": int(len(clouds[-1].rows)) if clouds else 0, "queue_overwrites": dropped,
         "restarts": nd.restarts, "windowing_s": t1 - t0, "tracking_s": t2 - t1,

@@ -298,6 +298,14 @@ int esvio_fe_kernel_launches(esvio_fe *fe, int64_t *count); /* kernels launched 
 /* plane: 0 sae[0], 1 sae[1], 2 sae_latest[0], 3 sae_latest[1]; dst = H*W doubles,
  * index x + y*W (event_detector.h:74-79) */
 int esvio_fe_get_sae(esvio_fe *fe, int32_t cam, int32_t plane, double *dst);
+/* Teacher forcing (parity tests): replace the tracker's carried state -- what trackEvent keeps
+ * from one call to the next (feature_tracker.cpp:585-590: prev_pts, ids, track_cnt,
+ * prev_un_pts_map, prev_un_right_pts_map, prev_time; :9 n_id) -- by the caller's, e.g. the
+ * reference's after the same window.  SAE state and images are left alone (they are exact).
+ * pts / un are n (x, y) pairs, un_r are n_r pairs keyed by ids_r. */
+int esvio_fe_stage_set_tracks(esvio_fe *fe, double prev_time, int32_t next_id, int32_t n,
+                              const float *pts, const int32_t *ids, const int32_t *track_cnt,
+                              const float *un, int32_t n_r, const int32_t *ids_r, const float *un_r);
 /* createSAE_* + SAEtoTimeSurface_* + pyramids only (feature_tracker.cpp:356-368) */
 int esvio_fe_stage_update(esvio_fe *fe, double t_ref, const esvio_events *left,
                           const esvio_events *right);

@@ -1521,6 +1521,9 @@ struct ora_tracker {
   double timers[6];
 };
 
+/* FeatureTracker::n_id (feature_tracker.cpp:9): the id the next new corner gets */
+ORA_API int ora_tracker_next_id(const ora_tracker *t) { return t->next_id; }
+
 ORA_API ora_tracker *ora_tracker_create(const ora_config *cfg) {
   ora_tracker *t = (ora_tracker *)calloc(1, sizeof(ora_tracker));
   t->cfg = *cfg;

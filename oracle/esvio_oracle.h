@@ -207,6 +207,7 @@ const uint8_t *ora_tracker_time_surface(const ora_tracker *t, int cam);
 const uint8_t *ora_tracker_lk_image(const ora_tracker *t, int cam);
 /* stage timers (seconds, accumulated): 0 sae,1 ts,2 temporal lk,3 ransac+mask+select,4 stereo lk,5 other */
 void ora_tracker_timers(const ora_tracker *t, double *out6);
+int ora_tracker_next_id(const ora_tracker *t); /* FeatureTracker::n_id */
 
 #ifdef __cplusplus
 }

@@ -173,6 +173,8 @@ def lib():
         L.ora_tracker_lk_image.restype = C.POINTER(C.c_uint8)
         L.ora_tracker_lk_image.argtypes = [C.c_void_p, C.c_int]
         L.ora_tracker_timers.argtypes = [C.c_void_p, C.c_void_p]
+        L.ora_tracker_next_id.restype = C.c_int
+        L.ora_tracker_next_id.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -561,6 +563,10 @@ class OracleTracker:
     def lk_image(self, cam):
         p = lib().ora_tracker_lk_image(self._h, cam)
         return np.ctypeslib.as_array(p, shape=(self.H, self.W)).copy()
+
+    def next_id(self):
+        """FeatureTracker::n_id (feature_tracker.cpp:9)."""
+        return int(lib().ora_tracker_next_id(self._h))
 
     def timers(self):
         out = np.zeros(6, np.float64)

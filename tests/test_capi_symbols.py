@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(capi):
     lib = C.CDLL(capi.LIB_PATH)
     for name in _declared_functions():
         assert hasattr(lib, name), f"{name} missing from libesvio_fe.so"
-    assert capi.lib().esvio_fe_abi_version() == 2
+    assert capi.lib().esvio_fe_abi_version() == 3
 
 
 def test_strerror_and_default_config(capi):

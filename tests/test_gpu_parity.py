@@ -13,8 +13,7 @@ from esvio_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-LK_TOL = 1e-3
-LK_TOL_MAX = 2e-2
+LK_TOL = 1e-3   # px against cv2 on identical inputs, every point (observed max: 2e-4)
 
 
 @pytest.fixture(scope="module")
@@ -156,11 +155,9 @@ def test_lk_matches_cv2_golden(fe_mod, ora, golden_lk, case):
 
     def cmp(got, st, ref, st_ref, what):
         st, st_ref = st.astype(bool), st_ref.astype(bool)
-        assert (st != st_ref).sum() <= max(1, len(st) // 50), f"{what}: status"
-        both = st & st_ref
-        d = np.abs(got[both] - ref[both]).max(axis=1)
-        assert (d > LK_TOL).sum() <= max(1, both.sum() // 50), f"{what}: {np.sort(d)[-5:]}"
-        assert d.max() <= LK_TOL_MAX, f"{what}: max {d.max()}"
+        assert np.array_equal(st, st_ref), f"{what}: {(st != st_ref).sum()} status flags differ"
+        d = np.abs(got[st] - ref[st]).max(axis=1)
+        assert d.max() <= LK_TOL, f"{what}: {np.sort(d)[-5:]}"
 
     fwd, st = fe.stage_lk(a, b, pts, None, 3)
     cmp(fwd, st, g[f"{case}_fwd"], g[f"{case}_st_f"], "fwd")
@@ -174,11 +171,17 @@ def test_lk_matches_cv2_golden(fe_mod, ora, golden_lk, case):
     fe.close()
 
 
-def test_select_parity(fe_mod, ora):
+# (W, H, rate, min_dist, max_cnt): config/esvio + esio (150 / 10), esvio_DSEC (100 / 30),
+# esvio_ecmd (200 / 20), esio_DSEC (300 / 10), and 20 / 30 at 346x260.  min_dist
+# > 15 takes the kernel's other disc-fill path, max_cnt > 256 its serial mask walk.
+@pytest.mark.parametrize("W,H,rate,min_dist,max_cnt", [
+    (346, 260, 1.0e6, 10, 150), (346, 260, 1.0e6, 20, 150), (346, 260, 1.0e6, 30, 100),
+    (640, 480, 5.0e6, 10, 150), (640, 480, 5.0e6, 30, 100), (640, 480, 5.0e6, 20, 200),
+    (640, 480, 5.0e6, 10, 300), (640, 480, 2.0e7, 10, 200)])
+def test_select_parity(fe_mod, ora, W, H, rate, min_dist, max_cnt):
     """Event_setMask + Event_FeaturesToTrack + id assignment, exact."""
-    W, H = 346, 260
-    fe, cfg = _mk(fe_mod, W, H)
-    s = synth.StereoEventStream(W, H, 1.0e6)
+    fe, cfg = _mk(fe_mod, W, H, min_dist=min_dist, max_cnt=max_cnt)
+    s = synth.StereoEventStream(W, H, rate)
     sae = ora.Sae(W, H)
     rng = np.random.default_rng(3)
     for k in range(4):
@@ -186,7 +189,7 @@ def test_select_parity(fe_mod, ora):
         fe.stage_update(t_ref, L, R)
         sae.update(*L)
         ts = sae.time_surface(t_ref)
-        n = [0, 40, 120, 150][k]
+        n = [0, max_cnt // 4, (4 * max_cnt) // 5, max_cnt][k]
         pts = np.stack([rng.uniform(1, W - 2, n), rng.uniform(1, H - 2, n)], 1).astype(np.float32)
         if n:
             pts[: n // 4] = pts[n // 4: 2 * (n // 4)] + 3.0  # force min-distance conflicts
@@ -196,6 +199,8 @@ def test_select_parity(fe_mod, ora):
         kp, ki, kc, mask = ora.set_mask(W, H, cfg["min_dist"], pts, ids, cnt)
         new, _ = sae.features_to_track(*L, cfg["max_cnt"] - len(ki), cfg["min_dist"], mask, ts)
         po, io, co, n_kept = fe.stage_select(L, pts, ids, cnt)
+        if k == 0:
+            assert len(new) > 0.5 * max_cnt   # the comparison sees a real selection
         assert n_kept == len(ki)
         assert np.array_equal(io[:n_kept], ki) and np.array_equal(co[:n_kept], kc)
         assert np.array_equal(po[:n_kept], kp)
@@ -853,3 +858,74 @@ def test_track_image_pipeline_equals_sync(fe_mod):
     assert len(sync[-1]["id"]) > 30
     a.close()
     b.close()
+
+
+# ---- parity over the whole run: every window, restarted from the reference's state ----
+# (name, W, H, rate, windows, pub_every, config overrides).  The first two are BASELINE
+# configs[1] and configs[2] over the 90 windows (3 s) SURVEY.md 8d times; then the shipped
+# parameter sets (config/esvio_DSEC 100 / 30, esvio_ecmd 200 / 20, esio_DSEC
+# 300 / 10 with EQUALIZE) and the event rates of configs[4] and configs[3].
+TEACHER_CASES = [
+    ("davis346_1mevs", 346, 260, 1.0e6, 90, 2, {}),
+    ("vga_5mevs", 640, 480, 5.0e6, 90, 3, {}),
+    ("vga_5mevs_dsec_100_30", 640, 480, 5.0e6, 24, 3, dict(max_cnt=100, min_dist=30)),
+    ("vga_5mevs_ecmd_200_20", 640, 480, 5.0e6, 24, 3, dict(max_cnt=200, min_dist=20)),
+    ("vga_5mevs_esio_dsec_300_10_equalize", 640, 480, 5.0e6, 16, 2, dict(max_cnt=300, min_dist=10, equalize=1)),
+    ("vga_10mevs", 640, 480, 1.0e7, 18, 3, {}),
+    ("vga_20mevs_burst_200", 640, 480, 2.0e7, 12, 3, dict(max_cnt=200)),
+]
+
+
+@pytest.mark.parametrize("name,W,H,rate,n_windows,pub_every,over", TEACHER_CASES,
+                         ids=[c[0] for c in TEACHER_CASES])
+def test_teacher_forced_every_window(fe_mod, ora, name, W, H, rate, n_windows, pub_every, over):
+    """FeatureTracker::trackEvent, one window at a time, over the WHOLE run: before every
+    window the CUDA tracker's carried state (prev_pts, ids, track_cnt, velocity maps, n_id,
+    prev_time: feature_tracker.cpp:585-590) is replaced by the reference's after the window
+    before, then both run the window and every output is compared.  Free-running trackers
+    drift apart once one forward-backward test flips (float-sum order inside LK, then the greedy
+    selection hands ids to other corners); restarted from the same state every window has to
+    agree: ids and track counts identical, (u, v) of both cameras within 1e-3 px, undistorted
+    points and velocities within float rounding of that.  The reference is the oracle with
+    real OpenCV (cv2) LK / findFundamentalMat / CLAHE where cv2 is importable."""
+    cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=int(rate / 30) + 64, **over)
+    fe = fe_mod.EventFrontEnd(cfg)
+    ot = ora.OracleTracker(cfg, use_cv2=True, cv2_threads=8)
+    s = synth.StereoEventStream(W, H, rate)
+    fx = cfg["cam"][0]["fx"]
+    prev, prev_time, next_id = None, 0.0, 0
+    max_d, max_dr, n_feat, n_right, bad = 0.0, 0.0, 0, 0, []
+    for k in range(n_windows):
+        L, R, t_ref = s.stereo_window(k)
+        pub = k % pub_every == 0
+        if prev is not None:
+            fe.stage_set_tracks(prev_time, next_id, prev)
+        g = fe.track(t_ref, L, R, pub)
+        o = ot.track(t_ref, L, R, pub)
+        prev, prev_time, next_id = o, t_ref, ot.next_id()
+        same = (np.array_equal(g["id"], o["id"]) and np.array_equal(g["track_cnt"], o["track_cnt"])
+                and np.array_equal(g["id_right"], o["id_right"]))
+        if not same:
+            bad.append((k, len(g["id"]), len(o["id"]), len(g["id_right"]), len(o["id_right"])))
+            continue
+        for key in ("n_after_temporal", "n_after_ransac", "n_after_mask", "n_new"):
+            assert g["stats"][key] == o["stats"][key], (k, key)
+        if len(o["id"]):
+            d = max(np.abs(g["u"] - o["u"]).max(), np.abs(g["v"] - o["v"]).max())
+            max_d = max(max_d, float(d))
+            assert np.abs(g["un_x"] - o["un_x"]).max() <= 2e-3 / fx + 1e-6, k
+            assert np.abs(g["un_y"] - o["un_y"]).max() <= 2e-3 / fx + 1e-6, k
+            # velocity = difference of undistorted points / dt (33 ms)
+            assert np.abs(g["vx"] - o["vx"]).max() <= 4e-3 / fx * 31 + 1e-4, k
+            assert np.abs(g["vy"] - o["vy"]).max() <= 4e-3 / fx * 31 + 1e-4, k
+            n_feat += len(o["id"])
+        if len(o["id_right"]):
+            dr = max(np.abs(g["ru"] - o["ru"]).max(), np.abs(g["rv"] - o["rv"]).max())
+            max_dr = max(max_dr, float(dr))
+            n_right += len(o["id_right"])
+    print(f"teacher-forced {name}: {n_windows} windows, {n_feat} left / {n_right} right features compared, "
+          f"max |d(u,v)| left {max_d:.2e} px right {max_dr:.2e} px, windows with different id sets: {bad}")
+    assert n_feat > 20 * n_windows and n_right > 10 * n_windows
+    assert not bad, bad
+    assert max_d <= 1e-3 and max_dr <= 1e-3, (max_d, max_dr)
+    fe.close()
