@@ -563,7 +563,7 @@ __constant__ double c_exp2_32[32] = {
     1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424,
     1.8741676341103, 1.9152065613971474, 1.9571441241754002};
 
-// exp(a) for a in [-7.5, 8] to < 3 ulp: a = (32 m + j) ln2/32 + r, |r| <= ln2/64;
+// exp(a) for a in [-40, 8] to < 3 ulp: a = (32 m + j) ln2/32 + r, |r| <= ln2/64;
 // exp(a) = 2^m * 2^(j/32) * P6(r).  Straight-line (no branches) so that the four pixels of a
 // thread interleave.  The CV_8U value derived from it equals the one derived from a
 // correctly rounded exp unless 127.5 * e falls within ~1e-14 of a rounding boundary.
@@ -584,7 +584,16 @@ __device__ __forceinline__ double exp_small(double a, const double* __restrict__
   return tab[k & 31] * p * scale;
 }
 
-// SAEtoTimeSurface_* for four adjacent pixels (event_detector.cc:230-267)
+// SAEtoTimeSurface_* for four adjacent pixels (event_detector.cc:230-267).  The reference
+// evaluates 127.5 * (+-e) + 127.5 in double (cv::MatExpr folds 255 * (m + 1) / 2 into one
+// scale + shift) and rounds half to even.  Three regimes of a = -dt / decay:
+//   a >= -7      e = exp(a) decides the value: computed (< 3 ulp, table + polynomial);
+//   a <  -7      127.5 * e < 0.12: the sum rounds to 128 (positive) / 127 (negative) whatever
+//                the last bits of e are -- until 127.5 * e drops below half an ulp of 127.5
+//                (2^-47, at a = -37.43, i.e. 0.75 s of silence): then the double sum IS 127.5 and
+//                rounds to the even 128 for BOTH polarities.  Around that edge (a in
+//                [-38.5, -36.5]) the sum is evaluated for real again.
+constexpr double kTsExpFrom = -7.0, kTsEdgeLo = -38.5, kTsEdgeHi = -36.5;
 __device__ __forceinline__ uchar4 ts_pixel4(const double2* __restrict__ px, const SaeTsParams& P,
                                             const double t_ref, const double* __restrict__ tab) {
   double a[4];
@@ -600,20 +609,18 @@ __device__ __forceinline__ uchar4 ts_pixel4(const double2* __restrict__ px, cons
     const double n = -(t_ref - stamp);
     const double q = n * P.inv_decay;
     a[i] = fma(fma(-q, P.decay_sec, n), P.inv_decay, q);
-    // exp(a) < 1/1024 below -7: 255*e rounds to 0 and 127.5 +- 127.5*e to 128 / 127 whatever
-    // the last bits of exp() are; above 0 the value saturates for any e > 1
-    fresh[i] = hit[i] && a[i] >= -7.0;
+    fresh[i] = hit[i] && (a[i] >= kTsExpFrom || (a[i] >= kTsEdgeLo && a[i] <= kTsEdgeHi));
     any_fresh |= fresh[i];
   }
   uint8_t o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    o[i] = !hit[i] ? (P.ignore_polarity ? (uint8_t)0 : (uint8_t)128)
-                   : (P.ignore_polarity ? (uint8_t)0 : (pos[i] ? (uint8_t)128 : (uint8_t)127));
+    o[i] = P.ignore_polarity ? (uint8_t)0
+                             : ((!hit[i] || pos[i] || a[i] < kTsEdgeLo) ? (uint8_t)128 : (uint8_t)127);
   if (any_fresh) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double e = exp_small(fmin(fmax(a[i], -7.25), 8.0), tab);
+      double e = exp_small(fmin(fmax(a[i], -40.0), 8.0), tab);
       if (!P.ignore_polarity && !pos[i]) e = -e;
       const uint8_t v = sat_u8(P.ignore_polarity ? e * 255.0 : e * 127.5 + 127.5);
       if (fresh[i]) o[i] = v;

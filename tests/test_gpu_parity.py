@@ -124,6 +124,31 @@ def test_sae_edge_cases(fe_mod, ora):
     fe.close()
 
 
+def test_time_surface_of_long_silent_pixels(fe_mod, ora):
+    """SAEtoTimeSurface_* (event_detector.cc:230-267) long after the last event.  The reference's
+    double arithmetic gives 127.5 -+ 127.5 e: 127 for a negative pixel while 127.5 e still
+    registers, and exactly 127.5 -> 128 (round half to even) once it drops below half an ulp,
+    0.7485 s after the event at decay_ms = 20.  Found by the every-window test: from window 23 of
+    a run on, hundreds of pixels were one grey level off."""
+    W, H = 346, 260
+    fe, _ = _mk(fe_mod, W, H)
+    sae = ora.Sae(W, H)
+    s = synth.StereoEventStream(W, H, 1.0e6)
+    empty = (np.zeros(0, np.uint16), np.zeros(0, np.uint16), np.zeros(0), np.zeros(0, np.uint8))
+    L, R, t_ref = s.stereo_window(0)
+    fe.stage_update(t_ref, L, R)
+    sae.update(*L)
+    n_neg_flip = 0
+    for dt in (0.0, 0.1, 0.139, 0.141, 0.5, 0.70, 0.72, 0.73, 0.74, 0.745, 0.7485, 0.75, 0.755, 0.76,
+               0.78, 0.8, 1.0, 5.0, 100.0):
+        fe.stage_update(t_ref + dt, empty, empty)
+        got, ref = fe.time_surface(0), sae.time_surface(t_ref + dt)
+        assert np.array_equal(got, ref), (dt, int((got != ref).sum()))
+        n_neg_flip += int(((ref == 127).sum() > 0))
+    assert n_neg_flip >= 8 and (ref != 127).all()   # both regimes were seen
+    fe.close()
+
+
 @pytest.mark.parametrize("W,H,rate", [(346, 260, 1.0e6), (640, 480, 5.0e6)])
 def test_corner_flags_parity(fe_mod, ora, W, H, rate):
     fe, cfg = _mk(fe_mod, W, H)
@@ -199,14 +224,14 @@ def test_select_parity(fe_mod, ora, W, H, rate, min_dist, max_cnt):
         kp, ki, kc, mask = ora.set_mask(W, H, cfg["min_dist"], pts, ids, cnt)
         new, _ = sae.features_to_track(*L, cfg["max_cnt"] - len(ki), cfg["min_dist"], mask, ts)
         po, io, co, n_kept = fe.stage_select(L, pts, ids, cnt)
-        if k == 0:
-            assert len(new) > 0.5 * max_cnt   # the comparison sees a real selection
+        n_new_total = (n_new_total if k else 0) + len(new)
         assert n_kept == len(ki)
         assert np.array_equal(io[:n_kept], ki) and np.array_equal(co[:n_kept], kc)
         assert np.array_equal(po[:n_kept], kp)
         assert len(po) - n_kept == len(new), (len(po) - n_kept, len(new))
         assert np.array_equal(po[n_kept:], new)
         assert (co[n_kept:] == 1).all()
+    assert n_new_total >= 20   # the comparison saw real selections
     fe.close()
 
 
@@ -883,18 +908,38 @@ def test_teacher_forced_every_window(fe_mod, ora, name, W, H, rate, n_windows, p
     window the CUDA tracker's carried state (prev_pts, ids, track_cnt, velocity maps, n_id,
     prev_time: feature_tracker.cpp:585-590) is replaced by the reference's after the window
     before, then both run the window and every output is compared.  Free-running trackers
-    drift apart once one forward-backward test flips (float-sum order inside LK, then the greedy
-    selection hands ids to other corners); restarted from the same state every window has to
-    agree: ids and track counts identical, (u, v) of both cameras within 1e-3 px, undistorted
-    points and velocities within float rounding of that.  The reference is the oracle with
-    real OpenCV (cv2) LK / findFundamentalMat / CLAHE where cv2 is importable."""
+    drift apart once one forward-backward test flips; restarted from the same state, every
+    window is one LK call away from the reference.  The reference is the oracle with real
+    OpenCV (cv2) LK / findFundamentalMat / CLAHE.
+
+    What can be demanded is bounded by OpenCV itself: LK sums 441 float products per iteration
+    in an order that depends on the build, and on these time surfaces two CPU builds of the
+    same algorithm (cv2's SIMD path and the oracle's scalar port, scratch/lk_ref_vs_ref.py)
+    already differ by 1e-6 px median, 7e-3 px at the 99.9th percentile and 0.2 px worst case
+    over 43 000 point-calls.  The kernel (exact integer sums) sits in the same cloud, and two
+    steps of trackEvent turn such a difference into a different DISCRETE outcome: a track on
+    the other side of the 0.5 px forward-backward threshold (then, on a publish window,
+    F-RANSAC draws its samples from a different point count), or a kept track whose
+    coordinate rounds to the neighbouring pixel (x.4999 / x.5001), which shifts its mask disc
+    and lets the greedy corner selection pick other corners.  Bars per run:
+      * >= 95 % of the windows agree in everything discrete: ids, track counts, right ids, the
+        positions of the new corners, n_after_temporal / ransac / mask / new (observed on B200:
+        90 of 90 windows at 640x480 @ 5 Mev/s, 87 of 90 at 346x260 @ 1 Mev/s, all windows of the
+        other five configurations);
+      * in every window the tracks carried over from the window before (track_cnt >= 2) differ
+        by at most 2 ids before F-RANSAC (n_after_temporal);
+      * LK accuracy over ALL windows, id-matched tracked points (track_cnt >= 2, both cameras):
+        median <= 1e-5 px, 99 % <= 1e-3 px, worst point <= 0.1 px (the north-star bar is
+        0.5 px), RMSE <= 2e-3 px (observed: 99 % 3e-5 .. 1e-4 px, worst 3.6e-2 px, RMSE
+        <= 3.5e-4 px); undistorted points follow (u, v)."""
     cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=int(rate / 30) + 64, **over)
     fe = fe_mod.EventFrontEnd(cfg)
     ot = ora.OracleTracker(cfg, use_cv2=True, cv2_threads=8)
     s = synth.StereoEventStream(W, H, rate)
-    fx = cfg["cam"][0]["fx"]
+    fx = min(cfg["cam"][0]["fx"], cfg["cam"][1]["fx"])
     prev, prev_time, next_id = None, 0.0, 0
-    max_d, max_dr, n_feat, n_right, bad = 0.0, 0.0, 0, 0, []
+    d_px, d_un, bad = [], [], []
+    n_feat = n_right = 0
     for k in range(n_windows):
         L, R, t_ref = s.stereo_window(k)
         pub = k % pub_every == 0
@@ -903,29 +948,46 @@ def test_teacher_forced_every_window(fe_mod, ora, name, W, H, rate, n_windows, p
         g = fe.track(t_ref, L, R, pub)
         o = ot.track(t_ref, L, R, pub)
         prev, prev_time, next_id = o, t_ref, ot.next_id()
+        new_g, new_o = g["track_cnt"] == 1, o["track_cnt"] == 1
         same = (np.array_equal(g["id"], o["id"]) and np.array_equal(g["track_cnt"], o["track_cnt"])
-                and np.array_equal(g["id_right"], o["id_right"]))
-        if not same:
-            bad.append((k, len(g["id"]), len(o["id"]), len(g["id_right"]), len(o["id_right"])))
-            continue
-        for key in ("n_after_temporal", "n_after_ransac", "n_after_mask", "n_new"):
-            assert g["stats"][key] == o["stats"][key], (k, key)
-        if len(o["id"]):
-            d = max(np.abs(g["u"] - o["u"]).max(), np.abs(g["v"] - o["v"]).max())
-            max_d = max(max_d, float(d))
-            assert np.abs(g["un_x"] - o["un_x"]).max() <= 2e-3 / fx + 1e-6, k
-            assert np.abs(g["un_y"] - o["un_y"]).max() <= 2e-3 / fx + 1e-6, k
-            # velocity = difference of undistorted points / dt (33 ms)
-            assert np.abs(g["vx"] - o["vx"]).max() <= 4e-3 / fx * 31 + 1e-4, k
-            assert np.abs(g["vy"] - o["vy"]).max() <= 4e-3 / fx * 31 + 1e-4, k
-            n_feat += len(o["id"])
-        if len(o["id_right"]):
-            dr = max(np.abs(g["ru"] - o["ru"]).max(), np.abs(g["rv"] - o["rv"]).max())
-            max_dr = max(max_dr, float(dr))
-            n_right += len(o["id_right"])
-    print(f"teacher-forced {name}: {n_windows} windows, {n_feat} left / {n_right} right features compared, "
-          f"max |d(u,v)| left {max_d:.2e} px right {max_dr:.2e} px, windows with different id sets: {bad}")
-    assert n_feat > 20 * n_windows and n_right > 10 * n_windows
-    assert not bad, bad
-    assert max_d <= 1e-3 and max_dr <= 1e-3, (max_d, max_dr)
+                and np.array_equal(g["id_right"], o["id_right"])
+                and np.array_equal(g["u"][new_g], o["u"][new_o]) and np.array_equal(g["v"][new_g], o["v"][new_o]))
+        if same:
+            for key in ("n_after_temporal", "n_after_ransac", "n_after_mask", "n_new"):
+                assert g["stats"][key] == o["stats"][key], (k, key)
+        else:
+            dn = abs(g["stats"]["n_after_temporal"] - o["stats"]["n_after_temporal"])
+            bad.append((k, int(pub), dn, len(np.setxor1d(g["id"], o["id"])),
+                        len(np.setxor1d(g["id_right"], o["id_right"]))))
+            assert dn <= 2, (k, dn)
+        # LK accuracy: tracks carried over from the window before, matched by id
+        old_g, old_o = g["id"][~new_g], o["id"][~new_o]
+        _, ia, ib = np.intersect1d(old_g, old_o, return_indices=True)
+        dl = np.maximum(np.abs(g["u"][~new_g][ia] - o["u"][~new_o][ib]), np.abs(g["v"][~new_g][ia] - o["v"][~new_o][ib]))
+        d_px.append(dl)
+        d_un.append(np.maximum(np.abs(g["un_x"][~new_g][ia] - o["un_x"][~new_o][ib]),
+                               np.abs(g["un_y"][~new_g][ia] - o["un_y"][~new_o][ib])))
+        # right points of the ids whose left points agree (a new corner on another pixel is
+        # another feature under the same id)
+        pos_g = dict(zip(g["id"].tolist(), zip(g["u"].tolist(), g["v"].tolist())))
+        pos_o = dict(zip(o["id"].tolist(), zip(o["u"].tolist(), o["v"].tolist())))
+        _, ra, rb = np.intersect1d(g["id_right"], o["id_right"], return_indices=True)
+        keep = np.array([max(abs(pos_g[i][0] - pos_o[i][0]), abs(pos_g[i][1] - pos_o[i][1])) <= 1e-2
+                         for i in g["id_right"][ra].tolist()], bool) if len(ra) else np.zeros(0, bool)
+        ra, rb = ra[keep], rb[keep]
+        d_px.append(np.maximum(np.abs(g["ru"][ra] - o["ru"][rb]), np.abs(g["rv"][ra] - o["rv"][rb])))
+        d_un.append(np.maximum(np.abs(g["run_x"][ra] - o["run_x"][rb]), np.abs(g["run_y"][ra] - o["run_y"][rb])))
+        n_feat += len(ia)
+        n_right += len(ra)
+    d_px, d_un = np.concatenate(d_px), np.concatenate(d_un)
+    med, q99, far = np.median(d_px), np.quantile(d_px, 0.99), float((d_px > 0.5).mean())
+    rmse = float(np.sqrt((d_px.astype(np.float64) ** 2).mean()))
+    print(f"teacher-forced {name}: {n_windows} windows, {n_feat} left / {n_right} right tracked points; |d(u,v)| median "
+          f"{med:.1e} 99 % {q99:.1e} max {d_px.max():.1e} px, beyond 0.5 px {far:.1e}, rmse {rmse:.1e} px; windows "
+          f"with a different discrete outcome (window, pub, d n_after_temporal, left ids, right ids): {bad}")
+    assert n_feat > 15 * n_windows and n_right > 10 * n_windows
+    assert len(bad) <= max(1, 0.05 * n_windows), bad
+    assert med <= 1e-5 and q99 <= 1e-3 and d_px.max() <= 0.1 and far == 0.0 and rmse <= 2e-3, (med, q99, d_px.max(), rmse)
+    # undistorted points follow (u, v) through a smooth map (|Jacobian| <= 3 / fx here)
+    assert (d_un <= 3.0 * np.maximum(d_px, 1e-4) / fx).all()
     fe.close()
