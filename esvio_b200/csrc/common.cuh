@@ -176,6 +176,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
       "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of one box (no shared memory, no barrier): the tile a CTA launched later will load
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -278,6 +285,7 @@ struct SaeTsParams {
   const uint16_t* bk[kMaxCams];
   uint8_t* ts[kMaxCams];      // level-0 images
   int ts_pitch;
+  int prefetch_dist;          // CTAs ahead whose tile state is prefetched into L2 (0 = off)
 };
 void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
                           const CUtensorMap& map_lat, cudaStream_t s, int64_t* launches);

@@ -540,6 +540,7 @@ void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const Dev
 // TMA store.
 constexpr int kSaeThreads = 32 * kFine;
 constexpr int kSaeAhead = 4;  // 32-event steps loaded per round trip to L2/HBM
+constexpr int kSaePrefetchDist = 1036;  // CTAs: half a wave ahead (sweep: profiles/r2_k1_prefetch.txt)
 
 // convertTo(CV_8U) of a double: cvRound (half to even) then saturate
 __device__ __forceinline__ uint8_t sat_u8(double v) {
@@ -655,6 +656,22 @@ k_sae_update_ts(const __grid_constant__ SaeMaps maps, const __grid_constant__ Sa
     tma_load_3d(s_sae, &maps.sae, &s_bar, 2 * x0, y0, cam);
     if (dirty) tma_load_3d(s_lat, &maps.lat, &s_bar, 2 * x0, y0, cam);
   }
+  // The grid is several waves deep and CTAs start in blockIdx order: pull the state of the tile
+  // a CTA `prefetch_dist` launches later will want into L2 now, so that its TMA load is an L2
+  // hit instead of a trip to HBM (the launch is latency-bound per CTA: load -> replay -> store).
+  if (P.prefetch_dist > 0 && threadIdx.x == 32) {
+    const int tiles_y = gridDim.y;
+    long long lin = (long long)blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)tiles_y * blockIdx.z) +
+                    P.prefetch_dist;
+    const int fx = (int)(lin % gridDim.x);
+    lin /= gridDim.x;
+    const int fy = (int)(lin % tiles_y), fc = (int)(lin / tiles_y);
+    if (fc < P.n_cams) {
+      const uint32_t* fbs = P.bin_start + fc * (P.n_tiles * kFine + 2) + (fy * P.tiles_x + fx) * kFine;
+      tma_prefetch_3d(&maps.sae, 2 * fx * kTileW, fy * kTileH, fc);
+      if (fbs[kFine] > fbs[0]) tma_prefetch_3d(&maps.lat, 2 * fx * kTileW, fy * kTileH, fc);
+    }
+  }
   // the first events of the run travel while the tile loads
   const double* __restrict__ bt = P.bt[cam];
   const uint16_t* __restrict__ bk = P.bk[cam];
@@ -741,8 +758,14 @@ k_sae_update_ts(const __grid_constant__ SaeMaps maps, const __grid_constant__ Sa
   }
 }
 
-void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
+void launch_sae_update_ts(const SaeTsParams& P_in, const CUtensorMap& map_sae,
                           const CUtensorMap& map_lat, cudaStream_t s, int64_t* launches) {
+  SaeTsParams P = P_in;
+  {
+    // half a wave of CTAs ahead (148 SMs x ~14 resident CTAs); experiments: ESVIO_K1_PREFETCH=<n>
+    static const int dist = getenv("ESVIO_K1_PREFETCH") ? atoi(getenv("ESVIO_K1_PREFETCH")) : kSaePrefetchDist;
+    P.prefetch_dist = dist;
+  }
   SaeMaps maps;
   maps.sae = map_sae;
   maps.lat = map_lat;
