@@ -55,6 +55,28 @@ def env_int(k, d):
     return int(os.environ.get(k, d))
 
 
+# stdout must carry exactly ONE JSON line, but NCCL (with NCCL_DEBUG set) and others write to
+# fd 1 whenever a communicator comes up: fd 1 points at stderr for the whole run, and the line
+# goes to the saved descriptor.
+_STDOUT_FD = None
+
+
+def claim_stdout():
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    sys.stdout.flush()
+    if _STDOUT_FD is None:
+        print(line)
+    else:
+        os.write(_STDOUT_FD, (line + "\n").encode())
+
+
 def default_workload(world):
     return WORKLOAD_N1 if world == 1 else WORKLOAD_NX
 
@@ -267,7 +289,7 @@ def main_reference(args):
                                "e2e": {"value": rv, "unit": UNIT},
                                "ms_per_step": 1e3 * rsec / max(args.steps, 1),
                                "stage_seconds": rtimers}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------
@@ -279,66 +301,29 @@ class _CudaArray:
                                          "data": (ptr, False), "version": 3, "strides": None}
 
 
-def init_nccl(local, p2p_peer=None):
-    """NCCL prints its version banner to stdout when the first communicator comes up; stdout
-    must carry exactly one JSON line, so fd 1 points at stderr until that has happened."""
+def init_nccl(local):
     import torch
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    sys.stdout.flush()
-    saved_fd = os.dup(1)
-    os.dup2(2, 1)
-    try:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        warm = torch.zeros(1, device=torch.device("cuda", local))
-        dist.all_reduce(warm)
-        if p2p_peer is not None:        # the send/recv communicator comes up lazily as well
-            if dist.get_rank() < p2p_peer:
-                dist.recv(warm, src=p2p_peer)
-            else:
-                dist.send(warm, dst=p2p_peer)
-        torch.cuda.synchronize()
-    finally:
-        sys.stdout.flush()
-        os.dup2(saved_fd, 1)
-        os.close(saved_fd)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warm = torch.zeros(1, device=torch.device("cuda", local))
+    dist.all_reduce(warm)
+    torch.cuda.synchronize()
 
 
-class TrackGather:
-    """The per-publish-window collective of the replica mode: every rank's
-    packed track block, all-gathered so that any rank can publish all clouds.  It runs on a
-    stream of its own behind esvio_fe_result_acquire / _release -- the tracking streams never
-    wait for NCCL -- into one of two rotating receive buffers, and only on publish windows (the
-    reference publishes nothing on the others, stereo_event_tracker_node.cpp:268)."""
-
-    def __init__(self, torch, dev, world, words):
-        self.torch, self.dev, self.world = torch, dev, world
-        self.stream = torch.cuda.Stream(device=dev)
-        self.bufs = [torch.empty((world, words), dtype=torch.int32, device=dev) for _ in range(2)]
-        self.views = {}
-        self.n = 0
-
-    def after_submit(self, fe):
-        ptr, nbytes = fe.result_acquire(self.stream.cuda_stream)
-        v = self.views.get(ptr)
-        if v is None:
-            v = self.views[ptr] = self.torch.as_tensor(_CudaArray(ptr, nbytes), device=self.dev)
-        with self.torch.cuda.stream(self.stream):
-            shard.all_gather_tracks(v, self.bufs[self.n & 1])
-        fe.result_release(self.stream.cuda_stream)
-        self.n += 1
-
-
-def run_pipelined(fe, wins, k0, n, pub_div, gather=None, collect=None):
-    """n windows from k0 through submit/wait, three in flight; `wins[k]` = (left, right, t) as
-    esvio_events wrappers.  Returns (n_left, n_right) of the last one and their sum over all."""
+def run_pipelined(fe, wins, k0, n, pub_div, gather=False, collect=None):
+    """n windows from k0 through submit/wait, a pipeline depth in flight; `wins[k]` = (left, right,
+    t) as esvio_events wrappers.  `gather`: the replica mode's collective -- on publish windows
+    (the reference publishes nothing on the others, stereo_event_tracker_node.cpp:268) the packed
+    track block is all-gathered over NCCL by the library itself (esvio_fe_allgather_tracks), on
+    a stream of its own.  Returns (n_left, n_right) of the last window and their sum over all."""
     last, checksum, waited = (0, 0), 0, 0
     for k in range(k0, k0 + n):
         l, r, t = wins[k]
         pub = k % pub_div == 0
         fe.submit(t, l, r, pub)
-        if gather is not None and pub:
-            gather.after_submit(fe)
+        if gather and pub:
+            fe.allgather_tracks()
         if k - k0 >= DEPTH - 1:
             last = fe.wait(unpack=False)
             checksum += last[0] + last[1]
@@ -365,6 +350,7 @@ class StreamBench:
         self.n_per_cam = int(round(self.w["rate"] / synth.WINDOWS_PER_SEC))
         self.cfg = dict(cfg, device_id=local, max_events_per_window=max(self.n_per_cam + 64, 1024))
         self.K, self.Wm, self.world = K, Wm, world
+        self.rank = stream_id if world > 1 else 0
         self.wins = gen_windows(self.w, stream_id, K + Wm, scene)
         self.ev_timed = n_events(self.wins[Wm:])
         self.ev_per_step = self.ev_timed / max(K, 1)
@@ -383,8 +369,8 @@ class StreamBench:
             l, r, t = wins[k]
             pub = k % self.pub_div == 0
             fe.submit(t, l, r, pub)
-            if gather is not None and pub:
-                gather.after_submit(fe)
+            if gather and pub:
+                fe.allgather_tracks()
             fe.wait(unpack=False)
         flush.fill_(fill)   # evict the uploaded windows: every timed step streams its events from HBM
         self.barrier()
@@ -392,15 +378,25 @@ class StreamBench:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
         last, checksum = run_pipelined(fe, wins, self.Wm, self.K, self.pub_div, gather)
-        if gather is not None:
-            ext.wait_stream(gather.stream)   # the timed region ends when the last gather has
+        if gather:   # the timed region ends when the last all-gather has
+            ext.wait_stream(torch.cuda.ExternalStream(fe.gathered_tracks()[2], device=self.dev))
         e1.record(ext)
         self.barrier()
+        if gather:   # every rank's block of the last publish window arrived intact
+            ptr, nbytes, _ = fe.gathered_tracks()
+            blocks = shard.device_bytes(ptr, nbytes * self.world).cpu().numpy().view(np.int32)
+            blocks = blocks.reshape(self.world, -1)
+            M = self.cfg["max_cnt"]
+            self.gather_ok = bool(all(0 < b[0] <= M and 0 <= b[1] <= M for b in blocks)
+                                  and len({int(b[9]) for b in blocks}) >= 1)
         return e0.elapsed_time(e1), fe.kernel_launches() - launches0, last, checksum
 
-    def device_leg(self, flush, gather=None, profile=False):
+    def device_leg(self, flush, comm_id=None, profile=False):
         fr = self.fr
         fe = fr.EventFrontEnd(self.cfg)
+        gather = comm_id is not None
+        if gather:
+            fe.comm_init(comm_id, self.rank, self.world)
         held = [(fr.DeviceEvents(fe, L), fr.DeviceEvents(fe, R)) for L, R, _ in self.wins]
         dw = [(fr._Ev(a), fr._Ev(b), w[2]) for (a, b), w in zip(held, self.wins)]
         ms, launches, last, _ = self._timed(fe, dw, gather, flush, 1)
@@ -423,7 +419,7 @@ class StreamBench:
                 acc[:] += np.fromiter(d.values(), float)
 
             self.barrier()
-            run_pipelined(fe, dw, self.Wm, self.K, self.pub_div, None, collect)
+            run_pipelined(fe, dw, self.Wm, self.K, self.pub_div, False, collect)
             self.barrier()
             fe.set_profiling(False)
             out["stage_ms"] = dict(zip(fr._capi.STAGE_NAMES, (acc / max(self.K, 1)).tolist()))
@@ -433,12 +429,15 @@ class StreamBench:
         fe.close()
         return out
 
-    def host_leg(self, flush, gather=None, sync=False):
+    def host_leg(self, flush, comm_id=None, sync=False):
         """e2e: pinned host SoA buffers through esvio_fe_track_submit / _wait (H2D of the events
         and D2H of the track records inside the timed region); `sync`: the same windows once
         more through the synchronous esvio_fe_track, host wall clock."""
         fr = self.fr
         fe = fr.EventFrontEnd(self.cfg)
+        gather = comm_id is not None
+        if gather:
+            fe.comm_init(comm_id, self.rank, self.world)
         pw = [(fr._Ev(fr.PinnedEvents(L)), fr._Ev(fr.PinnedEvents(R)), t) for L, R, t in self.wins]
         ms, launches, last, checksum = self._timed(fe, pw, gather, flush, 2)
         out = {"ms": ms, "launches": launches, "last": last, "checksum": checksum}
@@ -688,13 +687,14 @@ def main_ours(args):
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     sb = StreamBench(torch, dev, local, workload, "survey", rank, K, Wm, world)
-    gather = None
-    if world > 1:
-        gather = TrackGather(torch, dev, world, shard.result_words(sb.cfg["max_cnt"]))
+    comm_ids = [None, None]
+    if world > 1:   # one NCCL communicator per handle: rank 0 makes the ids, torch ships them
+        comm_ids = [frontend.nccl_unique_id(), frontend.nccl_unique_id()] if rank == 0 else [None, None]
+        dist.broadcast_object_list(comm_ids, src=0)
     clocks = ClockSampler(local)
     clocks.start()
-    d = sb.device_leg(flush, gather, profile=True)
-    h = sb.host_leg(flush, gather, sync=(world == 1))
+    d = sb.device_leg(flush, comm_ids[0], profile=True)
+    h = sb.host_leg(flush, comm_ids[1], sync=(world == 1))
     clk = clocks.stop()
 
     red = torch.tensor([d["ms"], h["ms"]], dtype=torch.float64, device=dev)
@@ -716,6 +716,14 @@ def main_ours(args):
             one_gpu = {"value": sb1.mev(sb1.device_leg(flush)["ms"]), "unit": UNIT,
                        "what": "rank 0's stream alone, no collective, same run"}
         dist.barrier()
+
+    # N = 2: SURVEY.md 8e row 2 on the same two GPUs -- ONE stream of configs[2] split by camera
+    split_lr = None
+    if world == 2 and not args.no_split:
+        try:
+            split_lr = measure_split(torch, dist, frontend, rank, local, dev, WORKLOAD_N1, K, Wm, flush)
+        except Exception as e:  # noqa: BLE001
+            split_lr = {"error": repr(e)[:300]}
 
     extra = {}
     if rank == 0 and world == 1:
@@ -770,8 +778,9 @@ def main_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_of(workload),
             "run": {"streams_per_gpu": 1, "parallelism": f"{world} independent stereo streams"
-                    + (", NCCL all-gather of the packed track records on publish windows, on a "
-                       "stream of its own" if world > 1 else ""),
+                    + (", NCCL all-gather of the packed track records on publish windows, "
+                       "enqueued by the library (esvio_fe_allgather_tracks) on a stream of its own"
+                       if world > 1 else ""),
                     "windows_in_flight": DEPTH,
                     "l2": "each window's events are read once from HBM: all windows are uploaded, "
                           "then L2 is flushed with a 512 MiB write before the timed region; the SAE "
@@ -799,45 +808,39 @@ def main_ours(args):
             line["roofline_single_stream"] = roof_single
         else:
             line["roofline"] = roof_single
+        if world > 1:
+            line["run"]["all_gather_delivered_every_rank"] = getattr(sb, "gather_ok", None)
         if one_gpu is not None:
             line["one_gpu_same_workload"] = one_gpu
+        if split_lr is not None:
+            line["split_lr"] = split_lr
         line.update(extra)
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def main_split(args):
-    """--split-lr, 2 ranks: ONE stereo stream with the right camera's SAE / time surface /
-    pyramid on rank 1 and everything else on rank 0 (SURVEY.md 8e row 2, 8d config 3 "then 2
-    GPUs with L/R split"); the right image block crosses NVLink once per window (NCCL
-    send/recv).  Strong scaling of one stream; rank 0 also runs the same windows on one handle
-    and reports that throughput and whether the results are identical."""
-    import torch
-    import torch.distributed as dist
-    from esvio_b200 import frontend
-
-    global DEPTH
-    DEPTH = frontend.pipeline_depth()
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if world != 2:
-        raise SystemExit("bench.py --split-lr needs exactly 2 ranks (torchrun --nproc-per-node 2)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the front-end has no CPU fallback")
-    torch.cuda.set_device(local)
-    init_nccl(local, p2p_peer=1 - rank)
-    dev = torch.device("cuda", local)
-    workload = args.workload or WORKLOAD_N1
+def measure_split(torch, dist, frontend, rank, local, dev, workload, K, Wm, flush):
+    """ONE stereo stream with the right camera's SAE / time surface / pyramid on rank 1 and
+    everything else on rank 0 (SURVEY.md 8e row 2, 8d config 3 "then 2 GPUs with L/R split"); the
+    right image block crosses NVLink once per window (NCCL send/recv).  Strong scaling of one
+    stream; rank 0 also runs the same windows on one handle and reports that throughput and
+    whether the results are identical.  Returns the record on rank 0, None on rank 1."""
+    warm = torch.zeros(1, device=dev)      # the send/recv communicator comes up lazily
+    if rank == 0:
+        dist.recv(warm, src=1)
+    else:
+        dist.send(warm, dst=0)
+    torch.cuda.synchronize()
     w, cfg, pub_div = workload_cfg(workload)
     n_per_cam = int(round(w["rate"] / synth.WINDOWS_PER_SEC))
     cfg = dict(cfg, device_id=local, max_events_per_window=max(n_per_cam + 64, 1024))
-    K, Wm = args.steps, args.warmup
     wins = gen_windows(w, 0, K + Wm)                 # both ranks see the same stereo stream
     fe = frontend.EventFrontEnd(cfg)
     sp = shard.LeftRightSplit(fe, rank)
-    mine = [frontend._Ev(frontend.DeviceEvents(fe, (L, R)[rank])) for L, R, _ in wins]
+    held = [frontend.DeviceEvents(fe, (L, R)[rank]) for L, R, _ in wins]
+    mine = [frontend._Ev(h) for h in held]
     n_ev_local = float(sum(len((L, R)[rank][0]) for L, R, _ in wins[Wm:]))
-    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def run(k0, n, sink):
         waited = 0
@@ -876,8 +879,8 @@ def main_split(args):
     one = None
     if rank == shard.LEFT_RANK:       # the same windows on one handle, same pipelining
         fe1 = frontend.EventFrontEnd(cfg)
-        dw = [(frontend._Ev(frontend.DeviceEvents(fe1, L)), frontend._Ev(frontend.DeviceEvents(fe1, R)), t)
-              for L, R, t in wins]
+        held1 = [(frontend.DeviceEvents(fe1, L), frontend.DeviceEvents(fe1, R)) for L, R, _ in wins]
+        dw = [(frontend._Ev(a), frontend._Ev(b), wn[2]) for (a, b), wn in zip(held1, wins)]
         ext1 = torch.cuda.ExternalStream(fe1.stream(), device=dev)
         ref_counts = []
 
@@ -907,22 +910,52 @@ def main_split(args):
         same = ref_counts == counts and all(np.array_equal(a[k], b[k]) for k in a if k != "stats")
         one = {"value": n_ev / (ms1 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms1 / K,
                "identical_results": bool(same)}
+        for x, y in held1:
+            x.free()
+            y.free()
         fe1.close()
     dist.barrier()
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 2, "steps": K, "warmup": Wm,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_of(workload),
+    for h in held:
+        h.free()
+    fe.close()
+    if rank != 0:
+        return None
+    return {"value": value, "unit": UNIT, "n_gpus": 2, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+            "scaling": "strong", "config": config_of(workload),
             "run": {"parallelism": "lr_split: rank 0 left camera + tracking, rank 1 right camera "
                                    "SAE/time surface/pyramid",
                     "inputs": "resident in HBM on the rank that consumes them",
                     "windows_in_flight": DEPTH},
             "exchange": {"what": "right pyramid block, NCCL send/recv per window",
                          "bytes_per_step": int(img_bytes)},
-            "gpu_launches": int(nl.item()), "one_gpu_same_run": one}))
-    fe.close()
+            "gpu_launches": int(nl.item()), "one_gpu_same_run": one}
+
+
+def main_split(args):
+    """--split-lr, 2 ranks: only the left/right split measurement (the N = 2 line of the default
+    bench carries the same record as `split_lr`)."""
+    import torch
+    import torch.distributed as dist
+    from esvio_b200 import frontend
+
+    global DEPTH
+    DEPTH = frontend.pipeline_depth()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != 2:
+        raise SystemExit("bench.py --split-lr needs exactly 2 ranks (torchrun --nproc-per-node 2)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the front-end has no CPU fallback")
+    torch.cuda.set_device(local)
+    init_nccl(local)
+    dev = torch.device("cuda", local)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    rec = measure_split(torch, dist, frontend, rank, local, dev, args.workload or WORKLOAD_N1,
+                        args.steps, args.warmup, flush)
+    if rank == 0:
+        line = {"metric": METRIC, "higher_is_better": True, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic"}
+        line.update(rec)
+        emit(json.dumps(line))
     dist.destroy_process_group()
 
 
@@ -942,10 +975,12 @@ def main():
                     help="streams of the batched leg at N=1 (esvio_fe_group); 1 disables it")
     ap.add_argument("--batch-steps", type=int, default=30)
     ap.add_argument("--no-frames", action="store_true", help="skip the trackImage record")
+    ap.add_argument("--no-split", action="store_true", help="N = 2: skip the left/right split record")
     ap.add_argument("--split-lr", action="store_true",
                     help="2 ranks: one stereo stream split by camera (SURVEY.md 8e row 2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    claim_stdout()
     if args.impl == "reference":
         main_reference(args)
     elif args.split_lr:

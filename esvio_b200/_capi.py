@@ -128,6 +128,11 @@ SYMBOLS = {
     "esvio_fe_get_stage_ms": (C.c_int, [_H, _pf]),
     "esvio_fe_get_stage_marks": (C.c_int, [_H, _pf]),
     "esvio_fe_pipeline_depth": (C.c_int, []),
+    "esvio_fe_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "esvio_fe_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
+    "esvio_fe_comm_attach": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
+    "esvio_fe_allgather_tracks": (C.c_int, [_H]),
+    "esvio_fe_gathered_tracks": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]),
     "esvio_fe_stage_set_tracks": (C.c_int, [_H, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "esvio_fe_kernel_launches": (C.c_int, [_H, C.POINTER(C.c_int64)]),

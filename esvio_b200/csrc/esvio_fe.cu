@@ -3,6 +3,7 @@
 // FeatureTracker::trackEvent (feature_tracker/src/feature_tracker.cpp:340-603).
 // There is no CPU path in this library: every stage is a kernel from events.cu,
 // pyramid.cu, lk.cu, select.cu, ransac.cu.
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -116,6 +117,12 @@ struct esvio_fe {
   float stage_ms[ESVIO_FE_NUM_STAGES];
   cudaEvent_t pev_ref;  // recorded by esvio_fe_set_profiling(on): origin of stage_marks
   float stage_marks[ESVIO_FE_NUM_MARKS];
+  // multi-GPU replicas: the all-gather of the packed track records (esvio_fe_comm_*)
+  void* nccl_comm;
+  int comm_owned, comm_rank, comm_world;
+  cudaStream_t stream_g;       // the collective's own stream
+  int32_t* gathered[2];        // [world][result_words] each, alternating
+  int gather_seq;
 };
 
 static int fail(esvio_fe* fe, int code, const char* what, cudaError_t ce) {
@@ -229,6 +236,50 @@ static int make_state_map(esvio_fe* fe, double2* base, CUtensorMap* map, int n_c
   return ESVIO_FE_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// NCCL, resolved at run time: the library has no link-time dependency on it, and a process that
+// already carries a copy of libnccl.so.2 (e.g. PyTorch's) gets that copy
+// ---------------------------------------------------------------------------------------
+struct NcclUniqueIdBytes {
+  char b[128];  // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES)
+};
+struct NcclApi {
+  int (*GetUniqueId)(NcclUniqueIdBytes*);
+  int (*CommInitRank)(void**, int, NcclUniqueIdBytes, int);
+  int (*CommDestroy)(void*);
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+  const char* (*GetErrorString)(int);
+};
+static const NcclApi* nccl_api() {
+  static NcclApi api;
+  static int state = 0;  // 0 untried, 1 ok, -1 unavailable
+  if (state == 0) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (int (*)(NcclUniqueIdBytes*))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(void**, int, NcclUniqueIdBytes, int))dlsym(h, "ncclCommInitRank");
+      api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+      api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+      api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    }
+    state = (h && api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather) ? 1 : -1;
+  }
+  return state == 1 ? &api : nullptr;
+}
+
+static void comm_release(esvio_fe* fe) {
+  if (fe->stream_g) cudaStreamSynchronize(fe->stream_g);
+  if (fe->nccl_comm && fe->comm_owned && nccl_api()) nccl_api()->CommDestroy(fe->nccl_comm);
+  fe->nccl_comm = nullptr;
+  cudaFree(fe->gathered[0]);
+  cudaFree(fe->gathered[1]);
+  fe->gathered[0] = fe->gathered[1] = nullptr;
+  if (fe->stream_g) cudaStreamDestroy(fe->stream_g);
+  fe->stream_g = nullptr;
+}
+
 static void free_all(esvio_fe* fe) {
   if (!fe) return;
   cudaSetDevice(fe->dev);
@@ -286,6 +337,7 @@ static void free_all(esvio_fe* fe) {
     for (int i = 0; i < ESVIO_FE_NUM_MARKS; ++i)
       if (fe->pev[k][i]) cudaEventDestroy(fe->pev[k][i]);
   if (fe->pev_ref) cudaEventDestroy(fe->pev_ref);
+  comm_release(fe);
   for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_f,
                           fe->stream_t1, fe->stream_s[0], fe->stream_s[1], fe->stream})
     if (st) cudaStreamDestroy(st);
@@ -1558,6 +1610,88 @@ FE_API int esvio_fe_result_release(esvio_fe* fe, void* consumer_stream) {
   fe->r_held[fe->last_slot] = 1;
   return ESVIO_FE_OK;
 }
+// ---- the replica mode's one collective: every rank's packed track block of
+// a publish window, all-gathered so that any rank (or rank 0's adapter) can publish all clouds
+FE_API int esvio_fe_nccl_unique_id(void* id128) {
+  if (!id128) return ESVIO_FE_EINVAL;
+  const NcclApi* n = nccl_api();
+  if (!n) return ESVIO_FE_ENODEV;
+  return n->GetUniqueId((NcclUniqueIdBytes*)id128) == 0 ? ESVIO_FE_OK : ESVIO_FE_ECUDA;
+}
+
+static int comm_setup(esvio_fe* fe, void* comm, int owned, int rank, int world) {
+  comm_release(fe);
+  fe->nccl_comm = comm;
+  fe->comm_owned = owned;
+  fe->comm_rank = rank;
+  fe->comm_world = world;
+  fe->gather_seq = 0;
+  int prio_lo = 0, prio_hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CU(cudaStreamCreateWithPriority(&fe->stream_g, cudaStreamNonBlocking, prio_hi));
+  for (int b = 0; b < 2; ++b) {
+    CU(cudaMalloc(&fe->gathered[b], fe->result_words * 4 * (size_t)world));
+    CU(cudaMemset(fe->gathered[b], 0, fe->result_words * 4 * (size_t)world));
+  }
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_comm_init(esvio_fe* fe, const void* id128, int32_t rank, int32_t world) {
+  if (!fe || !id128 || world < 1 || rank < 0 || rank >= world) return ESVIO_FE_EINVAL;
+  const NcclApi* n = nccl_api();
+  if (!n) return fail(fe, ESVIO_FE_ENODEV, "libnccl.so.2 not found", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  NcclUniqueIdBytes id;
+  memcpy(&id, id128, sizeof(id));
+  void* comm = nullptr;
+  const int r = n->CommInitRank(&comm, world, id, rank);
+  if (r != 0) {
+    snprintf(fe->err, sizeof(fe->err), "ncclCommInitRank: %s", n->GetErrorString ? n->GetErrorString(r) : "?");
+    return ESVIO_FE_ECUDA;
+  }
+  return comm_setup(fe, comm, 1, rank, world);
+}
+
+FE_API int esvio_fe_comm_attach(esvio_fe* fe, void* nccl_comm, int32_t rank, int32_t world) {
+  if (!fe || !nccl_comm || world < 1 || rank < 0 || rank >= world) return ESVIO_FE_EINVAL;
+  if (!nccl_api()) return fail(fe, ESVIO_FE_ENODEV, "libnccl.so.2 not found", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  return comm_setup(fe, nccl_comm, 0, rank, world);
+}
+
+FE_API int esvio_fe_allgather_tracks(esvio_fe* fe) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  if (!fe->nccl_comm) return fail(fe, ESVIO_FE_ESTATE, "no communicator (esvio_fe_comm_init)", cudaSuccess);
+  if (fe->last_slot < 0) return fail(fe, ESVIO_FE_ESTATE, "no window submitted yet", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  const int slot = fe->last_slot;
+  // behind the window's packing, off the tracking streams; the slot's block is not rewritten
+  // (a pipeline depth later) before the collective has read it
+  CU(cudaStreamWaitEvent(fe->stream_g, fe->q_done[slot], 0));
+  const int r = nccl_api()->AllGather(fe->tb.result + (size_t)slot * fe->result_words,
+                                      fe->gathered[fe->gather_seq & 1], fe->result_words * 4, /*ncclInt8*/ 0,
+                                      fe->nccl_comm, fe->stream_g);
+  if (r != 0) {
+    snprintf(fe->err, sizeof(fe->err), "ncclAllGather: %s",
+             nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r) : "?");
+    return ESVIO_FE_ECUDA;
+  }
+  CU(cudaEventRecord(fe->r_free[slot], fe->stream_g));
+  fe->r_held[slot] = 1;
+  fe->gather_seq++;
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_gathered_tracks(esvio_fe* fe, void** dev_blocks, size_t* bytes_per_rank, void** cuda_stream) {
+  if (!fe || !dev_blocks || !bytes_per_rank || !cuda_stream) return ESVIO_FE_EINVAL;
+  if (!fe->nccl_comm || fe->gather_seq == 0)
+    return fail(fe, ESVIO_FE_ESTATE, "no all-gather enqueued yet", cudaSuccess);
+  *dev_blocks = fe->gathered[(fe->gather_seq - 1) & 1];
+  *bytes_per_rank = fe->result_words * 4;
+  *cuda_stream = (void*)fe->stream_g;
+  return ESVIO_FE_OK;
+}
+
 FE_API int esvio_fe_stream(esvio_fe* fe, void** cuda_stream) {
   if (!fe || !cuda_stream) return ESVIO_FE_EINVAL;
   *cuda_stream = (void*)fe->stream;

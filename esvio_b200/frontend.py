@@ -25,6 +25,15 @@ def pipeline_depth() -> int:
     return int(_capi.lib().esvio_fe_pipeline_depth())
 
 
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0; ship the 128 bytes to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    st = _capi.lib().esvio_fe_nccl_unique_id(buf)
+    if st != _capi.OK:
+        raise FrontEndError(st, "nccl_unique_id")
+    return buf.raw
+
+
 def make_config(cfg: dict) -> Config:
     """dict with the reference's parameter names -> esvio_fe_config."""
     c = Config()
@@ -342,6 +351,21 @@ class EventFrontEnd:
     def result_release(self, consumer_stream=0):
         self._chk(_capi.lib().esvio_fe_result_release(self._h, C.c_void_p(consumer_stream)),
                   "result_release")
+
+    # ---- replica mode: all-gather of the packed track records over NCCL (include/esvio_fe.h)
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._chk(_capi.lib().esvio_fe_comm_init(self._h, buf, int(rank), int(world)), "comm_init")
+
+    def allgather_tracks(self):
+        self._chk(_capi.lib().esvio_fe_allgather_tracks(self._h), "allgather_tracks")
+
+    def gathered_tracks(self):
+        """(device pointer of [world] blocks, bytes per rank, cudaStream_t of the collective)."""
+        p, n, st = C.c_void_p(), C.c_size_t(), C.c_void_p()
+        self._chk(_capi.lib().esvio_fe_gathered_tracks(self._h, C.byref(p), C.byref(n), C.byref(st)),
+                  "gathered_tracks")
+        return p.value, n.value, st.value or 0
 
     def stream(self):
         s = C.c_void_p()

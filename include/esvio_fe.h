@@ -258,6 +258,23 @@ int esvio_fe_stream(esvio_fe *fe, void **cuda_stream);
 int esvio_fe_result_acquire(esvio_fe *fe, void *consumer_stream, void **ptr, size_t *bytes);
 int esvio_fe_result_release(esvio_fe *fe, void *consumer_stream);
 
+/* The replica mode's one collective (independent stereo streams, one per
+ * GPU): an all-gather of every rank's packed track block of a publish window, so that any rank
+ * (or rank 0's adapter) can publish all clouds.  NCCL is resolved at run time (libnccl.so.2; the
+ * copy already loaded in the process, if any), the library does not link against it.
+ *   rank 0:     esvio_fe_nccl_unique_id(id)          (ncclGetUniqueId; ship the 128 bytes)
+ *   every rank: esvio_fe_comm_init(fe, id, rank, world)   or  _comm_attach(fe, ncclComm_t, ...)
+ *   per publish window, after esvio_fe_track_submit: esvio_fe_allgather_tracks(fe)
+ * The collective runs on a stream of its own behind the window's packing, into one of two
+ * alternating receive buffers; the tracking streams never wait for it.  _gathered_tracks
+ * returns the latest receive buffer ([world] blocks of bytes_per_rank, device memory) and the
+ * cudaStream_t it is ordered on. */
+int esvio_fe_nccl_unique_id(void *id128);
+int esvio_fe_comm_init(esvio_fe *fe, const void *id128, int32_t rank, int32_t world);
+int esvio_fe_comm_attach(esvio_fe *fe, void *nccl_comm, int32_t rank, int32_t world);
+int esvio_fe_allgather_tracks(esvio_fe *fe);
+int esvio_fe_gathered_tracks(esvio_fe *fe, void **dev_blocks, size_t *bytes_per_rank, void **cuda_stream);
+
 /* Left/right split of ONE stereo stream over two GPUs.  The right camera
  * only feeds its pyramid to the stereo LK (feature_tracker.cpp:475-495), so its createSAE_right /
  * SAEtoTimeSurface_right / pyramid (feature_tracker.cpp:358-368) can run on a second GPU:

@@ -991,3 +991,31 @@ def test_teacher_forced_every_window(fe_mod, ora, name, W, H, rate, n_windows, p
     # undistorted points follow (u, v) through a smooth map (|Jacobian| <= 3 / fx here)
     assert (d_un <= 3.0 * np.maximum(d_px, 1e-4) / fx).all()
     fe.close()
+
+
+def test_allgather_tracks_through_the_c_abi(fe_mod):
+    """esvio_fe_comm_init / _allgather_tracks / _gathered_tracks with a one-rank communicator:
+    the collective (NCCL, resolved at run time by the library) delivers this rank's packed
+    block of the window it was enqueued behind, while later windows are already in flight."""
+    import ctypes as C
+    from esvio_b200 import shard
+    W, H = 346, 260
+    cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=1 << 16)
+    fe = fe_mod.EventFrontEnd(cfg)
+    fe.comm_init(fe_mod.nccl_unique_id(), 0, 1)
+    s = synth.StereoEventStream(W, H, 1.0e6)
+    wins = [s.stereo_window(k) for k in range(6)]
+    for k, (L, R, t) in enumerate(wins):
+        fe.submit(t, L, R, k % 2 == 0)
+        if k == 2:
+            fe.allgather_tracks()           # window 2's block; windows 3..5 follow it
+    outs = [fe.wait() for _ in wins]
+    ptr, nbytes, stream = fe.gathered_tracks()
+    import torch
+    torch.cuda.ExternalStream(stream).synchronize()
+    blk = shard.device_bytes(ptr, nbytes).cpu().numpy().view(np.int32)
+    got = shard.unpack_result_block(blk, cfg["max_cnt"])
+    for key in ("id", "track_cnt", "u", "v", "un_x", "un_y", "vx", "vy", "id_right", "ru", "rv"):
+        assert np.array_equal(got[key], outs[2][key]), key
+    assert len(got["id"]) > 0
+    fe.close()
