@@ -261,7 +261,8 @@ int esvio_fe_result_release(esvio_fe *fe, void *consumer_stream);
 /* The replica mode's one collective (independent stereo streams, one per
  * GPU): an all-gather of every rank's packed track block of a publish window, so that any rank
  * (or rank 0's adapter) can publish all clouds.  NCCL is resolved at run time (libnccl.so.2; the
- * copy already loaded in the process, if any), the library does not link against it.
+ * copy already loaded in the process, if any; a process that brings its own NCCL, e.g. through
+ * PyTorch, has to load it before the first call below), the library does not link against it.
  *   rank 0:     esvio_fe_nccl_unique_id(id)          (ncclGetUniqueId; ship the 128 bytes)
  *   every rank: esvio_fe_comm_init(fe, id, rank, world)   or  _comm_attach(fe, ncclComm_t, ...)
  *   per publish window, after esvio_fe_track_submit: esvio_fe_allgather_tracks(fe)

@@ -997,7 +997,7 @@ def test_allgather_tracks_through_the_c_abi(fe_mod):
     """esvio_fe_comm_init / _allgather_tracks / _gathered_tracks with a one-rank communicator:
     the collective (NCCL, resolved at run time by the library) delivers this rank's packed
     block of the window it was enqueued behind, while later windows are already in flight."""
-    import ctypes as C
+    import torch   # first: the library then finds (and shares) torch's copy of libnccl.so.2
     from esvio_b200 import shard
     W, H = 346, 260
     cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=1 << 16)
@@ -1011,7 +1011,6 @@ def test_allgather_tracks_through_the_c_abi(fe_mod):
             fe.allgather_tracks()           # window 2's block; windows 3..5 follow it
     outs = [fe.wait() for _ in wins]
     ptr, nbytes, stream = fe.gathered_tracks()
-    import torch
     torch.cuda.ExternalStream(stream).synchronize()
     blk = shard.device_bytes(ptr, nbytes).cpu().numpy().view(np.int32)
     got = shard.unpack_result_block(blk, cfg["max_cnt"])
