@@ -725,6 +725,15 @@ def main_ours(args):
         except Exception as e:  # noqa: BLE001
             split_lr = {"error": repr(e)[:300]}
 
+    # N = 4: SURVEY.md 8e row 3 on the same GPUs -- ONE stream of configs[3] sharded by time window
+    time_shard = None
+    if world == 4 and not args.no_split:
+        try:
+            time_shard = measure_time_shard(torch, dist, frontend, rank, world, local, dev,
+                                            "stereo_vga_20mevs_burst", K, Wm, flush)
+        except Exception as e:  # noqa: BLE001
+            time_shard = {"error": repr(e)[:300]}
+
     extra = {}
     if rank == 0 and world == 1:
         if not args.no_rigid:
@@ -814,6 +823,8 @@ def main_ours(args):
             line["one_gpu_same_workload"] = one_gpu
         if split_lr is not None:
             line["split_lr"] = split_lr
+        if time_shard is not None:
+            line["time_shard"] = time_shard
         line.update(extra)
         emit(json.dumps(line))
     if world > 1:
@@ -931,6 +942,140 @@ def measure_split(torch, dist, frontend, rank, local, dev, workload, K, Wm, flus
             "gpu_launches": int(nl.item()), "one_gpu_same_run": one}
 
 
+def measure_time_shard(torch, dist, frontend, rank, world, local, dev, workload, K, Wm, flush):
+    """ONE stereo stream whose SAE / time-surface / corner stages are sharded by time window over
+    `world` GPUs (BASELINE configs[3]): rank r replays window r of every
+    round of `world` windows with the carry-in protocol of shard.TimeShardRank (two all-gathers of
+    the state planes and one of the windows' images + corner candidates per round, NCCL), rank 0
+    runs the serial track chain.  Strong scaling of one stream; rank 0 also runs the same
+    windows through the ordinary pipelined path on its own and reports that throughput and
+    whether the results are identical.  Returns the record on rank 0, None elsewhere."""
+    w, cfg, pub_div = workload_cfg(workload)
+    n_per_cam = int(round(w["rate"] / synth.WINDOWS_PER_SEC))
+    cfg = dict(cfg, device_id=local, max_events_per_window=max(n_per_cam + 64, 1024))
+    R = world
+    n_rounds_w, n_rounds = -(-Wm // R), -(-K // R)
+    n_win = (n_rounds_w + n_rounds) * R
+    k_timed0 = n_rounds_w * R
+    wins = gen_windows(w, 0, n_win)
+    fe = frontend.EventFrontEnd(cfg)
+    stream = torch.cuda.Stream(device=dev)
+    rk = shard.TimeShardRank(fe, rank, R, stream)
+    held = {k: (frontend.DeviceEvents(fe, wins[k][0]), frontend.DeviceEvents(fe, wins[k][1]))
+            for k in range(rank, n_win, R)}
+    mine = {k: (frontend._Ev(a), frontend._Ev(b)) for k, (a, b) in held.items()}
+    empty = frontend._Ev(None)
+    planes = [torch.empty((R, rk.nd), dtype=torch.float64, device=dev) for _ in range(2)]
+    prods = torch.empty((R, rk.prod_bytes), dtype=torch.uint8, device=dev)
+    tracker = tr = None
+    if rank == 0:
+        tracker = frontend.EventFrontEnd(cfg)
+        tr = shard.TimeShardTracker(tracker, rk)
+    counts, pending = [], [0]
+
+    def one_round(rnd):
+        k = rnd * R + rank
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(planes[0].view(-1), rk.phase_a(wins[k][2], *mine[k]))
+            dist.all_gather_into_tensor(planes[1].view(-1), rk.phase_c(planes[0]))
+            dist.all_gather_into_tensor(prods.view(-1), rk.phase_d(planes[1], k % pub_div == 0, empty, empty))
+        if rank == 0:
+            for r in range(R):
+                kk = rnd * R + r
+                if pending[0] >= DEPTH:
+                    counts.append(tracker.wait(unpack=False))
+                    pending[0] -= 1
+                tr.submit(prods[r], wins[kk][2], len(wins[kk][0][0]), kk % pub_div == 0)
+                pending[0] += 1
+            # the products buffer is rewritten by the next round's all-gather: the tracker's
+            # copies out of it are ordered on `stream`, like the all-gather
+
+    def drain():
+        while rank == 0 and pending[0] > 0:
+            counts.append(tracker.wait(unpack=False))
+            pending[0] -= 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for rnd in range(n_rounds_w):
+        one_round(rnd)
+    drain()
+    flush.fill_(5)
+    barrier()
+    tstream = torch.cuda.ExternalStream(tracker.stream(), device=dev) if rank == 0 else stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(tstream)
+    for rnd in range(n_rounds_w, n_rounds_w + n_rounds):
+        one_round(rnd)
+    drain()
+    e1.record(tstream)
+    barrier()
+    n_ev = n_events(wins[k_timed0:])
+    value, ms = shard.aggregate_throughput(n_ev if rank == 0 else 0.0, e0.elapsed_time(e1))
+    nl = torch.tensor([fe.kernel_launches() + (tracker.kernel_launches() if tracker else 0)],
+                      dtype=torch.int64, device=dev)
+    dist.all_reduce(nl)
+    one = None
+    if rank == 0:
+        fe1 = frontend.EventFrontEnd(cfg)
+        held1 = [(frontend.DeviceEvents(fe1, L), frontend.DeviceEvents(fe1, Rr)) for L, Rr, _ in wins]
+        dw = [(frontend._Ev(a), frontend._Ev(b), wn[2]) for (a, b), wn in zip(held1, wins)]
+        ext1 = torch.cuda.ExternalStream(fe1.stream(), device=dev)
+        ref_counts = []
+
+        def run1(k0, n):
+            waited = 0
+            for k in range(k0, k0 + n):
+                fe1.submit(dw[k][2], dw[k][0], dw[k][1], k % pub_div == 0)
+                if k - k0 >= DEPTH - 1:
+                    ref_counts.append(fe1.wait(unpack=False))
+                    waited += 1
+            while waited < n:
+                ref_counts.append(fe1.wait(unpack=False))
+                waited += 1
+
+        run1(0, k_timed0)
+        flush.fill_(6)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(ext1)
+        run1(k_timed0, n_win - k_timed0)
+        f1.record(ext1)
+        torch.cuda.synchronize()
+        ms1 = f0.elapsed_time(f1)
+        a, b = tracker._unpack(), fe1._unpack()
+        same = ref_counts == counts and all(np.array_equal(a[k], b[k]) for k in a if k != "stats")
+        one = {"value": n_ev / (ms1 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms1 / (n_win - k_timed0),
+               "identical_results": bool(same)}
+        for x, y in held1:
+            x.free()
+            y.free()
+        fe1.close()
+        tracker.close()
+    dist.barrier()
+    for a, b in held.values():
+        a.free()
+        b.free()
+    fe.close()
+    if rank != 0:
+        return None
+    return {"value": value, "unit": UNIT, "n_gpus": world, "steps": n_win - k_timed0, "warmup": k_timed0,
+            "ms_per_step": ms / (n_win - k_timed0), "scaling": "strong", "config": config_of(workload),
+            "run": {"parallelism": f"time-window shard: rank r replays window r of every round of {R} "
+                                   "windows (SAE update, time surface, pyramids, Arc* candidates); "
+                                   "rank 0 also runs the serial track chain",
+                    "inputs": "resident in HBM on the rank that consumes them",
+                    "windows_in_flight": DEPTH},
+            "exchange": {"what": "per round: all-gather of the last-event planes, all-gather of the "
+                                 "accepted-time planes, all-gather of the windows' image pyramids + "
+                                 "corner candidate lists (NCCL)",
+                         "bytes_per_round_per_rank": int(2 * rk.nd * 8 + rk.prod_bytes)},
+            "gpu_launches": int(nl.item()), "one_gpu_same_run": one}
+
+
 def main_split(args):
     """--split-lr, 2 ranks: only the left/right split measurement (the N = 2 line of the default
     bench carries the same record as `split_lr`)."""
@@ -941,16 +1086,22 @@ def main_split(args):
     global DEPTH
     DEPTH = frontend.pipeline_depth()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if world != 2:
+    if args.split_lr and world != 2:
         raise SystemExit("bench.py --split-lr needs exactly 2 ranks (torchrun --nproc-per-node 2)")
+    if args.time_shard and world < 2:
+        raise SystemExit("bench.py --time-shard needs >= 2 ranks (torchrun --nproc-per-node N)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the front-end has no CPU fallback")
     torch.cuda.set_device(local)
     init_nccl(local)
     dev = torch.device("cuda", local)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    rec = measure_split(torch, dist, frontend, rank, local, dev, args.workload or WORKLOAD_N1,
-                        args.steps, args.warmup, flush)
+    if args.time_shard:
+        rec = measure_time_shard(torch, dist, frontend, rank, world, local, dev,
+                                 args.workload or "stereo_vga_20mevs_burst", args.steps, args.warmup, flush)
+    else:
+        rec = measure_split(torch, dist, frontend, rank, local, dev, args.workload or WORKLOAD_N1,
+                            args.steps, args.warmup, flush)
     if rank == 0:
         line = {"metric": METRIC, "higher_is_better": True, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic"}
@@ -976,6 +1127,8 @@ def main():
     ap.add_argument("--batch-steps", type=int, default=30)
     ap.add_argument("--no-frames", action="store_true", help="skip the trackImage record")
     ap.add_argument("--no-split", action="store_true", help="N = 2: skip the left/right split record")
+    ap.add_argument("--time-shard", action="store_true",
+                    help="N ranks: only the time-window shard measurement (SURVEY.md 8e row 3)")
     ap.add_argument("--split-lr", action="store_true",
                     help="2 ranks: one stereo stream split by camera (SURVEY.md 8e row 2)")
     args = ap.parse_args()
@@ -983,7 +1136,7 @@ def main():
     claim_stdout()
     if args.impl == "reference":
         main_reference(args)
-    elif args.split_lr:
+    elif args.split_lr or args.time_shard:
         main_split(args)
     else:
         main_ours(args)

@@ -128,6 +128,14 @@ SYMBOLS = {
     "esvio_fe_get_stage_ms": (C.c_int, [_H, _pf]),
     "esvio_fe_get_stage_marks": (C.c_int, [_H, _pf]),
     "esvio_fe_pipeline_depth": (C.c_int, []),
+    "esvio_fe_state_device_ptrs": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "esvio_fe_shard_merge_max": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_size_t, C.c_void_p]),
+    "esvio_fe_shard_event_stage": (C.c_int, [_H, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esvio_fe_shard_corner_candidates": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "esvio_fe_shard_sizes": (C.c_int, [_H, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "esvio_fe_shard_images": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "esvio_fe_external_buffers": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "esvio_fe_track_submit_external": (C.c_int, [_H, C.c_double, C.c_int32, C.c_int32, C.c_void_p]),
     "esvio_fe_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "esvio_fe_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "esvio_fe_comm_attach": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),

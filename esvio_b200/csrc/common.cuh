@@ -309,6 +309,12 @@ void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* fl
 void launch_pyramids(const PyrDesc& pd, uint8_t* const* pyr, int n_img, cudaStream_t s,
                      int64_t* launches);
 
+// dst[i] = max over the n_src planes of srcs[k][i] (time-window shard: times only grow, 0 =
+// never, so "the last event before me" over earlier windows is an element-wise maximum)
+constexpr int kMaxMergeSrc = 10;
+void launch_merge_max(double* dst, const double* const* srcs, int n_src, size_t n, cudaStream_t s,
+                      int64_t* launches);
+
 // optional conditioning of the time surface (imgops.cu)
 void launch_median(const uint8_t* const src[2], uint8_t* const dst[2], int n_img, int W, int H,
                    int pitch, int ksize, cudaStream_t s, int64_t* launches);

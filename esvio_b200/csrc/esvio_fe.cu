@@ -91,6 +91,7 @@ struct esvio_fe {
   cudaEvent_t s_done[kSlots];   // stereo LK done
   cudaEvent_t x_ready[kSlots];  // left/right split: marks on the caller's exchange stream
   int f_pending;                // slot whose corner flags the next K1 has to wait for, or -1
+  int shard_seq;                // esvio_fe_shard_event_stage calls so far (slot rotation)
   TrackBuffers tb;
   TrackParams tp;
   int32_t* h_result[kSlots];
@@ -361,6 +362,7 @@ static int reset_state(esvio_fe* fe) {
   fe->q_head = fe->q_count = 0;
   fe->last_slot = -1;
   fe->f_pending = -1;
+  fe->shard_seq = 0;
   for (int k = 0; k < kSlots; ++k) fe->pev_valid[k] = 0, fe->r_held[k] = 0;
   fe->stage_ms_valid = 0;
   return ESVIO_FE_OK;
@@ -1075,6 +1077,160 @@ FE_API int esvio_fe_track_submit_split(esvio_fe* fe, double cur_time, const esvi
                             true)) != ESVIO_FE_OK)
     return rc;
   fe->pev_valid[w.slot] = fe->profiling;
+  return ESVIO_FE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// time-window shard: building blocks
+// ---------------------------------------------------------------------------------------
+// createSAE_*'s acceptance test reads only sae_latest_ (event_detector.cc:149-166), which after
+// a window is "time of the last event per pixel and polarity": consecutive windows can therefore
+// be replayed on different GPUs once each knows the element-wise maximum of the windows before
+// it (its carry-in), and the accepted times (sae_) merge the same way afterwards.  The caller
+// (esvio_b200/shard.py TimeWindowShard) owns the protocol and the collectives; the library
+// provides: the state planes as device memory, an element-wise maximum over planes, the event
+// stage ordered on the caller's stream, the corner candidates of a window on the device, and
+// tracking from event-stage products computed elsewhere.
+FE_API int esvio_fe_state_device_ptrs(esvio_fe* fe, void** sae, void** lat, size_t* bytes) {
+  if (!fe || !sae || !lat || !bytes) return ESVIO_FE_EINVAL;
+  *sae = fe->sae;
+  *lat = fe->lat;
+  *bytes = fe->npx * 2 * sizeof(double2);
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_shard_merge_max(esvio_fe* fe, void* dst, const void* const* srcs, int32_t n_src,
+                                    size_t n_doubles, void* cuda_stream) {
+  if (!fe || !dst || !srcs || n_src < 1 || n_src > kMaxMergeSrc) return ESVIO_FE_EINVAL;
+  CU(cudaSetDevice(fe->dev));
+  launch_merge_max((double*)dst, (const double* const*)srcs, n_src, n_doubles, (cudaStream_t)cuda_stream,
+                   &fe->launches);
+  CU(cudaGetLastError());
+  return ESVIO_FE_OK;
+}
+
+// esvio_fe_stage_update without host synchronisation: binning + SAE update + time surface +
+// pyramids of one window on the handle's own streams, ordered behind and in front of the
+// caller's stream.  Events must be device-resident (or stay valid until the stream passed).
+FE_API int esvio_fe_shard_event_stage(esvio_fe* fe, double t_ref, const esvio_events* left,
+                                      const esvio_events* right, void* cuda_stream) {
+  if (!fe) return ESVIO_FE_EINVAL;
+  if (fe->group) return fail(fe, ESVIO_FE_ESTATE, "handle belongs to a group", cudaSuccess);
+  if (fe->q_count != 0) return fail(fe, ESVIO_FE_ESTATE, "windows in flight", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  cudaStream_t us = (cudaStream_t)cuda_stream;
+  const int slot = fe->shard_seq % kSlots;
+  fe->shard_seq++;
+  DevEvents ev[2];
+  int rc;
+  // everything the caller enqueued so far (state writes, earlier reads of the images) first
+  CU(cudaEventRecord(fe->x_ready[slot], us));
+  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p})
+    CU(cudaStreamWaitEvent(st, fe->x_ready[slot], 0));
+  if ((rc = stage_events(fe, slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
+  if ((rc = stage_events(fe, slot, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
+  if ((rc = staging_done(fe, slot)) != ESVIO_FE_OK) return rc;
+  if ((rc = run_event_stage(fe, slot, t_ref, ev, fe->cur_left, fe->cur_right)) != ESVIO_FE_OK) return rc;
+  CU(cudaStreamWaitEvent(us, fe->p_done[slot], 0));
+  return ESVIO_FE_OK;
+}
+
+// Arc* candidates of a window's left events against the handle's current state, on the caller's
+// stream; returns the device lists (layout: CornerParams::cand / cand_cnt)
+FE_API int esvio_fe_shard_corner_candidates(esvio_fe* fe, const esvio_events* left, void* cuda_stream,
+                                            void** cand, void** cand_cnt) {
+  if (!fe || !left || !cand || !cand_cnt) return ESVIO_FE_EINVAL;
+  if (!left->on_device && left->n) return fail(fe, ESVIO_FE_EINVAL, "device-resident events only", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  DevEvents ev;
+  int rc;
+  if ((rc = stage_events(fe, 0, 0, left, &ev)) != ESVIO_FE_OK) return rc;
+  launch_corner_flags(corner_params(fe, fe->cur_left, 1, kSlots - 1), ev, fe->flags[kSlots - 1],
+                      (cudaStream_t)cuda_stream, &fe->launches);
+  CU(cudaGetLastError());
+  *cand = fe->cand[kSlots - 1];
+  *cand_cnt = fe->cand_cnt[kSlots - 1];
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_shard_sizes(esvio_fe* fe, size_t* image_bytes, size_t* cand_bytes, size_t* cand_cnt_bytes) {
+  if (!fe || !image_bytes || !cand_bytes || !cand_cnt_bytes) return ESVIO_FE_EINVAL;
+  *image_bytes = fe->pd.bytes;
+  *cand_bytes = ((size_t)fe->cap + kCornerBlock) * sizeof(uint32_t);
+  *cand_cnt_bytes = ((size_t)fe->cap / kCornerBlock + 2) * sizeof(int);
+  return ESVIO_FE_OK;
+}
+
+FE_API int esvio_fe_shard_images(esvio_fe* fe, void** left_img, void** right_img) {
+  if (!fe || !left_img || !right_img) return ESVIO_FE_EINVAL;
+  *left_img = fe->pyr[fe->cur_left];
+  *right_img = fe->pyr[fe->cur_right];
+  return ESVIO_FE_OK;
+}
+
+// the buffers the NEXT submitted window reads its event-stage products from
+FE_API int esvio_fe_external_buffers(esvio_fe* fe, void** left_img, void** right_img, void** cand,
+                                     void** cand_cnt) {
+  if (!fe || !left_img || !right_img || !cand || !cand_cnt) return ESVIO_FE_EINVAL;
+  WindowPlan w;
+  int rc;
+  if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
+  *left_img = fe->pyr[w.cur];
+  *right_img = fe->pyr[w.rcur];
+  *cand = fe->cand[w.slot];
+  *cand_cnt = fe->cand_cnt[w.slot];
+  return ESVIO_FE_OK;
+}
+
+// esvio_fe_track_submit for a window whose event stage ran elsewhere: the image pyramids and
+// (publish windows) the corner candidate lists were written into esvio_fe_external_buffers on
+// `cuda_stream`; temporal chain, stereo LK and packing run here as usual.
+FE_API int esvio_fe_track_submit_external(esvio_fe* fe, double cur_time, int32_t n_left_events,
+                                          int32_t pub_this_frame, void* cuda_stream) {
+  if (!fe || n_left_events < 0) return ESVIO_FE_EINVAL;
+  if (fe->group) return fail(fe, ESVIO_FE_ESTATE, "handle belongs to a group", cudaSuccess);
+  CU(cudaSetDevice(fe->dev));
+  WindowPlan w;
+  int rc;
+  if ((rc = plan_window(fe, &w)) != ESVIO_FE_OK) return rc;
+  fe->pev_slot = w.slot;
+  const int slot = w.slot, M = fe->cfg.max_cnt;
+  const TrackBuffers& B = fe->tb;
+  cudaStream_t s1 = fe->stream_t1, ss = fe->stream_s[slot & 1], s2 = fe->stream;
+  CU(cudaEventRecord(fe->x_ready[slot], (cudaStream_t)cuda_stream));
+  CU(cudaStreamWaitEvent(s1, fe->x_ready[slot], 0));
+  launch_lk(fe->pd, fe->pyr[w.prev], fe->pyr[w.cur], B.prev_pts, B.cur_pts, B.st_fwd, B.rev_pts, B.st_bwd,
+            &B.st->n_prev, M, 3, 0, fe->cfg.flow_back ? 1 : 0, s1, &fe->launches);
+  launch_post_temporal(fe->tp, B, pub_this_frame ? -1 : slot, s1, &fe->launches);
+  if (pub_this_frame) {
+    if (fe->cfg.use_ransac) launch_ransac(fe->tp, B, s1, &fe->launches);
+    launch_select(fe->tp, B, n_left_events, fe->cand[slot], fe->cand_cnt[slot], slot, s1, &fe->launches);
+  }
+  CU(cudaEventRecord(fe->t1_done[slot], s1));
+  CU(cudaStreamWaitEvent(ss, fe->t1_done[slot], 0));
+  launch_lk(fe->pd, fe->pyr[w.cur], fe->pyr[w.rcur], B.snap_pts + (size_t)slot * M,
+            B.right_pts + (size_t)slot * M, B.st_sf + (size_t)slot * M, B.rev_left_pts + (size_t)slot * M,
+            B.st_sb + (size_t)slot * M, B.snap_hdr + slot * 16, M, 3, 0, fe->cfg.flow_back ? 2 : 0, ss,
+            &fe->launches);
+  CU(cudaEventRecord(fe->s_done[slot], ss));
+  CU(cudaStreamWaitEvent(s2, fe->s_done[slot], 0));
+  if (fe->r_held[slot]) {
+    CU(cudaStreamWaitEvent(s2, fe->r_free[slot], 0));
+    fe->r_held[slot] = 0;
+  }
+  launch_finalize(fe->tp, B, slot, cur_time, fe->prev_time, s2, &fe->launches);
+  CU(cudaMemcpyAsync(fe->h_result[slot], B.result + (size_t)slot * fe->result_words, fe->result_words * 4,
+                     cudaMemcpyDeviceToHost, s2));
+  CU(cudaEventRecord(fe->q_done[slot], s2));
+  CU(cudaGetLastError());
+  fe->q_count++;
+  fe->last_slot = slot;
+  fe->prev_left = w.prev;
+  fe->cur_left = w.cur;
+  fe->cur_right = w.rcur;
+  fe->windows++;
+  fe->prev_time = cur_time;
+  fe->pev_valid[slot] = 0;
   return ESVIO_FE_OK;
 }
 

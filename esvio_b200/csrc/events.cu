@@ -897,6 +897,36 @@ void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* fl
   ++*launches;
 }
 
+// =====================================================================================
+// time-window shard: element-wise maximum over state planes
+// =====================================================================================
+struct MergeSrc {
+  const double2* p[kMaxMergeSrc];
+};
+__global__ void __launch_bounds__(256)
+k_merge_max(double2* __restrict__ dst, const __grid_constant__ MergeSrc src, int n_src, size_t n2) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    double2 m = src.p[0][i];
+    for (int k = 1; k < n_src; ++k) {
+      const double2 v = src.p[k][i];
+      m.x = fmax(m.x, v.x);
+      m.y = fmax(m.y, v.y);
+    }
+    dst[i] = m;
+  }
+}
+
+void launch_merge_max(double* dst, const double* const* srcs, int n_src, size_t n, cudaStream_t s,
+                      int64_t* launches) {
+  if (n == 0 || n_src < 1) return;
+  MergeSrc src;
+  for (int k = 0; k < kMaxMergeSrc; ++k) src.p[k] = reinterpret_cast<const double2*>(srcs[k < n_src ? k : 0]);
+  const size_t n2 = n / 2;  // planes are double2 arrays
+  const int blocks = (int)((n2 + 255) / 256 < 148 * 8 ? (n2 + 255) / 256 : 148 * 8);
+  k_merge_max<<<blocks, 256, 0, s>>>(reinterpret_cast<double2*>(dst), src, n_src, n2);
+  ++*launches;
+}
+
 // see prefer_shared_lk (lk.cu): kernels that are to share an SM have to ask for the same
 // shared-memory carve-out
 void prefer_shared_events() {

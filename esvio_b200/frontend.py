@@ -352,6 +352,54 @@ class EventFrontEnd:
         self._chk(_capi.lib().esvio_fe_result_release(self._h, C.c_void_p(consumer_stream)),
                   "result_release")
 
+    # ---- time-window shard building blocks (include/esvio_fe.h, esvio_b200/shard.py)
+    def state_device_ptrs(self):
+        """(sae pointer, sae_latest pointer, bytes each): double2[2 cams][H][W] planes in HBM."""
+        a, b, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._chk(_capi.lib().esvio_fe_state_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(n)),
+                  "state_device_ptrs")
+        return a.value, b.value, n.value
+
+    def shard_merge_max(self, dst, srcs, n_doubles, stream=0):
+        arr = (C.c_void_p * len(srcs))(*[int(p) for p in srcs])
+        self._chk(_capi.lib().esvio_fe_shard_merge_max(self._h, C.c_void_p(int(dst)), arr, len(srcs),
+                                                       int(n_doubles), C.c_void_p(stream)), "shard_merge_max")
+
+    def shard_event_stage(self, t_ref, left, right, stream=0):
+        l = left if isinstance(left, _Ev) else _Ev(left)
+        r = right if isinstance(right, _Ev) else _Ev(right)
+        self._shard_keep = (l, r)
+        self._chk(_capi.lib().esvio_fe_shard_event_stage(self._h, float(t_ref), C.byref(l.s), C.byref(r.s),
+                                                         C.c_void_p(stream)), "shard_event_stage")
+
+    def shard_corner_candidates(self, left, stream=0):
+        l = left if isinstance(left, _Ev) else _Ev(left)
+        a, b = C.c_void_p(), C.c_void_p()
+        self._chk(_capi.lib().esvio_fe_shard_corner_candidates(self._h, C.byref(l.s), C.c_void_p(stream),
+                                                               C.byref(a), C.byref(b)), "shard_corner_candidates")
+        return a.value, b.value
+
+    def shard_sizes(self):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._chk(_capi.lib().esvio_fe_shard_sizes(self._h, C.byref(a), C.byref(b), C.byref(c)), "shard_sizes")
+        return a.value, b.value, c.value
+
+    def shard_images(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._chk(_capi.lib().esvio_fe_shard_images(self._h, C.byref(a), C.byref(b)), "shard_images")
+        return a.value, b.value
+
+    def external_buffers(self):
+        p = [C.c_void_p() for _ in range(4)]
+        self._chk(_capi.lib().esvio_fe_external_buffers(self._h, *[C.byref(x) for x in p]), "external_buffers")
+        return tuple(x.value for x in p)
+
+    def submit_external(self, cur_time, n_left_events, pub_this_frame=True, stream=0):
+        self._inflight.append((None, None))
+        self._chk(_capi.lib().esvio_fe_track_submit_external(self._h, float(cur_time), int(n_left_events),
+                                                             int(bool(pub_this_frame)), C.c_void_p(stream)),
+                  "track_submit_external")
+
     # ---- replica mode: all-gather of the packed track records over NCCL (include/esvio_fe.h)
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(bytes(unique_id), 128)

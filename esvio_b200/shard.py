@@ -159,3 +159,131 @@ class LeftRightSplit:
         if self.rank != LEFT_RANK:
             return None
         return self.fe.wait(unpack)
+
+
+# ---------------------------------------------------------------------------------------
+# time-window shard of ONE stereo stream (BASELINE configs[3])
+# ---------------------------------------------------------------------------------------
+class TimeShardRank:
+    """One rank of the time-window shard: consecutive windows' SAE / time-surface / corner stages
+    run on different GPUs, the serial track chain (feature_tracker.cpp:405-410,585-586) on rank 0.
+
+    createSAE_*'s acceptance test reads only sae_latest_ ("time of the last event per pixel and
+    polarity", event_detector.cc:149-166), and times only grow, so the state BEFORE window w is
+    the element-wise maximum of the state at the round's start and of the per-window "last
+    event" planes of the windows before w.  A round handles `world` consecutive windows, rank r
+    window r of the round:
+
+      phase_a   replay the window on a zeroed state        -> L_r = last event per pixel / polarity
+      (all-gather of L)
+      phase_c   carry-in = max(G_lat, L_0..L_{r-1}); sae := 0; replay again
+                -> sae_latest after the window (exact) and S_r = last ACCEPTED time in the window
+      (all-gather of S)
+      phase_d   sae := max(G_sae, S_0..S_r): the exact state after window r; time surface,
+                pyramids and Arc* candidates from it -> this window's products (one packed block)
+      (all-gather of the products; rank 0 tracks the windows in order)
+      G := max(G, L_*), max(G, S_*) on every rank.
+
+    Every plane and image equals the sequential ones bit for bit (tests: a single-process run
+    with `world` handles on one GPU against esvio_fe_track).  The collectives are the caller's
+    (torch.distributed all_gather_into_tensor in TimeWindowShard.run_round, plain concatenation
+    in the single-process test)."""
+
+    def __init__(self, fe, rank: int, world: int, stream=None):
+        import torch
+        self.torch, self.fe, self.rank, self.world = torch, fe, rank, world
+        self.stream = stream or torch.cuda.current_stream()
+        self.s = self.stream.cuda_stream
+        sae, lat, nbytes = fe.state_device_ptrs()
+        self.nd = nbytes // 8
+        f64 = lambda p: torch.as_tensor(_DeviceF64(p, self.nd), device="cuda")   # noqa: E731
+        self.sae, self.lat = f64(sae), f64(lat)
+        self.sae_ptr, self.lat_ptr = sae, lat
+        dev = self.sae.device
+        self.g_sae = torch.zeros(self.nd, dtype=torch.float64, device=dev)
+        self.g_lat = torch.zeros(self.nd, dtype=torch.float64, device=dev)
+        self.loc = torch.zeros(self.nd, dtype=torch.float64, device=dev)        # send buffer
+        self.img_bytes, self.cand_bytes, self.cnt_bytes = fe.shard_sizes()
+        self.prod_bytes = 2 * self.img_bytes + self.cand_bytes + self.cnt_bytes
+        self.prod = torch.zeros(self.prod_bytes, dtype=torch.uint8, device=dev)
+        self.window = None
+
+    def _merge(self, dst_ptr, srcs):
+        self.fe.shard_merge_max(dst_ptr, [t.data_ptr() for t in srcs], self.nd, self.s)
+
+    def phase_a(self, t_ref, left, right):
+        """left / right: device-resident events (frontend._Ev of DeviceEvents)."""
+        torch = self.torch
+        self.window = (t_ref, left, right)
+        with torch.cuda.stream(self.stream):
+            self.sae.zero_()
+            self.lat.zero_()
+        self.fe.shard_event_stage(t_ref, left, right, self.s)
+        with torch.cuda.stream(self.stream):
+            self.loc.copy_(self.lat)
+        return self.loc
+
+    def phase_c(self, gathered):
+        """gathered: [world, nd] last-event planes of the round's windows."""
+        torch = self.torch
+        t_ref, left, right = self.window
+        self.L = gathered
+        with torch.cuda.stream(self.stream):
+            self._merge(self.lat_ptr, [self.g_lat] + [gathered[k] for k in range(self.rank)])
+            self.sae.zero_()
+        self.fe.shard_event_stage(t_ref, left, right, self.s)
+        with torch.cuda.stream(self.stream):
+            self.loc.copy_(self.sae)
+        return self.loc
+
+    def phase_d(self, gathered, pub: bool, empty_left, empty_right):
+        """gathered: [world, nd] accepted-time planes.  Returns this window's packed products
+        (left image | right image | candidate lists | candidate counts) as a uint8 tensor."""
+        torch = self.torch
+        t_ref, left, right = self.window
+        self.S = gathered
+        with torch.cuda.stream(self.stream):
+            self._merge(self.sae_ptr, [self.g_sae] + [gathered[k] for k in range(self.rank + 1)])
+        # time surface + pyramids from the exact state: the event stage with no events
+        self.fe.shard_event_stage(t_ref, empty_left, empty_right, self.s)
+        li, ri = self.fe.shard_images()
+        ib, cb, nb = self.img_bytes, self.cand_bytes, self.cnt_bytes
+        with torch.cuda.stream(self.stream):
+            self.prod[:ib].copy_(device_bytes(li, ib))
+            self.prod[ib:2 * ib].copy_(device_bytes(ri, ib))
+        if pub:
+            cand, cnt = self.fe.shard_corner_candidates(left, self.s)
+            with torch.cuda.stream(self.stream):
+                self.prod[2 * ib:2 * ib + cb].copy_(device_bytes(cand, cb))
+                self.prod[2 * ib + cb:].copy_(device_bytes(cnt, nb))
+        # the state every rank starts the next round from
+        with torch.cuda.stream(self.stream):
+            self._merge(self.g_lat.data_ptr(), [self.g_lat] + [self.L[k] for k in range(self.world)])
+            self._merge(self.g_sae.data_ptr(), [self.g_sae] + [self.S[k] for k in range(self.world)])
+        return self.prod
+
+
+class _DeviceF64:
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8",
+                                         "data": (int(ptr), False), "version": 3}
+
+
+class TimeShardTracker:
+    """Rank 0's serial half: takes the gathered products of a round and tracks its windows in
+    order through esvio_fe_track_submit_external."""
+
+    def __init__(self, fe, shard_rank: TimeShardRank):
+        self.fe, self.r = fe, shard_rank
+
+    def submit(self, products, cur_time, n_left_events, pub):
+        torch = self.r.torch
+        li, ri, cand, cnt = self.fe.external_buffers()
+        ib, cb, nb = self.r.img_bytes, self.r.cand_bytes, self.r.cnt_bytes
+        with torch.cuda.stream(self.r.stream):
+            device_bytes(li, ib).copy_(products[:ib])
+            device_bytes(ri, ib).copy_(products[ib:2 * ib])
+            if pub:
+                device_bytes(cand, cb).copy_(products[2 * ib:2 * ib + cb])
+                device_bytes(cnt, nb).copy_(products[2 * ib + cb:])
+        self.fe.submit_external(cur_time, n_left_events, pub, self.r.s)

@@ -296,6 +296,35 @@ int esvio_fe_split_right_buffer(esvio_fe *fe, void **image, size_t *bytes);
 int esvio_fe_track_submit_split(esvio_fe *fe, double cur_time, const esvio_events *left,
                                 int32_t pub_this_frame, void *exchange_stream);
 
+/* Time-window shard: consecutive windows' SAE / time-surface / corner
+ * stages on different GPUs, the serial track chain on one.  createSAE_*'s acceptance test reads
+ * only sae_latest_ (event_detector.cc:149-166), so a window can be replayed from a carry-in that
+ * is the element-wise maximum of the windows before it; esvio_b200/shard.py TimeWindowShard owns
+ * the protocol and the collectives, these are its building blocks (all stream-ordered, no host
+ * synchronisation; `cuda_stream` is a cudaStream_t):
+ *   _state_device_ptrs  the handle's sae / sae_latest planes (double2[2 cams][H][W], .x = polarity 0)
+ *   _shard_merge_max    dst[i] = max_k srcs[k][i] over n_src <= 10 planes of n_doubles doubles
+ *   _shard_event_stage  binning + SAE update + time surface + pyramids of one window, ordered behind
+ *                       and in front of the caller's stream; images: _shard_images
+ *   _shard_corner_candidates  the window's Arc* candidates (per 128 events: pixels x | y << 16 in
+ *                       stream order, and their count) on the device; sizes: _shard_sizes
+ *   _external_buffers + _track_submit_external  track a window whose images and candidate lists
+ *                       were produced elsewhere and written into the returned buffers on the
+ *                       caller's stream; results through esvio_fe_track_wait. */
+int esvio_fe_state_device_ptrs(esvio_fe *fe, void **sae, void **lat, size_t *bytes);
+int esvio_fe_shard_merge_max(esvio_fe *fe, void *dst, const void *const *srcs, int32_t n_src,
+                             size_t n_doubles, void *cuda_stream);
+int esvio_fe_shard_event_stage(esvio_fe *fe, double t_ref, const esvio_events *left,
+                               const esvio_events *right, void *cuda_stream);
+int esvio_fe_shard_corner_candidates(esvio_fe *fe, const esvio_events *left, void *cuda_stream,
+                                     void **cand, void **cand_cnt);
+int esvio_fe_shard_sizes(esvio_fe *fe, size_t *image_bytes, size_t *cand_bytes, size_t *cand_cnt_bytes);
+int esvio_fe_shard_images(esvio_fe *fe, void **left_img, void **right_img);
+int esvio_fe_external_buffers(esvio_fe *fe, void **left_img, void **right_img, void **cand,
+                              void **cand_cnt);
+int esvio_fe_track_submit_external(esvio_fe *fe, double cur_time, int32_t n_left_events,
+                                   int32_t pub_this_frame, void *cuda_stream);
+
 /* ---- profiling ---- */
 #define ESVIO_FE_NUM_STAGES 9
 /* CUDA-event milliseconds of the last completed window when profiling is on:

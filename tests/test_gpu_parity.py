@@ -1018,3 +1018,49 @@ def test_allgather_tracks_through_the_c_abi(fe_mod):
         assert np.array_equal(got[key], outs[2][key]), key
     assert len(got["id"]) > 0
     fe.close()
+
+
+@pytest.mark.parametrize("W,H,rate,R,n_rounds", [(346, 260, 1.0e6, 4, 3), (640, 480, 5.0e6, 2, 3)])
+def test_time_window_shard_equals_sequential(fe_mod, W, H, rate, R, n_rounds):
+    """SURVEY.md 8e row 3 through the C ABI: R consecutive windows' SAE / time-surface / corner
+    stages replayed on R handles (the 'GPUs'; all on this one device here, the collectives are
+    plain stacking) with the carry-in protocol of shard.TimeShardRank, the track chain on one
+    more handle fed through esvio_fe_track_submit_external -- bit-identical to esvio_fe_track on
+    one handle: every track record of every window, the final SAE planes and time surface."""
+    import torch
+    from esvio_b200 import shard
+    cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=int(rate / 30) + 64)
+    ref = fe_mod.EventFrontEnd(cfg)
+    s = synth.StereoEventStream(W, H, rate)
+    n_win = R * n_rounds
+    wins = [s.stereo_window(k) for k in range(n_win)]
+    expect = [ref.track(t, L, Rr, k % 2 == 0) for k, (L, Rr, t) in enumerate(wins)]
+    handles = [fe_mod.EventFrontEnd(cfg) for _ in range(R)]
+    ranks = [shard.TimeShardRank(h, r, R) for r, h in enumerate(handles)]
+    tracker = fe_mod.EventFrontEnd(cfg)
+    tr = shard.TimeShardTracker(tracker, ranks[0])
+    empty = fe_mod._Ev(None)
+    got = []
+    for rnd in range(n_rounds):
+        ks = [rnd * R + r for r in range(R)]
+        dev = [(fe_mod._Ev(fe_mod.DeviceEvents(handles[r], wins[k][0])),
+                fe_mod._Ev(fe_mod.DeviceEvents(handles[r], wins[k][1]))) for r, k in enumerate(ks)]
+        A = torch.stack([ranks[r].phase_a(wins[k][2], *dev[r]) for r, k in enumerate(ks)])
+        B = torch.stack([ranks[r].phase_c(A) for r in range(R)])
+        P = [ranks[r].phase_d(B, k % 2 == 0, empty, empty).clone() for r, k in enumerate(ks)]
+        for r, k in enumerate(ks):
+            tr.submit(P[r], wins[k][2], len(wins[k][0][0]), k % 2 == 0)
+            got.append(tracker.wait())
+    for k, (x, y) in enumerate(zip(expect, got)):
+        for key in ("id", "track_cnt", "u", "v", "un_x", "un_y", "vx", "vy",
+                    "id_right", "ru", "rv", "run_x", "run_y", "rvx", "rvy"):
+            assert np.array_equal(x[key], y[key]), (k, key)
+    assert sum(len(x["id_right"]) for x in expect) > 0
+    torch.cuda.synchronize()
+    last = handles[R - 1]          # the last rank's state after its window = the sequential state
+    for cam in (0, 1):
+        for a, b in zip(ref.sae_planes(cam), last.sae_planes(cam)):
+            assert np.array_equal(a, b), cam
+    assert np.array_equal(ref.time_surface(0), last.time_surface(0))
+    for f in [ref, tracker] + handles:
+        f.close()
