@@ -323,6 +323,9 @@ void launch_equalize(const uint8_t* const src[2], uint8_t* const tmp[2], uint8_t
                      int n_img, int W, int H, int pitch, uint8_t* lut, int* minmax,
                      cudaStream_t s, int64_t* launches);
 
+void launch_clahe_inplace(uint8_t* const img[2], int n_img, int W, int H, int pitch, uint8_t* lut,
+                          int* minmax, cudaStream_t s, int64_t* launches);
+
 // cv::calcOpticalFlowPyrLK(I, J, prev, next, status, err, Size(21,21), max_level[, 30/0.01,
 // USE_INITIAL_FLOW]); n is read on the device.
 // mode 0: that call alone.  mode 1: followed, per point and in the same launch, by the
@@ -434,6 +437,26 @@ void launch_undistort(const Pinhole& cam, const float2* uv, int n, float2* out, 
                       int64_t* launches);
 
 size_t select_smem_bytes(int W, int H);
+
+// Raise a kernel's dynamic shared-memory limit on the CURRENT device to at least `bytes`
+// (cudaFuncSetAttribute is per device and a process may hold handles of several sizes on
+// several GPUs: the limit only ever grows).  `state` is the caller's static table.
+struct SmemLimit {
+  size_t bytes[64];  // per device ordinal
+};
+template <typename K>
+inline int raise_dyn_smem(K kernel, size_t bytes, SmemLimit* state) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  // benign race between handles created from different threads: both would set a sufficient value
+  if (bytes <= state->bytes[dev]) return 0;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  state->bytes[dev] = bytes;
+  return 0;
+}
 
 void prefer_shared_lk();  // k_lk's shared-memory carve-out preference (lk.cu)
 void prefer_shared_events();   // the same for k_sae_update_ts (events.cu)

@@ -1301,6 +1301,11 @@ FE_API int esvio_fe_track_image_submit(esvio_fe* fe, double cur_time, const uint
   prof_mark(fe, kMarkK1Start, sp);
   prof_mark(fe, kMarkK1Done, sp);
   uint8_t* imgs[2] = {fe->pyr[cur], fe->pyr[rcur]};
+  // EQUALIZE of the image node (stereo_image_tracker_node.cpp:93-97: createCLAHE()->apply on both
+  // frames before trackImage), done here when the handle was created with equalize = 1
+  if (fe->cfg.equalize)
+    launch_clahe_inplace(imgs, right ? 2 : 1, fe->W, fe->H, pitch, fe->clahe_lut, fe->clahe_minmax, sp,
+                         &fe->launches);
   launch_pyramids(fe->pd, imgs, right ? 2 : 1, sp, &fe->launches);
   fe->ts_sel[0] = fe->ts_sel[1] = nullptr;
   prof_mark(fe, kMarkPyrDone, sp);

@@ -494,10 +494,10 @@ static size_t scatter_smem_bytes(int n_bins) {
 }
 
 int bin_configure(int n_bins) {
+  static SmemLimit lim = {};
   const size_t bytes = scatter_smem_bytes(n_bins);
   if (bytes > 200 * 1024) return -1;
-  return cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)bytes) == cudaSuccess ? 0 : -1;
+  return raise_dyn_smem(k_bin_scatter, bytes, &lim);
 }
 
 void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents* ev,

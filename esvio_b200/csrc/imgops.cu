@@ -147,12 +147,11 @@ k_clahe_lut(ClaheGeom g, const uint8_t* __restrict__ src0, const uint8_t* __rest
 
 // bilinear blend of the four nearest tile LUTs + min/max of the result
 __global__ void __launch_bounds__(256)
-k_clahe_apply(ClaheGeom g, const uint8_t* __restrict__ src0, const uint8_t* __restrict__ src1,
-              const uint8_t* __restrict__ lut, uint8_t* __restrict__ dst0,
-              uint8_t* __restrict__ dst1, int* __restrict__ minmax) {
+k_clahe_apply(ClaheGeom g, const uint8_t* src0, const uint8_t* src1, const uint8_t* __restrict__ lut,
+              uint8_t* dst0, uint8_t* dst1, int* __restrict__ minmax) {
   const int cam = blockIdx.z;
-  const uint8_t* __restrict__ src = cam ? src1 : src0;
-  uint8_t* __restrict__ dst = cam ? dst1 : dst0;
+  const uint8_t* src = cam ? src1 : src0;  // may alias dst (launch_clahe_inplace): a thread
+  uint8_t* dst = cam ? dst1 : dst0;        // reads only the pixel it writes
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   int v_out = -1;
   if (x < g.W && y < g.H) {
@@ -214,6 +213,19 @@ void launch_equalize(const uint8_t* const src[2], uint8_t* const tmp[2], uint8_t
   k_clahe_apply<<<grid, 256, 0, s>>>(g, src[0], src[o], lut, tmp[0], tmp[o], minmax);
   k_normalize<<<grid, 256, 0, s>>>(W, H, pitch, tmp[0], tmp[o], dst[0], dst[o], minmax);
   *launches += 3;
+}
+
+// cv::createCLAHE()->apply(img, img) alone, in place (the image node's EQUALIZE,
+// stereo_image_tracker_node.cpp:93-97): the LUTs are complete before the first pixel changes,
+// and every thread rewrites only the pixel it read
+void launch_clahe_inplace(uint8_t* const img[2], int n_img, int W, int H, int pitch, uint8_t* lut,
+                          int* minmax, cudaStream_t s, int64_t* launches) {
+  const ClaheGeom g = clahe_geom(W, H, pitch);
+  const int o = n_img > 1 ? 1 : 0;
+  k_clahe_lut<<<dim3(kClaheTiles, kClaheTiles, n_img), 256, 0, s>>>(g, img[0], img[o], lut, minmax);
+  const dim3 grid((W + 31) / 32, (H + 7) / 8, n_img);
+  k_clahe_apply<<<grid, 256, 0, s>>>(g, img[0], img[o], lut, img[0], img[o], minmax);
+  *launches += 2;
 }
 
 }  // namespace esvio

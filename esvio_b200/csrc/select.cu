@@ -504,13 +504,18 @@ k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict
   SEL_CLK(6);
 }
 
+__global__ void k_image_set_mask(TrackParams P, TrackBuffers B, uint32_t* __restrict__ blocked);
+
+// called by esvio_fe_create on the handle's device: both single-CTA kernels that keep the
+// W x H bit mask in dynamic shared memory get room for this handle's frame size
 int select_configure(int W, int H) {
+  static SmemLimit lim_select = {}, lim_image = {};
   const size_t bytes = select_smem_bytes(W, H);
   cudaFuncAttributes fa;
   if (cudaFuncGetAttributes(&fa, k_select) != cudaSuccess) return -1;
   if (bytes + fa.sharedSizeBytes > 227 * 1024) return -1;
-  return cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)bytes) == cudaSuccess ? 0 : -1;
+  if (raise_dyn_smem(k_select, bytes, &lim_select) != 0) return -1;
+  return raise_dyn_smem(k_image_set_mask, bytes, &lim_image);
 }
 
 void launch_select(const TrackParams& P, const TrackBuffers& B, int n_events, const uint32_t* cand,
@@ -732,14 +737,9 @@ k_image_set_mask(TrackParams P, TrackBuffers B, uint32_t* __restrict__ blocked) 
 
 void launch_image_set_mask(const TrackParams& P, const TrackBuffers& B, const GfttBuffers& G,
                            cudaStream_t s, int64_t* launches) {
-  // the W x H bit mask lives in dynamic shared memory (38 KB at 640x480); raise the kernel's
-  // limit when a larger frame than any before comes along
-  static size_t configured = 48 * 1024 - 24 * 1024;  // default limit minus the static arrays
+  // the W x H bit mask lives in dynamic shared memory (38 KB at 640x480); the limit was raised
+  // for this device when the handle was created (select_configure)
   const size_t bytes = select_smem_bytes(P.W, P.H);
-  if (bytes > configured &&
-      cudaFuncSetAttribute(k_image_set_mask, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)bytes) == cudaSuccess)
-    configured = bytes;
   launch_pdl(k_image_set_mask, dim3(1), dim3(kSelThreads), bytes, s, P, B, G.blocked);
   ++*launches;
 }

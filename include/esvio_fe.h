@@ -192,6 +192,9 @@ int esvio_fe_track_submit_mc(esvio_fe *fe, double cur_time, const esvio_events *
  * MIN_DIST_IMG, mask) (:228), stereo LK against the right frame, undistortion, velocities.
  * Images are CV_8UC1, width x height of the config, `stride` bytes per row; config.max_cnt /
  * min_dist play MAX_CNT_IMG / MIN_DIST_IMG.  right == NULL is img_right.empty() (mono).
+ * config.equalize = 1 applies the image node's EQUALIZE step (cv::createCLAHE()->apply on both
+ * frames, stereo_image_tracker_node.cpp:93-97) on the GPU first: a node that keeps its own CLAHE
+ * call must create the frame handle with equalize = 0.
  * Use a handle of its own for frames (the reference runs them in a separate node,
  * stereo_image_tracker_node.cpp:45).  Results come back through esvio_fe_track_wait.  The
  * submit form copies the frames asynchronously: they must stay valid and unmodified until the

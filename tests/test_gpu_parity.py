@@ -861,6 +861,34 @@ def test_track_image_matches_oracle(fe_mod, ora):
     fe.close()
 
 
+def test_track_image_with_the_image_nodes_equalize(fe_mod, ora):
+    """EQUALIZE of the image node (stereo_image_tracker_node.cpp:93-97): cv::createCLAHE()->apply
+    on both frames before trackImage.  A frame handle created with equalize = 1 does that on the
+    GPU; compared with the oracle's trackImage fed frames equalised by real OpenCV (cv2) -- the
+    level-0 image bit for bit, tracks as in test_track_image_matches_oracle."""
+    cv2 = pytest.importorskip("cv2")
+    s = FRAME_SEQ
+    cfg = synth.default_config(s["W"], s["H"], max_cnt=s["max_cnt"], min_dist=s["min_dist"])
+    cfg["cam"] = FRAME_CAM
+    fe = fe_mod.EventFrontEnd(dict(cfg, equalize=1, max_events_per_window=1024))
+    trk = ora.OracleTracker(cfg)
+    clahe = cv2.createCLAHE()
+    n_right = 0
+    for k, (L, R) in enumerate(synth.stereo_frame_sequence(s["W"], s["H"], s["n_frames"])):
+        # darken the frames so that the equalisation matters
+        L, R = (L // 3 + 20).astype(np.uint8), (R // 3 + 20).astype(np.uint8)
+        t = 1.0 + k / 20.0
+        g = fe.track_image(t, L, R, k % 2 == 0)
+        Le, Re = clahe.apply(L), clahe.apply(R)
+        o = trk.track_image(t, Le, Re, k % 2 == 0)
+        assert np.array_equal(fe.time_surface(0), Le), k       # the equalised frame, bit for bit
+        assert np.array_equal(fe.time_surface(1), Re), k
+        _assert_tracks_agree(g, o, k)
+        n_right += len(g["id_right"])
+    assert n_right > 100
+    fe.close()
+
+
 def test_track_image_pipeline_equals_sync(fe_mod):
     """Three frames in flight give the results of the synchronous call, bit for bit."""
     s = FRAME_SEQ
