@@ -286,6 +286,9 @@ struct SaeTsParams {
   uint8_t* ts[kMaxCams];      // level-0 images
   int ts_pitch;
   int prefetch_dist;          // CTAs ahead whose tile state is prefetched into L2 (0 = off)
+  // filled in by launch_sae_update_ts:
+  int pf_dx, pf_dy, pf_dz;    // prefetch_dist split into grid coordinates (x + gx * (y + gy * z))
+  float ts_karg;              // -log2(e) / decay_sec: exponent of the float time-surface estimate
 };
 void launch_sae_update_ts(const SaeTsParams& P, const CUtensorMap& map_sae,
                           const CUtensorMap& map_lat, cudaStream_t s, int64_t* launches);

@@ -564,6 +564,12 @@ __constant__ double c_exp2_32[32] = {
     1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424,
     1.8741676341103, 1.9152065613971474, 1.9571441241754002};
 
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // exp(a) for a in [-40, 8] to < 3 ulp: a = (32 m + j) ln2/32 + r, |r| <= ln2/64;
 // exp(a) = 2^m * 2^(j/32) * P6(r).  Straight-line (no branches) so that the four pixels of a
 // thread interleave.  The CV_8U value derived from it equals the one derived from a
@@ -585,9 +591,11 @@ __device__ __forceinline__ double exp_small(double a, const double* __restrict__
   return tab[k & 31] * p * scale;
 }
 
-// SAEtoTimeSurface_* for four adjacent pixels (event_detector.cc:230-267).  The reference
-// evaluates 127.5 * (+-e) + 127.5 in double (cv::MatExpr folds 255 * (m + 1) / 2 into one
-// scale + shift) and rounds half to even.  Three regimes of a = -dt / decay:
+// SAEtoTimeSurface_* (event_detector.cc:230-267).  The reference evaluates 127.5 * (+-e) + 127.5
+// with e = exp(-dt / decay) in double (cv::MatExpr folds 255 * (m + 1) / 2 into one scale +
+// shift; 255 * e when polarity is ignored) and rounds half to even into CV_8U.
+//
+// ts_exact: that computation for one pixel, in double.  Three regimes of a = -dt / decay:
 //   a >= -7      e = exp(a) decides the value: computed (< 3 ulp, table + polynomial);
 //   a <  -7      127.5 * e < 0.12: the sum rounds to 128 (positive) / 127 (negative) whatever
 //                the last bits of e are -- until 127.5 * e drops below half an ulp of 127.5
@@ -595,39 +603,68 @@ __device__ __forceinline__ double exp_small(double a, const double* __restrict__
 //                rounds to the even 128 for BOTH polarities.  Around that edge (a in
 //                [-38.5, -36.5]) the sum is evaluated for real again.
 constexpr double kTsExpFrom = -7.0, kTsEdgeLo = -38.5, kTsEdgeHi = -36.5;
+__device__ __noinline__ uint32_t ts_exact(double stamp, bool pos, double t_ref, double decay_sec,
+                                          double inv_decay, int ignore_polarity,
+                                          const double* __restrict__ tab) {
+  // -dt / decay_sec, correctly rounded (Markstein: q + (n - q*d) * RN(1/d) with FMAs)
+  const double n = -(t_ref - stamp);
+  const double q = n * inv_decay;
+  const double a = fma(fma(-q, decay_sec, n), inv_decay, q);
+  if (!(a >= kTsExpFrom || (a >= kTsEdgeLo && a <= kTsEdgeHi)))
+    return ignore_polarity ? 0u : ((pos || a < kTsEdgeLo) ? 128u : 127u);
+  double e = exp_small(fmin(fmax(a, -40.0), 8.0), tab);
+  if (!ignore_polarity && !pos) e = -e;
+  return sat_u8(ignore_polarity ? e * 255.0 : e * 127.5 + 127.5);
+}
+
+// Four pixels of one column (rows r, r+1, r+2, r+3 of the tile: a warp reads 32 adjacent
+// double2 per row, free of bank conflicts).  Almost every pixel is settled by a float estimate: v ~ shift +
+// scale * 2^x, x = (float)dt * karg, karg = -log2(e) / decay.  Its error against the double
+// value is < 4e-4 grey levels (three float roundings of an exponent <= 10.2 in magnitude: 1.3e-6
+// relative in e, ex2.approx 2.4e-7, times <= 255; the FFMA rounds to 2^-17), so the rounded
+// value is the reference's unless the estimate lies within kTsGuard of a rounding boundary --
+// those pixels (0.3 % of the recently hit ones) take ts_exact.  Regimes of x:
+//   x >= -10.2 (a >= -7.07)      the estimate;
+//   -53.97 > x > -10.2           the constants 128 / 127 (valid for any a < -5.6);
+//   x in [-54.02, -53.97]        the far edge: 127.5 * e crosses half an ulp of 127.5 at
+//                                x* = -(47 + log2(127.5)) = -53.9943; ts_exact decides;
+//   x < -54.02                   128 for both polarities (the double sum is exactly 127.5).
+constexpr float kTsGuard = 1.5e-3f;
+constexpr float kTsXFast = -10.2f, kTsXEdgeHi = -53.97f, kTsXEdgeLo = -54.02f;
 __device__ __forceinline__ uchar4 ts_pixel4(const double2* __restrict__ px, const SaeTsParams& P,
                                             const double t_ref, const double* __restrict__ tab) {
-  double a[4];
-  bool pos[4], hit[4], fresh[4];
-  bool any_fresh = false;
+  // px[i * kTileW]: the pixel of row i
+  const float scale = P.ignore_polarity ? 255.f : 127.5f, shift = P.ignore_polarity ? 0.f : 127.5f;
+  const uint32_t none = P.ignore_polarity ? 0u : 128u;  // never hit, or silent beyond the far edge
+  uint32_t o[4];
+  double stamp[4];
+  bool pos[4];
+  uint32_t slow = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const double2 v = px[i];
+    const double2 v = px[i * kTileW];
     pos[i] = v.y > v.x;
-    const double stamp = pos[i] ? v.y : v.x;
-    hit[i] = stamp > 0.0;
-    // -dt / decay_sec, correctly rounded (Markstein: q + (n - q*d) * RN(1/d) with FMAs)
-    const double n = -(t_ref - stamp);
-    const double q = n * P.inv_decay;
-    a[i] = fma(fma(-q, P.decay_sec, n), P.inv_decay, q);
-    fresh[i] = hit[i] && (a[i] >= kTsExpFrom || (a[i] >= kTsEdgeLo && a[i] <= kTsEdgeHi));
-    any_fresh |= fresh[i];
+    stamp[i] = pos[i] ? v.y : v.x;
+    const bool hit = stamp[i] > 0.0;
+    const float x = fminf((float)(t_ref - stamp[i]) * P.ts_karg, 1.f);
+    const float e = exp2f_approx(x);
+    const float est = fmaf((P.ignore_polarity || pos[i]) ? e : -e, scale, shift);
+    const float r = rintf(est);
+    int vi = (int)r;
+    vi = vi < 0 ? 0 : (vi > 255 ? 255 : vi);
+    const bool fast = x >= kTsXFast;
+    const uint32_t konst = (P.ignore_polarity || x < kTsXEdgeLo) ? none : (pos[i] ? 128u : 127u);
+    o[i] = !hit ? none : (fast ? (uint32_t)vi : konst);
+    const bool edge = !P.ignore_polarity && x <= kTsXEdgeHi && x >= kTsXEdgeLo;
+    if (hit && ((fast && fabsf(est - r) > 0.5f - kTsGuard) || edge)) slow |= 1u << i;
   }
-  uint8_t o[4];
+  if (slow) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    o[i] = P.ignore_polarity ? (uint8_t)0
-                             : ((!hit[i] || pos[i] || a[i] < kTsEdgeLo) ? (uint8_t)128 : (uint8_t)127);
-  if (any_fresh) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double e = exp_small(fmin(fmax(a[i], -40.0), 8.0), tab);
-      if (!P.ignore_polarity && !pos[i]) e = -e;
-      const uint8_t v = sat_u8(P.ignore_polarity ? e * 255.0 : e * 127.5 + 127.5);
-      if (fresh[i]) o[i] = v;
-    }
+    for (int i = 0; i < 4; ++i)
+      if (slow & (1u << i))
+        o[i] = ts_exact(stamp[i], pos[i], t_ref, P.decay_sec, P.inv_decay, P.ignore_polarity, tab);
   }
-  return make_uchar4(o[0], o[1], o[2], o[3]);
+  return make_uchar4((uint8_t)o[0], (uint8_t)o[1], (uint8_t)o[2], (uint8_t)o[3]);
 }
 
 // DBG: perf-experiment switches (0 in the product): 1 skip events, 2 skip TS, 4 skip store
@@ -660,12 +697,9 @@ k_sae_update_ts(const __grid_constant__ SaeMaps maps, const __grid_constant__ Sa
   // a CTA `prefetch_dist` launches later will want into L2 now, so that its TMA load is an L2
   // hit instead of a trip to HBM (the launch is latency-bound per CTA: load -> replay -> store).
   if (P.prefetch_dist > 0 && threadIdx.x == 32) {
-    const int tiles_y = gridDim.y;
-    long long lin = (long long)blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)tiles_y * blockIdx.z) +
-                    P.prefetch_dist;
-    const int fx = (int)(lin % gridDim.x);
-    lin /= gridDim.x;
-    const int fy = (int)(lin % tiles_y), fc = (int)(lin / tiles_y);
+    int fx = (int)blockIdx.x + P.pf_dx, fy = (int)blockIdx.y + P.pf_dy, fc = cam + P.pf_dz;
+    if (fx >= (int)gridDim.x) fx -= gridDim.x, ++fy;
+    if (fy >= (int)gridDim.y) fy -= gridDim.y, ++fc;
     if (fc < P.n_cams) {
       const uint32_t* fbs = P.bin_start + fc * (P.n_tiles * kFine + 2) + (fy * P.tiles_x + fx) * kFine;
       tma_prefetch_3d(&maps.sae, 2 * fx * kTileW, fy * kTileH, fc);
@@ -736,14 +770,16 @@ k_sae_update_ts(const __grid_constant__ SaeMaps maps, const __grid_constant__ Sa
   }
   __syncthreads();
 
-  // time surface of the tile straight from shared memory: thread -> 4 adjacent pixels.
+  // time surface of the tile straight from shared memory: lane = column, warp w = rows 4w..4w+3.
   // Columns >= W of the last tile (zero-filled by TMA) land in the row padding of the image.
-  {
-    const int r = threadIdx.x >> 3, c = (threadIdx.x & 7) * 4;
-    const int y = y0 + r;
-    if (y < P.H && !(DBG & 2))
-      *reinterpret_cast<uchar4*>(P.ts[cam] + (size_t)y * P.ts_pitch + x0 + c) =
-          ts_pixel4(&s_sae[r * kTileW + c], P, P.t_ref[cam], s_exp2);
+  if (!(DBG & 2)) {
+    const int r0 = warp * (kTileH / kFine);
+    const uchar4 v = ts_pixel4(&s_sae[r0 * kTileW + lane], P, P.t_ref[cam], s_exp2);
+    uint8_t* __restrict__ out = P.ts[cam] + (size_t)(y0 + r0) * P.ts_pitch + x0 + lane;
+    const uint8_t b[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (y0 + r0 + i < P.H) out[(size_t)i * P.ts_pitch] = b[i];
   }
 
   if (dirty && !(DBG & 4)) {
@@ -765,6 +801,11 @@ void launch_sae_update_ts(const SaeTsParams& P_in, const CUtensorMap& map_sae,
     // half a wave of CTAs ahead (148 SMs x ~14 resident CTAs); experiments: ESVIO_K1_PREFETCH=<n>
     static const int dist = getenv("ESVIO_K1_PREFETCH") ? atoi(getenv("ESVIO_K1_PREFETCH")) : kSaePrefetchDist;
     P.prefetch_dist = dist;
+    const int gx = P.tiles_x, gy = P.n_tiles / P.tiles_x;
+    P.pf_dx = dist % gx;
+    P.pf_dy = (dist / gx) % gy;
+    P.pf_dz = dist / (gx * gy);
+    P.ts_karg = (float)(-1.4426950408889634 / P.decay_sec);
   }
   SaeMaps maps;
   maps.sae = map_sae;
@@ -930,7 +971,9 @@ void launch_merge_max(double* dst, const double* const* srcs, int n_src, size_t 
 // see prefer_shared_lk (lk.cu): kernels that are to share an SM have to ask for the same
 // shared-memory carve-out
 void prefer_shared_events() {
-  cudaFuncSetAttribute(k_sae_update_ts<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+  static const int pct = getenv("ESVIO_CARVEOUT_K1") ? atoi(getenv("ESVIO_CARVEOUT_K1"))
+                         : getenv("ESVIO_CARVEOUT") ? atoi(getenv("ESVIO_CARVEOUT")) : 50;  // experiments
+  cudaFuncSetAttribute(k_sae_update_ts<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 }  // namespace esvio

@@ -27,6 +27,7 @@
 // OpenCV accumulates the same integers in float, so results agree to float rounding
 // (~1e-4 px); against the round-1 kernel (one warp iterating) they are bit-identical.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -492,7 +493,8 @@ void launch_lk(const PyrDesc& pd, const uint8_t* I, const uint8_t* J, const floa
 // throughput at 640x480).  Both ask for half of the array: room for 3 LK CTAs plus 6 SAE
 // CTAs per SM, 114 KB of L1 left.
 void prefer_shared_lk() {
-  cudaFuncSetAttribute(k_lk, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+  static const int pct = getenv("ESVIO_CARVEOUT") ? atoi(getenv("ESVIO_CARVEOUT")) : 50;  // experiments
+  cudaFuncSetAttribute(k_lk, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 }  // namespace esvio

@@ -6,17 +6,23 @@
 
 namespace esvio {
 
-// All levels in one launch: a CTA owns an 8x8 tile of level 3 (16x16 of level 2, 32x32 of
-// level 1) and cascades through shared memory: level-0 patch 85x85 -> level-1 patch 41x41
-// -> level-2 patch 19x19 -> level-3 tile 8x8 (every patch carries the halo the next level's
+// All levels in one launch: a CTA owns a 4x4 tile of level 3 (8x8 of level 2, 16x16 of
+// level 1) and cascades through shared memory: level-0 patch 53x53 -> level-1 patch 25x25
+// -> level-2 patch 11x11 -> level-3 tile 4x4 (every patch carries the halo the next level's
 // 5x5 taps need; the halo pixels are recomputed by the neighbouring CTAs).  Patches are
 // addressed in the image coordinates of their level, so BORDER_REFLECT_101 is applied per
-// level exactly as a level-by-level build would.
-constexpr int kPyrT3 = 8;
-constexpr int kPyrN2 = 2 * kPyrT3 + 3;   // 19
-constexpr int kPyrN1 = 2 * kPyrN2 + 3;   // 41
-constexpr int kPyrN0 = 2 * kPyrN1 + 3;   // 85
-constexpr int kPyrThreads = 256;
+// level exactly as a level-by-level build would.  Small tiles on purpose: the kernel moves
+// ~0.4 MB per image and is bound by the length of one CTA's chain of passes, so it wants many
+// short CTAs (600 for a 640x480 stereo pair, 4 per SM) rather than few long ones.  The level-0
+// patch of tile bx spans columns [32 bx - 14, 32 bx + 39): four aligned 16-byte loads per row.
+constexpr int kPyrT3 = 4;
+constexpr int kPyrN2 = 2 * kPyrT3 + 3;   // 11
+constexpr int kPyrN1 = 2 * kPyrN2 + 3;   // 25
+constexpr int kPyrN0 = 2 * kPyrN1 + 3;   // 53
+constexpr int kPyrThreads = 128;
+constexpr int kPyrChunks = 4;            // 16-byte chunks per level-0 patch row
+constexpr int kPyrLead = 2;              // patch column 0 sits at byte 2 of the first chunk
+static_assert(8 * kPyrT3 == 32 && kPyrLead + kPyrN0 <= 16 * kPyrChunks, "level-0 patch = 4 aligned chunks");
 
 // dst patch (nd x nd at image origin (dx0, dy0), image dw x dh) from src patch (ns x ns at
 // (sx0, sy0), image sw x sh); pixels of the owned rectangle [ox0, ox0+on) x [oy0, oy0+on)
@@ -67,8 +73,8 @@ struct PyrImages {
 __global__ void __launch_bounds__(kPyrThreads)
 k_pyr_build(PyrDesc pd, const __grid_constant__ PyrImages imgs) {
   PDL_PROLOGUE();
-  constexpr int SP0 = kPyrN0 + 3, SP1 = kPyrN1 + 3, SP2 = kPyrN2 + 1;
-  __shared__ uint8_t s0[kPyrN0 * SP0];
+  constexpr int SP0 = 16 * kPyrChunks, SP1 = kPyrN1 + 3, SP2 = kPyrN2 + 1;
+  __shared__ __align__(16) uint8_t s0_raw[kPyrN0 * SP0];
   __shared__ uint8_t s1[kPyrN1 * SP1];
   __shared__ uint8_t s2[kPyrN2 * SP2];
   __shared__ uint8_t s3[kPyrT3 * kPyrT3];
@@ -78,13 +84,20 @@ k_pyr_build(PyrDesc pd, const __grid_constant__ PyrImages imgs) {
   const int p2x = 2 * o3x - 2, p2y = 2 * o3y - 2;
   const int p1x = 2 * p2x - 2, p1y = 2 * p2y - 2;
   const int p0x = 2 * p1x - 2, p0y = 2 * p1y - 2;
+  const uint8_t* s0 = s0_raw + kPyrLead;  // s0[r * SP0 + c] = patch pixel (r, c)
   {
+    // level-0 patch by 16-byte vector loads (rows are 32-byte aligned; bytes beyond the image
+    // width inside the pitch are never used: reflect-101 folds every tap back inside)
     const uint8_t* __restrict__ src = img + pd.off[0];
-    const int w = pd.w[0], h = pd.h[0], pitch = pd.pitch[0];
-    for (int i = threadIdx.x; i < kPyrN0 * kPyrN0; i += kPyrThreads) {
-      const int r = i / kPyrN0, c = i - r * kPyrN0;
-      const int gx = p0x + c, gy = p0y + r;
-      s0[r * SP0 + c] = (gx >= 0 && gx < w && gy >= 0 && gy < h) ? src[(size_t)gy * pitch + gx] : 0;
+    const int h = pd.h[0], pitch = pd.pitch[0];
+    const int xa = p0x - kPyrLead;  // 32 * blockIdx.x - 16
+    for (int i = threadIdx.x; i < kPyrN0 * kPyrChunks; i += kPyrThreads) {
+      const int r = i / kPyrChunks, j = i - r * kPyrChunks;
+      const int gy = p0y + r, gx = xa + 16 * j;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (gy >= 0 && gy < h && gx >= 0 && gx + 16 <= pitch)
+        v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)gy * pitch + gx));
+      *reinterpret_cast<uint4*>(s0_raw + r * SP0 + 16 * j) = v;
     }
   }
   __syncthreads();

@@ -149,6 +149,52 @@ def test_time_surface_of_long_silent_pixels(fe_mod, ora):
     fe.close()
 
 
+@pytest.mark.parametrize("ignore_polarity", [0, 1])
+def test_time_surface_dense_sweep_of_ages(fe_mod, ora, ignore_polarity):
+    """SAEtoTimeSurface_* (event_detector.cc:230-267) on 2.4 M (age, polarity) samples: the kernel
+    settles most pixels with a float estimate and hands the ones near a rounding boundary (and
+    the far edge at 0.7485 s) to the double evaluation -- every regime and both hand-overs must
+    give the reference's grey level.  One event per pixel, ages spread over [0, 8 decay
+    constants], around the far edge and log-uniformly up to 10 s; then the clock advances in
+    odd steps so that every pixel crosses many rounding boundaries."""
+    W, H = 640, 480
+    fe, cfg = _mk(fe_mod, W, H, ignore_polarity=ignore_polarity)
+    decay = cfg["decay_ms"] * 1e-3
+    rng = np.random.default_rng(7 + ignore_polarity)
+    n = W * H
+    age = np.empty(n)
+    kind = rng.random(n)
+    a, b = kind < 0.70, kind >= 0.85
+    age[a] = rng.random(a.sum()) * 8.0 * decay
+    far = 37.426 * decay
+    age[~a & ~b] = far + (rng.random((~a & ~b).sum()) - 0.5) * 0.01 * decay
+    age[b] = 10.0 ** (rng.random(b.sum()) * 7.0 - 6.0)
+    t_ref = 1000.0
+    t = t_ref - age
+    order = np.argsort(t, kind="stable")
+    x = (np.arange(n) % W).astype(np.uint16)[order]
+    y = (np.arange(n) // W).astype(np.uint16)[order]
+    pol = rng.integers(0, 2, n).astype(np.uint8)[order]
+    ev = (x, y, np.ascontiguousarray(t[order]), pol)
+    empty = (np.zeros(0, np.uint16), np.zeros(0, np.uint16), np.zeros(0), np.zeros(0, np.uint8))
+    sae = ora.Sae(W, H)
+    sae.update(*ev)
+    fe.stage_update(t_ref, ev, empty)
+    n_diff, n_px = 0, 0
+    for step in (0.0, 1.0e-7, 3.3e-5, 0.00071, 0.0123, 0.0301, 0.1417, 0.61):
+        if step:
+            fe.stage_update(t_ref + step, empty, empty)
+        got = fe.time_surface(0)
+        ref = sae.time_surface(t_ref + step, ignore_polarity=ignore_polarity)
+        d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+        assert d.max() <= 1, (step, int(d.max()))
+        n_diff += int((d > 0).sum())
+        n_px += n
+    # <= 1 LSB on <= 1e-6 of the samples (libm's exp against the kernel's < 3 ulp one at an exact tie)
+    assert n_diff <= max(2, n_px // 1000000), (n_diff, n_px)
+    fe.close()
+
+
 @pytest.mark.parametrize("W,H,rate", [(346, 260, 1.0e6), (640, 480, 5.0e6)])
 def test_corner_flags_parity(fe_mod, ora, W, H, rate):
     fe, cfg = _mk(fe_mod, W, H)
