@@ -240,13 +240,19 @@ struct BinLayout {
 // two cameras of one stereo stream, or the 2S cameras of a group of S streams.
 struct EventStageBuffers {
   int n_cams;
-  uint32_t* counts;     // [n_cams][max_chunks][n_bins+1]
-  uint32_t* bin_total;  // [n_cams][n_bins+1]
+  uint32_t* counts;     // [2 passes][n_cams][max_chunks][128]: per-chunk digit histograms
+  uint32_t* bin_total;  // [n_cams][n_bins+1] events per fine tile (cleared by the sort itself)
   uint32_t* bin_start;  // [n_cams][n_bins+2]
-  unsigned int* done_ctr;  // [n_cams] CTAs of k_bin_scan that finished (self-resetting)
   double* bt[kMaxCams];    // binned event times
   uint16_t* bk[kMaxCams];  // binned keys: local pixel (8 bits) | polarity << 8
+  double* it[kMaxCams];    // after the first pass (sorted by x / 16): time,
+  uint16_t* ik[kMaxCams];  // key,
+  uint8_t* im[kMaxCams];   // y / 8
 };
+int event_stage_alloc(const BinLayout& L, int n_cams, int cap, EventStageBuffers* E);
+void event_stage_free(EventStageBuffers* E);
+void event_stage_clear(const BinLayout& L, const EventStageBuffers& E, cudaStream_t s);
+int bin_configure(const BinLayout& L);
 
 // by-value kernel parameter (__grid_constant__: indexed by camera without a local copy)
 struct CamBatch {
@@ -255,6 +261,9 @@ struct CamBatch {
   DevEvents ev[kMaxCams];
   double* bt[kMaxCams];
   uint16_t* bk[kMaxCams];
+  double* it[kMaxCams];
+  uint16_t* ik[kMaxCams];
+  uint8_t* im[kMaxCams];
 };
 
 void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents* ev,

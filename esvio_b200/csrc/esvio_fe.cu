@@ -18,7 +18,7 @@ using namespace esvio;
 
 namespace esvio {
 int select_configure(int W, int H);
-int bin_configure(int n_bins);
+
 }
 
 #define FE_API extern "C" __attribute__((visibility("default")))
@@ -308,16 +308,7 @@ static void free_all(esvio_fe* fe) {
     if (fe->q_done[i]) cudaEventDestroy(fe->q_done[i]);
     if (fe->r_free[i]) cudaEventDestroy(fe->r_free[i]);
   }
-  for (int b = 0; b < 2; ++b) {
-    for (int i = 0; i < 2; ++i) {
-      cudaFree(fe->esb[b].bt[i]);
-      cudaFree(fe->esb[b].bk[i]);
-    }
-    cudaFree(fe->esb[b].counts);
-    cudaFree(fe->esb[b].bin_total);
-    cudaFree(fe->esb[b].bin_start);
-    cudaFree(fe->esb[b].done_ctr);
-  }
+  for (int b = 0; b < 2; ++b) event_stage_free(&fe->esb[b]);
   cudaFree(fe->tb.snap_pts);
   cudaFree(fe->tb.snap_ids);
   cudaFree(fe->tb.snap_hdr);
@@ -353,6 +344,8 @@ static int reset_state(esvio_fe* fe) {
   CU(cudaMemsetAsync(fe->tb.snap_hdr, 0, sizeof(int) * 16 * kSlots, fe->stream));
   CU(cudaMemsetAsync(fe->tb.st, 0, sizeof(TrackState), fe->stream));
   CU(cudaMemsetAsync(fe->tb.result, 0, fe->result_words * 4 * kSlots, fe->stream));
+  for (int b = 0; b < 2; ++b)
+    if (fe->esb[b].bin_total) event_stage_clear(fe->bl, fe->esb[b], fe->stream);
   CU(cudaStreamSynchronize(fe->stream));
   fe->cur_left = fe->prev_left = 0;
   fe->cur_right = kRightBase;
@@ -436,7 +429,6 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   L.n_bins = L.n_tiles * kFine;
   fe->cap = (int)align_up((size_t)cfg->max_events_per_window, 64);
   L.max_chunks = (fe->cap + kChunk - 1) / kChunk;
-  const int nb = L.n_bins + 1;
 
   CUC(cudaMalloc(&fe->sae, fe->npx * 2 * sizeof(double2)));
   CUC(cudaMalloc(&fe->lat, fe->npx * 2 * sizeof(double2)));
@@ -464,18 +456,8 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   if (cfg->do_motion_correction)
     for (int i = 0; i < 2; ++i)
       for (int c = 0; c < 2; ++c) CUC(cudaMalloc(&fe->warp_xy[i][c], (size_t)fe->cap * sizeof(uint16_t)));
-  for (int b = 0; b < 2; ++b) {
-    EventStageBuffers& E = fe->esb[b];
-    for (int c = 0; c < 2; ++c) {
-      CUC(cudaMalloc(&E.bt[c], (size_t)fe->cap * sizeof(double)));
-      CUC(cudaMalloc(&E.bk[c], (size_t)fe->cap * sizeof(uint16_t)));
-    }
-    CUC(cudaMalloc(&E.counts, (size_t)2 * nb * L.max_chunks * sizeof(uint32_t)));
-    CUC(cudaMalloc(&E.bin_total, (size_t)2 * nb * sizeof(uint32_t)));
-    CUC(cudaMalloc(&E.bin_start, (size_t)2 * (nb + 1) * sizeof(uint32_t)));
-    CUC(cudaMalloc(&E.done_ctr, 2 * sizeof(unsigned int)));
-    CUC(cudaMemset(E.done_ctr, 0, 2 * sizeof(unsigned int)));
-  }
+  for (int b = 0; b < 2; ++b)
+    CUC(event_stage_alloc(L, 2, fe->cap, &fe->esb[b]) == 0 ? cudaSuccess : cudaErrorMemoryAllocation);
 
   const int M = cfg->max_cnt;
   TrackBuffers& B = fe->tb;
@@ -567,7 +549,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   prefer_shared_lk();
   prefer_shared_events();
   cudaGetLastError();
-  if (select_configure(fe->W, fe->H) != 0 || bin_configure(L.n_bins) != 0) {
+  if (select_configure(fe->W, fe->H) != 0 || bin_configure(L) != 0) {
     fprintf(stderr, "esvio_fe_create: sensor too large for the shared-memory mask / histogram\n");
     free_all(fe);
     return ESVIO_FE_EINVAL;
@@ -1485,16 +1467,7 @@ FE_API void esvio_fe_group_destroy(esvio_fe_group* g) {
     }
   cudaFree(g->sae);
   cudaFree(g->lat);
-  for (int b = 0; b < 2; ++b) {
-    for (int c = 0; c < kMaxCams; ++c) {
-      cudaFree(g->esb[b].bt[c]);
-      cudaFree(g->esb[b].bk[c]);
-    }
-    cudaFree(g->esb[b].counts);
-    cudaFree(g->esb[b].bin_total);
-    cudaFree(g->esb[b].bin_start);
-    cudaFree(g->esb[b].done_ctr);
-  }
+  for (int b = 0; b < 2; ++b) event_stage_free(&g->esb[b]);
   for (int k = 0; k < kSlots; ++k)
     for (cudaEvent_t ev : {g->b_done[k], g->p_done[k], g->k1_beg[k], g->k1_end[k]})
       if (ev) cudaEventDestroy(ev);
@@ -1527,7 +1500,6 @@ FE_API int esvio_fe_group_create(const esvio_fe_config* cfg, int32_t n_streams,
   const int NC = 2 * n_streams;
   const size_t npx = f0->npx;
   g->bl = f0->bl;
-  const int nb = g->bl.n_bins + 1;
   cudaError_t ce = cudaSetDevice(g->dev);
 #define GC(call) if (ce == cudaSuccess) ce = (call)
   {
@@ -1541,19 +1513,8 @@ FE_API int esvio_fe_group_create(const esvio_fe_config* cfg, int32_t n_streams,
   GC(cudaMalloc(&g->lat, npx * NC * sizeof(double2)));
   GC(cudaMemset(g->sae, 0, npx * NC * sizeof(double2)));
   GC(cudaMemset(g->lat, 0, npx * NC * sizeof(double2)));
-  for (int b = 0; b < 2; ++b) {
-    EventStageBuffers& E = g->esb[b];
-    E.n_cams = NC;
-    for (int c = 0; c < NC; ++c) {
-      GC(cudaMalloc(&E.bt[c], (size_t)f0->cap * sizeof(double)));
-      GC(cudaMalloc(&E.bk[c], (size_t)f0->cap * sizeof(uint16_t)));
-    }
-    GC(cudaMalloc(&E.counts, (size_t)NC * nb * g->bl.max_chunks * sizeof(uint32_t)));
-    GC(cudaMalloc(&E.bin_total, (size_t)NC * nb * sizeof(uint32_t)));
-    GC(cudaMalloc(&E.bin_start, (size_t)NC * (nb + 1) * sizeof(uint32_t)));
-    GC(cudaMalloc(&E.done_ctr, NC * sizeof(unsigned int)));
-    GC(cudaMemset(E.done_ctr, 0, NC * sizeof(unsigned int)));
-  }
+  for (int b = 0; b < 2; ++b)
+    GC(event_stage_alloc(g->bl, NC, f0->cap, &g->esb[b]) == 0 ? cudaSuccess : cudaErrorMemoryAllocation);
   for (int k = 0; k < kSlots; ++k) {
     GC(cudaEventCreateWithFlags(&g->b_done[k], cudaEventDisableTiming));
     GC(cudaEventCreateWithFlags(&g->p_done[k], cudaEventDisableTiming));
@@ -1589,6 +1550,8 @@ FE_API int esvio_fe_group_reset(esvio_fe_group* g) {
     if (rc == ESVIO_FE_OK) rc = reset_state(g->m[i]);  // clears the member's slice of the SAE too
     if (rc != ESVIO_FE_OK) return rc;
   }
+  for (int b = 0; b < 2; ++b) event_stage_clear(g->bl, g->esb[b], g->stream_b);
+  CU(cudaStreamSynchronize(g->stream_b));
   for (int k = 0; k < kSlots; ++k) g->k1_slot_valid[k] = 0;
   g->k1_ms_valid = 0;
   return ESVIO_FE_OK;

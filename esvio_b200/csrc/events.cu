@@ -258,251 +258,427 @@ void launch_warp_points(const McParams& P, const float* xy_dt, int n, int* out_x
 }
 
 // =====================================================================================
-// K0: stable counting sort by fine tile
+// K0: stable sort of a window's events by fine tile, as a two-digit LSD radix sort
 // =====================================================================================
 // Same-pixel events must be applied in stream order (acceptance of an event depends on
 // the previous same- and opposite-polarity event at its pixel, event_detector.cc:157),
-// so the sort is stable: CTA c owns events [c*2048, (c+1)*2048), warp w of it owns the
-// 256 consecutive events [w*256, (w+1)*256) and walks them 32 at a time.
-// Bins are 16x8-pixel fine tiles, numbered tile*2 + (x%32)/16 so that the two fine tiles of
-// one 32x8 tile (one TMA box of the SAE state) are adjacent runs; bin n_bins collects
-// out-of-range events.
+// so the sort is stable.  Bins are 16x8-pixel fine tiles, numbered
+//     bin = (y / 8) * (2 * tiles_x) + x / 16          (the two fine tiles of one 32x8 tile, one
+//                                                      TMA box of the SAE state, are adjacent)
+// i.e. a two-digit key: minor = x / 16, major = y / 8, each < kDigit = 128 (W <= 2048,
+// H <= 1024).  A counting sort over the 2 400 bins of a 640x480 sensor needs tables as large as
+// the window itself (2 048-event chunks x 2 401 counters) and 86 KB of shared memory per
+// CTA; two stable passes over <= 128 bins need 4 KB and leave nothing to scan:
+//   k_bin_hist   per 2 048-event chunk: histogram of the minor digit -> cnt_a[cam][chunk][128];
+//                events per fine tile accumulated with global reductions -> bin_total
+//   k_bin_pass1  stable scatter by minor digit into (it, ik, im) = (time, key, major digit); a
+//                CTA derives its write bases from the cnt_a rows itself; the major-digit
+//                histogram of pass 2's chunks is accumulated on the way (cnt_b); one extra CTA
+//                per camera turns bin_total into bin_start and clears it for the next window
+//   k_bin_pass2  stable scatter by major digit into (bt, bk), the runs K1 replays
+// CTA c owns events [c*2048, (c+1)*2048), warp w of it the 256 consecutive events
+// [w*256, (w+1)*256), walked 32 at a time; events beyond the sensor are dropped in pass 1 (the
+// reference would index out of range).
+constexpr int kDigitBits = 7, kDigit = 1 << kDigitBits;
+constexpr int kBinWarps = kChunkThreads / 32;
 
-__device__ __forceinline__ int bin_of(const BinLayout& L, int x, int y) {
-  if (x >= L.W || y >= L.H) return L.n_bins;  // dropped (the reference would index out of range)
-  return ((y / kTileH) * L.tiles_x + (x / kTileW)) * kFine + ((x % kTileW) / kFineW);
+struct BinTables {
+  uint32_t* cnt_a;  // [n_cams][max_chunks][kDigit]
+  uint32_t* cnt_b;  // [n_cams][max_chunks][kDigit]
+};
+
+__device__ __forceinline__ void load_xy(const DevEvents& ev, int i, int& x, int& y) {
+  if (ev.wx) {
+    x = __ldg(ev.wx + i);
+    y = __ldg(ev.wy + i);
+  } else if (ev.aos) {
+    const uint32_t xy = __ldg(reinterpret_cast<const uint32_t*>(ev.aos + i));
+    x = xy & 0xffffu;
+    y = xy >> 16;
+  } else {
+    x = __ldg(ev.x + i);
+    y = __ldg(ev.y + i);
+  }
 }
 
-// counts[cam][chunk][bin]: per-chunk histogram, written coalesced
+// Global reductions on a few thousand hot counters are slow (events arrive in bursts on the same
+// tile: 333 k per-event reductions cost 6-12 us), so the CTAs first count in shared memory and
+// then send one reduction per counter they touched.  Sensors with more fine tiles than
+// kAggBins (> 1024x512) fall back to per-event reductions.
+constexpr int kAggBins = 4096;
+
 __global__ void __launch_bounds__(kChunkThreads)
-k_bin_hist(BinLayout L, const __grid_constant__ CamBatch B, uint32_t* __restrict__ counts) {
+k_bin_hist(BinLayout L, const __grid_constant__ CamBatch B, BinTables T, uint32_t* __restrict__ bin_total) {
   PDL_PROLOGUE();
-  extern __shared__ uint32_t s_hist[];
-  const int cam = blockIdx.y;
+  __shared__ uint32_t s_hist[kDigit];
+  extern __shared__ uint32_t s_fine[];  // [n_bins] when n_bins <= kAggBins
+  const int cam = blockIdx.y, chunk = blockIdx.x;
   const DevEvents& ev = B.ev[cam];
-  const int chunk = blockIdx.x;
-  const int nb = L.n_bins + 1;
-  if ((long long)chunk * kChunk >= ev.n) return;
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) s_hist[b] = 0;
+  if (chunk >= B.n_chunks[cam]) return;
+  const bool agg = L.n_bins <= kAggBins;
+  if (threadIdx.x < kDigit) s_hist[threadIdx.x] = 0;
+  if (agg)
+    for (int b = threadIdx.x; b < L.n_bins; b += kChunkThreads) s_fine[b] = 0;
   __syncthreads();
   const int base = chunk * kChunk;
+  const int minor_n = L.tiles_x * kFine;
+  uint32_t* __restrict__ tot = bin_total + (size_t)cam * (L.n_bins + 1);
 #pragma unroll
   for (int k = 0; k < kChunkSteps; ++k) {
     const int i = base + k * kChunkThreads + threadIdx.x;
     if (i < ev.n) {
       int x, y;
-      if (ev.wx) {
-        x = __ldg(ev.wx + i);
-        y = __ldg(ev.wy + i);
-      } else if (ev.aos) {
-        const uint32_t xy = __ldg(reinterpret_cast<const uint32_t*>(ev.aos + i));
-        x = xy & 0xffffu;
-        y = xy >> 16;
-      } else {
-        x = __ldg(ev.x + i);
-        y = __ldg(ev.y + i);
+      load_xy(ev, i, x, y);
+      if (x < L.W && y < L.H) {
+        const int mi = x / kFineW, ma = y / kTileH;
+        atomicAdd(&s_hist[mi], 1u);
+        if (agg) atomicAdd(&s_fine[ma * minor_n + mi], 1u);
+        else atomicAdd(tot + ma * minor_n + mi, 1u);
       }
-      atomicAdd(&s_hist[bin_of(L, x, y)], 1u);
     }
   }
   __syncthreads();
-  uint32_t* out = counts + ((size_t)cam * L.max_chunks + chunk) * nb;
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) out[b] = s_hist[b];
+  const size_t row = ((size_t)cam * L.max_chunks + chunk) * kDigit;
+  if (threadIdx.x < kDigit) {
+    T.cnt_a[row + threadIdx.x] = s_hist[threadIdx.x];
+    T.cnt_b[row + threadIdx.x] = 0;
+  }
+  if (agg)
+    for (int b = threadIdx.x; b < L.n_bins; b += kChunkThreads) {
+      const uint32_t c = s_fine[b];
+      if (c) atomicAdd(tot + b, c);
+    }
 }
 
-// Exclusive scan of every bin's per-chunk counts, in place.  CTA = 32 adjacent bins x 16
-// chunk phases (all accesses are 128-byte rows of `counts`); the last CTA of a camera to
-// finish then scans the bin totals into bin_start[0..nb].
-constexpr int kScanPhases = 16;
-
-__global__ void __launch_bounds__(32 * kScanPhases)
-k_bin_scan(BinLayout L, const __grid_constant__ CamBatch B, uint32_t* __restrict__ counts,
-           uint32_t* __restrict__ bin_total, uint32_t* __restrict__ bin_start,
-           unsigned int* __restrict__ done_ctr) {
-  PDL_PROLOGUE();
-  __shared__ uint32_t s_part[kScanPhases][33];
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
-  __shared__ bool s_last;
-  const int cam = blockIdx.y;
-  const int nb = L.n_bins + 1;
-  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
-  const int bin = blockIdx.x * 32 + lane;
-  const int n_chunks = B.n_chunks[cam];
-  const int per = (n_chunks + kScanPhases - 1) / kScanPhases;
-  const int c_lo = min(ph * per, n_chunks), c_hi = min(c_lo + per, n_chunks);
-  uint32_t* col = counts + (size_t)cam * L.max_chunks * nb + bin;
-  uint32_t sum = 0;
-  if (bin < nb) {
-    int c = c_lo;
-    for (; c + 4 <= c_hi; c += 4) {
-      const uint32_t v0 = col[(size_t)c * nb], v1 = col[(size_t)(c + 1) * nb],
-                     v2 = col[(size_t)(c + 2) * nb], v3 = col[(size_t)(c + 3) * nb];
-      sum += v0 + v1 + v2 + v3;
-    }
-    for (; c < c_hi; ++c) sum += col[(size_t)c * nb];
-  }
-  s_part[ph][lane] = sum;
-  __syncthreads();
-  uint32_t carry = 0, total = 0;
+// Write bases of this chunk for every digit value: s_base[d] = (events of smaller digits, all
+// chunks) + (events of digit d in earlier chunks), from the per-chunk histograms `cnt` (rows
+// 0..n_rows-1 of this camera).  Returns the total number of events in the table.
+__device__ __forceinline__ uint32_t bin_bases(const uint32_t* __restrict__ cnt, int n_rows, int chunk,
+                                              uint32_t* s_base, uint32_t (*s_red)[2][kDigit]) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  uint4 tot = make_uint4(0, 0, 0, 0), pre = make_uint4(0, 0, 0, 0);
+  // rows warp, warp + 8, ...: eight loads in flight per trip to L2
+  constexpr int kBatch = 8;
+  for (int c0 = warp; c0 < n_rows; c0 += kBinWarps * kBatch) {
+    uint4 v[kBatch];
 #pragma unroll
-  for (int q = 0; q < kScanPhases; ++q) {
-    const uint32_t v = s_part[q][lane];
-    if (q < ph) carry += v;
-    total += v;
-  }
-  if (bin < nb) {
-    for (int c = c_lo; c < c_hi; ++c) {
-      const uint32_t v = col[(size_t)c * nb];
-      col[(size_t)c * nb] = carry;
-      carry += v;
+    for (int j = 0; j < kBatch; ++j) {
+      const int c = c0 + j * kBinWarps;
+      v[j] = make_uint4(0, 0, 0, 0);
+      if (c < n_rows) v[j] = __ldcg(reinterpret_cast<const uint4*>(cnt + (size_t)c * kDigit) + lane);
     }
-    if (ph == 0) bin_total[cam * nb + bin] = total;
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int c = c0 + j * kBinWarps;
+      tot.x += v[j].x, tot.y += v[j].y, tot.z += v[j].z, tot.w += v[j].w;
+      if (c < chunk) pre.x += v[j].x, pre.y += v[j].y, pre.z += v[j].z, pre.w += v[j].w;
+    }
   }
-  // ---- last CTA of this camera: exclusive scan of the totals
-  __threadfence();
+  reinterpret_cast<uint4*>(s_red[warp][0])[lane] = tot;
+  reinterpret_cast<uint4*>(s_red[warp][1])[lane] = pre;
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&done_ctr[cam], 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x == 0) {
-    s_carry = 0;
-    done_ctr[cam] = 0;  // ready for the next window
-  }
-  __syncthreads();
-  const int warp = ph;
-  for (int b0 = 0; b0 < nb; b0 += blockDim.x) {
-    const int b = b0 + threadIdx.x;
-    const uint32_t v = b < nb ? __ldcg(bin_total + cam * nb + b) : 0u;
-    uint32_t incl = v;
+  uint32_t total = 0;
+  if (warp == 0) {
+    // lane owns digits 4*lane .. 4*lane+3
+    uint32_t t[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < kBinWarps; ++w)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t[j] += s_red[w][0][4 * lane + j];
+        q[j] += s_red[w][1][4 * lane + j];
+      }
+    const uint32_t mine = t[0] + t[1] + t[2] + t[3];
+    uint32_t incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += o;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = lane < kScanPhases ? s_warp[lane] : 0u;
+    uint32_t run = incl - mine;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += o;
-      }
-      if (lane < kScanPhases) s_warp[lane] = w;  // inclusive over warps
+    for (int j = 0; j < 4; ++j) {
+      s_base[4 * lane + j] = run + q[j];
+      run += t[j];
     }
-    __syncthreads();
-    const uint32_t warp_off = warp ? s_warp[warp - 1] : 0u;
-    const uint32_t base = s_carry;
-    if (b < nb) bin_start[cam * (nb + 1) + b] = base + warp_off + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry = base + s_warp[kScanPhases - 1];
-    __syncthreads();
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) s_base[kDigit] = total;
   }
-  if (threadIdx.x == 0) bin_start[cam * (nb + 1) + nb] = s_carry;
+  __syncthreads();
+  return s_base[kDigit];
+}
+
+// Stable rank of every lane's event among the events of the same digit in this warp's slice:
+// the lanes of a 32-event step that share a digit find each other with one ballot per digit
+// bit; the running per-digit count of the slice lives in the warp's own row of s_wc.
+__device__ __forceinline__ uint32_t bin_rank_step(uint32_t* my_wc, int d, bool valid, uint32_t lt_mask) {
+  uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int b = 0; b < kDigitBits; ++b) {
+    const uint32_t m = __ballot_sync(0xffffffffu, (d >> b) & 1);
+    peers &= ((d >> b) & 1) ? m : ~m;
+  }
+  uint32_t before = 0;
+  if (valid) before = my_wc[d];
+  __syncwarp();
+  if (valid && (peers & lt_mask) == 0) my_wc[d] = before + __popc(peers);
+  __syncwarp();
+  return before + __popc(peers & lt_mask);
+}
+
+// exclusive prefix of every digit's slice counts over the warps of the CTA, in place
+__device__ __forceinline__ void bin_warp_prefix(uint32_t (*s_wc)[kDigit]) {
+  if (threadIdx.x < kDigit) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < kBinWarps; ++w) {
+      const uint32_t c = s_wc[w][threadIdx.x];
+      s_wc[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kChunkThreads)
-k_bin_scatter(BinLayout L, const __grid_constant__ CamBatch B,
-              const uint32_t* __restrict__ counts, const uint32_t* __restrict__ bin_start) {
+k_bin_pass1(BinLayout L, const __grid_constant__ CamBatch B, BinTables T, uint32_t* __restrict__ bin_total,
+            uint32_t* __restrict__ bin_start) {
   PDL_PROLOGUE();
-  // s_base[nb]: position of this chunk's first event of each bin; s_wc[8 warps][nb]: events of
-  // the bin in each warp's 256-event slice, then the slice's offset inside the chunk
-  extern __shared__ uint32_t s_dyn[];
-  const int cam = blockIdx.y;
+  __shared__ __align__(16) uint32_t s_red[kBinWarps][2][kDigit];
+  __shared__ uint32_t s_wc[kBinWarps][kDigit];
+  __shared__ uint32_t s_base[kDigit + 1];
+  __shared__ uint32_t s_scan[kBinWarps + 1];
+  // [2][n_bins] when n_bins <= kAggBins: this chunk's events per (minor, major) that land below
+  // / at or above the one 2 048-boundary of pass 2's chunks their minor run can straddle
+  extern __shared__ uint32_t s_side[];
+  const int cam = blockIdx.y, chunk = blockIdx.x;
   const DevEvents& ev = B.ev[cam];
-  double* __restrict__ bt = B.bt[cam];
-  uint16_t* __restrict__ bk = B.bk[cam];
-  const int chunk = blockIdx.x;
-  const int nb = L.n_bins + 1;
-  if ((long long)chunk * kChunk >= ev.n) return;
-  uint32_t* s_base = s_dyn;
-  uint32_t* s_wc = s_dyn + nb;
+  const bool agg = L.n_bins <= kAggBins;
+  const int minor_n = L.tiles_x * kFine;
+  const int n_rows = B.n_chunks[cam];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int b = threadIdx.x; b < nb * 8; b += blockDim.x) s_wc[b] = 0;
+  if (chunk < n_rows) {
+    for (int b = threadIdx.x; b < kBinWarps * kDigit; b += blockDim.x) (&s_wc[0][0])[b] = 0;
+    if (agg)
+      for (int b = threadIdx.x; b < 2 * L.n_bins; b += kChunkThreads) s_side[b] = 0;
+    // this thread's events (in flight while the bases are summed up)
+    int dmi[kChunkSteps], dma[kChunkSteps];
+    uint32_t key[kChunkSteps], rank[kChunkSteps];
+    double tt[kChunkSteps];
+    const int wbase = chunk * kChunk + warp * (32 * kChunkSteps);
+#pragma unroll
+    for (int k = 0; k < kChunkSteps; ++k) {
+      const int i = wbase + k * 32 + lane;
+      dmi[k] = -1;
+      dma[k] = 0;
+      key[k] = 0;
+      tt[k] = 0.0;
+      if (i < ev.n) {
+        const Ev e = load_event(ev, i);
+        if (e.x < L.W && e.y < L.H) {
+          dmi[k] = e.x / kFineW;
+          dma[k] = e.y / kTileH;
+          key[k] = (uint32_t)((e.y % kTileH) * kTileW + (e.x % kTileW)) | ((uint32_t)e.p << kPolShift);
+          tt[k] = e.t;
+        }
+      }
+    }
+    bin_bases(T.cnt_a + (size_t)cam * L.max_chunks * kDigit, n_rows, chunk, s_base, s_red);
+#pragma unroll
+    for (int k = 0; k < kChunkSteps; ++k) rank[k] = bin_rank_step(s_wc[warp], dmi[k], dmi[k] >= 0, lt_mask);
+    __syncthreads();
+    bin_warp_prefix(s_wc);
+    __syncthreads();
+    double* __restrict__ it = B.it[cam];
+    uint16_t* __restrict__ ik = B.ik[cam];
+    uint8_t* __restrict__ im = B.im[cam];
+    uint32_t* __restrict__ cb = T.cnt_b + (size_t)cam * L.max_chunks * kDigit;
+#pragma unroll
+    for (int k = 0; k < kChunkSteps; ++k) {
+      if (dmi[k] >= 0) {
+        const uint32_t pos = s_base[dmi[k]] + s_wc[warp][dmi[k]] + rank[k];
+        it[pos] = tt[k];
+        ik[pos] = (uint16_t)key[k];
+        im[pos] = (uint8_t)dma[k];
+        if (agg) {
+          const int side = (int)(pos / kChunk) - (int)(s_base[dmi[k]] / kChunk);  // 0 or 1
+          atomicAdd(&s_side[side * L.n_bins + dma[k] * minor_n + dmi[k]], 1u);
+        } else {
+          atomicAdd(cb + (size_t)(pos / kChunk) * kDigit + dma[k], 1u);
+        }
+      }
+    }
+    if (agg) {
+      __syncthreads();
+      for (int b = threadIdx.x; b < 2 * L.n_bins; b += kChunkThreads) {
+        const uint32_t c = s_side[b];
+        if (c) {
+          const int side = b >= L.n_bins, bin = b - side * L.n_bins;
+          const int ma = bin / minor_n, mi = bin - ma * minor_n;
+          atomicAdd(cb + (size_t)(s_base[mi] / kChunk + side) * kDigit + ma, c);
+        }
+      }
+    }
+  }
+  if (chunk != (int)gridDim.x - 1) return;
+  // ---- the extra CTA of the camera: bin_start = exclusive scan of the fine-tile totals
+  // (complete since k_bin_hist); the totals are cleared for the next window that uses this table
+  const int nb = L.n_bins + 1;
+  uint32_t* __restrict__ tot = bin_total + (size_t)cam * nb;
+  uint32_t* __restrict__ bs = bin_start + (size_t)cam * (nb + 1);
+  // thread t owns bins [t * per, (t + 1) * per): all of its totals are loaded in one batch
+  constexpr int kRegPer = 16;  // kept in registers up to 4 096 bins (640x480: 10 per thread)
+  const int per = (L.n_bins + kChunkThreads - 1) / kChunkThreads;
+  const int b_lo = threadIdx.x * per;
+  uint32_t held[kRegPer];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int j = 0; j < kRegPer; ++j) {
+    const int b = b_lo + j;
+    held[j] = (j < per && b < L.n_bins) ? __ldcg(tot + b) : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < kRegPer; ++j) mine += held[j];
+  for (int j = kRegPer; j < per; ++j)
+    if (b_lo + j < L.n_bins) mine += __ldcg(tot + b_lo + j);
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < kBinWarps ? s_scan[lane] : 0u;
+#pragma unroll
+    for (int d = 1; d < kBinWarps; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += o;
+    }
+    if (lane < kBinWarps) s_scan[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  uint32_t run = (warp ? s_scan[warp - 1] : 0u) + incl - mine;
+#pragma unroll
+  for (int j = 0; j < kRegPer; ++j) {
+    const int b = b_lo + j;
+    if (j < per && b < L.n_bins) {
+      bs[b] = run;
+      tot[b] = 0;
+      run += held[j];
+    }
+  }
+  for (int j = kRegPer; j < per; ++j) {
+    const int b = b_lo + j;
+    if (b < L.n_bins) {
+      const uint32_t v = __ldcg(tot + b);
+      bs[b] = run;
+      tot[b] = 0;
+      run += v;
+    }
+  }
+  if (threadIdx.x == kChunkThreads - 1) {
+    // bins beyond the last: the out-of-range bin and the end marker both start at the total
+    bs[L.n_bins] = run;
+    bs[nb] = run;
+  }
+}
 
-  int bin[kChunkSteps];
+__global__ void __launch_bounds__(kChunkThreads)
+k_bin_pass2(BinLayout L, const __grid_constant__ CamBatch B, BinTables T) {
+  PDL_PROLOGUE();
+  __shared__ __align__(16) uint32_t s_red[kBinWarps][2][kDigit];
+  __shared__ uint32_t s_wc[kBinWarps][kDigit];
+  __shared__ uint32_t s_base[kDigit + 1];
+  const int cam = blockIdx.y, chunk = blockIdx.x;
+  const int n_rows = B.n_chunks[cam];
+  if (chunk >= n_rows) return;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int b = threadIdx.x; b < kBinWarps * kDigit; b += blockDim.x) (&s_wc[0][0])[b] = 0;
+  // the in-range events of the camera, sorted by minor digit: n = sum of the table
+  const int n = (int)bin_bases(T.cnt_b + (size_t)cam * L.max_chunks * kDigit, n_rows, chunk, s_base, s_red);
+  if (chunk * kChunk >= n) return;
+  const double* __restrict__ it = B.it[cam];
+  const uint16_t* __restrict__ ik = B.ik[cam];
+  const uint8_t* __restrict__ im = B.im[cam];
+  int dma[kChunkSteps];
   uint32_t key[kChunkSteps], rank[kChunkSteps];
   double tt[kChunkSteps];
   const int wbase = chunk * kChunk + warp * (32 * kChunkSteps);
 #pragma unroll
   for (int k = 0; k < kChunkSteps; ++k) {
     const int i = wbase + k * 32 + lane;
-    bin[k] = -1;
+    dma[k] = -1;
     key[k] = 0;
     tt[k] = 0.0;
-    if (i < ev.n) {
-      const Ev e = load_event(ev, i);
-      bin[k] = bin_of(L, e.x, e.y);
-      key[k] = (uint32_t)((e.y % kTileH) * kTileW + (e.x % kTileW)) | ((uint32_t)e.p << kPolShift);
-      tt[k] = e.t;
+    if (i < n) {
+      dma[k] = im[i];
+      key[k] = ik[i];
+      tt[k] = it[i];
     }
   }
-  // position of this chunk's first event of every bin (independent loads, in flight during
-  // the ranking pass)
-  const uint32_t* cnt_row = counts + ((size_t)cam * L.max_chunks + chunk) * nb;
-#pragma unroll 4
-  for (int b = threadIdx.x; b < nb; b += blockDim.x)
-    s_base[b] = __ldg(bin_start + cam * (nb + 1) + b) + __ldg(cnt_row + b);
+#pragma unroll
+  for (int k = 0; k < kChunkSteps; ++k) rank[k] = bin_rank_step(s_wc[warp], dma[k], dma[k] >= 0, lt_mask);
   __syncthreads();
-
-  // Stable rank of every event among the events of its bin in this warp's slice.  A step's
-  // 32 events mostly fall into 32 different bins, where match.any is at its slowest, so the
-  // lanes first count themselves with a shared-memory atomic and only the lanes that share a
-  // bin with another lane of the step (count grew by more than one) sort themselves out.
-  uint32_t* my = s_wc + warp * nb;
+  bin_warp_prefix(s_wc);
+  __syncthreads();
+  double* __restrict__ bt = B.bt[cam];
+  uint16_t* __restrict__ bk = B.bk[cam];
 #pragma unroll
   for (int k = 0; k < kChunkSteps; ++k) {
-    const bool valid = bin[k] >= 0;
-    uint32_t before = 0;
-    if (valid) before = my[bin[k]];
-    __syncwarp();
-    if (valid) atomicAdd(&my[bin[k]], 1u);
-    __syncwarp();
-    const bool shared = valid && my[bin[k]] - before > 1;
-    const uint32_t sh = __ballot_sync(0xffffffffu, shared);
-    rank[k] = before;
-    if (shared) rank[k] += __popc(__match_any_sync(sh, bin[k]) & lt_mask);
-    __syncwarp();
-  }
-  __syncthreads();
-  // per-bin exclusive prefix over the 8 warps
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-    uint32_t run = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const uint32_t c = s_wc[w * nb + b];
-      s_wc[w * nb + b] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < kChunkSteps; ++k) {
-    if (bin[k] >= 0 && bin[k] < L.n_bins) {
-      const uint32_t pos = s_base[bin[k]] + my[bin[k]] + rank[k];
+    if (dma[k] >= 0) {
+      const uint32_t pos = s_base[dma[k]] + s_wc[warp][dma[k]] + rank[k];
       bt[pos] = tt[k];
       bk[pos] = (uint16_t)key[k];
     }
   }
 }
 
-static size_t scatter_smem_bytes(int n_bins) {
-  return ((size_t)n_bins + 1) * 9 * sizeof(uint32_t);
+// sensor sizes the two 7-bit digits cover
+int bin_configure(const BinLayout& L) {
+  return (L.tiles_x * kFine <= kDigit && L.tiles_y <= kDigit) ? 0 : -1;
 }
 
-int bin_configure(int n_bins) {
-  static SmemLimit lim = {};
-  const size_t bytes = scatter_smem_bytes(n_bins);
-  if (bytes > 200 * 1024) return -1;
-  return raise_dyn_smem(k_bin_scatter, bytes, &lim);
+int event_stage_alloc(const BinLayout& L, int n_cams, int cap, EventStageBuffers* E) {
+  const size_t nb = (size_t)L.n_bins + 1;
+  E->n_cams = n_cams;
+  const size_t tab = (size_t)n_cams * L.max_chunks * kDigit;
+#define ESA(call) do { if ((call) != cudaSuccess) return -1; } while (0)
+  ESA(cudaMalloc(&E->counts, 2 * tab * sizeof(uint32_t)));
+  ESA(cudaMemset(E->counts, 0, 2 * tab * sizeof(uint32_t)));
+  ESA(cudaMalloc(&E->bin_total, n_cams * nb * sizeof(uint32_t)));
+  ESA(cudaMemset(E->bin_total, 0, n_cams * nb * sizeof(uint32_t)));
+  ESA(cudaMalloc(&E->bin_start, n_cams * (nb + 1) * sizeof(uint32_t)));
+  ESA(cudaMemset(E->bin_start, 0, n_cams * (nb + 1) * sizeof(uint32_t)));
+  for (int c = 0; c < n_cams; ++c) {
+    ESA(cudaMalloc(&E->bt[c], (size_t)cap * sizeof(double)));
+    ESA(cudaMalloc(&E->bk[c], (size_t)cap * sizeof(uint16_t)));
+    ESA(cudaMalloc(&E->it[c], (size_t)cap * sizeof(double)));
+    ESA(cudaMalloc(&E->ik[c], (size_t)cap * sizeof(uint16_t)));
+    ESA(cudaMalloc(&E->im[c], (size_t)cap));
+  }
+#undef ESA
+  return 0;
+}
+
+void event_stage_free(EventStageBuffers* E) {
+  for (int c = 0; c < kMaxCams; ++c) {
+    cudaFree(E->bt[c]), cudaFree(E->bk[c]), cudaFree(E->it[c]), cudaFree(E->ik[c]), cudaFree(E->im[c]);
+    E->bt[c] = nullptr, E->bk[c] = nullptr, E->it[c] = nullptr, E->ik[c] = nullptr, E->im[c] = nullptr;
+  }
+  cudaFree(E->counts), cudaFree(E->bin_total), cudaFree(E->bin_start);
+  E->counts = E->bin_total = E->bin_start = nullptr;
+}
+
+// a window that was abandoned half way (reset) may have left totals behind
+void event_stage_clear(const BinLayout& L, const EventStageBuffers& E, cudaStream_t s) {
+  cudaMemsetAsync(E.bin_total, 0, (size_t)E.n_cams * (L.n_bins + 1) * sizeof(uint32_t), s);
 }
 
 void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const DevEvents* ev,
                        cudaStream_t s, int64_t* launches) {
-  const int nb = L.n_bins + 1;
   CamBatch cb;
   cb.n_cams = B.n_cams;
   int nc = 0;
@@ -511,19 +687,26 @@ void launch_bin_events(const BinLayout& L, const EventStageBuffers& B, const Dev
     cb.ev[c] = on ? ev[c] : DevEvents{};
     cb.bt[c] = on ? B.bt[c] : nullptr;
     cb.bk[c] = on ? B.bk[c] : nullptr;
+    cb.it[c] = on ? B.it[c] : nullptr;
+    cb.ik[c] = on ? B.ik[c] : nullptr;
+    cb.im[c] = on ? B.im[c] : nullptr;
     cb.n_chunks[c] = on ? (ev[c].n + kChunk - 1) / kChunk : 0;
     if (cb.n_chunks[c] > nc) nc = cb.n_chunks[c];
   }
+  BinTables T;
+  T.cnt_a = B.counts;
+  T.cnt_b = B.counts + (size_t)B.n_cams * L.max_chunks * kDigit;
+  const size_t agg = L.n_bins <= kAggBins ? (size_t)L.n_bins * sizeof(uint32_t) : 0;
   if (nc > 0) {
-    launch_pdl(k_bin_hist, dim3(nc, B.n_cams), dim3(kChunkThreads), nb * sizeof(uint32_t), s, L, cb, B.counts);
+    launch_pdl(k_bin_hist, dim3(nc, B.n_cams), dim3(kChunkThreads), agg, s, L, cb, T, B.bin_total);
     ++*launches;
   }
-  launch_pdl(k_bin_scan, dim3((nb + 31) / 32, B.n_cams), dim3(32 * kScanPhases), 0, s, L, cb, B.counts,
-             B.bin_total, B.bin_start, B.done_ctr);
+  // one more CTA per camera than there are chunks: it writes bin_start
+  launch_pdl(k_bin_pass1, dim3(nc + 1, B.n_cams), dim3(kChunkThreads), 2 * agg, s, L, cb, T, B.bin_total,
+             B.bin_start);
   ++*launches;
   if (nc > 0) {
-    launch_pdl(k_bin_scatter, dim3(nc, B.n_cams), dim3(kChunkThreads), scatter_smem_bytes(L.n_bins), s, L, cb,
-               B.counts, B.bin_start);
+    launch_pdl(k_bin_pass2, dim3(nc, B.n_cams), dim3(kChunkThreads), 0, s, L, cb, T);
     ++*launches;
   }
 }

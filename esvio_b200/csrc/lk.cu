@@ -65,29 +65,57 @@ static_assert(kMaxLevels * kTplWarps == kLkWarps, "two warps per level in the te
 
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
+// d = c + a.s16[0] * b.u8[0 | 2] + a.s16[1] * b.u8[1 | 3]
+__device__ __forceinline__ int dp2a_lo_su(unsigned a, unsigned b, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(unsigned a, unsigned b, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// cvRound of a float in [0, 2^22): adding 1.5 * 2^23 leaves the rounded integer (half to even,
+// the FADD's own rounding) in the low mantissa bits -- two 4-cycle ALU instructions instead of
+// an F2I on the conversion pipe, which sits on the Newton iteration's dependent chain
+__device__ __forceinline__ int cv_round_small(float v) {
+  return __float_as_int(v + 12582912.f) - 0x4B400000;
+}
+
 __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int& w01, int& w10,
                                                  int& w11) {
-  w00 = cv_round((1.f - a) * (1.f - b) * (float)(1 << kWBits));
-  w01 = cv_round(a * (1.f - b) * (float)(1 << kWBits));
-  w10 = cv_round((1.f - a) * b * (float)(1 << kWBits));
+  w00 = cv_round_small((1.f - a) * (1.f - b) * (float)(1 << kWBits));
+  w01 = cv_round_small(a * (1.f - b) * (float)(1 << kWBits));
+  w10 = cv_round_small((1.f - a) * b * (float)(1 << kWBits));
   w11 = (1 << kWBits) - w00 - w01 - w10;
 }
 
-struct LkShared {
+struct LkPatches {
   uint8_t I[kMaxLevels][kIP][kIP];      // template neighbourhoods of all levels
   short2 D[kMaxLevels][kDP][kDP];       // their Scharr derivatives
+};
+struct LkShared {
+  // The patches only live until the templates are built (phases 1-3), the search regions only
+  // from then on: they share their bytes, which takes the CTA from 34.7 to 24.7 KB -- four
+  // CTAs per SM instead of three next to the event-stage kernels.
+  union {
+    LkPatches P;
+    // search regions (current level / prefetched next level) as packed 2x2 neighbourhoods:
+    // Q[r][c] = J(r,c) | J(r,c+1) << 8 | J(r+1,c) << 16 | J(r+1,c+1) << 24
+    uint32_t Q[2][kJR][kQS];
+  };
   short Tw[kMaxLevels][kTplLen];        // templates: Iw, Ixw, Iyw per window pixel
   short Tx[kMaxLevels][kTplLen];
   short Ty[kMaxLevels][kTplLen];
   long long Apart[kMaxLevels][kTplWarps][3];  // per-warp sums of Ixw^2, Ixw*Iyw, Iyw^2
   int flag_win[kMaxLevels];             // 1: template window outside the image
-  // search regions (current level / prefetched next level) as packed 2x2 neighbourhoods:
-  // Q[r][c] = J(r,c) | J(r,c+1) << 8 | J(r+1,c) << 16 | J(r+1,c+1) << 24
-  uint32_t Q[2][kJR][kQS];
   longlong2 part[2][kNWarps];           // per-iteration partial sums (b1, b2) of the N-group warps
   float2 np[2];                         // result of a level, slot = Newton levels run so far & 1
   int st[2];
 };
+static_assert(sizeof(LkPatches) <= sizeof(uint32_t) * 2 * kJR * kQS, "patches fit under the search regions");
 
 // exact sum over the warp of one int32 per lane, as int64
 __device__ __forceinline__ long long warp_sum_exact(int v) {
@@ -104,20 +132,31 @@ __device__ __forceinline__ void bar_newton() { asm volatile("bar.sync 1, 128;" :
 // loads back to back (one trip to L2 for the lot), pairs each byte with the right-hand
 // neighbour's by a shuffle and packs it with the row below.
 template <int NW>
-__device__ __forceinline__ void stage_J(uint32_t (*Q)[kQS], const uint8_t* __restrict__ Jl, int w,
-                                        int h, int pitch, int rx0, int ry0, int wi) {
+__device__ __forceinline__ void stage_J_load(uint32_t (&col)[kJR / NW + 1], const uint8_t* __restrict__ Jl,
+                                             int w, int h, int pitch, int rx0, int ry0, int wi) {
   constexpr int kRows = kJR / NW;
-  const int lane = lane_id();
-  const int gx = reflect101_nb(rx0 + lane, w);
+  const int gx = reflect101_nb(rx0 + lane_id(), w);
   const int r0 = wi * kRows;
-  uint32_t col[kRows + 1];
 #pragma unroll
   for (int r = 0; r <= kRows; ++r)
     col[r] = __ldg(Jl + (size_t)reflect101_nb(ry0 + r0 + r, h) * pitch + gx);
+}
+template <int NW>
+__device__ __forceinline__ void stage_J_store(uint32_t (*Q)[kQS], uint32_t (&col)[kJR / NW + 1], int wi) {
+  constexpr int kRows = kJR / NW;
+  const int lane = lane_id();
+  const int r0 = wi * kRows;
 #pragma unroll
   for (int r = 0; r <= kRows; ++r) col[r] |= __shfl_down_sync(0xffffffffu, col[r], 1) << 8;
 #pragma unroll
   for (int r = 0; r < kRows; ++r) Q[r0 + r][lane] = col[r] | (col[r + 1] << 16);
+}
+template <int NW>
+__device__ __forceinline__ void stage_J(uint32_t (*Q)[kQS], const uint8_t* __restrict__ Jl, int w,
+                                        int h, int pitch, int rx0, int ry0, int wi) {
+  uint32_t col[kJR / NW + 1];
+  stage_J_load<NW>(col, Jl, w, h, pitch, rx0, ry0, wi);
+  stage_J_store<NW>(Q, col, wi);
 }
 
 struct Region {
@@ -164,6 +203,7 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
   __syncthreads();  // previous use of S is over
   LK_CLK(0);
 
+  uint32_t top_col[kJR / kLkWarps + 1];
   // ---- phase 1: ONE batch of loads: the intensity patches of all levels (they depend on the
   // point only, not on the flow) and the search region of the top level around `np`.
   // Intensities reflect-101 outside the image like the border buildOpticalFlowPyramid adds.
@@ -185,13 +225,15 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
                        reflect101_nb(ipx - 1 + c, w));
       }
     }
+    // the top level's search region travels with them, but lands in shared memory only after
+    // phase 3: until then the patches occupy those bytes
     if (rc.level >= 0)
-      stage_J<kLkWarps>(S.Q[0], J + pd.off[top], pd.w[top], pd.h[top], pd.pitch[top], rc.rx0,
-                        rc.ry0, warp);
+      stage_J_load<kLkWarps>(top_col, J + pd.off[top], pd.w[top], pd.h[top], pd.pitch[top], rc.rx0,
+                             rc.ry0, warp);
 #pragma unroll
     for (int q = 0; q < kPerThread; ++q) {
       const int i = tid + q * kLkThreads;
-      if (i < nlev * kIP * kIP) (&S.I[0][0][0])[i] = v[q];
+      if (i < nlev * kIP * kIP) (&S.P.I[0][0][0])[i] = v[q];
     }
   }
   __syncthreads();
@@ -207,14 +249,14 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
     const int gx = ipx + c, gy = ipy + r;
     short2 d = make_short2(0, 0);
     if (gx >= 0 && gx < pd.w[L] && gy >= 0 && gy < pd.h[L]) {
-      const uint8_t *up = S.I[L][r], *mid = S.I[L][r + 1], *dn = S.I[L][r + 2];
+      const uint8_t *up = S.P.I[L][r], *mid = S.P.I[L][r + 1], *dn = S.P.I[L][r + 2];
       const int t0l = (up[c] + dn[c]) * 3 + mid[c] * 10;
       const int t0r = (up[c + 2] + dn[c + 2]) * 3 + mid[c + 2] * 10;
       const int t1l = dn[c] - up[c], t1m = dn[c + 1] - up[c + 1], t1r = dn[c + 2] - up[c + 2];
       d.x = (short)(t0r - t0l);
       d.y = (short)((t1r + t1l) * 3 + t1m * 10);
     }
-    S.D[L][r][c] = d;
+    S.P.D[L][r][c] = d;
   }
   __syncthreads();
   LK_CLK(2);
@@ -238,11 +280,11 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
           int iv = 0, ix = 0, iy = 0;
           if (kk < kWin * kWin) {
             const int y = kk / kWin, x = kk - y * kWin;
-            iv = descale(S.I[L][y + 1][x + 1] * iw00 + S.I[L][y + 1][x + 2] * iw01 +
-                             S.I[L][y + 2][x + 1] * iw10 + S.I[L][y + 2][x + 2] * iw11,
+            iv = descale(S.P.I[L][y + 1][x + 1] * iw00 + S.P.I[L][y + 1][x + 2] * iw01 +
+                             S.P.I[L][y + 2][x + 1] * iw10 + S.P.I[L][y + 2][x + 2] * iw11,
                          kWBits - 5);
-            const short2 d00 = S.D[L][y][x], d01 = S.D[L][y][x + 1], d10 = S.D[L][y + 1][x],
-                         d11 = S.D[L][y + 1][x + 1];
+            const short2 d00 = S.P.D[L][y][x], d01 = S.P.D[L][y][x + 1], d10 = S.P.D[L][y + 1][x],
+                         d11 = S.P.D[L][y + 1][x + 1];
             ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, kWBits);
             iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, kWBits);
             s11 += ix * ix;
@@ -263,6 +305,8 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
       }
     }
   }
+  __syncthreads();  // templates built: the patches are dead, their bytes become the search regions
+  if (rc.level >= 0) stage_J_store<kLkWarps>(S.Q[0], top_col, warp);
   __syncthreads();
   LK_CLK(3);
 
@@ -356,24 +400,26 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
         const float a = npx - (float)inx, b = npy - (float)iny;
         int iw00, iw01, iw10, iw11;
         bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-        // sum_i pix_i * w_i = 128 * dp4a(pix, w >> 7) + dp4a(pix, w & 127); w <= 2^14
-        const unsigned wh = (unsigned)(iw00 >> 7) | ((unsigned)(iw01 >> 7) << 8) |
-                            ((unsigned)(iw10 >> 7) << 16) | ((unsigned)(iw11 >> 7) << 24);
-        const unsigned wl = (unsigned)(iw00 & 127) | ((unsigned)(iw01 & 127) << 8) |
-                            ((unsigned)(iw10 & 127) << 16) | ((unsigned)(iw11 & 127) << 24);
+        // sum_i pix_i * w_i over the packed 2x2 neighbourhood: two dot products of SIGNED 16-bit
+        // weights with unsigned 8-bit pixels (top row, then bottom row).  iw11 is what is left
+        // of 2^14 after three roundings and is -1 when all three round up (a * b < 3e-5, about
+        // 5 iterations in 10^5): OpenCV multiplies by that -1, int in its scalar code and
+        // int16 in its SIMD code
+        const unsigned wa = ((unsigned)iw00 & 0xffffu) | ((unsigned)iw01 << 16);
+        const unsigned wb = ((unsigned)iw10 & 0xffffu) | ((unsigned)iw11 << 16);
         const uint32_t* base = &S.Q[cur][iny - ry0][inx - rx0];
         int sb1 = 0, sb2 = 0;
 #pragma unroll
         for (int j = 0; j < kPxN; ++j) {
           const unsigned q = base[joff[j]];
-          const unsigned v = (__dp4a(q, wh, 0u) << 7) + __dp4a(q, wl, 1u << (kWBits - 5 - 1));
-          const int diff = (int)(v >> (kWBits - 5)) - Iw[j];
+          const int v = dp2a_hi_su(wb, q, dp2a_lo_su(wa, q, 1 << (kWBits - 5 - 1)));
+          const int diff = (v >> (kWBits - 5)) - Iw[j];
           sb1 += diff * Dx[j];
           sb2 += diff * Dy[j];
         }
         const long long w1 = warp_sum_exact(sb1), w2 = warp_sum_exact(sb2);
         longlong2* part = S.part[it & 1];
-        if (lane == 0) part[warp] = make_longlong2(w1, w2);
+        part[warp] = make_longlong2(w1, w2);  // every lane, the same value: no divergent branch
         bar_newton();
         long long t1 = 0, t2 = 0;
 #pragma unroll

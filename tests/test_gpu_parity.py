@@ -242,6 +242,54 @@ def test_lk_matches_cv2_golden(fe_mod, ora, golden_lk, case):
     fe.close()
 
 
+def _lk_weights(px, py):
+    """The 14-bit bilinear weights calcOpticalFlowPyrLK derives from a window origin, in float32."""
+    f = np.float32
+    ox, oy = f(px) - f(10.0), f(py) - f(10.0)
+    a, b = f(ox - np.floor(ox)), f(oy - np.floor(oy))
+    one, sc = f(1.0), f(16384.0)
+    w00 = int(np.rint(f(f(f(one - a) * f(one - b)) * sc)))
+    w01 = int(np.rint(f(f(a * f(one - b)) * sc)))
+    w10 = int(np.rint(f(f(f(one - a) * b) * sc)))
+    return w00, w01, w10, 16384 - w00 - w01 - w10
+
+
+def test_lk_with_a_negative_fourth_weight(fe_mod, ora):
+    """calcOpticalFlowPyrLK's fourth bilinear weight is what the three rounded ones leave of 2^14
+    -- and that is -1 when all three round up (sub-pixel offsets a, b with a * b < 3e-5; about
+    5 Newton iterations in 10^5 on real tracks).  OpenCV multiplies by the -1; a kernel that
+    packs the weights as unsigned fields does not.  Points and initial flows are placed on
+    such offsets (maxLevel 0, so the first iteration of every point uses them) and compared
+    with the oracle's port, which is pinned on cv2."""
+    W, H = 346, 260
+    fe, _ = _mk(fe_mod, W, H)
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:H, 0:W]
+    a = (127 + 60 * np.sin(xx / 7.0) * np.cos(yy / 5.0) + rng.integers(-20, 21, (H, W))).clip(0, 255).astype(np.uint8)
+    b = np.roll(a, (1, 2), axis=(0, 1))
+    pts, init = [], []
+    for _ in range(20000):
+        x, y = rng.integers(30, W - 30), rng.integers(30, H - 30)
+        fx, fy = np.float32(x + rng.uniform(2e-5, 6e-5)), np.float32(y + rng.uniform(2e-5, 6e-5))
+        if _lk_weights(fx, fy)[3] < 0:
+            pts.append((fx, fy))
+            init.append((fx + np.float32(2.0), fy + np.float32(1.0)))
+        if len(pts) == 300:
+            break
+    assert len(pts) >= 100, len(pts)
+    pts, init = np.array(pts, np.float32), np.array(init, np.float32)
+    n_neg_init = sum(_lk_weights(x, y)[3] < 0 for x, y in init)
+    assert n_neg_init >= 50, n_neg_init   # the search window starts on such an offset too
+    got, st = fe.stage_lk(a, b, pts, init.copy(), 0)
+    ref, st_ref = ora.calc_optical_flow_pyr_lk(a, b, pts, init.copy(), max_level=0)
+    assert np.array_equal(st.astype(bool), st_ref.astype(bool))
+    ok = st_ref.astype(bool)
+    assert ok.sum() >= 0.8 * len(pts)
+    d = np.abs(got[ok] - ref[ok]).max(axis=1)
+    assert d.max() <= LK_TOL, np.sort(d)[-5:]
+    fe.close()
+
+
 # (W, H, rate, min_dist, max_cnt): config/esvio + esio (150 / 10), esvio_DSEC (100 / 30),
 # esvio_ecmd (200 / 20), esio_DSEC (300 / 10), and 20 / 30 at 346x260 (SURVEY.md 5.6).  min_dist
 # > 15 takes the kernel's other disc-fill path, max_cnt > 256 its serial mask walk.
