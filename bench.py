@@ -494,11 +494,12 @@ def batched_leg(torch, dev, local, workload, S, K, Wm, flush):
     cfg = dict(cfg, device_id=local, max_events_per_window=max(n_per_cam + 64, 1024))
     grp = frontend.EventFrontEndGroup(cfg, S)
     m0 = grp.member(0)
-    nb_w = Wm + K
+    n_alone = 6   # synchronous windows after the pipelined pass: the same launch with the GPU to itself
+    nb_w = Wm + K + n_alone
     bw, n_ev, held = [], 0.0, []
     for i in range(S):
         ws = gen_windows(w, 100 + i, nb_w)
-        n_ev += n_events(ws[Wm:])
+        n_ev += n_events(ws[Wm:Wm + K])
         row = []
         for L, R, t in ws:
             a, b = frontend.DeviceEvents(m0, L), frontend.DeviceEvents(m0, R)
@@ -534,6 +535,12 @@ def batched_leg(torch, dev, local, workload, S, K, Wm, flush):
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     k1 = float(np.mean(k1_ms))
+    k1_alone = []
+    for k in range(Wm + K, nb_w):
+        gsub(k)
+        grp.wait(unpack=False)
+        k1_alone.append(grp.sae_ts_ms())
+    k1_alone = float(np.mean(k1_alone[2:])) if len(k1_alone) > 2 else None
     alg = S * 2 * 17 * w["width"] * w["height"] + 45 * n_ev / K
     peak, peak_src = peaks()
     rec = {"streams": S, "steps": K, "config": config_of(workload),
@@ -546,13 +553,17 @@ def batched_leg(torch, dev, local, workload, S, K, Wm, flush):
             "traffic": ncu_traffic(f"{workload}_x{S}"),
             "algorithmic_bytes_per_launch": int(alg), "kernel_ms": k1,
             "share_of_step": k1 / (wall_ms / K), "peak_source": peak_src,
+            "kernel_ms_alone": k1_alone,
+            "frac_alone": (alg / (k1_alone * 1e-3) / 1e9 / peak) if k1_alone else None,
             "launch_covers": f"{2 * S} cameras = {S} stereo streams of {workload} in one esvio_fe_group",
             "note": "achieved = algorithmic bytes (SURVEY.md 8d: 17*W*H per camera + 45 B/event, "
                     "summed over the cameras of the launch) / CUDA-event time of the launch, "
                     "measured inside the pipeline (the LK / selection kernels of two other "
-                    "windows x S streams share the SMs); the group's SAE state (S x 19.7 MB at "
-                    "640x480) exceeds what stays in L2 next to the event buffers, so the launch "
-                    "streams from HBM"}
+                    "windows x S streams share the SMs: k_lk holds 64 registers x 256 threads x 4 "
+                    "CTAs = the whole register file of an SM, so this launch gets 4 of its 14 CTAs "
+                    "per SM there); *_alone = the same launch in synchronous group windows right "
+                    "after; the group's SAE state (S x 19.7 MB at 640x480) exceeds L2, so the "
+                    "launch streams from HBM (traffic: whole 16 KB tiles, profiles/r2_k1_l2_policy.txt)"}
     for a in held:
         a.free()
     grp.close()

@@ -205,6 +205,10 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// CAUTION: a plain load through a `const T* __restrict__` parameter compiles to ld.global.nc,
+// which nvcc may hoist ABOVE griddepcontrol.wait (it did in k_gftt_pick): whatever the
+// predecessor kernel produces must be read with __ldcg / through a non-const pointer.
+// tests/test_sass_pdl.py scans the SASS of every kernel for a global load in front of ACQBULK.
 #define PDL_PROLOGUE()       \
   do {                       \
     pdl_launch_dependents(); \
@@ -394,14 +398,12 @@ struct GfttBuffers {
   float* eig;                    // cornerMinEigenVal                        [H][W]
   uint32_t* blocked;             // 1 bit per pixel: mask == 0               [H][(W+31)/32]
   float* thr;                    // maxVal * qualityLevel
-  unsigned long long* keys;      // float_order(eig) << 32 | pixel, 0 = none [H*W]
-  unsigned long long* keys_sorted;
-  void* sort_temp;
-  size_t sort_temp_bytes;
+  unsigned long long* keys;      // float_order(eig) << 32 | pixel of the candidates, compacted [H*W]
+  unsigned long long* keys_sorted;  // the same, best first, then a zero key [H*W]
+  int* n_cand;                   // number of candidates of the frame
   float2* out_xy;                // stage entry: picked corners              [H*W] (capacity)
   int* out_n;
 };
-size_t gftt_sort_temp_bytes(int n);
 void launch_gftt_eig(const GfttBuffers& G, const uint8_t* img, int pitch, int W, int H,
                      cudaStream_t s, int64_t* launches);
 void launch_gftt_thr(const GfttBuffers& G, int W, int H, bool use_mask, cudaStream_t s,

@@ -1223,7 +1223,6 @@ FE_API int esvio_fe_track_submit_external(esvio_fe* fe, double cur_time, int32_t
 static int ensure_gftt(esvio_fe* fe) {
   if (fe->gftt_block) return ESVIO_FE_OK;
   const size_t N = fe->npx, words = (size_t)fe->H * ((fe->W + 31) / 32);
-  const size_t temp = gftt_sort_temp_bytes((int)N);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -1232,7 +1231,7 @@ static int ensure_gftt(esvio_fe* fe) {
   };
   const size_t o_cov = take(3 * N * 4), o_eig = take(N * 4), o_blk = take(words * 4),
                o_thr = take(256), o_keys = take(N * 8), o_sorted = take(N * 8),
-               o_temp = take(temp), o_xy = take(N * 8), o_n = take(256);
+               o_cnt = take(256), o_xy = take(N * 8), o_n = take(256);
   uint8_t* base = nullptr;
   CU(cudaMalloc(&base, off));
   CU(cudaMemset(base, 0, off));
@@ -1243,8 +1242,7 @@ static int ensure_gftt(esvio_fe* fe) {
   G.thr = (float*)(base + o_thr);
   G.keys = (unsigned long long*)(base + o_keys);
   G.keys_sorted = (unsigned long long*)(base + o_sorted);
-  G.sort_temp = base + o_temp;
-  G.sort_temp_bytes = temp;
+  G.n_cand = (int*)(base + o_cnt);
   G.out_xy = (float2*)(base + o_xy);
   G.out_n = (int*)(base + o_n);
   fe->gftt_block = base;

@@ -8,11 +8,10 @@
 //   k_gftt_cov   Sobel derivatives + their three products per pixel            (W x H threads)
 //   k_gftt_eig   3x3 box sums as RUNNING f64 column sums + minimum eigenvalue    (one thread per column)
 //   k_gftt_thr   max of the eigenvalues under the mask -> threshold              (one CTA)
-//   k_gftt_keys  thresholded 3x3 local maxima -> 64-bit sort keys                (W x H threads)
-//   radix sort of the keys, descending (value, then pixel index)                 (cub)
+//   k_gftt_keys  thresholded 3x3 local maxima -> compacted 64-bit sort keys       (W x H threads)
+//   k_gftt_rank  descending order (value, then pixel index) by counting: the rank of a
+//                candidate is the number of keys above it                        (one thread per candidate)
 //   k_gftt_pick  greedy minimum-distance pick in that order                      (select.cu)
-#include <cub/device/device_radix_sort.cuh>
-
 #include "common.cuh"
 
 namespace esvio {
@@ -115,8 +114,9 @@ __device__ __forceinline__ bool gftt_blocked(const uint32_t* __restrict__ blocke
 // minMaxLoc(eig, 0, &maxVal, 0, 0, mask); threshold = (float)(maxVal * qualityLevel)
 __global__ void __launch_bounds__(1024)
 k_gftt_thr(const float* __restrict__ eig, int W, int H, const uint32_t* __restrict__ blocked,
-           double quality, float* __restrict__ thr_out) {
+           double quality, float* __restrict__ thr_out, int* __restrict__ n_cand) {
   PDL_PROLOGUE();
+  if (threadIdx.x == 0) *n_cand = 0;  // k_gftt_keys of this frame counts from here
   __shared__ uint32_t s_max[32];
   const int words = (W + 31) / 32;
   uint32_t best = 0;  // below every float_order() value: "no pixel seen"
@@ -137,18 +137,22 @@ k_gftt_thr(const float* __restrict__ eig, int W, int H, const uint32_t* __restri
 }
 
 // threshold(THRESH_TOZERO) + dilate(3x3) + "val != 0 && val == dilated && mask": every such
-// pixel becomes the key (float_order(val) << 32 | pixel index), everything else key 0; the keys
-// sorted descending are featureselect.cpp's greaterThanPtr order (value, then address).
+// pixel becomes the key (float_order(val) << 32 | pixel index); the keys in descending order are
+// featureselect.cpp's greaterThanPtr order (value, then address).  A frame has a few thousand
+// candidates among its W x H pixels, so they are compacted here (a CTA reserves its slice of
+// the list with one atomic; the order inside the list does not matter) and only they are ordered.
 __global__ void __launch_bounds__(256)
 k_gftt_keys(const float* __restrict__ eig, int W, int H, const uint32_t* __restrict__ blocked,
-            const float* __restrict__ thr_ptr, unsigned long long* __restrict__ keys) {
+            const float* __restrict__ thr_ptr, unsigned long long* __restrict__ keys,
+            int* __restrict__ n_cand) {
   PDL_PROLOGUE();
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= W || y >= H) return;
-  const size_t i = (size_t)y * W + x;
+  __shared__ int s_wc[8], s_base;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + warp;
   unsigned long long key = 0;
   if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
-    const float thr = *thr_ptr;
+    const size_t i = (size_t)y * W + x;
+    const float thr = __ldcg(thr_ptr);
     const float v = eig[i];
     if (v > thr && v != 0.f && !gftt_blocked(blocked, (W + 31) / 32, x, y)) {
       bool is_max = true;
@@ -163,28 +167,64 @@ k_gftt_keys(const float* __restrict__ eig, int W, int H, const uint32_t* __restr
       if (is_max) key = ((unsigned long long)float_order(v) << 32) | (unsigned long long)i;
     }
   }
-  keys[i] = key;
+  const uint32_t m = __ballot_sync(0xffffffffu, key != 0);
+  if (lane == 0) s_wc[warp] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int c = s_wc[w];
+      s_wc[w] = total;
+      total += c;
+    }
+    s_base = total ? atomicAdd(n_cand, total) : 0;
+  }
+  __syncthreads();
+  if (key) keys[s_base + s_wc[warp] + __popc(m & ((1u << lane) - 1u))] = key;
 }
 
-size_t gftt_sort_temp_bytes(int n) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortKeysDescending(nullptr, bytes, (const unsigned long long*)nullptr,
-                                           (unsigned long long*)nullptr, n);
-  return bytes;
+// keys[0 .. *n_cand) -> sorted[rank], rank = number of keys greater than mine (the keys are
+// distinct: the pixel index is part of them); sorted[*n_cand] = 0 ends the list for k_gftt_pick.
+// All keys pass through shared memory in tiles; n^2 / 2 comparisons are ~10 us for the few
+// thousand candidates of a frame (a 640x480 noise image with 77 000 maxima takes ~1 ms).
+constexpr int kRankTile = 2048;
+__global__ void __launch_bounds__(256)
+k_gftt_rank(const unsigned long long* __restrict__ keys, const int* __restrict__ n_cand,
+            unsigned long long* __restrict__ sorted, int capacity) {
+  PDL_PROLOGUE();
+  __shared__ unsigned long long s_tile[kRankTile];
+  const int n = min(__ldcg(n_cand), capacity);  // not ld.global.nc: see k_gftt_pick
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n < capacity) sorted[n] = 0ull;
+  const int first = blockIdx.x * 256;
+  if (first >= n) return;
+  const int i = first + threadIdx.x;
+  const unsigned long long mine = i < n ? keys[i] : ~0ull;
+  int rank = 0;
+  for (int t0 = 0; t0 < n; t0 += kRankTile) {
+    const int cnt = min(kRankTile, n - t0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += 256) s_tile[j] = keys[t0 + j];
+    __syncthreads();
+    int j = 0;
+    for (; j + 4 <= cnt; j += 4)
+      rank += (s_tile[j] > mine) + (s_tile[j + 1] > mine) + (s_tile[j + 2] > mine) + (s_tile[j + 3] > mine);
+    for (; j < cnt; ++j) rank += s_tile[j] > mine;
+  }
+  if (i < n) sorted[rank] = mine;
 }
 
-// eig + thr (+ mask) -> keys_sorted[W*H]: candidate corners first, best first
+// eig + thr (+ mask) -> keys_sorted: the candidate corners, best first, then a zero key
 int launch_gftt_candidates(const GfttBuffers& G, int W, int H, bool use_mask, cudaStream_t s,
                            int64_t* launches) {
   const dim3 grid((W + 31) / 32, (H + 7) / 8);
   launch_pdl(k_gftt_keys, grid, dim3(256), 0, s, (const float*)G.eig, W, H,
              use_mask ? (const uint32_t*)G.blocked : (const uint32_t*)nullptr,
-             (const float*)G.thr, G.keys);
-  size_t bytes = G.sort_temp_bytes;
-  const cudaError_t e = cub::DeviceRadixSort::SortKeysDescending(
-      G.sort_temp, bytes, (const unsigned long long*)G.keys, G.keys_sorted, W * H, 0, 64, s);
-  *launches += 2;  // + the radix sort (its passes are library launches, counted as one)
-  return e == cudaSuccess ? 0 : -1;
+             (const float*)G.thr, G.keys, G.n_cand);
+  launch_pdl(k_gftt_rank, dim3((W * H + 255) / 256), dim3(256), 0, s, (const unsigned long long*)G.keys,
+             (const int*)G.n_cand, G.keys_sorted, W * H);
+  *launches += 2;
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
 void launch_gftt_eig(const GfttBuffers& G, const uint8_t* img, int pitch, int W, int H,
@@ -199,7 +239,7 @@ void launch_gftt_eig(const GfttBuffers& G, const uint8_t* img, int pitch, int W,
 void launch_gftt_thr(const GfttBuffers& G, int W, int H, bool use_mask, cudaStream_t s,
                      int64_t* launches) {
   launch_pdl(k_gftt_thr, dim3(1), dim3(1024), 0, s, (const float*)G.eig, W, H,
-             use_mask ? (const uint32_t*)G.blocked : (const uint32_t*)nullptr, 0.01, G.thr);
+             use_mask ? (const uint32_t*)G.blocked : (const uint32_t*)nullptr, 0.01, G.thr, G.n_cand);
   ++*launches;
 }
 

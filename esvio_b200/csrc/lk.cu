@@ -492,7 +492,7 @@ k_lk(const __grid_constant__ PyrDesc pd, const uint8_t* __restrict__ I, const ui
   PDL_PROLOGUE();
   __shared__ __align__(16) LkShared S;
   const int k = blockIdx.x;
-  if (k >= *n_ptr) return;
+  if (k >= __ldcg(n_ptr)) return;  // produced by the kernel before: never as ld.global.nc (see k_gftt_pick)
   const float2 p0 = prev_pts[k];
   float2 init = make_float2(0.f, 0.f);
   if (use_init) init = next_pts[k];

@@ -755,7 +755,8 @@ void launch_image_set_mask(const TrackParams& P, const TrackBuffers& B, const Gf
 template <bool TRACKS>
 __global__ void __launch_bounds__(1024)
 k_gftt_pick(TrackParams P, TrackBuffers B, int snap_slot, const unsigned long long* __restrict__ keys,
-            int n_keys, int W, int max_corners, float md2, int spaced, float2* __restrict__ out_xy,
+            const int* __restrict__ n_cand, int capacity, int W, int max_corners, float md2, int spaced,
+            float2* __restrict__ out_xy,
             int* __restrict__ out_n) {
   PDL_PROLOGUE();
   __shared__ int s_warp[33];
@@ -766,6 +767,11 @@ k_gftt_pick(TrackParams P, TrackBuffers B, int snap_slot, const unsigned long lo
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   const int kept = TRACKS ? st->n_cur : 0;
   // stage form: max_corners <= 0 = unlimited, which the spaced pass serves up to kMaxCnt
+  // the frame's candidates (k_gftt_rank sorted exactly these).  __ldcg, not a plain load through
+  // the const __restrict__ pointer: nvcc turns that into ld.global.nc and is then free to hoist it
+  // above griddepcontrol.wait, i.e. to read the count before k_gftt_keys has produced it
+  // (tests/test_sass_pdl.py checks every kernel for this)
+  const int n_keys = min(__ldcg(n_cand), capacity);
   int want = TRACKS ? P.max_cnt - kept : (max_corners > 0 ? max_corners : n_keys);
   if (spaced && want > kMaxCnt) want = kMaxCnt;  // capacity of s_acc (the ABI refuses more)
   if (tid == 0) s_found = 0, s_end = 0;
@@ -861,7 +867,7 @@ void launch_gftt_pick_tracks(const TrackParams& P, const TrackBuffers& B, const 
                              int snap_slot, cudaStream_t s, int64_t* launches) {
   const float md = (float)P.min_dist;
   launch_pdl(k_gftt_pick<true>, dim3(1), dim3(1024), 0, s, P, B, snap_slot,
-             (const unsigned long long*)G.keys_sorted, P.W * P.H, P.W, 0, md * md,
+             (const unsigned long long*)G.keys_sorted, (const int*)G.n_cand, P.W * P.H, P.W, 0, md * md,
              P.min_dist > 1 ? 1 : 0, (float2*)nullptr, (int*)nullptr);  // distance 1: distinct
                                                                           // pixels never clash
   ++*launches;
@@ -872,7 +878,7 @@ void launch_gftt_pick_stage(const GfttBuffers& G, int W, int H, int max_corners,
   TrackParams P{};
   TrackBuffers B{};
   launch_pdl(k_gftt_pick<false>, dim3(1), dim3(1024), 0, s, P, B, -1,
-             (const unsigned long long*)G.keys_sorted, W * H, W, max_corners,
+             (const unsigned long long*)G.keys_sorted, (const int*)G.n_cand, W * H, W, max_corners,
              (float)(min_distance * min_distance), min_distance > 1.0 ? 1 : 0, G.out_xy, G.out_n);
   ++*launches;
 }
