@@ -12,7 +12,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libesvio_fe.so")
+LIB_PATH = os.environ.get("ESVIO_FE_LIB") or os.path.join(CSRC, "libesvio_fe.so")  # override: instrumented scratch builds
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "esvio_fe.h")
 
 NUM_STAGES = 9

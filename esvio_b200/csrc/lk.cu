@@ -48,9 +48,8 @@ extern "C" __attribute__((visibility("default"))) int esvio_dbg_lk_clocks(long l
 constexpr int kWBits = 14;
 constexpr int kLkThreads = 256;
 constexpr int kLkWarps = kLkThreads / 32;
-constexpr int kNThreads = 128;                     // Newton group: warps 0-3
-constexpr int kNWarps = kNThreads / 32;
-constexpr int kPxN = (kWin * kWin + kNThreads - 1) / kNThreads;  // 4 window pixels per thread
+constexpr int kMaxNWarps = 4;                      // Newton group: warps 0 .. NW-1, NW = 1, 2 or 4
+constexpr int kSFirst = 4, kSWarps = 4;            // staging group: warps 4-7
 constexpr int kTplWarps = 2;                       // warps per level in the template phase
 constexpr int kPxT = (kWin * kWin + 32 * kTplWarps - 1) / (32 * kTplWarps);  // 7
 constexpr int kTplLen = 32 * kTplWarps * kPxT;     // 448 template slots per level
@@ -111,7 +110,7 @@ struct LkShared {
   short Ty[kMaxLevels][kTplLen];
   long long Apart[kMaxLevels][kTplWarps][3];  // per-warp sums of Ixw^2, Ixw*Iyw, Iyw^2
   int flag_win[kMaxLevels];             // 1: template window outside the image
-  longlong2 part[2][kNWarps];           // per-iteration partial sums (b1, b2) of the N-group warps
+  longlong2 part[2][kMaxNWarps];           // per-iteration partial sums (b1, b2) of the N-group warps
   float2 np[2];                         // result of a level, slot = Newton levels run so far & 1
   int st[2];
 };
@@ -124,8 +123,12 @@ __device__ __forceinline__ long long warp_sum_exact(int v) {
   return ((long long)hi << 16) + (long long)lo;
 }
 
-// barrier of the 128 threads of the N group (barrier 0 is __syncthreads of the whole CTA)
-__device__ __forceinline__ void bar_newton() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// barrier of the NW warps of the N group (barrier 0 is __syncthreads of the whole CTA)
+template <int NW>
+__device__ __forceinline__ void bar_newton() {
+  if (NW == 1) __syncwarp();
+  else asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory");
+}
 
 // Stage the kJR x kJR search region with origin (rx0, ry0) of one level of J into Q.  Warp
 // `wi` of NW cooperating warps owns kJR / NW rows: lane = column; every lane issues its row
@@ -181,6 +184,7 @@ __device__ __forceinline__ Region region_around(int level, int w, int h, float p
 
 // One calcOpticalFlowPyrLK call for one point, run by the whole CTA.  Every thread returns
 // the same (np, status).
+template <int NW>
 __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restrict__ I,
                          const uint8_t* __restrict__ J, float2 p0, float2 init, int use_init,
                          int top, float2& np_out, int& st_out, int clk_call = 0) {
@@ -188,6 +192,8 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
   const float half = (float)kHalfWin;
   const float flt_scale = 1.f / (float)(1 << 20);
   const int nlev = top + 1;
+  constexpr int kNThreads = 32 * NW;
+  constexpr int kPxN = (kWin * kWin + kNThreads - 1) / kNThreads;  // window pixels per thread: 14, 7 or 4
   const bool n_group = tid < kNThreads;
 
   // position at the top level (OpenCV: nextPt = prevPt, or the initial flow, scaled)
@@ -363,12 +369,11 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
     if (level > 0)
       rn = region_around(level - 1, pd.w[level - 1], pd.h[level - 1], 2.f * np.x, 2.f * np.y);
     const int slot = n_newton & 1;
-    if (!n_group) {
+    if (warp >= kSFirst) {
       if (rn.level >= 0)
-        stage_J<kLkWarps - kNWarps>(S.Q[cur ^ 1], J + pd.off[level - 1], pd.w[level - 1],
-                                    pd.h[level - 1], pd.pitch[level - 1], rn.rx0, rn.ry0,
-                                    warp - kNWarps);
-    } else {
+        stage_J<kSWarps>(S.Q[cur ^ 1], J + pd.off[level - 1], pd.w[level - 1], pd.h[level - 1],
+                         pd.pitch[level - 1], rn.rx0, rn.ry0, warp - kSFirst);
+    } else if (n_group) {
       int Iw[kPxN], Dx[kPxN], Dy[kPxN];
 #pragma unroll
       for (int j = 0; j < kPxN; ++j) {
@@ -393,9 +398,9 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
           // the window walked out of the staged region (rare): the N group re-stages it
           rx0 = inx - kJM;
           ry0 = iny - kJM;
-          bar_newton();  // everybody is done reading the old region
-          stage_J<kNWarps>(S.Q[cur], Jl, w, h, pitch, rx0, ry0, warp);
-          bar_newton();
+          bar_newton<NW>();  // everybody is done reading the old region
+          stage_J<NW>(S.Q[cur], Jl, w, h, pitch, rx0, ry0, warp);
+          bar_newton<NW>();
         }
         const float a = npx - (float)inx, b = npy - (float)iny;
         int iw00, iw01, iw10, iw11;
@@ -418,15 +423,18 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
           sb2 += diff * Dy[j];
         }
         const long long w1 = warp_sum_exact(sb1), w2 = warp_sum_exact(sb2);
-        longlong2* part = S.part[it & 1];
-        part[warp] = make_longlong2(w1, w2);  // every lane, the same value: no divergent branch
-        bar_newton();
-        long long t1 = 0, t2 = 0;
+        long long t1 = w1, t2 = w2;
+        if (NW > 1) {
+          longlong2* part = S.part[it & 1];
+          part[warp] = make_longlong2(w1, w2);  // every lane, the same value: no divergent branch
+          bar_newton<NW>();
+          t1 = 0, t2 = 0;
 #pragma unroll
-        for (int q = 0; q < kNWarps; ++q) {
-          const longlong2 p = part[q];
-          t1 += p.x;
-          t2 += p.y;
+          for (int q = 0; q < NW; ++q) {
+            const longlong2 p = part[q];
+            t1 += p.x;
+            t2 += p.y;
+          }
         }
         // the exact totals, rounded to float once
         const float b1 = __ll2float_rn(t1) * flt_scale;
@@ -484,6 +492,7 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
 // mode 1: temporal pair (feature_tracker.cpp:410,417-418): forward maxLevel `top`, then
 //         backward J->I from the forward result with initial flow = prev, maxLevel 1
 // mode 2: stereo pair (:490,495): forward, then backward J->I, both maxLevel `top`, no init
+template <int NW>
 __global__ void __launch_bounds__(kLkThreads)
 k_lk(const __grid_constant__ PyrDesc pd, const uint8_t* __restrict__ I, const uint8_t* __restrict__ J,
      const float2* __restrict__ prev_pts, float2* __restrict__ next_pts,
@@ -498,7 +507,7 @@ k_lk(const __grid_constant__ PyrDesc pd, const uint8_t* __restrict__ I, const ui
   if (use_init) init = next_pts[k];
   float2 np;
   int st;
-  lk_point(S, pd, I, J, p0, init, use_init, top, np, st);
+  lk_point<NW>(S, pd, I, J, p0, init, use_init, top, np, st);
   if (threadIdx.x == 0) {
     next_pts[k] = np;
     status[k] = (uint8_t)st;
@@ -508,9 +517,9 @@ k_lk(const __grid_constant__ PyrDesc pd, const uint8_t* __restrict__ I, const ui
   int rst;
   if (mode == 1) {
     const int top_b = top < 1 ? top : 1;
-    lk_point(S, pd, J, I, np, p0, 1, top_b, rp, rst, 1);
+    lk_point<NW>(S, pd, J, I, np, p0, 1, top_b, rp, rst, 1);
   } else {
-    lk_point(S, pd, J, I, np, init, 0, top, rp, rst, 1);
+    lk_point<NW>(S, pd, J, I, np, init, 0, top, rp, rst, 1);
   }
   if (threadIdx.x == 0) {
     rev_pts[k] = rp;
@@ -525,8 +534,14 @@ void launch_lk(const PyrDesc& pd, const uint8_t* I, const uint8_t* J, const floa
   if (n_max <= 0) return;
   int top = pd.levels - 1;
   if (top > max_level) top = max_level;
-  launch_pdl(k_lk, dim3(n_max), dim3(kLkThreads), 0, s, pd, I, J, prev_pts, next_pts, status, rev_pts,
-             rev_status, n_ptr, top, use_initial_flow, mode);
+  static const int nw = getenv("ESVIO_LK_NW") ? atoi(getenv("ESVIO_LK_NW")) : 4;  // experiments
+  auto go = [&](auto kern) {
+    launch_pdl(kern, dim3(n_max), dim3(kLkThreads), 0, s, pd, I, J, prev_pts, next_pts, status, rev_pts,
+               rev_status, n_ptr, top, use_initial_flow, mode);
+  };
+  if (nw == 1) go(k_lk<1>);
+  else if (nw == 2) go(k_lk<2>);
+  else go(k_lk<4>);
   ++*launches;
 }
 
@@ -540,7 +555,9 @@ void launch_lk(const PyrDesc& pd, const uint8_t* I, const uint8_t* J, const floa
 // CTAs per SM, 114 KB of L1 left.
 void prefer_shared_lk() {
   static const int pct = getenv("ESVIO_CARVEOUT") ? atoi(getenv("ESVIO_CARVEOUT")) : 50;  // experiments
-  cudaFuncSetAttribute(k_lk, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_lk<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_lk<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_lk<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 }  // namespace esvio

@@ -96,6 +96,9 @@ class GpuFeatureTracker {
   // the reference's image node does.
   template <class MatT>
   void trackImage(double _cur_time, const MatT& img_left, const MatT& img_right) {
+    // a frame smaller than the configured size would be an out-of-bounds host read in the copy
+    if (!dims_ok(img_left, 0) || (!img_right.empty() && !dims_ok(img_right, 0)))
+      throw std::invalid_argument("trackImage: frame size differs from the configured width x height");
     const uint8_t* r = img_right.empty() ? nullptr : (const uint8_t*)img_right.data;
     const int rc = esvio_fe_track_image(fe_, _cur_time, (const uint8_t*)img_left.data,
                                         (size_t)img_left.step, r, r ? (size_t)img_right.step : 0,
@@ -109,6 +112,17 @@ class GpuFeatureTracker {
   }
 
   void reset() { esvio_fe_reset(fe_); }
+
+ private:
+  // rows / cols are checked when MatT has them (cv::Mat does); a bare {data, step} view is trusted
+  template <class MatT>
+  auto dims_ok(const MatT& m, int) const -> decltype((void)m.rows, (void)m.cols, bool()) {
+    return m.rows == cfg_.height && m.cols == cfg_.width;
+  }
+  template <class MatT>
+  bool dims_ok(const MatT&, long) const { return true; }
+
+ public:
 
   // FeatureTracker::gettimesurface() (feature_tracker.cpp:894-897): CV_8U, row-major W x H
   std::vector<uint8_t> gettimesurface(int cam = 0) {

@@ -134,6 +134,22 @@ int main() {
       if (k == 1 && !imageTracker.ids_right.empty()) return 16;
     }
     if (imageTracker.ids.empty()) return 15;
+    {  // a Mat that knows its size (cv::Mat does) and is too small must be refused, not read
+      struct MatRC {
+        uint8_t* data;
+        size_t step;
+        int rows, cols;
+        bool empty() const { return data == nullptr; }
+      };
+      MatRC small{big.data(), (size_t)BW, H - 1, W}, none{nullptr, 0, 0, 0};
+      bool refused = false;
+      try {
+        imageTracker.trackImage(1.0, small, none);
+      } catch (const std::invalid_argument&) {
+        refused = true;
+      }
+      if (!refused) return 17;
+    }
     std::printf("trackImage: %zu left / %zu right features\n", imageTracker.ids.size(),
                 imageTracker.ids_right.size());
     return 0;
