@@ -110,7 +110,7 @@ struct LkShared {
   short Ty[kMaxLevels][kTplLen];
   long long Apart[kMaxLevels][kTplWarps][3];  // per-warp sums of Ixw^2, Ixw*Iyw, Iyw^2
   int flag_win[kMaxLevels];             // 1: template window outside the image
-  longlong2 part[2][kMaxNWarps];           // per-iteration partial sums (b1, b2) of the N-group warps
+  int4 part[2][kMaxNWarps];                // per-iteration partial sums (b1, b2 as low 16 bits / rest) of the N-group warps
   float2 np[2];                         // result of a level, slot = Newton levels run so far & 1
   int st[2];
 };
@@ -121,6 +121,27 @@ __device__ __forceinline__ long long warp_sum_exact(int v) {
   const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
   const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
   return ((long long)hi << 16) + (long long)lo;
+}
+
+// shared memory by 32-bit address (computed once per level: through a generic pointer the
+// compiler re-derives the shared window base inside the Newton loop, an S2R on the chain)
+__device__ __forceinline__ uint32_t keep_in_register(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, int a, int b, int c, int d) {
+  asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // barrier of the NW warps of the N group (barrier 0 is __syncthreads of the whole CTA)
@@ -326,7 +347,7 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
   for (int j = 0; j < kPxN; ++j) {
     const int kk = tid + kNThreads * j;
     const int y = kk / kWin, x = kk - y * kWin;
-    joff[j] = (n_group && kk < kWin * kWin) ? y * kQS + x : 0;  // in 32-bit words
+    joff[j] = (n_group && kk < kWin * kWin) ? 4 * (y * kQS + x) : 0;  // in bytes
   }
   for (int level = top; level >= 0; --level) {
     const int w = pd.w[level], h = pd.h[level], pitch = pd.pitch[level];
@@ -385,77 +406,110 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
       }
       float npx = np.x - half, npy = np.y - half;
       int rx0 = rc.rx0, ry0 = rc.ry0;
-      float pdx = 0.f, pdy = 0.f;
+      // An iteration is ONE dependent chain (position -> weights -> pixel sums -> reduction ->
+      // solve -> stopping rules) of which the 21x21 pixels are a small part: whatever the width
+      // of the N group, it costs what its ~150 dependent instructions cost (measured: 620-700
+      // cycles with 4, 2 or 1 warps).  So the chain itself is kept short: floor() and cvRound()
+      // as magic-number additions on the ALU pipe, weights packed with PRMT, the four bounds tests
+      // on the float position, shared memory addressed with 32-bit addresses computed once, the
+      // exact sums converted with one FFMA, one test in front of both stopping rules.
+      const float kMagic = 12582912.f;  // 1.5 * 2^23: x + kMagic has ulp 1 for |x| < 2^22
+      const float wf = (float)w, hf = (float)h;
+      // (passed through an opaque mov: otherwise the compiler re-derives them inside the loop)
+      const uint32_t q_base = keep_in_register((uint32_t)__cvta_generic_to_shared(&S.Q[cur][0][0]));
+      const uint32_t part_base = keep_in_register((uint32_t)__cvta_generic_to_shared(&S.part[0][0]));
+      // b = T * 2^-20 only ever enters products that are scaled by D afterwards: a power of two
+      // moves through every rounding unchanged (no intermediate comes near the denormals), so
+      // 2^-20 is applied to D once instead of to both sums in every iteration
+      const float Ds = D * flt_scale;
+      float pdx = 1e30f, pdy = 1e30f;  // no previous step: the oscillation rule cannot fire at it = 0
       int n_it = 0;
       for (int it = 0; it < 30; ++it) {
         ++n_it;
-        const int inx = (int)floorf(npx), iny = (int)floorf(npy);
-        if (inx < -kWin || inx >= w || iny < -kWin || iny >= h) {
+        // inx = floor(npx) < -kWin  <=>  npx < -kWin;  inx >= w  <=>  npx >= w (also catches NaN)
+        if (!(npx >= -(float)kWin && npx < wf && npy >= -(float)kWin && npy < hf)) {
           if (level == 0) st = 0;
           break;
         }
-        if (inx < rx0 || iny < ry0 || inx + kWin > rx0 + kJR - 1 || iny + kWin > ry0 + kJR - 1) {
+        // floor: round-toward-minus-infinity addition leaves kMagic + floor(x), exactly
+        const float rx = __fadd_rd(npx, kMagic), ry = __fadd_rd(npy, kMagic);
+        const int inx = __float_as_int(rx) - 0x4B400000, iny = __float_as_int(ry) - 0x4B400000;
+        int ox = inx - rx0, oy = iny - ry0;
+        if ((unsigned)ox > (unsigned)(kJR - 1 - kWin) || (unsigned)oy > (unsigned)(kJR - 1 - kWin)) {
           // the window walked out of the staged region (rare): the N group re-stages it
           rx0 = inx - kJM;
           ry0 = iny - kJM;
+          ox = kJM;
+          oy = kJM;
           bar_newton<NW>();  // everybody is done reading the old region
           stage_J<NW>(S.Q[cur], Jl, w, h, pitch, rx0, ry0, warp);
           bar_newton<NW>();
         }
-        const float a = npx - (float)inx, b = npy - (float)iny;
-        int iw00, iw01, iw10, iw11;
-        bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-        // sum_i pix_i * w_i over the packed 2x2 neighbourhood: two dot products of SIGNED 16-bit
-        // weights with unsigned 8-bit pixels (top row, then bottom row).  iw11 is what is left
-        // of 2^14 after three roundings and is -1 when all three round up (a * b < 3e-5, about
-        // 5 iterations in 10^5): OpenCV multiplies by that -1, int in its scalar code and
-        // int16 in its SIMD code
-        const unsigned wa = ((unsigned)iw00 & 0xffffu) | ((unsigned)iw01 << 16);
-        const unsigned wb = ((unsigned)iw10 & 0xffffu) | ((unsigned)iw11 << 16);
-        const uint32_t* base = &S.Q[cur][iny - ry0][inx - rx0];
+        const float a = npx - (rx - kMagic), b = npy - (ry - kMagic);  // rx - kMagic = (float)inx
+        const float a1 = 1.f - a, b1 = 1.f - b;
+        // cvRound(v * 2^14) for v in [0, 1]: the FFMA rounds v * 16384 + kMagic once (half to
+        // even), the product being exact, and leaves the integer in the low mantissa bits
+        const unsigned u00 = __float_as_uint(fmaf(__fmul_rn(a1, b1), 16384.f, kMagic));
+        const unsigned u01 = __float_as_uint(fmaf(__fmul_rn(a, b1), 16384.f, kMagic));
+        const unsigned u10 = __float_as_uint(fmaf(__fmul_rn(a1, b), 16384.f, kMagic));
+        // iw11 = 2^14 - iw00 - iw01 - iw10 (all three carry the 0x4B400000 of kMagic); it is
+        // what is left after three roundings and is -1 when all three round up (a * b < 3e-5,
+        // about 5 iterations in 10^5): OpenCV multiplies by that -1, int in its scalar code and
+        // int16 in its SIMD code, and so does the signed 16-bit lane of dp2a
+        const unsigned u11 = (0xE1C00000u + (1u << kWBits)) - (u00 + u01 + u10);
+        // sum_i pix_i * w_i over the packed 2x2 neighbourhood: two dot products of signed 16-bit
+        // weights with unsigned 8-bit pixels (top row, then bottom row)
+        const unsigned wa = __byte_perm(u00, u01, 0x5410);
+        const unsigned wb = __byte_perm(u10, u11, 0x5410);
+        const uint32_t qa = q_base + 4u * (unsigned)(oy * kQS + ox);
         int sb1 = 0, sb2 = 0;
 #pragma unroll
         for (int j = 0; j < kPxN; ++j) {
-          const unsigned q = base[joff[j]];
+          const unsigned q = lds_u32(qa + joff[j]);
           const int v = dp2a_hi_su(wb, q, dp2a_lo_su(wa, q, 1 << (kWBits - 5 - 1)));
           const int diff = (v >> (kWBits - 5)) - Iw[j];
           sb1 += diff * Dx[j];
           sb2 += diff * Dy[j];
         }
-        const long long w1 = warp_sum_exact(sb1), w2 = warp_sum_exact(sb2);
-        long long t1 = w1, t2 = w2;
+        // exact totals as (low 16 bits, the rest): per thread |sb| < 2^29, so over 441 pixels the
+        // low parts sum to < 2^23 and the high parts to < 2^19 in magnitude -- both exact in float,
+        // and hi * 65536 + lo rounded once by the FFMA is the exact integer rounded to float once
+        int lo1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)sb1 & 0xffffu);
+        int hi1 = __reduce_add_sync(0xffffffffu, sb1 >> 16);
+        int lo2 = (int)__reduce_add_sync(0xffffffffu, (unsigned)sb2 & 0xffffu);
+        int hi2 = __reduce_add_sync(0xffffffffu, sb2 >> 16);
         if (NW > 1) {
-          longlong2* part = S.part[it & 1];
-          part[warp] = make_longlong2(w1, w2);  // every lane, the same value: no divergent branch
+          const uint32_t pa = part_base + (uint32_t)((it & 1) * kMaxNWarps * 16);
+          sts_v4(pa + 16u * (unsigned)warp, lo1, hi1, lo2, hi2);  // every lane, the same value
           bar_newton<NW>();
-          t1 = 0, t2 = 0;
+          lo1 = hi1 = lo2 = hi2 = 0;
 #pragma unroll
           for (int q = 0; q < NW; ++q) {
-            const longlong2 p = part[q];
-            t1 += p.x;
-            t2 += p.y;
+            const int4 pq = lds_v4(pa + 16u * q);
+            lo1 += pq.x;
+            hi1 += pq.y;
+            lo2 += pq.z;
+            hi2 += pq.w;
           }
         }
-        // the exact totals, rounded to float once
-        const float b1 = __ll2float_rn(t1) * flt_scale;
-        const float b2 = __ll2float_rn(t2) * flt_scale;
-        const float dx = (A12 * b2 - A22 * b1) * D;
-        const float dy = (A12 * b1 - A11 * b2) * D;
+        const float b1s = fmaf((float)hi1, 65536.f, (float)lo1);
+        const float b2s = fmaf((float)hi2, 65536.f, (float)lo2);
+        const float dx = (A12 * b2s - A22 * b1s) * Ds;
+        const float dy = (A12 * b1s - A11 * b2s) * Ds;
         npx += dx;
         npy += dy;
         np.x = npx + half;
         np.y = npy + half;
         // OpenCV evaluates both stopping rules in double.  Far from the thresholds a float
         // estimate decides the same way (its error is ~1e-7 relative, the margins below are a
-        // factor 2 / 10 %), so the double arithmetic only runs in the rare close calls.
+        // factor 2 / 10 %), so one float test guards both rules and the double arithmetic only
+        // runs in the rare close calls.
         const float d2 = dx * dx + dy * dy;
-        if (d2 <= 2e-4f) {
-          if (d2 < 5e-5f || (double)dx * (double)dx + (double)dy * (double)dy <= eps2) break;
-        }
-        if (it > 0) {
-          const float sx = fabsf(dx + pdx), sy = fabsf(dy + pdy);
-          if (sx < 0.011f && sy < 0.011f &&
-              ((sx < 0.009f && sy < 0.009f) || ((double)sx < 0.01 && (double)sy < 0.01))) {
+        const float sx = fabsf(dx + pdx), sy = fabsf(dy + pdy);
+        const bool near_eps = d2 <= 2e-4f, near_osc = sx < 0.011f && sy < 0.011f;
+        if (near_eps || near_osc) {
+          if (near_eps && (d2 < 5e-5f || (double)dx * (double)dx + (double)dy * (double)dy <= eps2)) break;
+          if (near_osc && ((sx < 0.009f && sy < 0.009f) || ((double)sx < 0.01 && (double)sy < 0.01))) {
             np.x -= dx * 0.5f;
             np.y -= dy * 0.5f;
             break;

@@ -1,6 +1,6 @@
 #!/bin/bash
 T=${1:-s2o}
-for nw in 4 2 1; do
+for nw in ${NWS:-4 2 1}; do
 echo "== NW $nw"
 ESVIO_LK_NW=$nw python -m pytest tests -m gpu -x -q -k "lk_matches or teacher_forced" 2>&1 | tail -1
 ESVIO_LK_NW=$nw ESVIO_FE_LIB=$PWD/scratch/variants/libesvio_fe_clk.so python scratch/lk_clocks.py stereo_vga_5mevs 2>&1 | grep -E "cycles/iter|whole call"
