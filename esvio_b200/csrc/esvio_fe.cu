@@ -690,12 +690,12 @@ static bool mc_active(const esvio_motion* mc) {
 
 // createSAE_* + SAEtoTimeSurface_* + pyramids (feature_tracker.cpp:356-368) of the window in
 // `slot` into the pyramid buffers `left_idx` / `right_idx`: binning on stream_b behind the
-// window's copies, K1 (+ conditioning) on stream_e, pyramids on stream_p; records b_done,
+// window's copies, K1 (+ conditioning) and the pyramids on stream_e; records b_done,
 // k1_done and p_done of the slot.  n_cams = 1 (left/right split over two GPUs): only camera 0
 // of this handle -- ev_in[0], state plane 0, image `left_idx` -- is processed.
 static int run_event_stage(esvio_fe* fe, int slot, double t_ref, const DevEvents ev_in[2], int left_idx,
                            int right_idx, const esvio_motion* mc = nullptr, int n_cams = 2) {
-  cudaStream_t sb = fe->stream_b, se = fe->stream_e, s_pyr = fe->stream_p;
+  cudaStream_t sb = fe->stream_b, se = fe->stream_e, s_pyr = fe->stream_e;
   DevEvents ev[2] = {ev_in[0], n_cams == 2 ? ev_in[1] : DevEvents{}};
   // ---- K0 on stream_b.  The binned-event buffers alternate between even and odd slots; the
   // set of this slot was last read by the K1 two windows back.
@@ -760,8 +760,10 @@ static int run_event_stage(esvio_fe* fe, int slot, double t_ref, const DevEvents
   }
   prof_mark(fe, kMarkK1Done, se);
   CU(cudaEventRecord(fe->k1_done[slot], se));
-  // ---- pyramids on stream_p
-  CU(cudaStreamWaitEvent(s_pyr, fe->k1_done[slot], 0));
+  // ---- pyramids right behind K1 on the same stream (a programmatic dependent launch instead
+  // of an event hop to another stream: the temporal LK of a synchronous call starts ~8 us
+  // earlier; the next window's K1 queues 9 us later, which the pipeline does not notice --
+  // its period is set by the temporal chain)
   launch_pyramids(fe->pd, imgs, n_cams, s_pyr, &fe->launches);
   prof_mark(fe, kMarkPyrDone, s_pyr);
   CU(cudaEventRecord(fe->p_done[slot], s_pyr));

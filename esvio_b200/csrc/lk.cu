@@ -45,6 +45,9 @@ extern "C" __attribute__((visibility("default"))) int esvio_dbg_lk_clocks(long l
 #define LK_VAL(i, v)
 #endif
 
+#ifndef ESVIO_LK_MINB
+#define ESVIO_LK_MINB 3
+#endif
 constexpr int kWBits = 14;
 constexpr int kLkThreads = 256;
 constexpr int kLkWarps = kLkThreads / 32;
@@ -547,7 +550,7 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
 //         backward J->I from the forward result with initial flow = prev, maxLevel 1
 // mode 2: stereo pair (:490,495): forward, then backward J->I, both maxLevel `top`, no init
 template <int NW>
-__global__ void __launch_bounds__(kLkThreads)
+__global__ void __launch_bounds__(kLkThreads, ESVIO_LK_MINB)
 k_lk(const __grid_constant__ PyrDesc pd, const uint8_t* __restrict__ I, const uint8_t* __restrict__ J,
      const float2* __restrict__ prev_pts, float2* __restrict__ next_pts,
      uint8_t* __restrict__ status, float2* __restrict__ rev_pts, uint8_t* __restrict__ rev_status,

@@ -281,8 +281,9 @@ __device__ __forceinline__ void fill_disc_rows(uint32_t* mask, int words, int W,
 //  (2) Event_FeaturesToTrack (:13-38): k_corner_flags left the flagged events (Arc* corner on
 //      a live time-surface pixel) as one short list per 128 events, in stream order.  The
 //      lists of up to 1024 consecutive event blocks are gathered into shared memory (those
-//      already masked by a track are dropped on the way), one warp then serves them first
-//      come, first served, and the walk stops as soon as MAX_CNT is reached.
+//      already masked by a track are dropped on the way) and served first come, first served by
+//      the whole CTA, up to 32 free candidates per round; the walk stops as soon as MAX_CNT is
+//      reached.
 __global__ void __launch_bounds__(kSelThreads)
 k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict__ cand,
          const int* __restrict__ cand_cnt, int snap_slot) {
@@ -298,6 +299,8 @@ k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict
   __shared__ uint32_t s_keptbits[kSelFast / 32];
   __shared__ uint32_t s_cand[kSelThreads * kSelPerThread];
   __shared__ int s_kept, s_found;
+  __shared__ uint32_t s_first[32];  // the walk: the first free candidates of a round ...
+  __shared__ int s_first_idx[32];   // ... and their positions in s_cand
 
   TrackState* st = B.st;
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -449,32 +452,68 @@ k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict
       }
       __syncthreads();
       const int total = s_warp[32];
-      if (warp == 0 && total > 0) {
-        // 32 candidates at a time: the lowest lane whose pixel is still free is the next corner
-        // in stream order (everything before it is masked, and the mask only grows); its disc
-        // is filled and the remaining lanes are tested again
-        int found = s_found;
+      // The walk over the chunk, by the whole CTA in rounds.  A candidate becomes a corner iff its
+      // pixel is free when it is visited, i.e. free under the mask of the rounds before AND outside
+      // the discs of the corners accepted earlier in its own round.  Round: (a) every thread tests
+      // one candidate of the window [pos, pos + 1024) against the mask; (b) the first 32 free ones,
+      // in stream order, are compacted; (c) every warp settles them (the same computation in all
+      // warps: no broadcast): the lowest live lane is a corner, lanes inside its disc
+      // (in_disc = the raster of cv::circle) die; (d) the new discs are rastered, one per warp;
+      // (e) the next window starts behind the last settled candidate.  The mask only grows, so
+      // what a round skipped as masked stays masked.
+      if (total > 0) {
         const int r = P.min_dist;
-        const int my_k = lane - r;
-        const int my_hw = (r <= 15 && lane <= 2 * r) ? s_hw[my_k < 0 ? -my_k : my_k] : -1;
-        for (int c0 = 0; c0 < total && found < want; c0 += 32) {
-          const uint32_t xy = c0 + lane < total ? s_cand[c0 + lane] : kNone;
-          const int x = xy & 0xffff, y = xy >> 16;
-          uint32_t alive = __ballot_sync(0xffffffffu, xy != kNone);
-          while (found < want) {
-            const bool free_px = ((alive >> lane) & 1u) && !mask_test(s_mask, words, x, y);
-            const uint32_t fr = __ballot_sync(0xffffffffu, free_px);
-            if (!fr) break;
-            const int l = __ffs(fr) - 1;
-            const int ax = __shfl_sync(0xffffffffu, x, l), ay = __shfl_sync(0xffffffffu, y, l);
-            if (lane == 0) s_new[found] = (uint32_t)ax | ((uint32_t)ay << 16);
-            ++found;
-            alive &= ~((2u << l) - 1u);  // lanes up to l are settled
-            if (r <= 15) fill_disc_rows(s_mask, words, W, H, ax, ay, my_k, my_hw);
-            else fill_disc_warp(s_mask, words, W, H, ax, ay, r, s_hw);
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        int pos = 0, found = s_found;  // uniform over the CTA
+        while (pos < total && found < want) {
+          const int ci = pos + tid;
+          const uint32_t xy = ci < total ? s_cand[ci] : kNone;
+          const bool free_px = xy != kNone && !mask_test(s_mask, words, xy & 0xffff, xy >> 16);
+          const uint32_t fr = __ballot_sync(0xffffffffu, free_px);
+          if (lane == 0) s_warp[warp] = __popc(fr);
+          __syncthreads();
+          const int cnt_l = s_warp[lane];
+          int incl = cnt_l;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
           }
+          const int n_free = __shfl_sync(0xffffffffu, incl, 31);
+          const int my_rank = __shfl_sync(0xffffffffu, incl - cnt_l, warp) + __popc(fr & lt_mask);
+          if (free_px && my_rank < 32) {
+            s_first[my_rank] = xy;
+            s_first_idx[my_rank] = ci;
+          }
+          __syncthreads();
+          if (n_free == 0) {
+            pos += kSelThreads;
+            continue;
+          }
+          const int m = min(n_free, 32);
+          const uint32_t cxy = lane < m ? s_first[lane] : kNone;
+          const int cx = cxy & 0xffff, cy = cxy >> 16;
+          uint32_t alive = m == 32 ? 0xffffffffu : ((1u << m) - 1u), acc = 0;
+          int nacc = 0;
+          while (alive && found + nacc < want) {
+            const int l = __ffs(alive) - 1;
+            const int ax = __shfl_sync(0xffffffffu, cx, l), ay = __shfl_sync(0xffffffffu, cy, l);
+            acc |= 1u << l;
+            ++nacc;
+            const uint32_t covered = __ballot_sync(0xffffffffu, in_disc(ax, ay, cx, cy, r, s_hw));
+            alive &= ~covered & ~((2u << l) - 1u);  // lanes up to l are settled
+          }
+          if (warp == 0 && ((acc >> lane) & 1u)) s_new[found + __popc(acc & lt_mask)] = cxy;
+          for (int k = warp; k < nacc; k += kSelThreads / 32) {
+            const int l = __fns(acc, 0, k + 1);
+            fill_disc_warp_atomic(s_mask, words, W, H, __shfl_sync(0xffffffffu, cx, l),
+                                  __shfl_sync(0xffffffffu, cy, l), r, s_hw);
+          }
+          found += nacc;
+          pos = n_free > 32 ? s_first_idx[31] + 1 : pos + kSelThreads;
+          __syncthreads();  // the discs are in the mask; s_first / s_warp may be rewritten
         }
-        if (lane == 0) s_found = found;
+        if (tid == 0) s_found = found;
       }
       __syncthreads();
       if (s_found >= want) break;
