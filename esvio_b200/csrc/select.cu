@@ -208,11 +208,15 @@ size_t select_smem_bytes(int W, int H) { return (size_t)H * ((W + 31) / 32) * si
 #ifdef ESVIO_LK_CLOCKS  // scratch builds only: phase clocks of the last k_select launch
 __device__ long long g_sel_clk[16];
 #define SEL_CLK(i) do { if (threadIdx.x == 0) g_sel_clk[i] = clock64(); } while (0)
+#define SEL_ADD(i, v) do { if (threadIdx.x == 0) g_sel_clk[i] += (v); } while (0)
+#define SEL_SET(i, v) do { if (threadIdx.x == 0) g_sel_clk[i] = (v); } while (0)
 extern "C" __attribute__((visibility("default"))) int esvio_dbg_select_clocks(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_sel_clk, sizeof(g_sel_clk));
 }
 #else
 #define SEL_CLK(i)
+#define SEL_ADD(i, v)
+#define SEL_SET(i, v)
 #endif
 
 constexpr int kSelThreads = 1024;
@@ -301,6 +305,8 @@ k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict
   __shared__ int s_kept, s_found;
   __shared__ uint32_t s_first[32];  // the walk: the first free candidates of a round ...
   __shared__ int s_first_idx[32];   // ... and their positions in s_cand
+  __shared__ int s_nacc;
+  __shared__ uint32_t s_rows[32];        // the walk: s_rows[i] = lanes whose pixel candidate i's disc covers
 
   TrackState* st = B.st;
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -352,18 +358,33 @@ k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict
     __syncthreads();
     SEL_CLK(2);
     if (warp == 0) {
-      uint32_t kept_w = 0;  // lane w: survivors among order positions [32w, 32w+32)
+      // The greedy pass: a point survives iff no surviving earlier point covers it.  32 order
+      // positions at a time, lane = point: survivors of the blocks before are final, so whether
+      // one of them covers the point is a parallel test; inside the block the lowest live lane
+      // survives and the lanes it covers die (one ballot on its column of the conflict matrix),
+      // so the pass costs one step per SURVIVOR instead of one vote per point.
       int kept = 0;
-      for (int b = 0; b < n; ++b) {
-        const short2 pb = s_px[b];
-        const bool inside = pb.x >= 0 && pb.x < W && pb.y >= 0 && pb.y < H;
-        const uint32_t hit = lane < nw ? (s_conf[b][lane] & kept_w) : 0u;
-        if (inside && !__any_sync(0xffffffffu, hit != 0)) {
-          if (lane == (b >> 5)) kept_w |= 1u << (b & 31);
-          ++kept;
+      for (int w = 0; w < nw; ++w) {
+        const int b = 32 * w + lane;
+        bool ok = false;
+        uint32_t my_row = 0;  // bit a: point 32 w + a (earlier in the order) covers me
+        if (b < n) {
+          const short2 pb = s_px[b];
+          ok = pb.x >= 0 && pb.x < W && pb.y >= 0 && pb.y < H;
+          for (int w2 = 0; w2 < w; ++w2) ok = ok && (s_conf[b][w2] & s_keptbits[w2]) == 0;
+          my_row = s_conf[b][w];
         }
+        uint32_t alive = __ballot_sync(0xffffffffu, ok), acc = 0;
+        while (alive) {
+          const int l = __ffs(alive) - 1;
+          acc |= 1u << l;
+          alive &= ~__ballot_sync(0xffffffffu, (my_row >> l) & 1u) & ~((2u << l) - 1u);
+        }
+        if (lane == 0) s_keptbits[w] = acc;
+        kept += __popc(acc);
+        __syncwarp();
       }
-      if (lane < kSelFast / 32) s_keptbits[lane] = kept_w;
+      if (lane >= nw && lane < kSelFast / 32) s_keptbits[lane] = 0;
       if (lane == 0) s_kept = kept;
     }
     __syncthreads();
@@ -405,7 +426,12 @@ k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict
   SEL_CLK(4);
   const int kept = s_kept;
   const int want = P.max_cnt - kept;
-  uint32_t* s_new = &s_conf[0][0];  // the bit matrix is done with: accepted corners, x | y << 16
+  // the bit matrix is done with: its first half takes the accepted corners (x | y << 16), its
+  // second half the ends of the candidate lists of a chunk
+  uint32_t* s_new = &s_conf[0][0];
+  int* s_off = reinterpret_cast<int*>(&s_conf[kSelFast / 2][0]);
+  static_assert(kMaxCnt <= kSelFast * (kSelFast / 32) / 2 && kSelThreads <= kSelFast * (kSelFast / 32) / 2,
+                "accepted corners and list ends fit in the two halves of the conflict matrix");
 
   // ---- Event_FeaturesToTrack: first come, first served in stream order
   if (want > 0 && n_events > 0) {
@@ -442,23 +468,44 @@ k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict
       // most kCornerBlock entries, so at least one always fits)
       const bool fits = real && incl <= kCap;
       const int n_fit = __syncthreads_count(fits);
-      if (fits) {
-        const uint32_t* src = cand + (size_t)blk * kCornerBlock;
-        for (int j = 0; j < c; ++j) {
-          const uint32_t xy = __ldg(src + j);
-          s_cand[incl - c + j] = mask_test(s_mask, words, xy & 0xffff, xy >> 16) ? kNone : xy;
-        }
-        if (tid == n_fit - 1) s_warp[32] = incl;
-      }
+      s_off[tid] = fits ? incl : 0x7fffffff;  // inclusive end of block tid's list in s_cand
+      if (fits && tid == n_fit - 1) s_warp[32] = incl;
       __syncthreads();
       const int total = s_warp[32];
+      // entry e of the chunk belongs to the first block whose list ends behind e (binary search
+      // over the n_fit ends); a thread copies entries tid, tid + 1024, ... -- a thread per block
+      // walking its own list one entry at a time took five times as long
+      {
+        uint32_t xy[kSelPerThread];
+#pragma unroll
+        for (int q = 0; q < kSelPerThread; ++q) {  // all loads of a thread in flight together
+          const int e = tid + q * kSelThreads;
+          xy[q] = kNone;
+          if (e < total) {
+            int lo = 0, hi = n_fit - 1;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (s_off[mid] > e) hi = mid;
+              else lo = mid + 1;
+            }
+            const int first = lo ? s_off[lo - 1] : 0;
+            xy[q] = __ldg(cand + (size_t)(b0 + lo) * kCornerBlock + (e - first));
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kSelPerThread; ++q) {
+          const int e = tid + q * kSelThreads;
+          if (e < total) s_cand[e] = mask_test(s_mask, words, xy[q] & 0xffff, xy[q] >> 16) ? kNone : xy[q];
+        }
+      }
+      __syncthreads();
       // The walk over the chunk, by the whole CTA in rounds.  A candidate becomes a corner iff its
       // pixel is free when it is visited, i.e. free under the mask of the rounds before AND outside
       // the discs of the corners accepted earlier in its own round.  Round: (a) every thread tests
       // one candidate of the window [pos, pos + 1024) against the mask; (b) the first 32 free ones,
-      // in stream order, are compacted; (c) every warp settles them (the same computation in all
-      // warps: no broadcast): the lowest live lane is a corner, lanes inside its disc
-      // (in_disc = the raster of cv::circle) die; (d) the new discs are rastered, one per warp;
+      // in stream order, are compacted; (c) warp i computes which of them candidate i's disc covers (in_disc = the
+      // raster of cv::circle), warp 0 then settles them with bit operations: the lowest live lane is
+      // a corner, the lanes its disc covers die; (d) the new discs are rastered, one per warp;
       // (e) the next window starts behind the last settled candidate.  The mask only grows, so
       // what a round skipped as masked stays masked.
       if (total > 0) {
@@ -490,24 +537,35 @@ k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict
             pos += kSelThreads;
             continue;
           }
+          // who covers whom among the <= 32: warp i tests candidate i's disc against all of them
           const int m = min(n_free, 32);
-          const uint32_t cxy = lane < m ? s_first[lane] : kNone;
-          const int cx = cxy & 0xffff, cy = cxy >> 16;
-          uint32_t alive = m == 32 ? 0xffffffffu : ((1u << m) - 1u), acc = 0;
-          int nacc = 0;
-          while (alive && found + nacc < want) {
-            const int l = __ffs(alive) - 1;
-            const int ax = __shfl_sync(0xffffffffu, cx, l), ay = __shfl_sync(0xffffffffu, cy, l);
-            acc |= 1u << l;
-            ++nacc;
-            const uint32_t covered = __ballot_sync(0xffffffffu, in_disc(ax, ay, cx, cy, r, s_hw));
-            alive &= ~covered & ~((2u << l) - 1u);  // lanes up to l are settled
+          {
+            const uint32_t mine = lane < m ? s_first[lane] : kNone;
+            const uint32_t ci_xy = warp < m ? s_first[warp] : kNone;
+            const uint32_t row = __ballot_sync(0xffffffffu, lane < m && warp < m &&
+                                               in_disc(ci_xy & 0xffff, ci_xy >> 16, mine & 0xffff, mine >> 16, r, s_hw));
+            if (lane == 0) s_rows[warp] = row;
           }
-          if (warp == 0 && ((acc >> lane) & 1u)) s_new[found + __popc(acc & lt_mask)] = cxy;
+          __syncthreads();
+          if (warp == 0) {
+            const uint32_t cxy = lane < m ? s_first[lane] : kNone;
+            const uint32_t my_row = s_rows[lane];
+            uint32_t alive = m == 32 ? 0xffffffffu : ((1u << m) - 1u), acc = 0;
+            int nacc = 0;
+            while (alive && found + nacc < want) {
+              const int l = __ffs(alive) - 1;
+              acc |= 1u << l;
+              ++nacc;
+              alive &= ~__shfl_sync(0xffffffffu, my_row, l) & ~((2u << l) - 1u);  // lanes up to l are settled
+            }
+            if ((acc >> lane) & 1u) s_new[found + __popc(acc & lt_mask)] = cxy;
+            if (lane == 0) s_nacc = nacc;
+          }
+          __syncthreads();
+          const int nacc = s_nacc;
           for (int k = warp; k < nacc; k += kSelThreads / 32) {
-            const int l = __fns(acc, 0, k + 1);
-            fill_disc_warp_atomic(s_mask, words, W, H, __shfl_sync(0xffffffffu, cx, l),
-                                  __shfl_sync(0xffffffffu, cy, l), r, s_hw);
+            const uint32_t a = s_new[found + k];
+            fill_disc_warp_atomic(s_mask, words, W, H, a & 0xffff, a >> 16, r, s_hw);
           }
           found += nacc;
           pos = n_free > 32 ? s_first_idx[31] + 1 : pos + kSelThreads;

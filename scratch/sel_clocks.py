@@ -19,4 +19,4 @@ for k in range(10):
         b = np.zeros(16, np.int64)
         L.esvio_dbg_select_clocks(b.ctypes.data_as(C.c_void_p))
         d = np.diff(b[:7])
-        print(f"window {k}: stats {r['stats']} total {b[6]-b[0]} cycles = {(b[6]-b[0])/1965:.1f} us | " + ", ".join(f"{n} {int(v)}" for n, v in zip(names, d)))
+        print(f"window {k}: stats {r['stats']} total {b[6]-b[0]} cycles = {(b[6]-b[0])/1965:.1f} us | " + ", ".join(f"{n} {int(v)}" for n, v in zip(names, d)) + f" | chunks {b[10]} load cycles {b[9]} rounds-with-free {b[8]} accepted {b[11]}")
