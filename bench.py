@@ -460,6 +460,37 @@ class StreamBench:
             fe.close()
         return out
 
+    def dropin_leg(self, scene="survey", stream_id=0):
+        """The call exactly as the reference node would make it: esvio_fe_track on the 16-byte
+        dvs_msgs::Event records (AoS: u16 x, u16 y, u32 sec, u32 nsec, u8 polarity) of a
+        std::vector in ordinary, pageable host memory (stereo_event_tracker_node.cpp:193 holds the
+        events of both cameras that way); host wall clock, one window at a time."""
+        fr = self.fr
+        s = synth.StereoEventStream(self.w["width"], self.w["height"], self.w["rate"], stream=stream_id,
+                                    mono=self.w["mono"], rigid=(scene == "rigid"))
+        wins = []
+        for k in range(self.K + self.Wm):
+            recs = []
+            for cam in (0, 1):
+                x, y, t, p, sec, nsec = s.window(k, cam)
+                recs.append(fr._Ev(synth.to_aos(x, y, sec, nsec, p)))
+            wins.append((recs[0], recs[1], self.wins[k][2]))
+        fe = fr.EventFrontEnd(self.cfg)
+        for k in range(self.Wm):
+            fe.track_raw(wins[k][2], wins[k][0], wins[k][1], k % self.pub_div == 0)
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(self.Wm, self.Wm + self.K):
+            n = fe.track_raw(wins[k][2], wins[k][0], wins[k][1], k % self.pub_div == 0)
+        ms = (time.perf_counter() - t0) * 1e3 / self.K
+        fe.close()
+        return {"value": self.ev_per_step / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms,
+                "h2d_bytes_per_step": int(round(16 * self.ev_per_step)),
+                "tracks_last_window": {"left": int(n[0]), "right": int(n[1])},
+                "api": "esvio_fe_track (synchronous) on 16-byte dvs_msgs::Event records (AoS) in ordinary "
+                       "pageable host memory -- the buffers the reference node's callback holds "
+                       "(stereo_event_tracker_node.cpp:128-142,193); host wall clock"}
+
     def mev(self, ms):
         return self.ev_timed / (ms * 1e-3) / 1e6
 
@@ -823,6 +854,11 @@ def main_ours(args):
                             "api": "esvio_fe_track: the synchronous call the reference node makes "
                                    "(stereo_event_tracker_node.cpp:193), pinned host buffers, host "
                                    "wall clock"}
+        if world == 1:
+            try:
+                line["dropin"] = sb.dropin_leg("survey", rank)
+            except Exception as e:  # a secondary record must not take the line down
+                line["dropin"] = {"error": repr(e)}
         if world == 1 and extra.get("batched") and "error" not in extra["batched"] and roof_group:
             line["roofline"] = roof_group
             line["roofline_single_stream"] = roof_single

@@ -9,7 +9,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "../../include/esvio_fe.h"
 #include "common.cuh"
@@ -25,6 +30,131 @@ int select_configure(int W, int H);
 
 constexpr int kLeftBufs = kSlots + 1, kRightBufs = kSlots, kRightBase = kLeftBufs, kScratchBase = kLeftBufs + kRightBufs,
               kNumPyr = kScratchBase + 2;
+
+// ------------------------------------------------------------------------------------------
+// Staging of pageable host buffers.  The reference node holds a window's events in
+// std::vector<dvs_msgs::Event> (stereo_event_tracker_node.cpp:128-142): ordinary memory, which
+// cudaMemcpyAsync moves through the driver's own bounce buffers on one thread at ~10 GB/s --
+// 0.5 ms for the 5.3 MB of a 640x480 window at 5 Mev/s per camera, longer than all the kernels of
+// the window together.  Instead the calling thread and a few helpers copy the caller's buffer
+// into a pinned ring of the handle, chunk by chunk, and the DMA of a chunk starts as soon as it
+// and the chunks before it have landed; the call returns when the last chunk is enqueued, so
+// the caller's buffer is free again.  One pool per process, one job at a time.
+// ESVIO_FE_STAGE_THREADS=<n> sets the number of helpers (0: the driver's path).
+// ------------------------------------------------------------------------------------------
+class HostStager {
+ public:
+  static HostStager& get() {
+    static HostStager s;
+    return s;
+  }
+  int helpers() const { return (int)workers_.size(); }
+  // dst_pinned / dst_dev / src: `bytes` each.  The helpers and the calling thread copy chunks
+  // into pinned memory; only the calling thread talks to CUDA (concurrent cudaMemcpyAsync calls
+  // from several threads serialise on the driver's lock: measured, slower than no helpers at
+  // all): it enqueues the contiguous prefix of finished chunks host -> device on `stream`.
+  cudaError_t run(uint8_t* dst_pinned, uint8_t* dst_dev, const uint8_t* src, size_t bytes, cudaStream_t stream) {
+    std::lock_guard<std::mutex> one_job(job_mutex_);
+    const int n_chunks = (int)((bytes + kChunk - 1) / kChunk);
+    if (n_chunks > kMaxChunks) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream);
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      done_cv_.wait(lk, [&] { return working_ == 0; });  // stragglers of the job before
+      pinned_ = dst_pinned, src_ = src, bytes_ = bytes, n_chunks_ = n_chunks;
+      for (int c = 0; c < n_chunks; ++c) done_[c].store(0, std::memory_order_relaxed);
+      next_.store(0);
+      working_ = (int)workers_.size();
+      ++generation_;
+    }
+    cv_.notify_all();
+    cudaError_t err = cudaSuccess;
+    int enqueued = 0;
+    while (enqueued < n_chunks) {
+      const int c = next_.fetch_add(1);
+      if (c < n_chunks) copy_chunk(c);
+      int ready = enqueued;
+      while (ready < n_chunks && done_[ready].load(std::memory_order_acquire)) ++ready;
+      if (ready > enqueued) {
+        const size_t off = (size_t)enqueued * kChunk;
+        const size_t len = (ready == n_chunks ? bytes : (size_t)ready * kChunk) - off;
+        const cudaError_t e = cudaMemcpyAsync(dst_dev + off, dst_pinned + off, len, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) err = e;
+        enqueued = ready;
+      } else if (c >= n_chunks) {
+        std::this_thread::yield();  // the helpers hold the chunks that are still missing
+      }
+    }
+    return err;
+  }
+
+ private:
+  static constexpr size_t kChunk = 256 << 10;
+  static constexpr int kMaxChunks = 4096;
+  HostStager() : done_(kMaxChunks) {
+    int n = 1;  // measured on the B200 boxes (640x480 @5 Mev/s, 5.3 MB per window): 0 helpers 0.75 ms per
+                // synchronous call, 1: 0.66, 2: 0.74, 4: 0.95 -- more threads lose to their wake-ups
+    if (const char* e = getenv("ESVIO_FE_STAGE_THREADS")) n = atoi(e);
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && n > hw - 1) n = hw - 1;
+    if (n < 0) n = 0;
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~HostStager() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void copy_chunk(int c) {
+    const size_t off = (size_t)c * kChunk, len = bytes_ - off < kChunk ? bytes_ - off : kChunk;
+    memcpy(pinned_ + off, src_ + off, len);
+    done_[c].store(1, std::memory_order_release);
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+      }
+      for (;;) {
+        const int c = next_.fetch_add(1);
+        if (c >= n_chunks_) break;
+        copy_chunk(c);
+      }
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        --working_;
+      }
+      done_cv_.notify_all();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::vector<std::atomic<uint8_t>> done_;
+  std::mutex m_, job_mutex_;
+  std::condition_variable cv_, done_cv_;
+  bool stop_ = false;
+  uint64_t generation_ = 0;
+  int working_ = 0, n_chunks_ = 0;
+  uint8_t* pinned_ = nullptr;
+  const uint8_t* src_ = nullptr;
+  size_t bytes_ = 0;
+  std::atomic<int> next_{0};
+};
+
+// ordinary (pageable) host memory?  Pinned and registered buffers go straight to the DMA engine.
+static bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
 
 struct esvio_fe {
   esvio_fe_config cfg;
@@ -95,6 +225,7 @@ struct esvio_fe {
   TrackBuffers tb;
   TrackParams tp;
   int32_t* h_result[kSlots];
+  uint8_t* h_stage[kSlots][2];  // pinned ring for pageable input (allocated on first use), 16 B x cap each
   size_t result_words;
   int* d_scratch_n;
   float2 *d_scratch_p0, *d_scratch_p1;
@@ -305,6 +436,8 @@ static void free_all(esvio_fe* fe) {
                            fe->t1_done[i], fe->s_done[i], fe->x_ready[i]})
       if (ev) cudaEventDestroy(ev);
     if (fe->h_result[i]) cudaFreeHost(fe->h_result[i]);
+    for (int c = 0; c < 2; ++c)
+      if (fe->h_stage[i][c]) cudaFreeHost(fe->h_stage[i][c]);
     if (fe->q_done[i]) cudaEventDestroy(fe->q_done[i]);
     if (fe->r_free[i]) cudaEventDestroy(fe->r_free[i]);
   }
@@ -621,8 +754,21 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
   uint8_t* raw = fe->raw[slot][cam];
   cudaStream_t se = fe->stream_c;
   const size_t n = e->n, cap = (size_t)fe->cap;
+  // host -> raw + off: pinned memory goes straight to the DMA engine, large pageable buffers
+  // through the handle's pinned ring on the staging threads (HostStager)
+  auto h2d = [&](size_t off, const void* src, size_t bytes) -> int {
+    if (bytes >= (128u << 10) && HostStager::get().helpers() > 0 && is_pageable(src)) {
+      if (!fe->h_stage[slot][cam])
+        CU(cudaHostAlloc(&fe->h_stage[slot][cam], cap * 16, cudaHostAllocDefault));
+      CU(HostStager::get().run(fe->h_stage[slot][cam] + off, raw + off, (const uint8_t*)src, bytes, se));
+    } else {
+      CU(cudaMemcpyAsync(raw + off, src, bytes, cudaMemcpyHostToDevice, se));
+    }
+    return ESVIO_FE_OK;
+  };
+  int rc;
   if (e->aos) {
-    CU(cudaMemcpyAsync(raw, e->aos, n * 16, cudaMemcpyHostToDevice, se));
+    if ((rc = h2d(0, e->aos, n * 16)) != ESVIO_FE_OK) return rc;
     d->aos = (const uint4*)raw;
   } else {
     size_t off[4], total;
@@ -631,7 +777,7 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
     if ((const uint8_t*)e->y == hx + off[1] && (const uint8_t*)e->t == hx + off[2] &&
         (const uint8_t*)e->p == hx + off[3]) {
       // the four arrays sit in one block laid out by esvio_fe_soa_layout: one copy
-      CU(cudaMemcpyAsync(raw, hx, total, cudaMemcpyHostToDevice, se));
+      if ((rc = h2d(0, hx, total)) != ESVIO_FE_OK) return rc;
       d->x = (uint16_t*)raw, d->y = (uint16_t*)(raw + off[1]), d->t = (double*)(raw + off[2]),
       d->p = raw + off[3];
     } else {
@@ -639,10 +785,10 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
       uint16_t* dy = (uint16_t*)(raw + 2 * cap);
       double* dt = (double*)(raw + 4 * cap);
       uint8_t* dp = raw + 12 * cap;
-      CU(cudaMemcpyAsync(dx, e->x, n * 2, cudaMemcpyHostToDevice, se));
-      CU(cudaMemcpyAsync(dy, e->y, n * 2, cudaMemcpyHostToDevice, se));
-      CU(cudaMemcpyAsync(dt, e->t, n * 8, cudaMemcpyHostToDevice, se));
-      CU(cudaMemcpyAsync(dp, e->p, n, cudaMemcpyHostToDevice, se));
+      if ((rc = h2d(0, e->x, n * 2)) != ESVIO_FE_OK) return rc;
+      if ((rc = h2d(2 * cap, e->y, n * 2)) != ESVIO_FE_OK) return rc;
+      if ((rc = h2d(4 * cap, e->t, n * 8)) != ESVIO_FE_OK) return rc;
+      if ((rc = h2d(12 * cap, e->p, n)) != ESVIO_FE_OK) return rc;
       d->x = dx, d->y = dy, d->t = dt, d->p = dp;
     }
   }
