@@ -10,8 +10,9 @@
 //                     draws are a table in HBM; reduce them mod n and find for every stream
 //                     offset how many draws the "7 distinct indices" rule consumes
 //   k_ransac_chase    one CTA chases the offsets to the start of every sample (attempt)
-//   k_ransac_hyp      32 attempts per CTA: degeneracy test + 7-point solve on 32 lanes, then
-//                     one warp per attempt scores its <= 3 models against all points
+//   k_ransac_hyp      8 attempts per CTA, one warp each: degeneracy test, 7-point solve with
+//                     the elimination spread over the lanes, scores of its <= 3 models against
+//                     all points
 //   k_ransac_fold     one CTA: iteration index = prefix count of valid samples, running best
 //                     = prefix max of inlier counts, iteration budget = RANSACUpdateNumIters
 //                     of that prefix max; the first sample past the budget ends the loop; the
@@ -29,7 +30,9 @@ constexpr int kDrawsPerThread = 15;
 constexpr int kNumDraws = 1024 * kDrawsPerThread;  // 15360 raw draws of cv::RNG(-1)
 constexpr int kMaxLen = 48;                        // cap on draws consumed by one sample
 constexpr int kMaxAttempts = 1280;
-constexpr int kHyp = 32;                           // attempts per CTA in k_ransac_hyp
+constexpr int kHyp = 8;   // attempts (= warps) per CTA in k_ransac_hyp: 160 CTAs for the 1280 attempts, one per
+                          // SM (scoring 3 models x 150 points per attempt in f64 is the bulk of the kernel:
+                          // with 32 attempts per CTA only 40 SMs worked, 31 us instead of 10)
 // haveCollinearPoints: is the last point collinear with any earlier pair
 __device__ bool collinear_with_last(const float2* m, int count) {
   const int i = count - 1;
@@ -114,8 +117,20 @@ __device__ int solve_cubic(const double* c, double* roots) {
   return n;
 }
 
-// FMEstimatorCallback::runKernel for 7 points (run7Point): up to 3 matrices, row-major
-__device__ int run_7point(const float2* m1, const float2* m2, double* Fout) {
+// FMEstimatorCallback::runKernel for 7 points (run7Point): up to 3 matrices, row-major.
+// One WARP per sample.  The 7x9 system sits in shared memory (sA, 63 doubles; sperm, 9 ints):
+// Gauss-Jordan with complete pivoting, every step spread over the lanes -- the pivot is the
+// first maximum of |A[i][j]|, i, j >= k, in row-major order (warp arg-max, ties to the lower
+// index, like the serial scan with its strict >), row / column swaps, the scaling of the
+// pivot row and the elimination touch each element exactly once per step with the same two
+// operations (multiply, subtract) the serial code applies, so the result is bit-identical to
+// one thread doing it alone.  That serial version -- 32 samples on the 32 lanes of one warp,
+// the matrix in local memory because the pivots index it dynamically -- took ~40 000 cycles per
+// CTA while the other 31 warps waited; this one ~4 000, all 32 warps busy.
+// m1 / m2: the sample (the same values in every lane).  Returns the number of models
+// (warp-uniform); the models land in Fout (shared memory, 27 doubles).
+__device__ int run_7point_warp(const float2* m1, const float2* m2, double* sA, int* sperm, double* Fout) {
+  const int lane = lane_id();
   double c1x = 0, c1y = 0, c2x = 0, c2y = 0;
   for (int i = 0; i < 7; ++i) {
     c1x += m1[i].x;
@@ -138,56 +153,107 @@ __device__ int run_7point(const float2* m1, const float2* m2, double* Fout) {
   s1 = sqrt(2.) / s1;
   s2 = sqrt(2.) / s2;
 
-  double A[7][9];
-  for (int i = 0; i < 7; ++i) {
-    const double x0 = (m1[i].x - c1x) * s1, y0 = (m1[i].y - c1y) * s1;
-    const double x1 = (m2[i].x - c2x) * s2, y1 = (m2[i].y - c2y) * s2;
-    A[i][0] = x1 * x0, A[i][1] = x1 * y0, A[i][2] = x1;
-    A[i][3] = y1 * x0, A[i][4] = y1 * y0, A[i][5] = y1;
-    A[i][6] = x0, A[i][7] = y0, A[i][8] = 1;
-  }
+  // row i of the system by lane i
+#pragma unroll
+  for (int i = 0; i < 7; ++i)
+    if (lane == i) {
+      const double x0 = (m1[i].x - c1x) * s1, y0 = (m1[i].y - c1y) * s1;
+      const double x1 = (m2[i].x - c2x) * s2, y1 = (m2[i].y - c2y) * s2;
+      double* r = sA + 9 * i;
+      r[0] = x1 * x0, r[1] = x1 * y0, r[2] = x1;
+      r[3] = y1 * x0, r[4] = y1 * y0, r[5] = y1;
+      r[6] = x0, r[7] = y0, r[8] = 1;
+    }
+  if (lane < 9) sperm[lane] = lane;
+  __syncwarp();
   // Gauss-Jordan with complete pivoting -> [I | C] in permuted columns
-  int perm[9];
-  for (int j = 0; j < 9; ++j) perm[j] = j;
   for (int k = 0; k < 7; ++k) {
-    int pi = k, pj = k;
+    // lane owns elements e = lane and lane + 32 (e = 9 i + j)
     double best = -1;
-    for (int i = k; i < 7; ++i)
-      for (int j = k; j < 9; ++j)
-        if (fabs(A[i][j]) > best) best = fabs(A[i][j]), pi = i, pj = j;
+    int best_e = 63;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = lane + 32 * q;
+      if (e < 63) {
+        const int i = e / 9, j = e - 9 * i;
+        if (i >= k && j >= k) {
+          const double v = fabs(sA[e]);
+          if (v > best) best = v, best_e = e;  // e grows with q: the earlier element wins a tie
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+      const int oe = __shfl_xor_sync(0xffffffffu, best_e, d);
+      if (ob > best || (ob == best && oe < best_e)) best = ob, best_e = oe;
+    }
     if (!(best > 1e-14)) return 0;  // rank deficient sample
-    if (pi != k)
-      for (int j = 0; j < 9; ++j) {
-        const double tmp = A[k][j];
-        A[k][j] = A[pi][j];
-        A[pi][j] = tmp;
-      }
+    const int pi = best_e / 9, pj = best_e - 9 * pi;
+    if (pi != k && lane < 9) {
+      const double tmp = sA[9 * k + lane];
+      sA[9 * k + lane] = sA[9 * pi + lane];
+      sA[9 * pi + lane] = tmp;
+    }
+    __syncwarp();
     if (pj != k) {
-      for (int i = 0; i < 7; ++i) {
-        const double tmp = A[i][k];
-        A[i][k] = A[i][pj];
-        A[i][pj] = tmp;
+      if (lane < 7) {
+        const double tmp = sA[9 * lane + k];
+        sA[9 * lane + k] = sA[9 * lane + pj];
+        sA[9 * lane + pj] = tmp;
+      } else if (lane == 7) {
+        const int tp = sperm[k];
+        sperm[k] = sperm[pj];
+        sperm[pj] = tp;
       }
-      const int tp = perm[k];
-      perm[k] = perm[pj];
-      perm[pj] = tp;
     }
-    const double inv = 1.0 / A[k][k];
-    for (int j = k; j < 9; ++j) A[k][j] *= inv;
-    for (int i = 0; i < 7; ++i) {
-      if (i == k) continue;
-      const double f = A[i][k];
-      if (f != 0.0)
-        for (int j = k; j < 9; ++j) A[i][j] -= f * A[k][j];
+    __syncwarp();
+    const double inv = 1.0 / sA[9 * k + k];
+    __syncwarp();
+    if (lane >= k && lane < 9) sA[9 * k + lane] *= inv;
+    __syncwarp();
+    // A[i][j] -= A[i][k] * A[k][j] for i != k, j >= k: read everything, then write
+    double f[2], akj[2];
+    int ee[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = lane + 32 * q;
+      ee[q] = -1;
+      f[q] = 0, akj[q] = 0;
+      if (e < 63) {
+        const int i = e / 9, j = e - 9 * i;
+        if (i != k && j >= k) {
+          ee[q] = e;
+          f[q] = sA[9 * i + k];
+          akj[q] = sA[9 * k + j];
+        }
+      }
     }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (ee[q] >= 0 && f[q] != 0.0) sA[ee[q]] -= f[q] * akj[q];
+    __syncwarp();
   }
   double f1[9], f2[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) f1[j] = 0, f2[j] = 0;
   for (int j = 0; j < 7; ++j) {
-    f1[perm[j]] = -A[j][7];
-    f2[perm[j]] = -A[j][8];
+    const int pj = sperm[j];
+    const double a7 = -sA[9 * j + 7], a8 = -sA[9 * j + 8];
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+      if (q == pj) f1[q] = a7, f2[q] = a8;
   }
-  f1[perm[7]] = 1, f1[perm[8]] = 0;
-  f2[perm[7]] = 0, f2[perm[8]] = 1;
+  {
+    const int p7 = sperm[7], p8 = sperm[8];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      if (q == p7) f1[q] = 1, f2[q] = 0;
+      if (q == p8) f1[q] = 0, f2[q] = 1;
+    }
+  }
+  __syncwarp();
 
   for (int i = 0; i < 9; ++i) f1[i] -= f2[i];
   double c[4], r[3] = {0, 0, 0};
@@ -212,7 +278,7 @@ __device__ int run_7point(const float2* m1, const float2* m2, double* Fout) {
   const double T1[9] = {s1, 0, -s1 * c1x, 0, s1, -s1 * c1y, 0, 0, 1};
   const double T2[9] = {s2, 0, -s2 * c2x, 0, s2, -s2 * c2y, 0, 0, 1};
   for (int k = 0; k < n; ++k) {
-    double* F = Fout + 9 * k;
+    double F[9];
     double lambda = r[k], mu = 1.;
     const double s = f1[8] * r[k] + f2[8];
     double G[9];
@@ -240,9 +306,14 @@ __device__ int run_7point(const float2* m1, const float2* m2, double* Fout) {
       const double inv = 1. / F[8];
       for (int i = 0; i < 9; ++i) F[i] *= inv;
     }
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      if (lane == i) Fout[9 * k + i] = F[i];
   }
+  __syncwarp();
   return n;
 }
+
 
 // FMEstimatorCallback::computeError for one correspondence
 __device__ __forceinline__ float fm_error(const double* F, float2 p1, float2 p2) {
@@ -536,13 +607,14 @@ __global__ void k_ransac_cache_row(const RansacScratch* __restrict__ R, uint4* _
 }
 
 // ------------------------------------------------------------------------------------------
-// k_ransac_hyp: solve and score 32 attempts per CTA
+// k_ransac_hyp: solve and score kHyp attempts per CTA, one warp each
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_ransac_hyp(RansacScratch* __restrict__ R) {
+__global__ void __launch_bounds__(32 * kHyp) k_ransac_hyp(RansacScratch* __restrict__ R) {
   PDL_PROLOGUE();
   __shared__ float2 s_p1[kMaxCnt], s_p2[kMaxCnt];
   __shared__ double s_F[kHyp][27];
-  __shared__ int s_nm[kHyp];
+  __shared__ double s_A[kHyp][63];
+  __shared__ int s_perm[kHyp][9];
   const int mode = R->mode;
   if (mode == kModeSkip || mode == kModeFail) return;
   const int n = R->n, n_att = R->n_attempts;
@@ -554,53 +626,46 @@ __global__ void __launch_bounds__(1024) k_ransac_hyp(RansacScratch* __restrict__
     s_p2[i] = R->p2[i];
   }
   __syncthreads();
-  if (warp == 0) {
-    const int a = a0 + lane;
-    int nm = 0, valid = 0;
-    if (a < n_att) {
-      float2 m1[kModelPts], m2[kModelPts];
+  // one warp per attempt: degeneracy test, 7-point solve, then the scores of its <= 3 models
+  const int a = a0 + warp;
+  if (a >= n_att) return;
+  float2 m1[kModelPts], m2[kModelPts];
 #pragma unroll
-      for (int q = 0; q < kModelPts; ++q) {
-        const int id = R->idx[a][q];
-        m1[q] = s_p1[id];
-        m2[q] = s_p2[id];
-      }
-      // FMEstimatorCallback::checkSubset
-      valid = (mode == kModeSeven) ||
-              !(collinear_with_last(m1, kModelPts) || collinear_with_last(m2, kModelPts));
-      if (valid) {
-        nm = run_7point(m1, m2, s_F[lane]);
-        nm = nm < 0 ? 0 : (nm > 3 ? 3 : nm);
-      }
-      R->valid[a] = valid;
-      R->nmodels[a] = nm;
-    }
-    s_nm[lane] = nm;
+  for (int q = 0; q < kModelPts; ++q) {
+    const int id = R->idx[a][q];
+    m1[q] = s_p1[id];
+    m2[q] = s_p2[id];
   }
-  __syncthreads();
-  {
-    const int a = a0 + warp;
-    if (a >= n_att) return;
-    const int nm = s_nm[warp];
-    const float t2 = (float)(R->thresh * R->thresh);
-    for (int m = 0; m < nm; ++m) {
-      const double* F = s_F[warp] + 9 * m;
-      if (lane < 9) R->F[a][9 * m + lane] = F[lane];
-      if (mode == kModeRansac) {
-        int good = 0;
-        for (int i = lane; i < n; i += 32) good += fm_error(F, s_p1[i], s_p2[i]) <= t2;
-        good = __reduce_add_sync(0xffffffffu, good);
-        if (lane == 0) R->good[a][m] = good;
-      } else if (mode == kModeLmeds) {
-        // n < 15: median of the residuals = element n/2 of the sorted list
-        const float e = lane < n ? fm_error(F, s_p1[lane], s_p2[lane]) : FLT_MAX;
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-          const float o = __shfl_sync(0xffffffffu, e, j);
-          rank += (o < e) || (o == e && j < lane);
-        }
-        if (lane < n && rank == n / 2) R->median[a][m] = e;
+  // FMEstimatorCallback::checkSubset
+  const int valid = (mode == kModeSeven) ||
+                    !(collinear_with_last(m1, kModelPts) || collinear_with_last(m2, kModelPts));
+  int nm = 0;
+  if (valid) {
+    nm = run_7point_warp(m1, m2, s_A[warp], s_perm[warp], s_F[warp]);
+    nm = nm < 0 ? 0 : (nm > 3 ? 3 : nm);
+  }
+  if (lane == 0) {
+    R->valid[a] = valid;
+    R->nmodels[a] = nm;
+  }
+  const float t2 = (float)(R->thresh * R->thresh);
+  for (int m = 0; m < nm; ++m) {
+    const double* F = s_F[warp] + 9 * m;
+    if (lane < 9) R->F[a][9 * m + lane] = F[lane];
+    if (mode == kModeRansac) {
+      int good = 0;
+      for (int i = lane; i < n; i += 32) good += fm_error(F, s_p1[i], s_p2[i]) <= t2;
+      good = __reduce_add_sync(0xffffffffu, good);
+      if (lane == 0) R->good[a][m] = good;
+    } else if (mode == kModeLmeds) {
+      // n < 15: median of the residuals = element n/2 of the sorted list
+      const float e = lane < n ? fm_error(F, s_p1[lane], s_p2[lane]) : FLT_MAX;
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float o = __shfl_sync(0xffffffffu, e, j);
+        rank += (o < e) || (o == e && j < lane);
       }
+      if (lane < n && rank == n / 2) R->median[a][m] = e;
     }
   }
 }
@@ -879,7 +944,7 @@ void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,
   pa.thresh = P.f_threshold;
   pa.min_points = 8;
   launch_pdl(k_ransac_prepare_cached, dim3(1), dim3(1024), 0, s, P, B, pa, R);
-  launch_pdl(k_ransac_hyp, dim3(kMaxAttempts / kHyp), dim3(1024), 0, s, R);
+  launch_pdl(k_ransac_hyp, dim3(kMaxAttempts / kHyp), dim3(32 * kHyp), 0, s, R);
   FoldArgs fa;
   fa.to_tracks = 1;
   fa.mask = nullptr;
@@ -928,7 +993,7 @@ void launch_ransac_stage(const TrackParams& P, const TrackBuffers& B, const floa
   ransac_configure();
   launch_pdl(k_ransac_len, dim3(kNumDraws / 1024), dim3(1024), 0, s, B, pa, B.rng_draws, R);
   launch_pdl(k_ransac_chase, dim3(1), dim3(1024), kPrepareSmem, s, P, B, pa, R);
-  launch_pdl(k_ransac_hyp, dim3(kMaxAttempts / kHyp), dim3(1024), 0, s, R);
+  launch_pdl(k_ransac_hyp, dim3(kMaxAttempts / kHyp), dim3(32 * kHyp), 0, s, R);
   FoldArgs fa;
   fa.to_tracks = 0;
   fa.mask = mask;
