@@ -547,7 +547,15 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(cudaStreamCreateWithPriority(&fe->stream_p, cudaStreamNonBlocking, prio_hi));
     CUC(cudaStreamCreateWithPriority(&fe->stream_f, cudaStreamNonBlocking, prio_hi));
   }
-  CUC(cudaStreamCreateWithFlags(&fe->stream_t1, cudaStreamNonBlocking));
+  {
+    // The temporal chain is the one stage that is serial from window to window (it sets the
+    // period): its CTAs go first whenever an SM has room, ahead of the stereo LKs of the two
+    // windows before.  ESVIO_T1_PRIO=0 (experiments): default priority, as before.
+    int prio_lo = 0, prio_hi = 0;
+    CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    static const int t1_hi = getenv("ESVIO_T1_PRIO") ? atoi(getenv("ESVIO_T1_PRIO")) : 1;
+    CUC(cudaStreamCreateWithPriority(&fe->stream_t1, cudaStreamNonBlocking, t1_hi ? prio_hi : prio_lo));
+  }
   CUC(cudaStreamCreateWithFlags(&fe->stream_s[0], cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&fe->stream_s[1], cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&fe->stream_c, cudaStreamNonBlocking));

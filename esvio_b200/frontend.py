@@ -193,7 +193,8 @@ class EventFrontEnd:
             self._h = None
 
     def __del__(self):
-        self.close()
+        if _capi is not None:   # at interpreter shutdown the module globals may already be gone
+            self.close()
 
     def _chk(self, st, where):
         if st != _capi.OK:
@@ -582,7 +583,8 @@ class EventFrontEndGroup:
             self._h = None
 
     def __del__(self):
-        self.close()
+        if _capi is not None:
+            self.close()
 
     def reset(self):
         self._chk(_capi.lib().esvio_fe_group_reset(self._h), "group_reset")
