@@ -494,6 +494,76 @@ static int reset_state(esvio_fe* fe) {
   return ESVIO_FE_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// SM partition (CUDA green contexts).  Inside the pipeline the kernels of the temporal chain --
+// the one stage that is serial from window to window and so sets the period -- share every SM's
+// issue slots, shared memory and L1 with the event stage and the stereo LKs of five other
+// windows and run 1.3-1.5x slower than alone.  With ESVIO_T1_SMS=<n> (n a multiple of 8) the
+// device's SMs are split into two green contexts: the temporal chain's stream runs on n SMs of
+// its own, every other stream of the handle on the rest.  Same address space, same events; only
+// the streams differ.  One pair of contexts per device and per n, shared by all handles.
+// ------------------------------------------------------------------------------------------
+static thread_local bool g_creating_group_member = false;  // groups keep the whole device
+struct SmPartition {
+  CUgreenCtx chain = nullptr, rest = nullptr;
+  int n = 0;
+  bool tried = false;
+  CUresult (*stream_create)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+};
+static SmPartition g_partition[64];
+static std::mutex g_partition_mutex;
+
+static SmPartition* sm_partition(int dev, int n_chain) {
+  if (dev < 0 || dev >= 64 || n_chain <= 0) return nullptr;
+  std::lock_guard<std::mutex> lk(g_partition_mutex);
+  SmPartition& P = g_partition[dev];
+  if (P.tried) return (P.chain && P.n == n_chain) ? &P : nullptr;
+  P.tried = true;
+  auto entry = [](const char* name) -> void* {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return fn;
+  };
+  auto dev_get = (CUresult (*)(CUdevice*, int))entry("cuDeviceGet");
+  auto get_res = (CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType))entry("cuDeviceGetDevResource");
+  auto split = (CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int,
+                             unsigned int))entry("cuDevSmResourceSplitByCount");
+  auto gen = (CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int))entry("cuDevResourceGenerateDesc");
+  auto create = (CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int))entry("cuGreenCtxCreate");
+  P.stream_create = (CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int))entry("cuGreenCtxStreamCreate");
+  if (!dev_get || !get_res || !split || !gen || !create || !P.stream_create) return nullptr;
+  CUdevice cd;
+  CUdevResource all, part, rem;
+  unsigned int n_groups = 1;
+  CUdevResourceDesc d_chain, d_rest;
+  if (dev_get(&cd, dev) != CUDA_SUCCESS || get_res(cd, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return nullptr;
+  if (split(&part, &n_groups, &all, &rem, 0, (unsigned)n_chain) != CUDA_SUCCESS || n_groups != 1) return nullptr;
+  if (gen(&d_chain, &part, 1) != CUDA_SUCCESS || gen(&d_rest, &rem, 1) != CUDA_SUCCESS) return nullptr;
+  CUgreenCtx a = nullptr, b = nullptr;
+  if (create(&a, d_chain, cd, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return nullptr;
+  if (create(&b, d_rest, cd, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return nullptr;
+  P.chain = a, P.rest = b, P.n = n_chain;
+  if (getenv("ESVIO_FE_VERBOSE"))
+    fprintf(stderr, "esvio_fe: SM partition on device %d: %u SMs for the temporal chain, %u for the rest\n", dev,
+            part.sm.smCount, rem.sm.smCount);
+  return &P;
+}
+
+// a non-blocking stream of the given priority: in the partition's green context when there is one
+static cudaError_t make_stream(cudaStream_t* out, SmPartition* P, bool chain, int priority) {
+  if (P) {
+    CUstream st = nullptr;
+    if (P->stream_create(&st, chain ? P->chain : P->rest, CU_STREAM_NON_BLOCKING, priority) == CUDA_SUCCESS) {
+      *out = st;
+      return cudaSuccess;
+    }
+    return cudaErrorUnknown;
+  }
+  return cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, priority);
+}
+
 FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
   if (!cfg || !out) return ESVIO_FE_EINVAL;
   *out = nullptr;
@@ -536,28 +606,26 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     free_all(fe);
     return ESVIO_FE_ENODEV;
   }
-  CUC(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
   {
-    // the event-stage kernels are short, wide and latency-bound: let their CTAs go first when
-    // the long one-CTA-per-point LK kernels of other windows are also pending
     int prio_lo = 0, prio_hi = 0;
     CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    CUC(cudaStreamCreateWithPriority(&fe->stream_b, cudaStreamNonBlocking, prio_hi));
-    CUC(cudaStreamCreateWithPriority(&fe->stream_e, cudaStreamNonBlocking, prio_hi));
-    CUC(cudaStreamCreateWithPriority(&fe->stream_p, cudaStreamNonBlocking, prio_hi));
-    CUC(cudaStreamCreateWithPriority(&fe->stream_f, cudaStreamNonBlocking, prio_hi));
-  }
-  {
+    static const int chain_sms = getenv("ESVIO_T1_SMS") ? atoi(getenv("ESVIO_T1_SMS")) : 0;
+    SmPartition* part = g_creating_group_member ? nullptr : sm_partition(fe->dev, chain_sms);
+    CUC(make_stream(&fe->stream, part, false, prio_lo));
+    // the event-stage kernels are short, wide and latency-bound: let their CTAs go first when
+    // the long one-CTA-per-point LK kernels of other windows are also pending
+    CUC(make_stream(&fe->stream_b, part, false, prio_hi));
+    CUC(make_stream(&fe->stream_e, part, false, prio_hi));
+    CUC(make_stream(&fe->stream_p, part, false, prio_hi));
+    CUC(make_stream(&fe->stream_f, part, false, prio_hi));
     // The temporal chain is the one stage that is serial from window to window (it sets the
     // period): its CTAs go first whenever an SM has room, ahead of the stereo LKs of the two
     // windows before.  ESVIO_T1_PRIO=0 (experiments): default priority, as before.
-    int prio_lo = 0, prio_hi = 0;
-    CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     static const int t1_hi = getenv("ESVIO_T1_PRIO") ? atoi(getenv("ESVIO_T1_PRIO")) : 1;
-    CUC(cudaStreamCreateWithPriority(&fe->stream_t1, cudaStreamNonBlocking, t1_hi ? prio_hi : prio_lo));
+    CUC(make_stream(&fe->stream_t1, part, true, t1_hi ? prio_hi : prio_lo));
+    CUC(make_stream(&fe->stream_s[0], part, false, prio_lo));
+    CUC(make_stream(&fe->stream_s[1], part, false, prio_lo));
   }
-  CUC(cudaStreamCreateWithFlags(&fe->stream_s[0], cudaStreamNonBlocking));
-  CUC(cudaStreamCreateWithFlags(&fe->stream_s[1], cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&fe->stream_c, cudaStreamNonBlocking));
 
   fe->esb[0].n_cams = fe->esb[1].n_cams = 2;
@@ -1641,7 +1709,9 @@ FE_API int esvio_fe_group_create(const esvio_fe_config* cfg, int32_t n_streams,
   g->S = n_streams;
   g->dev = cfg->device_id;
   for (int i = 0; i < n_streams; ++i) {
+    g_creating_group_member = true;
     const int rc = esvio_fe_create(cfg, &g->m[i]);
+    g_creating_group_member = false;
     if (rc != ESVIO_FE_OK) {
       g->S = i;
       esvio_fe_group_destroy(g);

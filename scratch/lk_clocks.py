@@ -8,6 +8,8 @@ import bench
 wl = sys.argv[1] if len(sys.argv) > 1 else "stereo_vga_5mevs"
 w, cfg, pub_div = bench.workload_cfg(wl)
 cfg = dict(cfg, device_id=0, max_events_per_window=int(w["rate"]/30)+64)
+if len(sys.argv) > 2:
+    cfg["max_cnt"] = int(sys.argv[2])
 wins = bench.gen_windows(w, 0, 7)
 fe = frontend.EventFrontEnd(cfg)
 L = C.CDLL(_capi.LIB_PATH)
