@@ -1069,6 +1069,7 @@ def test_teacher_forced_every_window(fe_mod, ora, name, W, H, rate, n_windows, p
             fe.stage_set_tracks(prev_time, next_id, prev)
         g = fe.track(t_ref, L, R, pub)
         o = ot.track(t_ref, L, R, pub)
+        prev_t_for_vel = prev_time
         prev, prev_time, next_id = o, t_ref, ot.next_id()
         new_g, new_o = g["track_cnt"] == 1, o["track_cnt"] == 1
         same = (np.array_equal(g["id"], o["id"]) and np.array_equal(g["track_cnt"], o["track_cnt"])
@@ -1089,6 +1090,16 @@ def test_teacher_forced_every_window(fe_mod, ora, name, W, H, rate, n_windows, p
         d_px.append(dl)
         d_un.append(np.maximum(np.abs(g["un_x"][~new_g][ia] - o["un_x"][~new_o][ib]),
                                np.abs(g["un_y"][~new_g][ia] - o["un_y"][~new_o][ib])))
+        # ptsVelocity (feature_tracker.cpp:1004-1045): both sides divide by the same dt and
+        # subtract the same previous point (the carried state is the reference's), so the
+        # velocities differ by the difference of the undistorted points over dt and float rounding
+        if k > 0 and len(ia):
+            dt = t_ref - prev_t_for_vel
+            for vk, uk in (("vx", "un_x"), ("vy", "un_y")):
+                dv = np.abs(g[vk][~new_g][ia] - o[vk][~new_o][ib])
+                du = np.abs(g[uk][~new_g][ia] - o[uk][~new_o][ib])
+                assert (dv <= du / dt * 1.001 + 2e-5).all(), (k, vk, float(dv.max()), float((du / dt).max()))
+            assert (g["vx"][new_g] == 0).all() and (g["vy"][new_g] == 0).all(), k   # new ids: velocity 0
         # right points of the ids whose left points agree (a new corner on another pixel is
         # another feature under the same id)
         pos_g = dict(zip(g["id"].tolist(), zip(g["u"].tolist(), g["v"].tolist())))
