@@ -53,9 +53,7 @@ constexpr int kLkThreads = 256;
 constexpr int kLkWarps = kLkThreads / 32;
 constexpr int kMaxNWarps = 4;                      // Newton group: warps 0 .. NW-1, NW = 1, 2 or 4
 constexpr int kSFirst = 4, kSWarps = 4;            // staging group: warps 4-7
-constexpr int kTplWarps = 2;                       // warps per level in the template phase
-constexpr int kPxT = (kWin * kWin + 32 * kTplWarps - 1) / (32 * kTplWarps);  // 7
-constexpr int kTplLen = 32 * kTplWarps * kPxT;     // 448 template slots per level
+constexpr int kTplLen = 448;                       // template slots per level (441 used)
 constexpr int kIP = 24;  // staged intensity patch (window + bilinear tap + Scharr ring)
 constexpr int kDP = 22;  // derivative patch (window + bilinear tap)
 constexpr int kJM = 5;   // margin of the staged search region
@@ -63,7 +61,6 @@ constexpr int kJR = kWin + 1 + 2 * kJM;  // 32
 // Row stride of the search region in 32-bit words: 21 (mod 32), so that the word of window
 // pixel k = 21 * y + x sits in bank (k + const) % 32 and 32 consecutive pixels never collide.
 constexpr int kQS = 53;
-static_assert(kMaxLevels * kTplWarps == kLkWarps, "two warps per level in the template phase");
 
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
@@ -94,30 +91,27 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
   w11 = (1 << kWBits) - w00 - w01 - w10;
 }
 
-struct LkPatches {
-  uint8_t I[kMaxLevels][kIP][kIP];      // template neighbourhoods of all levels
-  short2 D[kMaxLevels][kDP][kDP];       // their Scharr derivatives
-};
 struct LkShared {
-  // The patches only live until the templates are built (phases 1-3), the search regions only
-  // from then on: they share their bytes, which takes the CTA from 34.7 to 24.7 KB -- four
-  // CTAs per SM instead of three next to the event-stage kernels.
-  union {
-    LkPatches P;
-    // search regions (current level / prefetched next level) as packed 2x2 neighbourhoods:
-    // Q[r][c] = J(r,c) | J(r,c+1) << 8 | J(r+1,c) << 16 | J(r+1,c+1) << 24
-    uint32_t Q[2][kJR][kQS];
-  };
-  short Tw[kMaxLevels][kTplLen];        // templates: Iw, Ixw, Iyw per window pixel
-  short Tx[kMaxLevels][kTplLen];
-  short Ty[kMaxLevels][kTplLen];
-  long long Apart[kMaxLevels][kTplWarps][3];  // per-warp sums of Ixw^2, Ixw*Iyw, Iyw^2
+  // search regions (current level / prefetched next level) as packed 2x2 neighbourhoods:
+  // Q[r][c] = J(r,c) | J(r,c+1) << 8 | J(r+1,c) << 16 | J(r+1,c+1) << 24
+  uint32_t Q[2][kJR][kQS];
+  // The template neighbourhoods of all levels arrive in one batch of loads; only the top
+  // level's template is built before the iterations start, the others one level ahead by the
+  // staging group while the Newton group iterates.  So what is live at any time is: the
+  // patches, ONE level's Scharr derivatives, and the templates of two levels (the one being
+  // iterated and the one being built) -- 23 KB per CTA, like the round-1 layout that built
+  // all four templates up front.
+  uint8_t I[kMaxLevels][kIP][kIP];
+  short2 D[kDP][kDP];
+  short Tw[2][kTplLen];                 // templates of level L in slot L & 1: Iw, Ixw, Iyw per window pixel
+  short Tx[2][kTplLen];
+  short Ty[2][kTplLen];
+  long long Apart[2][kLkWarps][3];      // per-warp sums of Ixw^2, Ixw*Iyw, Iyw^2 (unused warps: 0)
   int flag_win[kMaxLevels];             // 1: template window outside the image
-  int4 part[2][kMaxNWarps];                // per-iteration partial sums (b1, b2 as low 16 bits / rest) of the N-group warps
+  int4 part[2][kMaxNWarps];             // per-iteration partial sums (b1, b2 as low 16 bits / rest) of the N-group warps
   float2 np[2];                         // result of a level, slot = Newton levels run so far & 1
   int st[2];
 };
-static_assert(sizeof(LkPatches) <= sizeof(uint32_t) * 2 * kJR * kQS, "patches fit under the search regions");
 
 // exact sum over the warp of one int32 per lane, as int64
 __device__ __forceinline__ long long warp_sum_exact(int v) {
@@ -186,6 +180,76 @@ __device__ __forceinline__ void stage_J(uint32_t (*Q)[kQS], const uint8_t* __res
   stage_J_store<NW>(Q, col, wi);
 }
 
+// Scharr derivatives of level L's patch into S.D, zero outside the image like the constant
+// border of OpenCV's derivative buffer; NWB warps, this one is number wi.
+template <int NWB>
+__device__ __forceinline__ void lk_scharr_level(LkShared& S, const PyrDesc& pd, float2 p0, int L, int wi) {
+  const float sc = 1.f / (float)(1 << L);
+  const int ipx = (int)floorf(p0.x * sc - (float)kHalfWin), ipy = (int)floorf(p0.y * sc - (float)kHalfWin);
+  const int w = pd.w[L], h = pd.h[L];
+  for (int i = wi * 32 + lane_id(); i < kDP * kDP; i += 32 * NWB) {
+    const int r = i / kDP, c = i - r * kDP;
+    const int gx = ipx + c, gy = ipy + r;
+    short2 d = make_short2(0, 0);
+    if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+      const uint8_t *up = S.I[L][r], *mid = S.I[L][r + 1], *dn = S.I[L][r + 2];
+      const int t0l = (up[c] + dn[c]) * 3 + mid[c] * 10;
+      const int t0r = (up[c + 2] + dn[c + 2]) * 3 + mid[c + 2] * 10;
+      const int t1l = dn[c] - up[c], t1m = dn[c + 1] - up[c + 1], t1r = dn[c + 2] - up[c + 2];
+      d.x = (short)(t0r - t0l);
+      d.y = (short)((t1r + t1l) * 3 + t1m * 10);
+    }
+    S.D[r][c] = d;
+  }
+}
+
+// Template of level L (Iw, Ixw, Iyw at the 21x21 window pixels, bilinear at the sub-pixel
+// position of p0) into slot L & 1, the normal matrix's exact integer sums per warp; NWB warps.
+template <int NWB>
+__device__ __forceinline__ void lk_template_level(LkShared& S, const PyrDesc& pd, float2 p0, int L, int wi) {
+  constexpr int kPx = (kWin * kWin + 32 * NWB - 1) / (32 * NWB);
+  const int lane = lane_id(), tb = L & 1;
+  const float sc = 1.f / (float)(1 << L);
+  const float ppx = p0.x * sc - (float)kHalfWin, ppy = p0.y * sc - (float)kHalfWin;
+  const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
+  const bool outside = ipx < -kWin || ipx >= pd.w[L] || ipy < -kWin || ipy >= pd.h[L];
+  if (wi == 0 && lane == 0) S.flag_win[L] = outside ? 1 : 0;
+  if (NWB < kLkWarps && wi == 0 && lane < 3 * (kLkWarps - NWB)) (&S.Apart[tb][NWB][0])[lane] = 0;
+  if (outside) return;
+  const float a = ppx - (float)ipx, b = ppy - (float)ipy;
+  int iw00, iw01, iw10, iw11;
+  bilinear_weights(a, b, iw00, iw01, iw10, iw11);
+  int s11 = 0, s12 = 0, s22 = 0;
+#pragma unroll
+  for (int j = 0; j < kPx; ++j) {
+    const int kk = wi * 32 + lane + 32 * NWB * j;
+    if (kk < kWin * kWin) {
+      const int y = kk / kWin, x = kk - y * kWin;
+      const int iv = descale(S.I[L][y + 1][x + 1] * iw00 + S.I[L][y + 1][x + 2] * iw01 +
+                                 S.I[L][y + 2][x + 1] * iw10 + S.I[L][y + 2][x + 2] * iw11,
+                             kWBits - 5);
+      const short2 d00 = S.D[y][x], d01 = S.D[y][x + 1], d10 = S.D[y + 1][x], d11 = S.D[y + 1][x + 1];
+      const int ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, kWBits);
+      const int iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, kWBits);
+      s11 += ix * ix;
+      s12 += ix * iy;
+      s22 += iy * iy;
+      S.Tw[tb][kk] = (short)iv;
+      S.Tx[tb][kk] = (short)ix;
+      S.Ty[tb][kk] = (short)iy;
+    }
+  }
+  const long long t11 = warp_sum_exact(s11), t12 = warp_sum_exact(s12), t22 = warp_sum_exact(s22);
+  if (lane == 0) {
+    S.Apart[tb][wi][0] = t11;
+    S.Apart[tb][wi][1] = t12;
+    S.Apart[tb][wi][2] = t22;
+  }
+}
+
+// barrier of the four warps of the staging group
+__device__ __forceinline__ void bar_staging() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kSWarps) : "memory"); }
+
 struct Region {
   int level, rx0, ry0;  // level -1: nothing staged
 };
@@ -233,13 +297,13 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
   __syncthreads();  // previous use of S is over
   LK_CLK(0);
 
-  uint32_t top_col[kJR / kLkWarps + 1];
   // ---- phase 1: ONE batch of loads: the intensity patches of all levels (they depend on the
   // point only, not on the flow) and the search region of the top level around `np`.
   // Intensities reflect-101 outside the image like the border buildOpticalFlowPyramid adds.
   {
     constexpr int kPerThread = (kMaxLevels * kIP * kIP + kLkThreads - 1) / kLkThreads;  // 9
     uint8_t v[kPerThread];
+    uint32_t top_col[kJR / kLkWarps + 1];
 #pragma unroll
     for (int q = 0; q < kPerThread; ++q) {
       const int i = tid + q * kLkThreads;
@@ -255,88 +319,24 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
                        reflect101_nb(ipx - 1 + c, w));
       }
     }
-    // the top level's search region travels with them, but lands in shared memory only after
-    // phase 3: until then the patches occupy those bytes
     if (rc.level >= 0)
       stage_J_load<kLkWarps>(top_col, J + pd.off[top], pd.w[top], pd.h[top], pd.pitch[top], rc.rx0,
                              rc.ry0, warp);
 #pragma unroll
     for (int q = 0; q < kPerThread; ++q) {
       const int i = tid + q * kLkThreads;
-      if (i < nlev * kIP * kIP) (&S.P.I[0][0][0])[i] = v[q];
+      if (i < nlev * kIP * kIP) (&S.I[0][0][0])[i] = v[q];
     }
+    if (rc.level >= 0) stage_J_store<kLkWarps>(S.Q[0], top_col, warp);
   }
   __syncthreads();
   LK_CLK(1);
-  // ---- phase 2: Scharr derivatives, zero outside the image like the constant border of
-  // OpenCV's derivative buffer
-#pragma unroll 4
-  for (int i = tid; i < nlev * kDP * kDP; i += kLkThreads) {
-    const int L = i / (kDP * kDP), rem = i - L * (kDP * kDP);
-    const int r = rem / kDP, c = rem - r * kDP;
-    const float sc = 1.f / (float)(1 << L);
-    const int ipx = (int)floorf(p0.x * sc - half), ipy = (int)floorf(p0.y * sc - half);
-    const int gx = ipx + c, gy = ipy + r;
-    short2 d = make_short2(0, 0);
-    if (gx >= 0 && gx < pd.w[L] && gy >= 0 && gy < pd.h[L]) {
-      const uint8_t *up = S.P.I[L][r], *mid = S.P.I[L][r + 1], *dn = S.P.I[L][r + 2];
-      const int t0l = (up[c] + dn[c]) * 3 + mid[c] * 10;
-      const int t0r = (up[c + 2] + dn[c + 2]) * 3 + mid[c + 2] * 10;
-      const int t1l = dn[c] - up[c], t1m = dn[c + 1] - up[c + 1], t1r = dn[c + 2] - up[c + 2];
-      d.x = (short)(t0r - t0l);
-      d.y = (short)((t1r + t1l) * 3 + t1m * 10);
-    }
-    S.P.D[L][r][c] = d;
-  }
+  // ---- phases 2 and 3, for the TOP level only, by all eight warps: Scharr derivatives, then
+  // the template.  The lower levels' are built by the staging group during the iterations.
+  lk_scharr_level<kLkWarps>(S, pd, p0, top, warp);
   __syncthreads();
   LK_CLK(2);
-  // ---- phase 3: warps 2L and 2L+1 build the template of level L
-  {
-    const int L = warp / kTplWarps, sub = warp % kTplWarps;
-    if (L < nlev) {
-      const float sc = 1.f / (float)(1 << L);
-      const float ppx = p0.x * sc - half, ppy = p0.y * sc - half;
-      const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
-      const bool outside = ipx < -kWin || ipx >= pd.w[L] || ipy < -kWin || ipy >= pd.h[L];
-      if (sub == 0 && lane == 0) S.flag_win[L] = outside ? 1 : 0;
-      if (!outside) {
-        const float a = ppx - (float)ipx, b = ppy - (float)ipy;
-        int iw00, iw01, iw10, iw11;
-        bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-        int s11 = 0, s12 = 0, s22 = 0;
-#pragma unroll
-        for (int j = 0; j < kPxT; ++j) {
-          const int kk = sub * 32 + lane + 32 * kTplWarps * j;
-          int iv = 0, ix = 0, iy = 0;
-          if (kk < kWin * kWin) {
-            const int y = kk / kWin, x = kk - y * kWin;
-            iv = descale(S.P.I[L][y + 1][x + 1] * iw00 + S.P.I[L][y + 1][x + 2] * iw01 +
-                             S.P.I[L][y + 2][x + 1] * iw10 + S.P.I[L][y + 2][x + 2] * iw11,
-                         kWBits - 5);
-            const short2 d00 = S.P.D[L][y][x], d01 = S.P.D[L][y][x + 1], d10 = S.P.D[L][y + 1][x],
-                         d11 = S.P.D[L][y + 1][x + 1];
-            ix = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, kWBits);
-            iy = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, kWBits);
-            s11 += ix * ix;
-            s12 += ix * iy;
-            s22 += iy * iy;
-          }
-          S.Tw[L][kk] = (short)iv;
-          S.Tx[L][kk] = (short)ix;
-          S.Ty[L][kk] = (short)iy;
-        }
-        const long long t11 = warp_sum_exact(s11), t12 = warp_sum_exact(s12),
-                        t22 = warp_sum_exact(s22);
-        if (lane == 0) {
-          S.Apart[L][sub][0] = t11;
-          S.Apart[L][sub][1] = t12;
-          S.Apart[L][sub][2] = t22;
-        }
-      }
-    }
-  }
-  __syncthreads();  // templates built: the patches are dead, their bytes become the search regions
-  if (rc.level >= 0) stage_J_store<kLkWarps>(S.Q[0], top_col, warp);
+  lk_template_level<kLkWarps>(S, pd, p0, top, warp);
   __syncthreads();
   LK_CLK(3);
 
@@ -360,26 +360,34 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
       np.y *= 2.f;
     }
     // normal matrix of the level: every thread, from the exact integer sums
+    const int tb = level & 1;  // slot of this level's template
     float A11 = 0.f, A12 = 0.f, A22 = 0.f;
     int flag = S.flag_win[level];
     if (!flag) {
-      A11 = (float)(S.Apart[level][0][0] + S.Apart[level][1][0]) * flt_scale;
-      A12 = (float)(S.Apart[level][0][1] + S.Apart[level][1][1]) * flt_scale;
-      A22 = (float)(S.Apart[level][0][2] + S.Apart[level][1][2]) * flt_scale;
+      long long a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll
+      for (int q = 0; q < kLkWarps; ++q) {
+        a11 += S.Apart[tb][q][0];
+        a12 += S.Apart[tb][q][1];
+        a22 += S.Apart[tb][q][2];
+      }
+      A11 = (float)a11 * flt_scale;
+      A12 = (float)a12 * flt_scale;
+      A22 = (float)a22 * flt_scale;
       const float det = A11 * A22 - A12 * A12;
       const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) /
                             (float)(2 * kWin * kWin);
       if ((double)min_eig < 1e-4 || det < FLT_EPSILON) flag = 2;
     }
-    if (flag != 0) {  // template window outside the image, or minEig / determinant test failed
-      if (level == 0) st = 0;
-      continue;
-    }
-    const float D = 1.f / (A11 * A22 - A12 * A12);
+    // flag != 0: template window outside the image, or minEig / determinant test failed: OpenCV
+    // gives up on the level (the staging group still builds the next level's template)
+    const bool skip = flag != 0;
+    if (skip && level == 0) st = 0;
+    const float D = skip ? 0.f : 1.f / (A11 * A22 - A12 * A12);
     LK_CLK(4 + 4 * level);
     // the current buffer must hold this level around the start position (it does when the
     // prefetch of the level above predicted well, and for the top level from phase 1)
-    {
+    if (!skip) {
       const Region want = region_around(level, w, h, np.x, np.y);
       if (want.level >= 0 && !region_covers(rc, level, want.rx0 + kJM, want.ry0 + kJM)) {
         rc = want;
@@ -390,22 +398,27 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
     LK_CLK(5 + 4 * level);
     // the next level's region around the predicted position 2 * np
     rn.level = -1;
-    if (level > 0)
+    if (!skip && level > 0)
       rn = region_around(level - 1, pd.w[level - 1], pd.h[level - 1], 2.f * np.x, 2.f * np.y);
     const int slot = n_newton & 1;
     if (warp >= kSFirst) {
       if (rn.level >= 0)
         stage_J<kSWarps>(S.Q[cur ^ 1], J + pd.off[level - 1], pd.w[level - 1], pd.h[level - 1],
                          pd.pitch[level - 1], rn.rx0, rn.ry0, warp - kSFirst);
-    } else if (n_group) {
+      if (level > 0) {  // next level's derivatives and template, into the other template slot
+        lk_scharr_level<kSWarps>(S, pd, p0, level - 1, warp - kSFirst);
+        bar_staging();
+        lk_template_level<kSWarps>(S, pd, p0, level - 1, warp - kSFirst);
+      }
+    } else if (n_group && !skip) {
       int Iw[kPxN], Dx[kPxN], Dy[kPxN];
 #pragma unroll
       for (int j = 0; j < kPxN; ++j) {
         const int kk = tid + kNThreads * j;
         const bool on = kk < kWin * kWin;
-        Iw[j] = on ? S.Tw[level][kk] : 0;
-        Dx[j] = on ? S.Tx[level][kk] : 0;  // zero in the unused slots: they add nothing
-        Dy[j] = on ? S.Ty[level][kk] : 0;
+        Iw[j] = on ? S.Tw[tb][kk] : 0;
+        Dx[j] = on ? S.Tx[tb][kk] : 0;  // zero in the unused slots: they add nothing
+        Dy[j] = on ? S.Ty[tb][kk] : 0;
       }
       float npx = np.x - half, npy = np.y - half;
       int rx0 = rc.rx0, ry0 = rc.ry0;
@@ -533,12 +546,14 @@ __device__ void lk_point(LkShared& S, const PyrDesc& pd, const uint8_t* __restri
         S.st[slot] = st;
       }
     }
-    __syncthreads();  // level done: its result and the prefetched region are visible to all
-    np = S.np[slot];
-    st = S.st[slot];
-    ++n_newton;
-    cur ^= 1;
-    rc = rn;
+    __syncthreads();  // level done: its result, the prefetched region and the next template are visible to all
+    if (!skip) {
+      np = S.np[slot];
+      st = S.st[slot];
+      ++n_newton;
+      cur ^= 1;
+      rc = rn;
+    }
   }
   LK_CLK(20);
   np_out = np;
