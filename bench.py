@@ -430,7 +430,7 @@ class StreamBench:
         return out
 
     def host_leg(self, flush, comm_id=None, sync=False):
-        """e2e: pinned host SoA buffers through esvio_fe_track_submit / _wait (H2D of the events
+        """e2e: pinned host SoA buffers (one block per window) through esvio_fe_track_submit / _wait (H2D of the events
         and D2H of the track records inside the timed region); `sync`: the same windows once
         more through the synchronous esvio_fe_track, host wall clock."""
         fr = self.fr
@@ -438,7 +438,9 @@ class StreamBench:
         gather = comm_id is not None
         if gather:
             fe.comm_init(comm_id, self.rank, self.world)
-        pw = [(fr._Ev(fr.PinnedEvents(L)), fr._Ev(fr.PinnedEvents(R)), t) for L, R, t in self.wins]
+        # both cameras of a window in one pinned block (esvio_fe_soa_layout_stereo): one transfer
+        blocks = [fr.PinnedStereoEvents(L, R) for L, R, _ in self.wins]
+        pw = [(fr._Ev(b.left), fr._Ev(b.right), w[2]) for b, w in zip(blocks, self.wins)]
         ms, launches, last, checksum = self._timed(fe, pw, gather, flush, 2)
         out = {"ms": ms, "launches": launches, "last": last, "checksum": checksum}
         fe.close()

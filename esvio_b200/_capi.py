@@ -50,7 +50,10 @@ class Motion(C.Structure):
 class Events(C.Structure):
     _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("t", C.c_void_p), ("p", C.c_void_p),
                 ("aos", C.c_void_p), ("n", C.c_size_t), ("on_device", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("flags", C.c_int32)]
+
+
+EVENTS_STEREO_BLOCK = 1
 
 
 class Stats(C.Structure):
@@ -104,6 +107,8 @@ SYMBOLS = {
     "esvio_fe_group_sae_ts_ms": (C.c_int, [_H, _pf]),
     "esvio_fe_time_surface": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_size_t]),
     "esvio_fe_soa_layout": (None, [C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "esvio_fe_soa_layout_stereo": (None, [C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                          C.POINTER(C.c_size_t)]),
     "esvio_fe_host_alloc": (C.c_void_p, [C.c_size_t]),
     "esvio_fe_host_free": (None, [C.c_void_p]),
     "esvio_fe_device_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -87,6 +87,8 @@ class _Ev:
             self.s.aos = a.ctypes.data
             self.s.n = len(a)
             return
+        if getattr(ev, "stereo_block", False):
+            self.s.flags = _capi.EVENTS_STEREO_BLOCK
         x, y, t, p = ev[:4]
         x = np.ascontiguousarray(x, np.uint16)
         y = np.ascontiguousarray(y, np.uint16)
@@ -157,6 +159,48 @@ class PinnedEvents:
 
     def __getitem__(self, i):
         return self.arrays[i]
+
+    def free(self):
+        for p in self._raw:
+            _capi.lib().esvio_fe_host_free(p)
+        self._raw = []
+
+
+class _PinnedView:
+    def __init__(self, arrays):
+        self.arrays = tuple(arrays)
+        self.n = len(arrays[0])
+
+    def __getitem__(self, i):
+        return self.arrays[i]
+
+
+class PinnedStereoEvents:
+    """Both cameras' SoA event arrays of a window in ONE block of pinned host memory laid out by
+    esvio_fe_soa_layout_stereo: the window crosses PCIe as a single copy.  `.left` / `.right`
+    are (x, y, t, p) views to hand to submit()."""
+
+    def __init__(self, left, right):
+        L = _capi.lib()
+        nl, nr = len(left[0]), len(right[0])
+        ol, orr = (C.c_size_t * 4)(), (C.c_size_t * 4)()
+        total = C.c_size_t()
+        L.esvio_fe_soa_layout_stereo(nl, nr, ol, orr, C.byref(total))
+        ptr = L.esvio_fe_host_alloc(max(total.value, 16))
+        if not ptr:
+            raise MemoryError("esvio_fe_host_alloc failed")
+        self._raw = [ptr]
+        self._buf = (C.c_uint8 * max(total.value, 16)).from_address(ptr)
+        sides = []
+        for ev, n, off in ((left, nl, ol), (right, nr, orr)):
+            views = []
+            for a, dt, o in zip(ev[:4], (np.uint16, np.uint16, np.float64, np.uint8), off):
+                v = np.frombuffer(self._buf, dtype=dt, count=n, offset=o)
+                v[:] = np.ascontiguousarray(a, dt)
+                views.append(v)
+            sides.append(_PinnedView(views))
+        self.left, self.right = sides
+        self.left.stereo_block = self.right.stereo_block = True
 
     def free(self):
         for p in self._raw:

@@ -836,6 +836,34 @@ def test_single_copy_soa_block_equals_separate_arrays(fe_mod):
     fa.close(); fb.close()
 
 
+def test_stereo_block_one_copy_equals_separate_arrays(fe_mod):
+    """Both cameras of a window in ONE pinned block laid out by esvio_fe_soa_layout_stereo (a
+    single H2D copy for the window) give the same result as eight separate arrays; ragged and
+    empty cameras fall back to the per-camera path."""
+    W, H = 346, 260
+    fa, _ = _mk(fe_mod, W, H, use_ransac=1)
+    fb, _ = _mk(fe_mod, W, H, use_ransac=1)
+    s = synth.StereoEventStream(W, H, 1.0e6)
+    for k in range(5):
+        L, R, t_ref = s.stereo_window(k)
+        if k == 2:
+            L = tuple(a[:12345] for a in L)        # odd lengths: the paddings of the layout matter
+            R = tuple(a[:7001] for a in R)
+        if k == 3:
+            R = tuple(a[:0] for a in R)            # an empty camera: not a stereo block, still fine
+        blk = fe_mod.PinnedStereoEvents(L, R)
+        a = fa.track(t_ref, L, R, k % 2 == 0)
+        b = fb.track(t_ref, blk.left, blk.right, k % 2 == 0)
+        for key in ("id", "u", "v", "id_right", "ru", "rv"):
+            assert np.array_equal(a[key], b[key]), (k, key)
+        for cam in (0, 1):
+            for x, y in zip(fa.sae_planes(cam), fb.sae_planes(cam)):
+                assert np.array_equal(x, y)
+        assert np.array_equal(fa.time_surface(1), fb.time_surface(1))
+        blk.free()
+    fa.close(); fb.close()
+
+
 @pytest.mark.parametrize("W,H,rate,depth", [(346, 260, 1.0e6, 1), (640, 480, 5.0e6, 3), (346, 260, 1.0e6, 6)])
 def test_left_right_split_equals_one_handle(fe_mod, W, H, rate, depth):
     """SURVEY.md 8e row 2 through the C ABI: the right camera's SAE / time surface / pyramid on
