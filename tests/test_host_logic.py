@@ -215,3 +215,33 @@ def test_left_right_split_protocol_gloo_world2():
                        for k in range(5)]
     with pytest.raises(ValueError):
         shard.LeftRightSplit(None, 2, exchange_stream=0)
+
+def test_soa_layouts_are_aligned_and_disjoint():
+    """esvio_fe_soa_layout / esvio_fe_soa_layout_stereo (host-only entry points of the C ABI): every
+    array 16-byte aligned, arrays disjoint and in order, the right camera's block on a 256-byte
+    boundary behind the left one, totals tight -- what the single-transfer staging relies on."""
+    import ctypes as C
+    from esvio_b200 import _capi
+    L = _capi.lib()
+    width = (2, 2, 8, 1)
+    for n in (0, 1, 7, 33333, 166667, 666667):
+        off = (C.c_size_t * 4)()
+        tot = C.c_size_t()
+        L.esvio_fe_soa_layout(n, off, C.byref(tot))
+        end = 0
+        for o, w in zip(off, width):
+            assert o % 16 == 0 and o >= end
+            end = o + w * n
+        assert end <= tot.value < end + 16
+        for nr in (0, 5, n):
+            ol, orr = (C.c_size_t * 4)(), (C.c_size_t * 4)()
+            t2 = C.c_size_t()
+            L.esvio_fe_soa_layout_stereo(n, nr, ol, orr, C.byref(t2))
+            assert list(ol) == list(off)
+            assert orr[0] % 256 == 0 and tot.value <= orr[0] < tot.value + 256
+            offr = (C.c_size_t * 4)()
+            totr = C.c_size_t()
+            L.esvio_fe_soa_layout(nr, offr, C.byref(totr))
+            assert [o - orr[0] for o in orr] == list(offr)
+            assert t2.value == orr[0] + totr.value
+            assert t2.value <= 16 * (n + 64) + 16 * (nr + 64)      # fits the slot's 32 B x capacity block
