@@ -318,6 +318,9 @@ struct CornerParams {
   // and their number; null = flags only
   uint32_t* cand;   // [ceil(n / kCornerBlock) * kCornerBlock]
   int* cand_cnt;    // [ceil(n / kCornerBlock)]
+  // per-pixel plane of k_corner_plane ([H][W] bytes: bit p = Arc* verdict of polarity p, bit 2 + p =
+  // "evaluated"); null: every event evaluates its own pixel
+  uint8_t* plane;
 };
 void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* flags,
                          cudaStream_t s, int64_t* launches);

@@ -193,6 +193,7 @@ struct esvio_fe {
   EventStageBuffers esb[2];  // binned events of even / odd windows: binning of window k+1 runs
                              // while the SAE kernel of window k still reads window k's
   uint8_t* flags[kSlots];   // [slot] Arc* corner flags of the left events
+  uint8_t* corner_plane;    // [H][W] per-pixel Arc* verdicts of the window being flagged (k_corner_plane)
   uint32_t* cand[kSlots];   // [slot] the flagged events' pixels, one list per kCornerBlock events
   int* cand_cnt[kSlots];
   // A window is a graph of short kernels; every node that has no data dependency on another
@@ -442,6 +443,7 @@ static void free_all(esvio_fe* fe) {
   for (int i = 0; i < kSlots; ++i) {
     cudaFree(fe->raw[i][0]);  // raw[i][1] is the second half of the same block
     cudaFree(fe->flags[i]);
+    if (i == 0) cudaFree(fe->corner_plane);
     cudaFree(fe->cand[i]);
     cudaFree(fe->cand_cnt[i]);
     for (cudaEvent_t ev : {fe->c_done[i], fe->b_done[i], fe->k1_done[i], fe->p_done[i], fe->f_done[i],
@@ -670,6 +672,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(cudaMalloc(&fe->raw[c][0], (size_t)fe->cap * 32));
     fe->raw[c][1] = fe->raw[c][0] + (size_t)fe->cap * 16;
     CUC(cudaMalloc(&fe->flags[c], (size_t)fe->cap + 16));
+    if (c == 0) CUC(cudaMalloc(&fe->corner_plane, fe->npx));
     CUC(cudaMalloc(&fe->cand[c], ((size_t)fe->cap + kCornerBlock) * sizeof(uint32_t)));
     CUC(cudaMalloc(&fe->cand_cnt[c], ((size_t)fe->cap / kCornerBlock + 2) * sizeof(int)));
     for (cudaEvent_t* ev : {&fe->c_done[c], &fe->b_done[c], &fe->k1_done[c], &fe->p_done[c], &fe->f_done[c],
@@ -1054,6 +1057,7 @@ static CornerParams corner_params(esvio_fe* fe, int left_idx, int and_ts, int sl
   cp.and_ts_test = and_ts;
   cp.cand = fe->cand[slot];
   cp.cand_cnt = fe->cand_cnt[slot];
+  cp.plane = fe->corner_plane;
   return cp;
 }
 

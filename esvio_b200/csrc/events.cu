@@ -1025,15 +1025,18 @@ __constant__ int8_t c_ring4[20][2] = {{0, 4},   {1, 4},   {2, 3},   {3, 2},  {4,
 // ring element, repeatedly extend the arm (clockwise or counter-clockwise) whose next
 // element is newer, and remember the longest prefix whose elements are all newer than
 // everything outside it.
-template <int N, int LO, int HI>
-__device__ __forceinline__ bool arc_ring_valid(const double* ring) {
+// STRIDE: distance between consecutive ring elements (1 = a thread's own array; > 1 = a column of
+// a shared-memory array [element][thread], which keeps the dynamically indexed ring on chip)
+template <int N, int LO, int HI, int STRIDE = 1>
+__device__ __forceinline__ bool arc_ring_valid(const double* ring_base) {
+  auto R = [&](int i) { return ring_base[i * STRIDE]; };
   int newest = 0;
 #pragma unroll
   for (int i = 1; i < N; ++i)
-    if (ring[i] > ring[newest]) newest = i;
-  double seg_min = ring[newest];
+    if (R(i) > R(newest)) newest = i;
+  double seg_min = R(newest);
   int cw = (newest + 1) % N, ccw = (newest + N - 1) % N;
-  double cw_v = ring[cw], ccw_v = ring[ccw], cw_min = cw_v, ccw_min = ccw_v;
+  double cw_v = R(cw), ccw_v = R(ccw), cw_min = cw_v, ccw_min = ccw_v;
   int seg_len = LO;
   for (int it = 1; it < N; ++it) {
     const bool take_cw = cw_v > ccw_v;
@@ -1047,21 +1050,128 @@ __device__ __forceinline__ bool arc_ring_valid(const double* ring) {
     }
     if (take_cw) {
       cw = (cw + 1) % N;
-      cw_v = ring[cw];
+      cw_v = R(cw);
       cw_min = fmin(cw_min, cw_v);
     } else {
       ccw = (ccw + N - 1) % N;
-      ccw_v = ring[ccw];
+      ccw_v = R(ccw);
       ccw_min = fmin(ccw_min, ccw_v);
     }
   }
   return seg_len <= HI || (seg_len >= N - HI && seg_len <= N - LO);
 }
 
-// Besides the flag of every event the kernel leaves, per CTA of kCornerBlock consecutive
-// events, the flagged events' pixels compacted in stream order (cand[block * kCornerBlock + j],
-// x | y << 16) and their number: the selection kernel then walks a few thousand candidates
-// instead of re-reading the whole window.
+// Everything of EventDetector::isCorner (event_detector.cc:308-544) that depends on the pixel and
+// the polarity only -- the whole test except "t > latest[p] + threshold", which needs the
+// event's own time: not a live time-surface pixel -> no; the opposite polarity fired later ->
+// no; within MIN_DIST + 1 of the border -> no; then the two Arc* circles.  `ring(dx, dy)` returns
+// sae[pol] at (x + dx, y + dy).
+__device__ __forceinline__ bool corner_pixel_cheap(const CornerParams& P, int x, int y, int pol, double2 lat) {
+  if (P.and_ts_test && (double)P.ts[(size_t)y * P.ts_pitch + x] == P.ts_lk_threshold) return false;
+  const double last_same = pol ? lat.y : lat.x, last_opp = pol ? lat.x : lat.y;
+  if (last_opp > last_same) return false;
+  const int border = P.min_dist + 1;
+  return !(x < border || x >= P.W - border || y < border || y >= P.H - border);
+}
+template <class Ring>
+__device__ __forceinline__ bool corner_pixel_rings(Ring ring) {
+  double r[20];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) r[k] = ring(c_ring3[k][0], c_ring3[k][1]);
+  if (!arc_ring_valid<16, 4, 6>(r)) return false;
+#pragma unroll
+  for (int k = 0; k < 20; ++k) r[k] = ring(c_ring4[k][0], c_ring4[k][1]);
+  return arc_ring_valid<20, 5, 8>(r);
+}
+template <class Ring>
+__device__ __forceinline__ bool corner_pixel_test(const CornerParams& P, int x, int y, int pol, double2 lat,
+                                                  Ring ring) {
+  return corner_pixel_cheap(P, x, y, pol, lat) && corner_pixel_rings(ring);
+}
+
+// k_corner_plane: the pixel part of the Arc* test ONCE per (pixel, polarity) that an event of the
+// window can ask about, instead of once per event.  One CTA per 32x8 tile: the tile's sae planes
+// plus a 4-pixel halo go to shared memory (10 KB; the per-event kernel pulled 36 scattered
+// 32-byte sectors per event through L2, 190 MB per 640x480 window at 5 Mev/s, and took 40 us),
+// the (pixel, polarity) pairs whose last event is not older than the window's first event are
+// settled -- the cheap conditions per pixel, the circles compacted and tested densely -- and the
+// verdicts land in the byte plane: bit p = verdict, bit 2 + p = "tested".
+constexpr int kCpHalo = 4, kCpW = kTileW + 2 * kCpHalo, kCpH = kTileH + 2 * kCpHalo;
+__global__ void __launch_bounds__(kTileW* kTileH) k_corner_plane(CornerParams P, DevEvents ev) {
+  PDL_PROLOGUE();
+  __shared__ double2 s_sae[kCpH][kCpW];
+  __shared__ uint16_t s_item[2 * kTileW * kTileH];
+  __shared__ uint32_t s_bits[kTileW * kTileH];
+  __shared__ int s_wc[kTileW * kTileH / 32 + 1];
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  for (int i = tid; i < kCpW * kCpH; i += kTileW * kTileH) {
+    const int r = i / kCpW, c = i - r * kCpW;
+    const int gx = x0 - kCpHalo + c, gy = y0 - kCpHalo + r;
+    double2 v = make_double2(0.0, 0.0);
+    if (gx >= 0 && gx < P.W && gy >= 0 && gy < P.H) v = P.sae[(size_t)gy * P.W + gx];
+    s_sae[r][c] = v;
+  }
+  const int tx = tid % kTileW, ty = tid / kTileW;
+  const int x = x0 + tx, y = y0 + ty;
+  const bool inside = x < P.W && y < P.H;
+  double2 l = make_double2(0.0, 0.0);
+  if (inside) l = P.lat[(size_t)y * P.W + x];
+  // The pairs an event of this window can ask about: those whose last event is not older than
+  // the window's first event (minus the filter threshold: an event passes "t <= latest + thr").
+  // Events are time-ascending in the reference's windows; for any other order k_corner_flags
+  // tests what is missing here.  The cheap parts of the test are settled right away, only the
+  // pairs that reach the two circles are compacted over the CTA.
+  const double t_hint = load_event(ev, 0).t - P.filter_threshold - 1e-6;
+  int want = 0, tested = 0;
+  if (inside) {
+#pragma unroll
+    for (int pol = 0; pol < 2; ++pol) {
+      const double last = pol ? l.y : l.x;
+      if (last >= t_hint && last > 0.0) {
+        tested |= 4 << pol;
+        if (corner_pixel_cheap(P, x, y, pol, l)) want |= 1 << pol;
+      }
+    }
+  }
+  s_bits[tid] = (uint32_t)tested;
+  const int cnt = __popc(want);
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_wc[warp] = incl;
+  __syncthreads();
+  int base = 0, n_items = 0;
+#pragma unroll
+  for (int w = 0; w < kTileW * kTileH / 32; ++w) {
+    const int c = s_wc[w];
+    base += w < warp ? c : 0;
+    n_items += c;
+  }
+  int pos = base + incl - cnt;
+  if (want & 1) s_item[pos++] = (uint16_t)(tid << 1);
+  if (want & 2) s_item[pos] = (uint16_t)(tid << 1 | 1);
+  __syncthreads();
+  for (int i = tid; i < n_items; i += kTileW * kTileH) {
+    const int it = s_item[i], pol = it & 1, px = it >> 1;
+    const int ix = px % kTileW, iy = px / kTileW;
+    const double* S = reinterpret_cast<const double*>(&s_sae[iy + kCpHalo][ix + kCpHalo]) + pol;
+    if (corner_pixel_rings([&](int dx, int dy) { return S[2 * (dy * kCpW + dx)]; })) atomicOr(&s_bits[px], 1u << pol);
+  }
+  __syncthreads();
+  if (inside) P.plane[(size_t)y * P.W + x] = (uint8_t)s_bits[tid];
+}
+
+// k_corner_flags: the flag of every event.  With the pixel plane of k_corner_plane an event only
+// checks its own time against latest[p] and picks up its pixel's verdict; a (pixel, polarity)
+// the plane kernel did not test (an event older than its hint) is tested here, so the result
+// never depends on the hint.  Besides the flags the kernel leaves, per CTA of kCornerBlock
+// consecutive events, the flagged events' pixels compacted in stream order
+// (cand[block * kCornerBlock + j], x | y << 16) and their number: the selection kernel then
+// walks a few thousand candidates instead of re-reading the whole window.
 __global__ void __launch_bounds__(kCornerBlock)
 k_corner_flags(CornerParams P, DevEvents ev, uint8_t* __restrict__ flags) {
   PDL_PROLOGUE();
@@ -1076,23 +1186,21 @@ k_corner_flags(CornerParams P, DevEvents ev, uint8_t* __restrict__ flags) {
     do {
       if (e.x >= P.W || e.y >= P.H) break;
       const size_t px = (size_t)e.x + (size_t)e.y * P.W;
-      if (P.and_ts_test && (double)P.ts[(size_t)e.y * P.ts_pitch + e.x] == P.ts_lk_threshold) break;
       const double2 l = P.lat[px];
-      const double last_same = e.p ? l.y : l.x, last_opp = e.p ? l.x : l.y;
-      if (e.t > last_same + P.filter_threshold || last_opp > last_same) break;
-      const int border = P.min_dist + 1;
-      if (e.x < border || e.x >= P.W - border || e.y < border || e.y >= P.H - border) break;
+      const double last_same = e.p ? l.y : l.x;
+      if (e.t > last_same + P.filter_threshold) break;
+      if (P.plane) {
+        const uint32_t b = __ldcg(P.plane + px);  // written by the kernel before
+        if ((b >> (2 + e.p)) & 1u) {
+          out = (b >> e.p) & 1u;
+          break;
+        }
+      }
       const double* S = reinterpret_cast<const double*>(P.sae) + e.p;
-      double ring[20];
-#pragma unroll
-      for (int k = 0; k < 16; ++k)
-        ring[k] = S[2 * ((size_t)(e.x + c_ring3[k][0]) + (size_t)(e.y + c_ring3[k][1]) * P.W)];
-      if (!arc_ring_valid<16, 4, 6>(ring)) break;
-#pragma unroll
-      for (int k = 0; k < 20; ++k)
-        ring[k] = S[2 * ((size_t)(e.x + c_ring4[k][0]) + (size_t)(e.y + c_ring4[k][1]) * P.W)];
-      if (!arc_ring_valid<20, 5, 8>(ring)) break;
-      out = 1;
+      const int ex = e.x, ey = e.y, W = P.W;
+      out = corner_pixel_test(P, ex, ey, e.p, l, [&](int dx, int dy) {
+        return S[2 * ((size_t)(ex + dx) + (size_t)(ey + dy) * W)];
+      });
     } while (0);
     flags[i] = out;
   }
@@ -1116,6 +1224,11 @@ k_corner_flags(CornerParams P, DevEvents ev, uint8_t* __restrict__ flags) {
 void launch_corner_flags(const CornerParams& P, const DevEvents& ev, uint8_t* flags,
                          cudaStream_t s, int64_t* launches) {
   if (ev.n <= 0) return;
+  if (P.plane) {
+    launch_pdl(k_corner_plane, dim3((P.W + kTileW - 1) / kTileW, (P.H + kTileH - 1) / kTileH),
+               dim3(kTileW * kTileH), 0, s, P, ev);
+    ++*launches;
+  }
   launch_pdl(k_corner_flags, dim3((ev.n + kCornerBlock - 1) / kCornerBlock), dim3(kCornerBlock), 0, s, P, ev,
              flags);
   ++*launches;
