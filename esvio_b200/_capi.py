@@ -164,6 +164,7 @@ SYMBOLS = {
                                            C.c_void_p, _pi]),
     "esvio_fe_stage_select": (C.c_int, [_H, C.POINTER(Events), C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, _pi, C.c_void_p, C.c_void_p, C.c_void_p, _pi]),
+    "esvio_fe_stage_sort_order": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "esvio_fe_stage_undistort": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

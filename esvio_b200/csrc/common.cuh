@@ -436,6 +436,8 @@ void launch_post_temporal(const TrackParams& P, const TrackBuffers& B, int snap_
 // cand / cand_cnt: the candidate lists k_corner_flags left for the window's n_events left events
 void launch_select(const TrackParams& P, const TrackBuffers& B, int n_events, const uint32_t* cand,
                    const int* cand_cnt, int snap_slot, cudaStream_t s, int64_t* launches);
+// test entry: order[k] = index libstdc++'s std::sort (key descending) leaves at position k
+void launch_sort_order(const int* key, int n, int depth_limit, int* order, cudaStream_t s, int64_t* launches);
 void launch_finalize(const TrackParams& P, const TrackBuffers& B, int slot, double cur_time,
                      double prev_time, cudaStream_t s, int64_t* launches);
 void launch_ransac(const TrackParams& P, const TrackBuffers& B, cudaStream_t s,

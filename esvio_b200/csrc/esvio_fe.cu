@@ -2383,6 +2383,22 @@ FE_API int esvio_fe_stage_set_tracks(esvio_fe* fe, double prev_time, int32_t nex
   return ESVIO_FE_OK;
 }
 
+FE_API int esvio_fe_stage_sort_order(esvio_fe* fe, const int32_t* key, int32_t n, int32_t depth_limit,
+                                     int32_t* order) {
+  if (!fe || n < 0 || n > kMaxCnt || (n > 0 && (!key || !order))) return ESVIO_FE_EINVAL;
+  if (n == 0) return ESVIO_FE_OK;
+  CU(cudaSetDevice(fe->dev));
+  cudaStream_t s = fe->stream;
+  int* d_key = reinterpret_cast<int*>(fe->d_scratch_p0);   // 2 * kMaxCnt float2: room for both
+  int* d_order = d_key + kMaxCnt;
+  CU(cudaMemcpyAsync(d_key, key, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  launch_sort_order(d_key, n, depth_limit, d_order, s, &fe->launches);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(order, d_order, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return ESVIO_FE_OK;
+}
+
 FE_API int esvio_fe_stage_undistort(esvio_fe* fe, int32_t cam, const float* uv, int32_t n,
                                     float* out) {
   if (!fe || cam < 0 || cam > 1 || !uv || !out || n < 0 || n > kMaxCnt) return ESVIO_FE_EINVAL;

@@ -276,9 +276,180 @@ __device__ __forceinline__ void fill_disc_rows(uint32_t* mask, int words, int W,
   __syncwarp();
 }
 
+
+// ---- std::sort as libstdc++ runs it, as a permutation ---------------------------------------
+// Event_setMask / Image_setMask visit the tracks in the order `sort(cnt_pts_id.begin(),
+// cnt_pts_id.end(), a.first > b.first)` leaves them in (feature_tracker.cpp:100-103,132-135).
+// Equal track counts are the rule (every corner of a publish window starts at 1 together), and
+// std::sort is not stable: which of two close tracks of equal age survives the mask, and the
+// order of the published features, depend on where the library's introsort puts the ties.  The
+// reference is built with GCC, so its answer is libstdc++'s (bits/stl_algo.h): while a range
+// holds more than 16 elements -- median of (first+1, mid, last-1) swapped to the front,
+// unguarded Hoare partition around it, right part recursed into, left part continued, heap sort
+// when the budget 2*floor(log2 n) is spent -- then ONE insertion sort over everything.
+//
+// Here: warp 0 replays the partitions on a permutation of indices.  A Hoare partition pairs the
+// k-th element from the left that is not before the pivot (key <= pivot: a "left stopper") with
+// the k-th element from the right that is not after it (key >= pivot) and swaps them while the
+// left one lies left of the right one; the scans only ever read elements no swap has touched
+// yet, so both stopper lists can be taken from the range as it is (ballots), all swaps done at
+// once, and the cut is min(next left stopper, last swapped right position).  The final
+// insertion sort is a STABLE sort of what the partitions left (its comparator is strict), i.e.
+// a rank by (key descending, position ascending), one thread per element.
+// scratch: 2 * kMaxCnt + 3 * 32 words.  Called by the whole CTA (>= n threads).
+constexpr int kSortScratchWords = 2 * kMaxCnt + 96;
+
+__device__ void sort_adjust_heap(const int* key, int* o, int hole, int len, int value) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (key[o[child]] > key[o[child - 1]]) child--;
+    o[hole] = o[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    o[hole] = o[child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;  // __push_heap
+  while (hole > top && key[o[parent]] > key[value]) {
+    o[hole] = o[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  o[hole] = value;
+}
+
+// std::__partial_sort(first, last, last): __make_heap + __sort_heap (one thread; reached only
+// when the partitions of a range stay lopsided 2*floor(log2 n) times in a row)
+__device__ void sort_heap_range(const int* key, int* o, int len) {
+  if (len >= 2)
+    for (int parent = (len - 2) / 2;; --parent) {
+      sort_adjust_heap(key, o, parent, len, o[parent]);
+      if (parent == 0) break;
+    }
+  for (int last = len; last > 1;) {
+    --last;
+    const int value = o[last];
+    o[last] = o[0];
+    sort_adjust_heap(key, o, 0, last, value);
+  }
+}
+
+__device__ void std_sort_order(const int* __restrict__ s_key, int n, int depth_limit, int* __restrict__ s_order,
+                               uint32_t* __restrict__ scratch) {
+  int* perm = reinterpret_cast<int*>(scratch);
+  uint16_t* lo = reinterpret_cast<uint16_t*>(scratch + kMaxCnt);
+  uint16_t* ro = lo + kMaxCnt;
+  int* stack = reinterpret_cast<int*>(scratch + 2 * kMaxCnt);
+  const int tid = threadIdx.x, lane = lane_id();
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  if (tid < n) perm[tid] = tid;
+  __syncthreads();
+  if (n > 16 && tid < 32) {
+    int first = 0, last = n, sp = 0;
+    int depth = depth_limit >= 0 ? depth_limit : 2 * (31 - __clz(n));
+    for (;;) {
+      while (last - first > 16) {
+        if (depth == 0) {
+          if (lane == 0) sort_heap_range(s_key, perm + first, last - first);
+          __syncwarp();
+          break;
+        }
+        --depth;
+        if (lane == 0) {  // __move_median_to_first(first, first + 1, mid, last - 1)
+          const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
+          const int ka = s_key[perm[a]], kb = s_key[perm[b]], kc = s_key[perm[c]];
+          int m;
+          if (ka > kb) m = kb > kc ? b : (ka > kc ? c : a);
+          else m = ka > kc ? a : (kb > kc ? c : b);
+          const int t = perm[first];
+          perm[first] = perm[m];
+          perm[m] = t;
+        }
+        __syncwarp();
+        const int pk = s_key[perm[first]];
+        const int lo0 = first + 1, m = last - lo0;
+        int nL = 0, nR = 0;
+        for (int base = 0; base < m; base += 32) {
+          const bool v = base + lane < m;
+          const int i = lo0 + base + lane, j = last - 1 - base - lane;
+          const bool is_l = v && s_key[perm[i]] <= pk;
+          const bool is_r = v && s_key[perm[j]] >= pk;
+          const uint32_t bl = __ballot_sync(0xffffffffu, is_l), br = __ballot_sync(0xffffffffu, is_r);
+          if (is_l) lo[nL + __popc(bl & lt_mask)] = (uint16_t)i;
+          if (is_r) ro[nR + __popc(br & lt_mask)] = (uint16_t)j;
+          nL += __popc(bl);
+          nR += __popc(br);
+        }
+        __syncwarp();
+        const int kmax = min(nL, nR);
+        int ks = 0;  // swaps: pairs k < ks
+        for (int base = 0; base < kmax; base += 32) {
+          const int k = base + lane;
+          const uint32_t b = __ballot_sync(0xffffffffu, k < kmax && lo[k] < ro[k]);
+          ks += __popc(b);
+          if (b != 0xffffffffu) break;
+        }
+        int cut = ks < nL ? (int)lo[ks] : last;
+        if (ks > 0) cut = min(cut, (int)ro[ks - 1]);
+        for (int k = lane; k < ks; k += 32) {
+          const int a = lo[k], b = ro[k];
+          const int t = perm[a];
+          perm[a] = perm[b];
+          perm[b] = t;
+        }
+        if (lane == 0) {  // __introsort_loop(cut, last, depth) later; [first, cut) now
+          stack[3 * sp] = cut;
+          stack[3 * sp + 1] = last;
+          stack[3 * sp + 2] = depth;
+        }
+        ++sp;
+        last = cut;
+        __syncwarp();
+      }
+      if (sp == 0) break;
+      --sp;
+      first = stack[3 * sp];
+      last = stack[3 * sp + 1];
+      depth = stack[3 * sp + 2];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (tid < n) {  // __final_insertion_sort
+    const int c = s_key[perm[tid]];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const int cj = s_key[perm[j]];
+      rank += (cj > c) || (cj == c && j < tid);
+    }
+    s_order[rank] = perm[tid];
+  }
+  __syncthreads();
+}
+
+// test entry (esvio_fe_stage_sort_order): the permutation alone
+__global__ void __launch_bounds__(kSelThreads) k_sort_order(const int* __restrict__ key, int n, int depth_limit,
+                                                            int* __restrict__ order) {
+  __shared__ int s_key[kMaxCnt], s_order[kMaxCnt];
+  __shared__ uint32_t s_scratch[kSortScratchWords];
+  if (threadIdx.x < n) s_key[threadIdx.x] = key[threadIdx.x];
+  __syncthreads();
+  std_sort_order(s_key, n, depth_limit, s_order, s_scratch);
+  if (threadIdx.x < n) order[threadIdx.x] = s_order[threadIdx.x];
+}
+
+void launch_sort_order(const int* key, int n, int depth_limit, int* order, cudaStream_t s, int64_t* launches) {
+  k_sort_order<<<1, kSelThreads, 0, s>>>(key, n, depth_limit, order);
+  if (launches) ++*launches;
+}
+
 // Event_setMask + Event_FeaturesToTrack + id assignment.
-//  (1) Event_setMask (feature_tracker.cpp:123-151): points are visited by track_cnt descending
-//      (ties keep their order); a point survives iff no surviving earlier point's filled circle
+//  (1) Event_setMask (feature_tracker.cpp:123-151): points are visited by track_cnt descending,
+//      ties where libstdc++'s std::sort puts them (std_sort_order); a point survives iff no surviving earlier point's filled circle
 //      covers its rounded pixel.  "Covers" is evaluated pairwise for all pairs in parallel (bit
 //      matrix, <= 256 points), the greedy pass then only ANDs bit rows, and all surviving discs
 //      are rastered into the bit mask at once.  More than 256 points: the serial mask walk.
@@ -325,13 +496,8 @@ k_select(TrackParams P, TrackBuffers B, int n_events, const uint32_t* __restrict
     s_cnt[tid] = B.cnt[tid];
   }
   __syncthreads();
-  if (tid < n) {
-    const int c = s_cnt[tid];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += (s_cnt[j] > c) || (s_cnt[j] == c && j < tid);
-    s_order[rank] = tid;
-  }
-  __syncthreads();
+  static_assert(sizeof(s_cand) >= sizeof(uint32_t) * kSortScratchWords, "sort scratch");
+  std_sort_order(s_cnt, n, -1, s_order, s_cand);  // s_cand is filled further down
   SEL_CLK(1);
   if (n <= kSelFast) {
     // ---- (1) bit-matrix path
@@ -769,7 +935,7 @@ void launch_undistort(const Pinhole& cam, const float2* uv, int n, float2* out, 
 // frame path (FeatureTracker::trackImage, feature_tracker.cpp:164-338)
 // =====================================================================================
 // Image_setMask (feature_tracker.cpp:91-121): points are visited by track_cnt descending (ties
-// keep their order, as in Event_setMask above); a point survives iff its rounded pixel is
+// where std::sort puts them, as in Event_setMask above); a point survives iff its rounded pixel is
 // still free, and then blocks the filled circle of radius MIN_DIST_IMG around it.  Survivors
 // are compacted in place; the mask (1 bit per pixel, 1 = blocked) goes to global memory for
 // goodFeaturesToTrack.
@@ -781,6 +947,7 @@ k_image_set_mask(TrackParams P, TrackBuffers B, uint32_t* __restrict__ blocked) 
   __shared__ int s_order[kMaxCnt];
   __shared__ float2 s_pts[kMaxCnt];
   __shared__ int s_ids[kMaxCnt], s_cnt[kMaxCnt];
+  __shared__ uint32_t s_sort[kSortScratchWords];
   __shared__ int s_kept;
   TrackState* st = B.st;
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -797,13 +964,7 @@ k_image_set_mask(TrackParams P, TrackBuffers B, uint32_t* __restrict__ blocked) 
     s_cnt[tid] = B.cnt[tid];
   }
   __syncthreads();
-  if (tid < n) {
-    const int c = s_cnt[tid];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += (s_cnt[j] > c) || (s_cnt[j] == c && j < tid);
-    s_order[rank] = tid;
-  }
-  __syncthreads();
+  std_sort_order(s_cnt, n, -1, s_order, s_sort);
   if (warp == 0) {
     int kept = 0;
     for (int k = 0; k < n; ++k) {

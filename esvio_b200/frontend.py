@@ -575,6 +575,14 @@ class EventFrontEnd:
             self._h, float(prev_time), int(next_id), n, pts.ctypes.data, ids.ctypes.data,
             cnt.ctypes.data, un.ctypes.data, nr, idr.ctypes.data, unr.ctypes.data), "stage_set_tracks")
 
+    def stage_sort_order(self, key, depth_limit=-1):
+        """Visiting order of Event_setMask / Image_setMask (libstdc++'s std::sort, key descending)."""
+        key = np.ascontiguousarray(key, np.int32)
+        out = np.zeros(len(key), np.int32)
+        self._chk(_capi.lib().esvio_fe_stage_sort_order(self._h, key.ctypes.data, len(key), int(depth_limit),
+                                                        out.ctypes.data), "stage_sort_order")
+        return out
+
     def stage_undistort(self, cam, uv):
         uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
         out = np.zeros_like(uv)

@@ -420,23 +420,130 @@ ORA_API void ora_fill_disc_u8(uint8_t *mask, int W, int H, int cx, int cy, int r
 
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 
-/* feature_tracker.cpp:123-151.  Points are visited by track_cnt descending; the
- * reference uses std::sort (unspecified order among equal counts) -- here equal
- * counts keep their current relative order, and the CUDA path does the same. */
+/* ---- std::sort as libstdc++ implements it (bits/stl_algo.h: __sort -> __introsort_loop +
+ * __final_insertion_sort), on a permutation `o` of indices with the comparator of
+ * feature_tracker.cpp:100-103,132-135: comp(a, b) = key[a] > key[b].  std::sort leaves the order
+ * of equal keys unspecified; the reference is built with GCC (ROS), so "what the reference
+ * does" on ties is what this algorithm does: median-of-three pivot moved to the front,
+ * unguarded Hoare partition, recursion on the right part, ranges of <= 16 left to one final
+ * insertion sort, heap sort when the depth budget 2*floor(log2 n) runs out.  Pinned against the
+ * real std::sort by tests/test_oracle_ref_tracker.py (the reference's own Event_setMask and a
+ * direct randomized comparison). ---- */
+#define SORT_CMP(a, b) (key[(a)] > key[(b)])
+static void ss_adjust_heap(const int *key, int *o, int hole, int len, int value) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (SORT_CMP(o[child], o[child - 1])) child--;
+    o[hole] = o[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    o[hole] = o[child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2; /* __push_heap */
+  while (hole > top && SORT_CMP(o[parent], value)) {
+    o[hole] = o[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  o[hole] = value;
+}
+static void ss_heap_sort(const int *key, int *o, int len) { /* __partial_sort(first, last, last) */
+  if (len >= 2)
+    for (int parent = (len - 2) / 2;; --parent) { /* __make_heap */
+      ss_adjust_heap(key, o, parent, len, o[parent]);
+      if (parent == 0) break;
+    }
+  for (int last = len; last > 1;) { /* __sort_heap: __pop_heap(first, last - 1, last - 1) */
+    --last;
+    const int value = o[last];
+    o[last] = o[0];
+    ss_adjust_heap(key, o, 0, last, value);
+  }
+}
+static void ss_introsort_loop(const int *key, int *o, int first, int last, int depth) {
+  while (last - first > 16) {
+    if (depth == 0) {
+      ss_heap_sort(key, o + first, last - first);
+      return;
+    }
+    --depth;
+    /* __unguarded_partition_pivot: __move_median_to_first(first, first + 1, mid, last - 1) */
+    const int mid = first + (last - first) / 2, a = first + 1, b = mid, c = last - 1;
+    int m;
+    if (SORT_CMP(o[a], o[b])) m = SORT_CMP(o[b], o[c]) ? b : (SORT_CMP(o[a], o[c]) ? c : a);
+    else m = SORT_CMP(o[a], o[c]) ? a : (SORT_CMP(o[b], o[c]) ? c : b);
+    int tmp = o[first];
+    o[first] = o[m];
+    o[m] = tmp;
+    /* __unguarded_partition(first + 1, last, pivot = first) */
+    int i = first + 1, j = last;
+    for (;;) {
+      while (SORT_CMP(o[i], o[first])) ++i;
+      --j;
+      while (SORT_CMP(o[first], o[j])) --j;
+      if (!(i < j)) break;
+      tmp = o[i];
+      o[i] = o[j];
+      o[j] = tmp;
+      ++i;
+    }
+    ss_introsort_loop(key, o, i, last, depth);
+    last = i;
+  }
+}
+/* order[k] = index of the element std::sort puts at position k; depth_limit < 0: the library's
+ * own budget 2 * floor(log2 n) (tests force small budgets to reach the heap-sort branch) */
+ORA_API void ora_std_sort_order(const int *key, int n, int depth_limit, int *order) {
+  for (int i = 0; i < n; ++i) order[i] = i;
+  if (n <= 1) return;
+  if (depth_limit < 0) {
+    int lg = 0;
+    while ((n >> (lg + 1)) > 0) ++lg;
+    depth_limit = 2 * lg;
+  }
+  ss_introsort_loop(key, order, 0, n, depth_limit);
+  /* __final_insertion_sort: guarded insertion over the first 16, unguarded over the rest */
+  const int head = n > 16 ? 16 : n;
+  for (int i = 1; i < head; ++i) {
+    const int v = order[i];
+    if (SORT_CMP(v, order[0])) {
+      memmove(order + 1, order, sizeof(int) * i);
+      order[0] = v;
+    } else {
+      int j = i;
+      while (SORT_CMP(v, order[j - 1])) {
+        order[j] = order[j - 1];
+        --j;
+      }
+      order[j] = v;
+    }
+  }
+  for (int i = head; i < n; ++i) {
+    const int v = order[i];
+    int j = i;
+    while (SORT_CMP(v, order[j - 1])) {
+      order[j] = order[j - 1];
+      --j;
+    }
+    order[j] = v;
+  }
+}
+#undef SORT_CMP
+
+/* feature_tracker.cpp:123-151.  Points are visited in the order std::sort (libstdc++) leaves
+ * them in: track_cnt descending, ties as ora_std_sort_order documents; the CUDA path
+ * reproduces the same permutation. */
 ORA_API int ora_set_mask(int W, int H, int min_dist, int n, float *pts, int *ids, int *track_cnt,
                          uint8_t *mask) {
   memset(mask, 0, (size_t)W * H);
   if (n <= 0) return 0;
   int *order = (int *)malloc(sizeof(int) * n);
-  for (int i = 0; i < n; ++i) order[i] = i;
-  for (int i = 1; i < n; ++i) { /* stable insertion sort, descending count */
-    int o = order[i], j = i - 1;
-    while (j >= 0 && track_cnt[order[j]] < track_cnt[o]) {
-      order[j + 1] = order[j];
-      --j;
-    }
-    order[j + 1] = o;
-  }
+  ora_std_sort_order(track_cnt, n, -1, order);
   float *np = (float *)malloc(sizeof(float) * 2 * n);
   int *ni = (int *)malloc(sizeof(int) * n), *nc = (int *)malloc(sizeof(int) * n);
   int m = 0;

@@ -101,7 +101,10 @@ void ora_sae_update_mc(ora_sae *s, const uint16_t *x, const uint16_t *y, const d
 void ora_disc_half_widths(int r, int *half_width);
 void ora_fill_disc_u8(uint8_t *mask, int W, int H, int cx, int cy, int r, uint8_t value);
 
-/* feature_tracker.cpp:123-151 ; ties in track_cnt keep their current order (stable) */
+/* std::sort of libstdc++ (introsort) as a permutation: order[k] = index of the element at
+ * position k after sorting by key descending; depth_limit < 0 = the library's 2*floor(log2 n) */
+void ora_std_sort_order(const int *key, int n, int depth_limit, int *order);
+/* feature_tracker.cpp:123-151 ; ties in track_cnt end up where libstdc++'s std::sort puts them */
 int ora_set_mask(int W, int H, int min_dist, int n, float *pts /*2n*/, int *ids, int *track_cnt,
                  uint8_t *mask /*W*H out: 0 / 255*/);
 /* feature_tracker.cpp:13-38 */

@@ -113,6 +113,7 @@ def lib():
         L.ora_fill_disc_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_uint8]
         L.ora_set_mask.restype = C.c_int
+        L.ora_std_sort_order.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ora_set_mask.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
         L.ora_features_to_track.restype = C.c_int
@@ -329,6 +330,14 @@ def disc_half_widths(r):
 def fill_disc(mask, cx, cy, r, value=255):
     H, W = mask.shape
     lib().ora_fill_disc_u8(_p(mask), W, H, cx, cy, r, value)
+
+
+def std_sort_order(key, depth_limit=-1):
+    """order[k] = index libstdc++'s std::sort (key descending) leaves at position k."""
+    key = np.ascontiguousarray(key, np.int32)
+    out = np.zeros(len(key), np.int32)
+    lib().ora_std_sort_order(_p(key), len(key), int(depth_limit), _p(out))
+    return out
 
 
 def set_mask(W, H, min_dist, pts, ids, track_cnt):

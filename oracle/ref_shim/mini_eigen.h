@@ -78,6 +78,36 @@ struct Matrix : MatrixBase<Matrix<S, R, C>> {
   const S& operator()(int r, int c) const { return d[r + c * R]; }
   S& operator[](int i) { return d[i]; }
   const S& operator[](int i) const { return d[i]; }
+  // vector accessors (feature_tracker.cpp, PinholeCamera::liftProjective)
+  S& operator()(int i) { return d[i]; }
+  const S& operator()(int i) const { return d[i]; }
+  S& x() { return d[0]; }
+  S& y() { return d[1]; }
+  S& z() { return d[2]; }
+  const S& x() const { return d[0]; }
+  const S& y() const { return d[1]; }
+  const S& z() const { return d[2]; }
+  Matrix(S a, S b, S c) {
+    static_assert(R * C == 3, "3-vector");
+    d[0] = a;
+    d[1] = b;
+    d[2] = c;
+  }
+  Matrix operator-(const Matrix& b) const {
+    Matrix o;
+    for (int i = 0; i < R * C; ++i) o.d[i] = d[i] - b.d[i];
+    return o;
+  }
+  struct Head {  // v.head(n) = w  (visualisation code only)
+    Matrix& m;
+    int n;
+    template <class M2>
+    Head& operator=(const M2& w) {
+      for (int i = 0; i < n; ++i) m.d[i] = w[i];
+      return *this;
+    }
+  };
+  Head head(int n) { return Head{*this, n}; }
   void fill_seq(int k, S v) { d[(k / C) + (k % C) * R] = v; }
   template <class T>
   CommaInit<Matrix> operator<<(const T& v) {

@@ -329,6 +329,37 @@ def test_select_parity(fe_mod, ora, W, H, rate, min_dist, max_cnt):
     fe.close()
 
 
+def test_sort_order_is_libstdcxx_std_sort(fe_mod, ora):
+    """The visiting order of Event_setMask / Image_setMask: std::sort as libstdc++ runs it
+    (introsort: ties are NOT stable), replayed by one warp of k_select.  Against the oracle's
+    transcription -- itself pinned on the real std::sort, tests/test_oracle_ref_tracker.py --
+    for every length up to 80, random lengths up to the cap on MAX_CNT, few to many distinct
+    keys, sorted / reversed / organ-pipe inputs, and forced recursion budgets that reach the
+    heap-sort branch."""
+    fe, _ = _mk(fe_mod, 346, 260)
+    rng = np.random.default_rng(11)
+    cases = []
+    for n in range(0, 81):
+        for span in (1, 3, 1000):
+            cases.append(rng.integers(0, span, n).astype(np.int32))
+    for _ in range(120):
+        n = int(rng.integers(17, 1025))
+        cases.append(rng.integers(0, int(rng.choice([1, 2, 3, 8, 30, 200, 100000])), n).astype(np.int32))
+    for n in (17, 33, 150, 300, 1024):
+        up = np.arange(n, dtype=np.int32)
+        cases += [up, up[::-1].copy(), np.minimum(up, up[::-1]).astype(np.int32), (up // 3).astype(np.int32)]
+    unstable = 0
+    for key in cases:
+        for depth in ((-1,) if len(key) < 17 else (-1, 0, 1, 3)):
+            want = ora.std_sort_order(key, depth)
+            got = fe.stage_sort_order(key, depth)
+            assert np.array_equal(got, want), (len(key), depth, key[:24], got[:24], want[:24])
+        stable = np.argsort(-key.astype(np.int64), kind="stable")
+        unstable += int(not np.array_equal(ora.std_sort_order(key), stable))
+    assert unstable > 100   # the cases do tell the library's order from a stable one
+    fe.close()
+
+
 def test_fmat_mask_parity(fe_mod, ora, golden_fmat):
     fe, _ = _mk(fe_mod, 346, 260)
     g = golden_fmat
