@@ -39,10 +39,16 @@
  *     reference's control flow is pinned and Eigen's float kernels are not.)
  *   - the OpenCV-derived stages are pinned against real OpenCV (cv2) outputs
  *     committed under tests/golden/.
- *   - the bookkeeping of feature_tracker.cpp (mask, selection order, compaction,
- *     velocity, packing) has no compilable reference here (it needs OpenCV C++ and
- *     camodocal): PARITY UNPINNED for those, beyond hand-written known answers
- *     (tests/test_oracle_kat.py).
+ *   - the whole per-window tracker -- trackEvent (both overloads) and trackImage with the
+ *     bookkeeping of feature_tracker.cpp (mask, selection order, compaction, velocity,
+ *     ids, state roll) -- is checked against the REFERENCE'S OWN FeatureTracker:
+ *     oracle/_ref/libesvio_ref_ft.so is feature_tracker.cpp + event_detector.cc compiled
+ *     unmodified (liftProjective cut out of PinholeCamera.cc), with the OpenCV algorithms
+ *     supplied by this file's cv2-pinned restatements; tests/test_oracle_ref_tracker.py
+ *     demands bit-exact equality of every public result vector on every window.
+ *   - the order std::sort leaves equal track counts in (Event_setMask / Image_setMask) is
+ *     libstdc++'s, transcribed in ora_std_sort_order and checked against the real std::sort.
+ *   - what stays unpinned: Eigen's Matrix3f::exp() rounding (motion compensation, see above).
  */
 #ifndef ESVIO_ORACLE_H
 #define ESVIO_ORACLE_H
