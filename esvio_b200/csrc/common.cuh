@@ -255,6 +255,7 @@ struct EventStageBuffers {
 };
 int event_stage_alloc(const BinLayout& L, int n_cams, int cap, EventStageBuffers* E);
 void event_stage_free(EventStageBuffers* E);
+EventStageBuffers event_stage_cam_view(const BinLayout& L, const EventStageBuffers& E, int cam);
 void event_stage_clear(const BinLayout& L, const EventStageBuffers& E, cudaStream_t s);
 int bin_configure(const BinLayout& L);
 

@@ -166,6 +166,9 @@ struct esvio_fe {
   BinLayout bl;
   double2 *sae, *lat;  // [2][H][W]
   CUtensorMap map_sae, map_lat;
+  CUtensorMap map_sae_r, map_lat_r;  // the right camera's planes alone (left-first windows)
+  cudaEvent_t cl_done[kSlots], k1l_done[kSlots];  // left-first windows: left copy landed / left K1 done
+  int left_first;   // ESVIO_LEFT_FIRST (default 1)
   PyrDesc pd;
   // Pyramid buffers: kLeftBufs left, kRightBufs right, 2 scratch for esvio_fe_stage_lk.  Up to
   // kSlots windows are in flight.  The left image of window k is read by the temporal LK of k
@@ -209,7 +212,8 @@ struct esvio_fe {
   cudaStream_t stream_c;   // host -> device copies of a window's events
   cudaStream_t stream_b;   // K0: binning (+ the motion-compensation warp)
   cudaStream_t stream_e;   // K1: SAE update + time surface (+ median / CLAHE)
-  cudaStream_t stream_p;   // pyramids
+  cudaStream_t stream_p;   // pyramids (frame path)
+  cudaStream_t stream_r;   // left-first windows: the right camera's event stage
   cudaStream_t stream_f;   // Arc* corner flags (publish windows)
   cudaStream_t stream_t1;  // temporal chain: temporal LK, filter, F-RANSAC, selection
   cudaStream_t stream_s[2];  // stereo LK of even / odd slots
@@ -429,7 +433,7 @@ static void comm_release(esvio_fe* fe) {
 static void free_all(esvio_fe* fe) {
   if (!fe) return;
   cudaSetDevice(fe->dev);
-  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_f,
+  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_r, fe->stream_f,
                           fe->stream_t1, fe->stream_s[0], fe->stream_s[1], fe->stream})
     if (st) cudaStreamSynchronize(st);
   cudaFree(fe->sae);
@@ -447,7 +451,7 @@ static void free_all(esvio_fe* fe) {
     cudaFree(fe->cand[i]);
     cudaFree(fe->cand_cnt[i]);
     for (cudaEvent_t ev : {fe->c_done[i], fe->b_done[i], fe->k1_done[i], fe->p_done[i], fe->f_done[i],
-                           fe->t1_done[i], fe->s_done[i], fe->x_ready[i]})
+                           fe->t1_done[i], fe->s_done[i], fe->x_ready[i], fe->cl_done[i], fe->k1l_done[i]})
       if (ev) cudaEventDestroy(ev);
     if (fe->h_result[i]) cudaFreeHost(fe->h_result[i]);
     for (int c = 0; c < 2; ++c)
@@ -477,7 +481,7 @@ static void free_all(esvio_fe* fe) {
       if (fe->pev[k][i]) cudaEventDestroy(fe->pev[k][i]);
   if (fe->pev_ref) cudaEventDestroy(fe->pev_ref);
   comm_release(fe);
-  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_f,
+  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_r, fe->stream_f,
                           fe->stream_t1, fe->stream_s[0], fe->stream_s[1], fe->stream})
     if (st) cudaStreamDestroy(st);
   free(fe);
@@ -631,6 +635,8 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(make_stream(&fe->stream_b, part, false, prio_hi));
     CUC(make_stream(&fe->stream_e, part, false, prio_hi));
     CUC(make_stream(&fe->stream_p, part, false, prio_hi));
+    // the right camera's event stage of a left-first window: behind the temporal LK's CTAs
+    CUC(make_stream(&fe->stream_r, part, false, prio_lo));
     CUC(make_stream(&fe->stream_f, part, false, prio_hi));
     // The temporal chain is the one stage that is serial from window to window (it sets the
     // period): its CTAs go first whenever an SM has room, ahead of the stereo LKs of the two
@@ -676,7 +682,7 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     CUC(cudaMalloc(&fe->cand[c], ((size_t)fe->cap + kCornerBlock) * sizeof(uint32_t)));
     CUC(cudaMalloc(&fe->cand_cnt[c], ((size_t)fe->cap / kCornerBlock + 2) * sizeof(int)));
     for (cudaEvent_t* ev : {&fe->c_done[c], &fe->b_done[c], &fe->k1_done[c], &fe->p_done[c], &fe->f_done[c],
-                            &fe->t1_done[c], &fe->s_done[c], &fe->x_ready[c]})
+                            &fe->t1_done[c], &fe->s_done[c], &fe->x_ready[c], &fe->cl_done[c], &fe->k1l_done[c]})
       CUC(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
   if (cfg->do_motion_correction)
@@ -766,8 +772,14 @@ FE_API int esvio_fe_create(const esvio_fe_config* cfg, esvio_fe** out) {
     const esvio_pinhole& s = cfg->cam[c];
     P.cam[c] = Pinhole{s.fx, s.fy, s.cx, s.cy, s.k1, s.k2, s.p1, s.p2};
   }
+  {
+    static const int lf = getenv("ESVIO_LEFT_FIRST") ? atoi(getenv("ESVIO_LEFT_FIRST")) : 1;
+    fe->left_first = lf;
+  }
   if ((rc = make_state_map(fe, fe->sae, &fe->map_sae)) != ESVIO_FE_OK ||
-      (rc = make_state_map(fe, fe->lat, &fe->map_lat)) != ESVIO_FE_OK) {
+      (rc = make_state_map(fe, fe->lat, &fe->map_lat)) != ESVIO_FE_OK ||
+      (rc = make_state_map(fe, fe->sae + fe->npx, &fe->map_sae_r, 1)) != ESVIO_FE_OK ||
+      (rc = make_state_map(fe, fe->lat + fe->npx, &fe->map_lat_r, 1)) != ESVIO_FE_OK) {
     fprintf(stderr, "esvio_fe_create: %s\n", fe->err);
     free_all(fe);
     return rc;
@@ -815,7 +827,7 @@ FE_API void esvio_fe_destroy(esvio_fe* fe) {
 }
 
 static int sync_all(esvio_fe* fe) {
-  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_f,
+  for (cudaStream_t st : {fe->stream_c, fe->stream_b, fe->stream_e, fe->stream_p, fe->stream_r, fe->stream_f,
                           fe->stream_t1, fe->stream_s[0], fe->stream_s[1], fe->stream})
     CU(cudaStreamSynchronize(st));
   return ESVIO_FE_OK;
@@ -893,7 +905,7 @@ static int stage_events(esvio_fe* fe, int slot, int cam, const esvio_events* e, 
 // 96 vs 86 us per 640x480 window at 5 Mev/s per camera, which is what bounds the end-to-end rate).
 // Returns 1 when it took the window, 0 when the caller has to stage the cameras one by one.
 static int stage_events_stereo_block(esvio_fe* fe, int slot, const esvio_events* l, const esvio_events* r,
-                                     DevEvents* d, int* took) {
+                                     DevEvents* d, int* took, cudaEvent_t after_left = nullptr) {
   *took = 0;
   if (!l || !r || !(l->flags & r->flags & ESVIO_EVENTS_STEREO_BLOCK)) return ESVIO_FE_OK;  // the caller's promise
   if (l->n == 0 || r->n == 0 || l->on_device || r->on_device || l->aos || r->aos) return ESVIO_FE_OK;
@@ -908,7 +920,13 @@ static int stage_events_stereo_block(esvio_fe* fe, int slot, const esvio_events*
     return ESVIO_FE_OK;
   if (total > (size_t)fe->cap * 32 || is_pageable(h)) return ESVIO_FE_OK;
   uint8_t* raw = fe->raw[slot][0];
-  CU(cudaMemcpyAsync(raw, h, total, cudaMemcpyHostToDevice, fe->stream_c));
+  if (after_left) {  // left-first window: the left camera's arrays cross first and are marked
+    CU(cudaMemcpyAsync(raw, h, orr[0], cudaMemcpyHostToDevice, fe->stream_c));
+    CU(cudaEventRecord(after_left, fe->stream_c));
+    CU(cudaMemcpyAsync(raw + orr[0], h + orr[0], total - orr[0], cudaMemcpyHostToDevice, fe->stream_c));
+  } else {
+    CU(cudaMemcpyAsync(raw, h, total, cudaMemcpyHostToDevice, fe->stream_c));
+  }
   const size_t* off[2] = {ol, orr};
   const size_t n[2] = {l->n, r->n};
   for (int c = 0; c < 2; ++c) {
@@ -1043,6 +1061,84 @@ static int run_event_stage(esvio_fe* fe, int slot, double t_ref, const DevEvents
   return ESVIO_FE_OK;
 }
 
+// ---- left-first windows -------------------------------------------------------------------------
+// A window submitted while nothing else of the handle is in flight -- the synchronous call the
+// reference node makes (stereo_event_tracker_node.cpp:193) -- has nothing to overlap with but
+// itself.  The temporal chain (temporal LK, filter, F-RANSAC, selection) needs the LEFT camera
+// only (feature_tracker.cpp:405-468); the right image is not read before the stereo LK (:490).
+// So the left camera's events cross PCIe first and its binning, SAE update, time surface and
+// pyramid run as launches of their own, while the right camera's copy and event stage follow
+// on another stream next to the temporal LK.  Same kernels, same per-camera arithmetic, same
+// results; per-camera views of the two-camera buffers (event_stage_cam_view), a tensor map on
+// the right camera's planes.  Not taken with motion compensation, median blur or CLAHE (their
+// launches cover both cameras), nor while the per-stage events are on (they time the
+// two-camera launches).  ESVIO_LEFT_FIRST=0 switches it off.
+static int run_event_stage_cam(esvio_fe* fe, int slot, double t_ref, const DevEvents& ev, int cam, int img_idx,
+                               cudaStream_t sb, cudaStream_t se, cudaEvent_t copied, cudaEvent_t binned,
+                               cudaEvent_t k1, cudaEvent_t pyr) {
+  const EventStageBuffers esb = event_stage_cam_view(fe->bl, fe->esb[slot & 1], cam);
+  CU(cudaStreamWaitEvent(sb, copied, 0));
+  launch_bin_events(fe->bl, esb, &ev, sb, &fe->launches);
+  if (cam == 0) prof_mark(fe, kMarkBinned, sb);
+  if (sb != se) {
+    CU(cudaEventRecord(binned, sb));
+    CU(cudaStreamWaitEvent(se, binned, 0));
+  }
+  if (cam == 0 && fe->f_pending >= 0) {  // the corner flags of the window before read the left SAE state
+    CU(cudaStreamWaitEvent(se, fe->f_done[fe->f_pending], 0));
+    fe->f_pending = -1;
+  }
+  SaeTsParams sp;
+  sp.W = fe->W;
+  sp.H = fe->H;
+  sp.tiles_x = fe->bl.tiles_x;
+  sp.n_tiles = fe->bl.n_tiles;
+  sp.n_cams = 1;
+  for (int c = 0; c < kMaxCams; ++c) {
+    sp.t_ref[c] = t_ref;
+    sp.bt[c] = nullptr, sp.bk[c] = nullptr, sp.ts[c] = nullptr;
+  }
+  sp.decay_sec = fe->cfg.decay_ms / 1000.0;
+  sp.inv_decay = 1.0 / sp.decay_sec;
+  sp.filter_threshold = fe->cfg.feature_filter_threshold;
+  sp.ignore_polarity = fe->cfg.ignore_polarity;
+  sp.bin_start = esb.bin_start;
+  sp.bt[0] = esb.bt[0];
+  sp.bk[0] = esb.bk[0];
+  sp.ts[0] = fe->pyr[img_idx];
+  sp.ts_pitch = fe->pd.pitch[0];
+  if (cam == 0) prof_mark(fe, kMarkK1Start, se);
+  launch_sae_update_ts(sp, cam ? fe->map_sae_r : fe->map_sae, cam ? fe->map_lat_r : fe->map_lat, se, &fe->launches);
+  fe->ts_sel[cam] = fe->pyr[img_idx];
+  if (cam == 0) prof_mark(fe, kMarkK1Done, se);
+  CU(cudaEventRecord(k1, se));
+  uint8_t* imgs[1] = {fe->pyr[img_idx]};
+  launch_pyramids(fe->pd, imgs, 1, se, &fe->launches);
+  if (cam == 0) prof_mark(fe, kMarkPyrDone, se);
+  CU(cudaEventRecord(pyr, se));
+  CU(cudaGetLastError());
+  return ESVIO_FE_OK;
+}
+
+static int run_event_stage_left_first(esvio_fe* fe, int slot, double t_ref, const DevEvents ev[2], int left_idx,
+                                      int right_idx) {
+  int rc;
+  // left: one chain on stream_e (K0 too: nothing of an earlier window is there to overlap with, and a
+  // launch behind its predecessor on the same stream starts earlier than one behind an event)
+  if ((rc = run_event_stage_cam(fe, slot, t_ref, ev[0], 0, left_idx, fe->stream_e, fe->stream_e, fe->cl_done[slot],
+                                nullptr, fe->k1l_done[slot], fe->p_done[slot])) != ESVIO_FE_OK)
+    return rc;
+  // right: one chain on stream_r behind the whole copy; x_ready[slot] = its pyramid (the stereo LK waits for it)
+  if ((rc = run_event_stage_cam(fe, slot, t_ref, ev[1], 1, right_idx, fe->stream_r, fe->stream_r, fe->c_done[slot],
+                                nullptr, fe->x_ready[slot], fe->x_ready[slot])) != ESVIO_FE_OK)
+    return rc;
+  // k1_done[slot] keeps its meaning for the windows behind (both cameras' state and binned-event
+  // buffers are free again), and stream_e stays the one stream that orders the SAE updates
+  CU(cudaStreamWaitEvent(fe->stream_e, fe->x_ready[slot], 0));
+  CU(cudaEventRecord(fe->k1_done[slot], fe->stream_e));
+  return ESVIO_FE_OK;
+}
+
 static CornerParams corner_params(esvio_fe* fe, int left_idx, int and_ts, int slot) {
   CornerParams cp;
   cp.W = fe->W;
@@ -1172,13 +1268,27 @@ FE_API int esvio_fe_track_submit_mc(esvio_fe* fe, double cur_time, const esvio_e
   prof_mark(fe, kMarkSubmit, fe->stream_c);
   DevEvents ev[2];
   int one_block = 0;
-  if ((rc = stage_events_stereo_block(fe, w.slot, left, right, ev, &one_block)) != ESVIO_FE_OK) return rc;
+  const bool left_first = fe->left_first && fe->q_count == 0 && (!fe->profiling || fe->left_first == 2) && !mc &&
+                          !fe->cfg.median_blur_kernel_size && !fe->cfg.equalize && left && right &&
+                          left->n > 0 && right->n > 0;
+  if ((rc = stage_events_stereo_block(fe, w.slot, left, right, ev, &one_block,
+                                      left_first ? fe->cl_done[w.slot] : nullptr)) != ESVIO_FE_OK)
+    return rc;
   if (!one_block) {
     if ((rc = stage_events(fe, w.slot, 0, left, &ev[0])) != ESVIO_FE_OK) return rc;
+    if (left_first) CU(cudaEventRecord(fe->cl_done[w.slot], fe->stream_c));
     if ((rc = stage_events(fe, w.slot, 1, right, &ev[1])) != ESVIO_FE_OK) return rc;
   }
   prof_mark(fe, kMarkLanded, fe->stream_c);
   if ((rc = staging_done(fe, w.slot)) != ESVIO_FE_OK) return rc;
+  if (left_first) {
+    if ((rc = run_event_stage_left_first(fe, w.slot, cur_time, ev, w.cur, w.rcur)) != ESVIO_FE_OK) return rc;
+    if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame, fe->k1l_done[w.slot], fe->p_done[w.slot],
+                              true)) != ESVIO_FE_OK)
+      return rc;
+    fe->pev_valid[w.slot] = fe->profiling;  // ESVIO_LEFT_FIRST=2 (diagnosis): the marks follow the left camera
+    return ESVIO_FE_OK;
+  }
   if ((rc = run_event_stage(fe, w.slot, cur_time, ev, w.cur, w.rcur, mc)) != ESVIO_FE_OK) return rc;
   if ((rc = submit_tracking(fe, w, ev[0], cur_time, pub_this_frame, fe->k1_done[w.slot],
                             fe->p_done[w.slot])) != ESVIO_FE_OK)

@@ -663,6 +663,21 @@ int event_stage_alloc(const BinLayout& L, int n_cams, int cap, EventStageBuffers
   return 0;
 }
 
+// The part of a two-camera buffer set that belongs to ONE camera, as a one-camera set of its own
+// (left-first windows run the cameras' event stages as separate launches): the per-camera arrays,
+// the camera's rows of bin_total / bin_start, and one half of the histogram table (its two pass
+// tables laid out for n_cams = 1; the table is scratch, rebuilt by every k_bin_hist).
+EventStageBuffers event_stage_cam_view(const BinLayout& L, const EventStageBuffers& E, int cam) {
+  EventStageBuffers v = E;
+  v.n_cams = 1;
+  v.counts = E.counts + (size_t)cam * 2 * L.max_chunks * kDigit;
+  v.bin_total = E.bin_total + (size_t)cam * (L.n_bins + 1);
+  v.bin_start = E.bin_start + (size_t)cam * (L.n_bins + 2);
+  v.bt[0] = E.bt[cam], v.bk[0] = E.bk[cam], v.it[0] = E.it[cam], v.ik[0] = E.ik[cam], v.im[0] = E.im[cam];
+  for (int c = 1; c < kMaxCams; ++c) v.bt[c] = nullptr, v.bk[c] = nullptr, v.it[c] = nullptr, v.ik[c] = nullptr, v.im[c] = nullptr;
+  return v;
+}
+
 void event_stage_free(EventStageBuffers* E) {
   for (int c = 0; c < kMaxCams; ++c) {
     cudaFree(E->bt[c]), cudaFree(E->bk[c]), cudaFree(E->it[c]), cudaFree(E->ik[c]), cudaFree(E->im[c]);

@@ -15,7 +15,11 @@ n_per_cam = int(round(w["rate"] / 30))
 cfg = dict(cfg, device_id=0, max_events_per_window=n_per_cam + 64)
 wins = bench.gen_windows(w, 0, K + Wm)
 fe = frontend.EventFrontEnd(cfg)
-dw = [(frontend._Ev(frontend.DeviceEvents(fe, L)), frontend._Ev(frontend.DeviceEvents(fe, R)), t) for L, R, t in wins]
+if os.environ.get("SYNC_TL_HOST"):   # pinned host buffers, both cameras of a window in one block
+    blocks = [frontend.PinnedStereoEvents(L, R) for L, R, _ in wins]
+    dw = [(frontend._Ev(b.left), frontend._Ev(b.right), w[2]) for b, w in zip(blocks, wins)]
+else:
+    dw = [(frontend._Ev(frontend.DeviceEvents(fe, L)), frontend._Ev(frontend.DeviceEvents(fe, R)), t) for L, R, t in wins]
 for k in range(Wm):
     fe.submit(dw[k][2], dw[k][0], dw[k][1], k % pub_div == 0); fe.wait(unpack=False)
 torch.cuda.synchronize()

@@ -475,6 +475,49 @@ def test_track_end_to_end(fe_mod, ora, W, H, rate, use_ransac):
     ft.fe.close()
 
 
+@pytest.mark.parametrize("W,H,rate,min_dist,max_cnt", [(346, 260, 1.0e6, 10, 150), (640, 480, 5.0e6, 20, 200)])
+def test_track_end_to_end_against_the_reference_code(fe_mod, W, H, rate, min_dist, max_cnt):
+    """CUDA against the reference's OWN FeatureTracker, without the oracle in between:
+    oracle/_ref/libesvio_ref_ft.so is feature_tracker.cpp + event_detector.cc compiled unmodified
+    (prebuilt in the build container; it travels to the GPU box with the snapshot, the reference
+    tree does not).  Same bar as test_track_end_to_end: identical ids, track counts and stage
+    results and (u, v) within 0.05 px while the two run in lock step -- the library's LK sums in
+    float, the GPU in exact integers, so after some windows one forward-backward test flips."""
+    from tests.ref_tracker import RefTracker, load_ref_lib
+    L_ = load_ref_lib()
+    cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=1 << 20, min_dist=min_dist,
+                               max_cnt=max_cnt)
+    ft = fe_mod.FeatureTracker(cfg)
+    rt = RefTracker(L_, cfg)
+    s = synth.StereoEventStream(W, H, rate)
+    freq_div = 2 if W == 346 else 3
+    horizon, compared = 0, 0
+    try:
+        for k in range(10):
+            L6, R6 = s.window(k, 0), s.window(k, 1)
+            t_ref = float(L6[2][-1])
+            ft.PUB_THIS_FRAME = (k % freq_div) == 0
+            ft.trackEvent(t_ref, L6[:4], R6[:4])
+            r = rt.track(t_ref, L6, R6, ft.PUB_THIS_FRAME)
+            if not (np.array_equal(ft.ids, r["id"]) and np.array_equal(ft.ids_right, r["id_right"])):
+                break
+            horizon = k + 1
+            assert np.array_equal(ft.track_cnt, r["track_cnt"])
+            if len(ft.ids):
+                assert np.abs(ft.cur_pts - np.stack([r["u"], r["v"]], 1)).max() <= 0.05
+                assert np.abs(ft.cur_un_pts - np.stack([r["un_x"], r["un_y"]], 1)).max() <= 0.05 / 200.0
+                assert np.allclose(ft.pts_velocity, np.stack([r["vx"], r["vy"]], 1), atol=0.05 / 200.0 * 30 * 2)
+            if len(ft.ids_right):
+                assert np.abs(ft.cur_right_pts - np.stack([r["ru"], r["rv"]], 1)).max() <= 0.05
+                assert np.abs(ft.cur_un_right_pts - np.stack([r["run_x"], r["run_y"]], 1)).max() <= 0.05 / 200.0
+            compared += len(ft.ids) + len(ft.ids_right)
+    finally:
+        rt.close()
+        ft.fe.close()
+    print(f"CUDA vs reference code {W}x{H}: lock step for {horizon}/10 windows, {compared} features compared")
+    assert horizon >= 4 and compared > 300, (horizon, compared)
+
+
 def test_submit_wait_pipeline_equals_sync(fe_mod):
     W, H = 346, 260
     cfg = synth.default_config(W, H, use_ransac=1, max_events_per_window=1 << 18)
