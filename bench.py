@@ -257,6 +257,40 @@ def reference_measure(workload, scene, n_streams, steps, warmup, cores):
     return n_ev / sec / 1e6, sec, res[0][3], res[0][4], res[0][5], threads
 
 
+def reference_code_record(workload, n_windows=8, warmup=2):
+    """The reference's OWN FeatureTracker::trackEvent (feature_tracker.cpp + event_detector.cc
+    compiled unmodified, oracle/_ref/libesvio_ref_ft.so) on a few windows, one thread.  Its OpenCV
+    calls are the oracle's scalar C restatements, not OpenCV's SIMD kernels, so it is SLOWER than
+    the oracle + cv2 arm above and is reported for information only -- the headline CPU arm stays
+    the faster one."""
+    from oracle import ref_tracker
+    L = ref_tracker.load()
+    if L is None:
+        return {"unavailable": "oracle/_ref/libesvio_ref_ft.so not built"}
+    from esvio_b200 import synth
+    w, cfg, pub_div = workload_cfg(workload)
+    s = synth.StereoEventStream(w["width"], w["height"], w["rate"], mono=w["mono"])
+    cfg = synth.default_config(w["width"], w["height"], max_cnt=w["max_cnt"], min_dist=w["min_dist"])
+    wins = [(s.window(k, 0), s.window(k, 1)) for k in range(warmup + n_windows)]
+    rt = ref_tracker.RefTracker(L, cfg)
+    try:
+        ev = 0
+        for k, (a, b) in enumerate(wins):
+            if k == warmup:
+                t0 = time.perf_counter()
+            rt.track(float(a[2][-1]), a, b, k % pub_div == 0)
+            if k >= warmup:
+                ev += len(a[0]) + len(b[0])
+        sec = time.perf_counter() - t0
+    finally:
+        rt.close()
+    return {"value": ev / sec / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
+            "ms_per_step": 1e3 * sec / n_windows,
+            "sample": f"{n_windows} windows of {workload} after {warmup} warm-up through the reference's own "
+                      "FeatureTracker::trackEvent (unmodified feature_tracker.cpp + event_detector.cc, "
+                      "oracle/_ref); OpenCV stand-ins = the oracle's scalar C restatements"}
+
+
 def main_reference(args):
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     if rank != 0:
@@ -277,11 +311,17 @@ def main_reference(args):
                                    f"{args.warmup} warm-up; {desc}; {threads} OpenCV threads per stream"
                                    + (", one process per stream" if n_streams > 1 else "")
                                    + "; the reference's own node cannot be built here (needs "
-                                     "ROS/OpenCV C++/Eigen), its event_detector.cc pins the oracle "
-                                     "(oracle/_ref)"},
+                                     "ROS/OpenCV C++/Eigen); its feature_tracker.cpp + event_detector.cc, "
+                                     "compiled unmodified against stand-in headers (oracle/_ref), pin this "
+                                     "oracle bit for bit and are timed as `reference_code`"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "stage_seconds": timers,
     }
+    if n_streams == 1:
+        try:
+            line["reference_code"] = reference_code_record(workload)
+        except Exception as e:  # informational: must not take the line down
+            line["reference_code"] = {"error": repr(e)}
     if n_streams == 1 and not args.no_rigid:
         rv, rsec, _, _, rtimers, _ = reference_measure(workload, "rigid", 1, args.steps,
                                                        args.warmup, cores)
