@@ -51,11 +51,8 @@ struct RefTracker {
   FeatureTracker ft;
 };
 
-// cfg: W, H, max_cnt, min_dist, flow_back, equalize, ignore_polarity, median_k, focal_length (ints);
-// dcfg: f_threshold, ts_lk_threshold, decay_ms, filter_threshold, then 2 x (fx fy cx cy k1 k2 p1 p2).
-// One tracker at a time: `detector`, n_id and the parameter globals are process-wide in the
-// reference (feature_tracker.cpp:7-9, parameters.cpp).
-REF_API void* ref_ft_create(const int* cfg, const double* dcfg, int image_mode) {
+// the parameter globals, the process-wide detector and id counters, as a fresh process has them
+void esvio_ref_apply_config(const int* cfg, const double* dcfg) {
   ROW = ROW_event = cfg[1];
   COL = COL_event = cfg[0];
   MAX_CNT = MAX_CNT_IMG = cfg[2];
@@ -71,20 +68,34 @@ REF_API void* ref_ft_create(const int* cfg, const double* dcfg, int image_mode) 
   para_feature_filter_threshold = dcfg[3];
   SHOW_TRACK = 0;
   FISHEYE = 0;
-  (void)image_mode;
   detector.~EventDetector();  // not assignable (const members): rebuilt in place
   new (&detector) esvio::EventDetector();
   FeatureTracker::n_id = 0;
   FeatureTracker::n_id_right = 0;
-  RefTracker* t = new RefTracker();
-  for (int c = 0; c < 2; ++c) {
-    const double* k = dcfg + 4 + 8 * c;
-    t->ft.stereo_m_camera.push_back(
-        camodocal::CameraPtr(new camodocal::PinholeCamera(k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7])));
-  }
   // fx, fy, cx, cy: stereo_readIntrinsicParameter leaves the LAST camera's values there
   // (feature_tracker.cpp:972-976); the harness passes the values the detector should get
   fx = dcfg[4], fy = dcfg[5], cx = dcfg[6], cy = dcfg[7];
+}
+
+// what stereo_readIntrinsicParameter (feature_tracker.cpp:966-978) leaves in stereo_m_camera
+void esvio_ref_install_cameras(FeatureTracker& ft, const double* dcfg) {
+  ft.stereo_m_camera.clear();
+  for (int c = 0; c < 2; ++c) {
+    const double* k = dcfg + 4 + 8 * c;
+    ft.stereo_m_camera.push_back(
+        camodocal::CameraPtr(new camodocal::PinholeCamera(k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7])));
+  }
+}
+
+// cfg: W, H, max_cnt, min_dist, flow_back, equalize, ignore_polarity, median_k, focal_length (ints);
+// dcfg: f_threshold, ts_lk_threshold, decay_ms, filter_threshold, then 2 x (fx fy cx cy k1 k2 p1 p2).
+// One tracker at a time: `detector`, n_id and the parameter globals are process-wide in the
+// reference (feature_tracker.cpp:7-9, parameters.cpp).
+REF_API void* ref_ft_create(const int* cfg, const double* dcfg, int image_mode) {
+  (void)image_mode;
+  esvio_ref_apply_config(cfg, dcfg);
+  RefTracker* t = new RefTracker();
+  esvio_ref_install_cameras(t->ft, dcfg);
   return t;
 }
 

@@ -1,0 +1,290 @@
+"""CPU suite: the node mirror pinned on the REFERENCE'S OWN event node.
+
+oracle/_ref/libesvio_ref_node.so is feature_tracker/src/stereo_event_tracker_node.cpp compiled
+UNMODIFIED (its main() renamed on the command line) on top of the unmodified feature_tracker.cpp
++ event_detector.cc (recipe: oracle/Makefile); ROS is a set of stand-in headers whose
+Publisher::publish hands the message to the harness (oracle/ref_shim/ref_node_api.cc).
+
+Each test plays one scripted stream through the reference's functions -- handle_stereo_event
+(node.cpp:145-344), event_callback_left/right (:128-142), sync_process on its own thread
+(:372-419), imu_callback / state_callback (:104-126) -- and through esvio_b200/node.py
+(StereoEventNode, EventPairer, MotionAssembler) around the oracle tracker, and demands the same
+decisions (publish gate, restarts, node state after every window, what the queues hold) and the
+same published PointClouds bit for bit (header stamp, points, id*2+cam, u, v, vx, vy).  The C++
+twin include/esvio_fe_node.hpp is held to node.py by the decision-trace test
+(tests/test_node_logic.py), and the tracker inside to the reference's FeatureTracker by
+tests/test_oracle_ref_tracker.py.
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import pytest
+
+from esvio_b200 import node, synth
+from oracle import oracle as ora
+from oracle import ref_tracker
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NODE_SO = os.path.join(ROOT, "oracle", "_ref", "libesvio_ref_node.so")
+_p = ref_tracker._p
+W, H = 346, 260
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if ref_tracker.load() is None or not os.path.exists(NODE_SO):   # load() runs `make ref` where it can
+        pytest.skip("oracle/_ref/libesvio_ref_node.so not built and /root/reference absent")
+    L = C.CDLL(NODE_SO)
+    ev = [C.c_void_p] * 5 + [C.c_size_t]
+    L.ref_node_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.ref_node_handle.argtypes = ev + ev + [C.c_uint32, C.c_uint32, C.c_double]
+    L.ref_node_push_events.argtypes = [C.c_int] + ev + [C.c_uint32, C.c_uint32]
+    L.ref_node_push_imu.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
+    L.ref_node_push_odometry.argtypes = [C.c_double, C.c_void_p]
+    L.ref_node_queue_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_node_cloud.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_node_state.argtypes = [C.c_void_p] * 5
+    L.ref_node_tracker_time.restype = C.c_double
+    L.ref_node_tracker_prev_time.restype = C.c_double
+    return L
+
+
+def _cfg_arrays(cfg):
+    icfg = np.array([cfg["width"], cfg["height"], cfg["max_cnt"], cfg["min_dist"], cfg["flow_back"],
+                     cfg["equalize"], cfg["ignore_polarity"], cfg["median_blur_kernel_size"],
+                     int(cfg["focal_length"])], np.int32)
+    d = [cfg["f_threshold"], cfg["ts_lk_threshold"], cfg["decay_ms"], cfg["feature_filter_threshold"]]
+    for cam in cfg["cam"]:
+        d += [cam[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")]
+    return icfg, np.array(d, np.float64)
+
+
+class _OracleFeatureTracker:
+    """The oracle behind the reference's member names (what node.py drives)."""
+
+    def __init__(self, cfg):
+        self.t = ora.OracleTracker(cfg, use_cv2=False)
+        self.PUB_THIS_FRAME = True
+        cam = cfg["cam"][0]
+        self.K = (cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+        self.cur_time = 0.0
+
+    def trackEvent(self, cur_time, left, right, measurements=None):
+        m = dict(measurements, K=self.K) if measurements is not None else None
+        r = self.t.track(cur_time, left, right, self.PUB_THIS_FRAME, motion=m)
+        self.cur_time = cur_time
+        self.ids, self.track_cnt = r["id"], r["track_cnt"]
+        self.cur_pts = np.stack([r["u"], r["v"]], 1)
+        self.cur_un_pts = np.stack([r["un_x"], r["un_y"]], 1)
+        self.pts_velocity = np.stack([r["vx"], r["vy"]], 1)
+        self.ids_right = r["id_right"]
+        self.cur_right_pts = np.stack([r["ru"], r["rv"]], 1)
+        self.cur_un_right_pts = np.stack([r["run_x"], r["run_y"]], 1)
+        self.right_pts_velocity = np.stack([r["rvx"], r["rvy"]], 1)
+
+
+def _window(s, k, stamp_us, n=None):
+    """(events of window k for both cameras incl. sec / nsec, header stamp (sec, nsec))."""
+    L6, R6 = s.window(k, 0, n), s.window(k, 1, n)
+    stamp = (synth.T0_SEC + stamp_us // 1_000_000, (stamp_us % 1_000_000) * 1000)
+    return L6, R6, stamp
+
+
+def _ev_args(e6):
+    x, y, _, p, sec, nsec = (np.ascontiguousarray(a) for a in e6)
+    return [_p(x), _p(y), _p(sec), _p(nsec), _p(p), len(x)], (x, y, p, sec, nsec)
+
+
+def _msg(e6, stamp):
+    return node.EventArray(node.to_sec(*stamp), e6[0], e6[1], e6[2], e6[3])
+
+
+def _ref_state(L):
+    ft, lt = C.c_double(), C.c_double()
+    cnt, ff, ip = C.c_int(), C.c_int(), C.c_int()
+    L.ref_node_state(C.byref(ft), C.byref(lt), C.byref(cnt), C.byref(ff), C.byref(ip))
+    return ft.value, lt.value, cnt.value, bool(ff.value), bool(ip.value)
+
+
+def _mirror_state(n):
+    return n.first_image_time, n.last_image_time, n.pub_count, n.first_image_flag, n.init_pub
+
+
+def _ref_clouds(L):
+    out = []
+    for i in range(L.ref_node_n_clouds()):
+        n = L.ref_node_cloud_points(i)
+        rows = np.zeros((n, 8), np.float32)
+        sec, nsec = C.c_uint32(), C.c_uint32()
+        L.ref_node_cloud(i, C.byref(sec), C.byref(nsec), _p(rows))
+        out.append(((sec.value, nsec.value), rows))
+    return out
+
+
+def _same_clouds(ref_clouds, mirror_clouds):
+    assert len(ref_clouds) == len(mirror_clouds)
+    for (stamp, rows), c in zip(ref_clouds, mirror_clouds):
+        assert stamp == node.ros_time(c.stamp)            # feature_points->header.stamp = ros::Time(msg_timestamp)
+        assert rows.shape == c.rows.shape
+        assert np.array_equal(rows.view(np.int32), np.ascontiguousarray(c.rows).view(np.int32))
+
+
+@pytest.mark.parametrize("freq", [10, 15, 30])
+def test_handle_stereo_event_equals_reference(ref, freq):
+    """24 windows at 30 Hz with an empty left window, a forward jump of more than a second, a step
+    back in time, and the publish-rate gate at FREQ 10 / 15 / 30 (config/*/es*io.yaml): same
+    PUB_THIS_FRAME, same node state after every call, same restarts, same clouds."""
+    cfg = synth.default_config(W, H)
+    icfg, dcfg = _cfg_arrays(cfg)
+    ref.ref_node_reset(_p(icfg), _p(dcfg), freq, 0)
+    mt = _OracleFeatureTracker(cfg)
+    mn = node.StereoEventNode(mt, freq)
+    s = synth.StereoEventStream(W, H, 0.45e6)
+    win_us = 1_000_000 // synth.WINDOWS_PER_SEC
+    mirror_clouds, pubs = [], 0
+    # script: (stream window, header stamp in us since T0, events per camera or None = all)
+    script = [(k, (k + 1) * win_us, None) for k in range(10)]
+    script.insert(4, (4, 5 * win_us, 0))                                 # an EventArray without events
+    script += [(10, 11 * win_us + 1_500_000, None)]                      # > 1 s later: restart
+    script += [(11 + k, (12 + k) * win_us + 1_500_000, None) for k in range(7)]
+    script += [(18, 15 * win_us + 1_500_000, None)]                      # a step back in time: restart
+    script += [(19 + k, (20 + k) * win_us + 1_500_000, None) for k in range(5)]
+    for k, stamp_us, n in script:
+        L6, R6, stamp = _window(s, k, stamp_us, n)
+        la, keep_l = _ev_args(L6)
+        ra, keep_r = _ev_args(R6)
+        msg_t = node.to_sec(*stamp)                                       # sync_process: header stamp (:386,399)
+        pub_ref = ref.ref_node_handle(*la, *ra, stamp[0], stamp[1], msg_t)
+        tracked_before = mn.windows_tracked
+        c = mn.handle_stereo_event(_msg(L6, stamp), _msg(R6, stamp), msg_t)
+        if c is not None:
+            mirror_clouds.append(c)
+        assert _ref_state(ref) == _mirror_state(mn), (k, _ref_state(ref), _mirror_state(mn))
+        if mn.windows_tracked > tracked_before:          # the call got as far as trackEvent
+            assert bool(pub_ref) == bool(mt.PUB_THIS_FRAME), k
+            assert ref.ref_node_tracker_time() == mt.cur_time == float(L6[2][-1])   # :190,193
+        pubs += int(bool(pub_ref))
+    assert ref.ref_node_n_restarts() == mn.restarts == 2
+    _same_clouds(_ref_clouds(ref), mirror_clouds)
+    assert len(mirror_clouds) >= 3 and sum(len(c.rows) for c in mirror_clouds) > 50
+    assert 0 < pubs
+
+
+def test_motion_compensation_assembly_equals_reference(ref):
+    """Do_motion_correction = 1 (node.cpp:195-254): the Motion_correction_value assembled from the
+    IMU / odometry queues -- one odometry message consumed per window, velocity-differenced
+    acceleration, IMU messages before the first left event dropped, disordered IMU stamps refused
+    -- and the clock / header stamp handed to trackEvent."""
+    cfg = synth.default_config(W, H)
+    icfg, dcfg = _cfg_arrays(cfg)
+    ref.ref_node_reset(_p(icfg), _p(dcfg), 15, 1)
+    ma = node.MotionAssembler()
+    mt = _OracleFeatureTracker(cfg)
+    mn = node.StereoEventNode(mt, 15, do_motion_correction=True, motion=ma)
+    s = synth.StereoEventStream(W, H, 0.45e6, stream=3)
+    win_us = 1_000_000 // synth.WINDOWS_PER_SEC
+    mirror_clouds = []
+    rng = np.random.default_rng(4)
+    for k in range(12):
+        L6, R6, stamp = _window(s, k, (k + 1) * win_us)
+        t0 = float(L6[2][0])
+        # IMU at 200 Hz-ish around the window, one of them out of order; odometry on most windows
+        for j in range(5):
+            t_imu = t0 - 0.004 + 0.006 * j if j != 3 else t0 - 0.010
+            om = rng.normal(0, 1.2, 3)
+            ac = rng.normal(0, 2.0, 3) + (0, 0, 9.805)
+            ref.ref_node_push_imu(t_imu, _p(om), _p(ac))
+            ma.push_imu(node.Imu(t_imu, tuple(om), tuple(ac)))
+        if k % 4 != 1:
+            v = np.array([0.3 * k, -0.2 * k * (k % 3), 0.05 * k * k])      # accelerations above and below 5 m/s^2
+            ref.ref_node_push_odometry(t0 - 0.002, _p(v))
+            ma.push_odometry(node.Odometry(t0 - 0.002, tuple(v)))
+        la, _kl = _ev_args(L6)
+        ra, _kr = _ev_args(R6)
+        msg_t = node.to_sec(*stamp)
+        ref.ref_node_handle(*la, *ra, stamp[0], stamp[1], msg_t)
+        tracked_before = mn.windows_tracked
+        c = mn.handle_stereo_event(_msg(L6, stamp), _msg(R6, stamp), msg_t)
+        if c is not None:
+            mirror_clouds.append(c)
+        assert _ref_state(ref) == _mirror_state(mn), k
+        if mn.windows_tracked > tracked_before:
+            assert ref.ref_node_tracker_time() == mt.cur_time == float(L6[2][-1])   # :190,254
+    _same_clouds(_ref_clouds(ref), mirror_clouds)
+    assert len(mirror_clouds) >= 3
+
+
+def _settle(L, timeout=20.0):
+    """Wait until sync_process (2 ms poll, node.cpp:415) has taken what it can take: the queues
+    stop changing and no trackEvent is running (prev_time == cur_time at its end, :587)."""
+    deadline = time.time() + timeout
+    stable, last = 0, None
+    while time.time() < deadline:
+        a, b = C.c_int(), C.c_int()
+        L.ref_node_queue_sizes(C.byref(a), C.byref(b))
+        cur = (a.value, b.value, L.ref_node_tracker_time(), L.ref_node_n_clouds(), _ref_state(L))
+        busy = L.ref_node_tracker_prev_time() != L.ref_node_tracker_time()    # inside trackEvent
+        stable = stable + 1 if (cur == last and not busy) else 0
+        last = cur
+        if stable >= 6:
+            return a.value, b.value
+        time.sleep(0.01)
+    raise AssertionError("sync_process did not settle")
+
+
+def test_pairing_through_the_callbacks_and_sync_process(ref):
+    """Messages arrive through event_callback_left/right (depth-1 queues: a new message REPLACES
+    the waiting one) while sync_process runs on its own thread, as in the node: pairs within the
+    0.2 s tolerance are handled, an older side is thrown away, an overwritten message is never
+    seen.  The mirror's EventPairer + StereoEventNode must end every step with the same queues,
+    node state and clouds."""
+    cfg = synth.default_config(W, H)
+    icfg, dcfg = _cfg_arrays(cfg)
+    ref.ref_node_reset(_p(icfg), _p(dcfg), 30, 0)
+    ref.ref_node_start_sync_thread()
+    mt = _OracleFeatureTracker(cfg)
+    mn = node.StereoEventNode(mt, 30)
+    pairer = node.EventPairer()
+    s = synth.StereoEventStream(W, H, 0.3e6, stream=5)
+    win_us = 1_000_000 // synth.WINDOWS_PER_SEC
+    mirror_clouds = []
+
+    def push(side, k, stamp_us):
+        e6 = s.window(k, side)
+        stamp = (synth.T0_SEC + stamp_us // 1_000_000, (stamp_us % 1_000_000) * 1000)
+        args, _keep = _ev_args(e6)
+        ref.ref_node_push_events(side, *args, stamp[0], stamp[1])
+        (pairer.push_left if side == 0 else pairer.push_right)(_msg(e6, stamp))
+
+    def step(pushes):
+        for side, k, stamp_us in pushes:
+            push(side, k, stamp_us)
+        ql, qr = _settle(ref)
+        while pairer.left and pairer.right:          # the consumer keeps up: poll until nothing more can happen
+            pair = pairer.poll()
+            if pair is not None:
+                c = mn.handle_stereo_event(*pair)
+                if c is not None:
+                    mirror_clouds.append(c)
+        assert (ql, qr) == (len(pairer.left), len(pairer.right))
+        assert _ref_state(ref) == _mirror_state(mn)
+
+    T = win_us
+    step([(0, 0, 1 * T), (1, 0, 1 * T)])                          # a pair (first window: skipped by the node)
+    step([(0, 1, 2 * T)])                                         # left alone: waits
+    step([(1, 1, 2 * T)])                                         # its partner arrives
+    step([(0, 2, 3 * T), (0, 3, 4 * T)])                          # the second left message replaces the first ...
+    step([(1, 3, 4 * T)])                                         # ... and pairs with this one
+    step([(1, 4, 5 * T)])                                         # right alone
+    step([(0, 4, 5 * T + 150_000)])                               # 0.15 s apart: inside the tolerance
+    step([(0, 5, 6 * T), (1, 5, 6 * T + 400_000)])                # left older than right - 0.2 s: left thrown away
+    step([(0, 6, 6 * T + 450_000)])                               # pairs with the waiting right message
+    step([(1, 7, 8 * T), (0, 7, 8 * T + 900_000)])                # right older than left - 0.2 s: right thrown away
+    step([(1, 8, 8 * T + 900_000)])
+    for k in range(9, 14):                                        # a run of ordinary pairs: clouds get published
+        step([(0, k, (k + 20) * T), (1, k, (k + 20) * T)])
+    assert ref.ref_node_n_restarts() == mn.restarts
+    _same_clouds(_ref_clouds(ref), mirror_clouds)
+    assert mn.windows_tracked >= 8 and len(mirror_clouds) >= 3
