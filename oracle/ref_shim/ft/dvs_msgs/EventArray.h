@@ -4,6 +4,7 @@
 #include "Event.h"
 namespace dvs_msgs {
 struct EventArray {
+  typedef std::shared_ptr<const EventArray> ConstPtr;
   std_msgs::Header header;
   uint32_t height = 0, width = 0;
   std::vector<Event> events;

@@ -288,3 +288,57 @@ def test_pairing_through_the_callbacks_and_sync_process(ref):
     assert ref.ref_node_n_restarts() == mn.restarts
     _same_clouds(_ref_clouds(ref), mirror_clouds)
     assert mn.windows_tracked >= 8 and len(mirror_clouds) >= 3
+
+
+@pytest.mark.parametrize("frequency", [30.0, 1000.0])
+def test_event_windower_equals_event_message_editor(ref, frequency):
+    """The reference's re-packing tool (dependences/events_repacking_helper/src/
+    EventMessageEditor.cpp:8-57, included unmodified) fed event by event, against
+    node.EventWindower fed in chunks: same number of written messages, same header stamps (to the
+    nanosecond, ros::Time rounding included), same events in each -- over a dense stretch, holes
+    longer than a window (one short message per event until the end time has caught up), events
+    exactly on a window's end, and repeated timestamps."""
+    ref.ref_eme_create.restype = C.c_void_p
+    ref.ref_eme_create.argtypes = [C.c_double]
+    ref.ref_eme_insert.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_size_t]
+    ref.ref_eme_count.argtypes = [C.c_void_p]
+    ref.ref_eme_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    ref.ref_eme_destroy.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(7)
+    period_us = int(round(1e6 / frequency))
+    # event times in us since T0: dense noise, a hole of 3.7 windows, a burst of equal stamps, events
+    # placed exactly on multiples of the window length after the first event, a long hole, a tail
+    t0 = 123_456
+    parts = [t0 + np.sort(rng.integers(0, 12 * period_us, 4000))]
+    parts.append(parts[-1][-1] + int(3.7 * period_us) + np.sort(rng.integers(0, 5 * period_us, 1500)))
+    parts.append(np.full(40, parts[-1][-1] + 17))
+    parts.append(t0 + period_us * np.arange(30, 40))
+    parts.append(parts[-1][-1] + 25 * period_us + np.sort(rng.integers(0, 6 * period_us, 2000)))
+    us = np.sort(np.concatenate(parts)).astype(np.int64)
+    sec = (synth.T0_SEC + us // 1_000_000).astype(np.uint32)
+    nsec = ((us % 1_000_000) * 1000).astype(np.uint32)
+    t = sec.astype(np.float64) + 1e-9 * nsec.astype(np.float64)
+    n = len(us)
+    x = rng.integers(0, W, n).astype(np.uint16)
+    y = rng.integers(0, H, n).astype(np.uint16)
+    p = rng.integers(0, 2, n).astype(np.uint8)
+    h = ref.ref_eme_create(frequency)
+    wd = node.EventWindower(frequency)
+    msgs = []
+    cuts = [0, 1, 2, 700, 701, 4000, 5533, n]             # chunk boundaries: arbitrary, incl. one-event chunks
+    for a, b in zip(cuts, cuts[1:]):
+        ref.ref_eme_insert(h, _p(x[a:b].copy()), _p(y[a:b].copy()), _p(sec[a:b].copy()), _p(nsec[a:b].copy()),
+                           _p(p[a:b].copy()), b - a)
+        msgs += wd.insert(x[a:b], y[a:b], t[a:b], p[a:b])
+    assert ref.ref_eme_count(h) == len(msgs) > 40
+    short = 0
+    for i, m in enumerate(msgs):
+        r = np.zeros(9, np.uint32)
+        ref.ref_eme_get(h, i, _p(r))
+        assert (int(r[0]), int(r[1])) == (int(r[2]), int(r[3])) == node.ros_time(m.stamp), i   # write time = header stamp
+        assert int(r[4]) == len(m), i
+        if len(m):
+            assert node.to_sec(int(r[5]), int(r[6])) == m.t[0] and node.to_sec(int(r[7]), int(r[8])) == m.t[-1], i
+        short += len(m) == 1
+    assert short >= 3      # the holes produced their one-event messages
+    ref.ref_eme_destroy(h)
