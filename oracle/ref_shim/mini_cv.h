@@ -91,6 +91,7 @@ struct TermCriteria {
   TermCriteria(int t, int n, double e) : type(t), maxCount(n), epsilon(e) {}
 };
 enum { OPTFLOW_USE_INITIAL_FLOW = 4, FM_RANSAC = 8 };
+enum { COLOR_BGR2GRAY = 6, COLOR_RGB2GRAY = 7 };
 struct Vec3b {
   unsigned char v[3];
   Vec3b() : v{0, 0, 0} {}
@@ -239,6 +240,8 @@ inline void vconcat(const Mat& a, const Mat&, Mat& dst) { dst = a.clone(); }
 inline void cvtColor(const Mat& a, Mat& dst, int) { Mat t = a.clone(); dst = t; }
 template <class S>
 inline bool imwrite(const S&, const Mat&) { return false; }
+// the image node resizes frames whose size differs from the configuration (never the case here)
+inline void resize(const Mat& a, Mat& dst, Size) { Mat t = a.clone(); dst = t; }
 
 // cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, winSize, maxLevel,
 //                          criteria = (COUNT+EPS, 30, 0.01), flags = 0, minEigThreshold = 1e-4)

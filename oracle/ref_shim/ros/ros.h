@@ -50,6 +50,8 @@ class NodeHandle {
   NodeHandle(const char*) {}
   template <class F>
   Subscriber subscribe(const std::string&, int, F, TransportHints = TransportHints()) { return Subscriber(); }
+  template <class M>
+  Publisher advertise(const std::string&, int) { return Publisher(); }
 };
 inline void init(int&, char**, const char*) {}
 inline void spin() {}

@@ -342,3 +342,158 @@ def test_event_windower_equals_event_message_editor(ref, frequency):
         short += len(m) == 1
     assert short >= 3      # the holes produced their one-event messages
     ref.ref_eme_destroy(h)
+
+
+# ---- the image node (stereo_image_tracker_node.cpp) -----------------------------------------------
+IMG_SO = os.path.join(ROOT, "oracle", "_ref", "libesvio_ref_imgnode.so")
+IW, IH = 240, 180
+
+
+@pytest.fixture(scope="module")
+def ref_img():
+    if ref_tracker.load() is None or not os.path.exists(IMG_SO):
+        pytest.skip("oracle/_ref/libesvio_ref_imgnode.so not built and /root/reference absent")
+    L = C.CDLL(IMG_SO)
+    L.ref_imgnode_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.ref_imgnode_handle.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    L.ref_imgnode_push_image.argtypes = [C.c_int, C.c_void_p, C.c_double]
+    L.ref_imgnode_queue_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_imgnode_cloud.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_imgnode_state.argtypes = [C.c_void_p] * 5
+    L.ref_imgnode_tracker_time.restype = C.c_double
+    L.ref_imgnode_tracker_prev_time.restype = C.c_double
+    return L
+
+
+class _OracleImageTracker:
+    """The oracle's trackImage behind the reference's member names; `clahe`: the image node's own
+    CLAHE on both frames before the call (stereo_image_tracker_node.cpp:93-97)."""
+
+    def __init__(self, cfg, clahe=False):
+        self.t = ora.OracleTracker(cfg, use_cv2=False)
+        self.PUB_THIS_FRAME = True
+        self.clahe = clahe
+
+    def trackImage(self, cur_time, left, right):
+        if self.clahe:
+            left, right = ora.clahe(left), ora.clahe(right)
+        r = self.t.track_image(cur_time, left, right, self.PUB_THIS_FRAME)
+        self.ids, self.track_cnt = r["id"], r["track_cnt"]
+        self.cur_pts = np.stack([r["u"], r["v"]], 1)
+        self.cur_un_pts = np.stack([r["un_x"], r["un_y"]], 1)
+        self.pts_velocity = np.stack([r["vx"], r["vy"]], 1)
+        self.ids_right = r["id_right"]
+        self.cur_right_pts = np.stack([r["ru"], r["rv"]], 1)
+        self.cur_un_right_pts = np.stack([r["run_x"], r["run_y"]], 1)
+        self.right_pts_velocity = np.stack([r["rvx"], r["rvy"]], 1)
+
+
+def _img_state(L):
+    ft, lt = C.c_double(), C.c_double()
+    cnt, ff, ip = C.c_int(), C.c_int(), C.c_int()
+    L.ref_imgnode_state(C.byref(ft), C.byref(lt), C.byref(cnt), C.byref(ff), C.byref(ip))
+    return ft.value, lt.value, cnt.value, bool(ff.value), bool(ip.value)
+
+
+def _img_clouds(L):
+    out = []
+    for i in range(L.ref_imgnode_n_clouds()):
+        rows = np.zeros((L.ref_imgnode_cloud_points(i), 8), np.float32)
+        sec, nsec = C.c_uint32(), C.c_uint32()
+        L.ref_imgnode_cloud(i, C.byref(sec), C.byref(nsec), _p(rows))
+        out.append(((sec.value, nsec.value), rows))
+    return out
+
+
+@pytest.mark.parametrize("freq,equalize", [(10, 0), (20, 0), (10, 1)])
+def test_handle_stereo_image_equals_reference(ref_img, freq, equalize):
+    """handle_stereo_image (stereo_image_tracker_node.cpp:55-183) on a 14-frame stereo sequence at
+    20 Hz with a jump of more than a second: the publish-rate gate, restart, first-publish
+    suppression, the node's own CLAHE when EQUALIZE is set, and the published clouds."""
+    cfg = synth.default_config(IW, IH, min_dist=14, max_cnt=60, equalize=equalize)
+    icfg, dcfg = _cfg_arrays(cfg)
+    ref_img.ref_imgnode_reset(_p(icfg), _p(dcfg), freq)
+    mt = _OracleImageTracker(dict(cfg, equalize=0), clahe=bool(equalize))
+    mn = node.StereoImageNode(mt, freq)
+    frames = synth.stereo_frame_sequence(IW, IH, 14)
+    mirror_clouds = []
+    for k, (fl, fr_) in enumerate(frames):
+        t = 1_700_000_000.0 + k / 20.0 + (1.6 if k >= 8 else 0.0)
+        fl, fr_ = np.ascontiguousarray(fl), np.ascontiguousarray(fr_)
+        pub_ref = ref_img.ref_imgnode_handle(_p(fl), _p(fr_), t)
+        before = mn.windows_tracked
+        c = mn.handle_stereo_image(fl, fr_, t)
+        if c is not None:
+            mirror_clouds.append(c)
+        assert _img_state(ref_img) == _mirror_state(mn), k
+        if mn.windows_tracked > before:
+            assert bool(pub_ref) == bool(mt.PUB_THIS_FRAME), k
+            assert ref_img.ref_imgnode_tracker_time() == t                     # :99 hands msg_timestamp
+    assert ref_img.ref_imgnode_n_restarts() == mn.restarts == 1
+    _same_clouds(_img_clouds(ref_img), mirror_clouds)
+    assert len(mirror_clouds) >= 2 and sum(len(c.rows) for c in mirror_clouds) > 60
+
+
+def test_image_pairing_through_the_callbacks_and_sync_process(ref_img):
+    """mono8 frames through img_callback_left/right while the image node's sync_process runs on its
+    own thread: depth-1 queues, the 1 s tolerance with its asymmetric comparisons (a left frame
+    EXACTLY one second older than the right one is thrown, one exactly a second newer is not),
+    getImageFromMsg.  ImagePairer + StereoImageNode must end every step with the same queues,
+    node state and clouds."""
+    cfg = synth.default_config(IW, IH, min_dist=14, max_cnt=60)
+    icfg, dcfg = _cfg_arrays(cfg)
+    ref_img.ref_imgnode_reset(_p(icfg), _p(dcfg), 20)
+    ref_img.ref_imgnode_start_sync_thread()
+    mt = _OracleImageTracker(cfg)
+    mn = node.StereoImageNode(mt, 20)
+    pairer = node.ImagePairer()
+    frames = synth.stereo_frame_sequence(IW, IH, 14)
+    mirror_clouds = []
+    T0 = 1_700_000_000.0
+
+    def settle():
+        deadline, stable, last = time.time() + 20.0, 0, None
+        while time.time() < deadline:
+            a, b = C.c_int(), C.c_int()
+            ref_img.ref_imgnode_queue_sizes(C.byref(a), C.byref(b))
+            cur = (a.value, b.value, ref_img.ref_imgnode_tracker_time(), ref_img.ref_imgnode_n_clouds(),
+                   _img_state(ref_img))
+            busy = ref_img.ref_imgnode_tracker_prev_time() != ref_img.ref_imgnode_tracker_time()
+            stable = stable + 1 if (cur == last and not busy) else 0
+            last = cur
+            if stable >= 6:
+                return a.value, b.value
+            time.sleep(0.01)
+        raise AssertionError("sync_process did not settle")
+
+    def step(pushes):
+        for side, k, t in pushes:
+            img = np.ascontiguousarray(frames[k][side])
+            ref_img.ref_imgnode_push_image(side, _p(img), T0 + t)
+            (pairer.push_left if side == 0 else pairer.push_right)(node.ImageMsg(T0 + t, img))
+        ql, qr = settle()
+        while pairer.left and pairer.right:
+            pair = pairer.poll()
+            if pair is not None:
+                c = mn.handle_stereo_image(pair[0].image, pair[1].image, pair[2])
+                if c is not None:
+                    mirror_clouds.append(c)
+        assert (ql, qr) == (len(pairer.left), len(pairer.right))
+        assert _img_state(ref_img) == _mirror_state(mn)
+
+    step([(0, 0, 0.00), (1, 0, 0.00)])                 # first pair: skipped by the node
+    step([(0, 1, 0.05)])
+    step([(1, 1, 0.05)])
+    step([(0, 2, 0.10), (0, 3, 0.15)])                 # the waiting left frame is replaced
+    step([(1, 3, 0.15)])
+    step([(0, 4, 0.20), (1, 4, 1.20)])                 # left exactly 1 s older: thrown (`<=`)
+    step([(0, 5, 2.20)])                               # left exactly 1 s newer than the waiting right: a pair (`>`);
+    #                                                    2 s after the last handled frame: restart
+    step([(0, 6, 2.25), (1, 6, 2.25)])                 # first frame after the restart
+    step([(1, 7, 2.30), (0, 7, 3.35)])                 # right more than 1 s older: thrown
+    step([(1, 8, 3.35)])                               # more than 1 s after 2.25: another restart
+    for k in range(9, 14):
+        step([(0, k, 3.0 + k * 0.05), (1, k, 3.0 + k * 0.05)])
+    assert ref_img.ref_imgnode_n_restarts() == mn.restarts >= 1
+    _same_clouds(_img_clouds(ref_img), mirror_clouds)
+    assert mn.windows_tracked >= 5 and len(mirror_clouds) >= 1
