@@ -311,7 +311,8 @@ class StereoImageNode(StereoEventNode):
     reference's names: the same first-frame skip, restart rule, publish-rate gate, cloud
     packing and first-publish suppression as the event node; the tracker call is
     trackImage(msg_timestamp, img_left, img_right) (:99).  The node's own CLAHE (`EQUALIZE`,
-    :93-97) is not mirrored."""
+    :93-97) belongs to the tracker behind this class: the GPU frame path applies it to the
+    uploaded frames when cfg.equalize is set (esvio_fe_track_image)."""
 
     def __init__(self, tracker, freq: int):
         super().__init__(tracker, freq)
