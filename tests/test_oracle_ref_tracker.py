@@ -122,6 +122,12 @@ def test_track_event_equals_reference_vga(ref):
     _run_events(ref, cfg, 5.0e6, 7, 3, rigid=True)
 
 
+def test_track_event_equals_reference_vga_burst(ref):
+    """640x480 @20 Mev/s bursts with 200 corners (BASELINE configs[3]) and @10 Mev/s (configs[4])."""
+    _run_events(ref, synth.default_config(640, 480, max_cnt=200), 20.0e6, 4, 3)
+    _run_events(ref, synth.default_config(640, 480), 10.0e6, 4, 3, stream=1)
+
+
 @pytest.mark.parametrize("kw", [dict(equalize=1), dict(median_blur_kernel_size=3), dict(ignore_polarity=1),
                                 dict(flow_back=0), dict(decay_ms=30.0, feature_filter_threshold=0.02)])
 def test_track_event_equals_reference_options(ref, kw):
