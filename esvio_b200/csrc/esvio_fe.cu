@@ -2495,7 +2495,8 @@ FE_API int esvio_fe_stage_set_tracks(esvio_fe* fe, double prev_time, int32_t nex
 
 FE_API int esvio_fe_stage_sort_order(esvio_fe* fe, const int32_t* key, int32_t n, int32_t depth_limit,
                                      int32_t* order) {
-  if (!fe || n < 0 || n > kMaxCnt || (n > 0 && (!key || !order))) return ESVIO_FE_EINVAL;
+  // depth_limit: the replay keeps one pending range per level (32 slots); the library's own budget is <= 20
+  if (!fe || n < 0 || n > kMaxCnt || depth_limit > 30 || (n > 0 && (!key || !order))) return ESVIO_FE_EINVAL;
   if (n == 0) return ESVIO_FE_OK;
   CU(cudaSetDevice(fe->dev));
   cudaStream_t s = fe->stream;

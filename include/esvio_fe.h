@@ -418,7 +418,8 @@ int esvio_fe_stage_select(esvio_fe *fe, const esvio_events *left, int32_t n, con
 /* The visiting order of Event_setMask / Image_setMask: `sort(..., a.first > b.first)`
  * (feature_tracker.cpp:100-103,132-135) as GCC's libstdc++ runs it -- order[k] = index of the
  * element at position k; ties land where the library's introsort puts them.  depth_limit < 0:
- * the library's own recursion budget; n <= 1024. */
+ * the library's own recursion budget (test runs force 0..30 to reach its heap-sort branch);
+ * n <= 1024. */
 int esvio_fe_stage_sort_order(esvio_fe *fe, const int32_t *key, int32_t n, int32_t depth_limit,
                               int32_t *order);
 /* PinholeCamera::liftProjective (PinholeCamera.cc:450-510) -> (x/z, y/z) as f32 */
