@@ -115,6 +115,8 @@ REF_API void ref_imgnode_start_sync_thread() {
   if (started.exchange(true)) return;
   std::thread(sync_process).detach();
 }
+// see ref_node_park_sync_thread (ref_node_api.cc)
+REF_API void ref_imgnode_park_sync_thread() { m_buf.lock(); }
 REF_API void ref_imgnode_queue_sizes(int* left, int* right) {
   std::lock_guard<std::mutex> lock(m_buf);
   *left = (int)img_left_buf.size();

@@ -167,6 +167,11 @@ REF_API void ref_node_start_sync_thread() {
   std::thread(sync_process).detach();
 }
 
+// sync_process never returns; before the process ends the harness parks it: the node's own mutex is
+// taken and kept, so the thread blocks at its next poll and touches nothing while the library's
+// statics are torn down.  Nothing that takes m_buf_event may be called afterwards.
+REF_API void ref_node_park_sync_thread() { m_buf_event.lock(); }
+
 // sizes of the two depth-1 queues (under the node's own mutex)
 REF_API void ref_node_queue_sizes(int* left, int* right) {
   std::lock_guard<std::mutex> lock(m_buf_event);

@@ -48,7 +48,8 @@ def ref():
     L.ref_node_state.argtypes = [C.c_void_p] * 5
     L.ref_node_tracker_time.restype = C.c_double
     L.ref_node_tracker_prev_time.restype = C.c_double
-    return L
+    yield L
+    L.ref_node_park_sync_thread()     # the detached sync_process thread must not run into interpreter shutdown
 
 
 def _cfg_arrays(cfg):
@@ -362,7 +363,8 @@ def ref_img():
     L.ref_imgnode_state.argtypes = [C.c_void_p] * 5
     L.ref_imgnode_tracker_time.restype = C.c_double
     L.ref_imgnode_tracker_prev_time.restype = C.c_double
-    return L
+    yield L
+    L.ref_imgnode_park_sync_thread()
 
 
 class _OracleImageTracker:
