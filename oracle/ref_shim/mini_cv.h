@@ -47,6 +47,19 @@ int ora_good_features_to_track(const uint8_t* img, int W, int H, const uint8_t* 
                                float* out_xy);
 int ora_find_fundamental_mask(const float* pts1, const float* pts2, int n, double thresh,
                               double confidence, int max_iters, uint8_t* mask);
+// Optional replacements installed by the harness (ref_ft_set_cv_hooks): the same calls served by
+// REAL OpenCV (cv2, through ctypes callbacks) instead of the oracle's restatements -- the
+// reference's code then runs on the library it was written for.  Null = the restatement.
+typedef void (*esvio_ref_lk_hook)(const uint8_t* prev, const uint8_t* next, int W, int H, const float* prev_pts,
+                                  float* next_pts, int n, uint8_t* status, int max_level, int use_initial_flow);
+typedef int (*esvio_ref_fm_hook)(const float* pts1, const float* pts2, int n, double thresh, uint8_t* mask);
+typedef void (*esvio_ref_img_hook)(const uint8_t* src, int W, int H, uint8_t* dst);
+typedef int (*esvio_ref_gftt_hook)(const uint8_t* img, int W, int H, const uint8_t* mask, int max_corners,
+                                   double quality, double min_distance, float* out_xy);
+extern esvio_ref_lk_hook esvio_ref_hook_lk;
+extern esvio_ref_fm_hook esvio_ref_hook_fm;
+extern esvio_ref_img_hook esvio_ref_hook_clahe, esvio_ref_hook_normalize;
+extern esvio_ref_gftt_hook esvio_ref_hook_gftt;
 }
 
 namespace cv {
@@ -255,6 +268,11 @@ inline void calcOpticalFlowPyrLK(const Mat& prev, const Mat& next, const std::ve
   status.assign(n, 0);
   err.assign(n, 0.f);
   if (n == 0) return;
+  if (esvio_ref_hook_lk && win.width == 21 && crit.maxCount == 30 && crit.epsilon == 0.01 && min_eig == 1e-4) {
+    esvio_ref_hook_lk(prev.ptr(), next.ptr(), prev.cols, prev.rows, reinterpret_cast<const float*>(prev_pts.data()),
+                      reinterpret_cast<float*>(next_pts.data()), n, status.data(), max_level, init ? 1 : 0);
+    return;
+  }
   ora_calc_optical_flow_pyr_lk(prev.ptr(), next.ptr(), prev.cols, prev.rows,
                                reinterpret_cast<const float*>(prev_pts.data()),
                                reinterpret_cast<float*>(next_pts.data()), n, status.data(), win.width,
@@ -266,7 +284,10 @@ inline Mat findFundamentalMat(const std::vector<Point2f>& p1, const std::vector<
                               double thresh, double confidence, std::vector<unsigned char>& mask) {
   const int n = (int)p1.size();
   mask.assign(n, 0);
-  if (n > 0)
+  if (n > 0 && esvio_ref_hook_fm && confidence == 0.99)
+    esvio_ref_hook_fm(reinterpret_cast<const float*>(p1.data()), reinterpret_cast<const float*>(p2.data()), n, thresh,
+                      mask.data());
+  else if (n > 0)
     ora_find_fundamental_mask(reinterpret_cast<const float*>(p1.data()), reinterpret_cast<const float*>(p2.data()),
                               n, thresh, confidence, 1000, mask.data());
   return Mat();
@@ -276,7 +297,8 @@ inline Mat findFundamentalMat(const std::vector<Point2f>& p1, const std::vector<
 struct CLAHE {
   void apply(const Mat& src, Mat& dst) const {
     Mat out = Mat::zeros(src.size(), CV_8U);
-    ora_clahe_u8(src.ptr(), src.cols, src.rows, 40.0, 8, out.ptr());
+    if (esvio_ref_hook_clahe) esvio_ref_hook_clahe(src.ptr(), src.cols, src.rows, out.ptr());
+    else ora_clahe_u8(src.ptr(), src.cols, src.rows, 40.0, 8, out.ptr());
     dst = out;
   }
 };
@@ -286,7 +308,8 @@ inline Ptr<CLAHE> createCLAHE() { return std::make_shared<CLAHE>(); }
 // cv::normalize(src, dst, 0, 255, NORM_MINMAX) on CV_8U
 inline void normalize(const Mat& src, Mat& dst, double, double, int) {
   Mat out = Mat::zeros(src.size(), CV_8U);
-  ora_normalize_minmax_u8(src.ptr(), (size_t)src.rows * src.cols, out.ptr());
+  if (esvio_ref_hook_normalize) esvio_ref_hook_normalize(src.ptr(), src.cols, src.rows, out.ptr());
+  else ora_normalize_minmax_u8(src.ptr(), (size_t)src.rows * src.cols, out.ptr());
   dst = out;
 }
 // cv::goodFeaturesToTrack(image, corners, maxCorners, qualityLevel, minDistance, mask)
@@ -295,8 +318,11 @@ inline void goodFeaturesToTrack(const Mat& img, std::vector<Point2f>& corners, i
   corners.clear();
   const size_t cap = max_corners > 0 ? (size_t)max_corners : (size_t)img.rows * img.cols;
   std::vector<float> xy(2 * cap);
-  const int k = ora_good_features_to_track(img.ptr(), img.cols, img.rows, mask.empty() ? nullptr : mask.ptr(),
-                                           max_corners, quality, min_distance, xy.data());
+  const int k = esvio_ref_hook_gftt
+                    ? esvio_ref_hook_gftt(img.ptr(), img.cols, img.rows, mask.empty() ? nullptr : mask.ptr(),
+                                          max_corners, quality, min_distance, xy.data())
+                    : ora_good_features_to_track(img.ptr(), img.cols, img.rows, mask.empty() ? nullptr : mask.ptr(),
+                                                 max_corners, quality, min_distance, xy.data());
   for (int i = 0; i < k; ++i) corners.push_back(Point2f(xy[2 * i], xy[2 * i + 1]));
 }
 

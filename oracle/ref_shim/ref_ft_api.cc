@@ -47,6 +47,22 @@ namespace camodocal {
 
 #define REF_API extern "C" __attribute__((visibility("default")))
 
+// ---- real OpenCV behind the stand-ins (mini_cv.h): installed from Python, null = the oracle's restatements
+extern "C" {
+esvio_ref_lk_hook esvio_ref_hook_lk = nullptr;
+esvio_ref_fm_hook esvio_ref_hook_fm = nullptr;
+esvio_ref_img_hook esvio_ref_hook_clahe = nullptr, esvio_ref_hook_normalize = nullptr;
+esvio_ref_gftt_hook esvio_ref_hook_gftt = nullptr;
+}
+REF_API void ref_ft_set_cv_hooks(esvio_ref_lk_hook lk, esvio_ref_fm_hook fm, esvio_ref_img_hook clahe,
+                                 esvio_ref_img_hook normalize, esvio_ref_gftt_hook gftt) {
+  esvio_ref_hook_lk = lk;
+  esvio_ref_hook_fm = fm;
+  esvio_ref_hook_clahe = clahe;
+  esvio_ref_hook_normalize = normalize;
+  esvio_ref_hook_gftt = gftt;
+}
+
 struct RefTracker {
   FeatureTracker ft;
 };

@@ -44,6 +44,79 @@ def load():
     return L
 
 
+_LK_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                       C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int)
+_FM_HOOK = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_double, C.POINTER(C.c_uint8))
+_IMG_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_void_p)
+_GFTT_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                         C.POINTER(C.c_float))
+_installed = {}   # library handle -> the callback objects (ctypes callbacks must outlive their use)
+
+
+def use_real_opencv(L, on=True, threads=None):
+    """Serve the reference code's OpenCV calls (calcOpticalFlowPyrLK, findFundamentalMat, CLAHE,
+    normalize, goodFeaturesToTrack -- mini_cv.h) with REAL OpenCV through cv2 instead of the
+    oracle's restatements, with the arguments feature_tracker.cpp passes (:410,417-418,490,495,
+    935,228,377-381).  `on=False` restores the restatements."""
+    L.ref_ft_set_cv_hooks.argtypes = [C.c_void_p] * 5
+    if not on:
+        L.ref_ft_set_cv_hooks(None, None, None, None, None)
+        _installed.pop(id(L), None)
+        return
+    import cv2
+    if threads is not None:
+        cv2.setNumThreads(threads)
+    u8 = C.POINTER(C.c_uint8)
+
+    def img(p, w, h):
+        return np.ctypeslib.as_array(C.cast(p, u8), shape=(h, w))
+
+    def lk(prev, nxt, w, h, pp, npp, n, st, max_level, init):
+        a, b = img(prev, w, h), img(nxt, w, h)
+        p0 = np.ctypeslib.as_array(pp, shape=(n, 2))
+        p1 = np.ctypeslib.as_array(npp, shape=(n, 2))
+        s = np.ctypeslib.as_array(st, shape=(n,))
+        if init:
+            out, status, _ = cv2.calcOpticalFlowPyrLK(
+                a, b, p0.reshape(-1, 1, 2), p1.reshape(-1, 1, 2).copy(), winSize=(21, 21), maxLevel=max_level,
+                criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01),
+                flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        else:
+            out, status, _ = cv2.calcOpticalFlowPyrLK(a, b, p0.reshape(-1, 1, 2), None, winSize=(21, 21),
+                                                      maxLevel=max_level)
+        p1[:] = out.reshape(-1, 2)
+        s[:] = status.reshape(-1)
+
+    def fm(a, b, n, thr, mask):
+        m = np.ctypeslib.as_array(mask, shape=(n,))
+        _F, status = cv2.findFundamentalMat(np.ctypeslib.as_array(a, shape=(n, 2)),
+                                            np.ctypeslib.as_array(b, shape=(n, 2)), cv2.FM_RANSAC, thr, 0.99)
+        if status is None:
+            m[:] = 0
+            return 0
+        m[:] = status.reshape(-1)
+        return 1
+
+    def clahe(src, w, h, dst):
+        img(dst, w, h)[:] = cv2.createCLAHE().apply(img(src, w, h))
+
+    def normalize(src, w, h, dst):
+        img(dst, w, h)[:] = cv2.normalize(img(src, w, h), None, 0, 255, cv2.NORM_MINMAX)
+
+    def gftt(im, w, h, mask, max_corners, quality, min_dist, out_xy):
+        m = img(mask, w, h) if mask else None
+        c = cv2.goodFeaturesToTrack(img(im, w, h), max_corners, quality, min_dist, mask=m)
+        if c is None:
+            return 0
+        c = c.reshape(-1, 2).astype(np.float32)
+        np.ctypeslib.as_array(out_xy, shape=(len(c), 2))[:] = c
+        return len(c)
+
+    cbs = (_LK_HOOK(lk), _FM_HOOK(fm), _IMG_HOOK(clahe), _IMG_HOOK(normalize), _GFTT_HOOK(gftt))
+    _installed[id(L)] = cbs
+    L.ref_ft_set_cv_hooks(*[C.cast(cb, C.c_void_p) for cb in cbs])
+
+
 class RefTracker:
     """The reference's FeatureTracker behind oracle/ref_shim/ref_ft_api.cc (one at a time:
     `detector`, n_id and the parameters are process-wide globals in the reference)."""

@@ -137,6 +137,50 @@ def test_track_event_equals_reference_options(ref, kw):
     _run_events(ref, cfg, 0.6e6, 10, 2, stream=1)
 
 
+def test_reference_code_on_real_opencv_equals_oracle_on_real_opencv(ref):
+    """The same comparison with REAL OpenCV (cv2 4.13) behind both sides instead of the oracle's
+    restatements: the reference's feature_tracker.cpp calling cv2's calcOpticalFlowPyrLK /
+    findFundamentalMat / CLAHE / normalize / goodFeaturesToTrack through the stand-in headers,
+    against the oracle with its cv2 hooks.  Bit-exact again -- so the stand-ins pass the
+    arguments the reference passes (window, levels, criteria, OPTFLOW_USE_INITIAL_FLOW, threshold,
+    confidence), and nothing in the parity chain depends on the restatements being the judge of
+    themselves."""
+    if not ora.have_cv2():
+        pytest.skip("cv2 not importable")
+    from oracle import ref_tracker
+    ref_tracker.use_real_opencv(ref, True, threads=1)
+    try:
+        for cfg, rate, n, pub in ((synth.default_config(346, 260), 1.0e6, 12, 2),
+                                  (synth.default_config(346, 260, equalize=1, min_dist=20), 0.6e6, 8, 2),
+                                  (synth.default_config(640, 480), 5.0e6, 6, 3)):
+            s = synth.StereoEventStream(cfg["width"], cfg["height"], rate)
+            o = ora.OracleTracker(cfg, use_cv2=True, cv2_threads=1)
+            r = RefTracker(ref, cfg)
+            try:
+                for k in range(n):
+                    L6, R6 = s.window(k, 0), s.window(k, 1)
+                    t = float(L6[2][-1])
+                    _same(r.track(t, L6, R6, k % pub == 0), o.track(t, L6[:4], R6[:4], k % pub == 0), k, "cv2")
+            finally:
+                r.close()
+        # trackImage with cv2's goodFeaturesToTrack on both sides
+        cfg = synth.default_config(240, 180, min_dist=14, max_cnt=60)
+        frames = synth.stereo_frame_sequence(240, 180, 6)
+        r = RefTracker(ref, cfg)
+        try:
+            import cv2
+            prev = None
+            for k, (fl, fr_) in enumerate(frames):
+                a = r.track_image(100.0 + k / 20.0, fl, fr_, k % 2 == 0)
+                assert len(a["id"]) > 20 and (prev is None or len(np.intersect1d(prev, a["id"])) > 10)
+                prev = a["id"]
+            assert cv2.__version__
+        finally:
+            r.close()
+    finally:
+        ref_tracker.use_real_opencv(ref, False)
+
+
 def test_track_event_sparse_and_empty_right(ref):
     """Few events (under 8 tracks: rejectWithF_event is skipped, feature_tracker.cpp:912) and a
     window whose right camera is silent."""
