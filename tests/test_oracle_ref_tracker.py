@@ -24,10 +24,6 @@ The GPU parity tests compare the CUDA path with the oracle on the same streams
 (test_gpu_parity.py: test_track_end_to_end, test_teacher_forced_every_window), which closes
 the chain  reference code == oracle == CUDA  for the bookkeeping stages too.
 """
-import ctypes as C
-import os
-import subprocess
-
 import numpy as np
 import pytest
 
